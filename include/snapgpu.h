@@ -1,0 +1,233 @@
+/*
+ * snapgpu.h -- C ABI of the B200-native seed-and-extend engine that drops in behind SNAP's
+ * per-thread aligner hook.
+ *
+ * Every entry point is plain C: pointers, sizes, POD structs.  No C++/torch types cross this line.
+ * A SNAP maintainer binds these from `AlignerExtension::runIterationThread`
+ * (reference SNAPLib/AlignerContext.h:145-180, call sites SingleAligner.cpp:102 and
+ * PairedAligner.cpp:503); INTEGRATION.md shows the stub.
+ *
+ * Return convention: 0 = success, non-zero = failure and snapgpu_last_error() describes it
+ * (the reference's own convention is WriteErrorMessage()+soft_exit(1), exit.cpp:30-42; a library
+ * must not exit(), so errors are returned and the extension turns them into soft_exit).
+ * There is NO CPU fallback: if no CUDA device / kernel image is usable every call fails loudly.
+ */
+#ifndef SNAPGPU_H
+#define SNAPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNAPGPU_ABI_VERSION 1
+
+/* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
+enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
+/* Direction, reference SNAPLib/directions.h */
+enum { SNAPGPU_FORWARD = 0, SNAPGPU_RC = 1 };
+
+#define SNAPGPU_INVALID_LOCATION_32 0xffffffffLL /* InvalidGenomeLocation for 4-byte locations, GenomeIndex.cpp:511-517 */
+#define SNAPGPU_UNUSED_SCORE 0xffff               /* BaseAligner::UnusedScoreValue, BaseAligner.h:141 */
+#define SNAPGPU_MAX_K 127                         /* LandauVishkin.h:11 */
+#define SNAPGPU_MAX_READ_LENGTH 1000              /* Read.h:49 */
+
+/*
+ * POD mirror of SingleAlignmentResult (reference SNAPLib/AlignmentResult.h:49-77), field for field,
+ * minus alignmentTimeInNanoseconds (only meaningful with -at and measured by the caller).
+ */
+typedef struct snapgpu_single_result {
+    int32_t  status;                    /* SNAPGPU_NOT_FOUND / SINGLE_HIT / MULTIPLE_HITS */
+    int32_t  direction;                 /* SNAPGPU_FORWARD / SNAPGPU_RC */
+    int64_t  location;                  /* GenomeLocation; SNAPGPU_INVALID_LOCATION_32 when not found */
+    int64_t  origLocation;              /* location before indel adjustment */
+    int32_t  score;                     /* edit distance */
+    int32_t  scorePriorToClipping;
+    int32_t  mapq;
+    int32_t  clippingForReadAdjustment;
+    int32_t  usedAffineGapScoring;
+    int32_t  basesClippedBefore;
+    int32_t  basesClippedAfter;
+    int32_t  agScore;
+    int32_t  supplementary;
+    int32_t  seedOffset;
+    double   matchProbability;
+    double   probabilityAllCandidates;
+    uint32_t popularSeedsSkipped;
+    uint32_t reserved;
+} snapgpu_single_result;               /* 88 bytes */
+
+/*
+ * The AlignerContext / AlignerOptions fields the hot path reads
+ * (reference SNAPLib/AlignerContext.h:102-131, AlignerOptions.h:93-186, defaults AlignerOptions.cpp:39-121).
+ * snapgpu_params_default() fills the 2.0.5 single-end defaults.
+ */
+typedef struct snapgpu_params {
+    uint32_t struct_size;               /* sizeof(snapgpu_params), for ABI checking */
+    uint32_t maxHits;                   /* -h   (300)  */
+    uint32_t maxDist;                   /* -d   (14)   maxK */
+    uint32_t numSeedsFromCommandLine;   /* -n   (25)   */
+    double   seedCoverage;              /* -sc  (0.0); used when numSeedsFromCommandLine == 0 */
+    uint32_t minWeightToCheck;          /* -ms  (1)    */
+    uint32_t extraSearchDepth;          /* -D   (1)    */
+    uint32_t minReadLength;             /* -mrl (50)   */
+    int32_t  useAffineGap;              /* -G / -G-  (1) */
+    int32_t  matchReward;               /* -gm  (1)  */
+    int32_t  subPenalty;                /* -gs  (4)  */
+    int32_t  gapOpenPenalty;            /* -go  (6)  */
+    int32_t  gapExtendPenalty;          /* -ge  (1)  */
+    int32_t  fivePrimeEndBonus;         /* -g5  (10) */
+    int32_t  threePrimeEndBonus;        /* -g3  (7)  */
+    /* DisabledOptimizations, AlignerOptions.h:78-88 */
+    int32_t  noUkkonen;
+    int32_t  noOrderedEvaluation;
+    int32_t  noTruncation;
+    int32_t  noEditDistance;            /* -ne */
+    int32_t  noBandedAffineGap;
+    int32_t  altAwareness;              /* -ea- turns off (1) */
+    int32_t  maxScoreGapToPreferNonAltAlignment; /* (64) */
+    int32_t  explorePopularSeeds;       /* -x (0) */
+    int32_t  stopOnFirstHit;            /* -f (0) */
+    int32_t  maxSecondaryAlignmentAdditionalEditDistance; /* -om; only -1 (off) is supported */
+    int32_t  ignoreAlignmentAdjustmentsForOm; /* (1) -- AlignmentAdjuster is off by default; only 1 supported */
+} snapgpu_params;
+
+typedef struct snapgpu_index_info {
+    int64_t  countOfBases;              /* Genome::getCountOfBases() incl. inter-contig padding */
+    uint32_t seedLen;
+    uint32_t hashTableKeySize;          /* bytes of the seed kept as the in-table key */
+    uint32_t nHashTables;
+    uint32_t locationSize;              /* only 4 supported (lookupSeed32 path) */
+    uint32_t largeHashTable;            /* 1 = `-large` two-value entries */
+    uint32_t chromosomePadding;
+    uint32_t nContigs;
+    uint32_t reserved;
+    uint64_t overflowTableSize;         /* in 32-bit words */
+    uint64_t hashTableSlots;            /* total slots over all tables */
+    uint64_t hbmBytes;                  /* bytes resident on the device for this index */
+} snapgpu_index_info;
+
+/* Per-call work counters (reference BaseAligner.h:106-111 + AlignerStats.h:41-97 subset). */
+typedef struct snapgpu_counters {
+    int64_t totalReads;
+    int64_t uselessReads;               /* filtered up front: too short / too many Ns (SingleAligner.cpp:213) */
+    int64_t singleHits;
+    int64_t multiHits;
+    int64_t notFound;
+    int64_t nHashTableLookups;          /* lookupSeed32 calls */
+    int64_t nHashEntriesProbed;         /* hash-table entries examined over both strand probes */
+    int64_t nOverflowWordsRead;         /* overflow-table words touched (count word + hits used) */
+    int64_t lvCalls;                    /* locations scored with Landau-Vishkin */
+    int64_t affineGapCalls;             /* locations scored with affine gap */
+    int64_t nHitsIgnoredBecauseOfTooHighPopularity;
+    int64_t mapqHistogram[71];
+} snapgpu_counters;
+
+typedef struct snapgpu_index   snapgpu_index;   /* opaque: hash tables + overflow + bases resident in HBM */
+typedef struct snapgpu_aligner snapgpu_aligner; /* opaque: per-host-thread stream, scratch arenas, staging */
+
+const char *snapgpu_last_error(void);            /* thread-local, never NULL */
+int  snapgpu_abi_version(void);
+int  snapgpu_device_count(void);                 /* 0 if no usable CUDA device */
+void snapgpu_params_default(snapgpu_params *p);  /* `snap single` 2.0.5 defaults, AlignerOptions.cpp:39-121 */
+
+/*
+ * Index.  Replaces GenomeIndex::loadFromDirectory (reference SNAPLib/GenomeIndex.cpp:1838-2093):
+ * reads the four files `Genome`, `GenomeIndex`, `GenomeIndexHash`, `OverflowTable` written by
+ * `snap-aligner index` (format v7.1) and places them in HBM on `device`.
+ */
+int  snapgpu_index_open(const char *directory, int device, snapgpu_index **out);
+/*
+ * Builds the same lookup structure on the device from raw reference bases (one byte per base,
+ * already including SNAP's lowercase-'n' contig padding), for when no pre-built directory exists.
+ * Equivalent in *results* to GenomeIndex::BuildIndexToDirectory (GenomeIndex.cpp:527-1110): every
+ * seed maps to the same hit set in the same (descending) order; slot layout is not part of the contract.
+ * contigStarts[nContigs] are the beginningLocation values (first real base of each contig).
+ */
+int  snapgpu_index_build(const char *bases, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
+                         uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out);
+int  snapgpu_index_info_get(const snapgpu_index *idx, snapgpu_index_info *info);
+void snapgpu_index_close(snapgpu_index *idx);
+
+/*
+ * Batched GenomeIndex::lookupSeed32 (reference SNAPLib/GenomeIndex.cpp:2095-2157).
+ * seeds: nSeeds * seedLen ASCII bases (host memory).  For seed i: nHits[2*i] forward, nHits[2*i+1] RC;
+ * hits[(2*i+dir)*maxHitsPerSeed ...] receives the first min(nHits, maxHitsPerSeed) locations, descending
+ * as in the overflow table.  Seeds with non-ACGT bases report 0/0 (Seed::DoesTextRepresentASeed, Seed.cpp:28).
+ * probes[i] (optional) = hash entries examined for seed i.
+ */
+int  snapgpu_lookup_seeds(const snapgpu_index *idx, const char *seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,
+                          int64_t *nHits, uint32_t *hits, uint32_t *probes);
+
+/*
+ * Aligner handle.  One per host thread, like BaseAligner (reference SNAPLib/BaseAligner.h:19-20:
+ * "NOT thread safe"); owns a CUDA stream, pinned staging and the device scratch arenas.
+ * maxBatchReads bounds n in the align calls.
+ */
+int  snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *params, int64_t maxBatchReads,
+                            snapgpu_aligner **out);
+void snapgpu_aligner_destroy(snapgpu_aligner *a);
+
+/*
+ * Replaces the per-thread loop body `aligner->AlignRead(read, results, ...)` + pre-filter + updateStats
+ * (reference SNAPLib/SingleAligner.cpp:197-338, BaseAligner.cpp:272-763) for a batch of n reads.
+ * bases/quals: concatenated clipped views (Read::getData()/getQuality(), upper-cased), read i at
+ * [offsets[i], offsets[i]+lens[i]).  HOST pointers; copies are done inside.  results[n] caller-owned.
+ * counters may be NULL; when given it is *accumulated into*.
+ */
+int  snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals,
+                          const uint64_t *offsets, const uint32_t *lens,
+                          snapgpu_single_result *results, snapgpu_counters *counters);
+
+/*
+ * Same, but all five arrays are DEVICE pointers and the kernels are enqueued on `cudaStream`
+ * (a cudaStream_t / CUstream passed as void*; NULL = the aligner's own stream).  Does not synchronise.
+ * d_counters may be NULL; otherwise a device snapgpu_counters that is accumulated into.
+ */
+int  snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals,
+                                 const uint64_t *d_offsets, const uint32_t *d_lens,
+                                 snapgpu_single_result *d_results, snapgpu_counters *d_counters,
+                                 void *cudaStream);
+
+/* Number of kernel launches issued through this aligner since creation (bench.py's gpu_launches). */
+int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a);
+
+/*
+ * Leaf kernels exposed for parity tests (never used by the product path's callers).
+ * Batched LandauVishkin<dir>::computeEditDistance (reference SNAPLib/LandauVishkin.h:100-351).
+ * Job j: text = textBuf + textOff[j] (for dir=-1 the pointer is one past the first text char, as the
+ * reference's callers pass it), pattern/quality at patOff[j].  Outputs per job.
+ */
+typedef struct snapgpu_lv_job {
+    uint64_t textOff; uint64_t patOff; int32_t textLen; int32_t patternLen; int32_t k; int32_t dir;
+} snapgpu_lv_job;
+typedef struct snapgpu_lv_out {
+    int32_t score; int32_t netIndel; int32_t totalIndels; int32_t textSpan; double matchProbability;
+} snapgpu_lv_out;
+int  snapgpu_test_lv(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
+                     uint64_t patBytes, const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out);
+
+/*
+ * Batched AffineGapVectorized<dir>::computeScore / computeScoreBanded
+ * (reference SNAPLib/AffineGapVectorized.h:821-1339 / 256-819).
+ */
+typedef struct snapgpu_ag_job {
+    uint64_t textOff; uint64_t patOff; int32_t textLen; int32_t patternLen; int32_t w; int32_t scoreInit;
+    int32_t dir; int32_t isRC; int32_t banded; int32_t useClippingOptimizations;
+} snapgpu_ag_job;
+typedef struct snapgpu_ag_out {
+    int32_t agScore; int32_t textOffset; int32_t patternOffset; int32_t nEdits; double matchProbability;
+} snapgpu_ag_out;
+typedef struct snapgpu_ag_params {
+    int32_t matchReward, subPenalty, gapOpenPenalty, gapExtendPenalty, fivePrimeEndBonus, threePrimeEndBonus;
+} snapgpu_ag_params;
+int  snapgpu_test_ag(int device, const snapgpu_ag_params *p, const char *textBuf, uint64_t textBytes,
+                     const char *patBuf, const char *qualBuf, uint64_t patBytes,
+                     const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPGPU_H */

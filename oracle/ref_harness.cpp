@@ -1,0 +1,385 @@
+/*
+ * ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.  Thin C-ABI shim over the UNMODIFIED reference
+ * (amplab/snap 2.0.5) compiled from the sources where they lie under /root/reference by oracle/Makefile
+ * into oracle/_ref/libsnapref.so.  Nothing in the product path (snap_b200/, include/) may link, load or
+ * call this; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * It contains no algorithm of its own: every function forwards to the reference class named in its comment
+ * and copies the answer into the POD structs of include/snapgpu.h so that tests can memcmp them against
+ * the CUDA path.  Construction mirrors SingleAligner.cpp:133-180 (BigAllocator arena with 16-byte
+ * granularity -- required).
+ *
+ * Must be compiled as C++98 like the reference (Makefile:2).
+ */
+#include "stdafx.h"
+#include "Compat.h"
+#include "BigAlloc.h"
+#include "Genome.h"
+#include "GenomeIndex.h"
+#include "Seed.h"
+#include "SeedSequencer.h"
+#include "LandauVishkin.h"
+#include "AffineGapVectorized.h"
+#include "BaseAligner.h"
+#include "AlignerOptions.h"
+#include "Read.h"
+#include "mapq.h"
+#include "Tables.h"
+
+#include <pthread.h>
+#include <string.h>
+#include <stdio.h>
+#include <time.h>
+
+#include "../include/snapgpu.h"
+
+extern GenomeIndex *g_index;                 // AlignerContext.cpp:58
+extern _int64 nProbesInGetEntryForKey;       // HashTable.cpp:263 (probes beyond the first slot)
+
+static bool g_inited = false;
+
+extern "C" {
+
+int ref_init(void)
+{
+    if (!g_inited) {
+        InitializeSeedSequencers();                    // SeedSequencer.cpp:29
+        initializeLVProbabilitiesToPhredPlus33();      // LandauVishkin.cpp:716
+        g_inited = true;
+    }
+    return 0;
+}
+
+void *ref_index_load(const char *dir)
+{
+    ref_init();
+    GenomeIndex *index = GenomeIndex::loadFromDirectory((char *)dir, /*map*/false, /*prefetch*/false);
+    if (NULL != index) {
+        g_index = index;
+    }
+    return index;
+}
+
+int ref_index_info(void *vidx, snapgpu_index_info *info)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    memset(info, 0, sizeof(*info));
+    info->countOfBases = index->getGenome()->getCountOfBases();
+    info->seedLen = index->getSeedLength();
+    info->locationSize = index->doesGenomeIndexHave64BitLocations() ? 8 : 4;
+    info->nContigs = index->getGenome()->getNumContigs();
+    return 0;
+}
+
+/* Raw base array of the loaded genome (for building windows in leaf tests). */
+const char *ref_genome_bases(void *vidx, _int64 loc, _int64 len)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    return index->getGenome()->getSubstring(loc, len);
+}
+
+/* GenomeIndex::lookupSeed32 (GenomeIndex.cpp:2095).  Returns probes beyond first slot via *extraProbes. */
+int ref_lookup_seed(void *vidx, const char *bases, _int64 *nHits /*[2]*/, unsigned *hitsOut /*[2*maxOut]*/,
+                    unsigned maxOut, _int64 *extraProbes)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    unsigned seedLen = index->getSeedLength();
+    nHits[0] = nHits[1] = 0;
+    if (!Seed::DoesTextRepresentASeed(bases, seedLen)) {
+        if (extraProbes) *extraProbes = 0;
+        return 0;
+    }
+    Seed seed(bases, seedLen);
+    const unsigned *hits[2];
+    _int64 before = nProbesInGetEntryForKey;
+    index->lookupSeed32(seed, &nHits[0], &hits[0], &nHits[1], &hits[1]);
+    if (extraProbes) *extraProbes = nProbesInGetEntryForKey - before;
+    for (int d = 0; d < 2; d++) {
+        for (_int64 i = 0; i < nHits[d] && i < (_int64)maxOut; i++) {
+            hitsOut[d * maxOut + i] = hits[d][i];
+        }
+    }
+    return 0;
+}
+
+unsigned ref_wrapped_seed(unsigned seedLen, unsigned wrapCount)   // SeedSequencer.cpp:105
+{
+    ref_init();
+    return GetWrappedNextSeedToTest(seedLen, wrapCount);
+}
+
+int ref_mapq(double pAll, double pBest, int score, int popularSeedsSkipped)  // mapq.h:32
+{
+    return computeMAPQ(pAll, pBest, score, popularSeedsSkipped);
+}
+
+/* Copies of the global probability tables (LandauVishkin.cpp:715-763). */
+void ref_tables(double *phred /*[256]*/, double *indel /*[n]*/, int nIndel, double *perfect /*[n]*/, int nPerfect)
+{
+    ref_init();
+    for (int i = 0; i < 256; i++) phred[i] = lv_phredToProbability[i];
+    for (int i = 0; i < nIndel; i++) indel[i] = lv_indelProbabilities[i];
+    for (int i = 0; i < nPerfect; i++) perfect[i] = lv_perfectMatchProbability[i];
+}
+
+/*
+ * LandauVishkin<dir>::computeEditDistance (LandauVishkin.h:100).  One persistent object per direction,
+ * exactly like BaseAligner keeps (its L/A arrays carry state between calls).
+ */
+static LandauVishkin<1>  *g_lvF = NULL;
+static LandauVishkin<-1> *g_lvR = NULL;
+
+int ref_lv(int dir, const char *text, int textLen, const char *pattern, const char *quality, int patternLen, int k,
+           double *matchProbability, int *netIndel, int *totalIndels, int *textSpan)
+{
+    ref_init();
+    if (NULL == g_lvF) { g_lvF = new LandauVishkin<1>; g_lvR = new LandauVishkin<-1>; }
+    if (dir == 1) {
+        return g_lvF->computeEditDistance(text, textLen, pattern, quality, patternLen, k, matchProbability, netIndel, totalIndels, textSpan);
+    }
+    return g_lvR->computeEditDistance(text, textLen, pattern, quality, patternLen, k, matchProbability, netIndel, totalIndels, textSpan);
+}
+
+void ref_lv_batch(const char *textBuf, const char *patBuf, const char *qualBuf, const snapgpu_lv_job *jobs, _int64 nJobs,
+                  snapgpu_lv_out *out)
+{
+    for (_int64 j = 0; j < nJobs; j++) {
+        const snapgpu_lv_job *b = &jobs[j];
+        snapgpu_lv_out *o = &out[j];
+        o->matchProbability = 0; o->netIndel = 0; o->totalIndels = 0; o->textSpan = 0;
+        o->score = ref_lv(b->dir, textBuf + b->textOff, b->textLen, patBuf + b->patOff, qualBuf + b->patOff, b->patternLen, b->k,
+                          &o->matchProbability, &o->netIndel, &o->totalIndels, &o->textSpan);
+    }
+}
+
+/*
+ * AffineGapVectorized<dir>::computeScore / computeScoreBanded (AffineGapVectorized.h:821 / 256).
+ * The objects hold __m128i members => allocate 16-byte aligned.
+ */
+struct AGPair {
+    AffineGapVectorized<1>  *f;
+    AffineGapVectorized<-1> *r;
+    snapgpu_ag_params p;
+};
+static AGPair g_ag = {NULL, NULL, {0, 0, 0, 0, 0, 0}};
+
+static void ensure_ag(const snapgpu_ag_params *p)
+{
+    if (g_ag.f != NULL && 0 == memcmp(&g_ag.p, p, sizeof(*p))) return;
+    if (g_ag.f == NULL) {
+        void *m1 = NULL, *m2 = NULL;
+        if (posix_memalign(&m1, 64, sizeof(AffineGapVectorized<1>)) || posix_memalign(&m2, 64, sizeof(AffineGapVectorized<-1>))) {
+            fprintf(stderr, "ref_harness: posix_memalign failed\n");
+            abort();
+        }
+        memset(m1, 0, sizeof(AffineGapVectorized<1>));
+        memset(m2, 0, sizeof(AffineGapVectorized<-1>));
+        g_ag.f = (AffineGapVectorized<1> *)m1;
+        g_ag.r = (AffineGapVectorized<-1> *)m2;
+    }
+    g_ag.f->init(p->matchReward, p->subPenalty, p->gapOpenPenalty, p->gapExtendPenalty, p->fivePrimeEndBonus, p->threePrimeEndBonus);
+    g_ag.r->init(p->matchReward, p->subPenalty, p->gapOpenPenalty, p->gapExtendPenalty, p->fivePrimeEndBonus, p->threePrimeEndBonus);
+    g_ag.p = *p;
+}
+
+void ref_ag_batch(const snapgpu_ag_params *p, const char *textBuf, const char *patBuf, const char *qualBuf,
+                  const snapgpu_ag_job *jobs, _int64 nJobs, snapgpu_ag_out *out)
+{
+    ref_init();
+    ensure_ag(p);
+    for (_int64 j = 0; j < nJobs; j++) {
+        const snapgpu_ag_job *b = &jobs[j];
+        snapgpu_ag_out *o = &out[j];
+        o->textOffset = 0; o->patternOffset = 0; o->nEdits = 0; o->matchProbability = 0;
+        const char *text = textBuf + b->textOff;
+        const char *pat = patBuf + b->patOff;
+        const char *qual = qualBuf + b->patOff;
+        if (b->dir == 1) {
+            o->agScore = b->banded
+                ? g_ag.f->computeScoreBanded(text, b->textLen, pat, qual, b->patternLen, b->w, b->scoreInit, b->isRC != 0, &o->textOffset, &o->patternOffset, &o->nEdits, &o->matchProbability, b->useClippingOptimizations != 0)
+                : g_ag.f->computeScore(text, b->textLen, pat, qual, b->patternLen, b->w, b->scoreInit, b->isRC != 0, &o->textOffset, &o->patternOffset, &o->nEdits, &o->matchProbability, b->useClippingOptimizations != 0);
+        } else {
+            o->agScore = b->banded
+                ? g_ag.r->computeScoreBanded(text, b->textLen, pat, qual, b->patternLen, b->w, b->scoreInit, b->isRC != 0, &o->textOffset, &o->patternOffset, &o->nEdits, &o->matchProbability, b->useClippingOptimizations != 0)
+                : g_ag.r->computeScore(text, b->textLen, pat, qual, b->patternLen, b->w, b->scoreInit, b->isRC != 0, &o->textOffset, &o->patternOffset, &o->nEdits, &o->matchProbability, b->useClippingOptimizations != 0);
+        }
+    }
+}
+
+/*
+ * Single-end aligner, constructed exactly like SingleAligner.cpp:145-173.
+ */
+struct RefSingle {
+    GenomeIndex *index;
+    BigAllocator *allocator;
+    BaseAligner *aligner;
+    snapgpu_params params;
+};
+
+void *ref_single_create(void *vidx, const snapgpu_params *p)
+{
+    ref_init();
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    RefSingle *rs = new RefSingle;
+    rs->index = index;
+    rs->params = *p;
+    int maxReadSize = MAX_READ_LENGTH;
+    rs->allocator = new BigAllocator(BaseAligner::getBigAllocatorReservation(index, true, p->maxHits, maxReadSize, index->getSeedLength(),
+                                        p->numSeedsFromCommandLine, p->seedCoverage, -1, p->extraSearchDepth) + 4096, 16);
+    DisabledOptimizations dis;
+    dis.noUkkonen = p->noUkkonen != 0;
+    dis.noOrderedEvaluation = p->noOrderedEvaluation != 0;
+    dis.noTruncation = p->noTruncation != 0;
+    dis.noEditDistance = p->noEditDistance != 0;
+    dis.noBandedAffineGap = p->noBandedAffineGap != 0;
+    rs->aligner = new (rs->allocator) BaseAligner(index, p->maxHits, p->maxDist, maxReadSize, p->numSeedsFromCommandLine, p->seedCoverage,
+        p->minWeightToCheck, p->extraSearchDepth, dis, p->useAffineGap != 0, p->ignoreAlignmentAdjustmentsForOm != 0,
+        p->altAwareness != 0, /*emitALT*/false, p->maxScoreGapToPreferNonAltAlignment, /*maxSecondaryAlignmentsPerContig*/-1,
+        NULL, NULL, p->matchReward, p->subPenalty, p->gapOpenPenalty, p->gapExtendPenalty, p->fivePrimeEndBonus, p->threePrimeEndBonus,
+        NULL, rs->allocator);
+    rs->aligner->setExplorePopularSeeds(p->explorePopularSeeds != 0);
+    rs->aligner->setStopOnFirstHit(p->stopOnFirstHit != 0);
+    return rs;
+}
+
+void ref_single_destroy(void *v)
+{
+    RefSingle *rs = (RefSingle *)v;
+    rs->aligner->~BaseAligner();
+    delete rs->allocator;
+    delete rs;
+}
+
+static void copy_result(const SingleAlignmentResult *r, snapgpu_single_result *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->status = (int)r->status;
+    o->direction = (int)r->direction;
+    o->location = GenomeLocationAsInt64(r->location);
+    o->origLocation = GenomeLocationAsInt64(r->origLocation);
+    o->score = r->score;
+    o->scorePriorToClipping = r->scorePriorToClipping;
+    o->mapq = r->mapq;
+    o->clippingForReadAdjustment = r->clippingForReadAdjustment;
+    o->usedAffineGapScoring = r->usedAffineGapScoring ? 1 : 0;
+    o->basesClippedBefore = r->basesClippedBefore;
+    o->basesClippedAfter = r->basesClippedAfter;
+    o->agScore = r->agScore;
+    o->supplementary = r->supplementary ? 1 : 0;
+    o->seedOffset = r->seedOffset;
+    o->matchProbability = r->matchProbability;
+    o->probabilityAllCandidates = r->probabilityAllCandidates;
+    o->popularSeedsSkipped = r->popularSeedsSkipped;
+}
+
+/*
+ * The per-thread loop body of SingleAligner.cpp:197-338 without the writer: pre-filter (:213), AlignRead (:250),
+ * updateStats (:354-374).  Reads are given as the already-clipped view (Read::getData()/getQuality()).
+ */
+static void align_range(RefSingle *rs, _int64 begin, _int64 end, const char *bases, const char *quals,
+                        const _uint64 *offsets, const unsigned *lens, snapgpu_single_result *results, snapgpu_counters *ctr)
+{
+    const snapgpu_params *p = &rs->params;
+    _int64 lv0 = rs->aligner->getLocationsScoredWithLandauVishkin();
+    _int64 ag0 = rs->aligner->getLocationsScoredWithAffineGap();
+    _int64 lk0 = rs->aligner->getNHashTableLookups();
+    _int64 pop0 = rs->aligner->getNHitsIgnoredBecauseOfTooHighPopularity();
+    for (_int64 i = begin; i < end; i++) {
+        Read read;
+        read.init("r", 1, bases + offsets[i], quals + offsets[i], lens[i], NULL, 0);
+        SingleAlignmentResult res, alt;
+        memset(&res, 0, sizeof(res));
+        memset(&alt, 0, sizeof(alt));
+        ctr->totalReads++;
+        if (read.getDataLength() < p->minReadLength || read.countOfNs() > (int)p->maxDist) {
+            res.status = NotFound;
+            res.location = InvalidGenomeLocation;
+            res.mapq = 0;
+            res.direction = FORWARD;
+            ctr->uselessReads++;
+            copy_result(&res, &results[i]);
+            continue;
+        }
+        _int64 nSecondary = 0;
+        rs->aligner->AlignRead(&read, &res, &alt, p->maxSecondaryAlignmentAdditionalEditDistance, 0, &nSecondary, 0, NULL, 0, NULL, NULL);
+        copy_result(&res, &results[i]);
+        if (res.status == SingleHit) ctr->singleHits++;
+        else if (res.status == MultipleHits) ctr->multiHits++;
+        else ctr->notFound++;
+        if (res.status != NotFound && res.mapq >= 0 && res.mapq <= 70) ctr->mapqHistogram[res.mapq]++;
+    }
+    ctr->lvCalls += rs->aligner->getLocationsScoredWithLandauVishkin() - lv0;
+    ctr->affineGapCalls += rs->aligner->getLocationsScoredWithAffineGap() - ag0;
+    ctr->nHashTableLookups += rs->aligner->getNHashTableLookups() - lk0;
+    ctr->nHitsIgnoredBecauseOfTooHighPopularity += rs->aligner->getNHitsIgnoredBecauseOfTooHighPopularity() - pop0;
+}
+
+int ref_single_align(void *v, _int64 n, const char *bases, const char *quals, const _uint64 *offsets, const unsigned *lens,
+                     snapgpu_single_result *results, snapgpu_counters *counters)
+{
+    RefSingle *rs = (RefSingle *)v;
+    snapgpu_counters local;
+    memset(&local, 0, sizeof(local));
+    _int64 probes0 = nProbesInGetEntryForKey;
+    align_range(rs, 0, n, bases, quals, offsets, lens, results, &local);
+    // entries examined = first slot of each probe chain (2 per lookup on a small index) + extra probes
+    local.nHashEntriesProbed = (nProbesInGetEntryForKey - probes0) + 2 * local.nHashTableLookups;
+    if (counters) {
+        _int64 *dst = (_int64 *)counters;
+        const _int64 *src = (const _int64 *)&local;
+        for (size_t i = 0; i < sizeof(local) / sizeof(_int64); i++) dst[i] += src[i];
+    }
+    return 0;
+}
+
+/*
+ * Multi-threaded variant: nThreads pthreads, each with its own BaseAligner over a contiguous range, the
+ * way ParallelTask.h:40-120 runs SingleAlignerContext::runIterationThread.  Used for the CPU baseline.
+ * Returns wall seconds spent aligning (aligner construction excluded, like AlignerContext.cpp:420).
+ */
+struct MTArg {
+    RefSingle *rs; _int64 begin, end;
+    const char *bases; const char *quals; const _uint64 *offsets; const unsigned *lens;
+    snapgpu_single_result *results; snapgpu_counters ctr;
+};
+
+static void *mt_main(void *v)
+{
+    MTArg *a = (MTArg *)v;
+    align_range(a->rs, a->begin, a->end, a->bases, a->quals, a->offsets, a->lens, a->results, &a->ctr);
+    return NULL;
+}
+
+double ref_single_align_mt(void *vidx, const snapgpu_params *p, int nThreads, _int64 n, const char *bases, const char *quals,
+                           const _uint64 *offsets, const unsigned *lens, snapgpu_single_result *results, snapgpu_counters *counters)
+{
+    if (nThreads < 1) nThreads = 1;
+    MTArg *args = new MTArg[nThreads];
+    pthread_t *threads = new pthread_t[nThreads];
+    for (int t = 0; t < nThreads; t++) {
+        args[t].rs = (RefSingle *)ref_single_create(vidx, p);
+        args[t].begin = n * t / nThreads;
+        args[t].end = n * (t + 1) / nThreads;
+        args[t].bases = bases; args[t].quals = quals; args[t].offsets = offsets; args[t].lens = lens;
+        args[t].results = results;
+        memset(&args[t].ctr, 0, sizeof(args[t].ctr));
+    }
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < nThreads; t++) pthread_create(&threads[t], NULL, mt_main, &args[t]);
+    for (int t = 0; t < nThreads; t++) pthread_join(threads[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int t = 0; t < nThreads; t++) {
+        if (counters) {
+            _int64 *dst = (_int64 *)counters;
+            const _int64 *src = (const _int64 *)&args[t].ctr;
+            for (size_t i = 0; i < sizeof(snapgpu_counters) / sizeof(_int64); i++) dst[i] += src[i];
+        }
+        ref_single_destroy(args[t].rs);
+    }
+    delete[] args;
+    delete[] threads;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+} // extern "C"

@@ -1,0 +1,191 @@
+"""ctypes binding of oracle/_ref/libsnapref.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The product package (snap_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libsnapref.so")
+SNAP_ALIGNER = os.path.join(HERE, "_ref", "snap-aligner")
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("maxHits", C.c_uint32), ("maxDist", C.c_uint32),
+        ("numSeedsFromCommandLine", C.c_uint32), ("seedCoverage", C.c_double),
+        ("minWeightToCheck", C.c_uint32), ("extraSearchDepth", C.c_uint32), ("minReadLength", C.c_uint32),
+        ("useAffineGap", C.c_int32), ("matchReward", C.c_int32), ("subPenalty", C.c_int32),
+        ("gapOpenPenalty", C.c_int32), ("gapExtendPenalty", C.c_int32), ("fivePrimeEndBonus", C.c_int32),
+        ("threePrimeEndBonus", C.c_int32), ("noUkkonen", C.c_int32), ("noOrderedEvaluation", C.c_int32),
+        ("noTruncation", C.c_int32), ("noEditDistance", C.c_int32), ("noBandedAffineGap", C.c_int32),
+        ("altAwareness", C.c_int32), ("maxScoreGapToPreferNonAltAlignment", C.c_int32),
+        ("explorePopularSeeds", C.c_int32), ("stopOnFirstHit", C.c_int32),
+        ("maxSecondaryAlignmentAdditionalEditDistance", C.c_int32), ("ignoreAlignmentAdjustmentsForOm", C.c_int32),
+    ]
+
+
+def default_params(**kw) -> Params:
+    """`snap single` 2.0.5 defaults (reference AlignerOptions.cpp:39-121)."""
+    p = Params()
+    p.struct_size = C.sizeof(Params)
+    p.maxHits = 300
+    p.maxDist = 14
+    p.numSeedsFromCommandLine = 25
+    p.seedCoverage = 0.0
+    p.minWeightToCheck = 1
+    p.extraSearchDepth = 1
+    p.minReadLength = 50
+    p.useAffineGap = 1
+    p.matchReward, p.subPenalty, p.gapOpenPenalty, p.gapExtendPenalty = 1, 4, 6, 1
+    p.fivePrimeEndBonus, p.threePrimeEndBonus = 10, 7
+    p.altAwareness = 1
+    p.maxScoreGapToPreferNonAltAlignment = 64
+    p.maxSecondaryAlignmentAdditionalEditDistance = -1
+    p.ignoreAlignmentAdjustmentsForOm = 1
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("direction", "<i4"), ("location", "<i8"), ("origLocation", "<i8"),
+    ("score", "<i4"), ("scorePriorToClipping", "<i4"), ("mapq", "<i4"), ("clippingForReadAdjustment", "<i4"),
+    ("usedAffineGapScoring", "<i4"), ("basesClippedBefore", "<i4"), ("basesClippedAfter", "<i4"),
+    ("agScore", "<i4"), ("supplementary", "<i4"), ("seedOffset", "<i4"),
+    ("matchProbability", "<f8"), ("probabilityAllCandidates", "<f8"),
+    ("popularSeedsSkipped", "<u4"), ("reserved", "<u4"),
+])
+assert RESULT_DTYPE.itemsize == 88
+
+COUNTER_FIELDS = ["totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups",
+                  "nHashEntriesProbed", "nOverflowWordsRead", "lvCalls", "affineGapCalls",
+                  "nHitsIgnoredBecauseOfTooHighPopularity"]
+N_COUNTERS = len(COUNTER_FIELDS) + 71
+
+LV_JOB_DTYPE = np.dtype([("textOff", "<u8"), ("patOff", "<u8"), ("textLen", "<i4"), ("patternLen", "<i4"),
+                         ("k", "<i4"), ("dir", "<i4")])
+LV_OUT_DTYPE = np.dtype([("score", "<i4"), ("netIndel", "<i4"), ("totalIndels", "<i4"), ("textSpan", "<i4"),
+                         ("matchProbability", "<f8")])
+AG_JOB_DTYPE = np.dtype([("textOff", "<u8"), ("patOff", "<u8"), ("textLen", "<i4"), ("patternLen", "<i4"),
+                         ("w", "<i4"), ("scoreInit", "<i4"), ("dir", "<i4"), ("isRC", "<i4"), ("banded", "<i4"),
+                         ("useClippingOptimizations", "<i4")])
+AG_OUT_DTYPE = np.dtype([("agScore", "<i4"), ("textOffset", "<i4"), ("patternOffset", "<i4"), ("nEdits", "<i4"),
+                         ("matchProbability", "<f8")])
+AG_PARAMS_DEFAULT = np.array([1, 4, 6, 1, 10, 7], dtype=np.int32)
+
+
+def counters_dict(arr: np.ndarray) -> dict:
+    d = {k: int(arr[i]) for i, k in enumerate(COUNTER_FIELDS)}
+    d["mapqHistogram"] = [int(x) for x in arr[len(COUNTER_FIELDS):]]
+    return d
+
+
+def available() -> bool:
+    return os.path.exists(REF_SO)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libsnapref.so missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(REF_SO)
+        L.ref_index_load.restype = C.c_void_p
+        L.ref_index_load.argtypes = [C.c_char_p]
+        L.ref_single_create.restype = C.c_void_p
+        L.ref_single_create.argtypes = [C.c_void_p, C.POINTER(Params)]
+        L.ref_single_destroy.argtypes = [C.c_void_p]
+        L.ref_single_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.ref_single_align_mt.restype = C.c_double
+        L.ref_single_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int64] + [C.c_void_p] * 6
+        L.ref_lookup_seed.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+        L.ref_wrapped_seed.restype = C.c_uint
+        L.ref_wrapped_seed.argtypes = [C.c_uint, C.c_uint]
+        L.ref_mapq.restype = C.c_int
+        L.ref_mapq.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        L.ref_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+        L.ref_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_init()
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefIndex:
+    def __init__(self, directory: str):
+        self.handle = lib().ref_index_load(directory.encode())
+        if not self.handle:
+            raise RuntimeError("reference failed to load index " + directory)
+        self.directory = directory
+
+    def lookup(self, seed: bytes, max_out: int = 512):
+        nh = np.zeros(2, dtype=np.int64)
+        hits = np.zeros(2 * max_out, dtype=np.uint32)
+        extra = np.zeros(1, dtype=np.int64)
+        lib().ref_lookup_seed(self.handle, seed, _p(nh), _p(hits), max_out, _p(extra))
+        return (int(nh[0]), int(nh[1]), hits[:min(int(nh[0]), max_out)].copy(),
+                hits[max_out:max_out + min(int(nh[1]), max_out)].copy(), int(extra[0]))
+
+
+class RefSingleAligner:
+    def __init__(self, index: RefIndex, params: Params):
+        self.index = index
+        self.params = params
+        self.handle = lib().ref_single_create(index.handle, C.byref(params))
+
+    def align(self, batch):
+        res = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        ctr = np.zeros(N_COUNTERS, dtype=np.int64)
+        lib().ref_single_align(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens),
+                               _p(res), _p(ctr))
+        return res, counters_dict(ctr)
+
+    def close(self):
+        if self.handle:
+            lib().ref_single_destroy(self.handle)
+            self.handle = None
+
+
+def align_mt(index: RefIndex, params: Params, batch, threads: int):
+    res = np.zeros(batch.n, dtype=RESULT_DTYPE)
+    ctr = np.zeros(N_COUNTERS, dtype=np.int64)
+    secs = lib().ref_single_align_mt(index.handle, C.byref(params), threads, batch.n, _p(batch.bases), _p(batch.quals),
+                                     _p(batch.offsets), _p(batch.lens), _p(res), _p(ctr))
+    return res, counters_dict(ctr), float(secs)
+
+
+def lv_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray) -> np.ndarray:
+    out = np.zeros(jobs.size, dtype=LV_OUT_DTYPE)
+    lib().ref_lv_batch(_p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))
+    return out
+
+
+def ag_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray, params=AG_PARAMS_DEFAULT) -> np.ndarray:
+    out = np.zeros(jobs.size, dtype=AG_OUT_DTYPE)
+    params = np.ascontiguousarray(params, dtype=np.int32)
+    lib().ref_ag_batch(_p(params), _p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))
+    return out
+
+
+def tables(n_indel: int = 1200, n_perfect: int = 1001):
+    phred = np.zeros(256)
+    indel = np.zeros(n_indel)
+    perfect = np.zeros(n_perfect)
+    lib().ref_tables(_p(phred), _p(indel), n_indel, _p(perfect), n_perfect)
+    return phred, indel, perfect

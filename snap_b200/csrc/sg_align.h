@@ -1,0 +1,603 @@
+// sg_align.h -- the per-read single-end state machine.  Scalar form, host+device.
+// Restates BaseAligner::AlignRead (reference SNAPLib/BaseAligner.cpp:272-763), BaseAligner::score (:917-1534),
+// the candidate table (:1810-1973, :2331-2379), ScoreSet (:2143-2323) and scoreLimit (:2555-2570) for the
+// configuration `snap single` runs by default: no secondary results (-om unset), no Hamming pass.
+// Everything that decides *which* candidate is scored *when* (FIFO weight lists, per-seed score() calls, the
+// lowest-possible-score bound, early exits) is kept in the reference's order, because results depend on it.
+#pragma once
+#include "sg_common.h"
+#include "sg_seed.h"
+#include "sg_lv.h"
+#include "sg_ag.h"
+
+struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260-329
+    int      bestScore;
+    int64_t  bestScoreGenomeLocation, bestScoreOrigGenomeLocation;
+    int      bestScoreDirection;
+    int      bestScoreUsedAffineGapScoring;
+    int      bestScoreBasesClippedBefore, bestScoreBasesClippedAfter;
+    int      bestScoreAGScore;
+    int      bestScoreSeedOffset;
+    double   bestScoreMatchProbability;
+    double   probabilityOfAllCandidates, probabilityOfBestCandidate;
+
+    SG_HD void init(int64_t invalidLocation) {   // :2099-2114
+        bestScore = SG_UNUSED_SCORE;
+        bestScoreGenomeLocation = invalidLocation; bestScoreOrigGenomeLocation = invalidLocation;
+        bestScoreDirection = 0; bestScoreUsedAffineGapScoring = 0;
+        bestScoreBasesClippedBefore = 0; bestScoreBasesClippedAfter = 0;
+        bestScoreAGScore = -1; bestScoreSeedOffset = 0; bestScoreMatchProbability = 0.0;
+        probabilityOfAllCandidates = 0; probabilityOfBestCandidate = 0;
+    }
+    SG_HD void updateProbabilitiesForNearbyMatch(double p) {            // :2132-2135
+        double v = probabilityOfAllCandidates - p;
+        probabilityOfAllCandidates = v > 0.0 ? v : 0.0;
+    }
+    SG_HD void updateProbabilitiesForNewMatch(double newP, double nearbyP) {   // :2137-2141
+        double v = probabilityOfAllCandidates - nearbyP;
+        probabilityOfAllCandidates = v > 0.0 ? v : 0.0;
+        probabilityOfAllCandidates += newP;
+    }
+    // ScoreSet::updateBestScore with secondaryResults == NULL and candidatesForAffineGap == NULL (:2143-2299)
+    SG_HD void updateBestScore(int64_t genomeLocation, int64_t origGenomeLocation, unsigned score, bool useAffineGap, int agScore,
+                               double matchProbability, const SgElem *el) {
+        bool seenNewBestScore;
+        if (useAffineGap) {
+            seenNewBestScore = (agScore > bestScoreAGScore) || (bestScoreAGScore == agScore && matchProbability > probabilityOfBestCandidate);
+        } else {
+            seenNewBestScore = (score < (unsigned)bestScore) || (score == (unsigned)bestScore && matchProbability > probabilityOfBestCandidate);
+        }
+        if (seenNewBestScore) {
+            bestScore = (int)score;
+            bestScoreAGScore = agScore;
+            probabilityOfBestCandidate = matchProbability;
+            bestScoreGenomeLocation = genomeLocation;
+            bestScoreOrigGenomeLocation = origGenomeLocation;
+            bestScoreDirection = el->direction;
+            bestScoreUsedAffineGapScoring = el->usedAffineGapScoring;
+            bestScoreBasesClippedBefore = el->basesClippedBefore;
+            bestScoreBasesClippedAfter = el->basesClippedAfter;
+            bestScoreSeedOffset = el->seedOffset;
+            bestScoreMatchProbability = el->matchProbabilityForBestScore;
+        }
+    }
+    SG_HD void fillIn(const SgTables &T, snapgpu_single_result *r, int popularSeedsSkipped) const {   // :2301-2323
+        r->agScore = bestScoreAGScore;
+        r->basesClippedAfter = bestScoreBasesClippedAfter;
+        r->basesClippedBefore = bestScoreBasesClippedBefore;
+        r->clippingForReadAdjustment = 0;
+        r->direction = bestScoreDirection;
+        r->location = bestScoreGenomeLocation;
+        r->origLocation = bestScoreOrigGenomeLocation;
+        r->mapq = sg_compute_mapq(T, probabilityOfAllCandidates, probabilityOfBestCandidate, popularSeedsSkipped);
+        r->score = bestScore;
+        r->usedAffineGapScoring = bestScoreUsedAffineGapScoring;
+        r->seedOffset = bestScoreSeedOffset;
+        r->matchProbability = bestScoreMatchProbability;
+        r->popularSeedsSkipped = (uint32_t)popularSeedsSkipped;
+        r->status = (r->mapq >= SG_MAPQ_LIMIT_FOR_SINGLE_HIT) ? SNAPGPU_SINGLE_HIT : SNAPGPU_MULTIPLE_HITS;
+        r->probabilityAllCandidates = probabilityOfAllCandidates;
+    }
+};
+
+// The BaseAligner member state that lives across AlignRead()/score() for one read.
+struct SgAligner {
+    const SgIndexView *ix;
+    const SgParams    *pr;
+    const SgTables    *tb;
+    SgScratch          sc;
+    SgAgParams         ag;
+    SgWork             work;
+
+    // per-read state
+    const uint8_t *readData[2], *readQual[2];   // [FORWARD] = input, [RC] = rcRead/rcQual
+    uint32_t readLen;
+    uint32_t nUsedElements, highestUsedWeightList, wrapCount, nAddedToHashTable, popularSeedsSkipped;
+    uint32_t lowestPossibleScoreOfAnyUnseenLocation[2], currRoundLowestPossibleScoreOfAnyUnseenLocation[2];
+    uint32_t mostSeedsContainingAnyParticularBase[2], nSeedsApplied[2];
+    SgScoreSet all, nonAlt;
+    int64_t invalidLocation;
+
+    // ---- weight lists: doubly linked FIFO per weight; link values are element indices or SG_SENTINEL+w ----
+    SG_HD uint32_t getNext(uint32_t n) const { return (n & SG_SENTINEL) ? sc.listNext[n & ~SG_SENTINEL] : sc.pool[n].weightNext; }
+    SG_HD uint32_t getPrev(uint32_t n) const { return (n & SG_SENTINEL) ? sc.listPrev[n & ~SG_SENTINEL] : sc.pool[n].weightPrev; }
+    SG_HD void setNext(uint32_t n, uint32_t v) { if (n & SG_SENTINEL) sc.listNext[n & ~SG_SENTINEL] = v; else sc.pool[n].weightNext = v; }
+    SG_HD void setPrev(uint32_t n, uint32_t v) { if (n & SG_SENTINEL) sc.listPrev[n & ~SG_SENTINEL] = v; else sc.pool[n].weightPrev = v; }
+
+    SG_HD bool isALT(int64_t loc) const { return loc >= ix->altFirstLocation; }
+
+    // BaseAligner::scoreLimit (:2555-2570).  All quantities are non-negative, so the reference's mixed
+    // signed/unsigned __min chain reduces to plain integer minima.
+    SG_HD int scoreLimit(bool forALT) const {
+        int esd = (int)pr->extraSearchDepth, maxK = (int)pr->maxK;
+        if (pr->noUkkonen) { int v = maxK + esd; return v < SG_MAX_K - 1 ? v : SG_MAX_K - 1; }
+        int inner;
+        if (forALT) {
+            int g = pr->maxScoreGapToPreferNonAltAlignment < nonAlt.bestScore ? pr->maxScoreGapToPreferNonAltAlignment : nonAlt.bestScore;
+            int t = nonAlt.bestScore - g;
+            inner = all.bestScore < t ? all.bestScore : t;
+        } else {
+            int t = all.bestScore + pr->maxScoreGapToPreferNonAltAlignment;
+            inner = t < nonAlt.bestScore ? t : nonAlt.bestScore;
+        }
+        int v = esd + (maxK < inner ? maxK : inner);
+        return v < SG_MAX_K - 1 ? v : SG_MAX_K - 1;
+    }
+
+    // ---- candidate lookup table (our own open-addressing map standing in for the epoch-cleared chained table,
+    //      :340-364; only the key -> element mapping is observable) ----
+    SG_HD uint32_t tableHash(uint32_t baseLoc, uint32_t dir) const {
+        uint32_t k = (baseLoc / SG_ELEM_SIZE) * 2u + dir;
+        k *= 0x9E3779B1u;
+        return (k >> 7) & (pr->tableSlots - 1);
+    }
+    // findElement (:1810-1840): returns element index or ~0u
+    SG_HD uint32_t findElement(uint32_t genomeLocation32, uint32_t dir) const {
+        uint32_t base = genomeLocation32 - genomeLocation32 % SG_ELEM_SIZE;
+        uint32_t s = tableHash(base, dir);
+        for (;;) {
+            uint32_t v = sc.table[s];
+            if (v == 0) return ~0u;
+            const SgElem &el = sc.pool[v - 1];
+            if (el.baseGenomeLocation == base && el.direction == dir) return v - 1;
+            s = (s + 1) & (pr->tableSlots - 1);
+        }
+    }
+    // allocateNewCandidate (:1884-1973)
+    SG_HD uint32_t allocateNewCandidate(uint32_t genomeLocation32, uint32_t dir, uint32_t lowestPossibleScore, int seedOffset) {
+        uint32_t low = genomeLocation32 % SG_ELEM_SIZE;
+        uint32_t base = genomeLocation32 - low;
+        uint32_t ei = nUsedElements++;
+        SgElem &el = sc.pool[ei];
+        el.candidatesUsed = (uint64_t)1 << low;
+        el.candidatesScored = 0;
+        el.lowestPossibleScore = lowestPossibleScore;
+        el.direction = (uint8_t)dir;
+        el.weight = 1;
+        el.baseGenomeLocation = base;
+        el.bestScore = SG_UNUSED_SCORE;
+        el.allExtantCandidatesScored = 0;
+        el.matchProbabilityForBestScore = 0;
+        el.usedAffineGapScoring = 0;
+        el.basesClippedBefore = 0;
+        el.basesClippedAfter = 0;
+        el.agScore = 0;
+        el.seedOffset = 0;
+        el.bestScoreGenomeLocation = 0;
+        // insert at the tail of weight list 1
+        uint32_t head = SG_SENTINEL | 1u;
+        uint32_t tail = getPrev(head);
+        el.weightNext = head;
+        el.weightPrev = tail;
+        setPrev(head, ei);
+        setNext(tail, ei);
+        el.candSeedOffset[low] = (uint16_t)seedOffset;
+        if (highestUsedWeightList < 1) highestUsedWeightList = 1;
+        uint32_t s = tableHash(base, dir);
+        while (sc.table[s] != 0) s = (s + 1) & (pr->tableSlots - 1);
+        sc.table[s] = ei + 1;
+        el.slot = s;
+        return ei;
+    }
+    // incrementWeight (:2341-2379)
+    SG_HD void incrementWeight(uint32_t ei) {
+        SgElem &el = sc.pool[ei];
+        if (el.allExtantCandidatesScored) return;
+        if (el.weight >= pr->numWeightLists - 1) return;
+        setPrev(el.weightNext, el.weightPrev);
+        setNext(el.weightPrev, el.weightNext);
+        el.weight++;
+        if (highestUsedWeightList < el.weight) highestUsedWeightList = el.weight;
+        uint32_t head = SG_SENTINEL | el.weight;
+        uint32_t tail = getPrev(head);
+        el.weightNext = head;
+        el.weightPrev = tail;
+        setPrev(head, ei);
+        setNext(tail, ei);
+    }
+    // clearCandidates (:2331-2339), plus un-marking our lookup table
+    SG_HD void clearCandidates() {
+        for (uint32_t i = 0; i < nUsedElements; i++) sc.table[sc.pool[i].slot] = 0;
+        nUsedElements = 0;
+        highestUsedWeightList = 0;
+        for (uint32_t i = 1; i < pr->numWeightLists; i++) {
+            sc.listNext[i] = SG_SENTINEL | i;
+            sc.listPrev[i] = SG_SENTINEL | i;
+        }
+    }
+
+    SG_HD bool isSeedUsed(uint32_t i) const { return (sc.seedUsed[i / 8] & (1 << (i % 8))) != 0; }
+    SG_HD void setSeedUsed(uint32_t i) { sc.seedUsed[i / 8] |= (uint8_t)(1 << (i % 8)); }
+};
+
+// Result of scoring one candidate location: the block :1117-1334 of BaseAligner::score.
+struct SgCandScore {
+    unsigned score; double matchProbability; int64_t genomeLocation; int usedAffineGapScoring;
+    int basesClippedBefore, basesClippedAfter, agScore;
+};
+
+SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLocationIn, int seedOffset, int scoreLimitForThisElement, SgCandScore *o)
+{
+    const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
+    int64_t genomeLocation = genomeLocationIn;
+    unsigned score = (unsigned)SG_SCORE_ABOVE_LIMIT;
+    double matchProbability = 0.0;
+    const int dirn = el.direction;
+    int readLen = (int)A.readLen;
+    int64_t genomeDataLength = (int64_t)readLen + SG_MAX_K;
+    const uint8_t *data = sg_get_substring(ix, genomeLocation, genomeDataLength);
+    int usedAffineGapScoring = 0, basesClippedBefore = 0, basesClippedAfter = 0, agScore = -1;
+
+    if (data != (const uint8_t *)0) {
+        const uint8_t *readToScore = A.readData[dirn];
+        const uint8_t *qualToScore = A.readQual[dirn];
+        const uint8_t *oppQual = A.readQual[1 - dirn];
+        const uint8_t *revRead = A.sc.revRead[dirn];
+        double matchProb1 = 1.0, matchProb2 = 1.0;
+        int score1 = 0, score2 = 0;
+        int seedLen = (int)ix.seedLen;
+        int tailStart = seedOffset + seedLen;
+        int agScore1 = seedLen, agScore2 = 0;
+        int maxKForSameAlignment = pr.gapOpenPenalty / (pr.subPenalty - pr.gapExtendPenalty);
+        int genomeLocationOffset = 0;
+        int64_t tl = genomeDataLength - tailStart;
+        int textLen = (int)(tl < 0x7ffffff0 ? tl : 0x7ffffff0);
+
+        SgLvResult lv;
+        sg_lv_compute(T, A.sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart,
+                      scoreLimitForThisElement, &lv);
+        score1 = lv.score; matchProb1 = lv.matchProbability;
+        agScore1 = (seedLen + readLen - tailStart - score1) * pr.matchReward - score1 * pr.subPenalty;
+        if (score1 != SG_SCORE_ABOVE_LIMIT) {
+            int limitLeft = scoreLimitForThisElement - score1;
+            sg_lv_compute(T, A.sc, -1, data + seedOffset, seedOffset + SG_MAX_K, revRead + readLen - seedOffset, oppQual + readLen - seedOffset,
+                          seedOffset, limitLeft, &lv);
+            score2 = lv.score; matchProb2 = lv.matchProbability; genomeLocationOffset = lv.netIndel;
+            agScore2 = (seedOffset - score2) * pr.matchReward - score2 * pr.subPenalty;
+        }
+        A.work.lvCalls++;
+
+        if (score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT) {
+            // :1203
+            if (pr.noEditDistance || (pr.useAffineGap && (score1 + score2 > maxKForSameAlignment && el.lowestPossibleScore <= (unsigned)A.all.bestScore))) {
+                score1 = 0; score2 = 0; agScore1 = seedLen; agScore2 = 0;
+                usedAffineGapScoring = 1;
+                A.work.agCalls++;
+                SgAgResult ar;
+                if (tailStart != readLen) {
+                    int patternLen = readLen - tailStart;
+                    bool banded = (patternLen >= (3 * (2 * scoreLimitForThisElement + 1))) && !pr.noBandedAffineGap;
+                    sg_ag_compute(T, A.sc, A.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart,
+                                  patternLen, scoreLimitForThisElement, readLen, dirn != 0, false, &ar);
+                    agScore1 = ar.agScore; basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
+                    agScore1 += (seedLen - readLen);
+                }
+                if (score1 != SG_SCORE_ABOVE_LIMIT) {
+                    if (seedOffset != 0) {
+                        int limitLeft = scoreLimitForThisElement - score1;
+                        int patternLen = seedOffset;
+                        bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
+                        sg_ag_compute(T, A.sc, A.ag, -1, banded, data + seedOffset, seedOffset + limitLeft, revRead + readLen - seedOffset,
+                                      oppQual + readLen - seedOffset, seedOffset, limitLeft, readLen, dirn != 0, false, &ar);
+                        agScore2 = ar.agScore; genomeLocationOffset = ar.textOffset; basesClippedBefore = ar.patternOffset;
+                        score2 = ar.nEdits; matchProb2 = ar.matchProbability;
+                        agScore2 -= readLen;
+                    }
+                }
+            }
+        }
+
+        bool foundAlignment = (score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT);
+        if (foundAlignment && genomeLocationOffset != 0 &&
+            (const uint8_t *)0 == sg_get_substring(ix, genomeLocation + genomeLocationOffset, genomeDataLength)) {
+            foundAlignment = false;
+        }
+        if (foundAlignment) {
+            score = (unsigned)(score1 + score2);
+            matchProbability = matchProb1 * matchProb2 * T.snpPowSeedLen;
+            genomeLocation += genomeLocationOffset;
+            agScore = agScore1 + agScore2;
+        } else {
+            score = (unsigned)SG_SCORE_ABOVE_LIMIT;
+            agScore = SG_SCORE_ABOVE_LIMIT;
+            matchProbability = 0.0;
+        }
+    } else {
+        matchProbability = 0.0;
+    }
+    o->score = score; o->matchProbability = matchProbability; o->genomeLocation = genomeLocation;
+    o->usedAffineGapScoring = usedAffineGapScoring; o->basesClippedBefore = basesClippedBefore; o->basesClippedAfter = basesClippedAfter;
+    o->agScore = agScore;
+}
+
+// BaseAligner::score (:917-1534).  Returns true iff a result was reached.
+SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult)
+{
+    const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
+    if (0 == A.mostSeedsContainingAnyParticularBase[0] && 0 == A.mostSeedsContainingAnyParticularBase[1]) {
+        primaryResult->status = SNAPGPU_NOT_FOUND;
+        primaryResult->mapq = 0;
+        return true;
+    }
+    for (int direction = 0; direction < 2; direction++) {
+        if (0 != A.mostSeedsContainingAnyParticularBase[direction]) {
+            uint32_t v = A.nSeedsApplied[direction] / A.mostSeedsContainingAnyParticularBase[direction];
+            if (A.lowestPossibleScoreOfAnyUnseenLocation[direction] < v) A.lowestPossibleScoreOfAnyUnseenLocation[direction] = v;
+        }
+    }
+
+    uint32_t weightListToCheck = A.highestUsedWeightList;
+    do {
+        while (weightListToCheck > 0 && A.sc.listNext[weightListToCheck] == (SG_SENTINEL | weightListToCheck)) {
+            weightListToCheck--;
+            A.highestUsedWeightList = weightListToCheck;
+        }
+        uint32_t lpsMin = A.lowestPossibleScoreOfAnyUnseenLocation[0] < A.lowestPossibleScoreOfAnyUnseenLocation[1]
+                              ? A.lowestPossibleScoreOfAnyUnseenLocation[0] : A.lowestPossibleScoreOfAnyUnseenLocation[1];
+        int slT = A.scoreLimit(true), slF = A.scoreLimit(false);
+        int slMax = slT > slF ? slT : slF;
+        if ((lpsMin > (uint32_t)slMax && !pr.noTruncation) || forceResult) {
+            if (weightListToCheck < pr.minWeightToCheck) {
+                const SgScoreSet *fin;
+                if (!pr.altAwareness || A.nonAlt.bestScore > A.all.bestScore + pr.maxScoreGapToPreferNonAltAlignment) {
+                    fin = &A.all;
+                } else {
+                    fin = &A.nonAlt;
+                }
+                primaryResult->score = fin->bestScore;
+                if (fin->bestScore <= (int)pr.maxK) {
+                    fin->fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
+                    primaryResult->supplementary = 0;
+                    return true;
+                } else {
+                    primaryResult->status = SNAPGPU_NOT_FOUND;
+                    primaryResult->mapq = 0;
+                    return true;
+                }
+            }
+            forceResult = true;
+        } else if (weightListToCheck == 0) {
+            return false;
+        }
+
+        uint32_t ei = A.sc.listNext[weightListToCheck];
+        SgElem &el = A.sc.pool[ei];
+        int scoreLimitForThisElement = A.scoreLimit(pr.altAwareness && A.isALT((int64_t)el.baseGenomeLocation));
+        if (el.lowestPossibleScore <= (uint32_t)scoreLimitForThisElement) {
+            uint64_t candidatesMask = el.candidatesUsed;
+            while (candidatesMask != 0) {
+                uint32_t candidateIndexToScore = 0;
+                { uint64_t m = candidatesMask; while (!(m & 1)) { m >>= 1; candidateIndexToScore++; } }   // _BitScanForward64
+                uint64_t candidateBit = (uint64_t)1 << candidateIndexToScore;
+                candidatesMask &= ~candidateBit;
+                if ((el.candidatesScored & candidateBit) != 0) continue;
+                bool anyNearbyCandidatesAlreadyScored = el.candidatesScored != 0;
+                el.candidatesScored |= candidateBit;
+
+                int64_t genomeLocation = (int64_t)el.baseGenomeLocation + candidateIndexToScore;
+                int64_t origGenomeLocation = genomeLocation;
+                int64_t elementGenomeLocation = genomeLocation;
+                bool genomeLocationIsNonALT = (!pr.altAwareness) || !A.isALT(genomeLocation);
+
+                SgCandScore cs;
+                sg_score_candidate(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, &cs);
+                unsigned score = cs.score;
+                double matchProbability = cs.matchProbability;
+                genomeLocation = cs.genomeLocation;
+
+                if (anyNearbyCandidatesAlreadyScored) {
+                    if (el.bestScore < score || (el.bestScore == score && matchProbability <= el.matchProbabilityForBestScore)) {
+                        continue;
+                    }
+                }
+                el.bestScoreGenomeLocation = genomeLocation;
+                el.usedAffineGapScoring = (uint8_t)cs.usedAffineGapScoring;
+                el.basesClippedBefore = cs.basesClippedBefore;
+                el.basesClippedAfter = cs.basesClippedAfter;
+                el.agScore = cs.agScore;
+                el.seedOffset = (int)el.candSeedOffset[candidateIndexToScore];
+
+                uint32_t nearby = ~0u;
+                if ((unsigned)SG_SCORE_ABOVE_LIMIT != score && score < 2) {
+                    int64_t half = SG_ELEM_SIZE / 2;
+                    int64_t nearbyGenomeLocation = elementGenomeLocation + (2 * ((elementGenomeLocation % SG_ELEM_SIZE) / half) - 1) * half;
+                    // the reference keys its table on the 64-bit location, so a (negative / >32-bit) neighbour never matches
+                    if (nearbyGenomeLocation >= 0 && nearbyGenomeLocation <= 0xffffffffLL) {
+                        nearby = A.findElement((uint32_t)nearbyGenomeLocation, el.direction);
+                    }
+                }
+                if (nearby != ~0u && A.sc.pool[nearby].candidatesScored != 0) {
+                    SgElem &ne = A.sc.pool[nearby];
+                    int64_t dist = genomeLocation - ne.bestScoreGenomeLocation; if (dist < 0) dist = -dist;
+                    if (!(dist <= SG_MAX_MERGE_DIST)) {
+                        nearby = ~0u;
+                    } else {
+                        if (ne.bestScore < score || (ne.bestScore == score && ne.matchProbabilityForBestScore >= matchProbability)) {
+                            continue;
+                        }
+                        A.all.updateProbabilitiesForNearbyMatch(ne.matchProbabilityForBestScore);
+                        if (genomeLocationIsNonALT) A.nonAlt.updateProbabilitiesForNearbyMatch(ne.matchProbabilityForBestScore);
+                        anyNearbyCandidatesAlreadyScored = true;
+                        ne.matchProbabilityForBestScore = 0;
+                    }
+                }
+
+                A.all.updateProbabilitiesForNewMatch(matchProbability, el.matchProbabilityForBestScore);
+                if (genomeLocationIsNonALT) A.nonAlt.updateProbabilitiesForNewMatch(matchProbability, el.matchProbabilityForBestScore);
+                el.matchProbabilityForBestScore = matchProbability;
+                el.bestScore = score;
+
+                A.all.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
+                if (genomeLocationIsNonALT) {
+                    // the reference calls this twice more (:1463, :1484); with no secondary buffers the repeats are no-ops
+                    A.nonAlt.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
+                }
+
+                if (pr.stopOnFirstHit && (A.all.bestScore <= (int)pr.maxK)) {
+                    (pr.altAwareness ? A.nonAlt : A.all).fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
+                    primaryResult->status = SNAPGPU_MULTIPLE_HITS;
+                    primaryResult->mapq = 0;
+                    return true;
+                }
+                if ((pr.altAwareness ? A.nonAlt.probabilityOfAllCandidates : A.all.probabilityOfAllCandidates) >= 4.9) {
+                    (pr.altAwareness ? A.nonAlt : A.all).fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
+                    return true;
+                }
+            }
+        }
+        // remove the element from its weight list
+        el.allExtantCandidatesScored = 1;
+        A.setPrev(el.weightNext, el.weightPrev);
+        A.setNext(el.weightPrev, el.weightNext);
+        el.weightNext = el.weightPrev = ei;
+    } while (forceResult);
+    return false;
+}
+
+// BaseAligner::AlignRead (:272-763) for one read with the stock loop's arguments (SingleAligner.cpp:250).
+// `result` must be caller-zeroed POD; on return it holds what the reference would have put in primaryResult.
+SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult)
+{
+    const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
+    const uint32_t seedLen = ix.seedLen;
+    A.all.bestScore = A.nonAlt.bestScore = SG_TOO_BIG_SCORE;
+
+    uint32_t maxSeedsToUse;
+    if (0 != pr.numSeedsFromCommandLine) {
+        maxSeedsToUse = pr.numSeedsFromCommandLine;
+    } else {
+        maxSeedsToUse = (uint32_t)(int)(2 * pr.seedCoverage * readLen / (int)seedLen);
+    }
+
+    primaryResult->location = A.invalidLocation;
+    primaryResult->direction = SNAPGPU_FORWARD;
+    primaryResult->score = SG_UNUSED_SCORE;
+    primaryResult->status = SNAPGPU_NOT_FOUND;
+    primaryResult->clippingForReadAdjustment = 0;
+    primaryResult->usedAffineGapScoring = 0;
+    primaryResult->basesClippedBefore = 0;
+    primaryResult->basesClippedAfter = 0;
+    primaryResult->agScore = 0;
+    primaryResult->seedOffset = 0;
+    primaryResult->supplementary = 0;
+
+    A.popularSeedsSkipped = 0;
+    A.nAddedToHashTable = 0;
+    A.readLen = readLen;
+
+    if ((int)readLen < (int)seedLen) {
+        return;                      // :360-366, "hopeless"
+    }
+
+    for (uint32_t i = 0; i < (readLen + 7) / 8; i++) A.sc.seedUsed[i] = 0;
+
+    uint32_t countOfNs = 0;
+    for (uint32_t i = 0; i < readLen; i++) {
+        uint8_t baseByte = readData[i];
+        uint8_t complement = sg_complement(baseByte);
+        A.sc.rcRead[readLen - i - 1] = complement;
+        A.sc.rcQual[readLen - i - 1] = readQuality[i];
+        A.sc.revRead[0][readLen - i - 1] = baseByte;
+        A.sc.revRead[1][i] = complement;
+        countOfNs += (baseByte == 'N') ? 1u : 0u;                  // nTable, :212-214
+    }
+    if (countOfNs > pr.maxK) {
+        return;                      // :398-402
+    }
+    if (countOfNs > 0) {             // :407-420
+        int minSeedToConsiderNing = 0;
+        for (int i = 0; i < (int)readLen; i++) {
+            if (sg_base_value(readData[i]) > 3) {
+                int limit = (i + (int)seedLen - 1) < ((int)readLen - 1) ? (i + (int)seedLen - 1) : ((int)readLen - 1);
+                int j0 = minSeedToConsiderNing > (i - (int)seedLen + 1) ? minSeedToConsiderNing : (i - (int)seedLen + 1);
+                for (int j = j0; j <= limit; j++) A.setSeedUsed((uint32_t)j);
+                minSeedToConsiderNing = limit + 1;
+                if (minSeedToConsiderNing >= (int)readLen) break;
+            }
+        }
+    }
+
+    A.readData[0] = readData;   A.readQual[0] = readQuality;
+    A.readData[1] = A.sc.rcRead; A.readQual[1] = A.sc.rcQual;
+
+    A.clearCandidates();
+
+    uint32_t nPossibleSeeds = readLen - seedLen + 1;
+    uint32_t nextSeedToTest = 0;
+    A.wrapCount = 0;
+    A.lowestPossibleScoreOfAnyUnseenLocation[0] = A.lowestPossibleScoreOfAnyUnseenLocation[1] = 0;
+    A.currRoundLowestPossibleScoreOfAnyUnseenLocation[0] = A.currRoundLowestPossibleScoreOfAnyUnseenLocation[1] = 0;
+    A.mostSeedsContainingAnyParticularBase[0] = A.mostSeedsContainingAnyParticularBase[1] = 1;
+    A.all.init(A.invalidLocation);
+    if (pr.altAwareness) A.nonAlt.init(A.invalidLocation);
+    A.nSeedsApplied[0] = A.nSeedsApplied[1] = 0;
+
+    while (A.nSeedsApplied[0] + A.nSeedsApplied[1] < maxSeedsToUse) {
+        if (nextSeedToTest >= nPossibleSeeds) {
+            A.wrapCount++;
+            if (A.wrapCount >= seedLen) {
+                sg_score(A, true, primaryResult);
+                primaryResult->scorePriorToClipping = primaryResult->score;     // finalizeSecondaryResults, :2442
+                return;
+            }
+            nextSeedToTest = T.wrapSeed[A.wrapCount];
+            A.mostSeedsContainingAnyParticularBase[0] = A.mostSeedsContainingAnyParticularBase[1] = A.wrapCount + 1;
+            A.currRoundLowestPossibleScoreOfAnyUnseenLocation[0] = A.currRoundLowestPossibleScoreOfAnyUnseenLocation[1] = 0;
+        }
+        while (nextSeedToTest < nPossibleSeeds && A.isSeedUsed(nextSeedToTest)) nextSeedToTest++;
+        if (nextSeedToTest >= nPossibleSeeds) continue;
+        A.setSeedUsed(nextSeedToTest);
+
+        uint64_t sb, srcb;
+        if (!sg_seed_pack(readData + nextSeedToTest, seedLen, &sb, &srcb)) continue;
+
+        SgHits hits;
+        sg_lookup_seed32(ix, sb, srcb, &hits, &A.work.entriesProbed, &A.work.overflowWords);
+        A.work.lookups++;
+
+        bool appliedEitherSeed = false;
+        for (uint32_t direction = 0; direction < 2; direction++) {
+            if (hits.nHits[direction] > pr.maxHits && !pr.explorePopularSeeds) {
+                A.work.popularIgnored++;
+                A.popularSeedsSkipped++;
+            } else {
+                uint32_t offset = (direction == 0) ? nextSeedToTest : (readLen - seedLen - nextSeedToTest);
+                uint32_t limit = hits.nHits[direction] < pr.maxHits ? hits.nHits[direction] : pr.maxHits;
+                A.work.overflowWords += (hits.nHits[direction] > 1) ? limit : 0;
+                for (uint32_t i = 0; i < limit; i++) {
+                    uint32_t genomeLocationOfThisHit = hits.hits[direction][i] - offset;       // 32-bit wrap like the reference
+                    uint32_t ei = A.findElement(genomeLocationOfThisHit, direction);
+                    if (ei != ~0u) {
+                        // findCandidate (:1873-1878)
+                        SgElem &el = A.sc.pool[ei];
+                        uint32_t low = genomeLocationOfThisHit % SG_ELEM_SIZE;
+                        uint64_t bit = (uint64_t)1 << low;
+                        el.allExtantCandidatesScored = (uint8_t)(el.allExtantCandidatesScored && ((el.candidatesUsed & bit) != 0));
+                        el.candidatesUsed |= bit;
+                        if (!pr.noOrderedEvaluation) A.incrementWeight(ei);
+                        el.candSeedOffset[low] = (uint16_t)offset;
+                    } else {
+                        bool candidateIsALT = pr.altAwareness && A.isALT((int64_t)genomeLocationOfThisHit);
+                        if (A.lowestPossibleScoreOfAnyUnseenLocation[direction] <= (uint32_t)A.scoreLimit(candidateIsALT) || pr.noTruncation) {
+                            A.allocateNewCandidate(genomeLocationOfThisHit, direction, A.lowestPossibleScoreOfAnyUnseenLocation[direction], (int)offset);
+                            A.nAddedToHashTable++;
+                        }
+                    }
+                }
+                A.nSeedsApplied[direction]++;
+                A.currRoundLowestPossibleScoreOfAnyUnseenLocation[direction]++;
+                appliedEitherSeed = true;
+            }
+        }
+        nextSeedToTest += seedLen;
+
+        if (appliedEitherSeed) {
+            if (sg_score(A, false, primaryResult)) {
+                primaryResult->scorePriorToClipping = primaryResult->score;
+                return;
+            }
+        }
+    }
+    sg_score(A, true, primaryResult);
+    primaryResult->scorePriorToClipping = primaryResult->score;
+}

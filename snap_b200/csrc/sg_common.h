@@ -1,0 +1,160 @@
+// sg_common.h -- shared POD types of the device engine (index view, parameters, probability tables,
+// per-worker scratch).  Plain structs: usable from nvcc device code and from host C++.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/snapgpu.h"
+
+#if defined(__CUDACC__)
+#define SG_HD __host__ __device__ __forceinline__
+#define SG_HDN __host__ __device__ __noinline__
+#else
+#define SG_HD inline
+#define SG_HDN inline
+#endif
+
+#define SG_MAX_K 127                 // reference LandauVishkin.h:11
+#define SG_N_PADDING 1000            // reference Genome.h:446
+#define SG_MAX_MERGE_DIST 48         // reference BaseAligner.h:177 (also hashTableElementSize, :213)
+#define SG_ELEM_SIZE 48
+#define SG_UNUSED_SCORE 0xffffu      // BaseAligner.h:141
+#define SG_SCORE_ABOVE_LIMIT (-1)    // LandauVishkin.h:14
+#define SG_TOO_BIG_SCORE 65536       // LandauVishkin.h:15
+#define SG_MAX_INDEL_TABLE 1200
+#define SG_MAX_PERFECT_TABLE 1001
+#define SG_MAPQ_LIMIT_FOR_SINGLE_HIT 10   // AlignerOptions.h:49
+#define SG_VEC 8                     // AffineGapVectorized.h:18 VEC_SIZE
+
+// The index as it lives in HBM.
+struct SgIndexView {
+    const uint8_t  *tables;          // all hash tables, entries back to back; table t starts at entry tableStart[t]
+    const uint64_t *tableStart;      // [nTables]
+    const uint64_t *tableSize;       // [nTables] slots
+    const uint32_t *overflow;        // overflow table (count, hits descending ...)
+    const uint8_t  *bases;           // pointer to genome location 0; [-SG_N_PADDING, nBases+SG_N_PADDING) is readable, padding is 'n'
+    const int64_t  *contigStart;     // [nContigs] beginningLocation, ascending
+    int64_t  nBases;                 // Genome::getCountOfBases()
+    int64_t  altFirstLocation;       // genomeLocationOfFirstALTContig (LLONG_MAX if none), Genome.cpp:460-476
+    uint64_t overflowSize;
+    uint32_t nContigs;
+    uint32_t seedLen;
+    uint32_t keyBytes;               // hashTableKeySize
+    uint32_t nTables;
+    uint32_t large;                  // 1: two values per entry (-large)
+    uint32_t entryBytes;             // 4*valueCount + keyBytes
+    uint32_t chromosomePadding;
+    uint32_t invalidValue;           // 0xffffffff
+};
+
+// Probability / schedule tables (host-computed with the host libm so doubles are bit-identical to the reference's).
+struct SgTables {
+    double phred[256];                         // lv_phredToProbability, LandauVishkin.cpp:745-753
+    double indel[SG_MAX_INDEL_TABLE];          // lv_indelProbabilities, :735-740
+    double perfect[SG_MAX_PERFECT_TABLE];      // lv_perfectMatchProbability, :757-760
+    double mapqThreshold[72];                  // mapqThreshold[m] = largest x with (int)(-10*log10(x)) >= m   (mapq.h:54)
+    double snpPowSeedLen;                      // pow(1 - SNP_PROB, seedLen), BaseAligner.cpp:1314
+    uint32_t wrapSeed[33];                     // GetWrappedNextSeedToTest(seedLen, w), SeedSequencer.cpp:105
+};
+
+struct SgParams {
+    uint32_t maxHits, maxK, numSeedsFromCommandLine;
+    double   seedCoverage;
+    uint32_t minWeightToCheck, extraSearchDepth, minReadLength;
+    int32_t  useAffineGap, matchReward, subPenalty, gapOpenPenalty, gapExtendPenalty, fivePrimeEndBonus, threePrimeEndBonus;
+    int32_t  noUkkonen, noOrderedEvaluation, noTruncation, noEditDistance, noBandedAffineGap;
+    int32_t  altAwareness, maxScoreGapToPreferNonAltAlignment, explorePopularSeeds, stopOnFirstHit;
+    // derived on the host
+    uint32_t numWeightLists;         // BaseAligner.cpp:173-180
+    uint32_t poolSize;               // hashTableElementPoolSize, BaseAligner.cpp:183
+    uint32_t tableSlots;             // power of two >= 2*poolSize (our candidate lookup table)
+    uint32_t maxReadLen;             // scratch sizing bound
+};
+
+// One candidate-table element: reference BaseAligner::HashTableElement (BaseAligner.h:223-258), compacted.
+struct SgElem {
+    uint64_t candidatesUsed;
+    uint64_t candidatesScored;
+    double   matchProbabilityForBestScore;
+    int64_t  bestScoreGenomeLocation;
+    uint32_t baseGenomeLocation;     // 32-bit index path: location - location % 48
+    uint32_t weightNext, weightPrev; // element index, or SG_SENTINEL + weight for the list head
+    uint32_t slot;                   // where this element sits in the lookup table (for O(1) clearing)
+    uint32_t weight;
+    uint32_t lowestPossibleScore;
+    uint32_t bestScore;
+    int32_t  basesClippedBefore, basesClippedAfter, agScore, seedOffset;
+    uint8_t  direction, allExtantCandidatesScored, usedAffineGapScoring, pad;
+    uint16_t candSeedOffset[SG_ELEM_SIZE];   // Candidate::seedOffset
+};
+#define SG_SENTINEL 0x80000000u
+
+// Per-worker (per-warp) scratch arena; all pointers are device global (or host in the test build).
+struct SgScratch {
+    SgElem   *pool;                  // [poolSize]
+    uint32_t *table;                 // [tableSlots]  element index + 1, 0 = empty
+    uint32_t *listNext, *listPrev;   // [numWeightLists] list heads
+    uint8_t  *rcRead, *rcQual;       // [maxReadLen]  reverse complement read / reversed quality
+    uint8_t  *revRead[2];            // [maxReadLen]  reversedRead[FORWARD], reversedRead[RC]
+    uint8_t  *seedUsed;              // [(maxReadLen+7)/8]
+    // Landau-Vishkin
+    int16_t  *lvL;                   // [(MAX_K+1)*(2*MAX_K+1)]
+    uint8_t  *lvA;
+    int16_t  *lvBtMatched, *lvBtD;   // [MAX_K+1]
+    uint8_t  *lvBtAction;
+    // affine gap
+    int16_t  *agH, *agHm1, *agE;     // [agCols]
+    uint8_t  *agBt;                  // [agRows*agCols]
+    uint32_t agCols, agRows;
+};
+
+SG_HD size_t sg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bytes of scratch one worker needs, and the carving of it.  agCols: padded pattern length; agRows: text rows.
+SG_HD size_t sg_scratch_bytes(const SgParams &p)
+{
+    size_t agCols = sg_align_up((size_t)p.maxReadLen * 3 / 2 + 64, 64);   // banded layout needs numSeg*segLen <= 4/3*P + 7 columns
+    size_t agRows = (size_t)p.maxReadLen + SG_MAX_K + 1;
+    size_t b = 0;
+    b += sg_align_up(sizeof(SgElem) * (size_t)p.poolSize, 256);
+    b += sg_align_up(sizeof(uint32_t) * (size_t)p.tableSlots, 256);
+    b += sg_align_up(sizeof(uint32_t) * 2 * (size_t)p.numWeightLists, 256);
+    b += sg_align_up((size_t)p.maxReadLen + 16, 256) * 4;                 // rcRead, rcQual, revRead x2
+    b += sg_align_up(((size_t)p.maxReadLen + 7) / 8 + 16, 256);
+    b += sg_align_up(sizeof(int16_t) * (SG_MAX_K + 1) * (2 * SG_MAX_K + 3), 256);
+    b += sg_align_up((SG_MAX_K + 1) * (2 * SG_MAX_K + 3), 256);
+    b += sg_align_up(sizeof(int16_t) * (SG_MAX_K + 2), 256) * 2;
+    b += sg_align_up(SG_MAX_K + 2, 256);
+    b += sg_align_up(sizeof(int16_t) * agCols, 256) * 3;
+    b += sg_align_up(agRows * agCols, 256);
+    return b;
+}
+
+SG_HD void sg_scratch_carve(const SgParams &p, uint8_t *base, SgScratch *s)
+{
+    size_t agCols = sg_align_up((size_t)p.maxReadLen * 3 / 2 + 64, 64);   // banded layout needs numSeg*segLen <= 4/3*P + 7 columns
+    size_t agRows = (size_t)p.maxReadLen + SG_MAX_K + 1;
+    uint8_t *q = base;
+    s->pool = (SgElem *)q;            q += sg_align_up(sizeof(SgElem) * (size_t)p.poolSize, 256);
+    s->table = (uint32_t *)q;         q += sg_align_up(sizeof(uint32_t) * (size_t)p.tableSlots, 256);
+    s->listNext = (uint32_t *)q;      s->listPrev = s->listNext + p.numWeightLists;
+                                      q += sg_align_up(sizeof(uint32_t) * 2 * (size_t)p.numWeightLists, 256);
+    size_t rl = sg_align_up((size_t)p.maxReadLen + 16, 256);
+    s->rcRead = q; q += rl; s->rcQual = q; q += rl; s->revRead[0] = q; q += rl; s->revRead[1] = q; q += rl;
+    s->seedUsed = q;                  q += sg_align_up(((size_t)p.maxReadLen + 7) / 8 + 16, 256);
+    s->lvL = (int16_t *)q;            q += sg_align_up(sizeof(int16_t) * (SG_MAX_K + 1) * (2 * SG_MAX_K + 3), 256);
+    s->lvA = q;                       q += sg_align_up((SG_MAX_K + 1) * (2 * SG_MAX_K + 3), 256);
+    s->lvBtMatched = (int16_t *)q;    q += sg_align_up(sizeof(int16_t) * (SG_MAX_K + 2), 256);
+    s->lvBtD = (int16_t *)q;          q += sg_align_up(sizeof(int16_t) * (SG_MAX_K + 2), 256);
+    s->lvBtAction = q;                q += sg_align_up(SG_MAX_K + 2, 256);
+    s->agH = (int16_t *)q;            q += sg_align_up(sizeof(int16_t) * agCols, 256);
+    s->agHm1 = (int16_t *)q;          q += sg_align_up(sizeof(int16_t) * agCols, 256);
+    s->agE = (int16_t *)q;            q += sg_align_up(sizeof(int16_t) * agCols, 256);
+    s->agBt = q;                      q += sg_align_up(agRows * agCols, 256);
+    s->agCols = (uint32_t)agCols;
+    s->agRows = (uint32_t)agRows;
+}
+
+// Per-read work counters accumulated by a worker (flushed with atomics at the end).
+struct SgWork {
+    uint32_t lookups, entriesProbed, overflowWords, lvCalls, agCalls, popularIgnored;
+};

@@ -1,0 +1,250 @@
+// sg_host.h -- host-side C++: reading a SNAP index directory (format v7.1), probability tables, parameter
+// derivation.  Header-only; used by the CUDA library and by the test-only host simulation build.
+#pragma once
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+#include <string>
+#include <vector>
+#include "sg_common.h"
+
+struct SgHostIndex {
+    std::vector<uint8_t>  tables;        // repacked: entries of all tables back to back (+8 bytes slack)
+    std::vector<uint64_t> tableStart, tableSize;
+    std::vector<uint32_t> overflow;      // +1 word slack
+    std::vector<uint8_t>  basesPadded;   // SG_N_PADDING 'n' + bases + SG_N_PADDING 'n'
+    std::vector<int64_t>  contigStart;
+    std::vector<uint8_t>  contigIsAlt;
+    std::vector<std::string> contigName;
+    int64_t  nBases = 0, altFirstLocation = LLONG_MAX;
+    uint32_t seedLen = 0, keyBytes = 0, nTables = 0, large = 0, entryBytes = 0, chromosomePadding = 0, locationSize = 4;
+    uint32_t invalidValue = 0xffffffffu;
+    uint64_t overflowSize = 0, totalSlots = 0;
+
+    SgIndexView view() const {           // host-memory view (test build); the CUDA library builds a device one
+        SgIndexView v;
+        v.tables = tables.data(); v.tableStart = tableStart.data(); v.tableSize = tableSize.data();
+        v.overflow = overflow.data(); v.bases = basesPadded.data() + SG_N_PADDING; v.contigStart = contigStart.data();
+        v.nBases = nBases; v.altFirstLocation = altFirstLocation; v.overflowSize = overflowSize;
+        v.nContigs = (uint32_t)contigStart.size(); v.seedLen = seedLen; v.keyBytes = keyBytes; v.nTables = nTables;
+        v.large = large; v.entryBytes = entryBytes; v.chromosomePadding = chromosomePadding; v.invalidValue = invalidValue;
+        return v;
+    }
+};
+
+static inline bool sg_read_file(const std::string &path, std::vector<uint8_t> &out, std::string &err)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) { err = "unable to open '" + path + "'"; return false; }
+    fseeko(f, 0, SEEK_END);
+    off_t n = ftello(f);
+    fseeko(f, 0, SEEK_SET);
+    out.resize((size_t)n);
+    size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    if (got != (size_t)n) { err = "short read on '" + path + "'"; return false; }
+    return true;
+}
+
+// Replaces GenomeIndex::loadFromDirectory + Genome::loadFromFile + SNAPHashTable::loadCommon
+// (reference GenomeIndex.cpp:1838-2093, Genome.cpp:276-440, HashTable.cpp:98-175).
+static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &ix, std::string &err)
+{
+    std::vector<uint8_t> buf;
+    // --- GenomeIndex: "major minor nHashTables overflowTableSize seedLen chromosomePadding keySize hashFileSize small locationSize"
+    if (!sg_read_file(dir + "/GenomeIndex", buf, err)) return false;
+    buf.push_back(0);
+    unsigned major, minor, nHashTables, seedLen, chromosomePadding, keySize, smallHashTable, locationSize;
+    long long overflowTableSize, hashTablesFileSize;
+    if (10 != sscanf((const char *)buf.data(), "%u %u %u %lld %u %u %u %lld %u %u", &major, &minor, &nHashTables, &overflowTableSize,
+                     &seedLen, &chromosomePadding, &keySize, &hashTablesFileSize, &smallHashTable, &locationSize)) {
+        err = "GenomeIndex header unparsable (index older than 1.0.4?)"; return false;
+    }
+    if (major != 7) { err = "index format major version is not 7"; return false; }      // GenomeIndex.h:170
+    if (locationSize != 4) { err = "only 4-byte genome locations (lookupSeed32 path) are supported"; return false; }
+    if (seedLen == 0 || seedLen > 32) { err = "bad seed length"; return false; }
+    ix.seedLen = seedLen; ix.chromosomePadding = chromosomePadding; ix.keyBytes = keySize; ix.nTables = nHashTables;
+    ix.large = smallHashTable ? 0 : 1; ix.locationSize = locationSize; ix.overflowSize = (uint64_t)overflowTableSize;
+
+    // --- Genome: "%lld %d %d\n", per contig "%lld %x %d %lld %x %d %d %s %s\n", then raw bases
+    if (!sg_read_file(dir + "/Genome", buf, err)) return false;
+    {
+        const char *p = (const char *)buf.data();
+        const char *endp = p + buf.size();
+        long long nBases; int nContigs, flags;
+        const char *nl = (const char *)memchr(p, '\n', buf.size());
+        if (!nl || 3 != sscanf(p, "%lld %d %d", &nBases, &nContigs, &flags)) { err = "Genome header unparsable"; return false; }
+        p = nl + 1;
+        ix.nBases = nBases;
+        ix.contigStart.clear(); ix.contigIsAlt.clear(); ix.contigName.clear();
+        for (int i = 0; i < nContigs; i++) {
+            nl = (const char *)memchr(p, '\n', endp - p);
+            if (!nl) { err = "Genome contig line truncated"; return false; }
+            long long start, projStart; unsigned cflags, projRC; int origNum, nameLen, cigarLen;
+            if (7 != sscanf(p, "%lld %x %d %lld %x %d %d", &start, &cflags, &origNum, &projStart, &projRC, &nameLen, &cigarLen)) {
+                err = "Genome contig line unparsable"; return false;
+            }
+            // name starts after the 7th space
+            const char *q = p; int spaces = 0;
+            while (q < nl && spaces < 7) { if (*q == ' ') spaces++; q++; }
+            ix.contigStart.push_back(start);
+            ix.contigIsAlt.push_back((cflags & 1) ? 1 : 0);
+            ix.contigName.push_back(std::string(q, (size_t)nameLen));
+            p = nl + 1;
+        }
+        if ((long long)(endp - p) != nBases) { err = "Genome: base count does not match file size"; return false; }
+        ix.basesPadded.assign((size_t)nBases + 2 * SG_N_PADDING, (uint8_t)'n');
+        memcpy(ix.basesPadded.data() + SG_N_PADDING, p, (size_t)nBases);
+        // genomeLocationOfFirstALTContig, Genome.cpp:460-476
+        ix.altFirstLocation = LLONG_MAX;
+        for (size_t i = 0; i < ix.contigStart.size(); i++)
+            if (ix.contigIsAlt[i] && ix.contigStart[i] < ix.altFirstLocation) ix.altFirstLocation = ix.contigStart[i];
+    }
+
+    // --- OverflowTable: raw u32[]
+    if (!sg_read_file(dir + "/OverflowTable", buf, err)) return false;
+    if (buf.size() != ix.overflowSize * 4) { err = "OverflowTable size mismatch"; return false; }
+    ix.overflow.assign((size_t)ix.overflowSize + 1, 0);
+    if (!buf.empty()) memcpy(ix.overflow.data(), buf.data(), buf.size());
+
+    // --- GenomeIndexHash: per table {u32 magic, u64 tableSize, u64 used, u32 keySize, u32 valueSize, u32 valueCount, valueSize bytes invalid} + data
+    if (!sg_read_file(dir + "/GenomeIndexHash", buf, err)) return false;
+    if ((long long)buf.size() != hashTablesFileSize) { err = "GenomeIndexHash has unexpected size"; return false; }
+    const uint32_t valueCount = ix.large ? 2 : 1;
+    ix.entryBytes = 4 * valueCount + ix.keyBytes;
+    ix.tableStart.assign(nHashTables, 0); ix.tableSize.assign(nHashTables, 0);
+    // first pass: sizes
+    {
+        size_t off = 0; uint64_t slots = 0;
+        for (unsigned t = 0; t < nHashTables; t++) {
+            if (off + 36 > buf.size()) { err = "GenomeIndexHash truncated"; return false; }
+            uint32_t magic, ks, vs, vc, inval; uint64_t tsz, used;
+            memcpy(&magic, &buf[off], 4); memcpy(&tsz, &buf[off + 4], 8); memcpy(&used, &buf[off + 12], 8);
+            memcpy(&ks, &buf[off + 20], 4); memcpy(&vs, &buf[off + 24], 4); memcpy(&vc, &buf[off + 28], 4);
+            if (magic != 0xb111b010u) { err = "hash table magic mismatch"; return false; }      // HashTable.cpp:343
+            if (vs != 4 || vc != valueCount || ks != ix.keyBytes) { err = "hash table key/value geometry unsupported"; return false; }
+            memcpy(&inval, &buf[off + 32], 4);
+            ix.invalidValue = inval;
+            ix.tableStart[t] = slots; ix.tableSize[t] = tsz;
+            slots += tsz;
+            off += 36 + (size_t)tsz * ix.entryBytes;
+        }
+        if (off != buf.size()) { err = "GenomeIndexHash has trailing bytes"; return false; }
+        ix.totalSlots = slots;
+    }
+    ix.tables.assign((size_t)ix.totalSlots * ix.entryBytes + 16, 0);
+    {
+        size_t off = 0;
+        for (unsigned t = 0; t < nHashTables; t++) {
+            off += 36;
+            size_t bytes = (size_t)ix.tableSize[t] * ix.entryBytes;
+            memcpy(ix.tables.data() + (size_t)ix.tableStart[t] * ix.entryBytes, &buf[off], bytes);
+            off += bytes;
+        }
+    }
+    return true;
+}
+
+// ---- probability tables (reference LandauVishkin.cpp:715-763), MAPQ thresholds (mapq.h:54), wrap table ----
+
+// SeedSequencer::SeedSequencer (reference SeedSequencer.cpp:36-103): breadth-first midpoint order; the table is
+// indexed by position and stores the fill order, and is *read* as offsets[wrapCount] (SeedSequencer.h:40-43).
+static inline void sg_seed_sequencer(unsigned seedSize, uint32_t *offsets)
+{
+    for (unsigned i = 0; i < seedSize; i++) offsets[i] = 0;
+    if (seedSize == 1) return;
+    struct Item { unsigned lo, hi; };
+    std::vector<Item> queue;
+    size_t head = 0;
+    unsigned nFilled = 1;
+    Item first; first.lo = 1; first.hi = seedSize - 1;
+    queue.push_back(first);
+    while (head < queue.size()) {
+        Item it = queue[head++];
+        unsigned sel = (it.lo + it.hi) / 2;
+        offsets[sel] = nFilled++;
+        if (it.hi > sel) { Item up; up.lo = sel + 1; up.hi = it.hi; queue.push_back(up); }
+        if (it.lo < sel) { Item lowItem; lowItem.lo = it.lo; lowItem.hi = sel - 1; queue.push_back(lowItem); }
+    }
+}
+
+static inline int sg_mapq_of_x(double x) { return (int)(-10 * log10(x)); }
+
+static inline void sg_init_tables(SgTables &T, unsigned seedLen)
+{
+    const double SNP_PROB = 0.001, GAP_OPEN_PROB = 0.001, GAP_EXTEND_PROB = 0.5;      // BaseAligner.h:368-370
+    T.indel[0] = 1.0;
+    T.indel[1] = GAP_OPEN_PROB;
+    for (int i = 2; i < SG_MAX_INDEL_TABLE; i++) T.indel[i] = T.indel[i - 1] * GAP_EXTEND_PROB;
+    const double mutationRate = SNP_PROB;
+    for (int i = 0; i < 33; i++) T.phred[i] = mutationRate;
+    for (int i = 33; i <= 93 + 33; i++) T.phred[i] = 1.0 - (1.0 - pow(10.0, -1.0 * (i - 33.0) / 10.0)) * (1.0 - mutationRate);
+    for (int i = 93 + 33 + 1; i < 256; i++) T.phred[i] = mutationRate;
+    T.perfect[0] = 1.0;
+    for (int i = 1; i < SG_MAX_PERFECT_TABLE; i++) T.perfect[i] = T.perfect[i - 1] * (1 - SNP_PROB);
+    // BaseAligner.cpp:1314 `pow(1 - SNP_PROB, seedLen)` with an int exponent: the reference is built as C++98, where that
+    // resolves to std::pow(double,int) = __builtin_powi, i.e. libgcc's square-and-multiply __powidf2 (NOT libm pow).
+    {
+        double x = 1 - SNP_PROB; unsigned n = seedLen;
+        double y = (n % 2) ? x : 1;
+        while (n >>= 1) { x = x * x; if (n % 2) y *= x; }
+        T.snpPowSeedLen = y;
+    }
+    // mapqThreshold[m]: the largest double x in (0,1] with (int)(-10*log10(x)) >= m, by bisection on the bit pattern
+    // (positive doubles order like their bit patterns; glibc log10 is monotone).
+    T.mapqThreshold[0] = 1.0;
+    for (int m = 1; m <= 71; m++) {
+        uint64_t lo, hi; double dlo = 4.9406564584124654e-324, dhi = 1.0;
+        memcpy(&lo, &dlo, 8); memcpy(&hi, &dhi, 8);
+        // invariant: f(lo) >= m, f(hi) < m  (f(1.0) = 0 < m)
+        while (hi - lo > 1) {
+            uint64_t mid = lo + (hi - lo) / 2; double dm; memcpy(&dm, &mid, 8);
+            if (sg_mapq_of_x(dm) >= m) lo = mid; else hi = mid;
+        }
+        memcpy(&T.mapqThreshold[m], &lo, 8);
+    }
+    uint32_t offs[33];
+    memset(offs, 0, sizeof(offs));
+    sg_seed_sequencer(seedLen, offs);
+    for (unsigned i = 0; i < 33; i++) T.wrapSeed[i] = (i < seedLen) ? offs[i] : 0;
+}
+
+static inline uint32_t sg_next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
+
+// snapgpu_params -> SgParams, with the constructor-time derivations of BaseAligner::BaseAligner (BaseAligner.cpp:173-183).
+static inline bool sg_derive_params(const snapgpu_params &in, unsigned seedLen, uint32_t maxReadLen, SgParams &p, std::string &err)
+{
+    if (in.struct_size != sizeof(snapgpu_params)) { err = "snapgpu_params.struct_size mismatch (ABI)"; return false; }
+    if (in.maxSecondaryAlignmentAdditionalEditDistance != -1) { err = "secondary alignments (-om) are not supported"; return false; }
+    if (!in.ignoreAlignmentAdjustmentsForOm) { err = "alignment adjustment (-ae) is not supported"; return false; }
+    if ((unsigned)in.subPenalty > (unsigned)(in.gapOpenPenalty + in.gapExtendPenalty)) {
+        err = "subPenalty must be < gapOpen + gapExtend"; return false;                    // BaseAligner.cpp:141-144
+    }
+    if (in.maxDist > SG_MAX_K - 1) { err = "maxDist must be < MAX_K"; return false; }
+    if (maxReadLen > SNAPGPU_MAX_READ_LENGTH) { err = "maxReadLen exceeds MAX_READ_LENGTH"; return false; }
+    memset(&p, 0, sizeof(p));
+    p.maxHits = in.maxHits; p.maxK = in.maxDist; p.numSeedsFromCommandLine = in.numSeedsFromCommandLine;
+    p.seedCoverage = in.seedCoverage;
+    p.minWeightToCheck = in.minWeightToCheck > 1 ? in.minWeightToCheck : 1;                 // max(1u, ...)
+    p.extraSearchDepth = in.extraSearchDepth; p.minReadLength = in.minReadLength;
+    p.useAffineGap = in.useAffineGap; p.matchReward = in.matchReward; p.subPenalty = in.subPenalty;
+    p.gapOpenPenalty = in.gapOpenPenalty; p.gapExtendPenalty = in.gapExtendPenalty;
+    p.fivePrimeEndBonus = in.fivePrimeEndBonus; p.threePrimeEndBonus = in.threePrimeEndBonus;
+    p.noUkkonen = in.noUkkonen; p.noOrderedEvaluation = in.noOrderedEvaluation; p.noTruncation = in.noTruncation;
+    p.noEditDistance = in.noEditDistance; p.noBandedAffineGap = in.noBandedAffineGap;
+    p.altAwareness = in.altAwareness; p.maxScoreGapToPreferNonAltAlignment = in.maxScoreGapToPreferNonAltAlignment;
+    p.explorePopularSeeds = in.explorePopularSeeds; p.stopOnFirstHit = in.stopOnFirstHit;
+    unsigned maxSeedsToUse;
+    if (0 != in.numSeedsFromCommandLine) maxSeedsToUse = in.numSeedsFromCommandLine;
+    else maxSeedsToUse = (unsigned)(int)(in.seedCoverage * SNAPGPU_MAX_READ_LENGTH / (int)seedLen);
+    if (maxSeedsToUse == 0) { err = "no seeds to use"; return false; }
+    p.numWeightLists = maxSeedsToUse + 1;
+    uint64_t pool = (uint64_t)in.maxHits * maxSeedsToUse * 2;
+    if (pool > (1u << 24)) { err = "maxHits*maxSeeds too large"; return false; }
+    p.poolSize = (uint32_t)pool;
+    p.tableSlots = sg_next_pow2(p.poolSize * 2 + 16);
+    p.maxReadLen = maxReadLen;
+    return true;
+}

@@ -1,0 +1,181 @@
+// sg_lv.h -- Landau-Vishkin bounded-k edit distance with match-probability backtrace.  Scalar form, host+device.
+// Restates LandauVishkin<TEXT_DIRECTION>::computeEditDistance (reference SNAPLib/LandauVishkin.h:100-351)
+// including its d visiting order (0,1,-1,2,-2,...), strict '>' tie-breaks, 'X'-finish preference and the
+// order of the floating-point multiplies.
+#pragma once
+#include "sg_common.h"
+
+struct SgLvResult {
+    int score;            // edit distance or SG_SCORE_ABOVE_LIMIT
+    int netIndel;         // o_netIndel
+    int totalIndels;
+    int textSpan;
+    double matchProbability;
+};
+
+// L(e,d) storage: row e holds d in [-e, e]; cells outside were never written in the reference and hold -2
+// (LandauVishkin.h:55), which we return analytically.
+struct SgLvState {
+    int16_t *L; uint8_t *A; int stride; int kmax;
+    SG_HD int getL(int e, int d) const { return (d < -e || d > e) ? -2 : (int)L[e * stride + d + kmax]; }
+    SG_HD void setL(int e, int d, int v) { L[e * stride + d + kmax] = (int16_t)v; }
+    SG_HD uint8_t getA(int e, int d) const { return A[e * stride + d + kmax]; }
+    SG_HD void setA(int e, int d, uint8_t v) { A[e * stride + d + kmax] = v; }
+};
+
+// countPerfectMatch (LandauVishkin.h:377-407): number of equal leading characters of pattern[pi..] and the text
+// read in direction dir starting at text index ti, clamped to availBytes (which may be <= 0: the reference then
+// returns availBytes itself because the first characters were already known equal).
+SG_HD int sg_lv_cpm(const uint8_t *pattern, int pi, const uint8_t *text, int ti, int dir, int availBytes)
+{
+    if (availBytes <= 0) return availBytes;
+    int n = 0;
+    while (n < availBytes && pattern[pi + n] == text[(ti + n) * dir]) n++;
+    return n;
+}
+
+// text: as the reference's callers pass it (for dir == -1: one past the first text character).
+SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const uint8_t *text, int textLen,
+                          const uint8_t *pattern, const uint8_t *quality, int patternLen, int k, SgLvResult *out)
+{
+    out->netIndel = 0; out->totalIndels = 0; out->textSpan = 0; out->matchProbability = 0.0;
+    if (k < 0) { out->score = SG_SCORE_ABOVE_LIMIT; return; }
+    if (k > SG_MAX_K - 1) k = SG_MAX_K - 1;
+    if (text == (const uint8_t *)0) { out->matchProbability = 0.0; out->score = SG_SCORE_ABOVE_LIMIT; return; }
+    out->matchProbability = 1.0;
+    if (dir == -1) text--;
+
+    SgLvState st;
+    st.L = S.lvL; st.A = S.lvA; st.kmax = k; st.stride = 2 * k + 1;
+
+    int end = patternLen < textLen ? patternLen : textLen;
+    int L00 = 0;
+    while (L00 < end && pattern[L00] == text[L00 * dir]) L00++;      // countPerfectMatch(p, t, end) with end >= 0
+    st.setL(0, 0, L00);
+
+    if (L00 == end) {
+        int result = (patternLen > end ? patternLen - end : 0);
+        out->matchProbability = T.perfect[patternLen];
+        if (result > k) { out->score = SG_SCORE_ABOVE_LIMIT; return; }
+        out->textSpan += patternLen;
+        out->score = result;
+        return;
+    }
+
+    int lastBestD = SG_MAX_K + 1;
+    int e;
+    bool gotAnswer = false;
+    for (e = 1; e <= k; e++) {
+        // d = 0, 1, -1, 2, -2, ..., e, -e
+        int d = 0;
+        for (int i = 0; d != e + 1; i++, d = (d > 0 ? -d : -d + 1)) {
+            int endd = patternLen < textLen - d ? patternLen : textLen - d;
+            int best = st.getL(e - 1, d) + 1;                          // up
+            uint8_t a = 'X';
+            if (best >= 0 && best < patternLen + 1) {
+                // the reference compares *p == *t even at best == patternLen (then extends by min(.., 0) = 0)
+                if (endd - best > 0) {
+                    if (pattern[best] == text[(d + best) * dir]) best += sg_lv_cpm(pattern, best, text, d + best, dir, endd - best);
+                } else if (endd - best < 0) {
+                    if (pattern[best] == text[(d + best) * dir]) best += endd - best;
+                }
+            }
+            int left = st.getL(e - 1, d - 1);
+            if (left >= 0) {
+                if (endd - left > 0) {
+                    if (pattern[left] == text[(d + left) * dir]) left += sg_lv_cpm(pattern, left, text, d + left, dir, endd - left);
+                } else if (endd - left < 0) {
+                    if (pattern[left] == text[(d + left) * dir]) left += endd - left;
+                }
+            }
+            if (left > best) { best = left; a = 'D'; }
+            int right = st.getL(e - 1, d + 1) + 1;
+            if (right >= 0) {
+                if (endd - right > 0) {
+                    if (pattern[right] == text[(d + right) * dir]) right += sg_lv_cpm(pattern, right, text, d + right, dir, endd - right);
+                } else if (endd - right < 0) {
+                    if (pattern[right] == text[(d + right) * dir]) right += endd - right;
+                }
+            }
+            if (right > best) { best = right; a = 'I'; }
+            st.setA(e, d, a);
+
+            if (best == patternLen) {
+                if (a == 'X') {
+                    lastBestD = d;
+                    gotAnswer = true;      // goto got_answer: L(e,d) is NOT written on this path
+                    break;
+                } else {
+                    int ad = d < 0 ? -d : d, al = lastBestD < 0 ? -lastBestD : lastBestD;
+                    if (ad < al) lastBestD = d;
+                }
+            }
+            st.setL(e, d, best);
+        }
+        if (gotAnswer) break;
+        if (SG_MAX_K + 1 != lastBestD) break;
+    }
+
+    if (SG_MAX_K + 1 == lastBestD) { out->score = SG_SCORE_ABOVE_LIMIT; return; }
+    // note: when the e-loop ran to completion without an answer e == k+1 and we returned above
+
+    // Backtrace (LandauVishkin.h:286-304).  On the 'X' finish path L(e, lastBestD) was not written: the reference
+    // then reads a stale cell into backtraceMatched[e], which only feeds `offset` after its last use.  We use 0.
+    int16_t *btMatched = S.lvBtMatched; int16_t *btD = S.lvBtD; uint8_t *btAction = S.lvBtAction;
+    int curD = lastBestD;
+    for (int curE = e; curE >= 1; curE--) {
+        uint8_t a = st.getA(curE, curD);
+        btAction[curE] = a;
+        int Lcur = (gotAnswer && curE == e) ? 0 : st.getL(curE, curD);
+        if (a == 'I') {
+            btD[curE] = (int16_t)(curD + 1);
+            btMatched[curE] = (int16_t)(Lcur - st.getL(curE - 1, curD + 1) - 1);
+        } else if (a == 'D') {
+            btD[curE] = (int16_t)(curD - 1);
+            btMatched[curE] = (int16_t)(Lcur - st.getL(curE - 1, curD - 1));
+        } else {
+            btD[curE] = (int16_t)curD;
+            btMatched[curE] = (int16_t)(Lcur - st.getL(curE - 1, curD) - 1);
+        }
+        curD = btD[curE];
+    }
+
+    double mp = 1.0;
+    int curE = 1;
+    int offset = L00;
+    int netIndel = 0, totalIndels = 0, textSpan = 0;
+    while (curE <= e) {
+        uint8_t action = btAction[curE];
+        int actionCount = 1;
+        while (curE + 1 <= e && btMatched[curE] == 0 && btAction[curE + 1] == action) {
+            actionCount++;
+            curE++;
+        }
+        if (action == 'I') {
+            mp *= T.indel[actionCount];
+            offset += actionCount;
+            netIndel += actionCount;
+            totalIndels += actionCount;
+        } else if (action == 'D') {
+            mp *= T.indel[actionCount];
+            offset -= actionCount;
+            netIndel -= actionCount;
+            totalIndels += actionCount;
+            textSpan += actionCount;
+        } else {
+            for (int i = 0; i < actionCount; i++) {
+                int qi = offset > 0 ? offset : 0;
+                if (qi > patternLen - 1) qi = patternLen - 1;
+                mp *= T.phred[quality[qi]];
+                offset++;
+            }
+        }
+        offset += btMatched[curE];
+        curE++;
+    }
+    mp *= T.perfect[patternLen - e];
+    textSpan += patternLen;
+    out->matchProbability = mp;
+    out->netIndel = netIndel; out->totalIndels = totalIndels; out->textSpan = textSpan;
+    out->score = e;
+}

@@ -1,0 +1,188 @@
+"""Deterministic synthetic references and reads (SURVEY.md 8d "Synthetic inputs").
+
+CPU/numpy generator used by the tests, the golden-fixture script and the small bench configs.
+Reference: uniform i.i.d. ACGT contigs.  Reads: uniform start, 50% reverse-complemented, per-base
+substitution / insertion / deletion, qualities uniform Phred 20-40 ('5'..'I'), optional N runs and
+'#'-quality tails (the reader would clip those: FASTQ.cpp:294, Read.h:567-619 -- we emit the clipped view).
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+_COMP[:] = ord("N")
+for a, b in zip(b"ACGTN", b"TGCAN"):
+    _COMP[a] = b
+
+
+def revcomp(a: np.ndarray) -> np.ndarray:
+    return _COMP[a[::-1]]
+
+
+def make_contigs(n_contigs: int, contig_len: int, seed: int, repeat_frac: float = 0.0) -> list[np.ndarray]:
+    """Uniform random contigs; with repeat_frac>0, that fraction of bases comes from a small repeat
+    library at 0-5% divergence (exercises overflow lists / popular seeds / merge logic)."""
+    rng = np.random.default_rng(seed)
+    contigs = []
+    lib = None
+    if repeat_frac > 0:
+        lib = [ACGT[rng.integers(0, 4, size=int(rng.integers(200, 2000)))] for _ in range(8)]
+    for _ in range(n_contigs):
+        c = ACGT[rng.integers(0, 4, size=contig_len)]
+        if lib is not None:
+            placed = 0
+            while placed < repeat_frac * contig_len:
+                unit = lib[int(rng.integers(0, len(lib)))].copy()
+                div = rng.random() * 0.05
+                mut = rng.random(unit.size) < div
+                unit[mut] = ACGT[rng.integers(0, 4, size=int(mut.sum()))]
+                pos = int(rng.integers(0, max(1, contig_len - unit.size)))
+                n = min(unit.size, contig_len - pos)
+                c[pos:pos + n] = unit[:n]
+                placed += n
+        contigs.append(c)
+    return contigs
+
+
+def write_fasta(path: str, contigs: list[np.ndarray], width: int = 100) -> None:
+    with open(path, "wb") as f:
+        for i, c in enumerate(contigs):
+            f.write(b">chr%d\n" % (i + 1))
+            n = c.size
+            full = (n // width) * width
+            if full:
+                body = c[:full].reshape(-1, width)
+                out = np.empty((body.shape[0], width + 1), dtype=np.uint8)
+                out[:, :width] = body
+                out[:, width] = ord("\n")
+                f.write(out.tobytes())
+            if n > full:
+                f.write(c[full:].tobytes() + b"\n")
+
+
+class ReadBatch:
+    """Concatenated reads in the layout the C ABI takes (include/snapgpu.h snapgpu_align_single)."""
+
+    def __init__(self, bases: np.ndarray, quals: np.ndarray, offsets: np.ndarray, lens: np.ndarray,
+                 truth_contig=None, truth_pos=None, truth_rc=None):
+        self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        self.quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        self.truth_contig = truth_contig
+        self.truth_pos = truth_pos
+        self.truth_rc = truth_rc
+
+    @property
+    def n(self) -> int:
+        return int(self.lens.size)
+
+    def read(self, i: int) -> tuple[bytes, bytes]:
+        o, l = int(self.offsets[i]), int(self.lens[i])
+        return self.bases[o:o + l].tobytes(), self.quals[o:o + l].tobytes()
+
+    def slice(self, lo: int, hi: int) -> "ReadBatch":
+        o0 = int(self.offsets[lo])
+        o1 = int(self.offsets[hi - 1]) + int(self.lens[hi - 1]) if hi > lo else o0
+        return ReadBatch(self.bases[o0:o1], self.quals[o0:o1], self.offsets[lo:hi] - np.uint64(o0), self.lens[lo:hi])
+
+    def write_fastq(self, path: str) -> None:
+        with open(path, "wb") as f:
+            for i in range(self.n):
+                b, q = self.read(i)
+                f.write(b"@r%d\n%s\n+\n%s\n" % (i, b, q))
+
+    @staticmethod
+    def from_lists(reads: list[tuple[bytes, bytes]]) -> "ReadBatch":
+        lens = np.array([len(b) for b, _ in reads], dtype=np.uint32)
+        offsets = np.zeros(len(reads), dtype=np.uint64)
+        if len(reads) > 1:
+            offsets[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        bases = np.frombuffer(b"".join(b for b, _ in reads), dtype=np.uint8)
+        quals = np.frombuffer(b"".join(q for _, q in reads), dtype=np.uint8)
+        return ReadBatch(bases, quals, offsets, lens)
+
+
+def make_reads(contigs: list[np.ndarray], n: int, read_len: int, seed: int, sub_rate: float = 0.01,
+               ins_rate: float = 0.0005, del_rate: float = 0.0005, rc_frac: float = 0.5,
+               n_run_frac: float = 0.0, short_frac: float = 0.0, random_frac: float = 0.0) -> ReadBatch:
+    """n reads of read_len bases.  n_run_frac: fraction of reads given a run of 1-12 'N's;
+    short_frac: fraction emitted at a shorter length (as if '#'-clipped); random_frac: fraction of
+    reads that are pure noise (unalignable)."""
+    rng = np.random.default_rng(seed)
+    nc = len(contigs)
+    clen = np.array([c.size for c in contigs])
+    margin = read_len + 64
+    reads = []
+    t_contig = np.zeros(n, dtype=np.int32)
+    t_pos = np.zeros(n, dtype=np.int64)
+    t_rc = np.zeros(n, dtype=np.int8)
+    for i in range(n):
+        ci = int(rng.integers(0, nc))
+        pos = int(rng.integers(0, max(1, clen[ci] - margin)))
+        window = contigs[ci][pos:pos + margin]
+        if rng.random() < random_frac:
+            seq = ACGT[rng.integers(0, 4, size=read_len)]
+        else:
+            # walk the window applying edits until read_len bases are produced
+            r = rng.random(margin)
+            ops_sub = r < sub_rate
+            ops_ins = (r >= sub_rate) & (r < sub_rate + ins_rate)
+            ops_del = (r >= sub_rate + ins_rate) & (r < sub_rate + ins_rate + del_rate)
+            if not ops_ins.any() and not ops_del.any():
+                seq = window[:read_len].copy()
+                m = ops_sub[:read_len]
+                k = int(m.sum())
+                if k:
+                    seq[m] = ACGT[(np.searchsorted(ACGT, seq[m]) + rng.integers(1, 4, size=k)) % 4]
+            else:
+                out = []
+                j = 0
+                while len(out) < read_len and j < margin:
+                    if ops_del[j]:
+                        j += 1
+                        continue
+                    if ops_ins[j]:
+                        out.append(int(ACGT[rng.integers(0, 4)]))
+                        if len(out) >= read_len:
+                            break
+                    b = int(window[j])
+                    if ops_sub[j]:
+                        b = int(ACGT[(int(np.searchsorted(ACGT, b)) + int(rng.integers(1, 4))) % 4])
+                    out.append(b)
+                    j += 1
+                seq = np.array(out[:read_len], dtype=np.uint8)
+                if seq.size < read_len:
+                    seq = np.concatenate([seq, ACGT[rng.integers(0, 4, size=read_len - seq.size)]])
+        rc = rng.random() < rc_frac
+        if rc:
+            seq = revcomp(seq)
+        if rng.random() < n_run_frac:
+            run = int(rng.integers(1, 13))
+            at = int(rng.integers(0, read_len - run))
+            seq = seq.copy()
+            seq[at:at + run] = ord("N")
+        L = read_len
+        if rng.random() < short_frac:
+            L = int(rng.integers(20, read_len))
+        qual = rng.integers(20, 41, size=L).astype(np.uint8) + 33
+        reads.append((seq[:L].tobytes(), qual.tobytes()))
+        t_contig[i], t_pos[i], t_rc[i] = ci, pos, rc
+    rb = ReadBatch.from_lists(reads)
+    rb.truth_contig, rb.truth_pos, rb.truth_rc = t_contig, t_pos, t_rc
+    return rb
+
+
+def build_reference_index(snap_aligner: str, fasta: str, out_dir: str, seed_len: int = 20, large: bool = False,
+                          threads: int = 8) -> None:
+    """Runs the stock reference CLI `snap-aligner index` (oracle/_ref/snap-aligner). Test infrastructure only."""
+    import subprocess
+    os.makedirs(out_dir, exist_ok=True)
+    cmd = [snap_aligner, "index", fasta, out_dir, "-s", str(seed_len), "-t%d" % threads]
+    if large:
+        cmd.append("-large")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0 or not os.path.exists(os.path.join(out_dir, "GenomeIndexHash")):
+        raise RuntimeError("snap-aligner index failed:\n" + res.stdout)

@@ -1,0 +1,187 @@
+// hostsim.cpp -- TEST-ONLY host build of the engine's scalar algorithm headers (snap_b200/csrc/sg_*.h).
+//
+// The same headers are what the CUDA kernels compile; building them with g++ lets the CPU-side test suite
+// (`-m "not gpu"`) diff the restated state machine, LV and affine-gap code against the compiled reference
+// without a GPU.  This library is built into tests/_build/ and is never loaded by the snap_b200 package:
+// the product path has no CPU fallback.
+#include <string>
+#include <vector>
+#include <string.h>
+#include "../../snap_b200/csrc/sg_host.h"
+#include "../../snap_b200/csrc/sg_align.h"
+
+struct HsIndex {
+    SgHostIndex host;
+    SgIndexView view;
+};
+
+struct HsAligner {
+    HsIndex *index;
+    SgParams params;
+    SgTables tables;
+    std::vector<uint8_t> scratch;
+    SgAligner A;
+};
+
+static std::string g_err;
+
+extern "C" {
+
+const char *hs_last_error(void) { return g_err.c_str(); }
+
+void *hs_index_open(const char *dir)
+{
+    HsIndex *ix = new HsIndex;
+    if (!sg_load_index_directory(dir, ix->host, g_err)) { delete ix; return NULL; }
+    ix->view = ix->host.view();
+    return ix;
+}
+
+void hs_index_close(void *v) { delete (HsIndex *)v; }
+
+int hs_index_info(void *v, snapgpu_index_info *info)
+{
+    HsIndex *ix = (HsIndex *)v;
+    memset(info, 0, sizeof(*info));
+    info->countOfBases = ix->host.nBases; info->seedLen = ix->host.seedLen; info->hashTableKeySize = ix->host.keyBytes;
+    info->nHashTables = ix->host.nTables; info->locationSize = 4; info->largeHashTable = ix->host.large;
+    info->chromosomePadding = ix->host.chromosomePadding; info->nContigs = (uint32_t)ix->host.contigStart.size();
+    info->overflowTableSize = ix->host.overflowSize; info->hashTableSlots = ix->host.totalSlots;
+    return 0;
+}
+
+int hs_lookup_seeds(void *v, const char *seeds, int64_t nSeeds, uint32_t maxHitsPerSeed, int64_t *nHits, uint32_t *hits, uint32_t *probes)
+{
+    HsIndex *ix = (HsIndex *)v;
+    const uint32_t sl = ix->host.seedLen;
+    for (int64_t i = 0; i < nSeeds; i++) {
+        uint64_t b, rc;
+        nHits[2 * i] = nHits[2 * i + 1] = 0;
+        uint32_t examined = 0, ow = 0;
+        if (sg_seed_pack((const uint8_t *)seeds + i * sl, sl, &b, &rc)) {
+            SgHits h;
+            sg_lookup_seed32(ix->view, b, rc, &h, &examined, &ow);
+            for (int d = 0; d < 2; d++) {
+                nHits[2 * i + d] = h.nHits[d];
+                for (uint32_t k = 0; k < h.nHits[d] && k < maxHitsPerSeed; k++) hits[(2 * i + d) * (int64_t)maxHitsPerSeed + k] = h.hits[d][k];
+            }
+        }
+        if (probes) probes[i] = examined;
+    }
+    return 0;
+}
+
+void hs_tables(unsigned seedLen, double *phred, double *indel, int nIndel, double *perfect, int nPerfect, double *mapqThr, uint32_t *wrap)
+{
+    SgTables T;
+    sg_init_tables(T, seedLen);
+    memcpy(phred, T.phred, sizeof(T.phred));
+    for (int i = 0; i < nIndel; i++) indel[i] = T.indel[i];
+    for (int i = 0; i < nPerfect; i++) perfect[i] = T.perfect[i];
+    memcpy(mapqThr, T.mapqThreshold, sizeof(T.mapqThreshold));
+    memcpy(wrap, T.wrapSeed, sizeof(T.wrapSeed));
+}
+
+int hs_mapq(double pAll, double pBest, int popularSeedsSkipped)
+{
+    static SgTables T; static bool init = false;
+    if (!init) { sg_init_tables(T, 20); init = true; }
+    return sg_compute_mapq(T, pAll, pBest, popularSeedsSkipped);
+}
+
+static void make_scratch(const SgParams &p, std::vector<uint8_t> &mem, SgScratch *s)
+{
+    mem.assign(sg_scratch_bytes(p) + 256, 0);
+    uint8_t *base = (uint8_t *)(((uintptr_t)mem.data() + 255) & ~(uintptr_t)255);
+    sg_scratch_carve(p, base, s);
+}
+
+void hs_lv_batch(const char *textBuf, const char *patBuf, const char *qualBuf, const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out)
+{
+    SgTables T; sg_init_tables(T, 20);
+    SgParams p; memset(&p, 0, sizeof(p));
+    p.poolSize = 1; p.tableSlots = 2; p.numWeightLists = 2; p.maxReadLen = 1000;
+    std::vector<uint8_t> mem; SgScratch s; make_scratch(p, mem, &s);
+    for (int64_t j = 0; j < nJobs; j++) {
+        SgLvResult r;
+        sg_lv_compute(T, s, jobs[j].dir, (const uint8_t *)textBuf + jobs[j].textOff, jobs[j].textLen, (const uint8_t *)patBuf + jobs[j].patOff,
+                      (const uint8_t *)qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].k, &r);
+        out[j].score = r.score; out[j].netIndel = r.netIndel; out[j].totalIndels = r.totalIndels; out[j].textSpan = r.textSpan;
+        out[j].matchProbability = r.matchProbability;
+    }
+}
+
+void hs_ag_batch(const snapgpu_ag_params *ap, const char *textBuf, const char *patBuf, const char *qualBuf, const snapgpu_ag_job *jobs,
+                 int64_t nJobs, snapgpu_ag_out *out)
+{
+    SgTables T; sg_init_tables(T, 20);
+    SgParams p; memset(&p, 0, sizeof(p));
+    p.poolSize = 1; p.tableSlots = 2; p.numWeightLists = 2; p.maxReadLen = 1000;
+    std::vector<uint8_t> mem; SgScratch s; make_scratch(p, mem, &s);
+    SgAgParams P = sg_ag_params(ap->matchReward, ap->subPenalty, ap->gapOpenPenalty, ap->gapExtendPenalty, ap->fivePrimeEndBonus, ap->threePrimeEndBonus);
+    for (int64_t j = 0; j < nJobs; j++) {
+        SgAgResult r;
+        sg_ag_compute(T, s, P, jobs[j].dir, jobs[j].banded != 0, (const uint8_t *)textBuf + jobs[j].textOff, jobs[j].textLen,
+                      (const uint8_t *)patBuf + jobs[j].patOff, (const uint8_t *)qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].w,
+                      jobs[j].scoreInit, jobs[j].isRC != 0, jobs[j].useClippingOptimizations != 0, &r);
+        out[j].agScore = r.agScore; out[j].textOffset = r.textOffset; out[j].patternOffset = r.patternOffset; out[j].nEdits = r.nEdits;
+        out[j].matchProbability = r.matchProbability;
+    }
+}
+
+void *hs_aligner_create(void *vix, const snapgpu_params *params, uint32_t maxReadLen)
+{
+    HsIndex *ix = (HsIndex *)vix;
+    HsAligner *a = new HsAligner;
+    a->index = ix;
+    if (!sg_derive_params(*params, ix->host.seedLen, maxReadLen, a->params, g_err)) { delete a; return NULL; }
+    sg_init_tables(a->tables, ix->host.seedLen);
+    memset(&a->A, 0, sizeof(a->A));
+    make_scratch(a->params, a->scratch, &a->A.sc);
+    a->A.ix = &ix->view; a->A.pr = &a->params; a->A.tb = &a->tables;
+    a->A.ag = sg_ag_params(params->matchReward, params->subPenalty, params->gapOpenPenalty, params->gapExtendPenalty,
+                           params->fivePrimeEndBonus, params->threePrimeEndBonus);
+    a->A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    a->A.nUsedElements = 0;
+    return a;
+}
+
+void hs_aligner_destroy(void *v) { delete (HsAligner *)v; }
+
+// Same contract as snapgpu_align_single: pre-filter (SingleAligner.cpp:213), AlignRead, stats.
+int hs_align_single(void *v, int64_t n, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
+                    snapgpu_single_result *results, snapgpu_counters *ctr)
+{
+    HsAligner *a = (HsAligner *)v;
+    memset(&a->A.work, 0, sizeof(a->A.work));
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *rd = (const uint8_t *)bases + offsets[i];
+        const uint8_t *rq = (const uint8_t *)quals + offsets[i];
+        snapgpu_single_result *r = &results[i];
+        memset(r, 0, sizeof(*r));
+        if (lens[i] > a->params.maxReadLen) { g_err = "read longer than maxReadLen"; return 1; }
+        uint32_t countOfNs = 0;
+        for (uint32_t k = 0; k < lens[i]; k++) countOfNs += (rd[k] == 'N');
+        if (ctr) ctr->totalReads++;
+        if (lens[i] < a->params.minReadLength || countOfNs > a->params.maxK) {
+            r->status = SNAPGPU_NOT_FOUND; r->location = a->A.invalidLocation; r->mapq = 0; r->direction = SNAPGPU_FORWARD;
+            if (ctr) ctr->uselessReads++;
+            continue;
+        }
+        sg_align_read(a->A, rd, rq, lens[i], r);
+        if (ctr) {
+            if (r->status == SNAPGPU_SINGLE_HIT) ctr->singleHits++;
+            else if (r->status == SNAPGPU_MULTIPLE_HITS) ctr->multiHits++;
+            else ctr->notFound++;
+            if (r->status != SNAPGPU_NOT_FOUND && r->mapq >= 0 && r->mapq <= 70) ctr->mapqHistogram[r->mapq]++;
+        }
+    }
+    if (ctr) {
+        ctr->nHashTableLookups += a->A.work.lookups; ctr->nHashEntriesProbed += a->A.work.entriesProbed;
+        ctr->nOverflowWordsRead += a->A.work.overflowWords; ctr->lvCalls += a->A.work.lvCalls; ctr->affineGapCalls += a->A.work.agCalls;
+        ctr->nHitsIgnoredBecauseOfTooHighPopularity += a->A.work.popularIgnored;
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,111 @@
+"""ctypes binding of tests/_build/libhostsim.so: the TEST-ONLY g++ build of snap_b200/csrc/sg_*.h.
+
+Lets the CPU suite diff the engine's algorithm headers against the compiled reference without a GPU.
+Never imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "_build", "libhostsim.so")
+SRC = os.path.join(HERE, "hostsim", "hostsim.cpp")
+CSRC = os.path.join(ROOT, "snap_b200", "csrc")
+
+
+def build(force: bool = False) -> str:
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return SO
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, SRC]
+    subprocess.run(cmd, check=True)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.hs_last_error.restype = C.c_char_p
+        L.hs_index_open.restype = C.c_void_p
+        L.hs_index_open.argtypes = [C.c_char_p]
+        L.hs_index_close.argtypes = [C.c_void_p]
+        L.hs_lookup_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_tables.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hs_mapq.restype = C.c_int
+        L.hs_mapq.argtypes = [C.c_double, C.c_double, C.c_int]
+        L.hs_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+        L.hs_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.hs_aligner_create.restype = C.c_void_p
+        L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.hs_aligner_destroy.argtypes = [C.c_void_p]
+        L.hs_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HsIndex:
+    def __init__(self, directory: str):
+        self.handle = lib().hs_index_open(directory.encode())
+        if not self.handle:
+            raise RuntimeError(lib().hs_last_error().decode())
+
+    def lookup(self, seeds: np.ndarray, n: int, max_hits: int = 512):
+        nh = np.zeros(2 * n, dtype=np.int64)
+        hits = np.zeros(2 * n * max_hits, dtype=np.uint32)
+        probes = np.zeros(n, dtype=np.uint32)
+        lib().hs_lookup_seeds(self.handle, _p(seeds), n, max_hits, _p(nh), _p(hits), _p(probes))
+        return nh.reshape(n, 2), hits.reshape(n, 2, max_hits), probes
+
+
+class HsAligner:
+    def __init__(self, index: HsIndex, params, max_read_len: int = 400):
+        import ctypes
+        self.index = index
+        self.handle = lib().hs_aligner_create(index.handle, ctypes.byref(params), max_read_len)
+        if not self.handle:
+            raise RuntimeError(lib().hs_last_error().decode())
+
+    def align(self, batch, result_dtype, n_counters):
+        res = np.zeros(batch.n, dtype=result_dtype)
+        ctr = np.zeros(n_counters, dtype=np.int64)
+        rc = lib().hs_align_single(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(res), _p(ctr))
+        if rc != 0:
+            raise RuntimeError(lib().hs_last_error().decode())
+        return res, ctr
+
+
+def tables(seed_len=20, n_indel=1200, n_perfect=1001):
+    phred = np.zeros(256)
+    indel = np.zeros(n_indel)
+    perfect = np.zeros(n_perfect)
+    thr = np.zeros(72)
+    wrap = np.zeros(33, dtype=np.uint32)
+    lib().hs_tables(seed_len, _p(phred), _p(indel), n_indel, _p(perfect), n_perfect, _p(thr), _p(wrap))
+    return phred, indel, perfect, thr, wrap
+
+
+def lv_batch(text, pat, qual, jobs, out_dtype):
+    out = np.zeros(jobs.size, dtype=out_dtype)
+    lib().hs_lv_batch(_p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))
+    return out
+
+
+def ag_batch(text, pat, qual, jobs, out_dtype, params):
+    out = np.zeros(jobs.size, dtype=out_dtype)
+    params = np.ascontiguousarray(params, dtype=np.int32)
+    lib().hs_ag_batch(_p(params), _p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))
+    return out
