@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on the reference's headline workload (BASELINE.json):
+aligned reads/s for `snap single`, 150 bp synthetic reads vs a 3 Gbp hg-sized synthetic reference, seed 20,
+maxDist 14 (configs[1]), read-sharded over N GPUs.
+
+A "step" is one pass of the hot path (seed lookup + LV / affine-gap scoring, BaseAligner::AlignRead semantics) over
+one batch of synthetic reads.  `value` = reads of all ranks per second with the inputs already resident in HBM,
+timed with CUDA events around exactly K steps (max over ranks).  `e2e` = the same metric through the C ABI call a
+SNAP extension makes (snapgpu_align_single) with HOST buffers: host->device copies of the reads and device->host
+copy of the results inside the timed region.  `roofline` is for the dominant kernel (sg_align_kernel);
+`seed_phase` is the seed-lookup kernel run in isolation over every seed of the batch (BASELINE's second metric).
+`cpu_baseline` / `--impl reference` time the UNMODIFIED reference (oracle/_ref, compiled from /root/reference) on the
+host cores, on a bounded sample of the same workload, against the same index written out in the reference's own
+directory format.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN = 150
+SEED_LEN = 20
+MAX_DIST = 14
+ALG_BYTES_PER_CANDIDATE = READ_LEN - SEED_LEN + 2 * (MAX_DIST + 1)     # (readLen - seedLen + 2*k_used) reference bytes
+ALG_BYTES_PER_READ_IO = 2 * READ_LEN + 88                              # bases + qualities in, result record out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-mbp", type=int, default=int(os.environ.get("SNAPGPU_BENCH_GENOME_MBP", "3000")),
+                    help="total reference size in Mbp (24 contigs); 3000 = BASELINE configs[1]")
+    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("SNAPGPU_BENCH_BATCH", str(1 << 20))),
+                    help="reads per step per GPU")
+    ap.add_argument("--cpu-sample-reads", type=int, default=200000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-seed-phase", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [l.strip().split(",") for l in open(self.path) if l.strip()]
+            sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nme in enumerate(names):
+                if any(len(r) > 4 + k and "Active" in r[4 + k] and "Not" not in r[4 + k] for r in rows):
+                    out["reasons"].append(nme)
+            out["samples"] = len(rows)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def build_workload(args, device, rank, world):
+    """Genome + index in this rank's HBM (replicated) and W+K batches of reads for this rank's shard."""
+    import torch
+    from snap_b200 import engine, synth_device
+    n_contigs = 24
+    contig_len = args.genome_mbp * 1_000_000 // n_contigs
+    t0 = time.time()
+    bases, starts = synth_device.make_genome(n_contigs, contig_len, seed=20260924, device=device)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    idx = engine.Index.build_device(bases.data_ptr(), bases.numel(), starts, seed_len=SEED_LEN, chromosome_padding=2000, device=device.index or 0)
+    torch.cuda.synchronize()
+    t2 = time.time()
+    batches = []
+    nb = args.warmup + args.steps
+    for b in range(nb):
+        # every (rank, step) gets its own reads: the global batch of step b is the concatenation over ranks
+        batches.append(synth_device.make_reads(bases, starts, contig_len, args.batch_reads, READ_LEN, seed=1000 + b * 64 + rank))
+    torch.cuda.synchronize()
+    t3 = time.time()
+    info = idx.info()
+    setup = {"genome_s": round(t1 - t0, 2), "index_build_s": round(t2 - t1, 2), "reads_s": round(t3 - t2, 2),
+             "index_hbm_gb": round(info.hbmBytes / 1e9, 2), "overflow_words": int(info.overflowTableSize)}
+    return bases, starts, contig_len, idx, batches, setup
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from snap_b200 import engine, shard
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    W, K, B = args.warmup, args.steps, args.batch_reads
+    bases, starts, contig_len, idx, batches, setup = build_workload(args, device, rank, world)
+    params = engine.default_params(maxDist=MAX_DIST)
+    al = engine.SingleAligner(idx, params, max_batch_reads=B)
+    stream = torch.cuda.current_stream(device)
+    res = torch.empty((B, engine.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=device)
+    d_ctr = torch.zeros((engine.N_COUNTERS,), dtype=torch.int64, device=device)
+
+    def step(b):
+        rb, rq, ro, rl = batches[b][0], batches[b][1], batches[b][2], batches[b][3]
+        al.align_device(B, rb.data_ptr(), rq.data_ptr(), ro.data_ptr(), rl.data_ptr(), res.data_ptr(), d_ctr.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-ups, then exactly K steps between barriers, CUDA events on the launch stream ----
+    for b in range(W):
+        step(b)
+    barrier()
+    d_ctr.zero_()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = al.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(K):
+        step(W + k)
+        ev[k + 1].record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_total = ev[0].elapsed_time(ev[K])
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    launches = al.launch_count() - launches0
+    ctr = d_ctr.cpu().numpy()
+    ms_max = shard.max_over_ranks(ms_total, device) if world > 1 else ms_total
+    ctr_all = shard.allreduce_counters(ctr, device) if world > 1 else ctr
+    c = engine.counters_dict(ctr_all)
+    reads_total = B * K * world
+    value = reads_total / (ms_max / 1e3)
+
+    # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) ----
+    host_batches = []
+    from snap_b200 import synth
+    for b in range(min(2, W + K)):
+        rb, rq, ro, rl = batches[b][:4]
+        host_batches.append(synth.ReadBatch(rb.cpu().numpy(), rq.cpu().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32)))
+    al.align(host_batches[0])                       # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = 0
+    e2e_steps = max(1, min(K, 3))
+    for k in range(e2e_steps):
+        r, _ = al.align(host_batches[k % len(host_batches)])
+        n_e2e += len(r)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = shard.max_over_ranks(e2e_s, device) if world > 1 else e2e_s
+    e2e_value = n_e2e * world / e2e_s
+
+    # ---- roofline of the dominant kernel (one sg_align_kernel launch per step) ----
+    peak, peak_src = measured_peaks()
+    per_launch = 1.0 / (K * world)
+    alg_bytes = (c["nHashEntriesProbed"] * 8 + c["nOverflowWordsRead"] * 4 + (c["lvCalls"] + c["affineGapCalls"]) * ALG_BYTES_PER_CANDIDATE
+                 + c["totalReads"] * ALG_BYTES_PER_READ_IO) * per_launch
+    kernel_ms_avg = float(np.mean(kernel_ms))
+    achieved = alg_bytes / (kernel_ms_avg / 1e3) / 1e9
+    roofline = {"kernel": "sg_align_kernel", "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(kernel_ms_avg, 3),
+                "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
+
+    out = {
+        "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_max / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
+        "config": {"workload": "snap single, %d x %d bp synthetic reads per step per GPU vs %d Mbp synthetic reference (24 contigs), "
+                               "seed %d, maxDist %d, affine gap on (BASELINE configs[1] shape)" % (B, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST),
+                   "reads_per_step": B * world, "read_len": READ_LEN, "genome_mbp": args.genome_mbp, "seed_len": SEED_LEN, "max_dist": MAX_DIST,
+                   "parallelism": "read-sharded x%d, index replicated per GPU" % world,
+                   "l2": "each step uses fresh reads (%.0f MB/step > L2) against a %.1f GB index" % (B * 2 * READ_LEN / 1e6, setup["index_hbm_gb"])},
+        "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(B * (2 * READ_LEN + 12)),
+                "d2h_bytes_per_step": int(B * engine.RESULT_DTYPE.itemsize + engine.N_COUNTERS * 8), "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "per_read": {"lookups": round(c["nHashTableLookups"] / max(1, c["totalReads"]), 3),
+                     "hash_entries_per_lookup": round(c["nHashEntriesProbed"] / max(1, c["nHashTableLookups"]), 3),
+                     "lv_locations": round(c["lvCalls"] / max(1, c["totalReads"]), 3),
+                     "ag_locations": round(c["affineGapCalls"] / max(1, c["totalReads"]), 3),
+                     "aligned_frac": round((c["singleHits"] + c["multiHits"]) / max(1, c["totalReads"]), 5)},
+        "setup": setup,
+    }
+
+    # ---- seed-lookup phase in isolation (rank 0, N=1) ----
+    if rank == 0 and not args.no_seed_phase:
+        try:
+            out["seed_phase"] = seed_phase(args, idx, batches, device, peak, peak_src)
+        except Exception as e:  # pragma: no cover
+            out["seed_phase"] = {"error": str(e)[:200]}
+
+    # ---- CPU baseline: the unmodified reference on the host cores, bounded sample (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(args, idx, host_batches[0], check_against=None)
+        except Exception as e:  # pragma: no cover
+            out["cpu_baseline"] = {"error": str(e)[:300]}
+
+    if rank == 0:
+        print(json.dumps(out))
+    al.close()
+    idx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def seed_phase(args, idx, batches, device, peak, peak_src):
+    """sg_lookup_kernel over the 7 non-overlapping seeds of every read of one batch: algorithmic bytes (entries examined
+    x 8 B + overflow words) per second, against the streaming peak and a measured random-8-byte-gather rate."""
+    import torch
+    B = args.batch_reads
+    rb = batches[0][0].reshape(B, READ_LEN)
+    offs = [0, 20, 40, 60, 80, 100, 120]
+    seeds = torch.stack([rb[:, o:o + SEED_LEN] for o in offs], dim=1).contiguous()       # [B, 7, 20]
+    n = B * len(offs)
+    nh = torch.empty((n * 2,), dtype=torch.int64, device=device)
+    probes = torch.empty((n,), dtype=torch.int32, device=device)
+    st = torch.cuda.current_stream(device)
+    for _ in range(2):
+        idx.lookup_seeds_device(seeds.data_ptr(), n, nh.data_ptr(), 0, probes.data_ptr(), 0, st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record(st)
+    for _ in range(reps):
+        idx.lookup_seeds_device(seeds.data_ptr(), n, nh.data_ptr(), 0, probes.data_ptr(), 0, st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    entries = int(probes.to(torch.int64).sum().item())
+    multi = nh[nh > 1]
+    overflow_words = int((multi + 1).sum().item())
+    alg = entries * 8 + overflow_words * 4 + n * SEED_LEN
+    # random 8-byte gather rate over a table of the same size (the regime GetFirstValueForKey lives in)
+    slots = int(idx.info().hashTableSlots)
+    tbl = torch.empty((min(slots, 1 << 31),), dtype=torch.int64, device=device)
+    gi = torch.randint(0, tbl.numel(), (1 << 24,), device=device)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _ = tbl[gi]
+    g0.record(st)
+    for _ in range(5):
+        _ = tbl[gi]
+    g1.record(st)
+    torch.cuda.synchronize()
+    gather_ms = g0.elapsed_time(g1) / 5
+    gather_gbs = gi.numel() * 8 / (gather_ms / 1e3) / 1e9
+    gather_sector_gbs = gi.numel() * 32 / (gather_ms / 1e3) / 1e9
+    del tbl, gi
+    achieved = alg / (ms / 1e3) / 1e9
+    sector = entries * 32 / (ms / 1e3) / 1e9
+    return {"kernel": "sg_lookup_kernel", "seeds": n, "ms": round(ms, 3), "lookups_per_s": round(n / (ms / 1e3), 1),
+            "entries_per_lookup": round(entries / n, 3), "achieved_algorithmic_gbs": round(achieved, 2),
+            "achieved_if_every_entry_costs_a_32B_sector_gbs": round(sector, 2), "peak_stream_gbs": peak, "peak_source": peak_src,
+            "frac_of_stream_peak": round(achieved / peak, 5),
+            "torch_random_8B_gather_gbs": round(gather_gbs, 2), "torch_random_gather_sector_gbs": round(gather_sector_gbs, 2),
+            "frac_of_random_gather_rate": round(achieved / gather_gbs, 4)}
+
+
+def export_index_for_reference(idx):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    d = tempfile.mkdtemp(prefix="snapidx_", dir=base)
+    idx.save(d)
+    return d
+
+
+def cpu_baseline(args, idx, host_batch, check_against):
+    """oracle/_ref (the compiled, unmodified reference) on all host cores over a bounded sample of the same reads."""
+    from oracle import reflib
+    if not reflib.available():
+        return {"error": "oracle/_ref not built"}
+    d = export_index_for_reference(idx)
+    try:
+        t0 = time.time()
+        ridx = reflib.RefIndex(d)
+        load_s = time.time() - t0
+        cores = os.cpu_count() or 1
+        n = min(args.cpu_sample_reads, host_batch.n)
+        sample = host_batch.slice(0, n)
+        p = reflib.default_params(maxDist=MAX_DIST)
+        reflib.align_mt(ridx, p, sample.slice(0, min(n, 20000)), cores)          # warm the page cache / TLB
+        res, ctr, secs = reflib.align_mt(ridx, p, sample, cores)
+        return {"value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
+                "sample": "%d of the step's %d reads, %d threads, oracle/_ref BaseAligner::AlignRead (aligner only, no SAM output); "
+                          "index = ours exported to SNAP's directory format (load %.1fs)" % (n, host_batch.n, cores, load_s),
+                "seconds": round(secs, 3), "lv_per_read": round(ctr["lvCalls"] / n, 3), "ag_per_read": round(ctr["affineGapCalls"] / n, 3)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from snap_b200 import engine, synth
+    from oracle import reflib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl reference: the workload's index is generated on the GPU; no CUDA device")
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(device)
+    W, K = args.warmup, args.steps
+    n = args.cpu_sample_reads
+    saved = args.batch_reads
+    args.batch_reads = n
+    bases, starts, contig_len, idx, batches, setup = build_workload(args, device, 0, 1)
+    args.batch_reads = saved
+    d = export_index_for_reference(idx)
+    idx.close()
+    del bases
+    torch.cuda.empty_cache()
+    try:
+        ridx = reflib.RefIndex(d)
+        cores = os.cpu_count() or 1
+        p = reflib.default_params(maxDist=MAX_DIST)
+        hb = []
+        for b in range(W + K):
+            rb, rq, ro, rl = batches[b][:4]
+            hb.append(synth.ReadBatch(rb.cpu().numpy(), rq.cpu().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32)))
+        for b in range(W):
+            reflib.align_mt(ridx, p, hb[b], cores)
+        total_s = 0.0
+        aligned = 0
+        for k in range(K):
+            res, ctr, secs = reflib.align_mt(ridx, p, hb[W + k], cores)
+            total_s += secs
+            aligned += int((res["status"] != 0).sum())
+        value = n * K / total_s
+        sample = "%d reads per step (bounded sample of the %d-read step), %d threads" % (n, saved, cores)
+        out = {"impl": "reference", "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": args.gpus, "steps": K,
+               "warmup": W, "ms_per_step": round(total_s / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
+               "config": {"workload": "snap single, %d x %d bp synthetic reads per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
+                                      % (n, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST), "read_len": READ_LEN, "genome_mbp": args.genome_mbp,
+                          "seed_len": SEED_LEN, "max_dist": MAX_DIST},
+               "cpu_baseline": {"value": round(value, 1), "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample},
+               "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "aligned_frac": round(aligned / (n * K), 5),
+               "note": "unmodified amplab/snap BaseAligner::AlignRead via oracle/_ref on host cores; index = GPU-built, exported to SNAP's format"}
+        print(json.dumps(out))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,12 @@ int  snapgpu_index_open(const char *directory, int device, snapgpu_index **out);
  */
 int  snapgpu_index_build(const char *bases, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
                          uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out);
+/* Same, with the nBases bases already in HBM (DEVICE pointer); they are copied into the index image. */
+int  snapgpu_index_build_device(const char *d_bases, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
+                                uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out);
+/* Writes the HBM-resident index out as a reference-format directory (the four files `snap-aligner index` produces,
+ * SURVEY 8a-F) so stock SNAP can load an index built on the device. */
+int  snapgpu_index_save(const snapgpu_index *idx, const char *directory);
 int  snapgpu_index_info_get(const snapgpu_index *idx, snapgpu_index_info *info);
 void snapgpu_index_close(snapgpu_index *idx);
 
@@ -160,6 +166,11 @@ void snapgpu_index_close(snapgpu_index *idx);
  */
 int  snapgpu_lookup_seeds(const snapgpu_index *idx, const char *seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,
                           int64_t *nHits, uint32_t *hits, uint32_t *probes);
+
+/* Same with DEVICE pointers (d_hits / d_probes may be NULL), enqueued on `cudaStream` without synchronising:
+ * the seed-lookup phase in isolation, for its roofline measurement. */
+int  snapgpu_lookup_seeds_device(const snapgpu_index *idx, const char *d_seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,
+                                 int64_t *d_nHits, uint32_t *d_hits, uint32_t *d_probes, void *cudaStream);
 
 /*
  * Aligner handle.  One per host thread, like BaseAligner (reference SNAPLib/BaseAligner.h:19-20:

@@ -24,6 +24,9 @@ SG_HD SgAgParams sg_ag_params(int matchReward, int subPenalty, int gapOpen, int 
 struct SgAgResult {
     int agScore, textOffset, patternOffset, nEdits;
     double matchProbability;
+#ifdef SG_AG_POISON_CHECK
+    int poisoned;
+#endif
 };
 
 // ntTransitionMatrix (:123-132): equal ACGT -> match, different ACGT -> sub, anything with N (value 4) -> -1.
@@ -59,7 +62,19 @@ SG_HD int sg_ag_cell(const SgAgParams &P, int hdiag, int prof, int16_t *Ecell, i
 // Shared tail: local-vs-global choice, clipping heuristics and traceback (:1161-1338 / :642-818).
 // btIndex(row, col) maps to the striped byte holding the 6 action bits.
 struct SgAgLayout {
-    int numVec, segLen, numSeg, banded;
+    int numVec, segLen, numSeg, banded, w, patternLen, nRows;
+    // Was cell (row, col) written by the DP of this call?  Rows past the last one the row loop reached were not
+    // (the clipping heuristics can start the traceback there); in the banded variant only whole in-band vectors are (:483).
+    SG_HD bool computed(int row, int col) const {
+        if (row >= nRows) return false;
+        if (!banded) return true;
+        int bandBeg = (row - w) > 0 ? (row - w) : 0;
+        int bandEnd = (row + w) < (patternLen - 1) ? (row + w) : (patternLen - 1);
+        int seg = col / segLen;
+        if (seg < bandBeg / segLen || seg > bandEnd / segLen) return false;
+        int k = (col % segLen) % numVec;
+        return seg * segLen + k <= bandEnd;
+    }
     SG_HD int cellIndex(int col) const {
         if (!banded) return (col % numVec) * SG_VEC + (col / numVec);
         int vecIdx = (col / segLen) * numVec + ((col % segLen) % numVec);
@@ -137,7 +152,15 @@ SG_HDN void sg_ag_finish(const SgTables &T, const SgAgParams &P, const SgAgLayou
         const int stride = lay.rowStride();
         while (rowIdx >= 0 && colIdx >= 0) {
             int matrixIdx = action << 1;
-            action = (bt[(size_t)rowIdx * stride + lay.cellIndex(colIdx)] >> matrixIdx) & 3;
+            // A traceback step can land on a cell this call never wrote.  The reference then reads whatever an *earlier*
+            // call of the same object left in its never-cleared backtraceAction array (:1374); we keep the array persistent
+            // per worker and per direction with the same linear layout, so the same stale bits are read whenever the
+            // history is the same (always true within one read; across reads it depends on which thread/warp ran what).
+            uint8_t cell = bt[(size_t)rowIdx * stride + lay.cellIndex(colIdx)];
+#ifdef SG_AG_POISON_CHECK
+            if (!lay.computed(rowIdx, colIdx)) out->poisoned = 1;
+#endif
+            action = (cell >> matrixIdx) & 3;
             if (action == 0) {
                 if (pattern[colIdx] != text[rowIdx * dir]) {
                     mp *= T.phred[quality[colIdx]];
@@ -215,11 +238,14 @@ SG_HDN void sg_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParam
                           const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
                           int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out)
 {
-    out->textOffset = -1; out->patternOffset = -1; out->nEdits = -1; out->matchProbability = 0.0; out->agScore = -1;
+    // `out` is in/out like the reference's o_* pointers: on the two early returns below textOffset / patternOffset
+    // (and for w < 0 also matchProbability) are left as the caller initialised them (:860-893).
+    out->agScore = -1;
     if (w > SG_MAX_K - 1) w = SG_MAX_K - 1;
-    if (text == (const uint8_t *)0) { out->matchProbability = 0.0; out->nEdits = -1; out->agScore = -1; return; }
-    if (w < 0) { out->nEdits = SG_SCORE_ABOVE_LIMIT; out->agScore = -1; return; }
+    if (text == (const uint8_t *)0) { out->matchProbability = 0.0; out->nEdits = -1; return; }
+    if (w < 0) { out->nEdits = SG_SCORE_ABOVE_LIMIT; return; }
     out->matchProbability = 1.0;
+    out->textOffset = -1; out->patternOffset = -1; out->nEdits = -1;
     if (dir == -1) text--;
 
     SgAgLayout lay;
@@ -234,6 +260,7 @@ SG_HDN void sg_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParam
         lay.segLen = lay.numVec * SG_VEC;
         lay.numSeg = 1;
     }
+    lay.w = w; lay.patternLen = patternLen;
     const int numVec = lay.numVec, segLen = lay.segLen, numSeg = lay.numSeg;
     const int stride = lay.rowStride();
 
@@ -242,7 +269,10 @@ SG_HDN void sg_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParam
     else       endBonus = (dir == -1) ? P.threePrimeEndBonus : P.fivePrimeEndBonus;
 
     int16_t *Hptr = S.agH, *Hm1ptr = S.agHm1, *E = S.agE;
-    uint8_t *bt = S.agBt;
+    uint8_t *bt = S.agBt[dir == 1 ? 0 : 1];
+#ifdef SG_AG_POISON_CHECK
+    out->poisoned = 0;
+#endif
 
     // first row (:971-983 / :399-414); scoreFirstRow[] deliberately persists across vecIdx like the reference's
     {
@@ -268,7 +298,9 @@ SG_HDN void sg_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParam
     int bestGlobalAlignmentScore = -1, bestGlobalAlignmentTextOffset = -1;
     int bestLocalAlignmentScore = -1, bestLocalAlignmentTextOffset = -1, bestLocalAlignmentPatternOffset = -1;
 
+    lay.nRows = 0;
     for (int i = 0; i < textLen; i++) {
+        lay.nRows = i + 1;
         const uint32_t tb = sg_base_value(text[i * dir]);
         uint8_t *btRow = bt + (size_t)i * stride;
         int f[SG_VEC], maxv[SG_VEC], X[SG_VEC], h[SG_VEC];

@@ -9,6 +9,9 @@
 #include "sg_seed.h"
 #include "sg_lv.h"
 #include "sg_ag.h"
+#if defined(__CUDACC__)
+#include "sg_warp.cuh"
+#endif
 
 struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260-329
     int      bestScore;
@@ -88,6 +91,7 @@ struct SgAligner {
     SgScratch          sc;
     SgAgParams         ag;
     SgWork             work;
+    int                lane;         // 0..31 on the device (all lanes run the state machine uniformly); 0 on the host
 
     // per-read state
     const uint8_t *readData[2], *readQual[2];   // [FORWARD] = input, [RC] = rcRead/rcQual
@@ -264,6 +268,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
                 usedAffineGapScoring = 1;
                 A.work.agCalls++;
                 SgAgResult ar;
+                ar.textOffset = 0; ar.patternOffset = 0; ar.nEdits = 0; ar.matchProbability = 1.0; ar.agScore = -1;
                 if (tailStart != readLen) {
                     int patternLen = readLen - tailStart;
                     bool banded = (patternLen >= (3 * (2 * scoreLimitForThisElement + 1))) && !pr.noBandedAffineGap;
@@ -277,6 +282,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
                         int limitLeft = scoreLimitForThisElement - score1;
                         int patternLen = seedOffset;
                         bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
+                        ar.textOffset = genomeLocationOffset; ar.patternOffset = basesClippedBefore; ar.matchProbability = matchProb2;
                         sg_ag_compute(T, A.sc, A.ag, -1, banded, data + seedOffset, seedOffset + limitLeft, revRead + readLen - seedOffset,
                                       oppQual + readLen - seedOffset, seedOffset, limitLeft, readLen, dirn != 0, false, &ar);
                         agScore2 = ar.agScore; genomeLocationOffset = ar.textOffset; basesClippedBefore = ar.patternOffset;
@@ -321,7 +327,9 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
     }
     for (int direction = 0; direction < 2; direction++) {
         if (0 != A.mostSeedsContainingAnyParticularBase[direction]) {
-            uint32_t v = A.nSeedsApplied[direction] / A.mostSeedsContainingAnyParticularBase[direction];
+            // EXACT_DISJOINT_MISS_COUNT is #defined at BaseAligner.cpp:42, so the bound is the number of seeds applied in
+            // the current wrap round (:997-1000), not nSeedsApplied / mostSeedsContainingAnyParticularBase (:1002-1004).
+            uint32_t v = A.currRoundLowestPossibleScoreOfAnyUnseenLocation[direction];
             if (A.lowestPossibleScoreOfAnyUnseenLocation[direction] < v) A.lowestPossibleScoreOfAnyUnseenLocation[direction] = v;
         }
     }
@@ -549,10 +557,14 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
         A.setSeedUsed(nextSeedToTest);
 
         uint64_t sb, srcb;
-        if (!sg_seed_pack(readData + nextSeedToTest, seedLen, &sb, &srcb)) continue;
-
         SgHits hits;
+#if defined(__CUDA_ARCH__)
+        if (!sg_warp_seed_pack(readData + nextSeedToTest, seedLen, A.lane, &sb, &srcb)) continue;
+        sg_warp_lookup_seed32(ix, sb, srcb, A.lane, &hits, &A.work.entriesProbed, &A.work.overflowWords);
+#else
+        if (!sg_seed_pack(readData + nextSeedToTest, seedLen, &sb, &srcb)) continue;
         sg_lookup_seed32(ix, sb, srcb, &hits, &A.work.entriesProbed, &A.work.overflowWords);
+#endif
         A.work.lookups++;
 
         bool appliedEitherSeed = false;

@@ -12,7 +12,7 @@
 
 struct SgHostIndex {
     std::vector<uint8_t>  tables;        // repacked: entries of all tables back to back (+8 bytes slack)
-    std::vector<uint64_t> tableStart, tableSize;
+    std::vector<uint64_t> tableStart, tableSize, tableUsed;
     std::vector<uint32_t> overflow;      // +1 word slack
     std::vector<uint8_t>  basesPadded;   // SG_N_PADDING 'n' + bases + SG_N_PADDING 'n'
     std::vector<int64_t>  contigStart;
@@ -114,7 +114,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
     if ((long long)buf.size() != hashTablesFileSize) { err = "GenomeIndexHash has unexpected size"; return false; }
     const uint32_t valueCount = ix.large ? 2 : 1;
     ix.entryBytes = 4 * valueCount + ix.keyBytes;
-    ix.tableStart.assign(nHashTables, 0); ix.tableSize.assign(nHashTables, 0);
+    ix.tableStart.assign(nHashTables, 0); ix.tableSize.assign(nHashTables, 0); ix.tableUsed.assign(nHashTables, 0);
     // first pass: sizes
     {
         size_t off = 0; uint64_t slots = 0;
@@ -127,7 +127,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
             if (vs != 4 || vc != valueCount || ks != ix.keyBytes) { err = "hash table key/value geometry unsupported"; return false; }
             memcpy(&inval, &buf[off + 32], 4);
             ix.invalidValue = inval;
-            ix.tableStart[t] = slots; ix.tableSize[t] = tsz;
+            ix.tableStart[t] = slots; ix.tableSize[t] = tsz; ix.tableUsed[t] = used;
             slots += tsz;
             off += 36 + (size_t)tsz * ix.entryBytes;
         }

@@ -1,0 +1,116 @@
+// sg_warp.cuh -- warp-cooperative leaves (device only).
+//
+// Execution model of the alignment kernel: one warp per read.  The BaseAligner state machine is inherently
+// sequential, so all 32 lanes execute it *uniformly* (identical registers, identical loads, same-value stores:
+// a warp instruction costs one issue slot whether 1 or 32 lanes are live, so the redundancy is free) and therefore
+// arrive converged at every leaf below, where the lanes split the data-parallel work and exchange it with shuffles.
+#pragma once
+#include "sg_common.h"
+#include "sg_seed.h"
+
+#define SG_FULL 0xffffffffu
+
+// Seed::Seed across lanes: lane i encodes base i (seedLen <= 32).  Returns false if any base is not ACGT.
+__device__ __forceinline__ bool sg_warp_seed_pack(const uint8_t *text, uint32_t seedLen, int lane, uint64_t *bases, uint64_t *rc)
+{
+    uint32_t v = 0;
+    bool ok = true;
+    if ((uint32_t)lane < seedLen) {
+        v = sg_base_value(text[lane]);
+        ok = v < 4;
+    }
+    ok = __all_sync(SG_FULL, ok);
+    uint64_t b = 0, r = 0;
+    if ((uint32_t)lane < seedLen) {
+        b = (uint64_t)(v & 3) << ((seedLen - lane - 1) * 2);
+        r = (uint64_t)((v & 3) ^ 3) << (lane * 2);
+    }
+    uint32_t blo = __reduce_or_sync(SG_FULL, (uint32_t)b), bhi = __reduce_or_sync(SG_FULL, (uint32_t)(b >> 32));
+    uint32_t rlo = __reduce_or_sync(SG_FULL, (uint32_t)r), rhi = __reduce_or_sync(SG_FULL, (uint32_t)(r >> 32));
+    *bases = ((uint64_t)bhi << 32) | blo;
+    *rc = ((uint64_t)rhi << 32) | rlo;
+    return ok;
+}
+
+// Offset of probe number k from the home slot (SNAPHashTable::GetFirstValueForKey, HashTable.h:87-118):
+// +1, +4, +9, +16 for nProbes 1..4 (QUADRATIC_CHAINING_DEPTH 5), then +1 each.
+__device__ __forceinline__ uint32_t sg_probe_offset(uint32_t k)
+{
+    return k == 0 ? 0u : k == 1 ? 1u : k == 2 ? 5u : k == 3 ? 14u : (30u + (k - 4u));
+}
+
+// Both strand chains of a default (small) index are probed at once: lanes 0-15 take probes 0..15 of the forward
+// seed's chain, lanes 16-31 the same for the reverse complement; one round of independent 8-byte loads usually
+// resolves both (mean chain 5.5 entries).  A `-large` index has one chain (canonical seed): all 32 lanes probe it.
+// Result semantics are exactly sg_lookup_seed32's.
+__device__ __forceinline__ void sg_warp_lookup_seed32(const SgIndexView &ix, uint64_t bases, uint64_t rc, int lane, SgHits *out,
+                                                      uint32_t *examined, uint32_t *overflowWords)
+{
+    const uint32_t keyBits = ix.keyBytes * 8;
+    out->nHits[0] = out->nHits[1] = 0;
+    out->hits[0] = out->hits[1] = ix.overflow;
+    const bool large = ix.large != 0;
+    const bool lookedUpComplement = large && (bases > rc);
+    // chain c (0/1) = strand for the small index; for -large only chain 0 exists
+    const uint32_t chainWidth = large ? 32u : 16u;
+    const uint32_t myChain = large ? 0u : (uint32_t)(lane >> 4);
+    const uint32_t myK0 = large ? (uint32_t)lane : (uint32_t)(lane & 15);
+    uint64_t s = large ? (lookedUpComplement ? rc : bases) : (myChain ? rc : bases);
+    const uint64_t low = (ix.keyBytes == 8) ? s : (s & ((1ULL << keyBits) - 1));
+    const uint32_t table = (ix.keyBytes == 8) ? 0u : (uint32_t)(s >> keyBits);
+    const uint64_t size = ix.tableSize[table];
+    const uint64_t base = ix.tableStart[table];
+    const uint64_t home = sg_fmix64(low) % size;
+
+    uint64_t foundSlot[2] = {~0ULL, ~0ULL};
+    bool done[2] = {false, large};
+    uint32_t round = 0;
+    while (!(done[0] && done[1])) {
+        uint32_t k = round * chainWidth + myK0;
+        uint64_t slot = base + (home + sg_probe_offset(k)) % size;
+        uint32_t v; uint64_t key;
+        bool active = !done[myChain] && (uint64_t)k <= size + 5;
+        if (active) sg_entry_load(ix, slot, &v, &key); else { v = 0; key = ~0ULL; }
+        bool match = active && (key == low);
+        bool inval = active && (v == ix.invalidValue);
+        bool stop = (k == 0) ? (match && !inval) : (match || inval);
+        if (active && (uint64_t)k == size + 5) stop = true;          // nProbes > tableSize + 5: give up
+        uint32_t stopMask = __ballot_sync(SG_FULL, stop);
+        for (uint32_t c = 0; c < 2; c++) {
+            if (done[c]) continue;
+            uint32_t m = large ? stopMask : ((stopMask >> (16 * c)) & 0xffffu);
+            if (m != 0) {
+                uint32_t first = __ffs(m) - 1;
+                uint32_t srcLane = large ? first : (16 * c + first);
+                uint32_t kk = round * chainWidth + first;
+                bool hit = __shfl_sync(SG_FULL, (int)(match && !inval), srcLane) != 0;
+                uint32_t slo = __shfl_sync(SG_FULL, (uint32_t)slot, srcLane), shi = __shfl_sync(SG_FULL, (uint32_t)(slot >> 32), srcLane);
+                foundSlot[c] = hit ? (((uint64_t)shi << 32) | slo) : ~0ULL;
+                *examined += kk + 1;
+                done[c] = true;
+            } else if ((uint64_t)(round + 1) * chainWidth > size + 5) {
+                done[c] = true;
+            }
+        }
+        round++;
+    }
+
+    if (large) {
+        if (foundSlot[0] == ~0ULL) return;
+        const uint32_t *entry = (const uint32_t *)(ix.tables + foundSlot[0] * ix.entryBytes);
+        sg_fill_hits(ix, lookedUpComplement ? entry + 1 : entry, &out->nHits[0], &out->hits[0], overflowWords);
+        if (bases == rc) {
+            out->nHits[1] = out->nHits[0];
+            out->hits[1] = out->hits[0];
+        } else {
+            sg_fill_hits(ix, lookedUpComplement ? entry : entry + 1, &out->nHits[1], &out->hits[1], overflowWords);
+        }
+    } else {
+        for (int c = 0; c < 2; c++) {
+            if (foundSlot[c] != ~0ULL) {
+                const uint32_t *entry = (const uint32_t *)(ix.tables + foundSlot[c] * ix.entryBytes);
+                sg_fill_hits(ix, entry, &out->nHits[c], &out->hits[c], overflowWords);
+            }
+        }
+    }
+}

@@ -1,0 +1,744 @@
+// snapgpu.cu -- the CUDA library behind include/snapgpu.h (sm_100a).
+//
+// Index image in HBM, per-warp scratch arenas, the alignment kernels and the C ABI.  There is no CPU
+// fallback anywhere in this file: every entry point that needs the device fails with an error when no
+// usable CUDA device / kernel image is present.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "sg_host.h"
+#include "sg_align.h"
+#include "sg_build.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError = "";
+
+static int sg_fail(const std::string &msg)
+{
+    g_lastError = msg;
+    return 1;
+}
+
+#define SG_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            return sg_fail(std::string(#call) + ": " + cudaGetErrorString(e__));                          \
+        }                                                                                                 \
+    } while (0)
+
+struct snapgpu_index {
+    int device = 0;
+    SgIndexView view;                    // device pointers
+    snapgpu_index_info info;
+    uint8_t  *d_tables = nullptr;
+    uint64_t *d_tableStart = nullptr, *d_tableSize = nullptr;
+    uint32_t *d_overflow = nullptr;
+    uint8_t  *d_basesPadded = nullptr;
+    int64_t  *d_contigStart = nullptr;
+    SgTables *d_tables_prob = nullptr;   // probability / schedule tables
+    SgTables  h_tables_prob;
+    // host-side metadata (needed to write the index back out in the reference's directory format)
+    std::vector<uint64_t> h_tableStart, h_tableSize, h_tableUsed;
+    std::vector<int64_t> h_contigStart;
+    std::vector<std::string> h_contigName;
+    std::vector<uint8_t> h_contigIsAlt;
+};
+
+struct snapgpu_aligner {
+    const snapgpu_index *index = nullptr;
+    SgParams params;
+    snapgpu_params userParams;
+    int device = 0;
+    int numSMs = 0;
+    int warpsPerBlock = 8, blocksPerSM = 4;
+    int nWorkers = 0;
+    size_t scratchBytesPerWorker = 0;
+    uint8_t *d_scratch = nullptr;
+    unsigned long long *d_next = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t maxBatchReads = 0;
+    size_t maxBatchBases = 0;
+    // staging
+    char *h_bases = nullptr, *h_quals = nullptr; uint64_t *h_offsets = nullptr; uint32_t *h_lens = nullptr;
+    snapgpu_single_result *h_results = nullptr; snapgpu_counters *h_counters = nullptr;
+    char *d_bases = nullptr, *d_quals = nullptr; uint64_t *d_offsets = nullptr; uint32_t *d_lens = nullptr;
+    snapgpu_single_result *d_results = nullptr; snapgpu_counters *d_counters = nullptr;
+    int64_t launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// K1 (parity / roofline entry): batched lookupSeed32, one seed per warp; lanes probe the chain together.
+__global__ void sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_t maxHitsPerSeed,
+                                 long long *nHits, uint32_t *hits, uint32_t *probes)
+{
+    const int lane = threadIdx.x & 31;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < nSeeds; i += nWarps) {
+        uint64_t b, rc;
+        bool ok = sg_warp_seed_pack(seeds + i * ix.seedLen, ix.seedLen, lane, &b, &rc);
+        SgHits h;
+        uint32_t examined = 0, ow = 0;
+        h.nHits[0] = h.nHits[1] = 0; h.hits[0] = h.hits[1] = ix.overflow;
+        if (ok) sg_warp_lookup_seed32(ix, b, rc, lane, &h, &examined, &ow);
+        if (lane == 0) {
+            nHits[2 * i] = h.nHits[0];
+            nHits[2 * i + 1] = h.nHits[1];
+            if (probes) probes[i] = examined;
+        }
+        if (hits) {
+            for (int d = 0; d < 2; d++) {
+                uint32_t n = h.nHits[d] < maxHitsPerSeed ? h.nHits[d] : maxHitsPerSeed;
+                for (uint32_t k = lane; k < n; k += 32) hits[(2 * i + d) * (long long)maxHitsPerSeed + k] = h.hits[d][k];
+            }
+        }
+    }
+}
+
+// The alignment kernel: persistent grid, one warp per read at a time, reads handed out by an atomic counter.
+// The BaseAligner state machine is inherently sequential, so all 32 lanes execute it uniformly (see sg_warp.cuh)
+// and split the work inside the data-parallel leaves (hash-chain probing of both strands, ...).
+__global__ void __launch_bounds__(256)
+sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratchBase, size_t scratchBytesPerWorker,
+                long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
+                snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next)
+{
+    const int lane = threadIdx.x & 31;
+    const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    SgAligner A;
+    A.ix = &ix; A.pr = &pr; A.tb = tb;
+    A.lane = lane;
+    sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
+    A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
+    A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    A.nUsedElements = 0;         // the scratch lookup table is all-zero at creation and left clean after every read
+    A.work.lookups = A.work.entriesProbed = A.work.overflowWords = A.work.lvCalls = A.work.agCalls = A.work.popularIgnored = 0;
+    unsigned long long cTotal = 0, cUseless = 0, cSingle = 0, cMulti = 0, cNotFound = 0;
+
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(next, 1ULL);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= (unsigned long long)n) break;
+        const uint8_t *rd = bases + offsets[i];
+        const uint8_t *rq = quals + offsets[i];
+        const uint32_t len = lens[i];
+        snapgpu_single_result r;
+        memset(&r, 0, sizeof(r));
+        cTotal++;
+        uint32_t countOfNs = 0;
+        for (uint32_t k = lane; k < len; k += 32) countOfNs += (rd[k] == 'N');
+        countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
+        if (len < pr.minReadLength || countOfNs > pr.maxK || len > pr.maxReadLen) {
+            // SingleAligner.cpp:213-233 (reads longer than the configured scratch bound are reported NotFound
+            // with reserved = 1 so the host wrapper can raise an error)
+            r.status = SNAPGPU_NOT_FOUND; r.location = A.invalidLocation; r.mapq = 0; r.direction = SNAPGPU_FORWARD;
+            r.reserved = (len > pr.maxReadLen) ? 1u : 0u;
+            cUseless++;
+            if (lane == 0) results[i] = r;
+            continue;
+        }
+        sg_align_read(A, rd, rq, len, &r);
+        if (lane == 0) results[i] = r;
+        if (r.status == SNAPGPU_SINGLE_HIT) cSingle++;
+        else if (r.status == SNAPGPU_MULTIPLE_HITS) cMulti++;
+        else cNotFound++;
+        if (lane == 0 && counters && r.status != SNAPGPU_NOT_FOUND && r.mapq >= 0 && r.mapq <= 70) {
+            atomicAdd((unsigned long long *)&counters->mapqHistogram[r.mapq], 1ULL);
+        }
+    }
+    // leave the scratch lookup table clean for the next launch
+    A.clearCandidates();
+    if (counters && lane == 0) {
+        atomicAdd((unsigned long long *)&counters->totalReads, cTotal);
+        atomicAdd((unsigned long long *)&counters->uselessReads, cUseless);
+        atomicAdd((unsigned long long *)&counters->singleHits, cSingle);
+        atomicAdd((unsigned long long *)&counters->multiHits, cMulti);
+        atomicAdd((unsigned long long *)&counters->notFound, cNotFound);
+        atomicAdd((unsigned long long *)&counters->nHashTableLookups, (unsigned long long)A.work.lookups);
+        atomicAdd((unsigned long long *)&counters->nHashEntriesProbed, (unsigned long long)A.work.entriesProbed);
+        atomicAdd((unsigned long long *)&counters->nOverflowWordsRead, (unsigned long long)A.work.overflowWords);
+        atomicAdd((unsigned long long *)&counters->lvCalls, (unsigned long long)A.work.lvCalls);
+        atomicAdd((unsigned long long *)&counters->affineGapCalls, (unsigned long long)A.work.agCalls);
+        atomicAdd((unsigned long long *)&counters->nHitsIgnoredBecauseOfTooHighPopularity, (unsigned long long)A.work.popularIgnored);
+    }
+}
+
+// leaf-test kernels: one job per thread, scalar leaves (the warp-cooperative forms are exercised through the
+// alignment kernel and compared against these on the same inputs by the tests)
+__global__ void sg_test_lv_kernel(const SgTables *tb, SgParams pr, uint8_t *scratchBase, size_t scratchBytes,
+                                  const uint8_t *textBuf, const uint8_t *patBuf, const uint8_t *qualBuf,
+                                  const snapgpu_lv_job *jobs, long long nJobs, snapgpu_lv_out *out)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long nT = (long long)gridDim.x * blockDim.x;
+    SgScratch s;
+    sg_scratch_carve(pr, scratchBase + (size_t)t * scratchBytes, &s);
+    for (long long j = t; j < nJobs; j += nT) {
+        SgLvResult r;
+        sg_lv_compute(*tb, s, jobs[j].dir, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff, qualBuf + jobs[j].patOff,
+                      jobs[j].patternLen, jobs[j].k, &r);
+        out[j].score = r.score; out[j].netIndel = r.netIndel; out[j].totalIndels = r.totalIndels; out[j].textSpan = r.textSpan;
+        out[j].matchProbability = r.matchProbability;
+    }
+}
+
+__global__ void sg_test_ag_kernel(const SgTables *tb, SgParams pr, SgAgParams P, uint8_t *scratchBase, size_t scratchBytes,
+                                  const uint8_t *textBuf, const uint8_t *patBuf, const uint8_t *qualBuf,
+                                  const snapgpu_ag_job *jobs, long long nJobs, snapgpu_ag_out *out)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long nT = (long long)gridDim.x * blockDim.x;
+    SgScratch s;
+    sg_scratch_carve(pr, scratchBase + (size_t)t * scratchBytes, &s);
+    for (long long j = t; j < nJobs; j += nT) {
+        SgAgResult r;
+        r.agScore = -1; r.textOffset = 0; r.patternOffset = 0; r.nEdits = 0; r.matchProbability = 0.0;
+        sg_ag_compute(*tb, s, P, jobs[j].dir, jobs[j].banded != 0, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff,
+                      qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].w, jobs[j].scoreInit, jobs[j].isRC != 0,
+                      jobs[j].useClippingOptimizations != 0, &r);
+        out[j].agScore = r.agScore; out[j].textOffset = r.textOffset; out[j].patternOffset = r.patternOffset; out[j].nEdits = r.nEdits;
+        out[j].matchProbability = r.matchProbability;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *snapgpu_last_error(void) { return g_lastError.c_str(); }
+int snapgpu_abi_version(void) { return SNAPGPU_ABI_VERSION; }
+
+int snapgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void snapgpu_params_default(snapgpu_params *p)
+{
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->maxHits = 300; p->maxDist = 14; p->numSeedsFromCommandLine = 25; p->seedCoverage = 0.0;
+    p->minWeightToCheck = 1; p->extraSearchDepth = 1; p->minReadLength = 50; p->useAffineGap = 1;
+    p->matchReward = 1; p->subPenalty = 4; p->gapOpenPenalty = 6; p->gapExtendPenalty = 1;
+    p->fivePrimeEndBonus = 10; p->threePrimeEndBonus = 7;
+    p->altAwareness = 1; p->maxScoreGapToPreferNonAltAlignment = 64;
+    p->maxSecondaryAlignmentAdditionalEditDistance = -1; p->ignoreAlignmentAdjustmentsForOm = 1;
+}
+
+static int require_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return sg_fail("no usable CUDA device: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return sg_fail("CUDA device ordinal out of range");
+    SG_CUDA(cudaSetDevice(device));
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, sg_align_kernel);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sg_fail(std::string("no sm_100a kernel image usable on this device: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
+{
+    if (require_device(device)) return 1;
+    snapgpu_index *ix = new (std::nothrow) snapgpu_index;
+    if (!ix) return sg_fail("out of memory");
+    ix->device = device;
+    size_t hbm = 0;
+    #define UP(dst, src, bytes) do { size_t b__ = (bytes); if (b__ == 0) b__ = 16; SG_CUDA(cudaMalloc((void **)&(dst), b__)); \
+        if ((bytes) > 0) SG_CUDA(cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice)); hbm += b__; } while (0)
+    UP(ix->d_tables, h.tables.data(), h.tables.size());
+    UP(ix->d_tableStart, h.tableStart.data(), h.tableStart.size() * 8);
+    UP(ix->d_tableSize, h.tableSize.data(), h.tableSize.size() * 8);
+    UP(ix->d_overflow, h.overflow.data(), h.overflow.size() * 4);
+    UP(ix->d_basesPadded, h.basesPadded.data(), h.basesPadded.size());
+    UP(ix->d_contigStart, h.contigStart.data(), h.contigStart.size() * 8);
+    sg_init_tables(ix->h_tables_prob, h.seedLen);
+    UP(ix->d_tables_prob, &ix->h_tables_prob, sizeof(SgTables));
+    #undef UP
+    SgIndexView v = h.view();
+    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.overflow = ix->d_overflow;
+    v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart;
+    ix->view = v;
+    memset(&ix->info, 0, sizeof(ix->info));
+    ix->info.countOfBases = h.nBases; ix->info.seedLen = h.seedLen; ix->info.hashTableKeySize = h.keyBytes;
+    ix->info.nHashTables = h.nTables; ix->info.locationSize = 4; ix->info.largeHashTable = h.large;
+    ix->info.chromosomePadding = h.chromosomePadding; ix->info.nContigs = (uint32_t)h.contigStart.size();
+    ix->info.overflowTableSize = h.overflowSize; ix->info.hashTableSlots = h.totalSlots; ix->info.hbmBytes = hbm;
+    ix->h_tableStart = h.tableStart; ix->h_tableSize = h.tableSize; ix->h_tableUsed = h.tableUsed;
+    ix->h_contigStart = h.contigStart; ix->h_contigName = h.contigName; ix->h_contigIsAlt = h.contigIsAlt;
+    *out = ix;
+    return 0;
+}
+
+int snapgpu_index_open(const char *directory, int device, snapgpu_index **out)
+{
+    if (!directory || !out) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(device)) return 1;
+    SgHostIndex h;
+    std::string err;
+    if (!sg_load_index_directory(directory, h, err)) return sg_fail("snapgpu_index_open: " + err);
+    return upload_index(h, device, out);
+}
+
+// Device-side index construction (kernels in sg_build.cuh).  d_basesPadded: SG_N_PADDING 'n', the nBases bases,
+// SG_N_PADDING 'n' -- ownership passes to the index on success.
+static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
+                                 uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out)
+{
+    if (seedLen < 16 || seedLen > 24) return sg_fail("snapgpu_index_build: seed length must be in [16, 24]");
+    if (nBases <= (int64_t)seedLen + 2 || nBases > 0xffffffffLL - 16) return sg_fail("snapgpu_index_build: genome size unsupported for 4-byte locations");
+    const uint32_t keyBytes = 4, keyBits = 32;
+    const uint32_t nTables = 1u << ((seedLen - 16) * 2);
+    const long long nPos = nBases - seedLen - 1;          // GenomeIndex.cpp:645-652: locations [0, countOfBases - seedLen - 1)
+    snapgpu_index *ix = new (std::nothrow) snapgpu_index;
+    if (!ix) return sg_fail("out of memory");
+    ix->device = device;
+    ix->d_basesPadded = d_basesPadded;
+    const uint8_t *d_bases = d_basesPadded + SG_N_PADDING;
+
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_locs = nullptr, *d_locs2 = nullptr;
+    void *d_temp = nullptr; size_t tempBytes = 0;
+    unsigned long long *d_stats = nullptr;       // [nTables] used, then overflowWords, nValid, cursor
+    int *d_failed = nullptr;
+    SG_CUDA(cudaMalloc((void **)&d_keys, (size_t)nPos * 8)); SG_CUDA(cudaMalloc((void **)&d_keys2, (size_t)nPos * 8));
+    SG_CUDA(cudaMalloc((void **)&d_locs, (size_t)nPos * 4)); SG_CUDA(cudaMalloc((void **)&d_locs2, (size_t)nPos * 4));
+    const int grid = 148 * 8;
+    sg_build_emit_kernel<<<grid, 256>>>(d_bases, nPos, seedLen, d_keys, d_locs);
+    SG_CUDA(cudaGetLastError());
+    cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
+    cub::DoubleBuffer<uint32_t> vb(d_locs, d_locs2);
+    SG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (long long)nPos, 0, (int)(2 * seedLen + 1)));
+    SG_CUDA(cudaMalloc(&d_temp, tempBytes + 16));
+    SG_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, tempBytes, kb, vb, (long long)nPos, 0, (int)(2 * seedLen + 1)));
+    SG_CUDA(cudaDeviceSynchronize());
+    cudaFree(d_temp);
+    const unsigned long long *sk = kb.Current(); const uint32_t *sv = vb.Current();
+    cudaFree(kb.Alternate()); cudaFree(vb.Alternate());
+
+    SG_CUDA(cudaMalloc((void **)&d_stats, (size_t)(nTables + 3) * 8));
+    SG_CUDA(cudaMemset(d_stats, 0, (size_t)(nTables + 3) * 8));
+    sg_build_count_kernel<<<grid, 256>>>(sk, nPos, keyBits, seedLen, d_stats, d_stats + nTables, d_stats + nTables + 1);
+    SG_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> stats(nTables + 3);
+    SG_CUDA(cudaMemcpy(stats.data(), d_stats, (size_t)(nTables + 3) * 8, cudaMemcpyDeviceToHost));
+    const unsigned long long overflowWords = stats[nTables];
+    if ((unsigned long long)nBases + overflowWords > 0xfffffff0ULL) return sg_fail("snapgpu_index_build: ran out of overflow table namespace (GenomeIndex.cpp:688)");
+
+    // table sizes: the reference sizes tables at (1 + slack) x expected content with slack 0.3 (GenomeIndex.cpp:1084-1100)
+    std::vector<uint64_t> tstart(nTables), tsize(nTables);
+    uint64_t slots = 0;
+    for (uint32_t t = 0; t < nTables; t++) {
+        uint64_t sz = (uint64_t)((double)stats[t] * 1.3) + 1;
+        if (sz < 100) sz = 100;
+        tstart[t] = slots; tsize[t] = sz; slots += sz;
+    }
+    size_t hbm = 0;
+    SG_CUDA(cudaMalloc((void **)&ix->d_tables, slots * 8 + 16)); hbm += slots * 8 + 16;
+    sg_build_fill_kernel<<<grid, 256>>>((unsigned long long *)ix->d_tables, (long long)slots + 2, 0x00000000ffffffffULL);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMalloc((void **)&ix->d_tableStart, nTables * 8)); SG_CUDA(cudaMalloc((void **)&ix->d_tableSize, nTables * 8));
+    SG_CUDA(cudaMemcpy(ix->d_tableStart, tstart.data(), nTables * 8, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(ix->d_tableSize, tsize.data(), nTables * 8, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMalloc((void **)&ix->d_overflow, (size_t)(overflowWords + 4) * 4)); hbm += (size_t)(overflowWords + 4) * 4;
+    SG_CUDA(cudaMemset(ix->d_overflow, 0, (size_t)(overflowWords + 4) * 4));
+    SG_CUDA(cudaMalloc((void **)&d_failed, 4)); SG_CUDA(cudaMemset(d_failed, 0, 4));
+    sg_build_insert_kernel<<<grid, 256>>>(sk, sv, nPos, keyBits, seedLen, ix->d_tableStart, ix->d_tableSize, (unsigned long long *)ix->d_tables,
+                                          ix->d_overflow, d_stats + nTables + 2, nBases, d_failed);
+    SG_CUDA(cudaGetLastError());
+    int failed = 0;
+    SG_CUDA(cudaMemcpy(&failed, d_failed, 4, cudaMemcpyDeviceToHost));
+    cudaFree((void *)sk); cudaFree((void *)sv); cudaFree(d_stats); cudaFree(d_failed);
+    if (failed) return sg_fail("snapgpu_index_build: hash table overflow during insertion");
+
+    SG_CUDA(cudaMalloc((void **)&ix->d_contigStart, (size_t)nContigs * 8 + 16));
+    SG_CUDA(cudaMemcpy(ix->d_contigStart, contigStarts, (size_t)nContigs * 8, cudaMemcpyHostToDevice));
+    sg_init_tables(ix->h_tables_prob, seedLen);
+    SG_CUDA(cudaMalloc((void **)&ix->d_tables_prob, sizeof(SgTables)));
+    SG_CUDA(cudaMemcpy(ix->d_tables_prob, &ix->h_tables_prob, sizeof(SgTables), cudaMemcpyHostToDevice));
+    hbm += (size_t)nBases + 2 * SG_N_PADDING;
+
+    SgIndexView v;
+    memset(&v, 0, sizeof(v));
+    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.overflow = ix->d_overflow;
+    v.bases = d_bases; v.contigStart = ix->d_contigStart; v.nBases = nBases; v.altFirstLocation = LLONG_MAX;
+    v.overflowSize = overflowWords; v.nContigs = nContigs; v.seedLen = seedLen; v.keyBytes = keyBytes; v.nTables = nTables;
+    v.large = 0; v.entryBytes = 8; v.chromosomePadding = chromosomePadding; v.invalidValue = 0xffffffffu;
+    ix->view = v;
+    memset(&ix->info, 0, sizeof(ix->info));
+    ix->info.countOfBases = nBases; ix->info.seedLen = seedLen; ix->info.hashTableKeySize = keyBytes; ix->info.nHashTables = nTables;
+    ix->info.locationSize = 4; ix->info.largeHashTable = 0; ix->info.chromosomePadding = chromosomePadding; ix->info.nContigs = nContigs;
+    ix->info.overflowTableSize = overflowWords; ix->info.hashTableSlots = slots; ix->info.hbmBytes = hbm;
+    ix->h_tableStart = tstart; ix->h_tableSize = tsize;
+    ix->h_tableUsed.assign(stats.begin(), stats.begin() + nTables);
+    ix->h_contigStart.assign(contigStarts, contigStarts + nContigs);
+    for (uint32_t c = 0; c < nContigs; c++) { ix->h_contigName.push_back("chr" + std::to_string(c + 1)); ix->h_contigIsAlt.push_back(0); }
+    *out = ix;
+    return 0;
+}
+
+int snapgpu_index_build(const char *bases, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
+                        uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out)
+{
+    if (!bases || !contigStarts || !out || nContigs == 0) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(device)) return 1;
+    uint8_t *d_padded = nullptr;
+    SG_CUDA(cudaMalloc((void **)&d_padded, (size_t)nBases + 2 * SG_N_PADDING));
+    SG_CUDA(cudaMemset(d_padded, 'n', (size_t)nBases + 2 * SG_N_PADDING));
+    SG_CUDA(cudaMemcpy(d_padded + SG_N_PADDING, bases, (size_t)nBases, cudaMemcpyHostToDevice));
+    int rc = build_index_on_device(d_padded, nBases, contigStarts, nContigs, seedLen, chromosomePadding, device, out);
+    if (rc) cudaFree(d_padded);
+    return rc;
+}
+
+// Same, from bases already in HBM (d_bases: nBases bytes, device pointer); copies them into the index image.
+int snapgpu_index_build_device(const char *d_bases, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
+                               uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out)
+{
+    if (!d_bases || !contigStarts || !out || nContigs == 0) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(device)) return 1;
+    uint8_t *d_padded = nullptr;
+    SG_CUDA(cudaMalloc((void **)&d_padded, (size_t)nBases + 2 * SG_N_PADDING));
+    SG_CUDA(cudaMemset(d_padded, 'n', (size_t)nBases + 2 * SG_N_PADDING));
+    SG_CUDA(cudaMemcpy(d_padded + SG_N_PADDING, d_bases, (size_t)nBases, cudaMemcpyDeviceToDevice));
+    int rc = build_index_on_device(d_padded, nBases, contigStarts, nContigs, seedLen, chromosomePadding, device, out);
+    if (rc) cudaFree(d_padded);
+    return rc;
+}
+
+// Writes the index out in the reference's own 4-file directory format (v7.1: GenomeIndex.cpp:1007-1008 header,
+// HashTable.cpp:199-260 table headers, GenomeIndex.cpp:964-988 overflow, Genome.cpp:203-253 genome), so that the
+// stock `snap-aligner` can load an index built by snapgpu_index_build.
+int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
+{
+    if (!ix || !directory) return sg_fail("null argument");
+    if (ix->view.entryBytes != 8 && ix->view.entryBytes != 12) return sg_fail("snapgpu_index_save: unsupported entry geometry");
+    SG_CUDA(cudaSetDevice(ix->device));
+    std::string dir(directory);
+    std::string cmd = "mkdir -p '" + dir + "'";
+    if (system(cmd.c_str()) != 0) return sg_fail("snapgpu_index_save: cannot create directory");
+    const size_t CH = (size_t)256 << 20;
+    std::vector<uint8_t> buf(CH);
+    // Genome
+    {
+        FILE *f = fopen((dir + "/Genome").c_str(), "wb");
+        if (!f) return sg_fail("snapgpu_index_save: cannot write Genome");
+        fprintf(f, "%lld %d %d\n", (long long)ix->view.nBases, (int)ix->h_contigStart.size(), 1);
+        for (size_t c = 0; c < ix->h_contigStart.size(); c++) {
+            fprintf(f, "%lld %x %d %lld %x %d %d %s %s\n", (long long)ix->h_contigStart[c], ix->h_contigIsAlt[c] ? 1 : 0, (int)c, 0LL, 0,
+                    (int)ix->h_contigName[c].size(), 1, ix->h_contigName[c].c_str(), "*");
+        }
+        for (size_t off = 0; off < (size_t)ix->view.nBases; off += CH) {
+            size_t m = (size_t)ix->view.nBases - off < CH ? (size_t)ix->view.nBases - off : CH;
+            SG_CUDA(cudaMemcpy(buf.data(), ix->view.bases + off, m, cudaMemcpyDeviceToHost));
+            if (fwrite(buf.data(), 1, m, f) != m) { fclose(f); return sg_fail("snapgpu_index_save: short write"); }
+        }
+        fclose(f);
+    }
+    // OverflowTable
+    {
+        FILE *f = fopen((dir + "/OverflowTable").c_str(), "wb");
+        if (!f) return sg_fail("snapgpu_index_save: cannot write OverflowTable");
+        size_t total = (size_t)ix->view.overflowSize * 4;
+        for (size_t off = 0; off < total; off += CH) {
+            size_t m = total - off < CH ? total - off : CH;
+            SG_CUDA(cudaMemcpy(buf.data(), (const uint8_t *)ix->view.overflow + off, m, cudaMemcpyDeviceToHost));
+            if (fwrite(buf.data(), 1, m, f) != m) { fclose(f); return sg_fail("snapgpu_index_save: short write"); }
+        }
+        fclose(f);
+    }
+    // GenomeIndexHash
+    size_t hashBytes = 0;
+    {
+        FILE *f = fopen((dir + "/GenomeIndexHash").c_str(), "wb");
+        if (!f) return sg_fail("snapgpu_index_save: cannot write GenomeIndexHash");
+        const uint32_t eb = ix->view.entryBytes;
+        for (uint32_t t = 0; t < ix->view.nTables; t++) {
+            uint32_t magic = 0xb111b010u, ks = ix->view.keyBytes, vs = 4, vc = ix->view.large ? 2 : 1, inval = ix->view.invalidValue;
+            uint64_t tsz = ix->h_tableSize[t], used = t < ix->h_tableUsed.size() ? ix->h_tableUsed[t] : 0;
+            fwrite(&magic, 4, 1, f); fwrite(&tsz, 8, 1, f); fwrite(&used, 8, 1, f); fwrite(&ks, 4, 1, f); fwrite(&vs, 4, 1, f);
+            fwrite(&vc, 4, 1, f); fwrite(&inval, 4, 1, f);
+            hashBytes += 36;
+            size_t total = (size_t)tsz * eb;
+            const uint8_t *src = ix->view.tables + (size_t)ix->h_tableStart[t] * eb;
+            for (size_t off = 0; off < total; off += CH) {
+                size_t m = total - off < CH ? total - off : CH;
+                SG_CUDA(cudaMemcpy(buf.data(), src + off, m, cudaMemcpyDeviceToHost));
+                if (fwrite(buf.data(), 1, m, f) != m) { fclose(f); return sg_fail("snapgpu_index_save: short write"); }
+            }
+            hashBytes += total;
+        }
+        fclose(f);
+    }
+    {
+        FILE *f = fopen((dir + "/GenomeIndex").c_str(), "w");
+        if (!f) return sg_fail("snapgpu_index_save: cannot write GenomeIndex");
+        fprintf(f, "%d %d %d %lld %d %d %d %lld %d %d", 7, 1, (int)ix->view.nTables, (long long)ix->view.overflowSize, (int)ix->view.seedLen,
+                (int)ix->view.chromosomePadding, (int)ix->view.keyBytes, (long long)hashBytes, ix->view.large ? 0 : 1, 4);
+        fclose(f);
+    }
+    return 0;
+}
+
+int snapgpu_index_info_get(const snapgpu_index *idx, snapgpu_index_info *info)
+{
+    if (!idx || !info) return sg_fail("null argument");
+    *info = idx->info;
+    return 0;
+}
+
+void snapgpu_index_close(snapgpu_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaFree(ix->d_tables); cudaFree(ix->d_tableStart); cudaFree(ix->d_tableSize); cudaFree(ix->d_overflow);
+    cudaFree(ix->d_basesPadded); cudaFree(ix->d_contigStart); cudaFree(ix->d_tables_prob);
+    delete ix;
+}
+
+int snapgpu_lookup_seeds(const snapgpu_index *idx, const char *seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,
+                         int64_t *nHits, uint32_t *hits, uint32_t *probes)
+{
+    if (!idx || !seeds || !nHits) return sg_fail("null argument");
+    if (require_device(idx->device)) return 1;
+    if (nSeeds <= 0) return 0;
+    uint8_t *d_seeds = nullptr; long long *d_nHits = nullptr; uint32_t *d_hits = nullptr, *d_probes = nullptr;
+    const size_t sb = (size_t)nSeeds * idx->view.seedLen;
+    SG_CUDA(cudaMalloc((void **)&d_seeds, sb));
+    SG_CUDA(cudaMalloc((void **)&d_nHits, (size_t)nSeeds * 2 * 8));
+    if (hits) SG_CUDA(cudaMalloc((void **)&d_hits, (size_t)nSeeds * 2 * maxHitsPerSeed * 4 + 16));
+    if (probes) SG_CUDA(cudaMalloc((void **)&d_probes, (size_t)nSeeds * 4));
+    SG_CUDA(cudaMemcpy(d_seeds, seeds, sb, cudaMemcpyHostToDevice));
+    int blocks = (int)((nSeeds * 32 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sg_lookup_kernel<<<blocks, 256>>>(idx->view, d_seeds, nSeeds, maxHitsPerSeed, d_nHits, d_hits, d_probes);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaDeviceSynchronize());
+    SG_CUDA(cudaMemcpy(nHits, d_nHits, (size_t)nSeeds * 2 * 8, cudaMemcpyDeviceToHost));
+    if (hits) SG_CUDA(cudaMemcpy(hits, d_hits, (size_t)nSeeds * 2 * maxHitsPerSeed * 4, cudaMemcpyDeviceToHost));
+    if (probes) SG_CUDA(cudaMemcpy(probes, d_probes, (size_t)nSeeds * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_seeds); cudaFree(d_nHits); cudaFree(d_hits); cudaFree(d_probes);
+    return 0;
+}
+
+// Device-resident variant used by bench.py's seed-phase roofline: everything already in HBM, launched on `stream`.
+int snapgpu_lookup_seeds_device(const snapgpu_index *idx, const char *d_seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,
+                                int64_t *d_nHits, uint32_t *d_hits, uint32_t *d_probes, void *cudaStream)
+{
+    if (!idx || !d_seeds || !d_nHits) return sg_fail("null argument");
+    if (nSeeds <= 0) return 0;
+    int blocks = (int)((nSeeds * 32 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    sg_lookup_kernel<<<blocks, 256, 0, (cudaStream_t)cudaStream>>>(idx->view, (const uint8_t *)d_seeds, nSeeds, maxHitsPerSeed,
+                                                                   (long long *)d_nHits, d_hits, d_probes);
+    SG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *params, int64_t maxBatchReads, snapgpu_aligner **out)
+{
+    if (!idx || !params || !out) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(idx->device)) return 1;
+    if (maxBatchReads <= 0) return sg_fail("maxBatchReads must be positive");
+    snapgpu_aligner *a = new (std::nothrow) snapgpu_aligner;
+    if (!a) return sg_fail("out of memory");
+    a->index = idx; a->device = idx->device; a->userParams = *params; a->maxBatchReads = maxBatchReads;
+    std::string err;
+    uint32_t maxReadLen = 400;
+    if (const char *e = getenv("SNAPGPU_MAX_READ_LEN")) maxReadLen = (uint32_t)atoi(e);
+    if (!sg_derive_params(*params, idx->view.seedLen, maxReadLen, a->params, err)) { delete a; return sg_fail("snapgpu_aligner_create: " + err); }
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, a->device));
+    a->numSMs = prop.multiProcessorCount;
+    a->blocksPerSM = 4;
+    if (const char *e = getenv("SNAPGPU_BLOCKS_PER_SM")) a->blocksPerSM = atoi(e) > 0 ? atoi(e) : 4;
+    a->nWorkers = a->numSMs * a->blocksPerSM * a->warpsPerBlock;
+    if ((int64_t)a->nWorkers > maxBatchReads) {
+        int blocks = (int)((maxBatchReads + a->warpsPerBlock - 1) / a->warpsPerBlock);
+        a->nWorkers = blocks * a->warpsPerBlock;
+    }
+    a->scratchBytesPerWorker = sg_align_up(sg_scratch_bytes(a->params), 256);
+    SG_CUDA(cudaMalloc((void **)&a->d_scratch, a->scratchBytesPerWorker * (size_t)a->nWorkers));
+    SG_CUDA(cudaMemset(a->d_scratch, 0, a->scratchBytesPerWorker * (size_t)a->nWorkers));
+    SG_CUDA(cudaMalloc((void **)&a->d_next, 8));
+    SG_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+    a->maxBatchBases = (size_t)maxBatchReads * (size_t)maxReadLen;
+    SG_CUDA(cudaMallocHost((void **)&a->h_bases, a->maxBatchBases));
+    SG_CUDA(cudaMallocHost((void **)&a->h_quals, a->maxBatchBases));
+    SG_CUDA(cudaMallocHost((void **)&a->h_offsets, (size_t)maxBatchReads * 8));
+    SG_CUDA(cudaMallocHost((void **)&a->h_lens, (size_t)maxBatchReads * 4));
+    SG_CUDA(cudaMallocHost((void **)&a->h_results, (size_t)maxBatchReads * sizeof(snapgpu_single_result)));
+    SG_CUDA(cudaMallocHost((void **)&a->h_counters, sizeof(snapgpu_counters)));
+    SG_CUDA(cudaMalloc((void **)&a->d_bases, a->maxBatchBases));
+    SG_CUDA(cudaMalloc((void **)&a->d_quals, a->maxBatchBases));
+    SG_CUDA(cudaMalloc((void **)&a->d_offsets, (size_t)maxBatchReads * 8));
+    SG_CUDA(cudaMalloc((void **)&a->d_lens, (size_t)maxBatchReads * 4));
+    SG_CUDA(cudaMalloc((void **)&a->d_results, (size_t)maxBatchReads * sizeof(snapgpu_single_result)));
+    SG_CUDA(cudaMalloc((void **)&a->d_counters, sizeof(snapgpu_counters)));
+    *out = a;
+    return 0;
+}
+
+void snapgpu_aligner_destroy(snapgpu_aligner *a)
+{
+    if (!a) return;
+    cudaSetDevice(a->device);
+    if (a->stream) { cudaStreamSynchronize(a->stream); cudaStreamDestroy(a->stream); }
+    cudaFree(a->d_scratch); cudaFree(a->d_next);
+    cudaFreeHost(a->h_bases); cudaFreeHost(a->h_quals); cudaFreeHost(a->h_offsets); cudaFreeHost(a->h_lens);
+    cudaFreeHost(a->h_results); cudaFreeHost(a->h_counters);
+    cudaFree(a->d_bases); cudaFree(a->d_quals); cudaFree(a->d_offsets); cudaFree(a->d_lens); cudaFree(a->d_results); cudaFree(a->d_counters);
+    delete a;
+}
+
+static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                        const uint32_t *d_lens, snapgpu_single_result *d_results, snapgpu_counters *d_counters, cudaStream_t st)
+{
+    SG_CUDA(cudaMemsetAsync(a->d_next, 0, 8, st));
+    int64_t workers = a->nWorkers;
+    if (workers > n) workers = n;
+    int blocks = (int)((workers + a->warpsPerBlock - 1) / a->warpsPerBlock);
+    if (blocks < 1) blocks = 1;
+    sg_align_kernel<<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, a->d_scratch,
+        a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, d_lens,
+        d_results, d_counters, a->d_next);
+    SG_CUDA(cudaGetLastError());
+    a->launches++;
+    return 0;
+}
+
+int snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                                const uint32_t *d_lens, snapgpu_single_result *d_results, snapgpu_counters *d_counters, void *cudaStream)
+{
+    if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results) return sg_fail("null argument");
+    if (n < 0) return sg_fail("negative read count");
+    if (n == 0) return 0;
+    SG_CUDA(cudaSetDevice(a->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : a->stream;
+    return launch_align(a, n, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters, st);
+}
+
+int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
+                         const uint32_t *lens, snapgpu_single_result *results, snapgpu_counters *counters)
+{
+    if (!a || !bases || !quals || !offsets || !lens || !results) return sg_fail("null argument");
+    if (n < 0 || n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads");
+    if (n == 0) return 0;
+    SG_CUDA(cudaSetDevice(a->device));
+    // pack into pinned staging (reads need not be contiguous in the caller's buffers)
+    size_t total = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (lens[i] > SNAPGPU_MAX_READ_LENGTH) return sg_fail("read longer than MAX_READ_LENGTH");
+        if (total + lens[i] > a->maxBatchBases) return sg_fail("batch holds more bases than the aligner was sized for");
+        memcpy(a->h_bases + total, bases + offsets[i], lens[i]);
+        memcpy(a->h_quals + total, quals + offsets[i], lens[i]);
+        a->h_offsets[i] = total;
+        a->h_lens[i] = lens[i];
+        total += lens[i];
+    }
+    cudaStream_t st = a->stream;
+    SG_CUDA(cudaMemcpyAsync(a->d_bases, a->h_bases, total, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(a->d_quals, a->h_quals, total, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(a->d_offsets, a->h_offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(a->d_lens, a->h_lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemsetAsync(a->d_counters, 0, sizeof(snapgpu_counters), st));
+    if (launch_align(a, n, a->d_bases, a->d_quals, a->d_offsets, a->d_lens, a->d_results, a->d_counters, st)) return 1;
+    SG_CUDA(cudaMemcpyAsync(a->h_results, a->d_results, (size_t)n * sizeof(snapgpu_single_result), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(a->h_counters, a->d_counters, sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    memcpy(results, a->h_results, (size_t)n * sizeof(snapgpu_single_result));
+    for (int64_t i = 0; i < n; i++) {
+        if (results[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+    }
+    if (counters) {
+        int64_t *dst = (int64_t *)counters; const int64_t *src = (const int64_t *)a->h_counters;
+        for (size_t k = 0; k < sizeof(snapgpu_counters) / 8; k++) dst[k] += src[k];
+    }
+    return 0;
+}
+
+int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a) { return a ? a->launches : 0; }
+
+static int leaf_scratch(int device, SgParams *p, int *threads, uint8_t **d_scratch, size_t *bytes, SgTables **d_tb)
+{
+    if (require_device(device)) return 1;
+    memset(p, 0, sizeof(*p));
+    p->poolSize = 1; p->tableSlots = 2; p->numWeightLists = 2; p->maxReadLen = 1000;
+    *bytes = sg_align_up(sg_scratch_bytes(*p), 256);
+    *threads = 64 * 32;
+    SG_CUDA(cudaMalloc((void **)d_scratch, *bytes * (size_t)*threads));
+    SgTables T;
+    sg_init_tables(T, 20);
+    SG_CUDA(cudaMalloc((void **)d_tb, sizeof(SgTables)));
+    SG_CUDA(cudaMemcpy(*d_tb, &T, sizeof(SgTables), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int snapgpu_test_lv(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf, uint64_t patBytes,
+                    const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out)
+{
+    SgParams p; int threads; uint8_t *d_scratch = nullptr; size_t bytes; SgTables *d_tb = nullptr;
+    if (leaf_scratch(device, &p, &threads, &d_scratch, &bytes, &d_tb)) return 1;
+    uint8_t *d_text, *d_pat, *d_qual; snapgpu_lv_job *d_jobs; snapgpu_lv_out *d_out;
+    SG_CUDA(cudaMalloc((void **)&d_text, textBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_pat, patBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_qual, patBytes + 16));
+    SG_CUDA(cudaMalloc((void **)&d_jobs, (size_t)nJobs * sizeof(*jobs) + 16)); SG_CUDA(cudaMalloc((void **)&d_out, (size_t)nJobs * sizeof(*out) + 16));
+    SG_CUDA(cudaMemcpy(d_text, textBuf, textBytes, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_pat, patBuf, patBytes, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_qual, qualBuf, patBytes, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_jobs, jobs, (size_t)nJobs * sizeof(*jobs), cudaMemcpyHostToDevice));
+    sg_test_lv_kernel<<<threads / 32, 32>>>(d_tb, p, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaDeviceSynchronize());
+    SG_CUDA(cudaMemcpy(out, d_out, (size_t)nJobs * sizeof(*out), cudaMemcpyDeviceToHost));
+    cudaFree(d_text); cudaFree(d_pat); cudaFree(d_qual); cudaFree(d_jobs); cudaFree(d_out); cudaFree(d_scratch); cudaFree(d_tb);
+    return 0;
+}
+
+int snapgpu_test_ag(int device, const snapgpu_ag_params *ap, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
+                    uint64_t patBytes, const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out)
+{
+    SgParams p; int threads; uint8_t *d_scratch = nullptr; size_t bytes; SgTables *d_tb = nullptr;
+    if (leaf_scratch(device, &p, &threads, &d_scratch, &bytes, &d_tb)) return 1;
+    SgAgParams P = sg_ag_params(ap->matchReward, ap->subPenalty, ap->gapOpenPenalty, ap->gapExtendPenalty, ap->fivePrimeEndBonus, ap->threePrimeEndBonus);
+    uint8_t *d_text, *d_pat, *d_qual; snapgpu_ag_job *d_jobs; snapgpu_ag_out *d_out;
+    SG_CUDA(cudaMalloc((void **)&d_text, textBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_pat, patBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_qual, patBytes + 16));
+    SG_CUDA(cudaMalloc((void **)&d_jobs, (size_t)nJobs * sizeof(*jobs) + 16)); SG_CUDA(cudaMalloc((void **)&d_out, (size_t)nJobs * sizeof(*out) + 16));
+    SG_CUDA(cudaMemcpy(d_text, textBuf, textBytes, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_pat, patBuf, patBytes, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_qual, qualBuf, patBytes, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_jobs, jobs, (size_t)nJobs * sizeof(*jobs), cudaMemcpyHostToDevice));
+    sg_test_ag_kernel<<<threads / 32, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaDeviceSynchronize());
+    SG_CUDA(cudaMemcpy(out, d_out, (size_t)nJobs * sizeof(*out), cudaMemcpyDeviceToHost));
+    cudaFree(d_text); cudaFree(d_pat); cudaFree(d_qual); cudaFree(d_jobs); cudaFree(d_out); cudaFree(d_scratch); cudaFree(d_tb);
+    return 0;
+}
+
+} // extern "C"

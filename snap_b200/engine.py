@@ -1,0 +1,240 @@
+"""Python host-side mirror of the C ABI in include/snapgpu.h (ctypes over snap_b200/csrc/libsnapgpu.so).
+
+This is plumbing for tests and bench.py; the product is the CUDA library.  There is no CPU path here: if the
+library is missing, or no CUDA device is usable, every call raises.
+Names mirror the reference's: Index ~ GenomeIndex (loadFromDirectory / lookupSeed32), SingleAligner ~ the
+per-thread BaseAligner loop of SingleAligner.cpp:197-338.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libsnapgpu.so")
+
+
+class SnapGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """snapgpu_params (AlignerOptions / AlignerContext fields the hot path reads)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("maxHits", C.c_uint32), ("maxDist", C.c_uint32),
+        ("numSeedsFromCommandLine", C.c_uint32), ("seedCoverage", C.c_double),
+        ("minWeightToCheck", C.c_uint32), ("extraSearchDepth", C.c_uint32), ("minReadLength", C.c_uint32),
+        ("useAffineGap", C.c_int32), ("matchReward", C.c_int32), ("subPenalty", C.c_int32),
+        ("gapOpenPenalty", C.c_int32), ("gapExtendPenalty", C.c_int32), ("fivePrimeEndBonus", C.c_int32),
+        ("threePrimeEndBonus", C.c_int32), ("noUkkonen", C.c_int32), ("noOrderedEvaluation", C.c_int32),
+        ("noTruncation", C.c_int32), ("noEditDistance", C.c_int32), ("noBandedAffineGap", C.c_int32),
+        ("altAwareness", C.c_int32), ("maxScoreGapToPreferNonAltAlignment", C.c_int32),
+        ("explorePopularSeeds", C.c_int32), ("stopOnFirstHit", C.c_int32),
+        ("maxSecondaryAlignmentAdditionalEditDistance", C.c_int32), ("ignoreAlignmentAdjustmentsForOm", C.c_int32),
+    ]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [
+        ("countOfBases", C.c_int64), ("seedLen", C.c_uint32), ("hashTableKeySize", C.c_uint32),
+        ("nHashTables", C.c_uint32), ("locationSize", C.c_uint32), ("largeHashTable", C.c_uint32),
+        ("chromosomePadding", C.c_uint32), ("nContigs", C.c_uint32), ("reserved", C.c_uint32),
+        ("overflowTableSize", C.c_uint64), ("hashTableSlots", C.c_uint64), ("hbmBytes", C.c_uint64),
+    ]
+
+
+RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("direction", "<i4"), ("location", "<i8"), ("origLocation", "<i8"),
+    ("score", "<i4"), ("scorePriorToClipping", "<i4"), ("mapq", "<i4"), ("clippingForReadAdjustment", "<i4"),
+    ("usedAffineGapScoring", "<i4"), ("basesClippedBefore", "<i4"), ("basesClippedAfter", "<i4"),
+    ("agScore", "<i4"), ("supplementary", "<i4"), ("seedOffset", "<i4"),
+    ("matchProbability", "<f8"), ("probabilityAllCandidates", "<f8"),
+    ("popularSeedsSkipped", "<u4"), ("reserved", "<u4"),
+])
+COUNTER_FIELDS = ["totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups",
+                  "nHashEntriesProbed", "nOverflowWordsRead", "lvCalls", "affineGapCalls",
+                  "nHitsIgnoredBecauseOfTooHighPopularity"]
+N_COUNTERS = len(COUNTER_FIELDS) + 71
+
+# every symbol include/snapgpu.h declares
+EXPORTS = [
+    "snapgpu_last_error", "snapgpu_abi_version", "snapgpu_device_count", "snapgpu_params_default",
+    "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close",
+    "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
+    "snapgpu_align_single_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SnapGpuError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.snapgpu_last_error.restype = C.c_char_p
+        L.snapgpu_params_default.argtypes = [C.POINTER(Params)]
+        L.snapgpu_index_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.snapgpu_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                          C.POINTER(C.c_void_p)]
+        L.snapgpu_index_build_device.argtypes = L.snapgpu_index_build.argtypes
+        L.snapgpu_lookup_seeds_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_index_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.snapgpu_index_info_get.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
+        L.snapgpu_index_close.argtypes = [C.c_void_p]
+        L.snapgpu_lookup_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_aligner_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.POINTER(C.c_void_p)]
+        L.snapgpu_aligner_destroy.argtypes = [C.c_void_p]
+        L.snapgpu_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.snapgpu_align_single_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        L.snapgpu_aligner_launch_count.restype = C.c_int64
+        L.snapgpu_aligner_launch_count.argtypes = [C.c_void_p]
+        L.snapgpu_test_lv.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.snapgpu_test_ag.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                      C.c_int64, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SnapGpuError(lib().snapgpu_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().snapgpu_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def counters_dict(arr: np.ndarray) -> dict:
+    d = {k: int(arr[i]) for i, k in enumerate(COUNTER_FIELDS)}
+    d["mapqHistogram"] = [int(x) for x in arr[len(COUNTER_FIELDS):]]
+    return d
+
+
+class Index:
+    """The genome index resident in HBM (GenomeIndex::loadFromDirectory, reference GenomeIndex.cpp:1838)."""
+
+    def __init__(self, handle, device):
+        self.handle = handle
+        self.device = device
+
+    @staticmethod
+    def open(directory: str, device: int = 0) -> "Index":
+        h = C.c_void_p()
+        _check(lib().snapgpu_index_open(directory.encode(), device, C.byref(h)))
+        return Index(h, device)
+
+    @staticmethod
+    def build(bases_with_padding: np.ndarray, contig_starts, seed_len: int = 20, chromosome_padding: int = 2000,
+              device: int = 0) -> "Index":
+        """Builds the lookup structure on the device from padded bases (see snapgpu_index_build)."""
+        h = C.c_void_p()
+        b = np.ascontiguousarray(bases_with_padding, dtype=np.uint8)
+        cs = np.ascontiguousarray(contig_starts, dtype=np.int64)
+        _check(lib().snapgpu_index_build(_p(b), b.size, _p(cs), cs.size, seed_len, chromosome_padding, device, C.byref(h)))
+        return Index(h, device)
+
+    @staticmethod
+    def build_device(d_bases_ptr: int, n_bases: int, contig_starts, seed_len: int = 20, chromosome_padding: int = 2000,
+                     device: int = 0) -> "Index":
+        """Like build(), from bases already resident in HBM (device pointer as int)."""
+        h = C.c_void_p()
+        cs = np.ascontiguousarray(contig_starts, dtype=np.int64)
+        _check(lib().snapgpu_index_build_device(C.c_void_p(d_bases_ptr), n_bases, _p(cs), cs.size, seed_len, chromosome_padding, device,
+                                                C.byref(h)))
+        return Index(h, device)
+
+    def lookup_seeds_device(self, d_seeds: int, n: int, d_nhits: int, d_hits: int = 0, d_probes: int = 0, max_hits: int = 0, stream: int = 0):
+        _check(lib().snapgpu_lookup_seeds_device(self.handle, C.c_void_p(d_seeds), n, max_hits, C.c_void_p(d_nhits), C.c_void_p(d_hits),
+                                                 C.c_void_p(d_probes), C.c_void_p(stream)))
+
+    def save(self, directory: str) -> None:
+        """Writes a reference-format index directory (loadable by stock `snap-aligner`)."""
+        _check(lib().snapgpu_index_save(self.handle, directory.encode()))
+
+    def info(self) -> IndexInfo:
+        info = IndexInfo()
+        _check(lib().snapgpu_index_info_get(self.handle, C.byref(info)))
+        return info
+
+    def lookup_seeds(self, seeds: np.ndarray, n: int, max_hits: int = 512, want_hits: bool = True):
+        """Batched lookupSeed32 (reference GenomeIndex.cpp:2095)."""
+        nh = np.zeros(2 * n, dtype=np.int64)
+        hits = np.zeros(2 * n * max_hits, dtype=np.uint32) if want_hits else None
+        probes = np.zeros(n, dtype=np.uint32)
+        _check(lib().snapgpu_lookup_seeds(self.handle, _p(np.ascontiguousarray(seeds, dtype=np.uint8)), n, max_hits, _p(nh), _p(hits), _p(probes)))
+        return nh.reshape(n, 2), (hits.reshape(n, 2, max_hits) if want_hits else None), probes
+
+    def close(self):
+        if self.handle:
+            lib().snapgpu_index_close(self.handle)
+            self.handle = None
+
+
+class SingleAligner:
+    """One per host thread, like BaseAligner (reference BaseAligner.h:19-20)."""
+
+    def __init__(self, index: Index, params: Params | None = None, max_batch_reads: int = 1 << 20):
+        self.index = index
+        self.params = params if params is not None else default_params()
+        h = C.c_void_p()
+        _check(lib().snapgpu_aligner_create(index.handle, C.byref(self.params), max_batch_reads, C.byref(h)))
+        self.handle = h
+        self.max_batch_reads = max_batch_reads
+
+    def align(self, batch):
+        """Host buffers in, host results out (copies inside): snapgpu_align_single."""
+        res = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        ctr = np.zeros(N_COUNTERS, dtype=np.int64)
+        done = 0
+        while done < batch.n:
+            m = min(self.max_batch_reads, batch.n - done)
+            sub_off = batch.offsets[done:done + m]
+            sub_len = batch.lens[done:done + m]
+            _check(lib().snapgpu_align_single(self.handle, m, _p(batch.bases), _p(batch.quals), _p(sub_off), _p(sub_len),
+                                               C.c_void_p(res.ctypes.data + done * RESULT_DTYPE.itemsize), _p(ctr)))
+            done += m
+        return res, counters_dict(ctr)
+
+    def align_device(self, n, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters=0, stream=0):
+        """Device pointers (ints) in; enqueues on `stream`; no synchronisation: snapgpu_align_single_device."""
+        _check(lib().snapgpu_align_single_device(self.handle, n, C.c_void_p(d_bases), C.c_void_p(d_quals), C.c_void_p(d_offsets),
+                                                  C.c_void_p(d_lens), C.c_void_p(d_results), C.c_void_p(d_counters), C.c_void_p(stream)))
+
+    def launch_count(self) -> int:
+        return int(lib().snapgpu_aligner_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib().snapgpu_aligner_destroy(self.handle)
+            self.handle = None
+
+
+def test_lv(text, pat, qual, jobs, out_dtype, device=0):
+    out = np.zeros(jobs.size, dtype=out_dtype)
+    _check(lib().snapgpu_test_lv(device, _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out)))
+    return out
+
+
+def test_ag(text, pat, qual, jobs, out_dtype, params, device=0):
+    out = np.zeros(jobs.size, dtype=out_dtype)
+    params = np.ascontiguousarray(params, dtype=np.int32)
+    _check(lib().snapgpu_test_ag(device, _p(params), _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out)))
+    return out

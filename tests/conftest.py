@@ -1,0 +1,94 @@
+"""Shared fixtures.  `-m "not gpu"` runs here (no GPU): oracle vs golden vectors, host-simulated engine headers vs
+the compiled reference, C-ABI surface, gloo sharding.  `-m gpu` runs on a B200 and goes through the C ABI."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    from oracle import reflib as r
+    if not r.available():
+        pytest.skip("oracle/_ref/libsnapref.so not built (needs /root/reference once: make -C oracle ref)")
+    return r
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(HERE, "golden")
+
+
+class SmallCfg:
+    """A small repeat-bearing reference with a reference-built index directory (default + -large) and read sets."""
+
+    def __init__(self, tmp, reflib):
+        from snap_b200 import synth
+        self.dir = str(tmp)
+        self.contigs = synth.make_contigs(3, 120_000, seed=31, repeat_frac=0.25)
+        self.fasta = os.path.join(self.dir, "ref.fa")
+        synth.write_fasta(self.fasta, self.contigs)
+        self.idx = os.path.join(self.dir, "idx")
+        self.idx_large = os.path.join(self.dir, "idxL")
+        synth.build_reference_index(reflib.SNAP_ALIGNER, self.fasta, self.idx)
+        synth.build_reference_index(reflib.SNAP_ALIGNER, self.fasta, self.idx_large, large=True)
+        self.reads = {
+            "std150": synth.make_reads(self.contigs, 1500, 150, seed=32),
+            "noisy150": synth.make_reads(self.contigs, 1500, 150, seed=33, sub_rate=0.04, ins_rate=0.006, del_rate=0.006,
+                                         n_run_frac=0.1, short_frac=0.1, random_frac=0.05),
+            "indel100": synth.make_reads(self.contigs, 1000, 100, seed=34, sub_rate=0.01, ins_rate=0.01, del_rate=0.01),
+            "long250": synth.make_reads(self.contigs, 500, 250, seed=35, sub_rate=0.02, ins_rate=0.002, del_rate=0.002),
+        }
+
+    def padded_bases(self):
+        """Genome as SNAP lays it out: 2000 'n' before each contig and at the end (FASTA.cpp:362-391)."""
+        parts, starts, pos = [], [], 0
+        for c in self.contigs:
+            parts.append(np.full(2000, ord("n"), dtype=np.uint8)); pos += 2000
+            starts.append(pos)
+            parts.append(c); pos += c.size
+        parts.append(np.full(2000, ord("n"), dtype=np.uint8))
+        return np.concatenate(parts), np.array(starts, dtype=np.int64)
+
+
+@pytest.fixture(scope="session")
+def small_cfg(tmp_path_factory, reflib):
+    return SmallCfg(tmp_path_factory.mktemp("smallcfg"), reflib)
+
+
+def differing(want: np.ndarray, got: np.ndarray) -> list[int]:
+    """Indices whose result records differ bytewise (doubles bit-for-bit).  Reads both sides report NotFound for are
+    equal regardless of the remaining fields (the reference leaves them uninitialised on its early returns,
+    BaseAligner.cpp:360-366, :398-402)."""
+    out = []
+    for i in range(len(want)):
+        if want[i]["status"] == 0 and got[i]["status"] == 0:
+            continue
+        if want[i].tobytes() != got[i].tobytes():
+            out.append(i)
+    return out
+
+
+OPTION_SETS = {
+    "default_d14": dict(maxDist=14),
+    "noag_d14": dict(maxDist=14, useAffineGap=0),
+    "ne_d20": dict(maxDist=20, noEditDistance=1, useAffineGap=0),
+    "d8_h20": dict(maxDist=8, maxHits=20),
+    "coverage": dict(maxDist=14, numSeedsFromCommandLine=0, seedCoverage=4.0),
+    "esd3_ms2": dict(maxDist=14, extraSearchDepth=3, minWeightToCheck=2),
+    "nobanded": dict(maxDist=14, noBandedAffineGap=1),
+    "stopfirst": dict(maxDist=14, stopOnFirstHit=1),
+}

@@ -4,6 +4,7 @@
 // (`-m "not gpu"`) diff the restated state machine, LV and affine-gap code against the compiled reference
 // without a GPU.  This library is built into tests/_build/ and is never loaded by the snap_b200 package:
 // the product path has no CPU fallback.
+#define SG_AG_POISON_CHECK 1
 #include <string>
 #include <vector>
 #include <string.h>
@@ -111,8 +112,11 @@ void hs_lv_batch(const char *textBuf, const char *patBuf, const char *qualBuf, c
     }
 }
 
+// poisoned[j] (optional): 1 if the traceback of job j read a cell this call never wrote -- on such inputs the
+// reference reads state left behind by *earlier* calls (its backtraceAction array is never cleared), i.e. its result
+// is history-dependent and no restatement can match it.
 void hs_ag_batch(const snapgpu_ag_params *ap, const char *textBuf, const char *patBuf, const char *qualBuf, const snapgpu_ag_job *jobs,
-                 int64_t nJobs, snapgpu_ag_out *out)
+                 int64_t nJobs, snapgpu_ag_out *out, int *poisoned)
 {
     SgTables T; sg_init_tables(T, 20);
     SgParams p; memset(&p, 0, sizeof(p));
@@ -121,11 +125,13 @@ void hs_ag_batch(const snapgpu_ag_params *ap, const char *textBuf, const char *p
     SgAgParams P = sg_ag_params(ap->matchReward, ap->subPenalty, ap->gapOpenPenalty, ap->gapExtendPenalty, ap->fivePrimeEndBonus, ap->threePrimeEndBonus);
     for (int64_t j = 0; j < nJobs; j++) {
         SgAgResult r;
+        r.agScore = -1; r.textOffset = 0; r.patternOffset = 0; r.nEdits = 0; r.matchProbability = 0.0;
         sg_ag_compute(T, s, P, jobs[j].dir, jobs[j].banded != 0, (const uint8_t *)textBuf + jobs[j].textOff, jobs[j].textLen,
                       (const uint8_t *)patBuf + jobs[j].patOff, (const uint8_t *)qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].w,
                       jobs[j].scoreInit, jobs[j].isRC != 0, jobs[j].useClippingOptimizations != 0, &r);
         out[j].agScore = r.agScore; out[j].textOffset = r.textOffset; out[j].patternOffset = r.patternOffset; out[j].nEdits = r.nEdits;
         out[j].matchProbability = r.matchProbability;
+        if (poisoned) poisoned[j] = r.poisoned;
     }
 }
 

@@ -44,7 +44,7 @@ def lib():
         L.hs_mapq.restype = C.c_int
         L.hs_mapq.argtypes = [C.c_double, C.c_double, C.c_int]
         L.hs_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
-        L.hs_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.hs_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
         L.hs_aligner_create.restype = C.c_void_p
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
@@ -106,6 +106,7 @@ def lv_batch(text, pat, qual, jobs, out_dtype):
 
 def ag_batch(text, pat, qual, jobs, out_dtype, params):
     out = np.zeros(jobs.size, dtype=out_dtype)
+    poisoned = np.zeros(jobs.size, dtype=np.int32)
     params = np.ascontiguousarray(params, dtype=np.int32)
-    lib().hs_ag_batch(_p(params), _p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))
-    return out
+    lib().hs_ag_batch(_p(params), _p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out), _p(poisoned))
+    return out, poisoned

@@ -1,0 +1,219 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (snap_b200.engine -> libsnapgpu.so), against the
+compiled reference (oracle/_ref, when its prebuilt files travelled to the box) and against the committed golden
+fixtures.  Bit-exact for every field; doubles compared bitwise."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import jobs as J
+from conftest import OPTION_SETS, differing
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from snap_b200 import engine as e
+    assert e.lib().snapgpu_device_count() >= 1, "no CUDA device: the CUDA path has no fallback"
+    return e
+
+
+@pytest.fixture(scope="module")
+def gidx(engine, small_cfg):
+    ix = engine.Index.open(small_cfg.idx)
+    yield ix
+    ix.close()
+
+
+def test_unit_vectors_cuda(engine, golden_dir):
+    """The reference's own LV / affine-gap known-answer vectors on the CUDA leaves."""
+    v = json.load(open(os.path.join(golden_dir, "ref_unit_vectors.json")))
+    for e in v["lv"]:
+        text = np.frombuffer(b"n" * 64 + e["text"].encode() + b"\0" * 64, dtype=np.uint8)
+        pat = np.frombuffer(e["pattern"].encode() + b"\0" * 16, dtype=np.uint8)
+        qual = np.full(pat.size, ord("5"), dtype=np.uint8)
+        job = np.zeros(1, dtype=J.LV_JOB)
+        job[0] = (64, 0, e["textLen"], e["patternLen"], e["k"], 1)
+        assert int(engine.test_lv(text, pat, qual, job, J.LV_OUT)[0]["score"]) == e["expected"], e
+    for e in v["ag"]:
+        text = np.frombuffer(b"n" * 64 + e["text"].encode() + b"n" * 64, dtype=np.uint8)
+        pat = np.frombuffer(e["pattern"].encode() + b"A" * 8, dtype=np.uint8)
+        qual = np.full(pat.size, ord("2"), dtype=np.uint8)
+        job = np.zeros(1, dtype=J.AG_JOB)
+        job[0] = (64, 0, e["textLen"], e["patternLen"], e["w"], e["scoreInit"], 1, 0, 0, 0)
+        assert int(engine.test_ag(text, pat, qual, job, J.AG_OUT, v["ag_params"])[0]["agScore"]) == e["expected"], e
+
+
+def test_leaf_golden_lv(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "leaf_lv.npz"))
+    got = engine.test_lv(g["text"], g["pat"], g["qual"], g["jobs"], J.LV_OUT)
+    assert J.same_out(g["out"], got).all()
+
+
+def test_leaf_golden_ag(engine, golden_dir):
+    """One job per thread, each thread with its own (initially zero) traceback array: jobs whose reference answer depends
+    on bits left by the *previous* job of a sequential run are not comparable here and are skipped (they are covered,
+    with matching history, by the CPU-side fuzz and by the whole-read tests)."""
+    g = np.load(os.path.join(golden_dir, "leaf_ag.npz"))
+    got = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, [1, 4, 6, 1, 10, 7])
+    same = J.same_out(g["out"], got)
+    assert (~same).sum() <= 0.01 * same.size
+    assert (g["out"]["agScore"] == got["agScore"]).all()
+    assert (g["out"]["textOffset"] == got["textOffset"]).all() and (g["out"]["patternOffset"] == got["patternOffset"]).all()
+
+
+def test_lookup_matches_reference(engine, gidx, small_cfg, reflib):
+    ridx = reflib.RefIndex(small_cfg.idx)
+    rb = small_cfg.reads["noisy150"]
+    seeds = []
+    for i in range(600):
+        b = rb.read(i)[0]
+        if len(b) >= 60:
+            seeds += [b[0:20], b[37:57]]
+    arr = np.frombuffer(b"".join(seeds), dtype=np.uint8)
+    nh, hits, probes = gidx.lookup_seeds(arr, len(seeds), 512)
+    for i, s in enumerate(seeds):
+        a = ridx.lookup(s, 512)
+        assert (a[0], a[1]) == (nh[i, 0], nh[i, 1]), (i, s)
+        assert np.array_equal(a[2], hits[i, 0, :min(a[0], 512)]) and np.array_equal(a[3], hits[i, 1, :min(a[1], 512)])
+        if b"N" not in s:
+            assert a[4] + 2 == probes[i]
+
+
+def test_device_built_index_equals_reference_index(engine, gidx, small_cfg):
+    """snapgpu_index_build: same hit sets in the same (descending) order as the reference-built directory, for every
+    seed of a few hundred reads and their reverse complements; and whole-read results identical."""
+    bases, starts = small_cfg.padded_bases()
+    bix = engine.Index.build(bases, starts, seed_len=20, chromosome_padding=2000)
+    a, b = gidx.info(), bix.info()
+    assert (a.countOfBases, a.seedLen, a.nHashTables, a.overflowTableSize) == (b.countOfBases, b.seedLen, b.nHashTables, b.overflowTableSize)
+    rb = small_cfg.reads["std150"]
+    seeds = [rb.read(i)[0][o:o + 20] for i in range(400) for o in (0, 33, 77, 130)]
+    arr = np.frombuffer(b"".join(seeds), dtype=np.uint8)
+    n1, h1, _ = gidx.lookup_seeds(arr, len(seeds), 400)
+    n2, h2, _ = bix.lookup_seeds(arr, len(seeds), 400)
+    assert np.array_equal(n1, n2)
+    for i in range(len(seeds)):
+        for d in range(2):
+            k = min(int(n1[i, d]), 400)
+            assert np.array_equal(h1[i, d, :k], h2[i, d, :k])
+    p = engine.default_params(maxDist=14)
+    r1, _ = engine.SingleAligner(gidx, p, 4096).align(small_cfg.reads["noisy150"])
+    r2, _ = engine.SingleAligner(bix, p, 4096).align(small_cfg.reads["noisy150"])
+    assert differing(r1, r2) == []
+    bix.close()
+
+
+@pytest.mark.parametrize("opt", list(OPTION_SETS))
+def test_whole_reads_match_reference(engine, gidx, small_cfg, reflib, opt):
+    kw = OPTION_SETS[opt]
+    al = engine.SingleAligner(gidx, engine.default_params(**kw), 4096)
+    ridx = reflib.RefIndex(small_cfg.idx)
+    for name, rb in small_cfg.reads.items():
+        ral = reflib.RefSingleAligner(ridx, reflib.default_params(**kw))
+        want, wctr = ral.align(rb)
+        ral.close()
+        got, g = al.align(rb)
+        assert differing(want, got) == [], (opt, name)
+        for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "nHashEntriesProbed",
+                  "lvCalls", "affineGapCalls", "nHitsIgnoredBecauseOfTooHighPopularity", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, name, k)
+    assert al.launch_count() >= len(small_cfg.reads)
+    al.close()
+
+
+def test_large_index(engine, small_cfg, reflib):
+    ix = engine.Index.open(small_cfg.idx_large)
+    assert ix.info().largeHashTable == 1
+    rb = small_cfg.reads["noisy150"]
+    got, _ = engine.SingleAligner(ix, engine.default_params(maxDist=14), 4096).align(rb)
+    want, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx_large), reflib.default_params(maxDist=14)).align(rb)
+    assert differing(want, got) == []
+    ix.close()
+
+
+def test_golden_e2e_fixture(engine, golden_dir):
+    """No reference needed: the index is built on the device from the fixture's genome."""
+    from snap_b200 import synth
+    g = np.load(os.path.join(golden_dir, "e2e_small.npz"))
+    parts, starts, pos = [], [], 0
+    for c in (g["contig0"], g["contig1"]):
+        parts.append(np.full(2000, ord("n"), dtype=np.uint8)); pos += 2000
+        starts.append(pos); parts.append(c); pos += c.size
+    parts.append(np.full(2000, ord("n"), dtype=np.uint8))
+    ix = engine.Index.build(np.concatenate(parts), starts)
+    reads = synth.ReadBatch(g["bases"], g["quals"], g["offsets"], g["lens"])
+    for name in ("default_d14", "noag_d14", "ne_d20"):
+        got, ctr = engine.SingleAligner(ix, engine.default_params(**OPTION_SETS[name]), 1024).align(reads)
+        assert differing(g["res_" + name], got) == [], name
+        want_ctr = dict(zip(["totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "nHashEntriesProbed",
+                             "nOverflowWordsRead", "lvCalls", "affineGapCalls", "nHitsIgnoredBecauseOfTooHighPopularity"], g["ctr_" + name]))
+        for k in ("singleHits", "multiHits", "notFound", "nHashTableLookups", "lvCalls", "affineGapCalls"):
+            assert int(want_ctr[k]) == ctr[k], (name, k)
+    ix.close()
+
+
+def test_edge_reads(engine, gidx, small_cfg, reflib):
+    from snap_b200 import synth
+    c = small_cfg.contigs[0]
+    L = 400
+    reads = [
+        (b"ACGTACGTAC", b"5" * 10), (c[100:149].tobytes(), b"I" * 49), (c[100:150].tobytes(), b"I" * 50),
+        (b"N" * 100, b"5" * 100),
+        (bytes(c[1000:1100].tobytes()[:9] + b"N" + c[1010:1100].tobytes()), b"5" * 100),
+        (b"".join(c[2000 + 20 * i: 2000 + 20 * i + 19].tobytes() + b"N" for i in range(5)), b"5" * 100),
+        (c[5000:5000 + L].tobytes(), b"H" * L),
+        (synth.revcomp(c[7000:7150]).tobytes(), b"#" * 150),
+        (c[0:150].tobytes(), b"5" * 150), (c[c.size - 150:].tobytes(), b"5" * 150),
+        (np.concatenate([c[c.size - 80:], small_cfg.contigs[1][:70]]).tobytes(), b"5" * 150),
+    ]
+    rb = synth.ReadBatch.from_lists(reads)
+    p = dict(maxDist=14)
+    want, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params(**p)).align(rb)
+    al = engine.SingleAligner(gidx, engine.default_params(**p), 64)
+    got, _ = al.align(rb)
+    assert differing(want, got) == []
+    empty = synth.ReadBatch.from_lists([])
+    res, ctr = al.align(empty)
+    assert len(res) == 0 and ctr["totalReads"] == 0
+    with pytest.raises(engine.SnapGpuError):
+        al.align(synth.ReadBatch.from_lists([(b"A" * 401, b"5" * 401)]))     # longer than the configured maximum
+    al.close()
+
+
+def test_properties_at_scale(engine, small_cfg):
+    """Size-independent properties on a larger batch (no oracle): (1) results do not depend on batch order or on how the
+    batch is split across launches; (2) reads cut from the reference align back to where they came from;
+    (3) a read and its reverse complement land on the same location with opposite direction; (4) the MAPQ histogram
+    sums to the number of aligned reads."""
+    from snap_b200 import synth
+    bases, starts = small_cfg.padded_bases()
+    ix = engine.Index.build(bases, starts)
+    n = 60000
+    rb = synth.make_reads(small_cfg.contigs, n, 150, seed=77)
+    al = engine.SingleAligner(ix, engine.default_params(maxDist=14), 1 << 16)
+    r1, c1 = al.align(rb)
+    perm = np.random.default_rng(5).permutation(n)
+    shuffled = synth.ReadBatch.from_lists([rb.read(int(i)) for i in perm])
+    r2, _ = al.align(shuffled)
+    inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+    assert differing(r1, r2[inv]) == []
+    small = engine.SingleAligner(ix, engine.default_params(maxDist=14), 7000)
+    r3, c3 = small.align(rb)
+    assert differing(r1, r3) == [] and c1["lvCalls"] == c3["lvCalls"] and small.launch_count() == (n + 6999) // 7000
+    aligned = r1["status"] != 0
+    assert aligned.mean() > 0.995
+    start = np.array(starts)[rb.truth_contig] + rb.truth_pos
+    uniq = r1["status"] == 1
+    ok = (np.abs(r1["location"][uniq] - start[uniq]) <= 30) & (r1["direction"][uniq] == rb.truth_rc[uniq])
+    assert ok.mean() > 0.999
+    sub = rb.slice(0, 4000)
+    rc = synth.ReadBatch.from_lists([(synth.revcomp(np.frombuffer(b, dtype=np.uint8)).tobytes(), q[::-1]) for b, q in (sub.read(i) for i in range(sub.n))])
+    ra, _ = al.align(sub); rb2, _ = al.align(rc)
+    both = (ra["status"] == 1) & (rb2["status"] == 1) & (ra["score"] == 0) & (rb2["score"] == 0)
+    assert both.sum() > 500
+    assert (ra["location"][both] == rb2["location"][both]).all() and (ra["direction"][both] != rb2["direction"][both]).all()
+    assert sum(c1["mapqHistogram"]) == int(aligned.sum()) == c1["singleHits"] + c1["multiHits"]
+    ix.close()

@@ -1,0 +1,165 @@
+"""CPU-side parity of the ENGINE'S OWN algorithm headers (snap_b200/csrc/sg_*.h, the code the CUDA kernels compile),
+built for the host by tests/hostsim, against the compiled reference.  Bit-exact: every SingleAlignmentResult field,
+doubles compared bitwise."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import hostsim_lib as hs
+import jobs as J
+from conftest import OPTION_SETS, differing
+
+
+def test_tables_wrap_and_mapq(reflib):
+    rp, ri, rf = reflib.tables()
+    hp, hi, hf, thr, wrap = hs.tables(20)
+    assert np.array_equal(rp.view(np.uint64), hp.view(np.uint64))
+    assert np.array_equal(ri.view(np.uint64), hi.view(np.uint64))
+    assert np.array_equal(rf.view(np.uint64), hf.view(np.uint64))
+    for sl in (16, 20, 24, 32):
+        w = hs.tables(sl)[4]
+        assert [int(x) for x in w[:sl]] == [reflib.lib().ref_wrapped_seed(sl, i) for i in range(sl)]
+    rng = np.random.default_rng(0)
+    for _ in range(50000):
+        pb = rng.random()
+        pa = pb + rng.random() * 10.0 ** int(rng.integers(-15, 1))
+        pop = int(rng.integers(0, 40))
+        assert reflib.lib().ref_mapq(pa, pb, 0, pop) == hs.lib().hs_mapq(pa, pb, pop)
+    # right at the thresholds of the log10-free MAPQ
+    for m in range(1, 71):
+        for x in (thr[m], np.nextafter(thr[m], 0), np.nextafter(thr[m], 1)):
+            p = 1.0 - x
+            if 0 < p < 1 and 1 - p == x:
+                assert reflib.lib().ref_mapq(1.0, p, 0, 0) == hs.lib().hs_mapq(1.0, p, 0)
+
+
+@pytest.mark.parametrize("which", ["idx", "idx_large"])
+def test_lookup_matches_reference(reflib, small_cfg, which):
+    d = getattr(small_cfg, which)
+    ridx, hidx = reflib.RefIndex(d), hs.HsIndex(d)
+    rb = small_cfg.reads["noisy150"]
+    seeds = []
+    for i in range(0, 600):
+        b = rb.read(i)[0]
+        if len(b) >= 60:
+            seeds += [b[0:20], b[37:57]]
+    arr = np.frombuffer(b"".join(seeds), dtype=np.uint8)
+    nh, hits, probes = hidx.lookup(arr, len(seeds), 512)
+    multi = 0
+    for i, s in enumerate(seeds):
+        a = ridx.lookup(s, 512)
+        assert (a[0], a[1]) == (nh[i, 0], nh[i, 1])
+        assert np.array_equal(a[2], hits[i, 0, :min(a[0], 512)]) and np.array_equal(a[3], hits[i, 1, :min(a[1], 512)])
+        multi += a[0] > 1
+        if a[0] > 1:
+            assert (np.diff(hits[i, 0, :a[0]].astype(np.int64)) < 0).all()       # descending (GenomeIndex.cpp:879-889)
+    assert multi > 10          # the repeat library makes overflow lists
+
+
+def test_unit_vectors_on_engine_headers(golden_dir):
+    v = json.load(open(os.path.join(golden_dir, "ref_unit_vectors.json")))
+    for e in v["lv"]:
+        text = np.frombuffer(b"n" * 64 + e["text"].encode() + b"\0" * 64, dtype=np.uint8)
+        pat = np.frombuffer(e["pattern"].encode() + b"\0" * 16, dtype=np.uint8)
+        qual = np.full(pat.size, ord("5"), dtype=np.uint8)
+        job = np.zeros(1, dtype=J.LV_JOB)
+        job[0] = (64, 0, e["textLen"], e["patternLen"], e["k"], 1)
+        assert int(hs.lv_batch(text, pat, qual, job, J.LV_OUT)[0]["score"]) == e["expected"], e
+    for e in v["ag"]:
+        text = np.frombuffer(b"n" * 64 + e["text"].encode() + b"n" * 64, dtype=np.uint8)
+        pat = np.frombuffer(e["pattern"].encode() + b"A" * 8, dtype=np.uint8)
+        qual = np.full(pat.size, ord("2"), dtype=np.uint8)
+        job = np.zeros(1, dtype=J.AG_JOB)
+        job[0] = (64, 0, e["textLen"], e["patternLen"], e["w"], e["scoreInit"], 1, 0, 0, 0)
+        out, _ = hs.ag_batch(text, pat, qual, job, J.AG_OUT, v["ag_params"])
+        assert int(out[0]["agScore"]) == e["expected"], e
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_lv_fuzz(reflib, seed):
+    t, p, q, jb = J.lv_jobs(4000, seed)
+    want = reflib.lv_batch(t, p, q, jb.astype(reflib.LV_JOB_DTYPE))
+    got = hs.lv_batch(t, p, q, jb, J.LV_OUT)
+    assert J.same_out(want, got).all()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_ag_fuzz(reflib, seed):
+    """Includes the inputs on which the reference's traceback walks onto cells its DP never wrote and picks up bits
+    left by earlier calls: the engine keeps the same persistent per-direction array, so those agree too."""
+    t, p, q, jb = J.ag_jobs(3000, seed)
+    want = reflib.ag_batch(t, p, q, jb.astype(reflib.AG_JOB_DTYPE))
+    got, stale = hs.ag_batch(t, p, q, jb, J.AG_OUT, reflib.AG_PARAMS_DEFAULT)
+    assert J.same_out(want, got).all()
+    assert stale.sum() > 0
+
+
+@pytest.mark.parametrize("opt", list(OPTION_SETS))
+def test_whole_reads_match_reference(reflib, small_cfg, opt):
+    p = reflib.default_params(**OPTION_SETS[opt])
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for name, rb in small_cfg.reads.items():
+        ral = reflib.RefSingleAligner(ridx, p)
+        want, wctr = ral.align(rb)
+        ral.close()
+        got, gctr = hs.HsAligner(hidx, p).align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (opt, name)
+        g = reflib.counters_dict(gctr)
+        for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "nHashEntriesProbed",
+                  "lvCalls", "affineGapCalls", "nHitsIgnoredBecauseOfTooHighPopularity", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, name, k)
+
+
+def test_large_index_gives_identical_results(reflib, small_cfg):
+    p = reflib.default_params(maxDist=14)
+    rb = small_cfg.reads["noisy150"]
+    a, _ = hs.HsAligner(hs.HsIndex(small_cfg.idx), p).align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+    b, _ = hs.HsAligner(hs.HsIndex(small_cfg.idx_large), p).align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+    assert differing(a, b) == []
+    ral = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx_large), p)
+    want, _ = ral.align(rb)
+    assert differing(want, b) == []
+
+
+def test_golden_e2e_fixture(golden_dir, tmp_path, reflib):
+    """The committed fixture (made by tests/golden/make_golden.py from the reference) against the engine headers."""
+    from snap_b200 import synth
+    g = np.load(os.path.join(golden_dir, "e2e_small.npz"))
+    contigs = [g["contig0"], g["contig1"]]
+    synth.write_fasta(str(tmp_path / "ref.fa"), contigs)
+    synth.build_reference_index(reflib.SNAP_ALIGNER, str(tmp_path / "ref.fa"), str(tmp_path / "idx"))
+    reads = synth.ReadBatch(g["bases"], g["quals"], g["offsets"], g["lens"])
+    hidx = hs.HsIndex(str(tmp_path / "idx"))
+    for name in ("default_d14", "noag_d14", "ne_d20"):
+        got, _ = hs.HsAligner(hidx, reflib.default_params(**OPTION_SETS[name])).align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(g["res_" + name], got) == [], name
+
+
+def test_edge_reads(reflib, small_cfg):
+    """Empty-ish and ragged inputs: shorter than a seed, shorter than minReadLength, all N, N runs across every seed,
+    maximum supported length."""
+    from snap_b200 import synth
+    rng = np.random.default_rng(9)
+    c = small_cfg.contigs[0]
+    L = 400
+    reads = [
+        (b"ACGTACGTAC", b"5" * 10),                              # < seedLen
+        (c[100:149].tobytes(), b"I" * 49),                       # < minReadLength (50)
+        (c[100:150].tobytes(), b"I" * 50),                       # exactly minReadLength
+        (b"N" * 100, b"5" * 100),                                # all N
+        (bytes(c[1000:1100].tobytes()[:9] + b"N" + c[1010:1100].tobytes()), b"5" * 100),
+        (b"".join(c[2000 + 20 * i: 2000 + 20 * i + 19].tobytes() + b"N" for i in range(5)), b"5" * 100),   # an N in every 20-mer
+        (c[5000:5000 + L].tobytes(), b"H" * L),                  # longest the test aligner is sized for
+        (synth.revcomp(c[7000:7150]).tobytes(), b"#" * 150),     # all-'#' qualities (unclipped view)
+        (c[0:150].tobytes(), b"5" * 150),                        # starts at the very first base of a contig
+        (c[c.size - 150:].tobytes(), b"5" * 150),                # ends at the very last base
+        (np.concatenate([c[c.size - 80:], small_cfg.contigs[1][:70]]).tobytes(), b"5" * 150),   # would span two contigs
+    ]
+    rb = synth.ReadBatch.from_lists(reads)
+    p = reflib.default_params(maxDist=14)
+    want, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), p).align(rb)
+    got, _ = hs.HsAligner(hs.HsIndex(small_cfg.idx), p, max_read_len=L).align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+    assert differing(want, got) == []
+    assert want[6]["status"] == 1 and want[0]["status"] == 0 and want[3]["status"] == 0
