@@ -47,7 +47,7 @@ def parse_args():
                     help="total reference size in Mbp (24 contigs); 3000 = BASELINE configs[1]")
     ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("SNAPGPU_BENCH_BATCH", str(1 << 20))),
                     help="reads per step per GPU")
-    ap.add_argument("--cpu-sample-reads", type=int, default=200000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seed-phase", action="store_true")
     return ap.parse_args()
@@ -158,7 +158,10 @@ def run_ours(args):
     bases, starts, contig_len, idx, batches, setup = build_workload(args, device, rank, world)
     params = engine.default_params(maxDist=MAX_DIST)
     al = engine.SingleAligner(idx, params, max_batch_reads=B)
-    stream = torch.cuda.current_stream(device)
+    # a dedicated (non-default) stream: the kernels are launched on it through the C ABI and the CUDA events that time
+    # them are recorded on the same stream (a NULL stream argument would mean "the aligner's own stream")
+    stream = torch.cuda.Stream(device)
+    assert stream.cuda_stream != 0
     res = torch.empty((B, engine.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=device)
     d_ctr = torch.zeros((engine.N_COUNTERS,), dtype=torch.int64, device=device)
 
@@ -284,7 +287,8 @@ def seed_phase(args, idx, batches, device, peak, peak_src):
     n = B * len(offs)
     nh = torch.empty((n * 2,), dtype=torch.int64, device=device)
     probes = torch.empty((n,), dtype=torch.int32, device=device)
-    st = torch.cuda.current_stream(device)
+    st = torch.cuda.Stream(device)
+    torch.cuda.synchronize()
     for _ in range(2):
         idx.lookup_seeds_device(seeds.data_ptr(), n, nh.data_ptr(), 0, probes.data_ptr(), 0, st.cuda_stream)
     torch.cuda.synchronize()
@@ -306,11 +310,12 @@ def seed_phase(args, idx, batches, device, peak, peak_src):
     gi = torch.randint(0, tbl.numel(), (1 << 24,), device=device)
     torch.cuda.synchronize()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    _ = tbl[gi]
-    g0.record(st)
-    for _ in range(5):
+    with torch.cuda.stream(st):
         _ = tbl[gi]
-    g1.record(st)
+        g0.record(st)
+        for _ in range(5):
+            _ = tbl[gi]
+        g1.record(st)
     torch.cuda.synchronize()
     gather_ms = g0.elapsed_time(g1) / 5
     gather_gbs = gi.numel() * 8 / (gather_ms / 1e3) / 1e9

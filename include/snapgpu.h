@@ -238,6 +238,16 @@ int  snapgpu_test_ag(int device, const snapgpu_ag_params *p, const char *textBuf
                      const char *patBuf, const char *qualBuf, uint64_t patBytes,
                      const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out);
 
+/*
+ * The same leaves in their warp-cooperative form (the form the alignment kernel uses): one job per warp over nWarps
+ * warps.  With nWarps == 1 the jobs run in order on one scratch arena, i.e. with the call history of a sequential run.
+ */
+int  snapgpu_test_lv_warp(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
+                          uint64_t patBytes, const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out, int nWarps);
+int  snapgpu_test_ag_warp(int device, const snapgpu_ag_params *p, const char *textBuf, uint64_t textBytes,
+                          const char *patBuf, const char *qualBuf, uint64_t patBytes,
+                          const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out, int nWarps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,22 @@
 #include "sg_ag.h"
 #if defined(__CUDACC__)
 #include "sg_warp.cuh"
+#include "sg_warp_ag.cuh"
 #endif
+
+// Affine-gap leaf dispatch: on the device with a converged warp (lane >= 0) the rows are spread over the lanes.
+SG_HD void sg_ag_dispatch(const SgTables &T, const SgScratch &S, const SgAgParams &P, int dir, bool banded,
+                          const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
+                          int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out, int lane)
+{
+#if defined(__CUDA_ARCH__)
+    if (lane >= 0) {
+        sg_warp_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out, lane);
+        return;
+    }
+#endif
+    sg_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out);
+}
 
 struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260-329
     int      bestScore;
@@ -91,7 +106,7 @@ struct SgAligner {
     SgScratch          sc;
     SgAgParams         ag;
     SgWork             work;
-    int                lane;         // 0..31 on the device (all lanes run the state machine uniformly); 0 on the host
+    int                lane;         // 0..31 on the device (all lanes run the state machine uniformly); -1 on the host
 
     // per-read state
     const uint8_t *readData[2], *readQual[2];   // [FORWARD] = input, [RC] = rcRead/rcQual
@@ -201,6 +216,19 @@ struct SgAligner {
     }
     // clearCandidates (:2331-2339), plus un-marking our lookup table
     SG_HD void clearCandidates() {
+#if defined(__CUDA_ARCH__)
+        if (lane >= 0) {
+            for (uint32_t i = lane; i < nUsedElements; i += 32) sc.table[sc.pool[i].slot] = 0;
+            for (uint32_t i = 1 + lane; i < pr->numWeightLists; i += 32) {
+                sc.listNext[i] = SG_SENTINEL | i;
+                sc.listPrev[i] = SG_SENTINEL | i;
+            }
+            nUsedElements = 0;
+            highestUsedWeightList = 0;
+            __syncwarp();
+            return;
+        }
+#endif
         for (uint32_t i = 0; i < nUsedElements; i++) sc.table[sc.pool[i].slot] = 0;
         nUsedElements = 0;
         highestUsedWeightList = 0;
@@ -249,13 +277,13 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
 
         SgLvResult lv;
         sg_lv_compute(T, A.sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart,
-                      scoreLimitForThisElement, &lv);
+                      scoreLimitForThisElement, &lv, A.lane);
         score1 = lv.score; matchProb1 = lv.matchProbability;
         agScore1 = (seedLen + readLen - tailStart - score1) * pr.matchReward - score1 * pr.subPenalty;
         if (score1 != SG_SCORE_ABOVE_LIMIT) {
             int limitLeft = scoreLimitForThisElement - score1;
             sg_lv_compute(T, A.sc, -1, data + seedOffset, seedOffset + SG_MAX_K, revRead + readLen - seedOffset, oppQual + readLen - seedOffset,
-                          seedOffset, limitLeft, &lv);
+                          seedOffset, limitLeft, &lv, A.lane);
             score2 = lv.score; matchProb2 = lv.matchProbability; genomeLocationOffset = lv.netIndel;
             agScore2 = (seedOffset - score2) * pr.matchReward - score2 * pr.subPenalty;
         }
@@ -272,8 +300,8 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
                 if (tailStart != readLen) {
                     int patternLen = readLen - tailStart;
                     bool banded = (patternLen >= (3 * (2 * scoreLimitForThisElement + 1))) && !pr.noBandedAffineGap;
-                    sg_ag_compute(T, A.sc, A.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart,
-                                  patternLen, scoreLimitForThisElement, readLen, dirn != 0, false, &ar);
+                    sg_ag_dispatch(T, A.sc, A.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart,
+                                   patternLen, scoreLimitForThisElement, readLen, dirn != 0, false, &ar, A.lane);
                     agScore1 = ar.agScore; basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
                     agScore1 += (seedLen - readLen);
                 }
@@ -283,8 +311,8 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
                         int patternLen = seedOffset;
                         bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
                         ar.textOffset = genomeLocationOffset; ar.patternOffset = basesClippedBefore; ar.matchProbability = matchProb2;
-                        sg_ag_compute(T, A.sc, A.ag, -1, banded, data + seedOffset, seedOffset + limitLeft, revRead + readLen - seedOffset,
-                                      oppQual + readLen - seedOffset, seedOffset, limitLeft, readLen, dirn != 0, false, &ar);
+                        sg_ag_dispatch(T, A.sc, A.ag, -1, banded, data + seedOffset, seedOffset + limitLeft, revRead + readLen - seedOffset,
+                                       oppQual + readLen - seedOffset, seedOffset, limitLeft, readLen, dirn != 0, false, &ar, A.lane);
                         agScore2 = ar.agScore; genomeLocationOffset = ar.textOffset; basesClippedBefore = ar.patternOffset;
                         score2 = ar.nEdits; matchProb2 = ar.matchProbability;
                         agScore2 -= readLen;
@@ -497,17 +525,35 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
         return;                      // :360-366, "hopeless"
     }
 
-    for (uint32_t i = 0; i < (readLen + 7) / 8; i++) A.sc.seedUsed[i] = 0;
-
     uint32_t countOfNs = 0;
-    for (uint32_t i = 0; i < readLen; i++) {
-        uint8_t baseByte = readData[i];
-        uint8_t complement = sg_complement(baseByte);
-        A.sc.rcRead[readLen - i - 1] = complement;
-        A.sc.rcQual[readLen - i - 1] = readQuality[i];
-        A.sc.revRead[0][readLen - i - 1] = baseByte;
-        A.sc.revRead[1][i] = complement;
-        countOfNs += (baseByte == 'N') ? 1u : 0u;                  // nTable, :212-214
+#if defined(__CUDA_ARCH__)
+    if (A.lane >= 0) {
+        // the four derived strings (:388-396) are built 32 bases per step; every lane reads all of them afterwards
+        for (uint32_t i = A.lane; i < (readLen + 7) / 8; i += 32) A.sc.seedUsed[i] = 0;
+        for (uint32_t i = A.lane; i < readLen; i += 32) {
+            uint8_t baseByte = readData[i];
+            uint8_t complement = sg_complement(baseByte);
+            A.sc.rcRead[readLen - i - 1] = complement;
+            A.sc.rcQual[readLen - i - 1] = readQuality[i];
+            A.sc.revRead[0][readLen - i - 1] = baseByte;
+            A.sc.revRead[1][i] = complement;
+            countOfNs += (baseByte == 'N') ? 1u : 0u;
+        }
+        countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
+        __syncwarp();
+    } else
+#endif
+    {
+        for (uint32_t i = 0; i < (readLen + 7) / 8; i++) A.sc.seedUsed[i] = 0;
+        for (uint32_t i = 0; i < readLen; i++) {
+            uint8_t baseByte = readData[i];
+            uint8_t complement = sg_complement(baseByte);
+            A.sc.rcRead[readLen - i - 1] = complement;
+            A.sc.rcQual[readLen - i - 1] = readQuality[i];
+            A.sc.revRead[0][readLen - i - 1] = baseByte;
+            A.sc.revRead[1][i] = complement;
+            countOfNs += (baseByte == 'N') ? 1u : 0u;                  // nTable, :212-214
+        }
     }
     if (countOfNs > pr.maxK) {
         return;                      // :398-402

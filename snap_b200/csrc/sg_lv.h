@@ -26,9 +26,25 @@ struct SgLvState {
 // countPerfectMatch (LandauVishkin.h:377-407): number of equal leading characters of pattern[pi..] and the text
 // read in direction dir starting at text index ti, clamped to availBytes (which may be <= 0: the reference then
 // returns availBytes itself because the first characters were already known equal).
-SG_HD int sg_lv_cpm(const uint8_t *pattern, int pi, const uint8_t *text, int ti, int dir, int availBytes)
+// lane >= 0 (device, all 32 lanes converged with identical arguments): 32 characters are compared per step and the first
+// mismatch found with a ballot.  lane < 0: scalar.
+SG_HD int sg_lv_cpm(const uint8_t *pattern, int pi, const uint8_t *text, int ti, int dir, int availBytes, int lane)
 {
     if (availBytes <= 0) return availBytes;
+#if defined(__CUDA_ARCH__)
+    if (lane >= 0) {
+        for (int n = 0; n < availBytes; n += 32) {
+            int i = n + lane;
+            bool mism = (i < availBytes) ? (pattern[pi + i] != text[(ti + i) * dir]) : true;
+            unsigned m = __ballot_sync(0xffffffffu, mism);
+            if (m != 0) {
+                int r = n + (__ffs(m) - 1);
+                return r < availBytes ? r : availBytes;
+            }
+        }
+        return availBytes;
+    }
+#endif
     int n = 0;
     while (n < availBytes && pattern[pi + n] == text[(ti + n) * dir]) n++;
     return n;
@@ -36,7 +52,7 @@ SG_HD int sg_lv_cpm(const uint8_t *pattern, int pi, const uint8_t *text, int ti,
 
 // text: as the reference's callers pass it (for dir == -1: one past the first text character).
 SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const uint8_t *text, int textLen,
-                          const uint8_t *pattern, const uint8_t *quality, int patternLen, int k, SgLvResult *out)
+                          const uint8_t *pattern, const uint8_t *quality, int patternLen, int k, SgLvResult *out, int lane = -1)
 {
     out->netIndel = 0; out->totalIndels = 0; out->textSpan = 0; out->matchProbability = 0.0;
     if (k < 0) { out->score = SG_SCORE_ABOVE_LIMIT; return; }
@@ -49,8 +65,7 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
     st.L = S.lvL; st.A = S.lvA; st.kmax = k; st.stride = 2 * k + 1;
 
     int end = patternLen < textLen ? patternLen : textLen;
-    int L00 = 0;
-    while (L00 < end && pattern[L00] == text[L00 * dir]) L00++;      // countPerfectMatch(p, t, end) with end >= 0
+    int L00 = end > 0 ? sg_lv_cpm(pattern, 0, text, 0, dir, end, lane) : 0;      // countPerfectMatch(p, t, end) with end >= 0
     st.setL(0, 0, L00);
 
     if (L00 == end) {
@@ -75,7 +90,7 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
             if (best >= 0 && best < patternLen + 1) {
                 // the reference compares *p == *t even at best == patternLen (then extends by min(.., 0) = 0)
                 if (endd - best > 0) {
-                    if (pattern[best] == text[(d + best) * dir]) best += sg_lv_cpm(pattern, best, text, d + best, dir, endd - best);
+                    if (pattern[best] == text[(d + best) * dir]) best += sg_lv_cpm(pattern, best, text, d + best, dir, endd - best, lane);
                 } else if (endd - best < 0) {
                     if (pattern[best] == text[(d + best) * dir]) best += endd - best;
                 }
@@ -83,7 +98,7 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
             int left = st.getL(e - 1, d - 1);
             if (left >= 0) {
                 if (endd - left > 0) {
-                    if (pattern[left] == text[(d + left) * dir]) left += sg_lv_cpm(pattern, left, text, d + left, dir, endd - left);
+                    if (pattern[left] == text[(d + left) * dir]) left += sg_lv_cpm(pattern, left, text, d + left, dir, endd - left, lane);
                 } else if (endd - left < 0) {
                     if (pattern[left] == text[(d + left) * dir]) left += endd - left;
                 }
@@ -92,7 +107,7 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
             int right = st.getL(e - 1, d + 1) + 1;
             if (right >= 0) {
                 if (endd - right > 0) {
-                    if (pattern[right] == text[(d + right) * dir]) right += sg_lv_cpm(pattern, right, text, d + right, dir, endd - right);
+                    if (pattern[right] == text[(d + right) * dir]) right += sg_lv_cpm(pattern, right, text, d + right, dir, endd - right, lane);
                 } else if (endd - right < 0) {
                     if (pattern[right] == text[(d + right) * dir]) right += endd - right;
                 }

@@ -1,0 +1,247 @@
+// sg_warp_ag.cuh -- affine-gap seed extension, one warp per (text, pattern) pair (device only).
+//
+// Same results as the scalar restatement in sg_ag.h (which itself walks the reference's striped SSE2 coordinates,
+// AffineGapVectorized.h:256-819 / :821-1339), bit for bit, with the work of one DP row spread over the warp:
+//
+//   lane = q*8 + l      l = the SSE lane of the reference's 8 x int16 vector, q = one of 4 consecutive vectors.
+//
+// A block of 4 striped vectors (32 cells, contiguous in the H / E / traceback arrays => coalesced 64 B / 32 B rows)
+// is processed per step.  Everything in a cell except the horizontal-gap value F is independent of the other cells of
+// the row; F is a max-plus prefix over the vectors of one SSE lane (f' = max(f - ext, temp)), which the 4 sub-lanes
+// resolve with 3 shuffles, carrying the block's outgoing F to the next block.  The lazy-F loop of the reference
+// decays F by a constant per vector independently of H, so a whole block of it is evaluated at once and the
+// reference's "stop at the first vector where no lane can still change H" is recovered from a ballot: only vectors up to
+// that one are committed.  Integer DP on int16-range values: DPX-style min/max, no tensor cores.
+#pragma once
+#include "sg_ag.h"
+
+__device__ __forceinline__ int sg_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParams &P, int dir, bool banded,
+                                                const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
+                                                int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out, int lane)
+{
+    out->agScore = -1;
+    if (w > SG_MAX_K - 1) w = SG_MAX_K - 1;
+    if (text == (const uint8_t *)0) { out->matchProbability = 0.0; out->nEdits = -1; return; }
+    if (w < 0) { out->nEdits = SG_SCORE_ABOVE_LIMIT; return; }
+    out->matchProbability = 1.0;
+    out->textOffset = -1; out->patternOffset = -1; out->nEdits = -1;
+    if (dir == -1) text--;
+
+    SgAgLayout lay;
+    lay.banded = banded ? 1 : 0;
+    if (banded) {
+        int bandWidth = (2 * w + 1) < patternLen ? (2 * w + 1) : patternLen;
+        lay.numVec = (bandWidth + SG_VEC - 1) / SG_VEC;
+        lay.segLen = lay.numVec * SG_VEC;
+        lay.numSeg = (patternLen + lay.segLen - 1) / lay.segLen;
+    } else {
+        lay.numVec = (patternLen + SG_VEC - 1) / SG_VEC;
+        lay.segLen = lay.numVec * SG_VEC;
+        lay.numSeg = 1;
+    }
+    lay.w = w; lay.patternLen = patternLen; lay.nRows = 0;
+    const int numVec = lay.numVec, segLen = lay.segLen, numSeg = lay.numSeg;
+    const int stride = lay.rowStride();
+    const int l = lane & 7, q = lane >> 3;
+    const int open = P.gapOpenPenalty, ext = P.gapExtendPenalty;
+
+    int endBonus;
+    if (!isRC) endBonus = (dir == -1) ? P.fivePrimeEndBonus : P.threePrimeEndBonus;
+    else       endBonus = (dir == -1) ? P.threePrimeEndBonus : P.fivePrimeEndBonus;
+
+    int16_t *Hptr = S.agH, *Hm1ptr = S.agHm1, *E = S.agE;
+    uint8_t *bt = S.agBt[dir == 1 ? 0 : 1];
+
+    // first row (:971-983 / :399-414): per SSE lane the "last value assigned" persists across vectors and segments
+    if (q == 0) {
+        int last = 0;
+        for (int segIdx = 0; segIdx < numSeg; segIdx++) {
+            for (int vecIdx = 0; vecIdx < numVec; vecIdx++) {
+                int patternIdx = segIdx * segLen + l * numVec + vecIdx;
+                if (patternIdx < patternLen) {
+                    int v = scoreInit - open - patternIdx * ext;
+                    last = v > 0 ? v : 0;
+                }
+                int idx = (segIdx * numVec + vecIdx) * SG_VEC + l;
+                Hptr[idx] = (int16_t)last;
+                Hm1ptr[idx] = 0;
+                E[idx] = 0;
+            }
+        }
+    }
+    __syncwarp();
+
+    int bestGlobalAlignmentScore = -1, bestGlobalAlignmentTextOffset = -1;
+    int bestLocalAlignmentScore = -1, bestLocalAlignmentTextOffset = -1, bestLocalAlignmentPatternOffset = -1;
+
+    for (int i = 0; i < textLen; i++) {
+        lay.nRows = i + 1;
+        const uint32_t tb = sg_base_value(text[i * dir]);
+        uint8_t *btRow = bt + (size_t)i * stride;
+        int myMax = 0;                   // running max of H over the cells this lane committed in this row
+        int X0 = 0;                      // lane 0 of the reference's X register
+        int fcarry = 0;                  // F entering the next vector of my SSE lane (identical in the 4 sub-lanes)
+
+        int bandBeg = 0, bandEnd = patternLen - 1, segBeg = 0, segEnd = 0;
+        if (banded) {
+            bandBeg = (i - w) > 0 ? (i - w) : 0;
+            bandEnd = (i + w) < (patternLen - 1) ? (i + w) : (patternLen - 1);
+            segBeg = bandBeg / segLen;
+            segEnd = bandEnd / segLen;
+        }
+
+        for (int j = segBeg; j <= segEnd; j++) {
+            const int vbase = j * numVec;
+            int nVecHere = numVec;
+            if (banded) {
+                int lim = bandEnd - j * segLen + 1;
+                if (lim < nVecHere) nVecHere = lim;
+                if (nVecHere < 0) nVecHere = 0;
+            }
+            int hInit;
+            if (j == 0) {
+                hInit = scoreInit;
+                if (i > 0) { hInit = scoreInit - open - (i - 1) * ext; if (hInit < 0) hInit = 0; }
+            } else {
+                if (bandBeg > j * segLen) hInit = 0;
+                else hInit = Hptr[(vbase - 1) * SG_VEC + (SG_VEC - 1)];
+            }
+            // f entering vector 0 of this segment: 0, or (X0, 0, ..., 0) passed on from the previous segment (:572)
+            fcarry = (banded && j > segBeg) ? (l == 0 ? X0 : 0) : 0;
+
+            // ---------------- main pass, 4 vectors per step ----------------
+            const int nBlocks = (nVecHere + 3) >> 2;
+            for (int b = 0; b < nBlocks; b++) {
+                const int k = 4 * b + q;
+                const bool valid = k < nVecHere;
+                const int idx = (vbase + k) * SG_VEC + l;
+                int temp = 0, h1 = 0, act = 0;
+                if (valid) {
+                    int hdiag;
+                    if (k == 0) hdiag = (l == 0) ? hInit : (int)Hptr[(vbase + numVec - 1) * SG_VEC + l - 1];
+                    else hdiag = Hptr[idx - SG_VEC];
+                    const int col = j * segLen + l * numVec + k;
+                    const int prof = (col < patternLen) ? sg_ag_sub(P, tb, sg_base_value(pattern[col])) : -32768;
+                    const int m = (hdiag > 0) ? sg_sat16(hdiag + prof) : 0;
+                    const int e = E[idx];
+                    act = (e > m) ? 1 : 0;
+                    h1 = m > e ? m : e;
+                    const int e2 = sg_sat16(e - ext);
+                    temp = sg_sat16(m - open); if (temp < 0) temp = 0;
+                    if (e2 > temp) act |= 4;
+                    E[idx] = (int16_t)(e2 > temp ? e2 : temp);
+                }
+                // F entering vector k of SSE lane l: max(fcarry - q*ext, temp[k'] - (q-1-q')*ext for q' < q in this block).
+                // (the reference's saturating f - ext only ever matters through max(.., temp >= 0), so plain ints are exact)
+                const int t0 = sg_shfl(temp, l), t1 = sg_shfl(temp, 8 + l), t2 = sg_shfl(temp, 16 + l), t3 = sg_shfl(temp, 24 + l);
+                int fin = fcarry - q * ext;
+                if (q > 0) { int v = t0 - (q - 1) * ext; if (v > fin) fin = v; }
+                if (q > 1) { int v = t1 - (q - 2) * ext; if (v > fin) fin = v; }
+                if (q > 2) { int v = t2; if (v > fin) fin = v; }
+                // the reference's f register is max(f - ext, temp) >= 0 after the first vector and 0 (or X) before it
+                if (b > 0 || q > 0) { if (fin < 0) fin = 0; }
+                if (valid) {
+                    int h = h1;
+                    if (fin > h) { act |= 2; h = fin; }
+                    const int f2 = sg_sat16(fin - ext);
+                    if (f2 > temp) act |= 32;
+                    if (h > myMax) myMax = h;
+                    Hm1ptr[idx] = (int16_t)h;
+                    btRow[idx] = (uint8_t)act;
+                }
+                // carry out of this block = F entering vector 4b+4 (only vectors < nVecHere contribute)
+                int nv = nVecHere - 4 * b; if (nv > 4) nv = 4;
+                int c = fcarry - nv * ext;
+                { int v = t0 - (nv - 1) * ext; if (nv > 0 && v > c) c = v; }
+                { int v = t1 - (nv - 2) * ext; if (nv > 1 && v > c) c = v; }
+                { int v = t2 - (nv - 3) * ext; if (nv > 2 && v > c) c = v; }
+                { int v = t3 - (nv - 4) * ext; if (nv > 3 && v > c) c = v; }
+                if (c < 0) c = 0;
+                fcarry = c;
+            }
+            __syncwarp();
+
+            // ---------------- lazy F (:1080-1112 / :534-569) ----------------
+            int fl = fcarry;                 // f register of SSE lane l after the main pass
+            const int passes = banded ? (SG_VEC - 1) : SG_VEC;
+            bool converged = false;
+            for (int kk = 0; kk < passes && !converged; kk++) {
+                if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
+                { int up = sg_shfl(fl, (lane & 24) | ((l + 7) & 7)); fl = (l == 0) ? 0 : up; }      // f = f << one lane
+                for (int b = 0; b < nBlocks && !converged; b++) {
+                    const int v = 4 * b + q;
+                    const bool valid = v < nVecHere;
+                    const int idx = (vbase + v) * SG_VEC + l;
+                    int fv = fl - v * ext; if (fv < 0) fv = 0;
+                    int h = 0, act = 0, newh = 0;
+                    bool live = false, a2 = false;
+                    if (valid) {
+                        h = Hm1ptr[idx];
+                        act = btRow[idx];
+                        a2 = fv > h;
+                        newh = a2 ? fv : h;
+                        int temp = newh - open; if (temp < 0) temp = 0;
+                        int fn = fv - ext; if (fn < 0) fn = 0;
+                        live = fn > temp;
+                    }
+                    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+                    // first vector of this block (in order) at which no SSE lane is live any more
+                    int firstConv = 4;
+                    for (int qq = 3; qq >= 0; qq--) {
+                        if (4 * b + qq < nVecHere && ((liveMask >> (8 * qq)) & 0xffu) == 0) firstConv = qq;
+                    }
+                    if (valid && q <= firstConv) {
+                        Hm1ptr[idx] = (int16_t)newh;
+                        btRow[idx] = (uint8_t)(act | (a2 ? 2 : 0) | (live ? 32 : 0));
+                        if (newh > myMax) myMax = newh;
+                    }
+                    if (firstConv < 4) converged = true;
+                }
+                if (!converged) { fl = fl - nVecHere * ext; if (fl < 0) fl = 0; }
+            }
+            __syncwarp();
+        }
+
+        const int maxScoreRow = __reduce_max_sync(0xffffffffu, myMax);
+
+        if (!banded || bandEnd == patternLen - 1) {
+            int globalAlignmentScore = Hm1ptr[lay.cellIndex(banded ? bandEnd : patternLen - 1)];
+            if (globalAlignmentScore >= bestGlobalAlignmentScore) {
+                bestGlobalAlignmentScore = globalAlignmentScore;
+                bestGlobalAlignmentTextOffset = i;
+            }
+        }
+
+        if (maxScoreRow == 0) break;
+
+        if (maxScoreRow > bestLocalAlignmentScore) {
+            int best = -1;
+            for (int j = segBeg; j <= segEnd; j++) {
+                int nVecHere = numVec;
+                if (banded) {
+                    int lim = bandEnd - j * segLen + 1;
+                    if (lim < nVecHere) nVecHere = lim;
+                }
+                for (int k = q; k < nVecHere; k += 4) {
+                    if (Hm1ptr[(j * numVec + k) * SG_VEC + l] == maxScoreRow) {
+                        int patternOffset = j * segLen + l * numVec + k;
+                        if (patternOffset > best) best = patternOffset;
+                    }
+                }
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            bestLocalAlignmentScore = maxScoreRow;
+            bestLocalAlignmentTextOffset = i;
+            bestLocalAlignmentPatternOffset = best;
+        }
+
+        int16_t *tmp = Hm1ptr; Hm1ptr = Hptr; Hptr = tmp;
+    }
+    __syncwarp();
+
+    sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
+                 bestLocalAlignmentScore, bestLocalAlignmentTextOffset, bestLocalAlignmentPatternOffset,
+                 bestGlobalAlignmentScore, bestGlobalAlignmentTextOffset, out);
+}

@@ -214,6 +214,52 @@ __global__ void sg_test_ag_kernel(const SgTables *tb, SgParams pr, SgAgParams P,
     }
 }
 
+// warp-cooperative leaves, one job per warp; with a single warp the jobs run in order on one scratch arena, i.e. with the
+// same call history as a sequential CPU run (matters for the affine-gap traceback array, see sg_ag.h)
+__global__ void sg_test_lv_warp_kernel(const SgTables *tb, SgParams pr, uint8_t *scratchBase, size_t scratchBytes,
+                                       const uint8_t *textBuf, const uint8_t *patBuf, const uint8_t *qualBuf,
+                                       const snapgpu_lv_job *jobs, long long nJobs, snapgpu_lv_out *out)
+{
+    const int lane = threadIdx.x & 31;
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nW = ((long long)gridDim.x * blockDim.x) >> 5;
+    SgScratch s;
+    sg_scratch_carve(pr, scratchBase + (size_t)wid * scratchBytes, &s);
+    for (long long j = wid; j < nJobs; j += nW) {
+        SgLvResult r;
+        sg_lv_compute(*tb, s, jobs[j].dir, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff, qualBuf + jobs[j].patOff,
+                      jobs[j].patternLen, jobs[j].k, &r, lane);
+        __syncwarp();
+        if (lane == 0) {
+            out[j].score = r.score; out[j].netIndel = r.netIndel; out[j].totalIndels = r.totalIndels; out[j].textSpan = r.textSpan;
+            out[j].matchProbability = r.matchProbability;
+        }
+    }
+}
+
+__global__ void sg_test_ag_warp_kernel(const SgTables *tb, SgParams pr, SgAgParams P, uint8_t *scratchBase, size_t scratchBytes,
+                                       const uint8_t *textBuf, const uint8_t *patBuf, const uint8_t *qualBuf,
+                                       const snapgpu_ag_job *jobs, long long nJobs, snapgpu_ag_out *out)
+{
+    const int lane = threadIdx.x & 31;
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nW = ((long long)gridDim.x * blockDim.x) >> 5;
+    SgScratch s;
+    sg_scratch_carve(pr, scratchBase + (size_t)wid * scratchBytes, &s);
+    for (long long j = wid; j < nJobs; j += nW) {
+        SgAgResult r;
+        r.agScore = -1; r.textOffset = 0; r.patternOffset = 0; r.nEdits = 0; r.matchProbability = 0.0;
+        sg_warp_ag_compute(*tb, s, P, jobs[j].dir, jobs[j].banded != 0, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff,
+                           qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].w, jobs[j].scoreInit, jobs[j].isRC != 0,
+                           jobs[j].useClippingOptimizations != 0, &r, lane);
+        __syncwarp();
+        if (lane == 0) {
+            out[j].agScore = r.agScore; out[j].textOffset = r.textOffset; out[j].patternOffset = r.patternOffset; out[j].nEdits = r.nEdits;
+            out[j].matchProbability = r.matchProbability;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -693,6 +739,7 @@ static int leaf_scratch(int device, SgParams *p, int *threads, uint8_t **d_scrat
     *bytes = sg_align_up(sg_scratch_bytes(*p), 256);
     *threads = 64 * 32;
     SG_CUDA(cudaMalloc((void **)d_scratch, *bytes * (size_t)*threads));
+    SG_CUDA(cudaMemset(*d_scratch, 0, *bytes * (size_t)*threads));
     SgTables T;
     sg_init_tables(T, 20);
     SG_CUDA(cudaMalloc((void **)d_tb, sizeof(SgTables)));
@@ -700,8 +747,8 @@ static int leaf_scratch(int device, SgParams *p, int *threads, uint8_t **d_scrat
     return 0;
 }
 
-int snapgpu_test_lv(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf, uint64_t patBytes,
-                    const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out)
+static int test_lv_impl(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf, uint64_t patBytes,
+                        const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out, int nWarps)
 {
     SgParams p; int threads; uint8_t *d_scratch = nullptr; size_t bytes; SgTables *d_tb = nullptr;
     if (leaf_scratch(device, &p, &threads, &d_scratch, &bytes, &d_tb)) return 1;
@@ -712,7 +759,12 @@ int snapgpu_test_lv(int device, const char *textBuf, uint64_t textBytes, const c
     SG_CUDA(cudaMemcpy(d_pat, patBuf, patBytes, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(d_qual, qualBuf, patBytes, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(d_jobs, jobs, (size_t)nJobs * sizeof(*jobs), cudaMemcpyHostToDevice));
-    sg_test_lv_kernel<<<threads / 32, 32>>>(d_tb, p, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    if (nWarps > 0) {
+        if (nWarps > threads) nWarps = threads;
+        sg_test_lv_warp_kernel<<<nWarps, 32>>>(d_tb, p, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    } else {
+        sg_test_lv_kernel<<<threads / 32, 32>>>(d_tb, p, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    }
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaDeviceSynchronize());
     SG_CUDA(cudaMemcpy(out, d_out, (size_t)nJobs * sizeof(*out), cudaMemcpyDeviceToHost));
@@ -720,8 +772,20 @@ int snapgpu_test_lv(int device, const char *textBuf, uint64_t textBytes, const c
     return 0;
 }
 
-int snapgpu_test_ag(int device, const snapgpu_ag_params *ap, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
-                    uint64_t patBytes, const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out)
+int snapgpu_test_lv(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf, uint64_t patBytes,
+                    const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out)
+{
+    return test_lv_impl(device, textBuf, textBytes, patBuf, qualBuf, patBytes, jobs, nJobs, out, 0);
+}
+
+int snapgpu_test_lv_warp(int device, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf, uint64_t patBytes,
+                         const snapgpu_lv_job *jobs, int64_t nJobs, snapgpu_lv_out *out, int nWarps)
+{
+    return test_lv_impl(device, textBuf, textBytes, patBuf, qualBuf, patBytes, jobs, nJobs, out, nWarps < 1 ? 1 : nWarps);
+}
+
+static int test_ag_impl(int device, const snapgpu_ag_params *ap, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
+                        uint64_t patBytes, const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out, int nWarps)
 {
     SgParams p; int threads; uint8_t *d_scratch = nullptr; size_t bytes; SgTables *d_tb = nullptr;
     if (leaf_scratch(device, &p, &threads, &d_scratch, &bytes, &d_tb)) return 1;
@@ -733,12 +797,29 @@ int snapgpu_test_ag(int device, const snapgpu_ag_params *ap, const char *textBuf
     SG_CUDA(cudaMemcpy(d_pat, patBuf, patBytes, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(d_qual, qualBuf, patBytes, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(d_jobs, jobs, (size_t)nJobs * sizeof(*jobs), cudaMemcpyHostToDevice));
-    sg_test_ag_kernel<<<threads / 32, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    if (nWarps > 0) {
+        if (nWarps > threads) nWarps = threads;
+        sg_test_ag_warp_kernel<<<nWarps, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    } else {
+        sg_test_ag_kernel<<<threads / 32, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+    }
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaDeviceSynchronize());
     SG_CUDA(cudaMemcpy(out, d_out, (size_t)nJobs * sizeof(*out), cudaMemcpyDeviceToHost));
     cudaFree(d_text); cudaFree(d_pat); cudaFree(d_qual); cudaFree(d_jobs); cudaFree(d_out); cudaFree(d_scratch); cudaFree(d_tb);
     return 0;
+}
+
+int snapgpu_test_ag(int device, const snapgpu_ag_params *ap, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
+                    uint64_t patBytes, const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out)
+{
+    return test_ag_impl(device, ap, textBuf, textBytes, patBuf, qualBuf, patBytes, jobs, nJobs, out, 0);
+}
+
+int snapgpu_test_ag_warp(int device, const snapgpu_ag_params *ap, const char *textBuf, uint64_t textBytes, const char *patBuf, const char *qualBuf,
+                         uint64_t patBytes, const snapgpu_ag_job *jobs, int64_t nJobs, snapgpu_ag_out *out, int nWarps)
+{
+    return test_ag_impl(device, ap, textBuf, textBytes, patBuf, qualBuf, patBytes, jobs, nJobs, out, nWarps < 1 ? 1 : nWarps);
 }
 
 } // extern "C"

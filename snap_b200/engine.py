@@ -63,7 +63,7 @@ EXPORTS = [
     "snapgpu_last_error", "snapgpu_abi_version", "snapgpu_device_count", "snapgpu_params_default",
     "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close",
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
-    "snapgpu_align_single_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag",
+    "snapgpu_align_single_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 _lib = None
@@ -97,6 +97,8 @@ def lib():
         L.snapgpu_test_lv.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
         L.snapgpu_test_ag.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                       C.c_int64, C.c_void_p]
+        L.snapgpu_test_lv_warp.argtypes = L.snapgpu_test_lv.argtypes + [C.c_int]
+        L.snapgpu_test_ag_warp.argtypes = L.snapgpu_test_ag.argtypes + [C.c_int]
         _lib = L
     return _lib
 
@@ -227,14 +229,21 @@ class SingleAligner:
             self.handle = None
 
 
-def test_lv(text, pat, qual, jobs, out_dtype, device=0):
+def test_lv(text, pat, qual, jobs, out_dtype, device=0, warps=0):
+    """warps == 0: scalar leaf, one job per thread; warps >= 1: warp-cooperative leaf, one job per warp."""
     out = np.zeros(jobs.size, dtype=out_dtype)
-    _check(lib().snapgpu_test_lv(device, _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out)))
+    if warps:
+        _check(lib().snapgpu_test_lv_warp(device, _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out), warps))
+    else:
+        _check(lib().snapgpu_test_lv(device, _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out)))
     return out
 
 
-def test_ag(text, pat, qual, jobs, out_dtype, params, device=0):
+def test_ag(text, pat, qual, jobs, out_dtype, params, device=0, warps=0):
     out = np.zeros(jobs.size, dtype=out_dtype)
     params = np.ascontiguousarray(params, dtype=np.int32)
-    _check(lib().snapgpu_test_ag(device, _p(params), _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out)))
+    if warps:
+        _check(lib().snapgpu_test_ag_warp(device, _p(params), _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out), warps))
+    else:
+        _check(lib().snapgpu_test_ag(device, _p(params), _p(text), text.size, _p(pat), _p(qual), pat.size, _p(jobs), jobs.size, _p(out)))
     return out

@@ -149,6 +149,7 @@ void *hs_aligner_create(void *vix, const snapgpu_params *params, uint32_t maxRea
                            params->fivePrimeEndBonus, params->threePrimeEndBonus);
     a->A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     a->A.nUsedElements = 0;
+    a->A.lane = -1;
     return a;
 }
 

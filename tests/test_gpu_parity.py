@@ -64,6 +64,34 @@ def test_leaf_golden_ag(engine, golden_dir):
     assert (g["out"]["textOffset"] == got["textOffset"]).all() and (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
 
+def test_warp_leaves_golden(engine, golden_dir):
+    """The warp-cooperative forms (what the alignment kernel runs).  LV is a pure function: any number of warps.
+    Affine gap with ONE warp runs the jobs in order on one arena = the call history of the sequential reference run that
+    produced the fixture, so even the inputs whose traceback reads stale cells must agree; with many warps only those may
+    differ."""
+    g = np.load(os.path.join(golden_dir, "leaf_lv.npz"))
+    got = engine.test_lv(g["text"], g["pat"], g["qual"], g["jobs"], J.LV_OUT, warps=512)
+    assert J.same_out(g["out"], got).all()
+    g = np.load(os.path.join(golden_dir, "leaf_ag.npz"))
+    got1 = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, [1, 4, 6, 1, 10, 7], warps=1)
+    assert J.same_out(g["out"], got1).all()
+    gotn = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, [1, 4, 6, 1, 10, 7], warps=256)
+    same = J.same_out(g["out"], gotn)
+    assert (~same).sum() <= 0.01 * same.size
+    assert (g["out"]["agScore"] == gotn["agScore"]).all() and (g["out"]["textOffset"] == gotn["textOffset"]).all()
+
+
+def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib):
+    for seed in (301, 302):
+        t, p, q, jb = J.lv_jobs(3000, seed)
+        want = reflib.lv_batch(t, p, q, jb.astype(reflib.LV_JOB_DTYPE))
+        assert J.same_out(want, engine.test_lv(t, p, q, jb, J.LV_OUT, warps=256)).all()
+        assert J.same_out(want, engine.test_lv(t, p, q, jb, J.LV_OUT)).all()
+        t, p, q, jb = J.ag_jobs(2500, seed + 10)
+        want = reflib.ag_batch(t, p, q, jb.astype(reflib.AG_JOB_DTYPE))
+        assert J.same_out(want, engine.test_ag(t, p, q, jb, J.AG_OUT, reflib.AG_PARAMS_DEFAULT, warps=1)).all()
+
+
 def test_lookup_matches_reference(engine, gidx, small_cfg, reflib):
     ridx = reflib.RefIndex(small_cfg.idx)
     rb = small_cfg.reads["noisy150"]
