@@ -150,13 +150,16 @@ SG_HDN void sg_ag_finish(const SgTables &T, const SgAgParams &P, const SgAgLayou
         int nMatches = 0, nMismatches = 0, nGaps = 0;
         double mp = 1.0;
         const int stride = lay.rowStride();
+        // striped position of colIdx, maintained incrementally (no divisions in the loop): segment, SSE lane, vector
+        int cSeg = colIdx / lay.segLen, cLane = (colIdx % lay.segLen) / lay.numVec, cVec = (colIdx % lay.segLen) % lay.numVec;
         while (rowIdx >= 0 && colIdx >= 0) {
             int matrixIdx = action << 1;
+            const int cIdx = (cSeg * lay.numVec + cVec) * SG_VEC + cLane;
             // A traceback step can land on a cell this call never wrote.  The reference then reads whatever an *earlier*
             // call of the same object left in its never-cleared backtraceAction array (:1374); we keep the array persistent
             // per worker and per direction with the same linear layout, so the same stale bits are read whenever the
             // history is the same (always true within one read; across reads it depends on which thread/warp ran what).
-            uint8_t cell = bt[(size_t)rowIdx * stride + lay.cellIndex(colIdx)];
+            uint8_t cell = bt[(size_t)rowIdx * stride + cIdx];
 #ifdef SG_AG_POISON_CHECK
             if (!lay.computed(rowIdx, colIdx)) out->poisoned = 1;
 #endif
@@ -169,10 +172,12 @@ SG_HDN void sg_ag_finish(const SgTables &T, const SgAgParams &P, const SgAgLayou
                     nMatches++;
                 }
                 rowIdx--; colIdx--;
+                if (--cVec < 0) { cVec = lay.numVec - 1; if (--cLane < 0) { cLane = SG_VEC - 1; cSeg--; } }
             } else if (action == 1) {
                 rowIdx--;
             } else {
                 colIdx--;
+                if (--cVec < 0) { cVec = lay.numVec - 1; if (--cLane < 0) { cLane = SG_VEC - 1; cSeg--; } }
                 action = 2;
             }
             if (prevAction != 0) {

@@ -104,6 +104,7 @@ struct SgScratch {
     // affine gap
     int16_t  *agH, *agHm1, *agE;     // [agCols]
     uint8_t  *agBt[2];               // [agRows*agCols] traceback bits; [0] forward object, [1] reverse object; PERSISTENT across calls
+    int8_t   *agProf;                // [5*agCols] striped query profile of the current affine-gap call (device warp form)
     uint32_t agCols, agRows;
 };
 
@@ -126,6 +127,7 @@ SG_HD size_t sg_scratch_bytes(const SgParams &p)
     b += sg_align_up(SG_MAX_K + 2, 256);
     b += sg_align_up(sizeof(int16_t) * agCols, 256) * 3;
     b += sg_align_up(agRows * agCols, 256) * 2;
+    b += sg_align_up(5 * agCols, 256);
     return b;
 }
 
@@ -151,6 +153,7 @@ SG_HD void sg_scratch_carve(const SgParams &p, uint8_t *base, SgScratch *s)
     s->agE = (int16_t *)q;            q += sg_align_up(sizeof(int16_t) * agCols, 256);
     s->agBt[0] = q;                   q += sg_align_up(agRows * agCols, 256);
     s->agBt[1] = q;                   q += sg_align_up(agRows * agCols, 256);
+    s->agProf = (int8_t *)q;          q += sg_align_up(5 * agCols, 256);
     s->agCols = (uint32_t)agCols;
     s->agRows = (uint32_t)agRows;
 }

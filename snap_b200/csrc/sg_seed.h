@@ -5,7 +5,12 @@
 // BASE_VALUE, reference Tables.cpp:52-58: A=0 G=1 C=2 T=3, everything else 4.
 SG_HD uint32_t sg_base_value(uint8_t c)
 {
-    return c == 'A' ? 0u : c == 'G' ? 1u : c == 'C' ? 2u : c == 'T' ? 3u : 4u;
+    // bits 2:1 of the ASCII code separate A(0) C(1) T(2) G(3); two packed constants give the expected character (to reject
+    // everything else) and SNAP's value (A=0 G=1 C=2 T=3)
+    const uint32_t i = (c >> 1) & 3u;
+    const uint32_t expected = (0x47544341u >> (8u * i)) & 0xffu;
+    const uint32_t value = (0x1320u >> (4u * i)) & 0xfu;
+    return expected == c ? value : 4u;
 }
 
 // rcTranslationTable, reference BaseAligner.cpp:199-210: anything but ACGT becomes 'N'.

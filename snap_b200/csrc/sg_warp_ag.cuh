@@ -71,6 +71,14 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
             }
         }
     }
+    // striped query profile (the reference's qProfile, :921-935 / :348-365) as int8, -128 standing for the INT16_MIN padding
+    int8_t *prof = S.agProf;
+    for (int idx = lane; idx < stride; idx += 32) {
+        const int vec = idx >> 3, ll = idx & 7;
+        const int col = (vec / numVec) * segLen + ll * numVec + (vec % numVec);
+        const uint32_t pb = (col < patternLen) ? sg_base_value(pattern[col]) : 5u;
+        for (uint32_t t = 0; t < 5; t++) prof[t * stride + idx] = (pb == 5u) ? (int8_t)-128 : (int8_t)sg_ag_sub(P, t, pb);
+    }
     __syncwarp();
 
     int bestGlobalAlignmentScore = -1, bestGlobalAlignmentTextOffset = -1;
@@ -80,7 +88,9 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         lay.nRows = i + 1;
         const uint32_t tb = sg_base_value(text[i * dir]);
         uint8_t *btRow = bt + (size_t)i * stride;
+        const int8_t *profRow = prof + tb * stride;
         int myMax = 0;                   // running max of H over the cells this lane committed in this row
+        int myMaxCol = -1;               // ... and the largest column at which this lane saw it
         int X0 = 0;                      // lane 0 of the reference's X register
         int fcarry = 0;                  // F entering the next vector of my SSE lane (identical in the 4 sub-lanes)
 
@@ -122,9 +132,8 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                     int hdiag;
                     if (k == 0) hdiag = (l == 0) ? hInit : (int)Hptr[(vbase + numVec - 1) * SG_VEC + l - 1];
                     else hdiag = Hptr[idx - SG_VEC];
-                    const int col = j * segLen + l * numVec + k;
-                    const int prof = (col < patternLen) ? sg_ag_sub(P, tb, sg_base_value(pattern[col])) : -32768;
-                    const int m = (hdiag > 0) ? sg_sat16(hdiag + prof) : 0;
+                    const int pv = profRow[idx];
+                    const int m = (hdiag > 0) ? sg_sat16(hdiag + (pv == -128 ? -32768 : pv)) : 0;
                     const int e = E[idx];
                     act = (e > m) ? 1 : 0;
                     h1 = m > e ? m : e;
@@ -147,7 +156,8 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                     if (fin > h) { act |= 2; h = fin; }
                     const int f2 = sg_sat16(fin - ext);
                     if (f2 > temp) act |= 32;
-                    if (h > myMax) myMax = h;
+                    const int col = j * segLen + l * numVec + k;
+                    if (h > myMax || (h == myMax && col > myMaxCol)) { myMax = h; myMaxCol = col; }
                     Hm1ptr[idx] = (int16_t)h;
                     btRow[idx] = (uint8_t)act;
                 }
@@ -187,15 +197,18 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                         live = fn > temp;
                     }
                     const unsigned liveMask = __ballot_sync(0xffffffffu, live);
-                    // first vector of this block (in order) at which no SSE lane is live any more
-                    int firstConv = 4;
-                    for (int qq = 3; qq >= 0; qq--) {
-                        if (4 * b + qq < nVecHere && ((liveMask >> (8 * qq)) & 0xffu) == 0) firstConv = qq;
-                    }
-                    if (valid && q <= firstConv) {
+                    // first vector of this block (in order) at which no SSE lane is live any more: the lowest all-zero
+                    // byte of the ballot among the valid vectors
+                    int nv = nVecHere - 4 * b; if (nv > 4) nv = 4;
+                    const unsigned zeroBytes = __vcmpeq4(liveMask, 0u) & (nv >= 4 ? 0xffffffffu : ((1u << (8 * nv)) - 1u));
+                    const int firstConv = zeroBytes ? ((__ffs(zeroBytes) - 1) >> 3) : 4;
+                    if (valid && q <= firstConv && (a2 || live)) {      // nothing to write when the cell is unchanged
                         Hm1ptr[idx] = (int16_t)newh;
                         btRow[idx] = (uint8_t)(act | (a2 ? 2 : 0) | (live ? 32 : 0));
-                        if (newh > myMax) myMax = newh;
+                        if (a2) {
+                            const int col = j * segLen + l * numVec + v;
+                            if (newh > myMax || (newh == myMax && col > myMaxCol)) { myMax = newh; myMaxCol = col; }
+                        }
                     }
                     if (firstConv < 4) converged = true;
                 }
@@ -217,21 +230,9 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         if (maxScoreRow == 0) break;
 
         if (maxScoreRow > bestLocalAlignmentScore) {
-            int best = -1;
-            for (int j = segBeg; j <= segEnd; j++) {
-                int nVecHere = numVec;
-                if (banded) {
-                    int lim = bandEnd - j * segLen + 1;
-                    if (lim < nVecHere) nVecHere = lim;
-                }
-                for (int k = q; k < nVecHere; k += 4) {
-                    if (Hm1ptr[(j * numVec + k) * SG_VEC + l] == maxScoreRow) {
-                        int patternOffset = j * segLen + l * numVec + k;
-                        if (patternOffset > best) best = patternOffset;
-                    }
-                }
-            }
-            best = __reduce_max_sync(0xffffffffu, best);
+            // the largest column holding the row maximum (:1137-1148): H only grows within a row, so the (max, column)
+            // pair each lane kept while committing cells is exact
+            const int best = __reduce_max_sync(0xffffffffu, (myMax == maxScoreRow) ? myMaxCol : -1);
             bestLocalAlignmentScore = maxScoreRow;
             bestLocalAlignmentTextOffset = i;
             bestLocalAlignmentPatternOffset = best;

@@ -109,7 +109,10 @@ __global__ void sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long
 // The alignment kernel: persistent grid, one warp per read at a time, reads handed out by an atomic counter.
 // The BaseAligner state machine is inherently sequential, so all 32 lanes execute it uniformly (see sg_warp.cuh)
 // and split the work inside the data-parallel leaves (hash-chain probing of both strands, ...).
-__global__ void __launch_bounds__(256)
+// The register budget (and with it the number of resident warps per SM) is a template parameter so that the host can
+// pick the occupancy that measures best: MB CTAs of 8 warps per SM.
+template <int MB>
+__global__ void __launch_bounds__(256, MB)
 sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratchBase, size_t scratchBytesPerWorker,
                 long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
                 snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next)
@@ -298,7 +301,7 @@ static int require_device(int device)
     if (device < 0 || device >= n) return sg_fail("CUDA device ordinal out of range");
     SG_CUDA(cudaSetDevice(device));
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, sg_align_kernel);
+    e = cudaFuncGetAttributes(&fa, sg_align_kernel<2>);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return sg_fail(std::string("no sm_100a kernel image usable on this device: ") + cudaGetErrorString(e));
@@ -622,8 +625,10 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     cudaDeviceProp prop;
     SG_CUDA(cudaGetDeviceProperties(&prop, a->device));
     a->numSMs = prop.multiProcessorCount;
-    a->blocksPerSM = 4;
+    a->blocksPerSM = 4;              // resident CTAs (of 8 warps) per SM the kernel is compiled for: 2, 3 or 4
     if (const char *e = getenv("SNAPGPU_BLOCKS_PER_SM")) a->blocksPerSM = atoi(e) > 0 ? atoi(e) : 4;
+    if (a->blocksPerSM < 2) a->blocksPerSM = 2;
+    if (a->blocksPerSM > 4) a->blocksPerSM = 4;
     a->nWorkers = a->numSMs * a->blocksPerSM * a->warpsPerBlock;
     if ((int64_t)a->nWorkers > maxBatchReads) {
         int blocks = (int)((maxBatchReads + a->warpsPerBlock - 1) / a->warpsPerBlock);
@@ -671,9 +676,11 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
     if (workers > n) workers = n;
     int blocks = (int)((workers + a->warpsPerBlock - 1) / a->warpsPerBlock);
     if (blocks < 1) blocks = 1;
-    sg_align_kernel<<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, a->d_scratch,
-        a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, d_lens,
-        d_results, d_counters, a->d_next);
+#define SG_LAUNCH(MB) sg_align_kernel<MB><<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, \
+        a->d_scratch, a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, \
+        d_lens, d_results, d_counters, a->d_next)
+    if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
+#undef SG_LAUNCH
     SG_CUDA(cudaGetLastError());
     a->launches++;
     return 0;
