@@ -121,8 +121,73 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
             // f entering vector 0 of this segment: 0, or (X0, 0, ..., 0) passed on from the previous segment (:572)
             fcarry = (banded && j > segBeg) ? (l == 0 ? X0 : 0) : 0;
 
-            // ---------------- main pass, 4 vectors per step ----------------
             const int nBlocks = (nVecHere + 3) >> 2;
+            const int passes = banded ? (SG_VEC - 1) : SG_VEC;
+            if (nBlocks == 1) {
+                // ---- up to 4 vectors in this segment (band half-width <= 15): every lane owns one cell, which stays in
+                //      registers through the main pass and all lazy-F passes and is written once ----
+                const int k = q;
+                const bool valid = k < nVecHere;
+                const int idx = (vbase + k) * SG_VEC + l;
+                int temp = 0, h = 0, act = 0;
+                if (valid) {
+                    int hdiag;
+                    if (k == 0) hdiag = (l == 0) ? hInit : (int)Hptr[(vbase + numVec - 1) * SG_VEC + l - 1];
+                    else hdiag = Hptr[idx - SG_VEC];
+                    const int pv = profRow[idx];
+                    const int m = (hdiag > 0) ? sg_sat16(hdiag + (pv == -128 ? -32768 : pv)) : 0;
+                    const int e = E[idx];
+                    act = (e > m) ? 1 : 0;
+                    h = m > e ? m : e;
+                    const int e2 = sg_sat16(e - ext);
+                    temp = sg_sat16(m - open); if (temp < 0) temp = 0;
+                    if (e2 > temp) act |= 4;
+                    E[idx] = (int16_t)(e2 > temp ? e2 : temp);
+                }
+                const int t0 = sg_shfl(temp, l), t1 = sg_shfl(temp, 8 + l), t2 = sg_shfl(temp, 16 + l), t3 = sg_shfl(temp, 24 + l);
+                int fin = fcarry - q * ext;
+                if (q > 0) { int v = t0 - (q - 1) * ext; if (v > fin) fin = v; }
+                if (q > 1) { int v = t1 - (q - 2) * ext; if (v > fin) fin = v; }
+                if (q > 2) { int v = t2; if (v > fin) fin = v; }
+                if (valid) {
+                    if (fin > h) { act |= 2; h = fin; }
+                    if (sg_sat16(fin - ext) > temp) act |= 32;
+                }
+                int fl = fcarry - nVecHere * ext;            // f register of SSE lane l after the main pass
+                { int v = t0 - (nVecHere - 1) * ext; if (nVecHere > 0 && v > fl) fl = v; }
+                { int v = t1 - (nVecHere - 2) * ext; if (nVecHere > 1 && v > fl) fl = v; }
+                { int v = t2 - (nVecHere - 3) * ext; if (nVecHere > 2 && v > fl) fl = v; }
+                { int v = t3 - (nVecHere - 4) * ext; if (nVecHere > 3 && v > fl) fl = v; }
+                if (fl < 0) fl = 0;
+                const unsigned validBytes = nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u);
+                for (int kk = 0; kk < passes; kk++) {
+                    if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
+                    { int up = sg_shfl(fl, (lane & 24) | ((l + 7) & 7)); fl = (l == 0) ? 0 : up; }
+                    int fv = fl - k * ext; if (fv < 0) fv = 0;
+                    const bool a2 = valid && fv > h;
+                    const int newh = a2 ? fv : h;
+                    int tmp2 = newh - open; if (tmp2 < 0) tmp2 = 0;
+                    int fn = fv - ext; if (fn < 0) fn = 0;
+                    const bool live = valid && fn > tmp2;
+                    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+                    // lowest all-zero byte of the ballot among the valid vectors = first vector at which no lane is live
+                    const unsigned zb = (liveMask - 0x01010101u) & ~liveMask & 0x80808080u & validBytes;
+                    const int firstConv = zb ? ((__ffs(zb) - 1) >> 3) : 4;
+                    if (q <= firstConv) { h = newh; act |= (a2 ? 2 : 0) | (live ? 32 : 0); }
+                    if (firstConv < 4) break;
+                    fl = fl - nVecHere * ext; if (fl < 0) fl = 0;
+                }
+                if (valid) {
+                    const int col = j * segLen + l * numVec + k;
+                    if (h > myMax || (h == myMax && col > myMaxCol)) { myMax = h; myMaxCol = col; }
+                    Hm1ptr[idx] = (int16_t)h;
+                    btRow[idx] = (uint8_t)act;
+                }
+                __syncwarp();
+                continue;
+            }
+
+            // ---------------- main pass, 4 vectors per step ----------------
             for (int b = 0; b < nBlocks; b++) {
                 const int k = 4 * b + q;
                 const bool valid = k < nVecHere;
@@ -175,7 +240,6 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
 
             // ---------------- lazy F (:1080-1112 / :534-569) ----------------
             int fl = fcarry;                 // f register of SSE lane l after the main pass
-            const int passes = banded ? (SG_VEC - 1) : SG_VEC;
             bool converged = false;
             for (int kk = 0; kk < passes && !converged; kk++) {
                 if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
@@ -200,7 +264,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                     // first vector of this block (in order) at which no SSE lane is live any more: the lowest all-zero
                     // byte of the ballot among the valid vectors
                     int nv = nVecHere - 4 * b; if (nv > 4) nv = 4;
-                    const unsigned zeroBytes = __vcmpeq4(liveMask, 0u) & (nv >= 4 ? 0xffffffffu : ((1u << (8 * nv)) - 1u));
+                    const unsigned zeroBytes = (liveMask - 0x01010101u) & ~liveMask & 0x80808080u & (nv >= 4 ? 0xffffffffu : ((1u << (8 * nv)) - 1u));
                     const int firstConv = zeroBytes ? ((__ffs(zeroBytes) - 1) >> 3) : 4;
                     if (valid && q <= firstConv && (a2 || live)) {      // nothing to write when the cell is unchanged
                         Hm1ptr[idx] = (int16_t)newh;

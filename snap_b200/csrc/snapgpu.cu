@@ -63,14 +63,21 @@ struct snapgpu_aligner {
     size_t scratchBytesPerWorker = 0;
     uint8_t *d_scratch = nullptr;
     unsigned long long *d_next = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute stream (all kernels of this aligner are serialised on it: they share the arenas)
+    cudaStream_t streamIn = nullptr, streamOut = nullptr;   // H2D / D2H copy streams of the host-buffer path
     int64_t maxBatchReads = 0;
-    size_t maxBatchBases = 0;
-    // staging
-    char *h_bases = nullptr, *h_quals = nullptr; uint64_t *h_offsets = nullptr; uint32_t *h_lens = nullptr;
-    snapgpu_single_result *h_results = nullptr; snapgpu_counters *h_counters = nullptr;
-    char *d_bases = nullptr, *d_quals = nullptr; uint64_t *d_offsets = nullptr; uint32_t *d_lens = nullptr;
-    snapgpu_single_result *d_results = nullptr; snapgpu_counters *d_counters = nullptr;
+    int64_t chunkReads = 0;              // reads per pipeline stage of snapgpu_align_single
+    size_t chunkBases = 0;
+    // two pipeline slots: while the GPU aligns chunk c the host packs chunk c+1 into the other slot's pinned staging
+    struct Slot {
+        char *h_bases = nullptr, *h_quals = nullptr; uint64_t *h_offsets = nullptr; uint32_t *h_lens = nullptr;
+        snapgpu_single_result *h_results = nullptr;
+        char *d_bases = nullptr, *d_quals = nullptr; uint64_t *d_offsets = nullptr; uint32_t *d_lens = nullptr;
+        snapgpu_single_result *d_results = nullptr;
+        cudaEvent_t evIn = nullptr, evKernel = nullptr, evOut = nullptr;
+        int64_t pendingFirst = -1, pendingCount = 0;    // results waiting in h_results for reads [pendingFirst, +pendingCount)
+    } slot[2];
+    snapgpu_counters *h_counters = nullptr, *d_counters = nullptr;
     int64_t launches = 0;
 };
 
@@ -639,18 +646,29 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     SG_CUDA(cudaMemset(a->d_scratch, 0, a->scratchBytesPerWorker * (size_t)a->nWorkers));
     SG_CUDA(cudaMalloc((void **)&a->d_next, 8));
     SG_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
-    a->maxBatchBases = (size_t)maxBatchReads * (size_t)maxReadLen;
-    SG_CUDA(cudaMallocHost((void **)&a->h_bases, a->maxBatchBases));
-    SG_CUDA(cudaMallocHost((void **)&a->h_quals, a->maxBatchBases));
-    SG_CUDA(cudaMallocHost((void **)&a->h_offsets, (size_t)maxBatchReads * 8));
-    SG_CUDA(cudaMallocHost((void **)&a->h_lens, (size_t)maxBatchReads * 4));
-    SG_CUDA(cudaMallocHost((void **)&a->h_results, (size_t)maxBatchReads * sizeof(snapgpu_single_result)));
+    SG_CUDA(cudaStreamCreateWithFlags(&a->streamIn, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&a->streamOut, cudaStreamNonBlocking));
+    a->chunkReads = 131072;
+    if (const char *e = getenv("SNAPGPU_CHUNK_READS")) a->chunkReads = atoll(e) > 0 ? atoll(e) : a->chunkReads;
+    if (a->chunkReads > maxBatchReads) a->chunkReads = maxBatchReads;
+    a->chunkBases = (size_t)a->chunkReads * (size_t)maxReadLen;
+    for (int k = 0; k < 2; k++) {
+        snapgpu_aligner::Slot &sl = a->slot[k];
+        SG_CUDA(cudaMallocHost((void **)&sl.h_bases, a->chunkBases));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_quals, a->chunkBases));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_offsets, (size_t)a->chunkReads * 8));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_lens, (size_t)a->chunkReads * 4));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_results, (size_t)a->chunkReads * sizeof(snapgpu_single_result)));
+        SG_CUDA(cudaMalloc((void **)&sl.d_bases, a->chunkBases));
+        SG_CUDA(cudaMalloc((void **)&sl.d_quals, a->chunkBases));
+        SG_CUDA(cudaMalloc((void **)&sl.d_offsets, (size_t)a->chunkReads * 8));
+        SG_CUDA(cudaMalloc((void **)&sl.d_lens, (size_t)a->chunkReads * 4));
+        SG_CUDA(cudaMalloc((void **)&sl.d_results, (size_t)a->chunkReads * sizeof(snapgpu_single_result)));
+        SG_CUDA(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&sl.evKernel, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&sl.evOut, cudaEventDisableTiming));
+    }
     SG_CUDA(cudaMallocHost((void **)&a->h_counters, sizeof(snapgpu_counters)));
-    SG_CUDA(cudaMalloc((void **)&a->d_bases, a->maxBatchBases));
-    SG_CUDA(cudaMalloc((void **)&a->d_quals, a->maxBatchBases));
-    SG_CUDA(cudaMalloc((void **)&a->d_offsets, (size_t)maxBatchReads * 8));
-    SG_CUDA(cudaMalloc((void **)&a->d_lens, (size_t)maxBatchReads * 4));
-    SG_CUDA(cudaMalloc((void **)&a->d_results, (size_t)maxBatchReads * sizeof(snapgpu_single_result)));
     SG_CUDA(cudaMalloc((void **)&a->d_counters, sizeof(snapgpu_counters)));
     *out = a;
     return 0;
@@ -660,11 +678,20 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
 {
     if (!a) return;
     cudaSetDevice(a->device);
-    if (a->stream) { cudaStreamSynchronize(a->stream); cudaStreamDestroy(a->stream); }
+    cudaDeviceSynchronize();
+    if (a->stream) cudaStreamDestroy(a->stream);
+    if (a->streamIn) cudaStreamDestroy(a->streamIn);
+    if (a->streamOut) cudaStreamDestroy(a->streamOut);
     cudaFree(a->d_scratch); cudaFree(a->d_next);
-    cudaFreeHost(a->h_bases); cudaFreeHost(a->h_quals); cudaFreeHost(a->h_offsets); cudaFreeHost(a->h_lens);
-    cudaFreeHost(a->h_results); cudaFreeHost(a->h_counters);
-    cudaFree(a->d_bases); cudaFree(a->d_quals); cudaFree(a->d_offsets); cudaFree(a->d_lens); cudaFree(a->d_results); cudaFree(a->d_counters);
+    for (int k = 0; k < 2; k++) {
+        snapgpu_aligner::Slot &sl = a->slot[k];
+        cudaFreeHost(sl.h_bases); cudaFreeHost(sl.h_quals); cudaFreeHost(sl.h_offsets); cudaFreeHost(sl.h_lens); cudaFreeHost(sl.h_results);
+        cudaFree(sl.d_bases); cudaFree(sl.d_quals); cudaFree(sl.d_offsets); cudaFree(sl.d_lens); cudaFree(sl.d_results);
+        if (sl.evIn) cudaEventDestroy(sl.evIn);
+        if (sl.evKernel) cudaEventDestroy(sl.evKernel);
+        if (sl.evOut) cudaEventDestroy(sl.evOut);
+    }
+    cudaFreeHost(a->h_counters); cudaFree(a->d_counters);
     delete a;
 }
 
@@ -697,6 +724,20 @@ int snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bas
     return launch_align(a, n, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters, st);
 }
 
+// Drains a pipeline slot: waits for its D2H copy and hands the results to the caller's buffer.
+static int drain_slot(snapgpu_aligner *a, int k, snapgpu_single_result *results)
+{
+    snapgpu_aligner::Slot &sl = a->slot[k];
+    if (sl.pendingCount == 0) return 0;
+    SG_CUDA(cudaEventSynchronize(sl.evOut));
+    memcpy(results + sl.pendingFirst, sl.h_results, (size_t)sl.pendingCount * sizeof(snapgpu_single_result));
+    for (int64_t i = 0; i < sl.pendingCount; i++) {
+        if (sl.h_results[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+    }
+    sl.pendingCount = 0;
+    return 0;
+}
+
 int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
                          const uint32_t *lens, snapgpu_single_result *results, snapgpu_counters *counters)
 {
@@ -704,34 +745,59 @@ int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const
     if (n < 0 || n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads");
     if (n == 0) return 0;
     SG_CUDA(cudaSetDevice(a->device));
-    // pack into pinned staging (reads need not be contiguous in the caller's buffers)
-    size_t total = 0;
-    for (int64_t i = 0; i < n; i++) {
-        if (lens[i] > SNAPGPU_MAX_READ_LENGTH) return sg_fail("read longer than MAX_READ_LENGTH");
-        if (total + lens[i] > a->maxBatchBases) return sg_fail("batch holds more bases than the aligner was sized for");
-        memcpy(a->h_bases + total, bases + offsets[i], lens[i]);
-        memcpy(a->h_quals + total, quals + offsets[i], lens[i]);
-        a->h_offsets[i] = total;
-        a->h_lens[i] = lens[i];
-        total += lens[i];
+    SG_CUDA(cudaMemsetAsync(a->d_counters, 0, sizeof(snapgpu_counters), a->stream));
+    // Software pipeline over chunks of reads, two slots: pack chunk c+1 into pinned staging on the host and copy it in
+    // while the GPU aligns chunk c and chunk c-1's results stream out.  Kernels stay on one stream (they share the arenas).
+    int64_t done = 0;
+    int c = 0;
+    while (done < n) {
+        const int k = c & 1;
+        snapgpu_aligner::Slot &sl = a->slot[k];
+        if (drain_slot(a, k, results)) return 1;                    // slot k was used by chunk c-2
+        int64_t m = 0; size_t total = 0;
+        while (done + m < n && m < a->chunkReads) {
+            const uint32_t len = lens[done + m];
+            if (len > SNAPGPU_MAX_READ_LENGTH) return sg_fail("read longer than MAX_READ_LENGTH");
+            if (total + len > a->chunkBases) break;
+            sl.h_offsets[m] = total; sl.h_lens[m] = len;
+            total += len; m++;
+        }
+        if (m == 0) return sg_fail("a read does not fit the aligner's staging buffers");
+        // reads that are back to back in the caller's buffers (the common case) are packed with one memcpy each way
+        const uint64_t first = offsets[done];
+        bool contiguous = true;
+        for (int64_t i = 0; i < m; i++) { if (offsets[done + i] != first + sl.h_offsets[i]) { contiguous = false; break; } }
+        if (contiguous) {
+            memcpy(sl.h_bases, bases + first, total);
+            memcpy(sl.h_quals, quals + first, total);
+        } else {
+            for (int64_t i = 0; i < m; i++) {
+                memcpy(sl.h_bases + sl.h_offsets[i], bases + offsets[done + i], sl.h_lens[i]);
+                memcpy(sl.h_quals + sl.h_offsets[i], quals + offsets[done + i], sl.h_lens[i]);
+            }
+        }
+        SG_CUDA(cudaMemcpyAsync(sl.d_bases, sl.h_bases, total, cudaMemcpyHostToDevice, a->streamIn));
+        SG_CUDA(cudaMemcpyAsync(sl.d_quals, sl.h_quals, total, cudaMemcpyHostToDevice, a->streamIn));
+        SG_CUDA(cudaMemcpyAsync(sl.d_offsets, sl.h_offsets, (size_t)m * 8, cudaMemcpyHostToDevice, a->streamIn));
+        SG_CUDA(cudaMemcpyAsync(sl.d_lens, sl.h_lens, (size_t)m * 4, cudaMemcpyHostToDevice, a->streamIn));
+        SG_CUDA(cudaEventRecord(sl.evIn, a->streamIn));
+        SG_CUDA(cudaStreamWaitEvent(a->stream, sl.evIn, 0));
+        if (launch_align(a, m, sl.d_bases, sl.d_quals, sl.d_offsets, sl.d_lens, sl.d_results, a->d_counters, a->stream)) return 1;
+        SG_CUDA(cudaEventRecord(sl.evKernel, a->stream));
+        SG_CUDA(cudaStreamWaitEvent(a->streamOut, sl.evKernel, 0));
+        SG_CUDA(cudaMemcpyAsync(sl.h_results, sl.d_results, (size_t)m * sizeof(snapgpu_single_result), cudaMemcpyDeviceToHost, a->streamOut));
+        SG_CUDA(cudaEventRecord(sl.evOut, a->streamOut));
+        sl.pendingFirst = done; sl.pendingCount = m;
+        done += m;
+        c++;
     }
-    cudaStream_t st = a->stream;
-    SG_CUDA(cudaMemcpyAsync(a->d_bases, a->h_bases, total, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(a->d_quals, a->h_quals, total, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(a->d_offsets, a->h_offsets, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemcpyAsync(a->d_lens, a->h_lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMemsetAsync(a->d_counters, 0, sizeof(snapgpu_counters), st));
-    if (launch_align(a, n, a->d_bases, a->d_quals, a->d_offsets, a->d_lens, a->d_results, a->d_counters, st)) return 1;
-    SG_CUDA(cudaMemcpyAsync(a->h_results, a->d_results, (size_t)n * sizeof(snapgpu_single_result), cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaMemcpyAsync(a->h_counters, a->d_counters, sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
-    memcpy(results, a->h_results, (size_t)n * sizeof(snapgpu_single_result));
-    for (int64_t i = 0; i < n; i++) {
-        if (results[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
-    }
+    if (drain_slot(a, c & 1, results)) return 1;
+    if (drain_slot(a, (c + 1) & 1, results)) return 1;
+    SG_CUDA(cudaMemcpyAsync(a->h_counters, a->d_counters, sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, a->stream));
+    SG_CUDA(cudaStreamSynchronize(a->stream));
     if (counters) {
         int64_t *dst = (int64_t *)counters; const int64_t *src = (const int64_t *)a->h_counters;
-        for (size_t k = 0; k < sizeof(snapgpu_counters) / 8; k++) dst[k] += src[k];
+        for (size_t k2 = 0; k2 < sizeof(snapgpu_counters) / 8; k2++) dst[k2] += src[k2];
     }
     return 0;
 }
