@@ -79,7 +79,7 @@ struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260
             bestScoreMatchProbability = el->matchProbabilityForBestScore;
         }
     }
-    SG_HD void fillIn(const SgTables &T, snapgpu_single_result *r, int popularSeedsSkipped) const {   // :2301-2323
+    SG_HDN void fillIn(const SgTables &T, snapgpu_single_result *r, int popularSeedsSkipped) const {   // :2301-2323
         r->agScore = bestScoreAGScore;
         r->basesClippedAfter = bestScoreBasesClippedAfter;
         r->basesClippedBefore = bestScoreBasesClippedBefore;
@@ -218,7 +218,9 @@ struct SgAligner {
     SG_HD void clearCandidates() {
 #if defined(__CUDA_ARCH__)
         if (lane >= 0) {
+            #pragma unroll 1
             for (uint32_t i = lane; i < nUsedElements; i += 32) sc.table[sc.pool[i].slot] = 0;
+            #pragma unroll 1
             for (uint32_t i = 1 + lane; i < pr->numWeightLists; i += 32) {
                 sc.listNext[i] = SG_SENTINEL | i;
                 sc.listPrev[i] = SG_SENTINEL | i;
@@ -529,7 +531,9 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
 #if defined(__CUDA_ARCH__)
     if (A.lane >= 0) {
         // the four derived strings (:388-396) are built 32 bases per step; every lane reads all of them afterwards
+        #pragma unroll 1
         for (uint32_t i = A.lane; i < (readLen + 7) / 8; i += 32) A.sc.seedUsed[i] = 0;
+        #pragma unroll 1
         for (uint32_t i = A.lane; i < readLen; i += 32) {
             uint8_t baseByte = readData[i];
             uint8_t complement = sg_complement(baseByte);
@@ -622,6 +626,7 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
                 uint32_t offset = (direction == 0) ? nextSeedToTest : (readLen - seedLen - nextSeedToTest);
                 uint32_t limit = hits.nHits[direction] < pr.maxHits ? hits.nHits[direction] : pr.maxHits;
                 A.work.overflowWords += (hits.nHits[direction] > 1) ? limit : 0;
+                #pragma unroll 1
                 for (uint32_t i = 0; i < limit; i++) {
                     uint32_t genomeLocationOfThisHit = hits.hits[direction][i] - offset;       // 32-bit wrap like the reference
                     uint32_t ei = A.findElement(genomeLocationOfThisHit, direction);

@@ -30,6 +30,7 @@ struct SgIndexView {
     const uint8_t  *tables;          // all hash tables, entries back to back; table t starts at entry tableStart[t]
     const uint64_t *tableStart;      // [nTables]
     const uint64_t *tableSize;       // [nTables] slots
+    const uint64_t *tableMagic;      // [nTables] floor((2^64-1)/tableSize): h % size by multiply-high (device probe path)
     const uint32_t *overflow;        // overflow table (count, hits descending ...)
     const uint8_t  *bases;           // pointer to genome location 0; [-SG_N_PADDING, nBases+SG_N_PADDING) is readable, padding is 'n'
     const int64_t  *contigStart;     // [nContigs] beginningLocation, ascending

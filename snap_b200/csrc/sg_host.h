@@ -12,7 +12,7 @@
 
 struct SgHostIndex {
     std::vector<uint8_t>  tables;        // repacked: entries of all tables back to back (+8 bytes slack)
-    std::vector<uint64_t> tableStart, tableSize, tableUsed;
+    std::vector<uint64_t> tableStart, tableSize, tableUsed, tableMagic;
     std::vector<uint32_t> overflow;      // +1 word slack
     std::vector<uint8_t>  basesPadded;   // SG_N_PADDING 'n' + bases + SG_N_PADDING 'n'
     std::vector<int64_t>  contigStart;
@@ -25,7 +25,7 @@ struct SgHostIndex {
 
     SgIndexView view() const {           // host-memory view (test build); the CUDA library builds a device one
         SgIndexView v;
-        v.tables = tables.data(); v.tableStart = tableStart.data(); v.tableSize = tableSize.data();
+        v.tables = tables.data(); v.tableStart = tableStart.data(); v.tableSize = tableSize.data(); v.tableMagic = tableMagic.data();
         v.overflow = overflow.data(); v.bases = basesPadded.data() + SG_N_PADDING; v.contigStart = contigStart.data();
         v.nBases = nBases; v.altFirstLocation = altFirstLocation; v.overflowSize = overflowSize;
         v.nContigs = (uint32_t)contigStart.size(); v.seedLen = seedLen; v.keyBytes = keyBytes; v.nTables = nTables;
@@ -133,6 +133,8 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
         }
         if (off != buf.size()) { err = "GenomeIndexHash has trailing bytes"; return false; }
         ix.totalSlots = slots;
+        ix.tableMagic.assign(nHashTables, 0);
+        for (unsigned t = 0; t < nHashTables; t++) ix.tableMagic[t] = ~0ULL / ix.tableSize[t];
     }
     ix.tables.assign((size_t)ix.totalSlots * ix.entryBytes + 16, 0);
     {

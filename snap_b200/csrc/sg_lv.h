@@ -33,6 +33,7 @@ SG_HD int sg_lv_cpm(const uint8_t *pattern, int pi, const uint8_t *text, int ti,
     if (availBytes <= 0) return availBytes;
 #if defined(__CUDA_ARCH__)
     if (lane >= 0) {
+        #pragma unroll 1
         for (int n = 0; n < availBytes; n += 32) {
             int i = n + lane;
             bool mism = (i < availBytes) ? (pattern[pi + i] != text[(ti + i) * dir]) : true;
@@ -46,6 +47,7 @@ SG_HD int sg_lv_cpm(const uint8_t *pattern, int pi, const uint8_t *text, int ti,
     }
 #endif
     int n = 0;
+    #pragma unroll 1
     while (n < availBytes && pattern[pi + n] == text[(ti + n) * dir]) n++;
     return n;
 }
@@ -85,34 +87,22 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
         int d = 0;
         for (int i = 0; d != e + 1; i++, d = (d > 0 ? -d : -d + 1)) {
             int endd = patternLen < textLen - d ? patternLen : textLen - d;
-            int best = st.getL(e - 1, d) + 1;                          // up
+            // the three ways into L(e,d): 'X' up from (e-1,d) +1, 'D' from (e-1,d-1), 'I' from (e-1,d+1) +1; each is extended
+            // along the diagonal by countPerfectMatch if its first characters agree (the reference compares *p == *t even
+            // at index patternLen, where the extension is min(.., 0) = 0).  One loop body instead of three copies.
+            int best = -3;
             uint8_t a = 'X';
-            if (best >= 0 && best < patternLen + 1) {
-                // the reference compares *p == *t even at best == patternLen (then extends by min(.., 0) = 0)
-                if (endd - best > 0) {
-                    if (pattern[best] == text[(d + best) * dir]) best += sg_lv_cpm(pattern, best, text, d + best, dir, endd - best, lane);
-                } else if (endd - best < 0) {
-                    if (pattern[best] == text[(d + best) * dir]) best += endd - best;
+            #pragma unroll 1
+            for (int way = 0; way < 3; way++) {
+                int start = (way == 0) ? st.getL(e - 1, d) + 1 : (way == 1) ? st.getL(e - 1, d - 1) : st.getL(e - 1, d + 1) + 1;
+                if (start >= 0 && endd != start) {
+                    if (pattern[start] == text[(d + start) * dir]) {
+                        start += (endd - start > 0) ? sg_lv_cpm(pattern, start, text, d + start, dir, endd - start, lane) : (endd - start);
+                    }
                 }
+                if (way == 0) { best = start; }
+                else if (start > best) { best = start; a = (way == 1) ? 'D' : 'I'; }
             }
-            int left = st.getL(e - 1, d - 1);
-            if (left >= 0) {
-                if (endd - left > 0) {
-                    if (pattern[left] == text[(d + left) * dir]) left += sg_lv_cpm(pattern, left, text, d + left, dir, endd - left, lane);
-                } else if (endd - left < 0) {
-                    if (pattern[left] == text[(d + left) * dir]) left += endd - left;
-                }
-            }
-            if (left > best) { best = left; a = 'D'; }
-            int right = st.getL(e - 1, d + 1) + 1;
-            if (right >= 0) {
-                if (endd - right > 0) {
-                    if (pattern[right] == text[(d + right) * dir]) right += sg_lv_cpm(pattern, right, text, d + right, dir, endd - right, lane);
-                } else if (endd - right < 0) {
-                    if (pattern[right] == text[(d + right) * dir]) right += endd - right;
-                }
-            }
-            if (right > best) { best = right; a = 'I'; }
             st.setA(e, d, a);
 
             if (best == patternLen) {

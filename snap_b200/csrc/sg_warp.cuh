@@ -60,14 +60,24 @@ __device__ __forceinline__ void sg_warp_lookup_seed32(const SgIndexView &ix, uin
     const uint32_t table = (ix.keyBytes == 8) ? 0u : (uint32_t)(s >> keyBits);
     const uint64_t size = ix.tableSize[table];
     const uint64_t base = ix.tableStart[table];
-    const uint64_t home = sg_fmix64(low) % size;
+    // hash % size without a 64-bit division: multiply-high by floor((2^64-1)/size), then at most two corrections
+    uint64_t home;
+    {
+        const uint64_t hsh = sg_fmix64(low);
+        const uint64_t qq = __umul64hi(hsh, ix.tableMagic[table]);
+        home = hsh - qq * size;
+        if (home >= size) home -= size;
+        if (home >= size) home -= size;
+    }
 
     uint64_t foundSlot[2] = {~0ULL, ~0ULL};
     bool done[2] = {false, large};
     uint32_t round = 0;
     while (!(done[0] && done[1])) {
         uint32_t k = round * chainWidth + myK0;
-        uint64_t slot = base + (home + sg_probe_offset(k)) % size;
+        uint64_t pos = home + sg_probe_offset(k);       // probe offsets are small: wrap with subtractions, falling back to % for tiny tables
+        if (pos >= size) { pos -= size; if (pos >= size) pos %= size; }
+        uint64_t slot = base + pos;
         uint32_t v; uint64_t key;
         bool active = !done[myChain] && (uint64_t)k <= size + 5;
         if (active) sg_entry_load(ix, slot, &v, &key); else { v = 0; key = ~0ULL; }

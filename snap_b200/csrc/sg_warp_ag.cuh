@@ -83,7 +83,11 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
 
     int bestGlobalAlignmentScore = -1, bestGlobalAlignmentTextOffset = -1;
     int bestLocalAlignmentScore = -1, bestLocalAlignmentTextOffset = -1, bestLocalAlignmentPatternOffset = -1;
+    const int globalIdx = lay.cellIndex(patternLen - 1);     // where the last pattern column lives (constant)
+    // band edges advance by at most one column per row, so the segments they fall in are tracked without dividing
+    int segBegTrack = 0, segEndTrack = banded ? (((w < patternLen - 1) ? w : (patternLen - 1)) / segLen) : 0;
 
+    #pragma unroll 1
     for (int i = 0; i < textLen; i++) {
         lay.nRows = i + 1;
         const uint32_t tb = sg_base_value(text[i * dir]);
@@ -98,10 +102,13 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         if (banded) {
             bandBeg = (i - w) > 0 ? (i - w) : 0;
             bandEnd = (i + w) < (patternLen - 1) ? (i + w) : (patternLen - 1);
-            segBeg = bandBeg / segLen;
-            segEnd = bandEnd / segLen;
+            while (bandBeg >= (segBegTrack + 1) * segLen) segBegTrack++;
+            while (bandEnd >= (segEndTrack + 1) * segLen) segEndTrack++;
+            segBeg = segBegTrack;
+            segEnd = segEndTrack;
         }
 
+        #pragma unroll 1
         for (int j = segBeg; j <= segEnd; j++) {
             const int vbase = j * numVec;
             int nVecHere = numVec;
@@ -160,6 +167,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                 { int v = t3 - (nVecHere - 4) * ext; if (nVecHere > 3 && v > fl) fl = v; }
                 if (fl < 0) fl = 0;
                 const unsigned validBytes = nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u);
+                #pragma unroll 1
                 for (int kk = 0; kk < passes; kk++) {
                     if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
                     { int up = sg_shfl(fl, (lane & 24) | ((l + 7) & 7)); fl = (l == 0) ? 0 : up; }
@@ -284,7 +292,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         const int maxScoreRow = __reduce_max_sync(0xffffffffu, myMax);
 
         if (!banded || bandEnd == patternLen - 1) {
-            int globalAlignmentScore = Hm1ptr[lay.cellIndex(banded ? bandEnd : patternLen - 1)];
+            int globalAlignmentScore = Hm1ptr[globalIdx];
             if (globalAlignmentScore >= bestGlobalAlignmentScore) {
                 bestGlobalAlignmentScore = globalAlignmentScore;
                 bestGlobalAlignmentTextOffset = i;

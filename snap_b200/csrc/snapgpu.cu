@@ -39,7 +39,7 @@ struct snapgpu_index {
     SgIndexView view;                    // device pointers
     snapgpu_index_info info;
     uint8_t  *d_tables = nullptr;
-    uint64_t *d_tableStart = nullptr, *d_tableSize = nullptr;
+    uint64_t *d_tableStart = nullptr, *d_tableSize = nullptr, *d_tableMagic = nullptr;
     uint32_t *d_overflow = nullptr;
     uint8_t  *d_basesPadded = nullptr;
     int64_t  *d_contigStart = nullptr;
@@ -328,6 +328,7 @@ static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
     UP(ix->d_tables, h.tables.data(), h.tables.size());
     UP(ix->d_tableStart, h.tableStart.data(), h.tableStart.size() * 8);
     UP(ix->d_tableSize, h.tableSize.data(), h.tableSize.size() * 8);
+    UP(ix->d_tableMagic, h.tableMagic.data(), h.tableMagic.size() * 8);
     UP(ix->d_overflow, h.overflow.data(), h.overflow.size() * 4);
     UP(ix->d_basesPadded, h.basesPadded.data(), h.basesPadded.size());
     UP(ix->d_contigStart, h.contigStart.data(), h.contigStart.size() * 8);
@@ -335,7 +336,7 @@ static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
     UP(ix->d_tables_prob, &ix->h_tables_prob, sizeof(SgTables));
     #undef UP
     SgIndexView v = h.view();
-    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.overflow = ix->d_overflow;
+    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.tableMagic = ix->d_tableMagic; v.overflow = ix->d_overflow;
     v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart;
     ix->view = v;
     memset(&ix->info, 0, sizeof(ix->info));
@@ -405,18 +406,20 @@ static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const i
     if ((unsigned long long)nBases + overflowWords > 0xfffffff0ULL) return sg_fail("snapgpu_index_build: ran out of overflow table namespace (GenomeIndex.cpp:688)");
 
     // table sizes: the reference sizes tables at (1 + slack) x expected content with slack 0.3 (GenomeIndex.cpp:1084-1100)
-    std::vector<uint64_t> tstart(nTables), tsize(nTables);
+    std::vector<uint64_t> tstart(nTables), tsize(nTables), tmagic(nTables);
     uint64_t slots = 0;
     for (uint32_t t = 0; t < nTables; t++) {
         uint64_t sz = (uint64_t)((double)stats[t] * 1.3) + 1;
         if (sz < 100) sz = 100;
-        tstart[t] = slots; tsize[t] = sz; slots += sz;
+        tstart[t] = slots; tsize[t] = sz; tmagic[t] = ~0ULL / sz; slots += sz;
     }
     size_t hbm = 0;
     SG_CUDA(cudaMalloc((void **)&ix->d_tables, slots * 8 + 16)); hbm += slots * 8 + 16;
     sg_build_fill_kernel<<<grid, 256>>>((unsigned long long *)ix->d_tables, (long long)slots + 2, 0x00000000ffffffffULL);
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaMalloc((void **)&ix->d_tableStart, nTables * 8)); SG_CUDA(cudaMalloc((void **)&ix->d_tableSize, nTables * 8));
+    SG_CUDA(cudaMalloc((void **)&ix->d_tableMagic, nTables * 8));
+    SG_CUDA(cudaMemcpy(ix->d_tableMagic, tmagic.data(), nTables * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(ix->d_tableStart, tstart.data(), nTables * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(ix->d_tableSize, tsize.data(), nTables * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMalloc((void **)&ix->d_overflow, (size_t)(overflowWords + 4) * 4)); hbm += (size_t)(overflowWords + 4) * 4;
@@ -439,7 +442,7 @@ static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const i
 
     SgIndexView v;
     memset(&v, 0, sizeof(v));
-    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.overflow = ix->d_overflow;
+    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.tableMagic = ix->d_tableMagic; v.overflow = ix->d_overflow;
     v.bases = d_bases; v.contigStart = ix->d_contigStart; v.nBases = nBases; v.altFirstLocation = LLONG_MAX;
     v.overflowSize = overflowWords; v.nContigs = nContigs; v.seedLen = seedLen; v.keyBytes = keyBytes; v.nTables = nTables;
     v.large = 0; v.entryBytes = 8; v.chromosomePadding = chromosomePadding; v.invalidValue = 0xffffffffu;
@@ -572,7 +575,7 @@ void snapgpu_index_close(snapgpu_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    cudaFree(ix->d_tables); cudaFree(ix->d_tableStart); cudaFree(ix->d_tableSize); cudaFree(ix->d_overflow);
+    cudaFree(ix->d_tables); cudaFree(ix->d_tableStart); cudaFree(ix->d_tableSize); cudaFree(ix->d_tableMagic); cudaFree(ix->d_overflow);
     cudaFree(ix->d_basesPadded); cudaFree(ix->d_contigStart); cudaFree(ix->d_tables_prob);
     delete ix;
 }
