@@ -109,6 +109,57 @@ typedef struct snapgpu_index_info {
     uint64_t hbmBytes;                  /* bytes resident on the device for this index */
 } snapgpu_index_info;
 
+/*
+ * POD mirror of PairedAlignmentResult (reference SNAPLib/AlignmentResult.h:86-129), field for field, minus the two
+ * timing fields.  Index [r] = read r of the pair.
+ */
+typedef struct snapgpu_paired_result {
+    int32_t  status[2];
+    int32_t  direction[2];
+    int64_t  location[2];
+    int64_t  origLocation[2];
+    int32_t  score[2];
+    int32_t  scorePriorToClipping[2];
+    int32_t  mapq[2];
+    int32_t  clippingForReadAdjustment[2];
+    int32_t  usedAffineGapScoring[2];
+    int32_t  basesClippedBefore[2];
+    int32_t  basesClippedAfter[2];
+    int32_t  agScore[2];
+    int32_t  supplementary[2];
+    int32_t  seedOffset[2];
+    int32_t  lvIndels[2];
+    int32_t  usedGaplessClipping[2];
+    int32_t  refSpan[2];
+    int32_t  liftover[2];
+    uint32_t popularSeedsSkipped[2];
+    int32_t  alignedAsPair;
+    int32_t  agForcedSingleAlignerCall;
+    double   matchProbability[2];
+    double   probabilityAllPairs;
+} snapgpu_paired_result;                /* 200 bytes */
+
+/*
+ * The extra options `snap paired` reads (reference SNAPLib/PairedAligner.cpp:228-243, 288-364, AlignerOptions.cpp:101-111).
+ * The shared ones come from snapgpu_params (for pairs: maxDist -d, numSeedsFromCommandLine -n (8), maxHits -h).
+ */
+typedef struct snapgpu_paired_params {
+    uint32_t struct_size;
+    int32_t  minSpacing;                /* -s min (0)    */
+    uint32_t maxSpacing;                /* -s max (1000) */
+    uint32_t intersectingAlignerMaxHits;/* -H   (4000)   */
+    uint32_t maxCandidatePoolSize;      /* -mcp (1000000)*/
+    uint32_t maxSeedsSingleEnd;         /* -N   (25) seeds for the chimeric single-end fallback */
+    uint32_t maxDistForIndels;          /* -i   (40)     */
+    int32_t  forceSpacing;              /* -fs  (0)      */
+    int32_t  minScoreRealignment;       /* (3)  */
+    int32_t  minScoreGapRealignmentALT; /* (3)  */
+    int32_t  minAGScoreImprovement;     /* (24; 15 without soft clipping, PairedAligner.cpp:388) */
+    int32_t  enableHammingScoringBaseAligner; /* -eh / -eh- (1) */
+    int32_t  useSoftClipping;           /* -hc- / -hc (1) */
+    int32_t  flattenMAPQAtOrBelow;      /* -fmb (3) */
+} snapgpu_paired_params;
+
 /* Per-call work counters (reference BaseAligner.h:106-111 + AlignerStats.h:41-97 subset). */
 typedef struct snapgpu_counters {
     int64_t totalReads;

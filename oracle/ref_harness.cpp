@@ -21,6 +21,8 @@
 #include "LandauVishkin.h"
 #include "AffineGapVectorized.h"
 #include "BaseAligner.h"
+#include "IntersectingPairedEndAligner.h"
+#include "ChimericPairedEndAligner.h"
 #include "AlignerOptions.h"
 #include "Read.h"
 #include "mapq.h"
@@ -380,6 +382,127 @@ double ref_single_align_mt(void *vidx, const snapgpu_params *p, int nThreads, _i
     delete[] args;
     delete[] threads;
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/*
+ * Paired-end stack, constructed exactly like PairedAligner.cpp:547-638: one arena holding the
+ * IntersectingPairedEndAligner, the ChimericPairedEndAligner (with its single-end BaseAligner) and the result /
+ * candidate buffers; align() called with the arguments of PairedAligner.cpp:727-730 (-om unset).
+ */
+struct RefPaired {
+    GenomeIndex *index;
+    BigAllocator *allocator;
+    IntersectingPairedEndAligner *intersecting;
+    ChimericPairedEndAligner *aligner;
+    PairedAlignmentResult *results;
+    PairedAlignmentResult *pairedCandidates;
+    SingleAlignmentResult *singleCandidates;
+    SingleAlignmentResult *singleSecondary;
+    _int64 maxPairedCandidates, maxSingleCandidates;
+    snapgpu_params params;
+    snapgpu_paired_params pp;
+};
+
+void *ref_paired_create(void *vidx, const snapgpu_params *p, const snapgpu_paired_params *pp)
+{
+    ref_init();
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    RefPaired *rp = new RefPaired;
+    rp->index = index; rp->params = *p; rp->pp = *pp;
+    int maxReadSize = MAX_READ_LENGTH;
+    size_t memoryPoolSize = IntersectingPairedEndAligner::getBigAllocatorReservation(index, pp->intersectingAlignerMaxHits, maxReadSize, index->getSeedLength(),
+                                p->numSeedsFromCommandLine, p->seedCoverage, MAX_K, p->extraSearchDepth, pp->maxCandidatePoolSize, -1);
+    memoryPoolSize += ChimericPairedEndAligner::getBigAllocatorReservation(index, maxReadSize, p->maxHits, index->getSeedLength(), pp->maxSeedsSingleEnd, p->seedCoverage,
+                                MAX_K, p->extraSearchDepth, pp->maxCandidatePoolSize, -1);
+    rp->maxPairedCandidates = p->useAffineGap ? 4096 : 0;
+    rp->maxSingleCandidates = p->useAffineGap ? 4096 : 0;
+    memoryPoolSize += (1 + rp->maxPairedCandidates) * sizeof(PairedAlignmentResult) + (rp->maxSingleCandidates) * sizeof(SingleAlignmentResult) + 65536;
+    rp->allocator = new BigAllocator(memoryPoolSize, 16);
+    DisabledOptimizations dis;
+    dis.noUkkonen = p->noUkkonen != 0; dis.noOrderedEvaluation = p->noOrderedEvaluation != 0; dis.noTruncation = p->noTruncation != 0;
+    dis.noEditDistance = p->noEditDistance != 0; dis.noBandedAffineGap = p->noBandedAffineGap != 0;
+    rp->intersecting = new (rp->allocator) IntersectingPairedEndAligner(index, maxReadSize, p->maxHits, p->maxDist, pp->maxDistForIndels, p->numSeedsFromCommandLine,
+        p->seedCoverage, pp->minSpacing, pp->maxSpacing, pp->intersectingAlignerMaxHits, p->extraSearchDepth, pp->maxCandidatePoolSize, -1, rp->allocator, dis,
+        p->useAffineGap != 0, p->ignoreAlignmentAdjustmentsForOm != 0, p->altAwareness != 0, p->maxScoreGapToPreferNonAltAlignment,
+        p->matchReward, p->subPenalty, p->gapOpenPenalty, p->gapExtendPenalty, pp->useSoftClipping != 0);
+    rp->aligner = new (rp->allocator) ChimericPairedEndAligner(index, maxReadSize, p->maxHits, p->maxDist, pp->maxSeedsSingleEnd, p->seedCoverage, p->minWeightToCheck,
+        pp->forceSpacing != 0, p->extraSearchDepth, dis, p->useAffineGap != 0, p->ignoreAlignmentAdjustmentsForOm != 0, p->altAwareness != 0, /*emitALT*/false,
+        rp->intersecting, p->minReadLength, -1, p->maxScoreGapToPreferNonAltAlignment, pp->flattenMAPQAtOrBelow, pp->useSoftClipping != 0,
+        p->matchReward, p->subPenalty, p->gapOpenPenalty, p->gapExtendPenalty, p->fivePrimeEndBonus, p->threePrimeEndBonus,
+        pp->minScoreRealignment, pp->minScoreGapRealignmentALT, pp->minAGScoreImprovement, pp->enableHammingScoringBaseAligner != 0, rp->allocator);
+    rp->results = (PairedAlignmentResult *)rp->allocator->allocate(sizeof(PairedAlignmentResult));
+    rp->singleSecondary = (SingleAlignmentResult *)rp->allocator->allocate(16);
+    rp->pairedCandidates = NULL; rp->singleCandidates = NULL;
+    if (p->useAffineGap) {
+        rp->pairedCandidates = (PairedAlignmentResult *)rp->allocator->allocate(rp->maxPairedCandidates * sizeof(PairedAlignmentResult));
+        rp->singleCandidates = (SingleAlignmentResult *)rp->allocator->allocate(rp->maxSingleCandidates * sizeof(SingleAlignmentResult));
+    }
+    return rp;
+}
+
+void ref_paired_destroy(void *v)
+{
+    RefPaired *rp = (RefPaired *)v;
+    delete rp->allocator;
+    delete rp;
+}
+
+static void copy_paired(const PairedAlignmentResult *r, snapgpu_paired_result *o)
+{
+    memset(o, 0, sizeof(*o));
+    for (int i = 0; i < 2; i++) {
+        o->status[i] = (int)r->status[i]; o->direction[i] = (int)r->direction[i];
+        o->location[i] = GenomeLocationAsInt64(r->location[i]); o->origLocation[i] = GenomeLocationAsInt64(r->origLocation[i]);
+        o->score[i] = r->score[i]; o->scorePriorToClipping[i] = r->scorePriorToClipping[i]; o->mapq[i] = r->mapq[i];
+        o->clippingForReadAdjustment[i] = r->clippingForReadAdjustment[i]; o->usedAffineGapScoring[i] = r->usedAffineGapScoring[i] ? 1 : 0;
+        o->basesClippedBefore[i] = r->basesClippedBefore[i]; o->basesClippedAfter[i] = r->basesClippedAfter[i]; o->agScore[i] = r->agScore[i];
+        o->supplementary[i] = r->supplementary[i] ? 1 : 0; o->seedOffset[i] = r->seedOffset[i]; o->lvIndels[i] = r->lvIndels[i];
+        o->usedGaplessClipping[i] = r->usedGaplessClipping[i] ? 1 : 0; o->refSpan[i] = r->refSpan[i]; o->liftover[i] = r->liftover[i] ? 1 : 0;
+        o->popularSeedsSkipped[i] = r->popularSeedsSkipped[i]; o->matchProbability[i] = r->matchProbability[i];
+    }
+    o->alignedAsPair = r->alignedAsPair ? 1 : 0; o->agForcedSingleAlignerCall = r->agForcedSingleAlignerCall ? 1 : 0;
+    o->probabilityAllPairs = r->probabilityAllPairs;
+}
+
+/*
+ * The per-thread loop body of PairedAligner.cpp:676-790 without the writer.  Pair i = reads 2i and 2i+1 of the batch.
+ * nLV / nAG (optional): locations scored, summed over the call.
+ */
+int ref_paired_align(void *v, _int64 nPairs, const char *bases, const char *quals, const _uint64 *offsets, const unsigned *lens,
+                     snapgpu_paired_result *results, _int64 *nLV, _int64 *nAG)
+{
+    RefPaired *rp = (RefPaired *)v;
+    const snapgpu_params *p = &rp->params;
+    _int64 lv0 = rp->intersecting->getLocationsScoredWithLandauVishkin(), ag0 = rp->intersecting->getLocationsScoredWithAffineGap();
+    for (_int64 i = 0; i < nPairs; i++) {
+        Read r0, r1;
+        r0.init("r/1", 3, bases + offsets[2 * i], quals + offsets[2 * i], lens[2 * i], NULL, 0);
+        r1.init("r/2", 3, bases + offsets[2 * i + 1], quals + offsets[2 * i + 1], lens[2 * i + 1], NULL, 0);
+        bool useful0 = r0.getDataLength() >= p->minReadLength && (int)r0.countOfNs() <= (int)p->maxDist;
+        bool useful1 = r1.getDataLength() >= p->minReadLength && (int)r1.countOfNs() <= (int)p->maxDist;
+        PairedAlignmentResult *res = rp->results;
+        memset(res, 0, sizeof(*res));
+        if (!useful0 && !useful1) {
+            res->status[0] = res->status[1] = NotFound;
+            res->location[0] = res->location[1] = InvalidGenomeLocation;
+            copy_paired(res, &results[i]);
+            continue;
+        }
+        PairedAlignmentResult firstALT;
+        memset(&firstALT, 0, sizeof(firstALT));
+        _int64 nSecondary = 0, nPairedCand = 0, nSingleSecondary[2] = {0, 0}, nSingleCand[2] = {0, 0};
+        bool ok = rp->aligner->align(&r0, &r1, res, &firstALT, p->maxSecondaryAlignmentAdditionalEditDistance, 0, &nSecondary, res + 1,
+            0, 0, &nSingleSecondary[0], &nSingleSecondary[1], rp->singleSecondary,
+            rp->maxPairedCandidates, &nPairedCand, rp->pairedCandidates, rp->maxSingleCandidates, &nSingleCand[0], &nSingleCand[1], rp->singleCandidates, p->maxDist);
+        if (!ok) {
+            fprintf(stderr, "ref_paired_align: candidate buffer overflow on pair %lld (not handled by the harness)\n", (long long)i);
+            return 1;
+        }
+        copy_paired(res, &results[i]);
+    }
+    if (nLV) *nLV += rp->intersecting->getLocationsScoredWithLandauVishkin() - lv0;
+    if (nAG) *nAG += rp->intersecting->getLocationsScoredWithAffineGap() - ag0;
+    return 0;
 }
 
 } // extern "C"

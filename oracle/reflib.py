@@ -170,6 +170,77 @@ def align_mt(index: RefIndex, params: Params, batch, threads: int):
     return res, counters_dict(ctr), float(secs)
 
 
+class PairedParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("minSpacing", C.c_int32), ("maxSpacing", C.c_uint32),
+                ("intersectingAlignerMaxHits", C.c_uint32), ("maxCandidatePoolSize", C.c_uint32), ("maxSeedsSingleEnd", C.c_uint32),
+                ("maxDistForIndels", C.c_uint32), ("forceSpacing", C.c_int32), ("minScoreRealignment", C.c_int32),
+                ("minScoreGapRealignmentALT", C.c_int32), ("minAGScoreImprovement", C.c_int32),
+                ("enableHammingScoringBaseAligner", C.c_int32), ("useSoftClipping", C.c_int32), ("flattenMAPQAtOrBelow", C.c_int32)]
+
+
+def default_paired_params(**kw) -> PairedParams:
+    """`snap paired` 2.0.5 defaults (PairedAligner.cpp:55-57, 228-243; AlignerOptions.cpp:101-102)."""
+    p = PairedParams()
+    p.struct_size = C.sizeof(PairedParams)
+    p.minSpacing, p.maxSpacing = 0, 1000
+    p.intersectingAlignerMaxHits = 4000
+    p.maxCandidatePoolSize = 1000000
+    p.maxSeedsSingleEnd = 25
+    p.maxDistForIndels = 40
+    p.minScoreRealignment, p.minScoreGapRealignmentALT, p.minAGScoreImprovement = 3, 3, 24
+    p.enableHammingScoringBaseAligner = 1
+    p.useSoftClipping = 1
+    p.flattenMAPQAtOrBelow = 3
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def default_params_paired(**kw) -> Params:
+    """The shared options with their paired-end defaults: -n 8 (AlignerOptions.cpp:107-111)."""
+    kw.setdefault("numSeedsFromCommandLine", 8)
+    return default_params(**kw)
+
+
+PAIRED_RESULT_DTYPE = np.dtype([
+    ("status", "<i4", 2), ("direction", "<i4", 2), ("location", "<i8", 2), ("origLocation", "<i8", 2), ("score", "<i4", 2),
+    ("scorePriorToClipping", "<i4", 2), ("mapq", "<i4", 2), ("clippingForReadAdjustment", "<i4", 2), ("usedAffineGapScoring", "<i4", 2),
+    ("basesClippedBefore", "<i4", 2), ("basesClippedAfter", "<i4", 2), ("agScore", "<i4", 2), ("supplementary", "<i4", 2),
+    ("seedOffset", "<i4", 2), ("lvIndels", "<i4", 2), ("usedGaplessClipping", "<i4", 2), ("refSpan", "<i4", 2), ("liftover", "<i4", 2),
+    ("popularSeedsSkipped", "<u4", 2), ("alignedAsPair", "<i4"), ("agForcedSingleAlignerCall", "<i4"),
+    ("matchProbability", "<f8", 2), ("probabilityAllPairs", "<f8"),
+])
+assert PAIRED_RESULT_DTYPE.itemsize == 200
+
+
+class RefPairedAligner:
+    def __init__(self, index: RefIndex, params: Params, pparams: PairedParams):
+        L = lib()
+        L.ref_paired_create.restype = C.c_void_p
+        L.ref_paired_create.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams)]
+        L.ref_paired_destroy.argtypes = [C.c_void_p]
+        L.ref_paired_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        self.index = index
+        self.handle = L.ref_paired_create(index.handle, C.byref(params), C.byref(pparams))
+
+    def align(self, batch):
+        n = batch.n // 2
+        res = np.zeros(n, dtype=PAIRED_RESULT_DTYPE)
+        lvag = np.zeros(2, dtype=np.int64)
+        rc = lib().ref_paired_align(self.handle, n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(res),
+                                    C.c_void_p(lvag.ctypes.data), C.c_void_p(lvag.ctypes.data + 8))
+        if rc != 0:
+            raise RuntimeError("ref_paired_align failed")
+        return res, {"lvCalls": int(lvag[0]), "affineGapCalls": int(lvag[1])}
+
+    def close(self):
+        if self.handle:
+            lib().ref_paired_destroy(self.handle)
+            self.handle = None
+
+
 def lv_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray) -> np.ndarray:
     out = np.zeros(jobs.size, dtype=LV_OUT_DTYPE)
     lib().ref_lv_batch(_p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))

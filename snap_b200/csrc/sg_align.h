@@ -107,6 +107,7 @@ struct SgAligner {
     SgAgParams         ag;
     SgWork             work;
     int                lane;         // 0..31 on the device (all lanes run the state machine uniformly); -1 on the host
+    uint32_t           maxK;         // BaseAligner::maxK: pr->maxK unless the paired caller lowered it (setMaxK, BaseAligner.h:118)
 
     // per-read state
     const uint8_t *readData[2], *readQual[2];   // [FORWARD] = input, [RC] = rcRead/rcQual
@@ -128,7 +129,7 @@ struct SgAligner {
     // BaseAligner::scoreLimit (:2555-2570).  All quantities are non-negative, so the reference's mixed
     // signed/unsigned __min chain reduces to plain integer minima.
     SG_HD int scoreLimit(bool forALT) const {
-        int esd = (int)pr->extraSearchDepth, maxK = (int)pr->maxK;
+        int esd = (int)pr->extraSearchDepth, maxK = (int)this->maxK;
         if (pr->noUkkonen) { int v = maxK + esd; return v < SG_MAX_K - 1 ? v : SG_MAX_K - 1; }
         int inner;
         if (forALT) {
@@ -383,7 +384,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                     fin = &A.nonAlt;
                 }
                 primaryResult->score = fin->bestScore;
-                if (fin->bestScore <= (int)pr.maxK) {
+                if (fin->bestScore <= (int)A.maxK) {
                     fin->fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
                     primaryResult->supplementary = 0;
                     return true;
@@ -471,7 +472,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                     A.nonAlt.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
                 }
 
-                if (pr.stopOnFirstHit && (A.all.bestScore <= (int)pr.maxK)) {
+                if (pr.stopOnFirstHit && (A.all.bestScore <= (int)A.maxK)) {
                     (pr.altAwareness ? A.nonAlt : A.all).fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
                     primaryResult->status = SNAPGPU_MULTIPLE_HITS;
                     primaryResult->mapq = 0;
@@ -559,7 +560,7 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
             countOfNs += (baseByte == 'N') ? 1u : 0u;                  // nTable, :212-214
         }
     }
-    if (countOfNs > pr.maxK) {
+    if (countOfNs > A.maxK) {
         return;                      // :398-402
     }
     if (countOfNs > 0) {             // :407-420

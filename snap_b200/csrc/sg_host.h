@@ -250,3 +250,38 @@ static inline bool sg_derive_params(const snapgpu_params &in, unsigned seedLen, 
     p.maxReadLen = maxReadLen;
     return true;
 }
+
+#ifdef SG_WITH_PAIRED
+// snapgpu_params + snapgpu_paired_params -> the parameter blocks of the paired path: `pr` for the intersecting aligner
+// (IntersectingPairedEndAligner ctor, IntersectingPairedEndAligner.cpp:36-100), `prSingle` for the Chimeric aligner's
+// BaseAligner (maxK/2 and -N seeds, ChimericPairedEndAligner.cpp:80-87), `pp` for both.
+static inline bool sg_derive_paired_params(const snapgpu_params &in, const snapgpu_paired_params &pin, unsigned seedLen, uint32_t maxReadLen,
+                                           SgParams &pr, SgParams &prSingle, SgPairedParams &pp, std::string &err)
+{
+    if (pin.struct_size != sizeof(snapgpu_paired_params)) { err = "snapgpu_paired_params.struct_size mismatch (ABI)"; return false; }
+    if (!sg_derive_params(in, seedLen, maxReadLen, pr, err)) return false;
+    snapgpu_params s = in;
+    s.maxDist = in.maxDist / 2;
+    s.numSeedsFromCommandLine = pin.maxSeedsSingleEnd;
+    if (!sg_derive_params(s, seedLen, maxReadLen, prSingle, err)) return false;
+    if (in.stopOnFirstHit) { err = "paired path: stopOnFirstHit is not supported"; return false; }
+#ifndef SG_PAIRED_HAMMING
+    if (pin.useSoftClipping) { err = "paired path: soft clipping (the Hamming/gapless pass) is not implemented; run with useSoftClipping=0 (snap paired -hc)"; return false; }
+#endif
+    memset(&pp, 0, sizeof(pp));
+    pp.minSpacing = pin.minSpacing; pp.maxSpacing = pin.maxSpacing; pp.maxBigHits = pin.intersectingAlignerMaxHits;
+    pp.maxSeedsSingleEnd = pin.maxSeedsSingleEnd; pp.maxKForIndels = pin.maxDistForIndels; pp.forceSpacing = pin.forceSpacing;
+    pp.minScoreRealignment = pin.minScoreRealignment; pp.minScoreGapRealignmentALT = pin.minScoreGapRealignmentALT;
+    pp.minAGScoreImprovement = pin.minAGScoreImprovement; pp.enableHammingScoringBaseAligner = pin.enableHammingScoringBaseAligner;
+    pp.useSoftClip = pin.useSoftClipping; pp.flattenMAPQAtOrBelow = pin.flattenMAPQAtOrBelow;
+    pp.numSeedsFromCommandLine = in.numSeedsFromCommandLine < SG_MAX_MAX_SEEDS ? in.numSeedsFromCommandLine : SG_MAX_MAX_SEEDS;
+    if (0 != pp.numSeedsFromCommandLine) pp.maxSeedsToUse = pp.numSeedsFromCommandLine;
+    else pp.maxSeedsToUse = (unsigned)(SNAPGPU_MAX_READ_LENGTH * in.seedCoverage / seedLen);
+    if (pp.maxSeedsToUse == 0) { err = "no seeds to use"; return false; }
+    uint64_t pool = (uint64_t)pin.intersectingAlignerMaxHits * pp.maxSeedsToUse * 2;
+    if (pool > pin.maxCandidatePoolSize) pool = pin.maxCandidatePoolSize;
+    if (pool < 2 || pool > (1u << 22)) { err = "paired candidate pool size out of range"; return false; }
+    pp.poolSize = (uint32_t)pool;
+    return true;
+}
+#endif

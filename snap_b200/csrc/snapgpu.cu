@@ -129,7 +129,7 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
 
     SgAligner A;
     A.ix = &ix; A.pr = &pr; A.tb = tb;
-    A.lane = lane;
+    A.lane = lane; A.maxK = pr.maxK;
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
     A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;

@@ -186,3 +186,65 @@ def build_reference_index(snap_aligner: str, fasta: str, out_dir: str, seed_len:
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0 or not os.path.exists(os.path.join(out_dir, "GenomeIndexHash")):
         raise RuntimeError("snap-aligner index failed:\n" + res.stdout)
+
+
+def make_pairs(contigs: list[np.ndarray], n_pairs: int, read_len: int, seed: int, insert_mean: float = 400.0, insert_sd: float = 40.0,
+               sub_rate: float = 0.01, ins_rate: float = 0.0005, del_rate: float = 0.0005, chimeric_frac: float = 0.0,
+               n_run_frac: float = 0.0, short_frac: float = 0.0) -> ReadBatch:
+    """FR pairs (insert N(400,40)): read 2i = forward strand of the fragment start, read 2i+1 = reverse
+    complement of the fragment end; half the fragments are flipped.  chimeric_frac: mate drawn from an unrelated place."""
+    rng = np.random.default_rng(seed)
+    nc = len(contigs)
+    clen = np.array([c.size for c in contigs])
+    reads = []
+
+    def mutate(window):
+        out = []
+        j = 0
+        while len(out) < read_len and j < window.size:
+            r = rng.random()
+            if r < del_rate:
+                j += 1
+                continue
+            if r < del_rate + ins_rate:
+                out.append(int(ACGT[rng.integers(0, 4)]))
+                if len(out) >= read_len:
+                    break
+            b = int(window[j])
+            if r >= del_rate + ins_rate and r < del_rate + ins_rate + sub_rate:
+                b = int(ACGT[(int(np.searchsorted(ACGT, b)) + int(rng.integers(1, 4))) % 4])
+            out.append(b)
+            j += 1
+        seq = np.array(out[:read_len], dtype=np.uint8)
+        if seq.size < read_len:
+            seq = np.concatenate([seq, ACGT[rng.integers(0, 4, size=read_len - seq.size)]])
+        return seq
+
+    for _ in range(n_pairs):
+        ci = int(rng.integers(0, nc))
+        ins = int(max(read_len + 10, rng.normal(insert_mean, insert_sd)))
+        pos = int(rng.integers(0, max(1, clen[ci] - ins - 64)))
+        frag = contigs[ci][pos:pos + ins + 48]
+        r1 = mutate(frag[:read_len + 32])
+        tail = frag[max(0, ins - read_len - 32):ins]
+        r2 = mutate(revcomp(tail))
+        if rng.random() < chimeric_frac:
+            cj = int(rng.integers(0, nc))
+            p2 = int(rng.integers(0, max(1, clen[cj] - read_len - 64)))
+            r2 = mutate(revcomp(contigs[cj][p2:p2 + read_len + 32]))
+        if rng.random() < 0.5:
+            r1, r2 = r2, r1
+        pair = []
+        for seq in (r1, r2):
+            if rng.random() < n_run_frac:
+                run = int(rng.integers(1, 13))
+                at = int(rng.integers(0, read_len - run))
+                seq = seq.copy()
+                seq[at:at + run] = ord("N")
+            L = read_len
+            if rng.random() < short_frac:
+                L = int(rng.integers(20, read_len))
+            qual = (rng.integers(20, 41, size=L) + 33).astype(np.uint8)
+            pair.append((seq[:L].tobytes(), qual.tobytes()))
+        reads.extend(pair)
+    return ReadBatch.from_lists(reads)

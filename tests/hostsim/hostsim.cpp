@@ -8,8 +8,10 @@
 #include <string>
 #include <vector>
 #include <string.h>
-#include "../../snap_b200/csrc/sg_host.h"
+#define SG_WITH_PAIRED 1
 #include "../../snap_b200/csrc/sg_align.h"
+#include "../../snap_b200/csrc/sg_paired.h"
+#include "../../snap_b200/csrc/sg_host.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -149,7 +151,7 @@ void *hs_aligner_create(void *vix, const snapgpu_params *params, uint32_t maxRea
                            params->fivePrimeEndBonus, params->threePrimeEndBonus);
     a->A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     a->A.nUsedElements = 0;
-    a->A.lane = -1;
+    a->A.lane = -1; a->A.maxK = a->params.maxK;
     return a;
 }
 
@@ -188,6 +190,72 @@ int hs_align_single(void *v, int64_t n, const char *bases, const char *quals, co
         ctr->nOverflowWordsRead += a->A.work.overflowWords; ctr->lvCalls += a->A.work.lvCalls; ctr->affineGapCalls += a->A.work.agCalls;
         ctr->nHitsIgnoredBecauseOfTooHighPopularity += a->A.work.popularIgnored;
     }
+    return 0;
+}
+
+
+struct HsPaired {
+    HsIndex *index;
+    SgParams pr, prSingle;
+    SgPairedParams pp;
+    SgTables tables;
+    std::vector<uint8_t> scratch, pscratch;
+    SgAligner S;
+    SgPairedAligner P;
+};
+
+void *hs_paired_create(void *vix, const snapgpu_params *params, const snapgpu_paired_params *pparams, uint32_t maxReadLen)
+{
+    HsIndex *ix = (HsIndex *)vix;
+    HsPaired *a = new HsPaired;
+    a->index = ix;
+    if (!sg_derive_paired_params(*params, *pparams, ix->host.seedLen, maxReadLen, a->pr, a->prSingle, a->pp, g_err)) { delete a; return NULL; }
+    sg_init_tables(a->tables, ix->host.seedLen);
+    memset(&a->S, 0, sizeof(a->S));
+    make_scratch(a->prSingle, a->scratch, &a->S.sc);
+    a->S.ix = &ix->view; a->S.pr = &a->prSingle; a->S.tb = &a->tables;
+    a->S.ag = sg_ag_params(params->matchReward, params->subPenalty, params->gapOpenPenalty, params->gapExtendPenalty,
+                           params->fivePrimeEndBonus, params->threePrimeEndBonus);
+    a->S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    a->S.lane = -1; a->S.maxK = a->prSingle.maxK;
+    memset(&a->P, 0, sizeof(a->P));
+    a->pscratch.assign(sg_paired_scratch_bytes(a->pr, a->pp) + 256, 0);
+    sg_paired_scratch_carve(a->pr, a->pp, (uint8_t *)(((uintptr_t)a->pscratch.data() + 255) & ~(uintptr_t)255), &a->P.ps);
+    a->P.single = &a->S; a->P.ix = &ix->view; a->P.pr = &a->pr; a->P.pp = &a->pp; a->P.tb = &a->tables;
+    a->P.ag = a->S.ag; a->P.lane = -1; a->P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    return a;
+}
+
+void hs_paired_destroy(void *v) { delete (HsPaired *)v; }
+
+// Same contract as oracle ref_paired_align: pair i = reads 2i, 2i+1; the pre-filter of PairedAligner.cpp:669-707.
+int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
+                    snapgpu_paired_result *results, int64_t *nLV, int64_t *nAG)
+{
+    HsPaired *a = (HsPaired *)v;
+    a->P.lvCalls = a->P.agCalls = 0;
+    memset(&a->S.work, 0, sizeof(a->S.work));
+    for (int64_t i = 0; i < nPairs; i++) {
+        snapgpu_paired_result *r = &results[i];
+        memset(r, 0, sizeof(*r));
+        const uint8_t *rb[2], *rq[2]; uint32_t ln[2]; bool useful[2];
+        for (int w = 0; w < 2; w++) {
+            rb[w] = (const uint8_t *)bases + offsets[2 * i + w]; rq[w] = (const uint8_t *)quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w];
+            if (ln[w] > a->pr.maxReadLen) { g_err = "read longer than maxReadLen"; return 1; }
+            uint32_t countOfNs = 0;
+            for (uint32_t k = 0; k < ln[w]; k++) countOfNs += (rb[w][k] == 'N');
+            useful[w] = ln[w] >= a->pr.minReadLength && countOfNs <= a->pr.maxK;
+        }
+        if (!useful[0] && !useful[1]) {
+            for (int w = 0; w < 2; w++) { r->status[w] = SNAPGPU_NOT_FOUND; r->location[w] = a->P.invalidLocation; }
+            continue;
+        }
+        a->P.error = 0;
+        sg_paired_align(a->P, rb, rq, ln, r);
+        if (a->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
+    }
+    if (nLV) *nLV = a->P.lvCalls + a->S.work.lvCalls;
+    if (nAG) *nAG = a->P.agCalls + a->S.work.agCalls;
     return 0;
 }
 

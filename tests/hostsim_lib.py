@@ -49,6 +49,10 @@ def lib():
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
         L.hs_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.hs_paired_create.restype = C.c_void_p
+        L.hs_paired_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.hs_paired_destroy.argtypes = [C.c_void_p]
+        L.hs_align_paired.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         _lib = L
     return _lib
 
@@ -86,6 +90,30 @@ class HsAligner:
         if rc != 0:
             raise RuntimeError(lib().hs_last_error().decode())
         return res, ctr
+
+
+class HsPairedAligner:
+    def __init__(self, index: HsIndex, params, paired_params, max_read_len: int = 400):
+        import ctypes
+        self.index = index
+        self.handle = lib().hs_paired_create(index.handle, ctypes.byref(params), ctypes.byref(paired_params), max_read_len)
+        if not self.handle:
+            raise RuntimeError(lib().hs_last_error().decode())
+
+    def align(self, batch, result_dtype):
+        n_pairs = batch.n // 2
+        res = np.zeros(n_pairs, dtype=result_dtype)
+        nlv = np.zeros(1, dtype=np.int64)
+        nag = np.zeros(1, dtype=np.int64)
+        rc = lib().hs_align_paired(self.handle, n_pairs, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(res), _p(nlv), _p(nag))
+        if rc != 0:
+            raise RuntimeError(lib().hs_last_error().decode())
+        return res, int(nlv[0]), int(nag[0])
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().hs_paired_destroy(self.handle)
+            self.handle = None
 
 
 def tables(seed_len=20, n_indel=1200, n_perfect=1001):
