@@ -35,6 +35,10 @@ SEED_LEN = 20
 MAX_DIST = 14
 ALG_BYTES_PER_CANDIDATE = READ_LEN - SEED_LEN + 2 * (MAX_DIST + 1)     # (readLen - seedLen + 2*k_used) reference bytes
 ALG_BYTES_PER_READ_IO = 2 * READ_LEN + 88                              # bases + qualities in, result record out
+# `snap paired -hc` (soft clipping off: PairedAligner.cpp:380-392 sets the end bonuses to 5 and minAGScoreImprovement to 15);
+# -d 14 as in the single-end config, everything else at `snap paired` defaults (-n 8, -H 4000, -s 0 1000)
+PAIRED_KW = dict(maxDist=MAX_DIST, numSeedsFromCommandLine=8, fivePrimeEndBonus=5, threePrimeEndBonus=5)
+PAIRED_PKW = dict(useSoftClipping=0, minAGScoreImprovement=15)
 
 
 def parse_args():
@@ -50,6 +54,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seed-phase", action="store_true")
+    ap.add_argument("--workload", default=os.environ.get("SNAPGPU_BENCH_WORKLOAD", "single"), choices=["single", "paired"],
+                    help="single = BASELINE configs[1] (the default, headline); paired = configs[2] shape: `snap paired -hc`, "
+                         "--batch-reads/2 FR pairs per step, insert N(400,40)")
     return ap.parse_args()
 
 
@@ -129,7 +136,10 @@ def build_workload(args, device, rank, world):
     nb = args.warmup + args.steps
     for b in range(nb):
         # every (rank, step) gets its own reads: the global batch of step b is the concatenation over ranks
-        batches.append(synth_device.make_reads(bases, starts, contig_len, args.batch_reads, READ_LEN, seed=1000 + b * 64 + rank))
+        if args.workload == "paired":
+            batches.append(synth_device.make_pairs(bases, starts, contig_len, args.batch_reads // 2, READ_LEN, seed=1000 + b * 64 + rank))
+        else:
+            batches.append(synth_device.make_reads(bases, starts, contig_len, args.batch_reads, READ_LEN, seed=1000 + b * 64 + rank))
     torch.cuda.synchronize()
     t3 = time.time()
     info = idx.info()
@@ -156,18 +166,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     W, K, B = args.warmup, args.steps, args.batch_reads
     bases, starts, contig_len, idx, batches, setup = build_workload(args, device, rank, world)
-    params = engine.default_params(maxDist=MAX_DIST)
-    al = engine.SingleAligner(idx, params, max_batch_reads=B)
+    paired = args.workload == "paired"
+    if paired:
+        B = args.batch_reads = (B // 2) * 2
+        al = engine.PairedAligner(idx, engine.default_params(**PAIRED_KW), engine.default_paired_params(**PAIRED_PKW), max_batch_pairs=B // 2)
+        result_bytes_per_read = engine.PAIRED_RESULT_DTYPE.itemsize // 2
+    else:
+        al = engine.SingleAligner(idx, engine.default_params(maxDist=MAX_DIST), max_batch_reads=B)
+        result_bytes_per_read = engine.RESULT_DTYPE.itemsize
     # a dedicated (non-default) stream: the kernels are launched on it through the C ABI and the CUDA events that time
     # them are recorded on the same stream (a NULL stream argument would mean "the aligner's own stream")
     stream = torch.cuda.Stream(device)
     assert stream.cuda_stream != 0
-    res = torch.empty((B, engine.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=device)
+    res = torch.empty((B, result_bytes_per_read), dtype=torch.uint8, device=device)
     d_ctr = torch.zeros((engine.N_COUNTERS,), dtype=torch.int64, device=device)
 
     def step(b):
         rb, rq, ro, rl = batches[b][0], batches[b][1], batches[b][2], batches[b][3]
-        al.align_device(B, rb.data_ptr(), rq.data_ptr(), ro.data_ptr(), rl.data_ptr(), res.data_ptr(), d_ctr.data_ptr(), stream.cuda_stream)
+        al.align_device(B // 2 if paired else B, rb.data_ptr(), rq.data_ptr(), ro.data_ptr(), rl.data_ptr(), res.data_ptr(), d_ctr.data_ptr(),
+                        stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -194,6 +211,8 @@ def run_ours(args):
     ms_total = ev[0].elapsed_time(ev[K])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
     launches = al.launch_count() - launches0
+    if paired:
+        al.check(stream.cuda_stream)        # raises if a kernel latched an error (pool overflow)
     ctr = d_ctr.cpu().numpy()
     ms_max = shard.max_over_ranks(ms_total, device) if world > 1 else ms_total
     ctr_all = shard.allreduce_counters(ctr, device) if world > 1 else ctr
@@ -214,7 +233,7 @@ def run_ours(args):
     e2e_steps = max(1, min(K, 3))
     for k in range(e2e_steps):
         r, _ = al.align(host_batches[k % len(host_batches)])
-        n_e2e += len(r)
+        n_e2e += len(r) * (2 if paired else 1)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_s = shard.max_over_ranks(e2e_s, device) if world > 1 else e2e_s
@@ -224,10 +243,10 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     per_launch = 1.0 / (K * world)
     alg_bytes = (c["nHashEntriesProbed"] * 8 + c["nOverflowWordsRead"] * 4 + (c["lvCalls"] + c["affineGapCalls"]) * ALG_BYTES_PER_CANDIDATE
-                 + c["totalReads"] * ALG_BYTES_PER_READ_IO) * per_launch
+                 + c["totalReads"] * (2 * READ_LEN + result_bytes_per_read)) * per_launch
     kernel_ms_avg = float(np.mean(kernel_ms))
     achieved = alg_bytes / (kernel_ms_avg / 1e3) / 1e9
-    roofline = {"kernel": "sg_align_kernel", "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "sg_align_paired_kernel" if paired else "sg_align_kernel", "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(kernel_ms_avg, 3),
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
@@ -236,13 +255,16 @@ def run_ours(args):
         "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_max / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
-        "config": {"workload": "snap single, %d x %d bp synthetic reads per step per GPU vs %d Mbp synthetic reference (24 contigs), "
-                               "seed %d, maxDist %d, affine gap on (BASELINE configs[1] shape)" % (B, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST),
+        "config": {"workload": ("snap paired -hc (soft clipping off), 2 x %d x %d bp synthetic FR pairs (insert N(400,40)) per step per GPU vs %d Mbp "
+                                "synthetic reference (24 contigs), seed %d, maxDist %d, IntersectingPairedEndAligner + chimeric single-end fallback "
+                                "(BASELINE configs[2] shape)" % (B // 2, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)) if paired else
+                               ("snap single, %d x %d bp synthetic reads per step per GPU vs %d Mbp synthetic reference (24 contigs), "
+                                "seed %d, maxDist %d, affine gap on (BASELINE configs[1] shape)" % (B, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)),
                    "reads_per_step": B * world, "read_len": READ_LEN, "genome_mbp": args.genome_mbp, "seed_len": SEED_LEN, "max_dist": MAX_DIST,
                    "parallelism": "read-sharded x%d, index replicated per GPU" % world,
                    "l2": "each step uses fresh reads (%.0f MB/step > L2) against a %.1f GB index" % (B * 2 * READ_LEN / 1e6, setup["index_hbm_gb"])},
         "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(B * (2 * READ_LEN + 12)),
-                "d2h_bytes_per_step": int(B * engine.RESULT_DTYPE.itemsize + engine.N_COUNTERS * 8), "steps": e2e_steps},
+                "d2h_bytes_per_step": int(B * result_bytes_per_read + engine.N_COUNTERS * 8), "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -255,7 +277,9 @@ def run_ours(args):
     }
 
     # ---- seed-lookup phase in isolation (rank 0, N=1) ----
-    if rank == 0 and not args.no_seed_phase:
+    if paired:
+        out["per_read"]["aligned_as_pair_frac"] = None
+    if rank == 0 and not args.no_seed_phase and not paired:
         try:
             out["seed_phase"] = seed_phase(args, idx, batches, device, peak, peak_src)
         except Exception as e:  # pragma: no cover
@@ -265,6 +289,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_baseline(args, idx, host_batches[0], check_against=None)
+            if paired:
+                out["per_read"]["aligned_as_pair_frac"] = out["cpu_baseline"].pop("aligned_as_pair_frac", None)
         except Exception as e:  # pragma: no cover
             out["cpu_baseline"] = {"error": str(e)[:300]}
 
@@ -351,6 +377,17 @@ def cpu_baseline(args, idx, host_batch, check_against):
         cores = os.cpu_count() or 1
         n = min(args.cpu_sample_reads, host_batch.n)
         sample = host_batch.slice(0, n)
+        if args.workload == "paired":
+            n -= n % 2
+            sample = host_batch.slice(0, n)
+            p, pp = reflib.default_params(**PAIRED_KW), reflib.default_paired_params(**PAIRED_PKW)
+            reflib.paired_align_mt(ridx, p, pp, sample.slice(0, min(n, 20000)), cores)
+            res, ctr, secs = reflib.paired_align_mt(ridx, p, pp, sample, cores)
+            return {"value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
+                    "sample": "%d of the step's %d pairs, %d threads, oracle/_ref ChimericPairedEndAligner(IntersectingPairedEndAligner)::align "
+                              "(aligner only, no SAM output); index = ours exported to SNAP's directory format (load %.1fs)"
+                              % (n // 2, host_batch.n // 2, cores, load_s),
+                    "seconds": round(secs, 3), "aligned_as_pair_frac": round(float(res["alignedAsPair"].mean()), 5)}
         p = reflib.default_params(maxDist=MAX_DIST)
         reflib.align_mt(ridx, p, sample.slice(0, min(n, 20000)), cores)          # warm the page cache / TLB
         res, ctr, secs = reflib.align_mt(ridx, p, sample, cores)
@@ -392,12 +429,18 @@ def run_reference(args):
         for b in range(W + K):
             rb, rq, ro, rl = batches[b][:4]
             hb.append(synth.ReadBatch(rb.cpu().numpy(), rq.cpu().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32)))
+        paired = args.workload == "paired"
+        if paired:
+            p, pp = reflib.default_params(**PAIRED_KW), reflib.default_paired_params(**PAIRED_PKW)
+            run = lambda batch: reflib.paired_align_mt(ridx, p, pp, batch, cores)
+        else:
+            run = lambda batch: reflib.align_mt(ridx, p, batch, cores)
         for b in range(W):
-            reflib.align_mt(ridx, p, hb[b], cores)
+            run(hb[b])
         total_s = 0.0
         aligned = 0
         for k in range(K):
-            res, ctr, secs = reflib.align_mt(ridx, p, hb[W + k], cores)
+            res, ctr, secs = run(hb[W + k])
             total_s += secs
             aligned += int((res["status"] != 0).sum())
         value = n * K / total_s
@@ -405,13 +448,15 @@ def run_reference(args):
         out = {"impl": "reference", "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": args.gpus, "steps": K,
                "warmup": W, "ms_per_step": round(total_s / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
-               "config": {"workload": "snap single, %d x %d bp synthetic reads per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
-                                      % (n, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST), "read_len": READ_LEN, "genome_mbp": args.genome_mbp,
+               "config": {"workload": ("snap paired -hc, 2 x %d x %d bp synthetic FR pairs per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
+                                       % (n // 2, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)) if paired else
+                                      ("snap single, %d x %d bp synthetic reads per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
+                                       % (n, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)), "read_len": READ_LEN, "genome_mbp": args.genome_mbp,
                           "seed_len": SEED_LEN, "max_dist": MAX_DIST},
                "cpu_baseline": {"value": round(value, 1), "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample},
                "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "aligned_frac": round(aligned / (n * K), 5),
-               "note": "unmodified amplab/snap BaseAligner::AlignRead via oracle/_ref on host cores; index = GPU-built, exported to SNAP's format"}
+               "note": "unmodified amplab/snap aligner (BaseAligner::AlignRead / ChimericPairedEndAligner::align) via oracle/_ref on host cores; index = GPU-built, exported to SNAP's format"}
         print(json.dumps(out))
     finally:
         shutil.rmtree(d, ignore_errors=True)

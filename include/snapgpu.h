@@ -253,6 +253,40 @@ int  snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_ba
                                  snapgpu_single_result *d_results, snapgpu_counters *d_counters,
                                  void *cudaStream);
 
+/*
+ * Paired-end aligner handle: the ChimericPairedEndAligner(IntersectingPairedEndAligner) stack that
+ * PairedAlignerContext::runIterationThread builds per thread (reference SNAPLib/PairedAligner.cpp:547-638).
+ * Scope: no secondary results (-om unset), no ALT contigs, and useSoftClipping must be 0 (`snap paired -hc`): the
+ * Hamming / gapless-clipping pass that soft clipping adds is not implemented, and creation fails if it is asked for.
+ */
+void snapgpu_paired_params_default(snapgpu_paired_params *pp);   /* `snap paired` 2.0.5 defaults */
+int  snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params *params, const snapgpu_paired_params *pparams,
+                                   int64_t maxBatchPairs, snapgpu_aligner **out);
+
+/*
+ * Replaces the loop body `aligner->align(reads[0], reads[1], results, ...)` + the useful-read pre-filter
+ * (reference SNAPLib/PairedAligner.cpp:640-800, ChimericPairedEndAligner.cpp:126-448,
+ * IntersectingPairedEndAligner.cpp:169-252) for a batch of nPairs pairs.  Reads are laid out as in
+ * snapgpu_align_single with pair i = reads 2i (first in pair) and 2i+1; offsets/lens hold 2*nPairs entries.
+ * counters may be NULL; lvCalls / affineGapCalls count both the intersecting and the single-end fallback aligner.
+ * Fields the reference itself leaves undefined (mapq / scorePriorToClipping of an end reported NotFound by the
+ * single-end fallback: uninitialised stack there) are returned as 0.
+ */
+int  snapgpu_align_paired(snapgpu_aligner *a, int64_t nPairs, const char *bases, const char *quals,
+                          const uint64_t *offsets, const uint32_t *lens,
+                          snapgpu_paired_result *results, snapgpu_counters *counters);
+
+/* Device-pointer form (see snapgpu_align_single_device).  Errors raised inside the kernel (a candidate pool that the
+ * reference would soft_exit() on, an over-long read) are latched in the aligner: snapgpu_aligner_check() reports them. */
+int  snapgpu_align_paired_device(snapgpu_aligner *a, int64_t nPairs, const char *d_bases, const char *d_quals,
+                                 const uint64_t *d_offsets, const uint32_t *d_lens,
+                                 snapgpu_paired_result *d_results, snapgpu_counters *d_counters,
+                                 void *cudaStream);
+
+/* Synchronises `cudaStream` (NULL = the aligner's own) and returns non-zero (message in snapgpu_last_error) if a
+ * kernel of this aligner latched an error since the last check. */
+int  snapgpu_aligner_check(snapgpu_aligner *a, void *cudaStream);
+
 /* Number of kernel launches issued through this aligner since creation (bench.py's gpu_launches). */
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a);
 

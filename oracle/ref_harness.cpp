@@ -505,4 +505,51 @@ int ref_paired_align(void *v, _int64 nPairs, const char *bases, const char *qual
     return 0;
 }
 
+
+/* Multi-threaded paired variant for the CPU baseline: one ChimericPairedEndAligner stack per thread over a contiguous
+ * range of pairs (ParallelTask.h:40-120 / PairedAligner.cpp:520-800).  Returns wall seconds spent aligning. */
+struct MTPairedArg {
+    void *rp; _int64 begin, end;
+    const char *bases; const char *quals; const _uint64 *offsets; const unsigned *lens;
+    snapgpu_paired_result *results; _int64 nLV, nAG; int rc;
+};
+
+static void *mt_paired_main(void *v)
+{
+    MTPairedArg *a = (MTPairedArg *)v;
+    a->rc = ref_paired_align(a->rp, a->end - a->begin, a->bases, a->quals, a->offsets + 2 * a->begin, a->lens + 2 * a->begin,
+                             a->results + a->begin, &a->nLV, &a->nAG);
+    return NULL;
+}
+
+double ref_paired_align_mt(void *vidx, const snapgpu_params *p, const snapgpu_paired_params *pp, int nThreads, _int64 nPairs, const char *bases,
+                           const char *quals, const _uint64 *offsets, const unsigned *lens, snapgpu_paired_result *results, _int64 *nLV, _int64 *nAG)
+{
+    if (nThreads < 1) nThreads = 1;
+    MTPairedArg *args = new MTPairedArg[nThreads];
+    pthread_t *threads = new pthread_t[nThreads];
+    for (int t = 0; t < nThreads; t++) {
+        args[t].rp = ref_paired_create(vidx, p, pp);
+        args[t].begin = nPairs * t / nThreads;
+        args[t].end = nPairs * (t + 1) / nThreads;
+        args[t].bases = bases; args[t].quals = quals; args[t].offsets = offsets; args[t].lens = lens;
+        args[t].results = results; args[t].nLV = args[t].nAG = 0; args[t].rc = 0;
+    }
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < nThreads; t++) pthread_create(&threads[t], NULL, mt_paired_main, &args[t]);
+    for (int t = 0; t < nThreads; t++) pthread_join(threads[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    double secs = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    for (int t = 0; t < nThreads; t++) {
+        if (nLV) *nLV += args[t].nLV;
+        if (nAG) *nAG += args[t].nAG;
+        if (args[t].rc) secs = -1.0;
+        ref_paired_destroy(args[t].rp);
+    }
+    delete[] args;
+    delete[] threads;
+    return secs;
+}
+
 } // extern "C"

@@ -241,6 +241,21 @@ class RefPairedAligner:
             self.handle = None
 
 
+def paired_align_mt(index: RefIndex, params: Params, pparams: PairedParams, batch, n_threads: int):
+    """All-cores paired run (one aligner stack per thread): (results, {lvCalls, affineGapCalls}, seconds)."""
+    L = lib()
+    L.ref_paired_align_mt.restype = C.c_double
+    L.ref_paired_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams), C.c_int, C.c_int64] + [C.c_void_p] * 7
+    n = batch.n // 2
+    res = np.zeros(n, dtype=PAIRED_RESULT_DTYPE)
+    lvag = np.zeros(2, dtype=np.int64)
+    secs = L.ref_paired_align_mt(index.handle, C.byref(params), C.byref(pparams), n_threads, n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
+                                 _p(batch.lens), _p(res), C.c_void_p(lvag.ctypes.data), C.c_void_p(lvag.ctypes.data + 8))
+    if secs < 0:
+        raise RuntimeError("ref_paired_align_mt failed")
+    return res, {"lvCalls": int(lvag[0]), "affineGapCalls": int(lvag[1])}, float(secs)
+
+
 def lv_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray) -> np.ndarray:
     out = np.zeros(jobs.size, dtype=LV_OUT_DTYPE)
     lib().ref_lv_batch(_p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))

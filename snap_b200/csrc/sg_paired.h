@@ -547,26 +547,51 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
         popularSeedsSkipped[w] = 0;
         P.countOfHashTableLookups[w] = 0;
         for (int d = 0; d < 2; d++) { P.totalHashTableHits[w][d] = 0; ps.hitSets[w][d].init(); }
-        for (uint32_t i = 0; i < lens[w]; i++) {
-            ps.rcRead[w][i] = sg_complement(readBases[w][lens[w] - i - 1]);
-            ps.rcQual[w][i] = readQuals[w][lens[w] - i - 1];
-            countOfNs += (readBases[w][i] == 'N') ? 1u : 0u;
-        }
         P.readData[w][0] = readBases[w]; P.readQual[w][0] = readQuals[w];
         P.readData[w][1] = ps.rcRead[w]; P.readQual[w][1] = ps.rcQual[w];
+#if defined(__CUDA_ARCH__)
+        // the derived strings (:347-372) are built 32 bases per step; every lane reads all of them afterwards
+        #pragma unroll 1
+        for (uint32_t i = (uint32_t)P.lane; i < lens[w]; i += 32) {
+            const uint8_t b = readBases[w][i], c = sg_complement(b);
+            ps.rcRead[w][lens[w] - i - 1] = c;
+            ps.rcQual[w][lens[w] - i - 1] = readQuals[w][i];
+            ps.revRead[w][0][lens[w] - i - 1] = b;
+            ps.revRead[w][1][i] = c;
+            countOfNs += (b == 'N') ? 1u : 0u;
+        }
+#else
+        for (uint32_t i = 0; i < lens[w]; i++) {
+            const uint8_t b = readBases[w][i], c = sg_complement(b);
+            ps.rcRead[w][lens[w] - i - 1] = c;
+            ps.rcQual[w][lens[w] - i - 1] = readQuals[w][i];
+            ps.revRead[w][0][lens[w] - i - 1] = b;
+            ps.revRead[w][1][i] = c;
+            countOfNs += (b == 'N') ? 1u : 0u;
+        }
+#endif
     }
+#if defined(__CUDA_ARCH__)
+    countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
+    __syncwarp();
+#endif
     if ((int)countOfNs > maxK) return true;
-    for (uint32_t w = 0; w < 2; w++) for (int d = 0; d < 2; d++) {
-        const uint8_t *src = P.readData[w][d];
-        for (uint32_t i = 0; i < lens[w]; i++) ps.revRead[w][d][i] = src[lens[w] - i - 1];
-    }
 
     // ---- Phase 1: hash table lookups (:409-502) ----
     for (uint32_t w = 0; w < 2; w++) {
         int nextSeedToTest = 0;
         uint32_t wrapCount = 0;
         const int nPossibleSeeds = (int)lens[w] - (int)seedLen + 1;
-        { uint32_t ml = lens[0] > lens[1] ? lens[0] : lens[1]; for (uint32_t i = 0; i < (ml + 7) / 8; i++) ps.seedUsed[i] = 0; }
+        {
+            const uint32_t ml = lens[0] > lens[1] ? lens[0] : lens[1];
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+            for (uint32_t i = (uint32_t)P.lane; i < (ml + 7) / 8; i += 32) ps.seedUsed[i] = 0;
+            __syncwarp();
+#else
+            for (uint32_t i = 0; i < (ml + 7) / 8; i++) ps.seedUsed[i] = 0;
+#endif
+        }
         bool beginsDisjointHitSet[2] = {true, true};
         while (P.countOfHashTableLookups[w] < nPossibleSeeds && P.countOfHashTableLookups[w] < maxSeeds) {
             if (nextSeedToTest >= nPossibleSeeds) {

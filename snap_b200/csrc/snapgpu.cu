@@ -11,8 +11,10 @@
 #include <vector>
 #include <new>
 
-#include "sg_host.h"
+#define SG_WITH_PAIRED 1
 #include "sg_align.h"
+#include "sg_paired.h"
+#include "sg_host.h"
 #include "sg_build.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -56,6 +58,13 @@ struct snapgpu_aligner {
     const snapgpu_index *index = nullptr;
     SgParams params;
     snapgpu_params userParams;
+    // paired-end handle (snapgpu_paired_aligner_create): `params` drives the intersecting aligner, `paramsSingle` the
+    // single-end fallback aligner; a worker's arena = [single scratch | paired scratch]
+    bool paired = false;
+    SgParams paramsSingle;
+    SgPairedParams pparams;
+    size_t singleScratchBytes = 0;
+    int *d_error = nullptr;              // latched kernel-side error code (0 = none)
     int device = 0;
     int numSMs = 0;
     int warpsPerBlock = 8, blocksPerSM = 4;
@@ -71,9 +80,9 @@ struct snapgpu_aligner {
     // two pipeline slots: while the GPU aligns chunk c the host packs chunk c+1 into the other slot's pinned staging
     struct Slot {
         char *h_bases = nullptr, *h_quals = nullptr; uint64_t *h_offsets = nullptr; uint32_t *h_lens = nullptr;
-        snapgpu_single_result *h_results = nullptr;
+        uint8_t *h_results = nullptr;        // snapgpu_single_result[] or snapgpu_paired_result[]
         char *d_bases = nullptr, *d_quals = nullptr; uint64_t *d_offsets = nullptr; uint32_t *d_lens = nullptr;
-        snapgpu_single_result *d_results = nullptr;
+        uint8_t *d_results = nullptr;
         cudaEvent_t evIn = nullptr, evKernel = nullptr, evOut = nullptr;
         int64_t pendingFirst = -1, pendingCount = 0;    // results waiting in h_results for reads [pendingFirst, +pendingCount)
     } slot[2];
@@ -183,6 +192,94 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
         atomicAdd((unsigned long long *)&counters->lvCalls, (unsigned long long)A.work.lvCalls);
         atomicAdd((unsigned long long *)&counters->affineGapCalls, (unsigned long long)A.work.agCalls);
         atomicAdd((unsigned long long *)&counters->nHitsIgnoredBecauseOfTooHighPopularity, (unsigned long long)A.work.popularIgnored);
+    }
+}
+
+
+// The paired-end kernel: same execution model, one warp per PAIR.  Worker arena = single-end scratch followed by the
+// paired scratch (hit sets, candidate pools, merge anchors, phase-4 candidate buffer, the second pair of affine-gap
+// traceback arrays).
+template <int MB>
+__global__ void __launch_bounds__(256, MB)
+sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedParams pp, const SgTables *tb, uint8_t *scratchBase,
+                       size_t scratchBytesPerWorker, size_t singleScratchBytes, long long nPairs, const uint8_t *bases, const uint8_t *quals,
+                       const unsigned long long *offsets, const uint32_t *lens, snapgpu_paired_result *results, snapgpu_counters *counters,
+                       unsigned long long *next, int *errorWord)
+{
+    const int lane = threadIdx.x & 31;
+    const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t *arena = scratchBase + (size_t)worker * scratchBytesPerWorker;
+
+    SgAligner S;
+    S.ix = &ix; S.pr = &prSingle; S.tb = tb;
+    S.lane = lane; S.maxK = prSingle.maxK;
+    sg_scratch_carve(prSingle, arena, &S.sc);
+    S.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
+    S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    S.nUsedElements = 0;
+    S.work.lookups = S.work.entriesProbed = S.work.overflowWords = S.work.lvCalls = S.work.agCalls = S.work.popularIgnored = 0;
+
+    SgPairedAligner P;
+    P.single = &S; P.ix = &ix; P.pr = &pr; P.pp = &pp; P.tb = tb;
+    sg_paired_scratch_carve(pr, pp, arena + singleScratchBytes, &P.ps);
+    P.ag = S.ag; P.lane = lane; P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    P.lvCalls = P.agCalls = 0; P.error = 0; P.maxK = (int)pr.maxK;
+    unsigned long long cTotal = 0, cUseless = 0, cSingle = 0, cMulti = 0, cNotFound = 0;
+
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(next, 1ULL);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= (unsigned long long)nPairs) break;
+        const uint8_t *rb[2], *rq[2]; uint32_t ln[2]; bool useful[2]; bool tooLong = false;
+        for (int w = 0; w < 2; w++) {
+            rb[w] = bases + offsets[2 * i + w]; rq[w] = quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w];
+            uint32_t countOfNs = 0;
+            for (uint32_t k = lane; k < ln[w]; k += 32) countOfNs += (rb[w][k] == 'N');
+            countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
+            useful[w] = ln[w] >= pr.minReadLength && countOfNs <= pr.maxK;       // PairedAligner.cpp:669-676
+            tooLong = tooLong || ln[w] > pr.maxReadLen;
+        }
+        snapgpu_paired_result r;
+        memset(&r, 0, sizeof(r));
+        cTotal += 2;
+        if (tooLong) { if (lane == 0) atomicMax(errorWord, 3); useful[0] = useful[1] = false; }
+        if (!useful[0] && !useful[1]) {
+            r.status[0] = r.status[1] = SNAPGPU_NOT_FOUND; r.location[0] = r.location[1] = P.invalidLocation;
+            cUseless += 2;
+            if (lane == 0) results[i] = r;
+            continue;
+        }
+        P.error = 0;
+        sg_paired_align(P, rb, rq, ln, &r);
+        if (P.error) {
+            if (lane == 0) atomicMax(errorWord, P.error);
+            memset(&r, 0, sizeof(r));
+            r.status[0] = r.status[1] = SNAPGPU_NOT_FOUND; r.location[0] = r.location[1] = P.invalidLocation;
+        }
+        if (lane == 0) results[i] = r;
+        for (int w = 0; w < 2; w++) {
+            if (r.status[w] == SNAPGPU_SINGLE_HIT) cSingle++;
+            else if (r.status[w] == SNAPGPU_MULTIPLE_HITS) cMulti++;
+            else cNotFound++;
+            if (lane == 0 && counters && r.status[w] != SNAPGPU_NOT_FOUND && r.mapq[w] >= 0 && r.mapq[w] <= 70) {
+                atomicAdd((unsigned long long *)&counters->mapqHistogram[r.mapq[w]], 1ULL);
+            }
+        }
+    }
+    S.clearCandidates();
+    if (counters && lane == 0) {
+        atomicAdd((unsigned long long *)&counters->totalReads, cTotal);
+        atomicAdd((unsigned long long *)&counters->uselessReads, cUseless);
+        atomicAdd((unsigned long long *)&counters->singleHits, cSingle);
+        atomicAdd((unsigned long long *)&counters->multiHits, cMulti);
+        atomicAdd((unsigned long long *)&counters->notFound, cNotFound);
+        atomicAdd((unsigned long long *)&counters->nHashTableLookups, (unsigned long long)S.work.lookups);
+        atomicAdd((unsigned long long *)&counters->nHashEntriesProbed, (unsigned long long)S.work.entriesProbed);
+        atomicAdd((unsigned long long *)&counters->nOverflowWordsRead, (unsigned long long)S.work.overflowWords);
+        atomicAdd((unsigned long long *)&counters->lvCalls, (unsigned long long)S.work.lvCalls + P.lvCalls);
+        atomicAdd((unsigned long long *)&counters->affineGapCalls, (unsigned long long)S.work.agCalls + P.agCalls);
+        atomicAdd((unsigned long long *)&counters->nHitsIgnoredBecauseOfTooHighPopularity, (unsigned long long)S.work.popularIgnored);
     }
 }
 
@@ -619,6 +716,66 @@ int snapgpu_lookup_seeds_device(const snapgpu_index *idx, const char *d_seeds, i
     return 0;
 }
 
+// Shared part of the two create functions: worker arenas, streams, the two pipeline slots.
+// maxBatchReads counts READS (2 per pair); resultBytesPerRead: bytes of result per read in the staging buffers.
+static int aligner_init_common(snapgpu_aligner *a, int64_t maxBatchReads, int64_t maxUnits, size_t scratchBytesPerWorker, size_t resultBytesPerUnit,
+                               int readsPerUnit, int defaultBlocksPerSM, const char *blocksEnv)
+{
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, a->device));
+    a->numSMs = prop.multiProcessorCount;
+    a->blocksPerSM = defaultBlocksPerSM;      // resident CTAs (of 8 warps) per SM the kernel is compiled for: 2, 3 or 4
+    if (const char *e = getenv(blocksEnv)) a->blocksPerSM = atoi(e) > 0 ? atoi(e) : defaultBlocksPerSM;
+    if (a->blocksPerSM < 2) a->blocksPerSM = 2;
+    if (a->blocksPerSM > 4) a->blocksPerSM = 4;
+    a->nWorkers = a->numSMs * a->blocksPerSM * a->warpsPerBlock;
+    if ((int64_t)a->nWorkers > maxUnits) {
+        int blocks = (int)((maxUnits + a->warpsPerBlock - 1) / a->warpsPerBlock);
+        a->nWorkers = blocks * a->warpsPerBlock;
+    }
+    a->scratchBytesPerWorker = scratchBytesPerWorker;
+    SG_CUDA(cudaMalloc((void **)&a->d_scratch, a->scratchBytesPerWorker * (size_t)a->nWorkers));
+    SG_CUDA(cudaMemset(a->d_scratch, 0, a->scratchBytesPerWorker * (size_t)a->nWorkers));
+    SG_CUDA(cudaMalloc((void **)&a->d_next, 8));
+    SG_CUDA(cudaMalloc((void **)&a->d_error, sizeof(int)));
+    SG_CUDA(cudaMemset(a->d_error, 0, sizeof(int)));
+    SG_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&a->streamIn, cudaStreamNonBlocking));
+    SG_CUDA(cudaStreamCreateWithFlags(&a->streamOut, cudaStreamNonBlocking));
+    a->chunkReads = 131072;
+    if (const char *e = getenv("SNAPGPU_CHUNK_READS")) a->chunkReads = atoll(e) > 0 ? atoll(e) : a->chunkReads;
+    if (a->chunkReads > maxBatchReads) a->chunkReads = maxBatchReads;
+    a->chunkReads = (a->chunkReads + readsPerUnit - 1) / readsPerUnit * readsPerUnit;
+    a->chunkBases = (size_t)a->chunkReads * (size_t)a->params.maxReadLen;
+    const size_t resultBytes = (size_t)(a->chunkReads / readsPerUnit) * resultBytesPerUnit;
+    for (int k = 0; k < 2; k++) {
+        snapgpu_aligner::Slot &sl = a->slot[k];
+        SG_CUDA(cudaMallocHost((void **)&sl.h_bases, a->chunkBases));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_quals, a->chunkBases));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_offsets, (size_t)a->chunkReads * 8));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_lens, (size_t)a->chunkReads * 4));
+        SG_CUDA(cudaMallocHost((void **)&sl.h_results, resultBytes));
+        SG_CUDA(cudaMalloc((void **)&sl.d_bases, a->chunkBases));
+        SG_CUDA(cudaMalloc((void **)&sl.d_quals, a->chunkBases));
+        SG_CUDA(cudaMalloc((void **)&sl.d_offsets, (size_t)a->chunkReads * 8));
+        SG_CUDA(cudaMalloc((void **)&sl.d_lens, (size_t)a->chunkReads * 4));
+        SG_CUDA(cudaMalloc((void **)&sl.d_results, resultBytes));
+        SG_CUDA(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&sl.evKernel, cudaEventDisableTiming));
+        SG_CUDA(cudaEventCreateWithFlags(&sl.evOut, cudaEventDisableTiming));
+    }
+    SG_CUDA(cudaMallocHost((void **)&a->h_counters, sizeof(snapgpu_counters)));
+    SG_CUDA(cudaMalloc((void **)&a->d_counters, sizeof(snapgpu_counters)));
+    return 0;
+}
+
+static uint32_t env_max_read_len()
+{
+    uint32_t maxReadLen = 400;
+    if (const char *e = getenv("SNAPGPU_MAX_READ_LEN")) maxReadLen = (uint32_t)atoi(e);
+    return maxReadLen;
+}
+
 int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *params, int64_t maxBatchReads, snapgpu_aligner **out)
 {
     if (!idx || !params || !out) return sg_fail("null argument");
@@ -629,50 +786,44 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     if (!a) return sg_fail("out of memory");
     a->index = idx; a->device = idx->device; a->userParams = *params; a->maxBatchReads = maxBatchReads;
     std::string err;
-    uint32_t maxReadLen = 400;
-    if (const char *e = getenv("SNAPGPU_MAX_READ_LEN")) maxReadLen = (uint32_t)atoi(e);
-    if (!sg_derive_params(*params, idx->view.seedLen, maxReadLen, a->params, err)) { delete a; return sg_fail("snapgpu_aligner_create: " + err); }
-    cudaDeviceProp prop;
-    SG_CUDA(cudaGetDeviceProperties(&prop, a->device));
-    a->numSMs = prop.multiProcessorCount;
-    a->blocksPerSM = 4;              // resident CTAs (of 8 warps) per SM the kernel is compiled for: 2, 3 or 4
-    if (const char *e = getenv("SNAPGPU_BLOCKS_PER_SM")) a->blocksPerSM = atoi(e) > 0 ? atoi(e) : 4;
-    if (a->blocksPerSM < 2) a->blocksPerSM = 2;
-    if (a->blocksPerSM > 4) a->blocksPerSM = 4;
-    a->nWorkers = a->numSMs * a->blocksPerSM * a->warpsPerBlock;
-    if ((int64_t)a->nWorkers > maxBatchReads) {
-        int blocks = (int)((maxBatchReads + a->warpsPerBlock - 1) / a->warpsPerBlock);
-        a->nWorkers = blocks * a->warpsPerBlock;
+    if (!sg_derive_params(*params, idx->view.seedLen, env_max_read_len(), a->params, err)) { delete a; return sg_fail("snapgpu_aligner_create: " + err); }
+    if (aligner_init_common(a, maxBatchReads, maxBatchReads, sg_align_up(sg_scratch_bytes(a->params), 256), sizeof(snapgpu_single_result), 1, 4,
+                            "SNAPGPU_BLOCKS_PER_SM")) { snapgpu_aligner_destroy(a); return 1; }
+    *out = a;
+    return 0;
+}
+
+void snapgpu_paired_params_default(snapgpu_paired_params *pp)
+{
+    // PairedAligner.cpp:228-243 (PairedAlignerOptions ctor), AlignerOptions.cpp:101-111
+    memset(pp, 0, sizeof(*pp));
+    pp->struct_size = sizeof(*pp);
+    pp->minSpacing = 0; pp->maxSpacing = 1000; pp->intersectingAlignerMaxHits = 4000; pp->maxCandidatePoolSize = 1000000;
+    pp->maxSeedsSingleEnd = 25; pp->maxDistForIndels = 40; pp->forceSpacing = 0;
+    pp->minScoreRealignment = 3; pp->minScoreGapRealignmentALT = 3; pp->minAGScoreImprovement = 24;
+    pp->enableHammingScoringBaseAligner = 1; pp->useSoftClipping = 1; pp->flattenMAPQAtOrBelow = 3;
+}
+
+int snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params *params, const snapgpu_paired_params *pparams,
+                                  int64_t maxBatchPairs, snapgpu_aligner **out)
+{
+    if (!idx || !params || !pparams || !out) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(idx->device)) return 1;
+    if (maxBatchPairs <= 0) return sg_fail("maxBatchPairs must be positive");
+    if (idx->view.altFirstLocation < idx->view.nBases) return sg_fail("snapgpu_paired_aligner_create: indices with ALT contigs are not supported by the paired path");
+    snapgpu_aligner *a = new (std::nothrow) snapgpu_aligner;
+    if (!a) return sg_fail("out of memory");
+    a->index = idx; a->device = idx->device; a->userParams = *params; a->maxBatchReads = 2 * maxBatchPairs; a->paired = true;
+    std::string err;
+    if (!sg_derive_paired_params(*params, *pparams, idx->view.seedLen, env_max_read_len(), a->params, a->paramsSingle, a->pparams, err)) {
+        delete a; return sg_fail("snapgpu_paired_aligner_create: " + err);
     }
-    a->scratchBytesPerWorker = sg_align_up(sg_scratch_bytes(a->params), 256);
-    SG_CUDA(cudaMalloc((void **)&a->d_scratch, a->scratchBytesPerWorker * (size_t)a->nWorkers));
-    SG_CUDA(cudaMemset(a->d_scratch, 0, a->scratchBytesPerWorker * (size_t)a->nWorkers));
-    SG_CUDA(cudaMalloc((void **)&a->d_next, 8));
-    SG_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
-    SG_CUDA(cudaStreamCreateWithFlags(&a->streamIn, cudaStreamNonBlocking));
-    SG_CUDA(cudaStreamCreateWithFlags(&a->streamOut, cudaStreamNonBlocking));
-    a->chunkReads = 131072;
-    if (const char *e = getenv("SNAPGPU_CHUNK_READS")) a->chunkReads = atoll(e) > 0 ? atoll(e) : a->chunkReads;
-    if (a->chunkReads > maxBatchReads) a->chunkReads = maxBatchReads;
-    a->chunkBases = (size_t)a->chunkReads * (size_t)maxReadLen;
-    for (int k = 0; k < 2; k++) {
-        snapgpu_aligner::Slot &sl = a->slot[k];
-        SG_CUDA(cudaMallocHost((void **)&sl.h_bases, a->chunkBases));
-        SG_CUDA(cudaMallocHost((void **)&sl.h_quals, a->chunkBases));
-        SG_CUDA(cudaMallocHost((void **)&sl.h_offsets, (size_t)a->chunkReads * 8));
-        SG_CUDA(cudaMallocHost((void **)&sl.h_lens, (size_t)a->chunkReads * 4));
-        SG_CUDA(cudaMallocHost((void **)&sl.h_results, (size_t)a->chunkReads * sizeof(snapgpu_single_result)));
-        SG_CUDA(cudaMalloc((void **)&sl.d_bases, a->chunkBases));
-        SG_CUDA(cudaMalloc((void **)&sl.d_quals, a->chunkBases));
-        SG_CUDA(cudaMalloc((void **)&sl.d_offsets, (size_t)a->chunkReads * 8));
-        SG_CUDA(cudaMalloc((void **)&sl.d_lens, (size_t)a->chunkReads * 4));
-        SG_CUDA(cudaMalloc((void **)&sl.d_results, (size_t)a->chunkReads * sizeof(snapgpu_single_result)));
-        SG_CUDA(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
-        SG_CUDA(cudaEventCreateWithFlags(&sl.evKernel, cudaEventDisableTiming));
-        SG_CUDA(cudaEventCreateWithFlags(&sl.evOut, cudaEventDisableTiming));
+    a->singleScratchBytes = sg_align_up(sg_scratch_bytes(a->paramsSingle), 256);
+    const size_t perWorker = a->singleScratchBytes + sg_align_up(sg_paired_scratch_bytes(a->params, a->pparams), 256);
+    if (aligner_init_common(a, 2 * maxBatchPairs, maxBatchPairs, perWorker, sizeof(snapgpu_paired_result), 2, 3, "SNAPGPU_PAIRED_BLOCKS_PER_SM")) {
+        snapgpu_aligner_destroy(a); return 1;
     }
-    SG_CUDA(cudaMallocHost((void **)&a->h_counters, sizeof(snapgpu_counters)));
-    SG_CUDA(cudaMalloc((void **)&a->d_counters, sizeof(snapgpu_counters)));
     *out = a;
     return 0;
 }
@@ -685,7 +836,7 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
     if (a->stream) cudaStreamDestroy(a->stream);
     if (a->streamIn) cudaStreamDestroy(a->streamIn);
     if (a->streamOut) cudaStreamDestroy(a->streamOut);
-    cudaFree(a->d_scratch); cudaFree(a->d_next);
+    cudaFree(a->d_scratch); cudaFree(a->d_next); cudaFree(a->d_error);
     for (int k = 0; k < 2; k++) {
         snapgpu_aligner::Slot &sl = a->slot[k];
         cudaFreeHost(sl.h_bases); cudaFreeHost(sl.h_quals); cudaFreeHost(sl.h_offsets); cudaFreeHost(sl.h_lens); cudaFreeHost(sl.h_results);
@@ -698,28 +849,55 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
     delete a;
 }
 
+// n = units (reads for a single-end handle, pairs for a paired one)
 static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
-                        const uint32_t *d_lens, snapgpu_single_result *d_results, snapgpu_counters *d_counters, cudaStream_t st)
+                        const uint32_t *d_lens, void *d_results, snapgpu_counters *d_counters, cudaStream_t st)
 {
     SG_CUDA(cudaMemsetAsync(a->d_next, 0, 8, st));
     int64_t workers = a->nWorkers;
     if (workers > n) workers = n;
     int blocks = (int)((workers + a->warpsPerBlock - 1) / a->warpsPerBlock);
     if (blocks < 1) blocks = 1;
+    if (!a->paired) {
 #define SG_LAUNCH(MB) sg_align_kernel<MB><<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, \
         a->d_scratch, a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, \
-        d_lens, d_results, d_counters, a->d_next)
-    if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
+        d_lens, (snapgpu_single_result *)d_results, d_counters, a->d_next)
+        if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
 #undef SG_LAUNCH
+    } else {
+#define SG_LAUNCH(MB) sg_align_paired_kernel<MB><<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->paramsSingle, a->pparams, \
+        a->index->d_tables_prob, a->d_scratch, a->scratchBytesPerWorker, a->singleScratchBytes, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, \
+        (const unsigned long long *)d_offsets, d_lens, (snapgpu_paired_result *)d_results, d_counters, a->d_next, a->d_error)
+        if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
+#undef SG_LAUNCH
+    }
     SG_CUDA(cudaGetLastError());
     a->launches++;
     return 0;
+}
+
+int snapgpu_aligner_check(snapgpu_aligner *a, void *cudaStream)
+{
+    if (!a) return sg_fail("null argument");
+    SG_CUDA(cudaSetDevice(a->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : a->stream;
+    int code = 0;
+    SG_CUDA(cudaMemcpyAsync(&code, a->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (code == 0) return 0;
+    SG_CUDA(cudaMemsetAsync(a->d_error, 0, sizeof(int), st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (code == 1) return sg_fail("paired aligner: a scoring candidate / mate / merge-anchor pool overflowed (the reference exits here too; raise -mcp / -H)");
+    if (code == 2) return sg_fail("paired aligner: more than 4096 phase-4 affine-gap candidates for one pair (buffer growth is not implemented)");
+    if (code == 3) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+    return sg_fail("aligner kernel reported an unknown error");
 }
 
 int snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
                                 const uint32_t *d_lens, snapgpu_single_result *d_results, snapgpu_counters *d_counters, void *cudaStream)
 {
     if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results) return sg_fail("null argument");
+    if (a->paired) return sg_fail("snapgpu_align_single_device called on a paired-end aligner handle");
     if (n < 0) return sg_fail("negative read count");
     if (n == 0) return 0;
     SG_CUDA(cudaSetDevice(a->device));
@@ -727,43 +905,64 @@ int snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bas
     return launch_align(a, n, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters, st);
 }
 
+int snapgpu_align_paired_device(snapgpu_aligner *a, int64_t nPairs, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                                const uint32_t *d_lens, snapgpu_paired_result *d_results, snapgpu_counters *d_counters, void *cudaStream)
+{
+    if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results) return sg_fail("null argument");
+    if (!a->paired) return sg_fail("snapgpu_align_paired_device called on a single-end aligner handle");
+    if (nPairs < 0) return sg_fail("negative pair count");
+    if (nPairs == 0) return 0;
+    SG_CUDA(cudaSetDevice(a->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : a->stream;
+    return launch_align(a, nPairs, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters, st);
+}
+
 // Drains a pipeline slot: waits for its D2H copy and hands the results to the caller's buffer.
-static int drain_slot(snapgpu_aligner *a, int k, snapgpu_single_result *results)
+static int drain_slot(snapgpu_aligner *a, int k, uint8_t *results, size_t resultBytesPerUnit)
 {
     snapgpu_aligner::Slot &sl = a->slot[k];
     if (sl.pendingCount == 0) return 0;
     SG_CUDA(cudaEventSynchronize(sl.evOut));
-    memcpy(results + sl.pendingFirst, sl.h_results, (size_t)sl.pendingCount * sizeof(snapgpu_single_result));
-    for (int64_t i = 0; i < sl.pendingCount; i++) {
-        if (sl.h_results[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+    memcpy(results + (size_t)sl.pendingFirst * resultBytesPerUnit, sl.h_results, (size_t)sl.pendingCount * resultBytesPerUnit);
+    if (!a->paired) {
+        const snapgpu_single_result *r = (const snapgpu_single_result *)sl.h_results;
+        for (int64_t i = 0; i < sl.pendingCount; i++) {
+            if (r[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+        }
     }
     sl.pendingCount = 0;
     return 0;
 }
 
-int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
-                         const uint32_t *lens, snapgpu_single_result *results, snapgpu_counters *counters)
+// Host-buffer path shared by snapgpu_align_single / snapgpu_align_paired.  nUnits units of readsPerUnit reads each.
+// Software pipeline over chunks of reads, two slots: pack chunk c+1 into pinned staging on the host and copy it in
+// while the GPU aligns chunk c and chunk c-1's results stream out.  Kernels stay on one stream (they share the arenas).
+static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size_t resultBytesPerUnit, const char *bases, const char *quals,
+                      const uint64_t *offsets, const uint32_t *lens, uint8_t *results, snapgpu_counters *counters)
 {
-    if (!a || !bases || !quals || !offsets || !lens || !results) return sg_fail("null argument");
-    if (n < 0 || n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads");
-    if (n == 0) return 0;
+    const int64_t n = nUnits * readsPerUnit;
     SG_CUDA(cudaSetDevice(a->device));
     SG_CUDA(cudaMemsetAsync(a->d_counters, 0, sizeof(snapgpu_counters), a->stream));
-    // Software pipeline over chunks of reads, two slots: pack chunk c+1 into pinned staging on the host and copy it in
-    // while the GPU aligns chunk c and chunk c-1's results stream out.  Kernels stay on one stream (they share the arenas).
     int64_t done = 0;
     int c = 0;
     while (done < n) {
         const int k = c & 1;
         snapgpu_aligner::Slot &sl = a->slot[k];
-        if (drain_slot(a, k, results)) return 1;                    // slot k was used by chunk c-2
+        if (drain_slot(a, k, results, resultBytesPerUnit)) return 1;                    // slot k was used by chunk c-2
         int64_t m = 0; size_t total = 0;
         while (done + m < n && m < a->chunkReads) {
-            const uint32_t len = lens[done + m];
-            if (len > SNAPGPU_MAX_READ_LENGTH) return sg_fail("read longer than MAX_READ_LENGTH");
-            if (total + len > a->chunkBases) break;
-            sl.h_offsets[m] = total; sl.h_lens[m] = len;
-            total += len; m++;
+            size_t unitBases = 0;
+            for (int w = 0; w < readsPerUnit; w++) {
+                const uint32_t len = lens[done + m + w];
+                if (len > SNAPGPU_MAX_READ_LENGTH) return sg_fail("read longer than MAX_READ_LENGTH");
+                unitBases += len;
+            }
+            if (total + unitBases > a->chunkBases) break;
+            for (int w = 0; w < readsPerUnit; w++) {
+                sl.h_offsets[m + w] = total; sl.h_lens[m + w] = lens[done + m + w];
+                total += lens[done + m + w];
+            }
+            m += readsPerUnit;
         }
         if (m == 0) return sg_fail("a read does not fit the aligner's staging buffers");
         // reads that are back to back in the caller's buffers (the common case) are packed with one memcpy each way
@@ -785,24 +984,46 @@ int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const
         SG_CUDA(cudaMemcpyAsync(sl.d_lens, sl.h_lens, (size_t)m * 4, cudaMemcpyHostToDevice, a->streamIn));
         SG_CUDA(cudaEventRecord(sl.evIn, a->streamIn));
         SG_CUDA(cudaStreamWaitEvent(a->stream, sl.evIn, 0));
-        if (launch_align(a, m, sl.d_bases, sl.d_quals, sl.d_offsets, sl.d_lens, sl.d_results, a->d_counters, a->stream)) return 1;
+        const int64_t units = m / readsPerUnit;
+        if (launch_align(a, units, sl.d_bases, sl.d_quals, sl.d_offsets, sl.d_lens, sl.d_results, a->d_counters, a->stream)) return 1;
         SG_CUDA(cudaEventRecord(sl.evKernel, a->stream));
         SG_CUDA(cudaStreamWaitEvent(a->streamOut, sl.evKernel, 0));
-        SG_CUDA(cudaMemcpyAsync(sl.h_results, sl.d_results, (size_t)m * sizeof(snapgpu_single_result), cudaMemcpyDeviceToHost, a->streamOut));
+        SG_CUDA(cudaMemcpyAsync(sl.h_results, sl.d_results, (size_t)units * resultBytesPerUnit, cudaMemcpyDeviceToHost, a->streamOut));
         SG_CUDA(cudaEventRecord(sl.evOut, a->streamOut));
-        sl.pendingFirst = done; sl.pendingCount = m;
+        sl.pendingFirst = done / readsPerUnit; sl.pendingCount = units;
         done += m;
         c++;
     }
-    if (drain_slot(a, c & 1, results)) return 1;
-    if (drain_slot(a, (c + 1) & 1, results)) return 1;
+    if (drain_slot(a, c & 1, results, resultBytesPerUnit)) return 1;
+    if (drain_slot(a, (c + 1) & 1, results, resultBytesPerUnit)) return 1;
     SG_CUDA(cudaMemcpyAsync(a->h_counters, a->d_counters, sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, a->stream));
     SG_CUDA(cudaStreamSynchronize(a->stream));
+    if (a->paired && snapgpu_aligner_check(a, nullptr)) return 1;
     if (counters) {
         int64_t *dst = (int64_t *)counters; const int64_t *src = (const int64_t *)a->h_counters;
         for (size_t k2 = 0; k2 < sizeof(snapgpu_counters) / 8; k2++) dst[k2] += src[k2];
     }
     return 0;
+}
+
+int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
+                         const uint32_t *lens, snapgpu_single_result *results, snapgpu_counters *counters)
+{
+    if (!a || !bases || !quals || !offsets || !lens || !results) return sg_fail("null argument");
+    if (a->paired) return sg_fail("snapgpu_align_single called on a paired-end aligner handle");
+    if (n < 0 || n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads");
+    if (n == 0) return 0;
+    return align_host(a, n, 1, sizeof(snapgpu_single_result), bases, quals, offsets, lens, (uint8_t *)results, counters);
+}
+
+int snapgpu_align_paired(snapgpu_aligner *a, int64_t nPairs, const char *bases, const char *quals, const uint64_t *offsets,
+                         const uint32_t *lens, snapgpu_paired_result *results, snapgpu_counters *counters)
+{
+    if (!a || !bases || !quals || !offsets || !lens || !results) return sg_fail("null argument");
+    if (!a->paired) return sg_fail("snapgpu_align_paired called on a single-end aligner handle");
+    if (nPairs < 0 || 2 * nPairs > a->maxBatchReads) return sg_fail("pair count exceeds maxBatchPairs");
+    if (nPairs == 0) return 0;
+    return align_host(a, nPairs, 2, sizeof(snapgpu_paired_result), bases, quals, offsets, lens, (uint8_t *)results, counters);
 }
 
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a) { return a ? a->launches : 0; }

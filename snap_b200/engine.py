@@ -36,6 +36,16 @@ class Params(C.Structure):
     ]
 
 
+class PairedParams(C.Structure):
+    """snapgpu_paired_params (the extra options `snap paired` reads, PairedAligner.cpp:228-243)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("minSpacing", C.c_int32), ("maxSpacing", C.c_uint32), ("intersectingAlignerMaxHits", C.c_uint32),
+        ("maxCandidatePoolSize", C.c_uint32), ("maxSeedsSingleEnd", C.c_uint32), ("maxDistForIndels", C.c_uint32), ("forceSpacing", C.c_int32),
+        ("minScoreRealignment", C.c_int32), ("minScoreGapRealignmentALT", C.c_int32), ("minAGScoreImprovement", C.c_int32),
+        ("enableHammingScoringBaseAligner", C.c_int32), ("useSoftClipping", C.c_int32), ("flattenMAPQAtOrBelow", C.c_int32),
+    ]
+
+
 class IndexInfo(C.Structure):
     _fields_ = [
         ("countOfBases", C.c_int64), ("seedLen", C.c_uint32), ("hashTableKeySize", C.c_uint32),
@@ -53,6 +63,15 @@ RESULT_DTYPE = np.dtype([
     ("matchProbability", "<f8"), ("probabilityAllCandidates", "<f8"),
     ("popularSeedsSkipped", "<u4"), ("reserved", "<u4"),
 ])
+PAIRED_RESULT_DTYPE = np.dtype([
+    ("status", "<i4", 2), ("direction", "<i4", 2), ("location", "<i8", 2), ("origLocation", "<i8", 2), ("score", "<i4", 2),
+    ("scorePriorToClipping", "<i4", 2), ("mapq", "<i4", 2), ("clippingForReadAdjustment", "<i4", 2), ("usedAffineGapScoring", "<i4", 2),
+    ("basesClippedBefore", "<i4", 2), ("basesClippedAfter", "<i4", 2), ("agScore", "<i4", 2), ("supplementary", "<i4", 2),
+    ("seedOffset", "<i4", 2), ("lvIndels", "<i4", 2), ("usedGaplessClipping", "<i4", 2), ("refSpan", "<i4", 2), ("liftover", "<i4", 2),
+    ("popularSeedsSkipped", "<u4", 2), ("alignedAsPair", "<i4"), ("agForcedSingleAlignerCall", "<i4"),
+    ("matchProbability", "<f8", 2), ("probabilityAllPairs", "<f8"),
+])
+assert PAIRED_RESULT_DTYPE.itemsize == 200
 COUNTER_FIELDS = ["totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups",
                   "nHashEntriesProbed", "nOverflowWordsRead", "lvCalls", "affineGapCalls",
                   "nHitsIgnoredBecauseOfTooHighPopularity"]
@@ -63,7 +82,8 @@ EXPORTS = [
     "snapgpu_last_error", "snapgpu_abi_version", "snapgpu_device_count", "snapgpu_params_default",
     "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close",
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
-    "snapgpu_align_single_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
+    "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 _lib = None
@@ -92,6 +112,11 @@ def lib():
         L.snapgpu_aligner_destroy.argtypes = [C.c_void_p]
         L.snapgpu_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.snapgpu_align_single_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        L.snapgpu_paired_params_default.argtypes = [C.POINTER(PairedParams)]
+        L.snapgpu_paired_aligner_create.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams), C.c_int64, C.POINTER(C.c_void_p)]
+        L.snapgpu_align_paired.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.snapgpu_align_paired_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        L.snapgpu_aligner_check.argtypes = [C.c_void_p, C.c_void_p]
         L.snapgpu_aligner_launch_count.restype = C.c_int64
         L.snapgpu_aligner_launch_count.argtypes = [C.c_void_p]
         L.snapgpu_test_lv.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
@@ -117,6 +142,16 @@ def _p(a):
 def default_params(**kw) -> Params:
     p = Params()
     lib().snapgpu_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def default_paired_params(**kw) -> PairedParams:
+    p = PairedParams()
+    lib().snapgpu_paired_params_default(C.byref(p))
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)
@@ -219,6 +254,51 @@ class SingleAligner:
         """Device pointers (ints) in; enqueues on `stream`; no synchronisation: snapgpu_align_single_device."""
         _check(lib().snapgpu_align_single_device(self.handle, n, C.c_void_p(d_bases), C.c_void_p(d_quals), C.c_void_p(d_offsets),
                                                   C.c_void_p(d_lens), C.c_void_p(d_results), C.c_void_p(d_counters), C.c_void_p(stream)))
+
+    def launch_count(self) -> int:
+        return int(lib().snapgpu_aligner_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            lib().snapgpu_aligner_destroy(self.handle)
+            self.handle = None
+
+
+class PairedAligner:
+    """ChimericPairedEndAligner(IntersectingPairedEndAligner) for batches of pairs (reference PairedAligner.cpp:547-800).
+    Pair i = reads 2i, 2i+1 of the batch."""
+
+    def __init__(self, index: Index, params: Params, pparams: PairedParams, max_batch_pairs: int = 1 << 19):
+        self.index = index
+        self.params = params
+        self.pparams = pparams
+        h = C.c_void_p()
+        _check(lib().snapgpu_paired_aligner_create(index.handle, C.byref(params), C.byref(pparams), max_batch_pairs, C.byref(h)))
+        self.handle = h
+        self.max_batch_pairs = max_batch_pairs
+
+    def align(self, batch):
+        """Host buffers in, host results out (copies inside): snapgpu_align_paired."""
+        n_pairs = batch.n // 2
+        res = np.zeros(n_pairs, dtype=PAIRED_RESULT_DTYPE)
+        ctr = np.zeros(N_COUNTERS, dtype=np.int64)
+        done = 0
+        while done < n_pairs:
+            m = min(self.max_batch_pairs, n_pairs - done)
+            sub_off = batch.offsets[2 * done:2 * (done + m)]
+            sub_len = batch.lens[2 * done:2 * (done + m)]
+            _check(lib().snapgpu_align_paired(self.handle, m, _p(batch.bases), _p(batch.quals), _p(sub_off), _p(sub_len),
+                                               C.c_void_p(res.ctypes.data + done * PAIRED_RESULT_DTYPE.itemsize), _p(ctr)))
+            done += m
+        return res, counters_dict(ctr)
+
+    def align_device(self, n_pairs, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters=0, stream=0):
+        """Device pointers (ints) in; enqueues on `stream`; no synchronisation: snapgpu_align_paired_device."""
+        _check(lib().snapgpu_align_paired_device(self.handle, n_pairs, C.c_void_p(d_bases), C.c_void_p(d_quals), C.c_void_p(d_offsets),
+                                                  C.c_void_p(d_lens), C.c_void_p(d_results), C.c_void_p(d_counters), C.c_void_p(stream)))
+
+    def check(self, stream=0):
+        _check(lib().snapgpu_aligner_check(self.handle, C.c_void_p(stream)))
 
     def launch_count(self) -> int:
         return int(lib().snapgpu_aligner_launch_count(self.handle))

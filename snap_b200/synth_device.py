@@ -43,6 +43,31 @@ def _comp_table(device):
     return _COMP
 
 
+def _mutated_windows(bases, loc, read_len, g, lut, sub_rate, indel_rate):
+    """[m, read_len] reads cut at genome locations `loc` (forward strand) with substitutions and at most one indel each."""
+    device = bases.device
+    m = loc.numel()
+    ar = torch.arange(read_len, device=device, dtype=torch.int64)[None, :]
+    # at most one indel event per read: P(event) = 1 - (1 - indel_rate)^read_len, half insertions half deletions
+    ev = torch.rand((m,), generator=g, device=device) < (1.0 - (1.0 - indel_rate) ** read_len)
+    is_ins = torch.rand((m,), generator=g, device=device) < 0.5
+    p = torch.randint(1, read_len - 1, (m,), generator=g, device=device)
+    shift = torch.zeros((m, read_len), dtype=torch.int64, device=device)
+    dele = (ev & ~is_ins)[:, None] & (ar >= p[:, None])
+    ins = (ev & is_ins)[:, None] & (ar > p[:, None])
+    shift = shift + dele.to(torch.int64) - ins.to(torch.int64)
+    win = bases[(loc[:, None] + ar + shift).reshape(-1)].reshape(m, read_len)
+    inserted = (ev & is_ins)[:, None] & (ar == p[:, None])
+    rnd = lut[torch.randint(0, 4, (m, read_len), generator=g, device=device)]
+    win = torch.where(inserted, rnd, win)
+    sub = torch.rand((m, read_len), generator=g, device=device) < sub_rate
+    # substitute with a *different* base: rotate through ACGT by 1..3
+    code = torch.zeros_like(win, dtype=torch.int64)
+    code[win == ord("C")] = 1; code[win == ord("G")] = 2; code[win == ord("T")] = 3
+    rot = (code + torch.randint(1, 4, (m, read_len), generator=g, device=device)) % 4
+    return torch.where(sub, lut[rot], win)
+
+
 def make_reads(bases: torch.Tensor, contig_starts: np.ndarray, contig_len: int, n: int, read_len: int, seed: int,
                sub_rate: float = 0.01, indel_rate: float = 0.001, rc_frac: float = 0.5):
     """Returns device tensors (bases [n*read_len] u8, quals [n*read_len] u8, offsets [n] u64-as-i64, lens [n] i32->u32)
@@ -55,31 +80,13 @@ def make_reads(bases: torch.Tensor, contig_starts: np.ndarray, contig_len: int, 
     out_b = torch.empty((n, read_len), dtype=torch.uint8, device=device)
     truth_loc = torch.empty((n,), dtype=torch.int64, device=device)
     truth_rc = torch.empty((n,), dtype=torch.bool, device=device)
-    ar = torch.arange(read_len, device=device, dtype=torch.int64)[None, :]
     chunk = 1 << 20
     for o in range(0, n, chunk):
         m = min(chunk, n - o)
         ci = torch.randint(0, len(contig_starts), (m,), generator=g, device=device)
         pos = torch.randint(0, contig_len - read_len - 8, (m,), generator=g, device=device)
         loc = starts[ci] + pos
-        # at most one indel event per read: P(event) = 1 - (1 - indel_rate)^read_len, half insertions half deletions
-        ev = torch.rand((m,), generator=g, device=device) < (1.0 - (1.0 - indel_rate) ** read_len)
-        is_ins = torch.rand((m,), generator=g, device=device) < 0.5
-        p = torch.randint(1, read_len - 1, (m,), generator=g, device=device)
-        shift = torch.zeros((m, read_len), dtype=torch.int64, device=device)
-        dele = (ev & ~is_ins)[:, None] & (ar >= p[:, None])
-        ins = (ev & is_ins)[:, None] & (ar > p[:, None])
-        shift = shift + dele.to(torch.int64) - ins.to(torch.int64)
-        win = bases[(loc[:, None] + ar + shift).reshape(-1)].reshape(m, read_len)
-        inserted = (ev & is_ins)[:, None] & (ar == p[:, None])
-        rnd = lut[torch.randint(0, 4, (m, read_len), generator=g, device=device)]
-        win = torch.where(inserted, rnd, win)
-        sub = torch.rand((m, read_len), generator=g, device=device) < sub_rate
-        # substitute with a *different* base: rotate through ACGT by 1..3
-        code = torch.zeros_like(win, dtype=torch.int64)
-        code[win == ord("C")] = 1; code[win == ord("G")] = 2; code[win == ord("T")] = 3
-        rot = (code + torch.randint(1, 4, (m, read_len), generator=g, device=device)) % 4
-        win = torch.where(sub, lut[rot], win)
+        win = _mutated_windows(bases, loc, read_len, g, lut, sub_rate, indel_rate)
         rc = torch.rand((m,), generator=g, device=device) < rc_frac
         rcwin = _comp_table(device)[win.flip(1).to(torch.int64)]
         win = torch.where(rc[:, None], rcwin, win)
@@ -90,3 +97,38 @@ def make_reads(bases: torch.Tensor, contig_starts: np.ndarray, contig_len: int, 
     offsets = (torch.arange(n, device=device, dtype=torch.int64) * read_len)
     lens = torch.full((n,), read_len, dtype=torch.int32, device=device)
     return out_b.reshape(-1), quals.reshape(-1), offsets, lens, truth_loc, truth_rc
+
+
+def make_pairs(bases: torch.Tensor, contig_starts: np.ndarray, contig_len: int, n_pairs: int, read_len: int, seed: int,
+               insert_mean: float = 400.0, insert_sd: float = 40.0, sub_rate: float = 0.01, indel_rate: float = 0.001):
+    """FR pairs (insert N(400, 40)): reads 2i / 2i+1 are the two ends of fragment i, one end forward
+    from the fragment start, the other the reverse complement of the fragment end; which comes first is a coin flip.
+    Returns (bases [2n*read_len], quals, offsets [2n], lens [2n], fragment start location [n], insert [n])."""
+    device = bases.device
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    starts = torch.from_numpy(contig_starts).to(device)
+    out_b = torch.empty((n_pairs, 2, read_len), dtype=torch.uint8, device=device)
+    truth_loc = torch.empty((n_pairs,), dtype=torch.int64, device=device)
+    truth_ins = torch.empty((n_pairs,), dtype=torch.int64, device=device)
+    chunk = 1 << 19
+    for o in range(0, n_pairs, chunk):
+        m = min(chunk, n_pairs - o)
+        ci = torch.randint(0, len(contig_starts), (m,), generator=g, device=device)
+        ins = (torch.randn((m,), generator=g, device=device) * insert_sd + insert_mean).round().to(torch.int64).clamp(read_len + 10, 900)
+        pos = torch.randint(0, contig_len - 1000 - 8, (m,), generator=g, device=device)
+        loc = starts[ci] + pos
+        left = _mutated_windows(bases, loc, read_len, g, lut, sub_rate, indel_rate)
+        right = _mutated_windows(bases, loc + ins - read_len, read_len, g, lut, sub_rate, indel_rate)
+        right = _comp_table(device)[right.flip(1).to(torch.int64)]
+        flip = torch.rand((m,), generator=g, device=device) < 0.5
+        out_b[o:o + m, 0] = torch.where(flip[:, None], right, left)
+        out_b[o:o + m, 1] = torch.where(flip[:, None], left, right)
+        truth_loc[o:o + m] = loc
+        truth_ins[o:o + m] = ins
+    n = 2 * n_pairs
+    quals = (torch.randint(20, 41, (n, read_len), generator=g, device=device) + 33).to(torch.uint8)
+    offsets = (torch.arange(n, device=device, dtype=torch.int64) * read_len)
+    lens = torch.full((n,), read_len, dtype=torch.int32, device=device)
+    return out_b.reshape(-1), quals.reshape(-1), offsets, lens, truth_loc, truth_ins

@@ -53,6 +53,14 @@ class SmallCfg:
             "long250": synth.make_reads(self.contigs, 500, 250, seed=35, sub_rate=0.02, ins_rate=0.002, del_rate=0.002),
         }
 
+        self.pairs = {
+            "std150": synth.make_pairs(self.contigs, 600, 150, seed=41, chimeric_frac=0.03, n_run_frac=0.03, short_frac=0.03),
+            "noisy150": synth.make_pairs(self.contigs, 600, 150, seed=42, sub_rate=0.04, ins_rate=0.004, del_rate=0.004,
+                                         chimeric_frac=0.05, n_run_frac=0.05, short_frac=0.05),
+            "len100": synth.make_pairs(self.contigs, 400, 100, seed=43, sub_rate=0.02, ins_rate=0.002, del_rate=0.002),
+            "len250": synth.make_pairs(self.contigs, 300, 250, seed=44, sub_rate=0.02, ins_rate=0.003, del_rate=0.003, insert_mean=500),
+        }
+
     def padded_bases(self):
         """Genome as SNAP lays it out: 2000 'n' before each contig and at the end (FASTA.cpp:362-391)."""
         parts, starts, pos = [], [], 0
@@ -91,4 +99,33 @@ OPTION_SETS = {
     "esd3_ms2": dict(maxDist=14, extraSearchDepth=3, minWeightToCheck=2),
     "nobanded": dict(maxDist=14, noBandedAffineGap=1),
     "stopfirst": dict(maxDist=14, stopOnFirstHit=1),
+}
+
+
+def differing_pairs(want: np.ndarray, got: np.ndarray) -> list[int]:
+    """Indices of pairs whose result records differ (doubles bit-for-bit).  mapq / scorePriorToClipping of an end that is
+    reported NotFound are excluded: ChimericPairedEndAligner copies them from a stack SingleAlignmentResult that
+    BaseAligner::AlignRead leaves unwritten on its NotFound paths (ChimericPairedEndAligner.cpp:268, :417-426), i.e. the
+    reference's own values there are whatever the previous pair left on the stack."""
+    w, g = want.copy(), got.copy()
+    for arr in (w, g):
+        nf = arr["status"] == 0
+        arr["mapq"][nf] = 0
+        arr["scorePriorToClipping"][nf] = 0
+    return [i for i in range(len(w)) if w[i].tobytes() != g[i].tobytes()]
+
+
+# `snap paired -hc` style option sets (soft clipping off: bonuses 5/5, minAGScoreImprovement 15, PairedAligner.cpp:380-392)
+_HC = dict(fivePrimeEndBonus=5, threePrimeEndBonus=5)
+_HCP = dict(useSoftClipping=0, minAGScoreImprovement=15)
+PAIRED_OPTION_SETS = {
+    "hc_d14": (dict(maxDist=14, **_HC), dict(**_HCP)),
+    "hc_d27": (dict(maxDist=27, **_HC), dict(**_HCP)),
+    "hc_h20_H50": (dict(maxDist=14, maxHits=20, **_HC), dict(intersectingAlignerMaxHits=50, **_HCP)),
+    "hc_coverage": (dict(maxDist=14, numSeedsFromCommandLine=0, seedCoverage=2.0, **_HC), dict(**_HCP)),
+    "hc_noag": (dict(maxDist=14, useAffineGap=0), dict(**_HCP)),
+    "hc_forcespacing": (dict(maxDist=14, **_HC), dict(forceSpacing=1, **_HCP)),
+    "hc_spacing_300_450": (dict(maxDist=14, **_HC), dict(minSpacing=300, maxSpacing=450, **_HCP)),
+    "hc_noopt": (dict(maxDist=10, noUkkonen=1, noOrderedEvaluation=1, noTruncation=1, **_HC), dict(**_HCP)),
+    "hc_nobanded_esd4": (dict(maxDist=14, noBandedAffineGap=1, extraSearchDepth=4, **_HC), dict(maxDistForIndels=20, **_HCP)),
 }

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import jobs as J
-from conftest import OPTION_SETS, differing
+from conftest import OPTION_SETS, PAIRED_OPTION_SETS, differing, differing_pairs
 
 pytestmark = pytest.mark.gpu
 
@@ -245,3 +245,95 @@ def test_properties_at_scale(engine, small_cfg):
     assert (ra["location"][both] == rb2["location"][both]).all() and (ra["direction"][both] != rb2["direction"][both]).all()
     assert sum(c1["mapqHistogram"]) == int(aligned.sum()) == c1["singleHits"] + c1["multiHits"]
     ix.close()
+
+
+@pytest.mark.parametrize("opt", list(PAIRED_OPTION_SETS))
+def test_pairs_match_reference(engine, gidx, small_cfg, reflib, opt):
+    """snapgpu_align_paired (one warp per pair) vs ChimericPairedEndAligner(IntersectingPairedEndAligner) of the compiled reference."""
+    kw, pkw = PAIRED_OPTION_SETS[opt]
+    al = engine.PairedAligner(gidx, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 2048)
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    ridx = reflib.RefIndex(small_cfg.idx)
+    for name, pb in small_cfg.pairs.items():
+        ral = reflib.RefPairedAligner(ridx, p, pp)
+        want, _ = ral.align(pb)
+        ral.close()
+        got, ctr = al.align(pb)
+        assert differing_pairs(want, got) == [], (opt, name)
+        assert ctr["totalReads"] == pb.n
+    al.close()
+
+
+def test_pairs_large_index_and_split_batches(engine, small_cfg, reflib):
+    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    ix = engine.Index.open(small_cfg.idx_large)
+    pb = small_cfg.pairs["noisy150"]
+    want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx_large), reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)).align(pb)
+    big = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 4096)
+    got, c1 = big.align(pb)
+    assert differing_pairs(want, got) == []
+    small = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 100)
+    got2, c2 = small.align(pb)
+    assert differing_pairs(want, got2) == [] and c1["lvCalls"] == c2["lvCalls"] and small.launch_count() == (pb.n // 2 + 99) // 100
+    big.close(); small.close(); ix.close()
+
+
+def test_paired_edge_cases(engine, gidx, small_cfg, reflib):
+    from snap_b200 import synth
+    c = small_cfg.contigs[0]
+    rc = synth.revcomp
+    def q(n): return b"5" * n
+    pairs = [
+        (c[1000:1150].tobytes(), rc(c[1300:1450]).tobytes()),              # clean FR pair
+        (rc(c[1300:1450]).tobytes(), c[1000:1150].tobytes()),              # same, ends swapped
+        (c[1000:1150].tobytes(), c[1300:1450].tobytes()),                  # FF: not a proper pair
+        (c[1000:1150].tobytes(), rc(small_cfg.contigs[1][5000:5150]).tobytes()),   # mates on different contigs
+        (c[1000:1150].tobytes(), rc(c[9000:9150]).tobytes()),              # too far apart
+        (c[1000:1150].tobytes(), b"ACGTACGTAC"),                           # mate shorter than a seed
+        (c[1000:1040].tobytes(), rc(c[1300:1450]).tobytes()),              # first end < minReadLength
+        (b"N" * 150, rc(c[1300:1450]).tobytes()),                          # all-N end
+        (c[1000:1040].tobytes(), c[1300:1330].tobytes()),                  # both ends too short
+        (c[0:150].tobytes(), rc(c[250:400]).tobytes()),                    # at the very start of a contig
+        (c[c.size - 400:c.size - 250].tobytes(), rc(c[c.size - 150:]).tobytes()),   # at the very end
+        (c[1000:1150].tobytes(), rc(c[1020:1170]).tobytes()),              # overlapping mates
+        (c[1000:1150].tobytes(), rc(c[1000:1150]).tobytes()),              # identical span
+    ]
+    rb = synth.ReadBatch.from_lists([(x, q(len(x))) for pr in pairs for x in pr])
+    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)).align(rb)
+    al = engine.PairedAligner(gidx, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 64)
+    got, _ = al.align(rb)
+    assert differing_pairs(want, got) == []
+    res, ctr = al.align(synth.ReadBatch.from_lists([]))
+    assert len(res) == 0 and ctr["totalReads"] == 0
+    with pytest.raises(engine.SnapGpuError):
+        al.align(synth.ReadBatch.from_lists([(b"A" * 401, b"5" * 401), (b"A" * 100, b"5" * 100)]))
+    with pytest.raises(engine.SnapGpuError):      # soft clipping (Hamming pass) is not implemented: must be refused, not approximated
+        engine.PairedAligner(gidx, engine.default_params(numSeedsFromCommandLine=8, maxDist=14), engine.default_paired_params(), 64)
+    al.close()
+
+
+def test_paired_properties_at_scale(engine, small_cfg):
+    """No oracle: results independent of batch order; pairs cut from the reference come back as proper pairs at their
+    source positions; swapping the ends of every pair swaps the result columns."""
+    from snap_b200 import synth
+    bases, starts = small_cfg.padded_bases()
+    ix = engine.Index.build(bases, starts)
+    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    n = 20000
+    pb = synth.make_pairs(small_cfg.contigs, n, 150, seed=91)
+    al = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 1 << 15)
+    r1, c1 = al.align(pb)
+    perm = np.random.default_rng(6).permutation(n)
+    lst = []
+    for i in perm:
+        lst += [pb.read(2 * int(i)), pb.read(2 * int(i) + 1)]
+    r2, _ = al.align(synth.ReadBatch.from_lists(lst))
+    inv = np.empty(n, dtype=np.int64); inv[perm] = np.arange(n)
+    assert differing_pairs(r1, r2[inv]) == []
+    assert r1["alignedAsPair"].mean() > 0.97
+    proper = (r1["alignedAsPair"] == 1) & (r1["status"][:, 0] != 0) & (r1["status"][:, 1] != 0)
+    d = np.abs(r1["location"][proper, 0] - r1["location"][proper, 1])
+    assert (d <= 1000).all() and (r1["direction"][proper, 0] != r1["direction"][proper, 1]).all()
+    assert c1["totalReads"] == 2 * n and sum(c1["mapqHistogram"]) == int((r1["status"] != 0).sum())
+    al.close(); ix.close()

@@ -9,7 +9,7 @@ import pytest
 
 import hostsim_lib as hs
 import jobs as J
-from conftest import OPTION_SETS, differing
+from conftest import OPTION_SETS, PAIRED_OPTION_SETS, differing, differing_pairs
 
 
 def test_tables_wrap_and_mapq(reflib):
@@ -163,3 +163,33 @@ def test_edge_reads(reflib, small_cfg):
     got, _ = hs.HsAligner(hs.HsIndex(small_cfg.idx), p, max_read_len=L).align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
     assert differing(want, got) == []
     assert want[6]["status"] == 1 and want[0]["status"] == 0 and want[3]["status"] == 0
+
+
+@pytest.mark.parametrize("opt", list(PAIRED_OPTION_SETS))
+def test_pairs_match_reference(reflib, small_cfg, opt):
+    """ChimericPairedEndAligner(IntersectingPairedEndAligner) restated in sg_paired.h vs the compiled reference."""
+    kw, pkw = PAIRED_OPTION_SETS[opt]
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for name, pb in small_cfg.pairs.items():
+        ral = reflib.RefPairedAligner(ridx, p, pp)
+        want, _ = ral.align(pb)
+        ral.close()
+        got, _, _ = hs.HsPairedAligner(hidx, p, pp).align(pb, reflib.PAIRED_RESULT_DTYPE)
+        assert differing_pairs(want, got) == [], (opt, name)
+        assert int(want["alignedAsPair"].sum()) > 0 or opt == "hc_spacing_300_450"
+
+
+def test_pairs_large_index(reflib, small_cfg):
+    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    pb = small_cfg.pairs["noisy150"]
+    want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx_large), p, pp).align(pb)
+    got, _, _ = hs.HsPairedAligner(hs.HsIndex(small_cfg.idx_large), p, pp).align(pb, reflib.PAIRED_RESULT_DTYPE)
+    assert differing_pairs(want, got) == []
+
+
+def test_paired_soft_clipping_is_refused(reflib, small_cfg):
+    """The Hamming / gapless pass is not restated: asking for it must fail loudly, not silently align differently."""
+    with pytest.raises(RuntimeError):
+        hs.HsPairedAligner(hs.HsIndex(small_cfg.idx), reflib.default_params_paired(maxDist=14), reflib.default_paired_params())
