@@ -256,8 +256,9 @@ int  snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_ba
 /*
  * Paired-end aligner handle: the ChimericPairedEndAligner(IntersectingPairedEndAligner) stack that
  * PairedAlignerContext::runIterationThread builds per thread (reference SNAPLib/PairedAligner.cpp:547-638).
- * Scope: no secondary results (-om unset), no ALT contigs, and useSoftClipping must be 0 (`snap paired -hc`): the
- * Hamming / gapless-clipping pass that soft clipping adds is not implemented, and creation fails if it is asked for.
+ * Scope: no secondary results (-om unset), no ALT contigs.  Soft clipping (the default) runs the Hamming / gapless
+ * passes of both aligners (IntersectingPairedEndAligner::alignHamming, BaseAligner::AlignRead(useHamming) +
+ * alignAffineGap); useSoftClipping = 0 is `snap paired -hc`.
  */
 void snapgpu_paired_params_default(snapgpu_paired_params *pp);   /* `snap paired` 2.0.5 defaults */
 int  snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params *params, const snapgpu_paired_params *pparams,

@@ -405,3 +405,45 @@ SG_HDN void sg_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParam
                  bestLocalAlignmentScore, bestLocalAlignmentTextOffset, bestLocalAlignmentPatternOffset,
                  bestGlobalAlignmentScore, bestGlobalAlignmentTextOffset, out);
 }
+
+// AffineGapVectorized<dir>::computeGaplessScore (AffineGapVectorized.h:139-255): Hamming extension from the seed with the
+// poorly matching end clipped at the prefix of maximum score.  In/out like the reference: *o_nEdits, *o_textOffset,
+// *o_patternOffset, *matchProbability and *o_nEditsGapless are only written on the paths that write them there
+// (pass NULL for the ones the caller passes NULL for).  `dir` = +1 forward text, -1 text read backwards from text-1.
+struct SgGaplessOut { int nEdits, textOffset, patternOffset, nEditsGapless; double matchProbability; };
+
+SG_HDN int sg_gapless_compute(const SgTables &T, const SgAgParams &P, int dir, const uint8_t *text, int textLen, const uint8_t *pattern,
+                              const uint8_t *quality, int patternLen, int scoreInit, int scoreLimit, SgGaplessOut *o)
+{
+    (void)textLen;
+    if (scoreLimit < 0 || (const uint8_t *)0 == text) {
+        o->nEdits = SG_SCORE_ABOVE_LIMIT; o->nEditsGapless = SG_SCORE_ABOVE_LIMIT;
+        return SG_SCORE_ABOVE_LIMIT;
+    }
+    o->matchProbability = 1.0;
+    if (dir == -1) text--;
+    int gapLessScore = scoreInit, maxScore = scoreInit, best = 0;
+    for (int i = 0; i < patternLen; i++) {
+        gapLessScore += (pattern[i] == text[i * dir]) ? P.matchReward : P.subPenalty;
+        if (gapLessScore > maxScore) { maxScore = gapLessScore; best = i; }
+    }
+    if (maxScore > scoreInit) {
+        int nEdits = 0, nMatches = 0;
+        double mp = 1.0;
+        for (int i = 0; i <= best; i++) {
+            if (pattern[i] != text[i * dir]) { nEdits += 1; mp *= T.phred[quality[i]]; }
+            else nMatches++;
+        }
+        mp *= T.perfect[nMatches];
+        int po = patternLen - (best + 1);
+        o->patternOffset = po;
+        o->textOffset = po;
+        o->nEditsGapless = (nEdits <= scoreLimit) ? nEdits : -1;
+        o->nEdits = nEdits + po;
+        mp *= T.indel[po];
+        o->matchProbability = mp;
+        return maxScore;
+    }
+    o->nEdits = SG_SCORE_ABOVE_LIMIT; o->nEditsGapless = SG_SCORE_ABOVE_LIMIT;
+    return SG_SCORE_ABOVE_LIMIT;
+}

@@ -79,6 +79,75 @@ struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260
             bestScoreMatchProbability = el->matchProbabilityForBestScore;
         }
     }
+    // ScoreSet::updateBestScore with a candidatesForAffineGap buffer (the Hamming pass, :1444-1456): the displaced best / the
+    // near-best candidate is appended when it is within extraSearchDepth of the best (:2202-2226, :2273-2297).
+    // Returns false if the buffer is full (the reference's caller then reports an overflow).
+    SG_HD bool updateBestScoreRecording(int64_t genomeLocation, int64_t origGenomeLocation, unsigned score, bool useAffineGap, int agScore,
+                                        double matchProbability, const SgElem *el, snapgpu_single_result *cands, int *nCands, int maxCands, int extraSearchDepth) {
+        bool seenNewBestScore;
+        if (useAffineGap) {
+            seenNewBestScore = (agScore > bestScoreAGScore) || (bestScoreAGScore == agScore && matchProbability > probabilityOfBestCandidate);
+        } else {
+            seenNewBestScore = (score < (unsigned)bestScore) || (score == (unsigned)bestScore && matchProbability > probabilityOfBestCandidate);
+        }
+        if (seenNewBestScore) {
+            if ((unsigned)bestScore >= score) {
+                if ((unsigned)bestScore >= score && (int)((unsigned)bestScore - score) <= extraSearchDepth) {
+                    if (*nCands >= maxCands) { *nCands = maxCands + 1; return false; }
+                    snapgpu_single_result *r = &cands[*nCands];
+                    r->direction = bestScoreDirection; r->location = bestScoreGenomeLocation; r->origLocation = bestScoreOrigGenomeLocation;
+                    r->mapq = 0; r->score = bestScore; r->status = SNAPGPU_MULTIPLE_HITS; r->clippingForReadAdjustment = 0;
+                    r->usedAffineGapScoring = bestScoreUsedAffineGapScoring; r->basesClippedBefore = bestScoreBasesClippedBefore;
+                    r->basesClippedAfter = bestScoreBasesClippedAfter; r->agScore = bestScoreAGScore; r->matchProbability = bestScoreMatchProbability;
+                    r->seedOffset = bestScoreSeedOffset;
+                    (*nCands)++;
+                }
+            }
+            bestScore = (int)score;
+            bestScoreAGScore = agScore;
+            probabilityOfBestCandidate = matchProbability;
+            bestScoreGenomeLocation = genomeLocation;
+            bestScoreOrigGenomeLocation = origGenomeLocation;
+            bestScoreDirection = el->direction;
+            bestScoreUsedAffineGapScoring = el->usedAffineGapScoring;
+            bestScoreBasesClippedBefore = el->basesClippedBefore;
+            bestScoreBasesClippedAfter = el->basesClippedAfter;
+            bestScoreSeedOffset = el->seedOffset;
+            bestScoreMatchProbability = el->matchProbabilityForBestScore;
+        } else {
+            if ((int)((unsigned)bestScore - score) <= extraSearchDepth && score != (unsigned)SG_SCORE_ABOVE_LIMIT && (unsigned)bestScore >= score) {
+                if (*nCands >= maxCands) { *nCands = maxCands + 1; return false; }
+                snapgpu_single_result *r = &cands[*nCands];
+                r->direction = el->direction; r->location = genomeLocation; r->origLocation = origGenomeLocation;
+                r->mapq = 0; r->score = (int)score; r->status = SNAPGPU_MULTIPLE_HITS; r->clippingForReadAdjustment = 0;
+                r->usedAffineGapScoring = el->usedAffineGapScoring; r->basesClippedBefore = el->basesClippedBefore;
+                r->basesClippedAfter = el->basesClippedAfter; r->agScore = el->agScore; r->seedOffset = el->seedOffset;
+                r->matchProbability = el->matchProbabilityForBestScore;
+                (*nCands)++;
+            }
+        }
+        return true;
+    }
+    SG_HD void initFrom(const snapgpu_single_result *r) {               // ScoreSet::init(SingleAlignmentResult*), :2116-2130
+        bestScore = r->score; bestScoreGenomeLocation = r->location; bestScoreOrigGenomeLocation = r->origLocation;
+        bestScoreDirection = r->direction; bestScoreUsedAffineGapScoring = r->usedAffineGapScoring;
+        bestScoreBasesClippedBefore = r->basesClippedBefore; bestScoreBasesClippedAfter = r->basesClippedAfter;
+        bestScoreAGScore = r->agScore; bestScoreSeedOffset = r->seedOffset; bestScoreMatchProbability = r->matchProbability;
+        probabilityOfAllCandidates = r->probabilityAllCandidates; probabilityOfBestCandidate = r->matchProbability;
+    }
+    SG_HD void updateProbabilityOfAllMatches(double oldP) { double v = probabilityOfAllCandidates - oldP; probabilityOfAllCandidates = 0 > v ? 0 : v; }   // BaseAligner.h:282
+    SG_HD void updateProbabilityOfBestMatch(double newP) { probabilityOfBestCandidate = newP; probabilityOfAllCandidates += newP; }
+    SG_HD bool updateBestScoreFromResult(const snapgpu_single_result *r) {   // BaseAligner.h:308-326 (probabilityOfBestCandidate is NOT touched there)
+        probabilityOfAllCandidates += r->matchProbability;
+        if (r->agScore > bestScoreAGScore || (r->agScore == bestScoreAGScore && r->matchProbability > bestScoreMatchProbability)) {
+            bestScore = r->score; bestScoreAGScore = r->agScore; bestScoreMatchProbability = r->matchProbability;
+            bestScoreGenomeLocation = r->location; bestScoreOrigGenomeLocation = r->origLocation; bestScoreDirection = r->direction;
+            bestScoreUsedAffineGapScoring = r->usedAffineGapScoring; bestScoreBasesClippedBefore = r->basesClippedBefore;
+            bestScoreBasesClippedAfter = r->basesClippedAfter; bestScoreSeedOffset = r->seedOffset;
+            return true;
+        }
+        return false;
+    }
     SG_HDN void fillIn(const SgTables &T, snapgpu_single_result *r, int popularSeedsSkipped) const {   // :2301-2323
         r->agScore = bestScoreAGScore;
         r->basesClippedAfter = bestScoreBasesClippedAfter;
@@ -117,6 +186,8 @@ struct SgAligner {
     uint32_t mostSeedsContainingAnyParticularBase[2], nSeedsApplied[2];
     SgScoreSet all, nonAlt;
     int64_t invalidLocation;
+    // candidatesForAffineGap of the Hamming pass (only the paired caller provides a buffer)
+    snapgpu_single_result *agCands; int nAgCands, maxAgCands; int agCandsOverflow;
 
     // ---- weight lists: doubly linked FIFO per weight; link values are element indices or SG_SENTINEL+w ----
     SG_HD uint32_t getNext(uint32_t n) const { return (n & SG_SENTINEL) ? sc.listNext[n & ~SG_SENTINEL] : sc.pool[n].weightNext; }
@@ -251,7 +322,8 @@ struct SgCandScore {
     int basesClippedBefore, basesClippedAfter, agScore;
 };
 
-SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLocationIn, int seedOffset, int scoreLimitForThisElement, SgCandScore *o)
+SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLocationIn, int seedOffset, int scoreLimitForThisElement, bool useHamming,
+                               SgCandScore *o)
 {
     const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
     int64_t genomeLocation = genomeLocationIn;
@@ -278,21 +350,45 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
         int64_t tl = genomeDataLength - tailStart;
         int textLen = (int)(tl < 0x7ffffff0 ? tl : 0x7ffffff0);
 
-        SgLvResult lv;
-        sg_lv_compute(T, A.sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart,
-                      scoreLimitForThisElement, &lv, A.lane);
-        score1 = lv.score; matchProb1 = lv.matchProbability;
-        agScore1 = (seedLen + readLen - tailStart - score1) * pr.matchReward - score1 * pr.subPenalty;
-        if (score1 != SG_SCORE_ABOVE_LIMIT) {
-            int limitLeft = scoreLimitForThisElement - score1;
-            sg_lv_compute(T, A.sc, -1, data + seedOffset, seedOffset + SG_MAX_K, revRead + readLen - seedOffset, oppQual + readLen - seedOffset,
-                          seedOffset, limitLeft, &lv, A.lane);
-            score2 = lv.score; matchProb2 = lv.matchProbability; genomeLocationOffset = lv.netIndel;
-            agScore2 = (seedOffset - score2) * pr.matchReward - score2 * pr.subPenalty;
+        int score1Gapless = 0, score2Gapless = 0;
+        if (!useHamming) {
+            SgLvResult lv;
+            sg_lv_compute(T, A.sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart,
+                          scoreLimitForThisElement, &lv, A.lane);
+            score1 = lv.score; matchProb1 = lv.matchProbability;
+            agScore1 = (seedLen + readLen - tailStart - score1) * pr.matchReward - score1 * pr.subPenalty;
+            if (score1 != SG_SCORE_ABOVE_LIMIT) {
+                int limitLeft = scoreLimitForThisElement - score1;
+                sg_lv_compute(T, A.sc, -1, data + seedOffset, seedOffset + SG_MAX_K, revRead + readLen - seedOffset, oppQual + readLen - seedOffset,
+                              seedOffset, limitLeft, &lv, A.lane);
+                score2 = lv.score; matchProb2 = lv.matchProbability; genomeLocationOffset = lv.netIndel;
+                agScore2 = (seedOffset - score2) * pr.matchReward - score2 * pr.subPenalty;
+            }
+            A.work.lvCalls++;
+        } else {
+            // the Hamming / gapless pass (:1177-1199): extend from the seed without indels, clipping the poorly matching end
+            SgGaplessOut g;
+            if (tailStart != readLen) {
+                g.nEdits = score1; g.matchProbability = matchProb1; g.nEditsGapless = score1Gapless;
+                agScore1 = sg_gapless_compute(T, A.ag, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart,
+                                              readLen, scoreLimitForThisElement, &g);
+                score1 = g.nEdits; matchProb1 = g.matchProbability; score1Gapless = g.nEditsGapless;
+                agScore1 += (seedLen - readLen);
+            }
+            if (score1Gapless != SG_SCORE_ABOVE_LIMIT) {
+                int limitLeft = scoreLimitForThisElement - score1Gapless;
+                if (seedOffset != 0) {
+                    g.nEdits = score2; g.matchProbability = matchProb2; g.nEditsGapless = score2Gapless; g.textOffset = genomeLocationOffset;
+                    agScore2 = sg_gapless_compute(T, A.ag, -1, data + seedOffset, seedOffset + SG_MAX_K, revRead + readLen - seedOffset,
+                                                  oppQual + readLen - seedOffset, seedOffset, readLen, limitLeft, &g);
+                    score2 = g.nEdits; matchProb2 = g.matchProbability; score2Gapless = g.nEditsGapless; genomeLocationOffset = g.textOffset;
+                    agScore2 -= readLen;
+                    if (score2Gapless == SG_SCORE_ABOVE_LIMIT) genomeLocationOffset = 0;
+                }
+            }
         }
-        A.work.lvCalls++;
 
-        if (score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT) {
+        if (!useHamming && score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT) {
             // :1203
             if (pr.noEditDistance || (pr.useAffineGap && (score1 + score2 > maxKForSameAlignment && el.lowestPossibleScore <= (unsigned)A.all.bestScore))) {
                 score1 = 0; score2 = 0; agScore1 = seedLen; agScore2 = 0;
@@ -324,7 +420,8 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
             }
         }
 
-        bool foundAlignment = (score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT);
+        bool foundAlignment = useHamming ? (score1Gapless != SG_SCORE_ABOVE_LIMIT && score2Gapless != SG_SCORE_ABOVE_LIMIT)
+                                         : (score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT);
         if (foundAlignment && genomeLocationOffset != 0 &&
             (const uint8_t *)0 == sg_get_substring(ix, genomeLocation + genomeLocationOffset, genomeDataLength)) {
             foundAlignment = false;
@@ -348,7 +445,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
 }
 
 // BaseAligner::score (:917-1534).  Returns true iff a result was reached.
-SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult)
+SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult, bool useHamming = false)
 {
     const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
     if (0 == A.mostSeedsContainingAnyParticularBase[0] && 0 == A.mostSeedsContainingAnyParticularBase[1]) {
@@ -384,7 +481,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                     fin = &A.nonAlt;
                 }
                 primaryResult->score = fin->bestScore;
-                if (fin->bestScore <= (int)A.maxK) {
+                if (fin->bestScore <= (int)A.maxK || (useHamming && fin->bestScore != (int)SG_UNUSED_SCORE)) {
                     fin->fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
                     primaryResult->supplementary = 0;
                     return true;
@@ -419,12 +516,13 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                 bool genomeLocationIsNonALT = (!pr.altAwareness) || !A.isALT(genomeLocation);
 
                 SgCandScore cs;
-                sg_score_candidate(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, &cs);
+                sg_score_candidate(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, useHamming, &cs);
                 unsigned score = cs.score;
                 double matchProbability = cs.matchProbability;
                 genomeLocation = cs.genomeLocation;
 
                 if (anyNearbyCandidatesAlreadyScored) {
+                    if (useHamming && matchProbability <= el.matchProbabilityForBestScore) continue;      // :1362
                     if (el.bestScore < score || (el.bestScore == score && matchProbability <= el.matchProbabilityForBestScore)) {
                         continue;
                     }
@@ -451,6 +549,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                     if (!(dist <= SG_MAX_MERGE_DIST)) {
                         nearby = ~0u;
                     } else {
+                        if (useHamming && ne.matchProbabilityForBestScore >= matchProbability) continue;      // :1418
                         if (ne.bestScore < score || (ne.bestScore == score && ne.matchProbabilityForBestScore >= matchProbability)) {
                             continue;
                         }
@@ -466,13 +565,24 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                 el.matchProbabilityForBestScore = matchProbability;
                 el.bestScore = score;
 
-                A.all.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
-                if (genomeLocationIsNonALT) {
-                    // the reference calls this twice more (:1463, :1484); with no secondary buffers the repeats are no-ops
-                    A.nonAlt.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
+                if (useHamming && A.agCands != (snapgpu_single_result *)0) {
+                    // :1444-1456: both score sets append to the same candidatesForAffineGap buffer
+                    bool ok = A.all.updateBestScoreRecording(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el,
+                                                             A.agCands, &A.nAgCands, A.maxAgCands, (int)pr.extraSearchDepth);
+                    if (ok && genomeLocationIsNonALT) {
+                        ok = A.nonAlt.updateBestScoreRecording(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el,
+                                                               A.agCands, &A.nAgCands, A.maxAgCands, (int)pr.extraSearchDepth);
+                    }
+                    if (!ok || A.nAgCands >= A.maxAgCands) { A.agCandsOverflow = 1; return true; }      // :1475-1478 (the reference returns false = overflow)
+                } else {
+                    A.all.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
+                    if (genomeLocationIsNonALT) {
+                        // the reference calls this twice more (:1463, :1484); with no secondary buffers the repeats are no-ops
+                        A.nonAlt.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
+                    }
                 }
 
-                if (pr.stopOnFirstHit && (A.all.bestScore <= (int)A.maxK)) {
+                if (pr.stopOnFirstHit && ((A.all.bestScore <= (int)A.maxK) || (useHamming && A.all.bestScore != (int)SG_UNUSED_SCORE))) {
                     (pr.altAwareness ? A.nonAlt : A.all).fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
                     primaryResult->status = SNAPGPU_MULTIPLE_HITS;
                     primaryResult->mapq = 0;
@@ -495,7 +605,8 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
 
 // BaseAligner::AlignRead (:272-763) for one read with the stock loop's arguments (SingleAligner.cpp:250).
 // `result` must be caller-zeroed POD; on return it holds what the reference would have put in primaryResult.
-SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult)
+SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult,
+                          bool useHamming = false)
 {
     const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
     const uint32_t seedLen = ix.seedLen;
@@ -595,7 +706,7 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
         if (nextSeedToTest >= nPossibleSeeds) {
             A.wrapCount++;
             if (A.wrapCount >= seedLen) {
-                sg_score(A, true, primaryResult);
+                sg_score(A, true, primaryResult, useHamming);
                 primaryResult->scorePriorToClipping = primaryResult->score;     // finalizeSecondaryResults, :2442
                 return;
             }
@@ -656,12 +767,142 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
         nextSeedToTest += seedLen;
 
         if (appliedEitherSeed) {
-            if (sg_score(A, false, primaryResult)) {
+            if (sg_score(A, false, primaryResult, useHamming)) {
                 primaryResult->scorePriorToClipping = primaryResult->score;
                 return;
             }
         }
     }
-    sg_score(A, true, primaryResult);
+    sg_score(A, true, primaryResult, useHamming);
     primaryResult->scorePriorToClipping = primaryResult->score;
+}
+
+// BaseAligner::scoreLocationWithAffineGap (:766-915): the affine-gap rescoring used by alignAffineGap below.  Note the
+// asymmetry it has in the reference: the forward call passes useClippingOptimizations = true and no text offset, the
+// reverse call leaves useClippingOptimizations at its default (false).
+SG_HDN void sg_single_score_location_ag(SgAligner &A, int direction, int64_t genomeLocation, uint32_t seedOffset, int scoreLimit, int *score,
+                                        double *matchProbability, int *genomeLocationOffset, int *basesClippedBefore, int *basesClippedAfter, int *agScore)
+{
+    const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
+    const int readLen = (int)A.readLen;
+    const int64_t genomeDataLength = (int64_t)readLen + SG_MAX_K;
+    const uint8_t *data = sg_get_substring(ix, genomeLocation, genomeDataLength);
+    *genomeLocationOffset = 0;
+    if (data == (const uint8_t *)0) { *score = SG_SCORE_ABOVE_LIMIT; *matchProbability = 0; *genomeLocationOffset = 0; *agScore = SG_SCORE_ABOVE_LIMIT; return; }
+    *basesClippedBefore = 0; *basesClippedAfter = 0;
+    double matchProb1 = 1.0, matchProb2 = 1.0;
+    int score1 = 0, score2 = 0;
+    const int seedLen = (int)ix.seedLen;
+    const int tailStart = (int)seedOffset + seedLen;
+    int agScore1 = seedLen, agScore2 = 0;
+    const int textLen = (int)(genomeDataLength - tailStart);
+    const uint8_t *readToScore = A.readData[direction], *qualToScore = A.readQual[direction];
+    SgAgResult ar;
+    if (tailStart != readLen) {
+        int patternLen = readLen - tailStart;
+        bool banded = (patternLen >= (3 * (2 * scoreLimit + 1))) && !pr.noBandedAffineGap;
+        ar.textOffset = 0; ar.patternOffset = *basesClippedAfter; ar.nEdits = score1; ar.matchProbability = matchProb1; ar.agScore = -1;
+        sg_ag_dispatch(T, A.sc, A.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, patternLen, scoreLimit, readLen,
+                       direction != 0, true, &ar, A.lane);
+        agScore1 = ar.agScore; *basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
+        agScore1 += (seedLen - readLen);
+        A.work.agCalls++;
+    }
+    if (score1 != SG_SCORE_ABOVE_LIMIT) {
+        if (seedOffset != 0) {
+            int limitLeft = scoreLimit - score1;
+            int patternLen = (int)seedOffset;
+            bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
+            ar.textOffset = *genomeLocationOffset; ar.patternOffset = *basesClippedBefore; ar.nEdits = score2; ar.matchProbability = matchProb2; ar.agScore = -1;
+            sg_ag_dispatch(T, A.sc, A.ag, -1, banded, data + seedOffset, (int)seedOffset + limitLeft, A.sc.revRead[direction] + readLen - seedOffset,
+                           A.readQual[1 - direction] + readLen - seedOffset, patternLen, limitLeft, readLen, direction != 0, false, &ar, A.lane);
+            agScore2 = ar.agScore; *genomeLocationOffset = ar.textOffset; *basesClippedBefore = ar.patternOffset; score2 = ar.nEdits; matchProb2 = ar.matchProbability;
+            agScore2 -= readLen;
+            if (score2 == SG_SCORE_ABOVE_LIMIT) { *score = SG_SCORE_ABOVE_LIMIT; *genomeLocationOffset = 0; *agScore = -1; }
+        }
+    } else {
+        *score = SG_SCORE_ABOVE_LIMIT; *genomeLocationOffset = 0; *agScore = -1;
+    }
+    if (score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT) {
+        *score = score1 + score2;
+        *matchProbability = matchProb1 * matchProb2 * T.snpPowSeedLen;
+        *agScore = agScore1 + agScore2;
+    } else {
+        *score = SG_SCORE_ABOVE_LIMIT; *agScore = -1; *matchProbability = 0.0;
+    }
+}
+
+// BaseAligner::alignAffineGap (:1536-1784) for the read the aligner has just run AlignRead on (its RC / reversed strings and
+// its member score sets, which scoreLimit() reads at :1757, are still in place).  No ALT result.
+SG_HDN void sg_align_affine_gap(SgAligner &A, snapgpu_single_result *result, int nCands, snapgpu_single_result *cands)
+{
+    const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
+    if (result->status == SNAPGPU_NOT_FOUND) return;
+    const int bestScore = result->score;
+    int scoreLimitForCandidate = SG_MAX_K - 1;
+    int genomeOffset = 0;
+    bool skipAffineGap = false;
+    const double oldProbabilityBestResult = result->matchProbability;
+    const int maxKForSameAlignment = pr.gapOpenPenalty / (pr.subPenalty - pr.gapExtendPenalty);
+    result->usedAffineGapScoring = 0;
+    if (result->score > maxKForSameAlignment) {
+        result->usedAffineGapScoring = 1;
+        sg_single_score_location_ag(A, result->direction, result->origLocation, (uint32_t)result->seedOffset, scoreLimitForCandidate, &result->score,
+                                    &result->matchProbability, &genomeOffset, &result->basesClippedBefore, &result->basesClippedAfter, &result->agScore);
+        if (result->score != SG_SCORE_ABOVE_LIMIT) result->location = result->origLocation + genomeOffset;
+        else result->status = SNAPGPU_NOT_FOUND;
+    } else {
+        skipAffineGap = true;
+    }
+    if (result->status == SNAPGPU_NOT_FOUND || result->score > SG_MAX_K - 1) {
+        result->location = A.invalidLocation; result->mapq = 0; result->score = SG_SCORE_ABOVE_LIMIT; result->status = SNAPGPU_NOT_FOUND;
+        result->clippingForReadAdjustment = 0; result->usedAffineGapScoring = 0; result->basesClippedBefore = 0; result->basesClippedAfter = 0;
+        result->agScore = SG_SCORE_ABOVE_LIMIT; result->seedOffset = 0; result->matchProbability = 0.0;
+        return;
+    }
+    SgScoreSet all, nonAlt;
+    nonAlt.init(A.invalidLocation);              // ScoreSet::ScoreSet() (default ctor calls init())
+    const bool nonALTAlignment = (!pr.altAwareness) || !A.isALT(result->location);
+    all.initFrom(result);
+    if (nonALTAlignment) nonAlt.initFrom(result);
+    if (!skipAffineGap) {
+        const double newProbability = result->matchProbability;
+        all.updateProbabilityOfAllMatches(oldProbabilityBestResult);
+        all.updateProbabilityOfBestMatch(newProbability);
+        if (nonALTAlignment) {
+            nonAlt.updateProbabilityOfAllMatches(oldProbabilityBestResult);
+            nonAlt.updateProbabilityOfBestMatch(newProbability);
+        }
+    }
+    if (nCands > 0 && !skipAffineGap) {
+        scoreLimitForCandidate = ((int)A.maxK < bestScore ? (int)A.maxK : bestScore) + (int)pr.extraSearchDepth;
+        // qsort(compareByScore): stable (glibc merge sort)
+        for (int i = 1; i < nCands; i++) {
+            snapgpu_single_result key = cands[i];
+            int j = i - 1;
+            while (j >= 0 && cands[j].score > key.score) { cands[j + 1] = cands[j]; j--; }
+            cands[j + 1] = key;
+        }
+        for (int i = 0; i < nCands; i++) {
+            snapgpu_single_result *c = &cands[i];
+            const bool nonALT = (!pr.altAwareness) || !A.isALT(c->location);
+            const double oldProbability = c->matchProbability;
+            c->usedAffineGapScoring = 1;
+            sg_single_score_location_ag(A, c->direction, c->origLocation, (uint32_t)c->seedOffset, scoreLimitForCandidate, &c->score, &c->matchProbability,
+                                        &genomeOffset, &c->basesClippedBefore, &c->basesClippedAfter, &c->agScore);
+            if (c->score != SG_SCORE_ABOVE_LIMIT && (c->score <= SG_MAX_K - 1)) {
+                c->location = c->origLocation + genomeOffset;
+                if (result->location == c->location) continue;
+                all.updateProbabilityOfAllMatches(oldProbability);
+                all.updateBestScoreFromResult(c);
+                if (nonALT) {
+                    nonAlt.updateProbabilityOfAllMatches(oldProbability);
+                    nonAlt.updateBestScoreFromResult(c);
+                }
+                scoreLimitForCandidate = A.scoreLimit(pr.altAwareness && !nonALT);       // the MEMBER score sets (:1757)
+            }
+        }
+    }
+    const SgScoreSet *emit = ((!pr.altAwareness) || nonAlt.bestScore > all.bestScore + pr.maxScoreGapToPreferNonAltAlignment) ? &all : &nonAlt;
+    emit->fillIn(T, result, (int)result->popularSeedsSkipped);
 }

@@ -265,9 +265,6 @@ static inline bool sg_derive_paired_params(const snapgpu_params &in, const snapg
     s.numSeedsFromCommandLine = pin.maxSeedsSingleEnd;
     if (!sg_derive_params(s, seedLen, maxReadLen, prSingle, err)) return false;
     if (in.stopOnFirstHit) { err = "paired path: stopOnFirstHit is not supported"; return false; }
-#ifndef SG_PAIRED_HAMMING
-    if (pin.useSoftClipping) { err = "paired path: soft clipping (the Hamming/gapless pass) is not implemented; run with useSoftClipping=0 (snap paired -hc)"; return false; }
-#endif
     memset(&pp, 0, sizeof(pp));
     pp.minSpacing = pin.minSpacing; pp.maxSpacing = pin.maxSpacing; pp.maxBigHits = pin.intersectingAlignerMaxHits;
     pp.maxSeedsSingleEnd = pin.maxSeedsSingleEnd; pp.maxKForIndels = pin.maxDistForIndels; pp.forceSpacing = pin.forceSpacing;

@@ -6,9 +6,9 @@
 // HashTableHitSet (:3500-3817), MergeAnchor::checkMerge (:3820-3871), ScoreSet (:3873-3973), computeScoreLimit
 // (:3975-3988); and ChimericPairedEndAligner::align (ChimericPairedEndAligner.cpp:126-448), which falls back to /
 // cross-checks with the single-end aligner of sg_align.h.
-// Configuration covered: no secondary results (-om unset), no ALT contigs; the Hamming / gapless pass that
-// `useSoftClipping` adds (alignHamming :1441-2487 and BaseAligner's useHamming mode) is NOT restated yet, so the
-// paired entry points require useSoftClipping == 0 (`snap paired -hc`) and say so loudly otherwise.
+// alignHamming (:1441-2487) is the same three phases with gapless (Hamming + end clipping) scoring
+// (scoreLocationWithHammingDistance :3401-3497); it is restated here as the `hamming` mode of the same function.
+// Configuration covered: no secondary results (-om unset), no ALT contigs.
 #pragma once
 #include "sg_align.h"
 
@@ -279,6 +279,7 @@ struct SgPairedScratch {
     SgMergeAnchor *anchors;          // [poolSize]
     int32_t *scoreLists;             // [MAX_K + extraSearchDepth + 2] heads (pool index or -1)
     snapgpu_paired_result *lvCandidates;   // [SG_MAX_AG_CANDIDATES]
+    snapgpu_single_result *singleCandidates;   // [SG_MAX_AG_CANDIDATES] candidatesForAffineGap of the single-end Hamming pass
     uint8_t *agBt[2];                // the Chimeric aligner's own AffineGapVectorized objects used by the intersecting aligner
 };
 
@@ -293,6 +294,7 @@ SG_HD size_t sg_paired_scratch_bytes(const SgParams &p, const SgPairedParams &pp
     b += sg_align_up(sizeof(SgMergeAnchor) * (size_t)pp.poolSize, 256);
     b += sg_align_up(4 * (SG_MAX_K + 64), 256);
     b += sg_align_up(sizeof(snapgpu_paired_result) * SG_MAX_AG_CANDIDATES, 256);
+    b += sg_align_up(sizeof(snapgpu_single_result) * SG_MAX_AG_CANDIDATES, 256);
     b += 2 * sg_align_up(agRows * agCols, 256);
     return b;
 }
@@ -316,6 +318,7 @@ SG_HD void sg_paired_scratch_carve(const SgParams &p, const SgPairedParams &pp, 
     s->anchors = (SgMergeAnchor *)q; q += sg_align_up(sizeof(SgMergeAnchor) * (size_t)pp.poolSize, 256);
     s->scoreLists = (int32_t *)q; q += sg_align_up(4 * (SG_MAX_K + 64), 256);
     s->lvCandidates = (snapgpu_paired_result *)q; q += sg_align_up(sizeof(snapgpu_paired_result) * SG_MAX_AG_CANDIDATES, 256);
+    s->singleCandidates = (snapgpu_single_result *)q; q += sg_align_up(sizeof(snapgpu_single_result) * SG_MAX_AG_CANDIDATES, 256);
     s->agBt[0] = q; q += sg_align_up(agRows * agCols, 256);
     s->agBt[1] = q; q += sg_align_up(agRows * agCols, 256);
 }
@@ -466,6 +469,58 @@ SG_HDN void sg_paired_score_location(SgPairedAligner &P, uint32_t whichRead, int
     (void)usedAffineGapScoring;
 }
 
+// IntersectingPairedEndAligner::scoreLocationWithHammingDistance (:3401-3497).  Note what it does NOT set: the clip counts
+// stay 0 (the gapless scorer's pattern offsets go to locals), only the reverse extension's text offset is returned.
+SG_HDN void sg_paired_score_location_hamming(SgPairedAligner &P, uint32_t whichRead, int direction, int64_t genomeLocation, uint32_t seedOffset, int scoreLimit,
+                                             int *score, double *matchProbability, int *genomeLocationOffset, int *basesClippedBefore, int *basesClippedAfter,
+                                             int *agScore, uint8_t *usedGaplessClipping, int *scoreGapless)
+{
+    const SgIndexView &ix = *P.ix; const SgParams &pr = *P.pr; const SgTables &T = *P.tb;
+    if (pr.noUkkonen) scoreLimit = P.maxK + (int)pr.extraSearchDepth;
+    const int readLen = (int)P.readLen[whichRead];
+    const int64_t genomeDataLength = (int64_t)readLen + SG_MAX_K;
+    const uint8_t *data = sg_get_substring(ix, genomeLocation, genomeDataLength);
+    *genomeLocationOffset = 0;
+    *usedGaplessClipping = 0;
+    if (data == (const uint8_t *)0) { *score = SG_SCORE_ABOVE_LIMIT; *matchProbability = 0; *genomeLocationOffset = 0; *agScore = SG_SCORE_ABOVE_LIMIT; return; }
+    *basesClippedBefore = 0; *basesClippedAfter = 0;
+    double matchProb1 = 1.0, matchProb2 = 1.0;
+    int score1 = 0, score2 = 0;
+    const int seedLen = (int)ix.seedLen;
+    const int tailStart = (int)seedOffset + seedLen;
+    int agScore1 = seedLen, agScore2 = 0;
+    const int textLen = (int)(genomeDataLength - tailStart);
+    int score1Gapless = 0, score2Gapless = 0;
+    SgGaplessOut g;
+    if (tailStart != readLen) {
+        g.nEdits = score1; g.matchProbability = matchProb1; g.nEditsGapless = score1Gapless;
+        agScore1 = sg_gapless_compute(T, P.ag, 1, data + tailStart, textLen, P.readData[whichRead][direction] + tailStart, P.readQual[whichRead][direction] + tailStart,
+                                      readLen - tailStart, readLen, scoreLimit, &g);
+        score1 = g.nEdits; matchProb1 = g.matchProbability; score1Gapless = g.nEditsGapless;
+        agScore1 += (seedLen - readLen);
+    }
+    if (score1Gapless != SG_SCORE_ABOVE_LIMIT) {
+        int limitLeft = scoreLimit - score1Gapless;
+        if (seedOffset != 0) {
+            g.nEdits = score2; g.matchProbability = matchProb2; g.nEditsGapless = score2Gapless; g.textOffset = *genomeLocationOffset;
+            agScore2 = sg_gapless_compute(T, P.ag, -1, data + seedOffset, (int)seedOffset + SG_MAX_K, P.ps.revRead[whichRead][direction] + readLen - seedOffset,
+                                          P.readQual[whichRead][1 - direction] + readLen - seedOffset, (int)seedOffset, readLen, limitLeft, &g);
+            score2 = g.nEdits; matchProb2 = g.matchProbability; score2Gapless = g.nEditsGapless; *genomeLocationOffset = g.textOffset;
+            agScore2 -= readLen;
+            if (score2Gapless == SG_SCORE_ABOVE_LIMIT) { *score = SG_SCORE_ABOVE_LIMIT; *genomeLocationOffset = 0; *agScore = SG_SCORE_ABOVE_LIMIT; }
+        }
+    }
+    if (score1Gapless != SG_SCORE_ABOVE_LIMIT && score2Gapless != SG_SCORE_ABOVE_LIMIT) {
+        *score = score1 + score2;
+        *matchProbability = matchProb1 * matchProb2 * T.snpPowSeedLen;
+        *agScore = agScore1 + agScore2;
+        *scoreGapless = score1Gapless + score2Gapless;
+        *usedGaplessClipping = 1;
+    } else {
+        *score = SG_SCORE_ABOVE_LIMIT; *agScore = SG_SCORE_ABOVE_LIMIT; *matchProbability = 0.0; *scoreGapless = SG_SCORE_ABOVE_LIMIT;
+    }
+}
+
 SG_HD void sg_paired_fill_candidate_result(snapgpu_paired_result *r, const SgPairedAligner &P, const SgScoringCandidate *c, const SgMateCandidate *m,
                                            int fewerEndScore, int fewerEndGenomeLocationOffset, const uint32_t *popularSeedsSkipped)
 {
@@ -505,9 +560,10 @@ SG_HD void sg_paired_fill_best_result(snapgpu_paired_result *r, const SgPairScor
     }
 }
 
-// IntersectingPairedEndAligner::alignLandauVishkin (:254-1435).  Returns false if the phase-4 candidate buffer overflowed.
+// IntersectingPairedEndAligner::alignLandauVishkin (:254-1435) and, with hamming = true, ::alignHamming (:1441-2487): the same
+// function but for the scorer, the missing phase 2a and a few conditions.  Returns false if the phase-4 candidate buffer overflowed.
 SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
-                               snapgpu_paired_result *result, int *nLVCandidatesForAffineGap)
+                               snapgpu_paired_result *result, int *nLVCandidatesForAffineGap, bool hamming = false)
 {
     const SgIndexView &ix = *P.ix; const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp; const SgTables &T = *P.tb;
     SgPairedScratch &ps = P.ps;
@@ -522,8 +578,10 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
     result->basesClippedAfter[0] = result->basesClippedAfter[1] = 0;
     result->agScore[0] = result->agScore[1] = 0;
     result->usedGaplessClipping[0] = result->usedGaplessClipping[1] = 0;
-    result->refSpan[0] = result->refSpan[1] = 0;
-    result->liftover[0] = result->liftover[1] = 0;
+    if (!hamming) {
+        result->refSpan[0] = result->refSpan[1] = 0;
+        result->liftover[0] = result->liftover[1] = 0;
+    }
     *nLVCandidatesForAffineGap = 0;
 
     int maxSeeds;
@@ -709,7 +767,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
 
     // ---- Phase 2a: big-indel hints (:723-801) ----
     const int64_t maxKForIndels = (int64_t)pp.maxKForIndels;
-    for (int whichSetPair = 0; whichSetPair < 2; whichSetPair++) {
+    for (int whichSetPair = 0; whichSetPair < 2 && !hamming; whichSetPair++) {
         SgMateCandidate *mates = ps.mates[whichSetPair];
         int bottom = 0, top = 1;
         while (top < (int)P.lowestFreeScoringMateCandidate[whichSetPair]) {
@@ -725,7 +783,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
             }
         }
     }
-    {
+    if (!hamming) {
         int bottom = 0, top = 1;
         while (top < (int)P.lowestFreeScoringCandidatePoolEntry) {
             if (ps.candPool[bottom].whichSetPair != ps.candPool[top].whichSetPair) { bottom = top; top = top + 1; continue; }
@@ -756,13 +814,21 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
         SgScoringCandidate *candidate = &ps.candPool[ci];
         int fewerEndScore; double fewerEndMatchProbability; int fewerEndGenomeLocationOffset;
         bool nonALTAlignment = (!pr.altAwareness) || !P.isALT(candidate->readWithFewerHitsGenomeLocation);
-        int scoreLimit = P.computeScoreLimit(nonALTAlignment, &all, &nonAlt, candidate->largestBigIndelDetected);
+        int scoreLimit = P.computeScoreLimit(nonALTAlignment, &all, &nonAlt, hamming ? 0 : candidate->largestBigIndelDetected);
         if (currentBestPossibleScoreList > scoreLimit) { ps.scoreLists[currentBestPossibleScoreList] = candidate->scoreListNext; continue; }
 
-        sg_paired_score_location(P, FEWER, SgPairedAligner::setPairDirection(candidate->whichSetPair, FEWER), candidate->readWithFewerHitsGenomeLocation,
-                                 candidate->seedOffset, scoreLimit, &fewerEndScore, &fewerEndMatchProbability, &fewerEndGenomeLocationOffset,
-                                 &candidate->usedAffineGapScoring, &candidate->basesClippedBefore, &candidate->basesClippedAfter, &candidate->agScore,
-                                 &candidate->lvIndels, &candidate->usedGaplessClipping, &candidate->refSpan);
+        if (!hamming) {
+            sg_paired_score_location(P, FEWER, SgPairedAligner::setPairDirection(candidate->whichSetPair, FEWER), candidate->readWithFewerHitsGenomeLocation,
+                                     candidate->seedOffset, scoreLimit, &fewerEndScore, &fewerEndMatchProbability, &fewerEndGenomeLocationOffset,
+                                     &candidate->usedAffineGapScoring, &candidate->basesClippedBefore, &candidate->basesClippedAfter, &candidate->agScore,
+                                     &candidate->lvIndels, &candidate->usedGaplessClipping, &candidate->refSpan);
+        } else {
+            int fewerEndScoreGapless;
+            sg_paired_score_location_hamming(P, FEWER, SgPairedAligner::setPairDirection(candidate->whichSetPair, FEWER), candidate->readWithFewerHitsGenomeLocation,
+                                             candidate->seedOffset, scoreLimit, &fewerEndScore, &fewerEndMatchProbability, &fewerEndGenomeLocationOffset,
+                                             &candidate->basesClippedBefore, &candidate->basesClippedAfter, &candidate->agScore, &candidate->usedGaplessClipping,
+                                             &fewerEndScoreGapless);
+        }
         candidate->matchProbability = fewerEndMatchProbability;
 
         if (fewerEndScore != SG_SCORE_ABOVE_LIMIT) {
@@ -770,20 +836,33 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
             SgMateCandidate *mates = ps.mates[candidate->whichSetPair];
             for (;;) {
                 SgMateCandidate *mate = &mates[mateIndex];
-                int64_t lim = candidate->largestBigIndelDetected < fewerEndScore ? candidate->largestBigIndelDetected : fewerEndScore;
-                if (mate->largestBigIndelDetected > lim) lim = mate->largestBigIndelDetected;
-                scoreLimit = P.computeScoreLimit(nonALTAlignment, &all, &nonAlt, lim);
+                if (!hamming) {
+                    int64_t lim = candidate->largestBigIndelDetected < fewerEndScore ? candidate->largestBigIndelDetected : fewerEndScore;
+                    if (mate->largestBigIndelDetected > lim) lim = mate->largestBigIndelDetected;
+                    scoreLimit = P.computeScoreLimit(nonALTAlignment, &all, &nonAlt, lim);
+                }
+                const bool candGapless = hamming && candidate->usedGaplessClipping;
                 if (!SgHitSet::within(mate->readWithMoreHitsGenomeLocation, candidate->readWithFewerHitsGenomeLocation, (int64_t)pp.minSpacing - 1) &&
-                    (mate->bestPossibleScore <= scoreLimit - fewerEndScore)) {
-                    int mateScoreLimit = scoreLimit - fewerEndScore;
-                    if (mate->score == SG_LOCATION_NOT_YET_SCORED || (mate->score == SG_SCORE_ABOVE_LIMIT && mate->scoreLimit < scoreLimit - fewerEndScore)) {
-                        sg_paired_score_location(P, MORE, SgPairedAligner::setPairDirection(candidate->whichSetPair, MORE), mate->readWithMoreHitsGenomeLocation,
-                                                 mate->seedOffset, mateScoreLimit, &mate->score, &mate->matchProbability, &mate->genomeOffset,
-                                                 &mate->usedAffineGapScoring, &mate->basesClippedBefore, &mate->basesClippedAfter, &mate->agScore, &mate->lvIndels,
-                                                 &mate->usedGaplessClipping, &mate->refSpan);
-                        mate->scoreLimit = scoreLimit - fewerEndScore;
+                    ((mate->bestPossibleScore <= scoreLimit - fewerEndScore) || candGapless)) {
+                    // (Hamming) a gapless-clipped fewer end does not lower the mate's limit: its reported score includes the clip (:1968-1990)
+                    int mateScoreLimit = candGapless ? scoreLimit : scoreLimit - fewerEndScore;
+                    if (mate->score == SG_LOCATION_NOT_YET_SCORED || (mate->score == SG_SCORE_ABOVE_LIMIT && mate->scoreLimit < scoreLimit - fewerEndScore) || candGapless) {
+                        if (!hamming) {
+                            sg_paired_score_location(P, MORE, SgPairedAligner::setPairDirection(candidate->whichSetPair, MORE), mate->readWithMoreHitsGenomeLocation,
+                                                     mate->seedOffset, mateScoreLimit, &mate->score, &mate->matchProbability, &mate->genomeOffset,
+                                                     &mate->usedAffineGapScoring, &mate->basesClippedBefore, &mate->basesClippedAfter, &mate->agScore, &mate->lvIndels,
+                                                     &mate->usedGaplessClipping, &mate->refSpan);
+                        } else {
+                            int mateScoreGapless;
+                            sg_paired_score_location_hamming(P, MORE, SgPairedAligner::setPairDirection(candidate->whichSetPair, MORE), mate->readWithMoreHitsGenomeLocation,
+                                                             mate->seedOffset, mateScoreLimit, &mate->score, &mate->matchProbability, &mate->genomeOffset,
+                                                             &mate->basesClippedBefore, &mate->basesClippedAfter, &mate->agScore, &mate->usedGaplessClipping,
+                                                             &mateScoreGapless);
+                        }
+                        mate->scoreLimit = mateScoreLimit;
                     }
-                    if (mate->score != SG_SCORE_ABOVE_LIMIT && (fewerEndScore + mate->score <= scoreLimit)) {
+                    if (mate->score != SG_SCORE_ABOVE_LIMIT &&
+                        ((fewerEndScore + mate->score <= scoreLimit) || candGapless || (hamming && mate->usedGaplessClipping))) {
                         double pairProbability = mate->matchProbability * fewerEndMatchProbability;
                         int pairScore = mate->score + fewerEndScore;
                         int pairAGScore = mate->agScore + candidate->agScore;
@@ -834,7 +913,8 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
                         if (!eliminatedByMerge) {
                             all.updateProbabilityOfAllPairs(oldPairProbability);
                             if (nonALTAlignment) nonAlt.updateProbabilityOfAllPairs(oldPairProbability);
-                            if (!mergeReplacement && (pairProbability > all.probabilityOfBestPair) && (maxLVCand > 0) && (esd >= all.bestPairScore - pairScore)) {
+                            if (!mergeReplacement && (pairProbability > all.probabilityOfBestPair) && (maxLVCand > 0) &&
+                                (!hamming || pairScore <= all.bestPairScore) && (esd >= all.bestPairScore - pairScore)) {
                                 if (*nLVCandidatesForAffineGap >= maxLVCand) { *nLVCandidatesForAffineGap = maxLVCand + 1; return false; }
                                 sg_paired_fill_best_result(&ps.lvCandidates[*nLVCandidatesForAffineGap], all, popularSeedsSkipped);
                                 (*nLVCandidatesForAffineGap)++;
@@ -843,7 +923,8 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
                                 nonAlt.updateBestHitIfNeeded(pairScore, pairAGScore, pairProbability, fewerEndScore, (int)MORE, fewerEndGenomeLocationOffset, candidate, mate);
                             }
                             bool updatedBestScore = all.updateBestHitIfNeeded(pairScore, pairAGScore, pairProbability, fewerEndScore, (int)MORE, fewerEndGenomeLocationOffset, candidate, mate);
-                            if ((!updatedBestScore) && maxLVCand > 0 && (pairScore <= (maxK + esd)) && (esd >= pairScore - all.bestPairScore)) {
+                            if ((!updatedBestScore) && maxLVCand > 0 && (hamming ? (pairScore >= all.bestPairScore) : (pairScore <= (maxK + esd))) &&
+                                (esd >= pairScore - all.bestPairScore)) {
                                 if (*nLVCandidatesForAffineGap >= maxLVCand) { *nLVCandidatesForAffineGap = maxLVCand + 1; return false; }
                                 sg_paired_fill_candidate_result(&ps.lvCandidates[*nLVCandidatesForAffineGap], P, candidate, mate, fewerEndScore, fewerEndGenomeLocationOffset, popularSeedsSkipped);
                                 (*nLVCandidatesForAffineGap)++;
@@ -1029,7 +1110,11 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
         bool fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, &nLVCand);
         if (!fit || P.error) { P.error = P.error ? P.error : 2; return; }      // buffer growth + retry (PairedAligner.cpp:727-780) is not implemented
         if (pr.useAffineGap) {
-            // (alignHamming would run here when useSoftClip and an end is NotFound: not restated, see the file header)
+            if (pp.useSoftClip && (result->status[0] == SNAPGPU_NOT_FOUND || result->status[1] == SNAPGPU_NOT_FOUND)) {
+                // IntersectingPairedEndAligner.cpp:220-233: try again with Hamming scoring that clips a poorly matching start / end
+                fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, &nLVCand, true);
+                if (!fit || P.error) { P.error = P.error ? P.error : 2; return; }
+            }
             sg_paired_align_ag(P, result, &nLVCand);
         }
         result->alignedAsPair = 1;
@@ -1055,6 +1140,7 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
     memset(singleResult, 0, sizeof(singleResult));
     int singleEndAGScore = 0;
     bool chooseSingleEndMapq = true;
+    int nSingleCandsFirstRead = 0;
     for (int r = 0; r < 2; r++) {
         if (compareWithSingleEndAlignment) pairAGScore += result->agScore[r];
         S.maxK = (uint32_t)maxKSingleEnd;
@@ -1069,9 +1155,26 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
                 int m = result->score[r] < scoreLimitLeft ? result->score[r] : scoreLimitLeft;
                 S.maxK = (uint32_t)(maxKSingleEnd < m ? maxKSingleEnd : m);
             }
+            S.agCands = (snapgpu_single_result *)0;
             sg_align_read(S, readBases[r], readQuals[r], lens[r], &singleResult[r]);
+            bool usedHammingScoringBaseAligner = false;
+            if (pp.useSoftClip && pp.enableHammingScoringBaseAligner) {
+                if (singleResult[r].status == SNAPGPU_NOT_FOUND && result->status[r] == SNAPGPU_NOT_FOUND) {
+                    // ChimericPairedEndAligner.cpp:330-362: Hamming scoring in the base aligner for an end nothing else could place
+                    usedHammingScoringBaseAligner = true;
+                    S.agCands = P.ps.singleCandidates + nSingleCandsFirstRead;
+                    S.nAgCands = 0; S.maxAgCands = SG_MAX_AG_CANDIDATES - nSingleCandsFirstRead; S.agCandsOverflow = 0;
+                    sg_align_read(S, readBases[r], readQuals[r], lens[r], &singleResult[r], true);
+                    if (S.agCandsOverflow) { P.error = 2; S.agCands = (snapgpu_single_result *)0; return; }
+                    sg_align_affine_gap(S, &singleResult[r], S.nAgCands, S.agCands);
+                    if (r == 0) nSingleCandsFirstRead = S.nAgCands;
+                    S.agCands = (snapgpu_single_result *)0;
+                }
+            }
             if (compareWithSingleEndAlignment) {
-                if (singleResult[r].score != SG_SCORE_ABOVE_LIMIT && singleResult[r].score != (int)SG_UNUSED_SCORE) scoreLimitLeft -= singleResult[r].score;
+                if (usedHammingScoringBaseAligner) {
+                    // the mate's limit is not lowered when this end needed Hamming scoring (:369-379)
+                } else if (singleResult[r].score != SG_SCORE_ABOVE_LIMIT && singleResult[r].score != (int)SG_UNUSED_SCORE) scoreLimitLeft -= singleResult[r].score;
                 else scoreLimitLeft = SG_SCORE_ABOVE_LIMIT;
                 singleEndAGScore += singleResult[r].agScore;
                 if (result->agScore[r] >= singleResult[r].agScore) chooseSingleEndMapq = false;

@@ -32,6 +32,31 @@ def golden_dir():
     return os.path.join(HERE, "golden")
 
 
+def _clipped_pairs(synth, contigs, n, seed):
+    """Pairs where ~45% of the ends carry an adapter-like junk head / tail (20-110 bases) or a burst of substitutions:
+    the inputs the soft-clipping (Hamming / gapless) passes exist for."""
+    rng = np.random.default_rng(seed)
+    base = synth.make_pairs(contigs, n, 150, seed=seed, sub_rate=0.01)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = []
+    for i in range(2 * n):
+        b, q = base.read(i)
+        b = bytearray(b)
+        r = rng.random()
+        if r < 0.35:
+            k = int(rng.integers(20, 110))
+            junk = bytes(rng.choice(acgt, size=k))
+            if rng.random() < 0.5:
+                b[150 - k:] = junk
+            else:
+                b[:k] = junk
+        elif r < 0.45:
+            for _ in range(int(rng.integers(15, 40))):
+                b[int(rng.integers(0, 150))] = b"ACGT"[int(rng.integers(0, 4))]
+        out.append((bytes(b), q))
+    return synth.ReadBatch.from_lists(out)
+
+
 class SmallCfg:
     """A small repeat-bearing reference with a reference-built index directory (default + -large) and read sets."""
 
@@ -54,6 +79,7 @@ class SmallCfg:
         }
 
         self.pairs = {
+            "clipped150": _clipped_pairs(synth, self.contigs, 500, 45),
             "std150": synth.make_pairs(self.contigs, 600, 150, seed=41, chimeric_frac=0.03, n_run_frac=0.03, short_frac=0.03),
             "noisy150": synth.make_pairs(self.contigs, 600, 150, seed=42, sub_rate=0.04, ins_rate=0.004, del_rate=0.004,
                                          chimeric_frac=0.05, n_run_frac=0.05, short_frac=0.05),
@@ -115,17 +141,21 @@ def differing_pairs(want: np.ndarray, got: np.ndarray) -> list[int]:
     return [i for i in range(len(w)) if w[i].tobytes() != g[i].tobytes()]
 
 
-# `snap paired -hc` style option sets (soft clipping off: bonuses 5/5, minAGScoreImprovement 15, PairedAligner.cpp:380-392)
+# `snap paired` defaults (soft clipping on: the Hamming / gapless passes run) and `snap paired -hc` style option sets (soft clipping off: bonuses 5/5, minAGScoreImprovement 15, PairedAligner.cpp:380-392)
 _HC = dict(fivePrimeEndBonus=5, threePrimeEndBonus=5)
 _HCP = dict(useSoftClipping=0, minAGScoreImprovement=15)
 PAIRED_OPTION_SETS = {
+    "default_d14": (dict(maxDist=14), dict()),
+    "default_d27": (dict(maxDist=27), dict()),          # `snap paired` really defaults to -d 27
+    "default_coverage": (dict(maxDist=14, numSeedsFromCommandLine=0, seedCoverage=2.0), dict()),
+    "default_no_eh": (dict(maxDist=14), dict(enableHammingScoringBaseAligner=0)),
+    "default_noopt": (dict(maxDist=10, noUkkonen=1, noOrderedEvaluation=1, noTruncation=1), dict()),
+    "default_spacing_300_450": (dict(maxDist=14), dict(minSpacing=300, maxSpacing=450)),
     "hc_d14": (dict(maxDist=14, **_HC), dict(**_HCP)),
     "hc_d27": (dict(maxDist=27, **_HC), dict(**_HCP)),
     "hc_h20_H50": (dict(maxDist=14, maxHits=20, **_HC), dict(intersectingAlignerMaxHits=50, **_HCP)),
-    "hc_coverage": (dict(maxDist=14, numSeedsFromCommandLine=0, seedCoverage=2.0, **_HC), dict(**_HCP)),
     "hc_noag": (dict(maxDist=14, useAffineGap=0), dict(**_HCP)),
     "hc_forcespacing": (dict(maxDist=14, **_HC), dict(forceSpacing=1, **_HCP)),
     "hc_spacing_300_450": (dict(maxDist=14, **_HC), dict(minSpacing=300, maxSpacing=450, **_HCP)),
-    "hc_noopt": (dict(maxDist=10, noUkkonen=1, noOrderedEvaluation=1, noTruncation=1, **_HC), dict(**_HCP)),
     "hc_nobanded_esd4": (dict(maxDist=14, noBandedAffineGap=1, extraSearchDepth=4, **_HC), dict(maxDistForIndels=20, **_HCP)),
 }

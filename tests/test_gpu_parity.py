@@ -265,9 +265,9 @@ def test_pairs_match_reference(engine, gidx, small_cfg, reflib, opt):
 
 
 def test_pairs_large_index_and_split_batches(engine, small_cfg, reflib):
-    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
     ix = engine.Index.open(small_cfg.idx_large)
-    pb = small_cfg.pairs["noisy150"]
+    pb = small_cfg.pairs["clipped150"]
     want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx_large), reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)).align(pb)
     big = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 4096)
     got, c1 = big.align(pb)
@@ -299,7 +299,7 @@ def test_paired_edge_cases(engine, gidx, small_cfg, reflib):
         (c[1000:1150].tobytes(), rc(c[1000:1150]).tobytes()),              # identical span
     ]
     rb = synth.ReadBatch.from_lists([(x, q(len(x))) for pr in pairs for x in pr])
-    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
     want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)).align(rb)
     al = engine.PairedAligner(gidx, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 64)
     got, _ = al.align(rb)
@@ -308,8 +308,6 @@ def test_paired_edge_cases(engine, gidx, small_cfg, reflib):
     assert len(res) == 0 and ctr["totalReads"] == 0
     with pytest.raises(engine.SnapGpuError):
         al.align(synth.ReadBatch.from_lists([(b"A" * 401, b"5" * 401), (b"A" * 100, b"5" * 100)]))
-    with pytest.raises(engine.SnapGpuError):      # soft clipping (Hamming pass) is not implemented: must be refused, not approximated
-        engine.PairedAligner(gidx, engine.default_params(numSeedsFromCommandLine=8, maxDist=14), engine.default_paired_params(), 64)
     al.close()
 
 
@@ -319,7 +317,7 @@ def test_paired_properties_at_scale(engine, small_cfg):
     from snap_b200 import synth
     bases, starts = small_cfg.padded_bases()
     ix = engine.Index.build(bases, starts)
-    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
     n = 20000
     pb = synth.make_pairs(small_cfg.contigs, n, 150, seed=91)
     al = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 1 << 15)

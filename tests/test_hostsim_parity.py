@@ -177,19 +177,15 @@ def test_pairs_match_reference(reflib, small_cfg, opt):
         ral.close()
         got, _, _ = hs.HsPairedAligner(hidx, p, pp).align(pb, reflib.PAIRED_RESULT_DTYPE)
         assert differing_pairs(want, got) == [], (opt, name)
-        assert int(want["alignedAsPair"].sum()) > 0 or opt == "hc_spacing_300_450"
+        assert int(want["alignedAsPair"].sum()) > 0
+        if name == "clipped150" and opt.startswith("default") and opt != "default_d27":
+            assert int(want["usedGaplessClipping"].sum()) > 0 and int((want["basesClippedBefore"] + want["basesClippedAfter"] > 0).sum()) > 0
 
 
 def test_pairs_large_index(reflib, small_cfg):
-    kw, pkw = PAIRED_OPTION_SETS["hc_d14"]
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
     p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
-    pb = small_cfg.pairs["noisy150"]
+    pb = small_cfg.pairs["clipped150"]
     want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx_large), p, pp).align(pb)
     got, _, _ = hs.HsPairedAligner(hs.HsIndex(small_cfg.idx_large), p, pp).align(pb, reflib.PAIRED_RESULT_DTYPE)
     assert differing_pairs(want, got) == []
-
-
-def test_paired_soft_clipping_is_refused(reflib, small_cfg):
-    """The Hamming / gapless pass is not restated: asking for it must fail loudly, not silently align differently."""
-    with pytest.raises(RuntimeError):
-        hs.HsPairedAligner(hs.HsIndex(small_cfg.idx), reflib.default_params_paired(maxDist=14), reflib.default_paired_params())
