@@ -35,10 +35,10 @@ SEED_LEN = 20
 MAX_DIST = 14
 ALG_BYTES_PER_CANDIDATE = READ_LEN - SEED_LEN + 2 * (MAX_DIST + 1)     # (readLen - seedLen + 2*k_used) reference bytes
 ALG_BYTES_PER_READ_IO = 2 * READ_LEN + 88                              # bases + qualities in, result record out
-# `snap paired -hc` (soft clipping off: PairedAligner.cpp:380-392 sets the end bonuses to 5 and minAGScoreImprovement to 15);
-# -d 14 as in the single-end config, everything else at `snap paired` defaults (-n 8, -H 4000, -s 0 1000)
-PAIRED_KW = dict(maxDist=MAX_DIST, numSeedsFromCommandLine=8, fivePrimeEndBonus=5, threePrimeEndBonus=5)
-PAIRED_PKW = dict(useSoftClipping=0, minAGScoreImprovement=15)
+# stock `snap paired` (BASELINE configs[2] names no options): -d 27, -n 8, -H 4000, -s 0 1000, soft clipping on
+PAIRED_MAX_DIST = 27
+PAIRED_KW = dict(maxDist=PAIRED_MAX_DIST, numSeedsFromCommandLine=8)
+PAIRED_PKW = dict()
 
 
 def parse_args():
@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seed-phase", action="store_true")
     ap.add_argument("--workload", default=os.environ.get("SNAPGPU_BENCH_WORKLOAD", "single"), choices=["single", "paired"],
-                    help="single = BASELINE configs[1] (the default, headline); paired = configs[2] shape: `snap paired -hc`, "
+                    help="single = BASELINE configs[1] (the default, headline); paired = configs[2] shape: stock `snap paired`, "
                          "--batch-reads/2 FR pairs per step, insert N(400,40)")
     return ap.parse_args()
 
@@ -255,12 +255,13 @@ def run_ours(args):
         "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_max / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
-        "config": {"workload": ("snap paired -hc (soft clipping off), 2 x %d x %d bp synthetic FR pairs (insert N(400,40)) per step per GPU vs %d Mbp "
+        "config": {"workload": ("snap paired (stock options), 2 x %d x %d bp synthetic FR pairs (insert N(400,40)) per step per GPU vs %d Mbp "
                                 "synthetic reference (24 contigs), seed %d, maxDist %d, IntersectingPairedEndAligner + chimeric single-end fallback "
-                                "(BASELINE configs[2] shape)" % (B // 2, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)) if paired else
+                                "(BASELINE configs[2] shape)" % (B // 2, READ_LEN, args.genome_mbp, SEED_LEN, PAIRED_MAX_DIST)) if paired else
                                ("snap single, %d x %d bp synthetic reads per step per GPU vs %d Mbp synthetic reference (24 contigs), "
                                 "seed %d, maxDist %d, affine gap on (BASELINE configs[1] shape)" % (B, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)),
-                   "reads_per_step": B * world, "read_len": READ_LEN, "genome_mbp": args.genome_mbp, "seed_len": SEED_LEN, "max_dist": MAX_DIST,
+                   "reads_per_step": B * world, "read_len": READ_LEN, "genome_mbp": args.genome_mbp, "seed_len": SEED_LEN,
+                   "max_dist": PAIRED_MAX_DIST if paired else MAX_DIST,
                    "parallelism": "read-sharded x%d, index replicated per GPU" % world,
                    "l2": "each step uses fresh reads (%.0f MB/step > L2) against a %.1f GB index" % (B * 2 * READ_LEN / 1e6, setup["index_hbm_gb"])},
         "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(B * (2 * READ_LEN + 12)),
@@ -448,8 +449,8 @@ def run_reference(args):
         out = {"impl": "reference", "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": args.gpus, "steps": K,
                "warmup": W, "ms_per_step": round(total_s / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
-               "config": {"workload": ("snap paired -hc, 2 x %d x %d bp synthetic FR pairs per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
-                                       % (n // 2, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)) if paired else
+               "config": {"workload": ("snap paired (stock options), 2 x %d x %d bp synthetic FR pairs per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
+                                       % (n // 2, READ_LEN, args.genome_mbp, SEED_LEN, PAIRED_MAX_DIST)) if paired else
                                       ("snap single, %d x %d bp synthetic reads per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
                                        % (n, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)), "read_len": READ_LEN, "genome_mbp": args.genome_mbp,
                           "seed_len": SEED_LEN, "max_dist": MAX_DIST},

@@ -279,6 +279,7 @@ static inline bool sg_derive_paired_params(const snapgpu_params &in, const snapg
     if (pool > pin.maxCandidatePoolSize) pool = pin.maxCandidatePoolSize;
     if (pool < 2 || pool > (1u << 22)) { err = "paired candidate pool size out of range"; return false; }
     pp.poolSize = (uint32_t)pool;
+    pp.poolCap = pp.poolSize; pp.agCandCap = SG_MAX_AG_CANDIDATES;
     return true;
 }
 #endif

@@ -23,6 +23,9 @@ struct SgPairedParams {
              useSoftClip, flattenMAPQAtOrBelow;
     uint32_t numSeedsFromCommandLine;   // min(MAX_MAX_SEEDS, -n)
     uint32_t maxSeedsToUse;             // ctor-time value sizing the hit sets
+    // capacities of THIS worker's arena (<= the reference's poolSize / 4096): a pair that needs more is retried by a worker
+    // with full-size pools (error code 4) -- results do not depend on the caps
+    uint32_t poolCap, agCandCap;
 };
 
 struct SgHitLookup {                 // HashTableLookup<unsigned>, IntersectingPairedEndAligner.h
@@ -278,8 +281,8 @@ struct SgPairedScratch {
     SgMateCandidate *mates[2];       // [poolSize/2] each
     SgMergeAnchor *anchors;          // [poolSize]
     int32_t *scoreLists;             // [MAX_K + extraSearchDepth + 2] heads (pool index or -1)
-    snapgpu_paired_result *lvCandidates;   // [SG_MAX_AG_CANDIDATES]
-    snapgpu_single_result *singleCandidates;   // [SG_MAX_AG_CANDIDATES] candidatesForAffineGap of the single-end Hamming pass
+    snapgpu_paired_result *lvCandidates;   // [agCandCap]
+    snapgpu_single_result *singleCandidates;   // [agCandCap] candidatesForAffineGap of the single-end Hamming pass
     uint8_t *agBt[2];                // the Chimeric aligner's own AffineGapVectorized objects used by the intersecting aligner
 };
 
@@ -289,12 +292,12 @@ SG_HD size_t sg_paired_scratch_bytes(const SgParams &p, const SgPairedParams &pp
     size_t rl = sg_align_up((size_t)p.maxReadLen + 16, 256);
     size_t b = rl * 8 + sg_align_up(((size_t)p.maxReadLen + 7) / 8 + 128, 256);
     b += 4 * (sg_align_up(sizeof(SgHitLookup) * pp.maxSeedsToUse, 256) + 2 * sg_align_up(4 * (size_t)pp.maxSeedsToUse, 256));
-    b += sg_align_up(sizeof(SgScoringCandidate) * (size_t)pp.poolSize, 256);
-    b += 2 * sg_align_up(sizeof(SgMateCandidate) * (size_t)(pp.poolSize / 2), 256);
-    b += sg_align_up(sizeof(SgMergeAnchor) * (size_t)pp.poolSize, 256);
+    b += sg_align_up(sizeof(SgScoringCandidate) * (size_t)pp.poolCap, 256);
+    b += 2 * sg_align_up(sizeof(SgMateCandidate) * (size_t)(pp.poolCap / 2), 256);
+    b += sg_align_up(sizeof(SgMergeAnchor) * (size_t)pp.poolCap, 256);
     b += sg_align_up(4 * (SG_MAX_K + 64), 256);
-    b += sg_align_up(sizeof(snapgpu_paired_result) * SG_MAX_AG_CANDIDATES, 256);
-    b += sg_align_up(sizeof(snapgpu_single_result) * SG_MAX_AG_CANDIDATES, 256);
+    b += sg_align_up(sizeof(snapgpu_paired_result) * (size_t)pp.agCandCap, 256);
+    b += sg_align_up(sizeof(snapgpu_single_result) * (size_t)pp.agCandCap, 256);
     b += 2 * sg_align_up(agRows * agCols, 256);
     return b;
 }
@@ -313,12 +316,12 @@ SG_HD void sg_paired_scratch_carve(const SgParams &p, const SgPairedParams &pp, 
         h.missCount = (uint32_t *)q; q += sg_align_up(4 * (size_t)pp.maxSeedsToUse, 256);
         h.nLookupsUsed = 0; h.currentDisjointHitSet = -1; h.mostRecentLocationReturned = 0;
     }
-    s->candPool = (SgScoringCandidate *)q; q += sg_align_up(sizeof(SgScoringCandidate) * (size_t)pp.poolSize, 256);
-    for (int k = 0; k < 2; k++) { s->mates[k] = (SgMateCandidate *)q; q += sg_align_up(sizeof(SgMateCandidate) * (size_t)(pp.poolSize / 2), 256); }
-    s->anchors = (SgMergeAnchor *)q; q += sg_align_up(sizeof(SgMergeAnchor) * (size_t)pp.poolSize, 256);
+    s->candPool = (SgScoringCandidate *)q; q += sg_align_up(sizeof(SgScoringCandidate) * (size_t)pp.poolCap, 256);
+    for (int k = 0; k < 2; k++) { s->mates[k] = (SgMateCandidate *)q; q += sg_align_up(sizeof(SgMateCandidate) * (size_t)(pp.poolCap / 2), 256); }
+    s->anchors = (SgMergeAnchor *)q; q += sg_align_up(sizeof(SgMergeAnchor) * (size_t)pp.poolCap, 256);
     s->scoreLists = (int32_t *)q; q += sg_align_up(4 * (SG_MAX_K + 64), 256);
-    s->lvCandidates = (snapgpu_paired_result *)q; q += sg_align_up(sizeof(snapgpu_paired_result) * SG_MAX_AG_CANDIDATES, 256);
-    s->singleCandidates = (snapgpu_single_result *)q; q += sg_align_up(sizeof(snapgpu_single_result) * SG_MAX_AG_CANDIDATES, 256);
+    s->lvCandidates = (snapgpu_paired_result *)q; q += sg_align_up(sizeof(snapgpu_paired_result) * (size_t)pp.agCandCap, 256);
+    s->singleCandidates = (snapgpu_single_result *)q; q += sg_align_up(sizeof(snapgpu_single_result) * (size_t)pp.agCandCap, 256);
     s->agBt[0] = q; q += sg_align_up(agRows * agCols, 256);
     s->agBt[1] = q; q += sg_align_up(agRows * agCols, 256);
 }
@@ -570,7 +573,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
     const uint32_t seedLen = ix.seedLen;
     const int maxK = P.maxK;
     const int esd = (int)pr.extraSearchDepth;
-    const int maxLVCand = pr.useAffineGap ? SG_MAX_AG_CANDIDATES : 0;
+    const int maxLVCand = pr.useAffineGap ? (int)pp.agCandCap : 0;
 
     result->clippingForReadAdjustment[0] = result->clippingForReadAdjustment[1] = 0;
     result->usedAffineGapScoring[0] = result->usedAffineGapScoring[1] = 0;
@@ -722,7 +725,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
             }
             while (lastGenomeLocationForReadWithMoreHits + maxSpacing >= lastGenomeLocationForReadWithFewerHits && !outOfMoreHitsLocations) {
                 uint32_t bestPossibleScoreForReadWithMoreHits = pr.noTruncation ? 0u : setPair[MORE]->computeBestPossibleScoreForCurrentHit();
-                if (P.lowestFreeScoringMateCandidate[whichSetPair] >= pp.poolSize / 2) { P.error = 1; return true; }
+                if (P.lowestFreeScoringMateCandidate[whichSetPair] >= pp.poolCap / 2) { P.error = pp.poolCap < pp.poolSize ? 4 : 1; return true; }
                 SgMateCandidate &m = mates[P.lowestFreeScoringMateCandidate[whichSetPair]];
                 m.readWithMoreHitsGenomeLocation = lastGenomeLocationForReadWithMoreHits;
                 m.bestPossibleScore = (int)bestPossibleScoreForReadWithMoreHits;
@@ -745,7 +748,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
                 if (mates[i].bestPossibleScore < lowestBestPossibleScoreOfAnyPossibleMate) lowestBestPossibleScoreOfAnyPossibleMate = mates[i].bestPossibleScore;
             }
             if (lowestBestPossibleScoreOfAnyPossibleMate + bestPossibleScoreForReadWithFewerHits <= maxK + esd) {
-                if (P.lowestFreeScoringCandidatePoolEntry >= pp.poolSize) { P.error = 1; return true; }
+                if (P.lowestFreeScoringCandidatePoolEntry >= pp.poolCap) { P.error = pp.poolCap < pp.poolSize ? 4 : 1; return true; }
                 int bestPossibleScore = pr.noOrderedEvaluation ? 0 : lowestBestPossibleScoreOfAnyPossibleMate + bestPossibleScoreForReadWithFewerHits;
                 SgScoringCandidate &c = ps.candPool[P.lowestFreeScoringCandidatePoolEntry];
                 c.readWithFewerHitsGenomeLocation = lastGenomeLocationForReadWithFewerHits;
@@ -885,7 +888,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
                         const int64_t newMore = mate->readWithMoreHitsGenomeLocation + mate->genomeOffset;
                         const int64_t newFewer = candidate->readWithFewerHitsGenomeLocation + fewerEndGenomeLocationOffset;
                         if (mergeAnchor == -1) {
-                            if (P.firstFreeMergeAnchor >= pp.poolSize) { P.error = 1; return true; }
+                            if (P.firstFreeMergeAnchor >= pp.poolCap) { P.error = pp.poolCap < pp.poolSize ? 4 : 1; return true; }
                             mergeAnchor = (int32_t)P.firstFreeMergeAnchor++;
                             SgMergeAnchor &an = ps.anchors[mergeAnchor];
                             an.locationForReadWithMoreHits = newMore; an.locationForReadWithFewerHits = newFewer;
@@ -1108,12 +1111,12 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
         P.maxK = maxKPairedEnd;
         int nLVCand = 0;
         bool fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, &nLVCand);
-        if (!fit || P.error) { P.error = P.error ? P.error : 2; return; }      // buffer growth + retry (PairedAligner.cpp:727-780) is not implemented
+        if (!fit || P.error) { P.error = P.error ? P.error : (pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2); return; }      // buffer growth + retry (PairedAligner.cpp:727-780) is not implemented
         if (pr.useAffineGap) {
             if (pp.useSoftClip && (result->status[0] == SNAPGPU_NOT_FOUND || result->status[1] == SNAPGPU_NOT_FOUND)) {
                 // IntersectingPairedEndAligner.cpp:220-233: try again with Hamming scoring that clips a poorly matching start / end
                 fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, &nLVCand, true);
-                if (!fit || P.error) { P.error = P.error ? P.error : 2; return; }
+                if (!fit || P.error) { P.error = P.error ? P.error : (pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2); return; }
             }
             sg_paired_align_ag(P, result, &nLVCand);
         }
@@ -1163,9 +1166,9 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
                     // ChimericPairedEndAligner.cpp:330-362: Hamming scoring in the base aligner for an end nothing else could place
                     usedHammingScoringBaseAligner = true;
                     S.agCands = P.ps.singleCandidates + nSingleCandsFirstRead;
-                    S.nAgCands = 0; S.maxAgCands = SG_MAX_AG_CANDIDATES - nSingleCandsFirstRead; S.agCandsOverflow = 0;
+                    S.nAgCands = 0; S.maxAgCands = (int)pp.agCandCap - nSingleCandsFirstRead; S.agCandsOverflow = 0;
                     sg_align_read(S, readBases[r], readQuals[r], lens[r], &singleResult[r], true);
-                    if (S.agCandsOverflow) { P.error = 2; S.agCands = (snapgpu_single_result *)0; return; }
+                    if (S.agCandsOverflow) { P.error = pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2; S.agCands = (snapgpu_single_result *)0; return; }
                     sg_align_affine_gap(S, &singleResult[r], S.nAgCands, S.agCands);
                     if (r == 0) nSingleCandsFirstRead = S.nAgCands;
                     S.agCands = (snapgpu_single_result *)0;

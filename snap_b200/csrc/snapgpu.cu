@@ -65,6 +65,14 @@ struct snapgpu_aligner {
     SgPairedParams pparams;
     size_t singleScratchBytes = 0;
     int *d_error = nullptr;              // latched kernel-side error code (0 = none)
+    // Pairs whose candidate pools outgrow the (small) per-worker caps are queued and re-aligned from scratch by a few
+    // workers that own full-size pools: second launch of the same kernel over the retry list.
+    SgPairedParams pparamsBig;
+    int nBigWorkers = 0;
+    size_t bigScratchBytesPerWorker = 0;
+    uint8_t *d_bigScratch = nullptr;
+    uint32_t *d_retryList = nullptr;     // [maxUnits]
+    unsigned long long *d_retryCount = nullptr, *d_next2 = nullptr;
     int device = 0;
     int numSMs = 0;
     int warpsPerBlock = 8, blocksPerSM = 4;
@@ -139,6 +147,7 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
     SgAligner A;
     A.ix = &ix; A.pr = &pr; A.tb = tb;
     A.lane = lane; A.maxK = pr.maxK;
+    A.agCands = nullptr; A.nAgCands = 0; A.maxAgCands = 0; A.agCandsOverflow = 0;
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
     A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
@@ -204,8 +213,11 @@ __global__ void __launch_bounds__(256, MB)
 sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedParams pp, const SgTables *tb, uint8_t *scratchBase,
                        size_t scratchBytesPerWorker, size_t singleScratchBytes, long long nPairs, const uint8_t *bases, const uint8_t *quals,
                        const unsigned long long *offsets, const uint32_t *lens, snapgpu_paired_result *results, snapgpu_counters *counters,
-                       unsigned long long *next, int *errorWord)
+                       unsigned long long *next, int *errorWord, const uint32_t *workList, unsigned long long *retryCount, uint32_t *retryList)
 {
+    // workList == NULL: first pass over pairs [0, nPairs), pairs that outgrow this arena's caps go to retryList.
+    // workList != NULL: retry pass over workList[0, *retryCount) with full-size pools.
+    if (workList) nPairs = (long long)*retryCount;
     const int lane = threadIdx.x & 31;
     const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t *arena = scratchBase + (size_t)worker * scratchBytesPerWorker;
@@ -213,6 +225,7 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
     SgAligner S;
     S.ix = &ix; S.pr = &prSingle; S.tb = tb;
     S.lane = lane; S.maxK = prSingle.maxK;
+    S.agCands = nullptr; S.nAgCands = 0; S.maxAgCands = 0; S.agCandsOverflow = 0;
     sg_scratch_carve(prSingle, arena, &S.sc);
     S.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
     S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
@@ -231,6 +244,8 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
         if (lane == 0) i = atomicAdd(next, 1ULL);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= (unsigned long long)nPairs) break;
+        const bool firstPass = workList == (const uint32_t *)0;
+        if (!firstPass) i = workList[i];
         const uint8_t *rb[2], *rq[2]; uint32_t ln[2]; bool useful[2]; bool tooLong = false;
         for (int w = 0; w < 2; w++) {
             rb[w] = bases + offsets[2 * i + w]; rq[w] = quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w];
@@ -242,7 +257,7 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
         }
         snapgpu_paired_result r;
         memset(&r, 0, sizeof(r));
-        cTotal += 2;
+        if (firstPass) cTotal += 2;
         if (tooLong) { if (lane == 0) atomicMax(errorWord, 3); useful[0] = useful[1] = false; }
         if (!useful[0] && !useful[1]) {
             r.status[0] = r.status[1] = SNAPGPU_NOT_FOUND; r.location[0] = r.location[1] = P.invalidLocation;
@@ -251,7 +266,14 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
             continue;
         }
         P.error = 0;
+        const SgWork workBefore = S.work; const uint32_t lvBefore = P.lvCalls, agBefore = P.agCalls;
         sg_paired_align(P, rb, rq, ln, &r);
+        if (P.error == 4 && firstPass) {
+            // this arena's pools are too small for the pair: hand it to the retry pass (and do not count the aborted work)
+            if (lane == 0) retryList[atomicAdd(retryCount, 1ULL)] = (uint32_t)i;
+            S.work = workBefore; P.lvCalls = lvBefore; P.agCalls = agBefore;
+            continue;
+        }
         if (P.error) {
             if (lane == 0) atomicMax(errorWord, P.error);
             memset(&r, 0, sizeof(r));
@@ -820,9 +842,34 @@ int snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params
         delete a; return sg_fail("snapgpu_paired_aligner_create: " + err);
     }
     a->singleScratchBytes = sg_align_up(sg_scratch_bytes(a->paramsSingle), 256);
+    // per-worker pool caps (results do not depend on them: pairs that need more are re-aligned by the full-size workers)
+    a->pparamsBig = a->pparams;
+    uint32_t poolCap = 4096, candCap = 512;
+    if (const char *e = getenv("SNAPGPU_PAIRED_POOL_CAP")) poolCap = (uint32_t)atoi(e);
+    if (const char *e = getenv("SNAPGPU_PAIRED_CAND_CAP")) candCap = (uint32_t)atoi(e);
+    if (poolCap < 16) poolCap = 16;
+    if (candCap < 4) candCap = 4;
+    a->pparams.poolCap = poolCap < a->pparams.poolSize ? (poolCap & ~1u) : a->pparams.poolSize;
+    a->pparams.agCandCap = candCap < SG_MAX_AG_CANDIDATES ? candCap : SG_MAX_AG_CANDIDATES;
     const size_t perWorker = a->singleScratchBytes + sg_align_up(sg_paired_scratch_bytes(a->params, a->pparams), 256);
-    if (aligner_init_common(a, 2 * maxBatchPairs, maxBatchPairs, perWorker, sizeof(snapgpu_paired_result), 2, 3, "SNAPGPU_PAIRED_BLOCKS_PER_SM")) {
+    if (aligner_init_common(a, 2 * maxBatchPairs, maxBatchPairs, perWorker, sizeof(snapgpu_paired_result), 2, 4, "SNAPGPU_PAIRED_BLOCKS_PER_SM")) {
         snapgpu_aligner_destroy(a); return 1;
+    }
+    a->bigScratchBytesPerWorker = a->singleScratchBytes + sg_align_up(sg_paired_scratch_bytes(a->params, a->pparamsBig), 256);
+    size_t budget = (size_t)4 << 30;
+    int nBig = (int)(budget / a->bigScratchBytesPerWorker);
+    if (nBig > 128) nBig = 128;
+    if (nBig < a->warpsPerBlock) nBig = a->warpsPerBlock;
+    nBig = nBig / a->warpsPerBlock * a->warpsPerBlock;
+    if ((int64_t)nBig > maxBatchPairs) nBig = (int)((maxBatchPairs + a->warpsPerBlock - 1) / a->warpsPerBlock) * a->warpsPerBlock;
+    a->nBigWorkers = nBig;
+    if (cudaMalloc((void **)&a->d_bigScratch, a->bigScratchBytesPerWorker * (size_t)nBig) != cudaSuccess ||
+        cudaMemset(a->d_bigScratch, 0, a->bigScratchBytesPerWorker * (size_t)nBig) != cudaSuccess ||
+        cudaMalloc((void **)&a->d_retryList, (size_t)maxBatchPairs * 4) != cudaSuccess ||
+        cudaMalloc((void **)&a->d_retryCount, 8) != cudaSuccess || cudaMalloc((void **)&a->d_next2, 8) != cudaSuccess) {
+        std::string msg = std::string("snapgpu_paired_aligner_create: retry arena: ") + cudaGetErrorString(cudaGetLastError());
+        snapgpu_aligner_destroy(a);
+        return sg_fail(msg);
     }
     *out = a;
     return 0;
@@ -837,6 +884,7 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
     if (a->streamIn) cudaStreamDestroy(a->streamIn);
     if (a->streamOut) cudaStreamDestroy(a->streamOut);
     cudaFree(a->d_scratch); cudaFree(a->d_next); cudaFree(a->d_error);
+    cudaFree(a->d_bigScratch); cudaFree(a->d_retryList); cudaFree(a->d_retryCount); cudaFree(a->d_next2);
     for (int k = 0; k < 2; k++) {
         snapgpu_aligner::Slot &sl = a->slot[k];
         cudaFreeHost(sl.h_bases); cudaFreeHost(sl.h_quals); cudaFreeHost(sl.h_offsets); cudaFreeHost(sl.h_lens); cudaFreeHost(sl.h_results);
@@ -865,11 +913,26 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
         if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
 #undef SG_LAUNCH
     } else {
-#define SG_LAUNCH(MB) sg_align_paired_kernel<MB><<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->paramsSingle, a->pparams, \
-        a->index->d_tables_prob, a->d_scratch, a->scratchBytesPerWorker, a->singleScratchBytes, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, \
-        (const unsigned long long *)d_offsets, d_lens, (snapgpu_paired_result *)d_results, d_counters, a->d_next, a->d_error)
-        if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
+        SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));
+        SG_CUDA(cudaMemsetAsync(a->d_next2, 0, 8, st));
+#define SG_LAUNCH(MB, GRID, PP, SCRATCH, BYTES, NEXT, LIST) sg_align_paired_kernel<MB><<<GRID, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, \
+        a->paramsSingle, PP, a->index->d_tables_prob, SCRATCH, BYTES, a->singleScratchBytes, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, \
+        (const unsigned long long *)d_offsets, d_lens, (snapgpu_paired_result *)d_results, d_counters, NEXT, a->d_error, LIST, a->d_retryCount, a->d_retryList)
+#define SG_LAUNCH_MB(GRID, PP, SCRATCH, BYTES, NEXT, LIST) \
+        if (a->blocksPerSM >= 4) SG_LAUNCH(4, GRID, PP, SCRATCH, BYTES, NEXT, LIST); else if (a->blocksPerSM == 3) SG_LAUNCH(3, GRID, PP, SCRATCH, BYTES, NEXT, LIST); \
+        else SG_LAUNCH(2, GRID, PP, SCRATCH, BYTES, NEXT, LIST)
+        SG_LAUNCH_MB(blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
+        SG_CUDA(cudaGetLastError());
+        a->launches++;
+        if (a->pparams.poolCap < a->pparamsBig.poolCap || a->pparams.agCandCap < a->pparamsBig.agCandCap) {
+            // retry pass: exits at once when the list is empty
+            SG_LAUNCH_MB(a->nBigWorkers / a->warpsPerBlock, a->pparamsBig, a->d_bigScratch, a->bigScratchBytesPerWorker, a->d_next2, (const uint32_t *)a->d_retryList);
+            SG_CUDA(cudaGetLastError());
+            a->launches++;
+        }
+#undef SG_LAUNCH_MB
 #undef SG_LAUNCH
+        return 0;
     }
     SG_CUDA(cudaGetLastError());
     a->launches++;

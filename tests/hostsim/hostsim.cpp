@@ -202,14 +202,23 @@ struct HsPaired {
     std::vector<uint8_t> scratch, pscratch;
     SgAligner S;
     SgPairedAligner P;
+    HsPaired *big = nullptr;         // full-size fallback when this one runs with reduced pool caps (mirrors the GPU retry pass)
+    int64_t retried = 0;
 };
 
-void *hs_paired_create(void *vix, const snapgpu_params *params, const snapgpu_paired_params *pparams, uint32_t maxReadLen)
+// poolCap / candCap: 0 = the reference's sizes; otherwise this aligner's pools are capped and a pair that needs more is
+// re-aligned from scratch by a second, full-size aligner -- exactly what the CUDA path's retry launch does.
+void *hs_paired_create(void *vix, const snapgpu_params *params, const snapgpu_paired_params *pparams, uint32_t maxReadLen, uint32_t poolCap, uint32_t candCap)
 {
     HsIndex *ix = (HsIndex *)vix;
     HsPaired *a = new HsPaired;
     a->index = ix;
     if (!sg_derive_paired_params(*params, *pparams, ix->host.seedLen, maxReadLen, a->pr, a->prSingle, a->pp, g_err)) { delete a; return NULL; }
+    if (poolCap || candCap) {
+        a->big = (HsPaired *)hs_paired_create(vix, params, pparams, maxReadLen, 0, 0);
+        if (poolCap && poolCap < a->pp.poolSize) a->pp.poolCap = poolCap & ~1u;
+        if (candCap && candCap < SG_MAX_AG_CANDIDATES) a->pp.agCandCap = candCap;
+    }
     sg_init_tables(a->tables, ix->host.seedLen);
     memset(&a->S, 0, sizeof(a->S));
     make_scratch(a->prSingle, a->scratch, &a->S.sc);
@@ -226,7 +235,8 @@ void *hs_paired_create(void *vix, const snapgpu_params *params, const snapgpu_pa
     return a;
 }
 
-void hs_paired_destroy(void *v) { delete (HsPaired *)v; }
+void hs_paired_destroy(void *v) { HsPaired *a = (HsPaired *)v; if (a->big) hs_paired_destroy(a->big); delete a; }
+int64_t hs_paired_retried(void *v) { return ((HsPaired *)v)->retried; }
 
 // Same contract as oracle ref_paired_align: pair i = reads 2i, 2i+1; the pre-filter of PairedAligner.cpp:669-707.
 int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
@@ -252,6 +262,14 @@ int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *qual
         }
         a->P.error = 0;
         sg_paired_align(a->P, rb, rq, ln, r);
+        if (a->P.error == 4 && a->big) {
+            a->retried++;
+            memset(r, 0, sizeof(*r));
+            a->big->P.error = 0;
+            sg_paired_align(a->big->P, rb, rq, ln, r);
+            if (a->big->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
+            continue;
+        }
         if (a->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
     }
     if (nLV) *nLV = a->P.lvCalls + a->S.work.lvCalls;

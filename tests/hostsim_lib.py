@@ -50,7 +50,9 @@ def lib():
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
         L.hs_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.hs_paired_create.restype = C.c_void_p
-        L.hs_paired_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.hs_paired_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.hs_paired_retried.restype = C.c_int64
+        L.hs_paired_retried.argtypes = [C.c_void_p]
         L.hs_paired_destroy.argtypes = [C.c_void_p]
         L.hs_align_paired.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         _lib = L
@@ -93,10 +95,10 @@ class HsAligner:
 
 
 class HsPairedAligner:
-    def __init__(self, index: HsIndex, params, paired_params, max_read_len: int = 400):
+    def __init__(self, index: HsIndex, params, paired_params, max_read_len: int = 400, pool_cap: int = 0, cand_cap: int = 0):
         import ctypes
         self.index = index
-        self.handle = lib().hs_paired_create(index.handle, ctypes.byref(params), ctypes.byref(paired_params), max_read_len)
+        self.handle = lib().hs_paired_create(index.handle, ctypes.byref(params), ctypes.byref(paired_params), max_read_len, pool_cap, cand_cap)
         if not self.handle:
             raise RuntimeError(lib().hs_last_error().decode())
 
@@ -109,6 +111,9 @@ class HsPairedAligner:
         if rc != 0:
             raise RuntimeError(lib().hs_last_error().decode())
         return res, int(nlv[0]), int(nag[0])
+
+    def retried(self) -> int:
+        return int(lib().hs_paired_retried(self.handle))
 
     def __del__(self):
         if getattr(self, "handle", None):

@@ -297,6 +297,9 @@ def test_paired_edge_cases(engine, gidx, small_cfg, reflib):
         (c[c.size - 400:c.size - 250].tobytes(), rc(c[c.size - 150:]).tobytes()),   # at the very end
         (c[1000:1150].tobytes(), rc(c[1020:1170]).tobytes()),              # overlapping mates
         (c[1000:1150].tobytes(), rc(c[1000:1150]).tobytes()),              # identical span
+        (c[1000:1090].tobytes() + rc(c[40000:40060]).tobytes(), rc(c[1300:1450]).tobytes()),   # junk tail on one end: soft clip
+        (rc(c[40000:40070]).tobytes() + c[1070:1150].tobytes(), rc(c[1300:1450]).tobytes()),   # junk head
+        (c[1000:1075].tobytes() + c[60000:60075].tobytes(), rc(c[1300:1375]).tobytes() + c[70000:70075].tobytes()),   # both ends half junk
     ]
     rb = synth.ReadBatch.from_lists([(x, q(len(x))) for pr in pairs for x in pr])
     kw, pkw = PAIRED_OPTION_SETS["default_d14"]
@@ -335,3 +338,19 @@ def test_paired_properties_at_scale(engine, small_cfg):
     assert (d <= 1000).all() and (r1["direction"][proper, 0] != r1["direction"][proper, 1]).all()
     assert c1["totalReads"] == 2 * n and sum(c1["mapqHistogram"]) == int((r1["status"] != 0).sum())
     al.close(); ix.close()
+
+
+def test_pairs_tiny_pool_caps_take_the_retry_pass(engine, gidx, small_cfg, reflib, monkeypatch):
+    """Per-warp candidate pools far too small for most pairs: everything that overflows is re-aligned by the full-size
+    retry launch, and the results must still be the reference's."""
+    monkeypatch.setenv("SNAPGPU_PAIRED_POOL_CAP", "16")
+    monkeypatch.setenv("SNAPGPU_PAIRED_CAND_CAP", "4")
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
+    al = engine.PairedAligner(gidx, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 2048)
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    for name in ("noisy150", "clipped150"):
+        pb = small_cfg.pairs[name]
+        want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), p, pp).align(pb)
+        got, _ = al.align(pb)
+        assert differing_pairs(want, got) == [], name
+    al.close()

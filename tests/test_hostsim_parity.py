@@ -189,3 +189,20 @@ def test_pairs_large_index(reflib, small_cfg):
     want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx_large), p, pp).align(pb)
     got, _, _ = hs.HsPairedAligner(hs.HsIndex(small_cfg.idx_large), p, pp).align(pb, reflib.PAIRED_RESULT_DTYPE)
     assert differing_pairs(want, got) == []
+
+@pytest.mark.parametrize("caps", [(16, 0), (0, 4), (64, 8)])
+def test_pairs_pool_caps_do_not_change_results(reflib, small_cfg, caps):
+    """The CUDA path gives each warp small candidate pools and re-aligns the pairs that outgrow them with full-size ones.
+    Same scheme on the host build: aborting a pair mid-way and redoing it elsewhere must not change any result."""
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    retried = 0
+    for name in ("noisy150", "clipped150"):
+        pb = small_cfg.pairs[name]
+        want, _ = reflib.RefPairedAligner(ridx, p, pp).align(pb)
+        al = hs.HsPairedAligner(hidx, p, pp, pool_cap=caps[0], cand_cap=caps[1])
+        got, _, _ = al.align(pb, reflib.PAIRED_RESULT_DTYPE)
+        assert differing_pairs(want, got) == [], (caps, name)
+        retried += al.retried()
+    assert retried > 0
