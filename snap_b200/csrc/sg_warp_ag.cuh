@@ -15,7 +15,9 @@
 #pragma once
 #include "sg_ag.h"
 
-#define SG_AG_REG_BLOCKS 5
+#ifndef SG_AG_REG_BLOCKS
+#define SG_AG_REG_BLOCKS 0        // > 1: keep up to that many blocks of a row in registers through the lazy-F passes (measured slower: spills + code size)
+#endif
 
 __device__ __forceinline__ int sg_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -197,6 +199,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                 continue;
             }
 
+#if SG_AG_REG_BLOCKS > 1
             if (nBlocks <= SG_AG_REG_BLOCKS) {
                 // ---- up to 4*SG_AG_REG_BLOCKS vectors (pattern <= 160 columns unbanded): each lane keeps its cell of every
                 //      block in registers through the main pass and all lazy-F passes; H and the traceback byte are written once.
@@ -288,6 +291,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                 __syncwarp();
                 continue;
             }
+#endif
 
             // ---------------- main pass, 4 vectors per step ----------------
             for (int b = 0; b < nBlocks; b++) {

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsnapgpu.so")
+LIB_PATH = os.environ.get("SNAPGPU_LIB") or os.path.join(HERE, "csrc", "libsnapgpu.so")      # SNAPGPU_LIB: A/B builds of the same library
 
 
 class SnapGpuError(RuntimeError):

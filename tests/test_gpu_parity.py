@@ -64,21 +64,31 @@ def test_leaf_golden_ag(engine, golden_dir):
     assert (g["out"]["textOffset"] == got["textOffset"]).all() and (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
 
+def _history_dependent(t, p, q, jb, params):
+    """Jobs whose REFERENCE answer depends on what earlier calls left in its never-cleared traceback array (the traceback
+    steps onto a cell this call's DP did not write).  Flagged by the host build of the scalar restatement (test-only)."""
+    import hostsim_lib as hs
+    _, poisoned = hs.ag_batch(t, p, q, jb, J.AG_OUT, params)
+    return poisoned != 0
+
+
 def test_warp_leaves_golden(engine, golden_dir):
-    """The warp-cooperative forms (what the alignment kernel runs).  LV is a pure function: any number of warps.
-    Affine gap with ONE warp runs the jobs in order on one arena = the call history of the sequential reference run that
-    produced the fixture, so even the inputs whose traceback reads stale cells must agree; with many warps only those may
-    differ."""
+    """The warp-cooperative forms (what the alignment kernels run).  LV is a pure function: any number of warps.
+    Affine gap: every job whose reference answer is a function of its inputs must match bit for bit, on one warp or many.
+    The history-dependent ones (see _history_dependent; < 1 %) still have to agree on score and offsets."""
     g = np.load(os.path.join(golden_dir, "leaf_lv.npz"))
     got = engine.test_lv(g["text"], g["pat"], g["qual"], g["jobs"], J.LV_OUT, warps=512)
     assert J.same_out(g["out"], got).all()
     g = np.load(os.path.join(golden_dir, "leaf_ag.npz"))
-    got1 = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, [1, 4, 6, 1, 10, 7], warps=1)
-    assert J.same_out(g["out"], got1).all()
-    gotn = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, [1, 4, 6, 1, 10, 7], warps=256)
-    same = J.same_out(g["out"], gotn)
-    assert (~same).sum() <= 0.01 * same.size
-    assert (g["out"]["agScore"] == gotn["agScore"]).all() and (g["out"]["textOffset"] == gotn["textOffset"]).all()
+    params = [1, 4, 6, 1, 10, 7]
+    hist = _history_dependent(g["text"], g["pat"], g["qual"], g["jobs"], params)
+    assert hist.sum() <= 0.01 * hist.size
+    for warps in (1, 256):
+        got = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, params, warps=warps)
+        same = J.same_out(g["out"], got)
+        assert same[~hist].all(), warps
+        assert (g["out"]["agScore"] == got["agScore"]).all() and (g["out"]["textOffset"] == got["textOffset"]).all()
+        assert (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
 
 def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib):
@@ -89,7 +99,10 @@ def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib):
         assert J.same_out(want, engine.test_lv(t, p, q, jb, J.LV_OUT)).all()
         t, p, q, jb = J.ag_jobs(2500, seed + 10)
         want = reflib.ag_batch(t, p, q, jb.astype(reflib.AG_JOB_DTYPE))
-        assert J.same_out(want, engine.test_ag(t, p, q, jb, J.AG_OUT, reflib.AG_PARAMS_DEFAULT, warps=1)).all()
+        hist = _history_dependent(t, p, q, jb, reflib.AG_PARAMS_DEFAULT)
+        got = engine.test_ag(t, p, q, jb, J.AG_OUT, reflib.AG_PARAMS_DEFAULT, warps=64)
+        assert J.same_out(want, got)[~hist].all()
+        assert (want["agScore"] == got["agScore"]).all() and (want["textOffset"] == got["textOffset"]).all()
 
 
 def test_lookup_matches_reference(engine, gidx, small_cfg, reflib):
