@@ -163,6 +163,8 @@ def run_ours(args):
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=device)
     W, K, B = args.warmup, args.steps, args.batch_reads
     bases, starts, contig_len, idx, batches, setup = build_workload(args, device, rank, world)

@@ -84,6 +84,22 @@ struct SgAgLayout {
     SG_HD int rowStride() const { return banded ? numVec * numSeg * SG_VEC : numVec * SG_VEC; }
 };
 
+// Row pruning of the unbanded DP (ours; the reference walks all textLen rows).  After row i: every cell of a row r >= patternLen
+// lies on a path that consumed r+1 text characters against at most patternLen pattern characters, so it holds at least
+// r+1-patternLen vertical-gap steps and H(r, .) <= max(0, scoreInit + matchReward*patternLen - open - (r - patternLen)*ext),
+// non-increasing in r.  Once that bound is below both running bests no later row can replace them (local needs >, global
+// needs >=).  The only other use of later rows is the traceback, which the clipping heuristics of sg_ag_finish may start
+// up to patternLen-1-bestLocalPatternOffset rows below the best local row: those rows are kept.
+SG_HD bool sg_ag_can_stop_after_row(const SgAgParams &P, int i, int patternLen, int scoreInit, int bestLocalScore, int bestLocalTextOffset,
+                                    int bestLocalPatternOffset, int bestGlobalScore)
+{
+    if (i + 1 < patternLen) return false;
+    int ub = scoreInit + (P.matchReward > 0 ? P.matchReward : 0) * patternLen - P.gapOpenPenalty - (i + 1 - patternLen) * P.gapExtendPenalty;
+    if (ub < 0) ub = 0;              // H is floored at 0
+    if (!(ub < bestLocalScore && ub < bestGlobalScore)) return false;
+    return i >= bestLocalTextOffset + (patternLen - 1 - bestLocalPatternOffset);
+}
+
 SG_HDN void sg_ag_finish(const SgTables &T, const SgAgParams &P, const SgAgLayout &lay, const uint8_t *bt, int dir,
                          const uint8_t *text /* already decremented for dir==-1 */, const uint8_t *pattern, const uint8_t *quality,
                          int patternLen, int scoreInit, int endBonus, bool useClippingOptimizations,
@@ -397,6 +413,9 @@ SG_HDN void sg_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParam
             bestLocalAlignmentTextOffset = i;
             bestLocalAlignmentPatternOffset = localAlignmentPatternOffset;
         }
+
+        if (!banded && sg_ag_can_stop_after_row(P, i, patternLen, scoreInit, bestLocalAlignmentScore, bestLocalAlignmentTextOffset,
+                                                bestLocalAlignmentPatternOffset, bestGlobalAlignmentScore)) break;
 
         int16_t *tmp = Hm1ptr; Hm1ptr = Hptr; Hptr = tmp;
     }

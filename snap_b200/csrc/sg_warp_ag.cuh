@@ -14,6 +14,7 @@
 // that one are committed.  Integer DP on int16-range values: DPX-style min/max, no tensor cores.
 #pragma once
 #include "sg_ag.h"
+#include "sg_warp_ag_packed.cuh"
 
 #ifndef SG_AG_REG_BLOCKS
 #define SG_AG_REG_BLOCKS 0        // > 1: keep up to that many blocks of a row in registers through the lazy-F passes (measured slower: spills + code size)
@@ -75,6 +76,17 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
             }
         }
     }
+#ifndef SG_AG_NO_PACKED
+    if (!banded && numVec <= SG_AGP_MAX_VEC) {
+        // unbanded, up to 192 columns: the packed (two cells per lane, DPX s16x2) register-resident form
+        __syncwarp();
+        SgAgBests bb;
+        sg_warp_ag_rows_packed(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
+        sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
+                     bb.lScore, bb.lText, bb.lPat, bb.gScore, bb.gText, out);
+        return;
+    }
+#endif
     // striped query profile (the reference's qProfile, :921-935 / :348-365) as int8, -128 standing for the INT16_MIN padding
     int8_t *prof = S.agProf;
     for (int idx = lane; idx < stride; idx += 32) {
@@ -408,16 +420,8 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
             bestLocalAlignmentPatternOffset = best;
         }
 
-        // Row pruning (ours; the reference walks all textLen rows).  Every cell of row r >= patternLen lies on a path that
-        // consumed r+1 text characters against at most patternLen pattern characters, i.e. holds at least r+1-patternLen
-        // vertical-gap steps: H(r, .) <= max(0, scoreInit + matchReward*patternLen - open - (r - patternLen)*ext), non-increasing in r.
-        // Once that bound is below both running bests no later row can replace them (local needs >, global needs >=), and
-        // nothing else of the result depends on those rows.
-        if (!banded && i + 1 >= patternLen) {
-            int ub = scoreInit + (P.matchReward > 0 ? P.matchReward : 0) * patternLen - open - (i + 1 - patternLen) * ext;
-            if (ub < 0) ub = 0;          // H is floored at 0
-            if (ub < bestLocalAlignmentScore && ub < bestGlobalAlignmentScore) break;
-        }
+        if (!banded && sg_ag_can_stop_after_row(P, i, patternLen, scoreInit, bestLocalAlignmentScore, bestLocalAlignmentTextOffset,
+                                                bestLocalAlignmentPatternOffset, bestGlobalAlignmentScore)) break;      // row pruning, see sg_ag.h
 
         int16_t *tmp = Hm1ptr; Hm1ptr = Hptr; Hptr = tmp;
     }

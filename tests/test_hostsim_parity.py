@@ -87,13 +87,18 @@ def test_lv_fuzz(reflib, seed):
 
 @pytest.mark.parametrize("seed", [11, 12])
 def test_ag_fuzz(reflib, seed):
-    """Includes the inputs on which the reference's traceback walks onto cells its DP never wrote and picks up bits
-    left by earlier calls: the engine keeps the same persistent per-direction array, so those agree too."""
+    """Every job whose reference answer is a function of its inputs must match bit for bit.  On the rest (`stale`: the
+    reference's traceback walks onto cells its DP never wrote and picks up bits left by EARLIER calls in its never-cleared
+    array, < 1 % of random jobs) the engine keeps the same persistent per-direction array, but it does not write the rows
+    it prunes (sg_ag_can_stop_after_row), so the left-over bits can differ: score and offsets must still agree."""
     t, p, q, jb = J.ag_jobs(3000, seed)
     want = reflib.ag_batch(t, p, q, jb.astype(reflib.AG_JOB_DTYPE))
     got, stale = hs.ag_batch(t, p, q, jb, J.AG_OUT, reflib.AG_PARAMS_DEFAULT)
-    assert J.same_out(want, got).all()
-    assert stale.sum() > 0
+    stale = stale != 0
+    assert J.same_out(want, got)[~stale].all()
+    assert 0 < stale.sum() <= 0.01 * stale.size
+    for f in ("agScore", "textOffset", "patternOffset"):
+        assert (want[f] == got[f]).all(), f
 
 
 @pytest.mark.parametrize("opt", list(OPTION_SETS))
