@@ -442,6 +442,7 @@ SG_HDN int sg_gapless_compute(const SgTables &T, const SgAgParams &P, int dir, c
     o->matchProbability = 1.0;
     if (dir == -1) text--;
     int gapLessScore = scoreInit, maxScore = scoreInit, best = 0;
+    #pragma unroll 1
     for (int i = 0; i < patternLen; i++) {
         gapLessScore += (pattern[i] == text[i * dir]) ? P.matchReward : P.subPenalty;
         if (gapLessScore > maxScore) { maxScore = gapLessScore; best = i; }
@@ -449,6 +450,7 @@ SG_HDN int sg_gapless_compute(const SgTables &T, const SgAgParams &P, int dir, c
     if (maxScore > scoreInit) {
         int nEdits = 0, nMatches = 0;
         double mp = 1.0;
+        #pragma unroll 1
         for (int i = 0; i <= best; i++) {
             if (pattern[i] != text[i * dir]) { nEdits += 1; mp *= T.phred[quality[i]]; }
             else nMatches++;

@@ -20,12 +20,12 @@ SG_HD void sg_ag_dispatch(const SgTables &T, const SgScratch &S, const SgAgParam
                           int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out, int lane)
 {
 #if defined(__CUDA_ARCH__)
-    if (lane >= 0) {
-        sg_warp_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out, lane);
-        return;
-    }
-#endif
+    // every device caller is a converged warp (lane >= 0); the scalar form is not compiled into the kernels
+    sg_warp_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out, lane);
+#else
+    (void)lane;
     sg_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out);
+#endif
 }
 
 struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260-329
@@ -322,9 +322,11 @@ struct SgCandScore {
     int basesClippedBefore, basesClippedAfter, agScore;
 };
 
-SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLocationIn, int seedOffset, int scoreLimitForThisElement, bool useHamming,
-                               SgCandScore *o)
+// HAM: the Hamming / gapless pass (AlignRead(..., useHamming = true)); a template parameter so that the stock pass carries none of its code
+template <bool HAM>
+SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLocationIn, int seedOffset, int scoreLimitForThisElement, SgCandScore *o)
 {
+    const bool useHamming = HAM;
     const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
     int64_t genomeLocation = genomeLocationIn;
     unsigned score = (unsigned)SG_SCORE_ABOVE_LIMIT;
@@ -445,8 +447,10 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
 }
 
 // BaseAligner::score (:917-1534).  Returns true iff a result was reached.
-SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult, bool useHamming = false)
+template <bool HAM>
+SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult)
 {
+    const bool useHamming = HAM;
     const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
     if (0 == A.mostSeedsContainingAnyParticularBase[0] && 0 == A.mostSeedsContainingAnyParticularBase[1]) {
         primaryResult->status = SNAPGPU_NOT_FOUND;
@@ -516,7 +520,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                 bool genomeLocationIsNonALT = (!pr.altAwareness) || !A.isALT(genomeLocation);
 
                 SgCandScore cs;
-                sg_score_candidate(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, useHamming, &cs);
+                sg_score_candidate<HAM>(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, &cs);
                 unsigned score = cs.score;
                 double matchProbability = cs.matchProbability;
                 genomeLocation = cs.genomeLocation;
@@ -605,8 +609,8 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
 
 // BaseAligner::AlignRead (:272-763) for one read with the stock loop's arguments (SingleAligner.cpp:250).
 // `result` must be caller-zeroed POD; on return it holds what the reference would have put in primaryResult.
-SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult,
-                          bool useHamming = false)
+template <bool HAM>
+SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult)
 {
     const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
     const uint32_t seedLen = ix.seedLen;
@@ -706,7 +710,7 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
         if (nextSeedToTest >= nPossibleSeeds) {
             A.wrapCount++;
             if (A.wrapCount >= seedLen) {
-                sg_score(A, true, primaryResult, useHamming);
+                sg_score<HAM>(A, true, primaryResult);
                 primaryResult->scorePriorToClipping = primaryResult->score;     // finalizeSecondaryResults, :2442
                 return;
             }
@@ -767,14 +771,21 @@ SG_HDN void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *
         nextSeedToTest += seedLen;
 
         if (appliedEitherSeed) {
-            if (sg_score(A, false, primaryResult, useHamming)) {
+            if (sg_score<HAM>(A, false, primaryResult)) {
                 primaryResult->scorePriorToClipping = primaryResult->score;
                 return;
             }
         }
     }
-    sg_score(A, true, primaryResult, useHamming);
+    sg_score<HAM>(A, true, primaryResult);
     primaryResult->scorePriorToClipping = primaryResult->score;
+}
+
+SG_HD void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult,
+                         bool useHamming = false)
+{
+    if (useHamming) sg_align_read_t<true>(A, readData, readQuality, readLen, primaryResult);
+    else sg_align_read_t<false>(A, readData, readQuality, readLen, primaryResult);
 }
 
 // BaseAligner::scoreLocationWithAffineGap (:766-915): the affine-gap rescoring used by alignAffineGap below.  Note the

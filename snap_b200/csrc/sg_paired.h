@@ -60,6 +60,7 @@ struct SgHitSet {                    // HashTableHitSet
             lk.nHits = nHits;
             lk.seedOffset = seedOffset;
             lk.whichDisjointHitSet = (uint32_t)currentDisjointHitSet;
+            #pragma unroll 1
             while (lk.nHits > 0 && lk.hits[lk.nHits - 1] < lk.seedOffset) lk.nHits--;
             nLookupsUsed++;
         }

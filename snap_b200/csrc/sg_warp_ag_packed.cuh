@@ -67,13 +67,16 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
         int hInit = scoreInit;
         if (i > 0) { hInit = scoreInit - open - (i - 1) * ext; if (hInit < 0) hInit = 0; }
 
-        unsigned hreg[SG_AGP_BLOCKS], areg[SG_AGP_BLOCKS];
+        // The row's (up to) three blocks live in three register pairs.  To keep the hot loop bodies single-copy (instruction
+        // cache: the kernel is fetch-bound) the block loops are NOT unrolled: each iteration works on (h0, a0) and then rotates
+        // (h0,h1,h2) <- (h1,h2,h0); every loop makes exactly SG_AGP_BLOCKS rotations, so the registers end up in place again.
+        unsigned h0 = 0, h1r = 0, h2 = 0, a0 = 0, a1 = 0, a2r = 0;
         unsigned fcarry = 0;                         // F entering the next vector of SSE lanes (2a, 2a+1); identical for all qq
 
         // ---------------- main pass: 8 vectors per step ----------------
-        #pragma unroll
+        #pragma unroll 1
         for (int b = 0; b < SG_AGP_BLOCKS; b++) {
-            hreg[b] = 0; areg[b] = 0;
+            unsigned hnew = 0, anew = 0;
             if (b < nBlocks) {
                 const int k = 8 * b + qq;
                 const bool valid = k < numVec;
@@ -106,17 +109,19 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
                 if (qq > 0) fin = __vimax_s16x2_relu(gi, __vadd2(fcarry, nQqExt2));
                 const unsigned h = __vibmax_s16x2(h1, fin, &hgeHi, &hgeLo);        // bit 2: f > h
                 (void)__vibmax_s16x2(temp, __vadd2(fin, nExt2), &t2Hi, &t2Lo);     // bit 32: f - ext > temp
-                hreg[b] = valid ? h : 0u;
-                areg[b] = ((mgeLo ? 0u : 1u) | (hgeLo ? 0u : 2u) | (tgeLo ? 0u : 4u) | (t2Lo ? 0u : 32u)) |
-                          (((mgeHi ? 0u : 1u) | (hgeHi ? 0u : 2u) | (tgeHi ? 0u : 4u) | (t2Hi ? 0u : 32u)) << 8);
+                hnew = valid ? h : 0u;
+                anew = ((mgeLo ? 0u : 1u) | (hgeLo ? 0u : 2u) | (tgeLo ? 0u : 4u) | (t2Lo ? 0u : 32u)) |
+                       (((mgeHi ? 0u : 1u) | (hgeHi ? 0u : 2u) | (tgeHi ? 0u : 4u) | (t2Hi ? 0u : 32u)) << 8);
                 // F leaving the block
                 int nv = numVec - 8 * b; if (nv > 8) nv = 8;
                 const unsigned gl = __shfl_sync(0xffffffffu, g, (nv - 1) * 4 + a);
                 fcarry = __vimax_s16x2_relu(gl, __vadd2(fcarry, sg_pk2(-nv * ext)));
             }
+            h0 = h1r; h1r = h2; h2 = hnew;           // rotate: after the loop (h0,h1r,h2) = blocks (0,1,2)
+            a0 = a1; a1 = a2r; a2r = anew;
         }
 
-        // ---------------- lazy F (:1080-1112): whole passes evaluated at once, committed up to the first vector at which
+        // ---------------- lazy F (:1080-1112): whole blocks evaluated at once, committed up to the first vector at which
         //                  no SSE lane can still change H ----------------
         unsigned fl = fcarry;
         bool converged = false;
@@ -124,14 +129,14 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
         for (int kk = 0; kk < SG_VEC && !converged; kk++) {
             const unsigned below = __shfl_up_sync(0xffffffffu, fl, 1);
             fl = (fl << 16) | (a == 0 ? 0u : (below >> 16));                       // f = f << one SSE lane
-            #pragma unroll
+            #pragma unroll 1
             for (int b = 0; b < SG_AGP_BLOCKS; b++) {
                 if (b < nBlocks && !converged) {
                     const int k = 8 * b + qq;
                     const bool valid = k < numVec;
                     bool hgeHi, hgeLo, tgeHi, tgeLo;
                     const unsigned fv = __viaddmax_s16x2_relu(fl, sg_pk2(-k * ext), 0u);
-                    const unsigned newh = __vibmax_s16x2(hreg[b], fv, &hgeHi, &hgeLo);             // f > h
+                    const unsigned newh = __vibmax_s16x2(h0, fv, &hgeHi, &hgeLo);                  // f > h
                     const unsigned temp = __viaddmax_s16x2_relu(newh, nOpen2, 0u);
                     const unsigned fn = __viaddmax_s16x2_relu(fv, nExt2, 0u);
                     (void)__vibmax_s16x2(temp, fn, &tgeHi, &tgeLo);                                // f - ext > h - open
@@ -141,29 +146,33 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
                     const unsigned z = (liveMask - 0x11111111u) & ~liveMask & 0x88888888u & (nv >= 8 ? 0xffffffffu : ((1u << (4 * nv)) - 1u));
                     const int firstConv = z ? ((__ffs(z) - 1) >> 2) : 8;
                     if (valid && qq <= firstConv) {
-                        hreg[b] = newh;
-                        areg[b] |= ((hgeLo ? 0u : 2u) | (tgeLo ? 0u : 32u)) | (((hgeHi ? 0u : 2u) | (tgeHi ? 0u : 32u)) << 8);
+                        h0 = newh;
+                        a0 |= ((hgeLo ? 0u : 2u) | (tgeLo ? 0u : 32u)) | (((hgeHi ? 0u : 2u) | (tgeHi ? 0u : 32u)) << 8);
                     }
                     if (firstConv < 8) converged = true;
                 }
+                { const unsigned t = h0; h0 = h1r; h1r = h2; h2 = t; }
+                { const unsigned t = a0; a0 = a1; a1 = a2r; a2r = t; }
             }
             if (!converged) fl = __viaddmax_s16x2_relu(fl, nRowExt2, 0u);
         }
 
         // ---------------- write the row once; per-lane row maximum and the largest column holding it ----------------
         unsigned rmax = 0; int kLo = -1, kHi = -1;
-        #pragma unroll
+        #pragma unroll 1
         for (int b = 0; b < SG_AGP_BLOCKS; b++) {
             const int k = 8 * b + qq;
             if (b < nBlocks && k < numVec) {
                 const int w = k * 4 + a;
-                Hm[w] = hreg[b];
-                *(uint16_t *)(btRow + 2 * w) = (uint16_t)areg[b];
+                Hm[w] = h0;
+                *(uint16_t *)(btRow + 2 * w) = (uint16_t)a0;
                 bool geHi, geLo;
-                rmax = __vibmax_s16x2(hreg[b], rmax, &geHi, &geLo);
+                rmax = __vibmax_s16x2(h0, rmax, &geHi, &geLo);
                 if (geLo) kLo = k;
                 if (geHi) kHi = k;
             }
+            { const unsigned t = h0; h0 = h1r; h1r = h2; h2 = t; }
+            { const unsigned t = a0; a0 = a1; a1 = a2r; a2r = t; }
         }
         __syncwarp();
         const int mLo = (int)(short)(rmax & 0xffffu), mHi = (int)(short)(rmax >> 16);

@@ -167,6 +167,7 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
         memset(&r, 0, sizeof(r));
         cTotal++;
         uint32_t countOfNs = 0;
+        #pragma unroll 1
         for (uint32_t k = lane; k < len; k += 32) countOfNs += (rd[k] == 'N');
         countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
         if (len < pr.minReadLength || countOfNs > pr.maxK || len > pr.maxReadLen) {
@@ -250,6 +251,7 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
         for (int w = 0; w < 2; w++) {
             rb[w] = bases + offsets[2 * i + w]; rq[w] = quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w];
             uint32_t countOfNs = 0;
+            #pragma unroll 1
             for (uint32_t k = lane; k < ln[w]; k += 32) countOfNs += (rb[w][k] == 'N');
             countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
             useful[w] = ln[w] >= pr.minReadLength && countOfNs <= pr.maxK;       // PairedAligner.cpp:669-676
@@ -1098,6 +1100,7 @@ static int leaf_scratch(int device, SgParams *p, int *threads, uint8_t **d_scrat
     p->poolSize = 1; p->tableSlots = 2; p->numWeightLists = 2; p->maxReadLen = 1000;
     *bytes = sg_align_up(sg_scratch_bytes(*p), 256);
     *threads = 64 * 32;
+    if (const char *e = getenv("SNAPGPU_TEST_WORKERS")) { int v = atoi(e); if (v >= 32 && v <= 8192) *threads = v / 32 * 32; }   // leaf micro-benchmarks
     SG_CUDA(cudaMalloc((void **)d_scratch, *bytes * (size_t)*threads));
     SG_CUDA(cudaMemset(*d_scratch, 0, *bytes * (size_t)*threads));
     SgTables T;
@@ -1160,6 +1163,17 @@ static int test_ag_impl(int device, const snapgpu_ag_params *ap, const char *tex
     if (nWarps > 0) {
         if (nWarps > threads) nWarps = threads;
         sg_test_ag_warp_kernel<<<nWarps, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+        if (const char *e = getenv("SNAPGPU_TEST_REPEAT")) {           // leaf micro-benchmark: time R more launches of the same batch
+            int reps = atoi(e);
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0);
+            for (int r = 0; r < reps; r++) sg_test_ag_warp_kernel<<<nWarps, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "snapgpu_test_ag_warp: %d jobs x %d launches on %d warps: %.3f ms per launch, %.1f ns per job\n", (int)nJobs, reps, nWarps,
+                    ms / reps, 1e6 * ms / reps / (double)nJobs);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
     } else {
         sg_test_ag_kernel<<<threads / 32, 32>>>(d_tb, p, P, d_scratch, bytes, d_text, d_pat, d_qual, d_jobs, nJobs, d_out);
     }
