@@ -11,6 +11,7 @@
 
 struct SgAgParams {
     int matchReward, subPenalty /* negative */, gapOpenPenalty /* open+extend */, gapExtendPenalty, fivePrimeEndBonus, threePrimeEndBonus;
+    int usePacked;                   // device: take the packed s16x2 form for unbanded problems (results are identical either way)
 };
 
 SG_HD SgAgParams sg_ag_params(int matchReward, int subPenalty, int gapOpen, int gapExtend, int five, int three)
@@ -18,6 +19,7 @@ SG_HD SgAgParams sg_ag_params(int matchReward, int subPenalty, int gapOpen, int 
     SgAgParams p;                    // AffineGapVectorized::init, :105-133
     p.matchReward = matchReward; p.subPenalty = -subPenalty; p.gapOpenPenalty = gapOpen + gapExtend;
     p.gapExtendPenalty = gapExtend; p.fivePrimeEndBonus = five; p.threePrimeEndBonus = three;
+    p.usePacked = 0;
     return p;
 }
 

@@ -77,7 +77,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         }
     }
 #ifndef SG_AG_NO_PACKED
-    if (!banded && numVec <= SG_AGP_MAX_VEC) {
+    if (!banded && numVec <= SG_AGP_MAX_VEC && P.usePacked) {
         // unbanded, up to 192 columns: the packed (two cells per lane, DPX s16x2) register-resident form
         __syncwarp();
         SgAgBests bb;

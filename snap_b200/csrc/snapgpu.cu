@@ -229,6 +229,7 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
     S.agCands = nullptr; S.nAgCands = 0; S.maxAgCands = 0; S.agCandsOverflow = 0;
     sg_scratch_carve(prSingle, arena, &S.sc);
     S.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
+    S.ag.usePacked = 1;          // `snap paired` rescoring is mostly unbanded (wide score limits): the packed form pays here, not in sg_align_kernel
     S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     S.nUsedElements = 0;
     S.work.lookups = S.work.entriesProbed = S.work.overflowWords = S.work.lvCalls = S.work.agCalls = S.work.popularIgnored = 0;
@@ -1153,6 +1154,8 @@ static int test_ag_impl(int device, const snapgpu_ag_params *ap, const char *tex
     SgParams p; int threads; uint8_t *d_scratch = nullptr; size_t bytes; SgTables *d_tb = nullptr;
     if (leaf_scratch(device, &p, &threads, &d_scratch, &bytes, &d_tb)) return 1;
     SgAgParams P = sg_ag_params(ap->matchReward, ap->subPenalty, ap->gapOpenPenalty, ap->gapExtendPenalty, ap->fivePrimeEndBonus, ap->threePrimeEndBonus);
+    P.usePacked = 1;                 // leaf tests: the packed form unless SNAPGPU_TEST_AG_PACKED=0 (the tests run both)
+    if (const char *e = getenv("SNAPGPU_TEST_AG_PACKED")) P.usePacked = atoi(e) != 0;
     uint8_t *d_text, *d_pat, *d_qual; snapgpu_ag_job *d_jobs; snapgpu_ag_out *d_out;
     SG_CUDA(cudaMalloc((void **)&d_text, textBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_pat, patBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_qual, patBytes + 16));
     SG_CUDA(cudaMalloc((void **)&d_jobs, (size_t)nJobs * sizeof(*jobs) + 16)); SG_CUDA(cudaMalloc((void **)&d_out, (size_t)nJobs * sizeof(*out) + 16));

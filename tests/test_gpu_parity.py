@@ -91,7 +91,10 @@ def test_warp_leaves_golden(engine, golden_dir):
         assert (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
 
-def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib):
+@pytest.mark.parametrize("packed", ["1", "0"])
+def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib, monkeypatch, packed):
+    """packed = 1: unbanded jobs take the s16x2 (DPX) form used by the paired kernel; 0: the int form used by sg_align_kernel."""
+    monkeypatch.setenv("SNAPGPU_TEST_AG_PACKED", packed)
     for seed in (301, 302):
         t, p, q, jb = J.lv_jobs(3000, seed)
         want = reflib.lv_batch(t, p, q, jb.astype(reflib.LV_JOB_DTYPE))
@@ -367,3 +370,4 @@ def test_pairs_tiny_pool_caps_take_the_retry_pass(engine, gidx, small_cfg, refli
         got, _ = al.align(pb)
         assert differing_pairs(want, got) == [], name
     al.close()
+
