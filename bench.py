@@ -60,6 +60,17 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(workload, batch_reads, genome_mbp):
+    """DRAM bytes of ONE launch of the alignment kernel from the committed `ncu --set full` capture of this same workload
+    (profiles/traffic.json, written by profiles/extract_traffic.py); None when the capture is of another configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s_%dreads_%dmbp" % (workload, batch_reads, genome_mbp)
+        return int(t[key]["dram_bytes_per_launch"]) if key in t else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -249,7 +260,7 @@ def run_ours(args):
     kernel_ms_avg = float(np.mean(kernel_ms))
     achieved = alg_bytes / (kernel_ms_avg / 1e3) / 1e9
     roofline = {"kernel": "sg_align_paired_kernel" if paired else "sg_align_kernel", "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 6), "traffic": measured_traffic(args.workload, B, args.genome_mbp), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(kernel_ms_avg, 3),
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
 
@@ -287,6 +298,13 @@ def run_ours(args):
             out["seed_phase"] = seed_phase(args, idx, batches, device, peak, peak_src)
         except Exception as e:  # pragma: no cover
             out["seed_phase"] = {"error": str(e)[:200]}
+
+    # ---- FASTQ ingest in isolation (rank 0) ----
+    if rank == 0 and not args.no_seed_phase and not paired:
+        try:
+            out["ingest_phase"] = ingest_phase(args, host_batches[0], device, peak, peak_src)
+        except Exception as e:  # pragma: no cover
+            out["ingest_phase"] = {"error": str(e)[:200]}
 
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -358,6 +376,69 @@ def seed_phase(args, idx, batches, device, peak, peak_src):
             "frac_of_stream_peak": round(achieved / peak, 5),
             "torch_random_8B_gather_gbs": round(gather_gbs, 2), "torch_random_gather_sector_gbs": round(gather_sector_gbs, 2),
             "frac_of_random_gather_rate": round(achieved / gather_gbs, 4)}
+
+
+def ingest_phase(args, host_batch, device, peak, peak_src):
+    """FASTQ ingest: snapgpu_fastq_parse_device over the FASTQ text of one batch, text resident in HBM.
+    Algorithmic bytes = text read once + clipped bases and qualities + offsets/lengths/id table written once."""
+    import torch
+    from snap_b200 import engine
+    n = host_batch.n
+    L = READ_LEN
+    rec = 2 + 8 + 1 + L + 3 + L + 1
+    txt = np.empty((n, rec), dtype=np.uint8)
+    txt[:, 0] = ord("@"); txt[:, 1] = ord("r")
+    ids = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        txt[:, 2 + 7 - d] = (ids // 10 ** d % 10 + 48).astype(np.uint8)
+    txt[:, 10] = 10
+    txt[:, 11:11 + L] = host_batch.bases.reshape(n, L)
+    txt[:, 11 + L] = 10; txt[:, 12 + L] = ord("+"); txt[:, 13 + L] = 10
+    q = host_batch.quals.reshape(n, L).copy()
+    q[::7, L - 9:] = ord("#")                       # every 7th read carries a '#' tail the reader clips
+    txt[:, 14 + L:14 + 2 * L] = q
+    txt[:, 14 + 2 * L] = 10
+    text = txt.reshape(-1)
+    d_text = torch.from_numpy(text).to(device)
+    fq = engine.FastqParser(max_bytes=int(text.size) + 64, max_reads=n + 8, device=device.index or 0)
+    d_b = torch.empty((text.size // 2 + 64,), dtype=torch.uint8, device=device); d_q = torch.empty_like(d_b)
+    d_off = torch.empty((n + 8,), dtype=torch.int64, device=device); d_len = torch.empty((n + 8,), dtype=torch.int32, device=device)
+    d_ido = torch.empty((n + 8,), dtype=torch.int64, device=device); d_idl = torch.empty((n + 8,), dtype=torch.int32, device=device)
+    d_fc = torch.empty((n + 8,), dtype=torch.int32, device=device)
+    st = torch.cuda.Stream(device)
+
+    def run():
+        return fq.parse_device(d_text.data_ptr(), int(text.size), 2, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_ido.data_ptr(),
+                               d_idl.data_ptr(), d_fc.data_ptr(), st.cuda_stream)
+    for _ in range(3):
+        nr, used = run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record(st)
+    for _ in range(reps):
+        run()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    kept = int(d_len[:nr].to(torch.int64).sum().item())
+    alg = int(text.size) + 2 * kept + nr * (8 + 4 + 8 + 4 + 4)
+    out = {"kernels": "sg_fastq_count/positions/records/copy + 2 cub scans", "reads": int(nr), "text_bytes": int(text.size), "ms": round(ms, 3),
+           "text_gbs": round(text.size / (ms / 1e3) / 1e9, 2), "reads_per_s": round(nr / (ms / 1e3), 1),
+           "achieved_algorithmic_gbs": round(alg / (ms / 1e3) / 1e9, 2), "peak_gbs": peak, "peak_source": peak_src,
+           "frac": round(alg / (ms / 1e3) / 1e9 / peak, 4), "bytes_consumed_ok": bool(used == text.size)}
+    try:
+        from oracle import reflib
+        if reflib.available():
+            m = min(n, 200000)
+            t0 = time.perf_counter()
+            reflib.fastq_parse(text[:m * rec], 2)
+            dt = time.perf_counter() - t0
+            out["cpu_reference_1thread_text_gbs"] = round(m * rec / dt / 1e9, 3)
+    except Exception as e:  # pragma: no cover
+        out["cpu_reference_error"] = str(e)[:100]
+    fq.close()
+    return out
 
 
 def export_index_for_reference(idx):

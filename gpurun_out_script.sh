@@ -1,8 +1,14 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --no-cpu-baseline --no-seed-phase --steps 4 --warmup 3 > gpurun_out/bench_v10.json 2> gpurun_out/bench_v10.err; echo "bench rc=$?"
-tail -2 gpurun_out/bench_v10.err; python -c "import json;d=json.load(open('gpurun_out/bench_v10.json'));print('V10',d['value'],d['e2e']['value'],d['ms_per_step'])"
-timeout 900 python bench.py --workload paired --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/bench_p8.json 2> gpurun_out/bench_p8.err; echo "bench paired rc=$?"
-tail -2 gpurun_out/bench_p8.err; python -c "import json;d=json.load(open('gpurun_out/bench_p8.json'));print('P8',d['value'],d['e2e']['value'],d['ms_per_step'])"
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"sg_fastq|DeviceScan" -c 40 --csv --log-file gpurun_out/launches_fastq.csv python bench.py --no-cpu-baseline --steps 1 --warmup 3 --genome-mbp 240 > gpurun_out/ncu_fastq.log 2>&1; echo rc=$?
+python - <<'PY'
+import csv
+rows=list(csv.reader(open('gpurun_out/launches_fastq.csv')))
+hdr=[r for r in rows if 'Kernel Name' in r][0]
+ki=hdr.index('Kernel Name'); mi=hdr.index('Metric Name'); vi=hdr.index('Metric Value'); ii=hdr.index('ID')
+cur={}
+for r in rows:
+    if len(r)==len(hdr) and r[ii].isdigit():
+        cur.setdefault((int(r[ii]), r[ki][:50]), {})[r[mi]]=r[vi]
+for k in sorted(cur)[-16:]: print(k, cur[k])
+PY

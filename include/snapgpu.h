@@ -288,6 +288,34 @@ int  snapgpu_align_paired_device(snapgpu_aligner *a, int64_t nPairs, const char 
  * kernel of this aligner latched an error since the last check. */
 int  snapgpu_aligner_check(snapgpu_aligner *a, void *cudaStream);
 
+/*
+ * FASTQ ingest.  Replaces, for a whole buffer of FASTQ text at once, FASTQReader::getReadFromBuffer
+ * (reference SNAPLib/FASTQ.cpp:229-300), the upper-casing / '.' -> 'N' of Read::init (Read.h:465-492) and Read::clip
+ * (Read.h:567-619), and leaves the reads in HBM in exactly the layout snapgpu_align_single_device /
+ * snapgpu_align_paired_device take (for pairs from two files: parse each, interleave offsets/lens on the host, or hand an
+ * interleaved FASTQ).  Only complete 4-line records are consumed; *bytesConsumed says where the next call must start.
+ * clippingType: 0 none, 1 front, 2 back (SNAP's default, `-C-+`), 3 both (Read.h:88); quality '#' is what gets clipped.
+ * Per read r: bases/quals at [offsets[r], offsets[r]+lens[r]) of the output buffers (already clipped and upper-cased),
+ * idOffsets[r]/idLens[r] = the read name inside `text` (without '@', up to the first space), frontClipped[r] = bases
+ * removed at the front.  Any of idOffsets / idLens / frontClipped may be NULL.
+ * A syntax error the reference would exit on (blank line, bad first character of a line, read longer than
+ * MAX_READ_LENGTH) makes the call fail with the reason in snapgpu_last_error().
+ */
+typedef struct snapgpu_fastq snapgpu_fastq;     /* opaque: workspace for buffers of up to maxBytes / maxReads */
+int  snapgpu_fastq_create(int device, int64_t maxBytes, int64_t maxReads, snapgpu_fastq **out);
+void snapgpu_fastq_destroy(snapgpu_fastq *f);
+/* DEVICE pointers for text and all outputs; output buffers must hold nBytes/2 bytes and maxReads entries.  Synchronises
+ * `cudaStream` (NULL = the handle's own) once, to learn the record count. */
+int  snapgpu_fastq_parse_device(snapgpu_fastq *f, const char *d_text, int64_t nBytes, int clippingType,
+                                char *d_bases, char *d_quals, uint64_t *d_offsets, uint32_t *d_lens,
+                                uint64_t *d_idOffsets, uint32_t *d_idLens, uint32_t *d_frontClipped,
+                                int64_t *nReads, int64_t *bytesConsumed, void *cudaStream);
+/* HOST pointers; copies inside. */
+int  snapgpu_fastq_parse(snapgpu_fastq *f, const char *text, int64_t nBytes, int clippingType,
+                         char *bases, char *quals, uint64_t *offsets, uint32_t *lens,
+                         uint64_t *idOffsets, uint32_t *idLens, uint32_t *frontClipped,
+                         int64_t *nReads, int64_t *bytesConsumed);
+
 /* Number of kernel launches issued through this aligner since creation (bench.py's gpu_launches). */
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a);
 

@@ -27,6 +27,8 @@
 #include "Read.h"
 #include "mapq.h"
 #include "Tables.h"
+#include "FASTQ.h"
+#include "DataReader.h"
 
 #include <pthread.h>
 #include <string.h>
@@ -550,6 +552,63 @@ double ref_paired_align_mt(void *vidx, const snapgpu_params *p, const snapgpu_pa
     delete[] args;
     delete[] threads;
     return secs;
+}
+
+
+/*
+ * FASTQ ingest: FASTQReader::getReadFromBuffer (FASTQ.cpp:229-300) + Read::init upper-casing (Read.h:465-492)
+ * + Read::clip (Read.h:567-619) over a whole in-memory buffer.  The parser only asks its DataReader for error context and the
+ * batch id, so a stub that answers "end of file" is enough.  `buf` must be readable one byte past nBytes.
+ * Outputs per read: clipped bases / qualities copied back to back, their offset and length, the id's offset and length in
+ * `buf`, the number of bases clipped from the front.  Returns the bytes consumed.
+ */
+class RefStubDataReader : public DataReader {
+public:
+    virtual bool init(const char *) { return true; }
+    virtual char *readHeader(_int64 *) { return NULL; }
+    virtual void reinit(_int64, _int64) {}
+    virtual bool getData(char **, _int64 *, _int64 *) { return false; }
+    virtual void advance(_int64) {}
+    virtual void nextBatch() {}
+    virtual bool isEOF() { return true; }
+    virtual DataBatch getBatch() { return DataBatch(); }
+    virtual void holdBatch(DataBatch) {}
+    virtual bool releaseBatch(DataBatch) { return true; }
+    virtual _int64 getFileOffset() { return 0; }
+    virtual void getExtra(char **, _int64 *) {}
+    virtual const char *getFilename() { return "buffer"; }
+};
+
+_int64 ref_fastq_parse(char *buf, _int64 nBytes, int clippingType, _int64 maxReads, _int64 *nReads, char *basesOut, char *qualsOut,
+                       _uint64 *outOff, unsigned *outLen, _uint64 *idOff, unsigned *idLen, unsigned *frontClipped)
+{
+    ref_init();
+    RefStubDataReader stub;
+    ReaderContext context;
+    memset(&context, 0, sizeof(context));
+    context.clipping = ReadClippingType((ClippingType)clippingType);
+    context.preserveFASTQComments = false;
+    _int64 pos = 0, n = 0;
+    _uint64 out = 0;
+    while (pos < nBytes && n < maxReads) {
+        // stop at an incomplete trailing record instead of letting the parser exit the process: count the newlines that are left
+        int nl = 0;
+        for (_int64 k = pos; k < nBytes && nl < 4; k++) nl += (buf[k] == '\n');
+        if (nl < 4) break;
+        Read read;
+        _int64 consumed = FASTQReader::getReadFromBuffer(buf + pos, nBytes - pos, &read, "buffer", &stub, context);
+        if (consumed == 0) break;
+        memcpy(basesOut + out, read.getData(), read.getDataLength());
+        memcpy(qualsOut + out, read.getQuality(), read.getDataLength());
+        outOff[n] = out; outLen[n] = read.getDataLength();
+        idOff[n] = (_uint64)(read.getId() - buf); idLen[n] = read.getIdLength();
+        frontClipped[n] = read.getFrontClippedLength();
+        out += read.getDataLength();
+        pos += consumed;
+        n++;
+    }
+    *nReads = n;
+    return pos;
 }
 
 } // extern "C"

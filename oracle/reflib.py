@@ -256,6 +256,25 @@ def paired_align_mt(index: RefIndex, params: Params, pparams: PairedParams, batc
     return res, {"lvCalls": int(lvag[0]), "affineGapCalls": int(lvag[1])}, float(secs)
 
 
+def fastq_parse(text: np.ndarray, clipping: int = 2, max_reads: int | None = None):
+    """FASTQReader::getReadFromBuffer + Read::clip over a whole buffer (SURVEY 8f N2 oracle).  Returns
+    (bases, quals, offsets, lens, id_offsets, id_lens, front_clipped, bytes_consumed)."""
+    L = lib()
+    L.ref_fastq_parse.restype = C.c_int64
+    L.ref_fastq_parse.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_int64)] + [C.c_void_p] * 7
+    buf = np.concatenate([np.ascontiguousarray(text, dtype=np.uint8), np.zeros(16, dtype=np.uint8)])
+    cap = max_reads if max_reads is not None else int((text == 10).sum()) // 4 + 1
+    bases = np.zeros(text.size + 16, dtype=np.uint8)
+    quals = np.zeros(text.size + 16, dtype=np.uint8)
+    offs = np.zeros(cap, dtype=np.uint64); lens = np.zeros(cap, dtype=np.uint32)
+    ido = np.zeros(cap, dtype=np.uint64); idl = np.zeros(cap, dtype=np.uint32); fc = np.zeros(cap, dtype=np.uint32)
+    n = C.c_int64(0)
+    used = L.ref_fastq_parse(_p(buf), text.size, clipping, cap, C.byref(n), _p(bases), _p(quals), _p(offs), _p(lens), _p(ido), _p(idl), _p(fc))
+    r = n.value
+    total = int(offs[r - 1] + lens[r - 1]) if r else 0
+    return bases[:total], quals[:total], offs[:r], lens[:r], ido[:r], idl[:r], fc[:r], int(used)
+
+
 def lv_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray) -> np.ndarray:
     out = np.zeros(jobs.size, dtype=LV_OUT_DTYPE)
     lib().ref_lv_batch(_p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))

@@ -124,3 +124,82 @@ __device__ __forceinline__ void sg_warp_lookup_seed32(const SgIndexView &ix, uin
         }
     }
 }
+
+// ---- split form of the first probe round, for the batched seed-lookup kernel: issue the 32 entry loads of several seeds
+//      back to back (memory-level parallelism), then resolve them one after the other ----
+struct SgProbeRound {
+    uint64_t slot, key;
+    uint32_t v;
+    bool active;
+};
+
+__device__ __forceinline__ void sg_warp_probe_issue(const SgIndexView &ix, uint64_t bases, uint64_t rc, int lane, SgProbeRound &r)
+{
+    const uint32_t keyBits = ix.keyBytes * 8;
+    const bool large = ix.large != 0;
+    const bool lookedUpComplement = large && (bases > rc);
+    const uint32_t myChain = large ? 0u : (uint32_t)(lane >> 4);
+    const uint32_t k = large ? (uint32_t)lane : (uint32_t)(lane & 15);
+    const uint64_t s = large ? (lookedUpComplement ? rc : bases) : (myChain ? rc : bases);
+    const uint64_t low = (ix.keyBytes == 8) ? s : (s & ((1ULL << keyBits) - 1));
+    const uint32_t table = (ix.keyBytes == 8) ? 0u : (uint32_t)(s >> keyBits);
+    const uint64_t size = ix.tableSize[table];
+    const uint64_t base = ix.tableStart[table];
+    const uint64_t hsh = sg_fmix64(low);
+    const uint64_t qq = __umul64hi(hsh, ix.tableMagic[table]);
+    uint64_t home = hsh - qq * size;
+    if (home >= size) home -= size;
+    if (home >= size) home -= size;
+    uint64_t pos = home + sg_probe_offset(k);
+    if (pos >= size) { pos -= size; if (pos >= size) pos %= size; }
+    r.slot = base + pos;
+    r.active = (uint64_t)k <= size + 5;
+    if (r.active) sg_entry_load(ix, r.slot, &r.v, &r.key); else { r.v = 0; r.key = ~0ULL; }
+}
+
+// Returns false when a chain did not stop within the first round (caller falls back to sg_warp_lookup_seed32).
+__device__ __forceinline__ bool sg_warp_probe_finish(const SgIndexView &ix, const SgProbeRound &r, uint64_t bases, uint64_t rc, int lane, SgHits *out,
+                                                     uint32_t *examined, uint32_t *overflowWords)
+{
+    const bool large = ix.large != 0;
+    const bool lookedUpComplement = large && (bases > rc);
+    const uint32_t k = large ? (uint32_t)lane : (uint32_t)(lane & 15);
+    const uint32_t keyBits = ix.keyBytes * 8;
+    const uint64_t s = large ? (lookedUpComplement ? rc : bases) : ((lane >> 4) ? rc : bases);
+    const uint64_t low = (ix.keyBytes == 8) ? s : (s & ((1ULL << keyBits) - 1));
+    const uint64_t size = ix.tableSize[(ix.keyBytes == 8) ? 0u : (uint32_t)(s >> keyBits)];
+    out->nHits[0] = out->nHits[1] = 0;
+    out->hits[0] = out->hits[1] = ix.overflow;
+    const bool match = r.active && (r.key == low);
+    const bool inval = r.active && (r.v == ix.invalidValue);
+    bool stop = (k == 0) ? (match && !inval) : (match || inval);
+    if (r.active && (uint64_t)k == size + 5) stop = true;
+    const uint32_t stopMask = __ballot_sync(SG_FULL, stop);
+    uint64_t foundSlot[2] = {~0ULL, ~0ULL};
+    const int nChains = large ? 1 : 2;
+    for (int c = 0; c < nChains; c++) {
+        const uint32_t m = large ? stopMask : ((stopMask >> (16 * c)) & 0xffffu);
+        if (m == 0) return false;
+        const uint32_t first = __ffs(m) - 1;
+        const uint32_t srcLane = large ? first : (16 * c + first);
+        const bool hit = __shfl_sync(SG_FULL, (int)(match && !inval), srcLane) != 0;
+        const uint32_t slo = __shfl_sync(SG_FULL, (uint32_t)r.slot, srcLane), shi = __shfl_sync(SG_FULL, (uint32_t)(r.slot >> 32), srcLane);
+        foundSlot[c] = hit ? (((uint64_t)shi << 32) | slo) : ~0ULL;
+        *examined += first + 1;
+    }
+    if (large) {
+        if (foundSlot[0] == ~0ULL) return true;
+        const uint32_t *entry = (const uint32_t *)(ix.tables + foundSlot[0] * ix.entryBytes);
+        sg_fill_hits(ix, lookedUpComplement ? entry + 1 : entry, &out->nHits[0], &out->hits[0], overflowWords);
+        if (bases == rc) { out->nHits[1] = out->nHits[0]; out->hits[1] = out->hits[0]; }
+        else sg_fill_hits(ix, lookedUpComplement ? entry : entry + 1, &out->nHits[1], &out->hits[1], overflowWords);
+    } else {
+        for (int c = 0; c < 2; c++) {
+            if (foundSlot[c] != ~0ULL) {
+                const uint32_t *entry = (const uint32_t *)(ix.tables + foundSlot[c] * ix.entryBytes);
+                sg_fill_hits(ix, entry, &out->nHits[c], &out->hits[c], overflowWords);
+            }
+        }
+    }
+    return true;
+}

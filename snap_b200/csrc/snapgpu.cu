@@ -16,6 +16,7 @@
 #include "sg_paired.h"
 #include "sg_host.h"
 #include "sg_build.cuh"
+#include "sg_fastq.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -102,29 +103,57 @@ struct snapgpu_aligner {
 // kernels
 // ------------------------------------------------------------------------------------------------
 
-// K1 (parity / roofline entry): batched lookupSeed32, one seed per warp; lanes probe the chain together.
-__global__ void sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_t maxHitsPerSeed,
-                                 long long *nHits, uint32_t *hits, uint32_t *probes)
+// K1 (parity / roofline entry): batched lookupSeed32.  One seed per warp at a time (lanes probe the chains together), but
+// SG_LOOKUP_BATCH seeds per warp are in flight: their 32 entry loads are all issued before the first one is resolved.
+#ifndef SG_LOOKUP_BATCH
+#define SG_LOOKUP_BATCH 2            // measured on a 31 GB table (G lookups/s): 1 -> 1.64, 2 -> 1.83, 4 -> 0.89, 8 -> 0.33: past two seeds per warp
+#endif                              // the extra outstanding misses only thrash address translation (DRAM is ~20 % busy throughout)
+#ifndef SG_LOOKUP_MB
+#define SG_LOOKUP_MB 4
+#endif
+__global__ void __launch_bounds__(256, SG_LOOKUP_MB)
+sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_t maxHitsPerSeed,
+                 long long *nHits, uint32_t *hits, uint32_t *probes)
 {
     const int lane = threadIdx.x & 31;
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long i = warp; i < nSeeds; i += nWarps) {
-        uint64_t b, rc;
-        bool ok = sg_warp_seed_pack(seeds + i * ix.seedLen, ix.seedLen, lane, &b, &rc);
-        SgHits h;
-        uint32_t examined = 0, ow = 0;
-        h.nHits[0] = h.nHits[1] = 0; h.hits[0] = h.hits[1] = ix.overflow;
-        if (ok) sg_warp_lookup_seed32(ix, b, rc, lane, &h, &examined, &ow);
-        if (lane == 0) {
-            nHits[2 * i] = h.nHits[0];
-            nHits[2 * i + 1] = h.nHits[1];
-            if (probes) probes[i] = examined;
+    for (long long i0 = warp * SG_LOOKUP_BATCH; i0 < nSeeds; i0 += nWarps * SG_LOOKUP_BATCH) {
+        uint64_t b[SG_LOOKUP_BATCH], rc[SG_LOOKUP_BATCH];
+        bool ok[SG_LOOKUP_BATCH];
+        SgProbeRound pr[SG_LOOKUP_BATCH];
+        #pragma unroll
+        for (int g = 0; g < SG_LOOKUP_BATCH; g++) {
+            const long long i = i0 + g;
+            ok[g] = false;
+            if (i < nSeeds) {
+                ok[g] = sg_warp_seed_pack(seeds + i * ix.seedLen, ix.seedLen, lane, &b[g], &rc[g]);
+                if (ok[g]) sg_warp_probe_issue(ix, b[g], rc[g], lane, pr[g]);
+            }
         }
-        if (hits) {
-            for (int d = 0; d < 2; d++) {
-                uint32_t n = h.nHits[d] < maxHitsPerSeed ? h.nHits[d] : maxHitsPerSeed;
-                for (uint32_t k = lane; k < n; k += 32) hits[(2 * i + d) * (long long)maxHitsPerSeed + k] = h.hits[d][k];
+        #pragma unroll
+        for (int g = 0; g < SG_LOOKUP_BATCH; g++) {
+            const long long i = i0 + g;
+            if (i >= nSeeds) break;
+            SgHits h;
+            uint32_t examined = 0, ow = 0;
+            h.nHits[0] = h.nHits[1] = 0; h.hits[0] = h.hits[1] = ix.overflow;
+            if (ok[g]) {
+                if (!sg_warp_probe_finish(ix, pr[g], b[g], rc[g], lane, &h, &examined, &ow)) {
+                    examined = 0; ow = 0;
+                    sg_warp_lookup_seed32(ix, b[g], rc[g], lane, &h, &examined, &ow);       // a chain longer than one round: exact slow path
+                }
+            }
+            if (lane == 0) {
+                nHits[2 * i] = h.nHits[0];
+                nHits[2 * i + 1] = h.nHits[1];
+                if (probes) probes[i] = examined;
+            }
+            if (hits) {
+                for (int d = 0; d < 2; d++) {
+                    uint32_t n = h.nHits[d] < maxHitsPerSeed ? h.nHits[d] : maxHitsPerSeed;
+                    for (uint32_t k = lane; k < n; k += 32) hits[(2 * i + d) * (long long)maxHitsPerSeed + k] = h.hits[d][k];
+                }
             }
         }
     }
@@ -1090,6 +1119,138 @@ int snapgpu_align_paired(snapgpu_aligner *a, int64_t nPairs, const char *bases, 
     if (nPairs < 0 || 2 * nPairs > a->maxBatchReads) return sg_fail("pair count exceeds maxBatchPairs");
     if (nPairs == 0) return 0;
     return align_host(a, nPairs, 2, sizeof(snapgpu_paired_result), bases, quals, offsets, lens, (uint8_t *)results, counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FASTQ ingest
+// ------------------------------------------------------------------------------------------------
+struct snapgpu_fastq {
+    int device = 0;
+    int64_t maxBytes = 0, maxReads = 0, nTilesMax = 0;
+    uint8_t *d_text = nullptr, *d_bases = nullptr, *d_quals = nullptr;     // staging of the host-buffer path
+    uint32_t *d_tileCounts = nullptr, *d_tileBase = nullptr, *d_nlPos = nullptr, *d_lens = nullptr, *d_idLens = nullptr, *d_front = nullptr;
+    unsigned long long *d_offsets = nullptr, *d_idOffsets = nullptr;
+    SgFastqRecord *d_rec = nullptr;
+    long long *d_meta = nullptr, *h_meta = nullptr;
+    int *d_status = nullptr, *h_status = nullptr;
+    void *d_cub = nullptr; size_t cubBytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+void snapgpu_fastq_destroy(snapgpu_fastq *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaDeviceSynchronize();
+    cudaFree(f->d_text); cudaFree(f->d_bases); cudaFree(f->d_quals); cudaFree(f->d_tileCounts); cudaFree(f->d_tileBase); cudaFree(f->d_nlPos);
+    cudaFree(f->d_lens); cudaFree(f->d_idLens); cudaFree(f->d_front); cudaFree(f->d_offsets); cudaFree(f->d_idOffsets); cudaFree(f->d_rec);
+    cudaFree(f->d_meta); cudaFreeHost(f->h_meta); cudaFree(f->d_status); cudaFreeHost(f->h_status); cudaFree(f->d_cub);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+}
+
+int snapgpu_fastq_create(int device, int64_t maxBytes, int64_t maxReads, snapgpu_fastq **out)
+{
+    if (!out) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(device)) return 1;
+    if (maxBytes <= 0 || maxBytes >= (int64_t)0xfffffff0LL) return sg_fail("snapgpu_fastq_create: maxBytes must be in (0, 4 GiB)");
+    if (maxReads <= 0) return sg_fail("snapgpu_fastq_create: maxReads must be positive");
+    snapgpu_fastq *f = new (std::nothrow) snapgpu_fastq;
+    if (!f) return sg_fail("out of memory");
+    f->device = device; f->maxBytes = maxBytes; f->maxReads = maxReads;
+    f->nTilesMax = (maxBytes + SG_FQ_TILE - 1) / SG_FQ_TILE;
+    size_t c1 = 0, c2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, c1, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(f->nTilesMax + 1));
+    cub::DeviceScan::ExclusiveSum(nullptr, c2, (uint32_t *)nullptr, (unsigned long long *)nullptr, (int)maxReads);
+    f->cubBytes = (c1 > c2 ? c1 : c2) + 256;
+    const size_t maxLines = (size_t)maxReads * 4 + 4;
+    cudaError_t e = cudaSuccess;
+    #define SG_FQ_ALLOC(p, n) if (e == cudaSuccess) e = cudaMalloc((void **)&(p), (n))
+    SG_FQ_ALLOC(f->d_text, (size_t)maxBytes + 16); SG_FQ_ALLOC(f->d_bases, (size_t)maxBytes / 2 + 16); SG_FQ_ALLOC(f->d_quals, (size_t)maxBytes / 2 + 16);
+    SG_FQ_ALLOC(f->d_tileCounts, (size_t)(f->nTilesMax + 1) * 4); SG_FQ_ALLOC(f->d_tileBase, (size_t)(f->nTilesMax + 1) * 4);
+    SG_FQ_ALLOC(f->d_nlPos, maxLines * 4); SG_FQ_ALLOC(f->d_lens, (size_t)maxReads * 4); SG_FQ_ALLOC(f->d_idLens, (size_t)maxReads * 4);
+    SG_FQ_ALLOC(f->d_front, (size_t)maxReads * 4); SG_FQ_ALLOC(f->d_offsets, (size_t)maxReads * 8); SG_FQ_ALLOC(f->d_idOffsets, (size_t)maxReads * 8);
+    SG_FQ_ALLOC(f->d_rec, (size_t)maxReads * sizeof(SgFastqRecord)); SG_FQ_ALLOC(f->d_meta, 4 * sizeof(long long)); SG_FQ_ALLOC(f->d_status, sizeof(int));
+    SG_FQ_ALLOC(f->d_cub, f->cubBytes);
+    #undef SG_FQ_ALLOC
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&f->h_meta, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&f->h_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { std::string msg = std::string("snapgpu_fastq_create: ") + cudaGetErrorString(e); snapgpu_fastq_destroy(f); return sg_fail(msg); }
+    *out = f;
+    return 0;
+}
+
+int snapgpu_fastq_parse_device(snapgpu_fastq *f, const char *d_text, int64_t nBytes, int clippingType, char *d_bases, char *d_quals, uint64_t *d_offsets,
+                               uint32_t *d_lens, uint64_t *d_idOffsets, uint32_t *d_idLens, uint32_t *d_frontClipped, int64_t *nReads,
+                               int64_t *bytesConsumed, void *cudaStream)
+{
+    if (!f || !d_text || !d_bases || !d_quals || !d_offsets || !d_lens || !nReads || !bytesConsumed) return sg_fail("null argument");
+    if (nBytes < 0 || nBytes > f->maxBytes) return sg_fail("snapgpu_fastq_parse: nBytes exceeds the handle's maxBytes");
+    if (clippingType < 0 || clippingType > 3) return sg_fail("snapgpu_fastq_parse: clippingType must be 0..3");
+    *nReads = 0; *bytesConsumed = 0;
+    if (nBytes == 0) return 0;
+    SG_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : f->stream;
+    const uint8_t *text = (const uint8_t *)d_text;
+    const long long nTiles = (nBytes + SG_FQ_TILE - 1) / SG_FQ_TILE;
+    int grid = (int)(nTiles < 148LL * 16 ? nTiles : 148LL * 16);
+    SG_CUDA(cudaMemsetAsync(f->d_status, 0, sizeof(int), st));
+    SG_CUDA(cudaMemsetAsync(f->d_tileCounts + nTiles, 0, 4, st));
+    sg_fastq_count_kernel<<<grid, SG_FQ_THREADS, 0, st>>>(text, nBytes, f->d_tileCounts, nTiles);
+    size_t cb = f->cubBytes;
+    SG_CUDA(cub::DeviceScan::ExclusiveSum(f->d_cub, cb, f->d_tileCounts, f->d_tileBase, (int)(nTiles + 1), st));
+    const long long maxLines = f->maxReads * 4 + 4;
+    sg_fastq_positions_kernel<<<grid, SG_FQ_THREADS, 0, st>>>(text, nBytes, f->d_tileBase, f->d_nlPos, maxLines, nTiles);
+    sg_fastq_meta_kernel<<<1, 1, 0, st>>>(text, nBytes, f->d_tileBase, nTiles, f->d_nlPos, f->maxReads, f->d_meta);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(f->h_meta, f->d_meta, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    const long long R = f->h_meta[1];
+    *nReads = R; *bytesConsumed = f->h_meta[2];
+    if (R == 0) return 0;
+    sg_fastq_records_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(text, nBytes, f->d_nlPos, R, clippingType, (uint8_t)'#', (uint8_t)'#',
+                                                                      (uint32_t)SNAPGPU_MAX_READ_LENGTH, f->d_rec, d_lens, (unsigned long long *)d_idOffsets,
+                                                                      d_idLens, d_frontClipped, f->d_status);
+    cb = f->cubBytes;
+    SG_CUDA(cub::DeviceScan::ExclusiveSum(f->d_cub, cb, d_lens, (unsigned long long *)d_offsets, (int)R, st));
+    long long warps = R < 148LL * 64 ? R : 148LL * 64;
+    sg_fastq_copy_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(text, nBytes, f->d_rec, (const unsigned long long *)d_offsets, R,
+                                                                              (uint8_t *)d_bases, (uint8_t *)d_quals);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(f->h_status, f->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if (*f->h_status == SG_FQ_ERR_BLANK_LINE) return sg_fail("Syntax error in FASTQ file: blank line.");
+    if (*f->h_status == SG_FQ_ERR_BAD_START) return sg_fail("FASTQ file has an invalid starting character on a line");
+    if (*f->h_status == SG_FQ_ERR_TOO_LONG) return sg_fail("Saw a read longer than MAX_READ_LENGTH");
+    return 0;
+}
+
+int snapgpu_fastq_parse(snapgpu_fastq *f, const char *text, int64_t nBytes, int clippingType, char *bases, char *quals, uint64_t *offsets, uint32_t *lens,
+                        uint64_t *idOffsets, uint32_t *idLens, uint32_t *frontClipped, int64_t *nReads, int64_t *bytesConsumed)
+{
+    if (!f || !text || !bases || !quals || !offsets || !lens || !nReads || !bytesConsumed) return sg_fail("null argument");
+    if (nBytes < 0 || nBytes > f->maxBytes) return sg_fail("snapgpu_fastq_parse: nBytes exceeds the handle's maxBytes");
+    SG_CUDA(cudaSetDevice(f->device));
+    SG_CUDA(cudaMemcpyAsync(f->d_text, text, (size_t)nBytes, cudaMemcpyHostToDevice, f->stream));
+    if (snapgpu_fastq_parse_device(f, (const char *)f->d_text, nBytes, clippingType, (char *)f->d_bases, (char *)f->d_quals, (uint64_t *)f->d_offsets, f->d_lens,
+                                   (uint64_t *)f->d_idOffsets, f->d_idLens, f->d_front, nReads, bytesConsumed, nullptr)) return 1;
+    const int64_t R = *nReads;
+    if (R == 0) return 0;
+    SG_CUDA(cudaMemcpyAsync(offsets, f->d_offsets, (size_t)R * 8, cudaMemcpyDeviceToHost, f->stream));
+    SG_CUDA(cudaMemcpyAsync(lens, f->d_lens, (size_t)R * 4, cudaMemcpyDeviceToHost, f->stream));
+    if (idOffsets) SG_CUDA(cudaMemcpyAsync(idOffsets, f->d_idOffsets, (size_t)R * 8, cudaMemcpyDeviceToHost, f->stream));
+    if (idLens) SG_CUDA(cudaMemcpyAsync(idLens, f->d_idLens, (size_t)R * 4, cudaMemcpyDeviceToHost, f->stream));
+    if (frontClipped) SG_CUDA(cudaMemcpyAsync(frontClipped, f->d_front, (size_t)R * 4, cudaMemcpyDeviceToHost, f->stream));
+    SG_CUDA(cudaStreamSynchronize(f->stream));
+    const uint64_t total = offsets[R - 1] + lens[R - 1];
+    if (total) {
+        SG_CUDA(cudaMemcpyAsync(bases, f->d_bases, (size_t)total, cudaMemcpyDeviceToHost, f->stream));
+        SG_CUDA(cudaMemcpyAsync(quals, f->d_quals, (size_t)total, cudaMemcpyDeviceToHost, f->stream));
+        SG_CUDA(cudaStreamSynchronize(f->stream));
+    }
+    return 0;
 }
 
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a) { return a ? a->launches : 0; }

@@ -83,7 +83,8 @@ EXPORTS = [
     "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close",
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
-    "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
+    "snapgpu_fastq_parse", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 _lib = None
@@ -117,6 +118,10 @@ def lib():
         L.snapgpu_align_paired.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.snapgpu_align_paired_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         L.snapgpu_aligner_check.argtypes = [C.c_void_p, C.c_void_p]
+        L.snapgpu_fastq_create.argtypes = [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+        L.snapgpu_fastq_destroy.argtypes = [C.c_void_p]
+        L.snapgpu_fastq_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.snapgpu_fastq_parse_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_aligner_launch_count.restype = C.c_int64
         L.snapgpu_aligner_launch_count.argtypes = [C.c_void_p]
         L.snapgpu_test_lv.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
@@ -306,6 +311,49 @@ class PairedAligner:
     def close(self):
         if self.handle:
             lib().snapgpu_aligner_destroy(self.handle)
+            self.handle = None
+
+
+class FastqParser:
+    """FASTQ text -> clipped, upper-cased reads in the aligners' layout (FASTQReader::getReadFromBuffer + Read::clip for a whole buffer)."""
+
+    CLIP_NONE, CLIP_FRONT, CLIP_BACK, CLIP_FRONT_AND_BACK = 0, 1, 2, 3
+
+    def __init__(self, max_bytes: int, max_reads: int, device: int = 0):
+        h = C.c_void_p()
+        _check(lib().snapgpu_fastq_create(device, max_bytes, max_reads, C.byref(h)))
+        self.handle = h
+        self.max_bytes, self.max_reads = max_bytes, max_reads
+
+    def parse(self, text: np.ndarray, clipping: int = 2):
+        """Host buffer in (uint8 array), host arrays out: (bases, quals, offsets, lens, id_offsets, id_lens, front_clipped, bytes_consumed)."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        n = C.c_int64(0)
+        used = C.c_int64(0)
+        bases = np.zeros(text.size // 2 + 16, dtype=np.uint8)
+        quals = np.zeros(text.size // 2 + 16, dtype=np.uint8)
+        offs = np.zeros(self.max_reads, dtype=np.uint64)
+        lens = np.zeros(self.max_reads, dtype=np.uint32)
+        ido = np.zeros(self.max_reads, dtype=np.uint64)
+        idl = np.zeros(self.max_reads, dtype=np.uint32)
+        fc = np.zeros(self.max_reads, dtype=np.uint32)
+        _check(lib().snapgpu_fastq_parse(self.handle, _p(text), text.size, clipping, _p(bases), _p(quals), _p(offs), _p(lens), _p(ido), _p(idl), _p(fc),
+                                          C.byref(n), C.byref(used)))
+        r = n.value
+        total = int(offs[r - 1] + lens[r - 1]) if r else 0
+        return bases[:total], quals[:total], offs[:r], lens[:r], ido[:r], idl[:r], fc[:r], used.value
+
+    def parse_device(self, d_text, n_bytes, clipping, d_bases, d_quals, d_offsets, d_lens, d_id_offsets=0, d_id_lens=0, d_front=0, stream=0):
+        n = C.c_int64(0)
+        used = C.c_int64(0)
+        _check(lib().snapgpu_fastq_parse_device(self.handle, C.c_void_p(d_text), n_bytes, clipping, C.c_void_p(d_bases), C.c_void_p(d_quals),
+                                                 C.c_void_p(d_offsets), C.c_void_p(d_lens), C.c_void_p(d_id_offsets), C.c_void_p(d_id_lens), C.c_void_p(d_front),
+                                                 C.byref(n), C.byref(used), C.c_void_p(stream)))
+        return n.value, used.value
+
+    def close(self):
+        if self.handle:
+            lib().snapgpu_fastq_destroy(self.handle)
             self.handle = None
 
 

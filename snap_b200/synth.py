@@ -248,3 +248,34 @@ def make_pairs(contigs: list[np.ndarray], n_pairs: int, read_len: int, seed: int
             pair.append((seq[:L].tobytes(), qual.tobytes()))
         reads.extend(pair)
     return ReadBatch.from_lists(reads)
+
+
+def make_fastq_text(batch: ReadBatch, seed: int = 0, crlf_frac: float = 0.0, lower_frac: float = 0.0, dot_frac: float = 0.0, hash_tail_frac: float = 0.0,
+                    hash_head_frac: float = 0.0, comment_frac: float = 0.0, plus_id_frac: float = 0.0, truncate_last: bool = False) -> np.ndarray:
+    """FASTQ text (uint8 array) for the reads of `batch`, decorated with the things FASTQReader / Read::clip must cope with:
+    CRLF line ends, lower-case bases and '.', '#'-quality heads and tails (clipped by the reader), a comment after the id,
+    the id repeated on the '+' line, and optionally a last record cut in the middle."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for i in range(batch.n):
+        b, q = batch.read(i)
+        b = bytearray(b); q = bytearray(q)
+        L = len(b)
+        if L and rng.random() < lower_frac:
+            for k in rng.integers(0, L, size=max(1, L // 10)):
+                b[int(k)] = ord(chr(b[int(k)]).lower())
+        if L and rng.random() < dot_frac:
+            b[int(rng.integers(0, L))] = ord(".")
+        if L and rng.random() < hash_tail_frac:
+            k = int(rng.integers(1, min(L, 40) + 1)); q[L - k:] = b"#" * k
+        if L and rng.random() < hash_head_frac:
+            k = int(rng.integers(1, min(L, 20) + 1)); q[:k] = b"#" * k
+        name = b"read%d" % i
+        line0 = b"@" + name + (b" 1:N:0:ACGT extra" if rng.random() < comment_frac else b"")
+        line2 = b"+" + (name if rng.random() < plus_id_frac else b"")
+        eol = b"\r\n" if rng.random() < crlf_frac else b"\n"
+        parts.append(line0 + eol + bytes(b) + eol + line2 + eol + bytes(q) + eol)
+    text = b"".join(parts)
+    if truncate_last and parts:
+        text = text[:len(text) - len(parts[-1]) // 2]
+    return np.frombuffer(text, dtype=np.uint8).copy()

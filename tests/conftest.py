@@ -125,6 +125,8 @@ OPTION_SETS = {
     "esd3_ms2": dict(maxDist=14, extraSearchDepth=3, minWeightToCheck=2),
     "nobanded": dict(maxDist=14, noBandedAffineGap=1),
     "stopfirst": dict(maxDist=14, stopOnFirstHit=1),
+    "ag_d20": dict(maxDist=20, useAffineGap=1),          # BASELINE configs[3]: `snap single -G -d 20`
+    "d8": dict(maxDist=8),                                # BASELINE configs[0]
 }
 
 

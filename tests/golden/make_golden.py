@@ -82,6 +82,21 @@ def e2e_small(tmp):
     return arrays
 
 
+def fastq_small():
+    """FASTQ text with CRLF ends, lower case, '.', '#' heads/tails, comments, a truncated last record, and the reference
+    reader's output (FASTQReader::getReadFromBuffer + Read::clip via oracle/_ref) for every clipping mode."""
+    contigs = synth.make_contigs(1, 60_000, seed=51)
+    rb = synth.make_reads(contigs, 400, 120, seed=52, short_frac=0.25, n_run_frac=0.1)
+    text = synth.make_fastq_text(rb, 53, crlf_frac=0.2, lower_frac=0.3, dot_frac=0.2, hash_tail_frac=0.35, hash_head_frac=0.2, comment_frac=0.3,
+                                 plus_id_frac=0.3, truncate_last=True)
+    out = {"text": text}
+    for clip in (0, 1, 2, 3):
+        b, q, off, ln, ido, idl, fc, used = reflib.fastq_parse(text, clip)
+        out.update({"bases%d" % clip: b, "quals%d" % clip: q, "offsets%d" % clip: off, "lens%d" % clip: ln, "idoff%d" % clip: ido, "idlen%d" % clip: idl,
+                    "front%d" % clip: fc, "used%d" % clip: np.array([used], dtype=np.int64)})
+    return out
+
+
 def main():
     import tempfile
     with open(os.path.join(HERE, "ref_unit_vectors.json"), "w") as f:
@@ -94,6 +109,7 @@ def main():
     t, p, q, jb = J.ag_jobs(1200, 202)
     np.savez_compressed(os.path.join(HERE, "leaf_ag.npz"), text=t, pat=p, qual=q, jobs=jb,
                         out=reflib.ag_batch(t, p, q, jb.astype(reflib.AG_JOB_DTYPE)))
+    np.savez_compressed(os.path.join(HERE, "fastq_small.npz"), **fastq_small())
     for f in sorted(os.listdir(HERE)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))
 

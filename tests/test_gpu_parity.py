@@ -371,3 +371,50 @@ def test_pairs_tiny_pool_caps_take_the_retry_pass(engine, gidx, small_cfg, refli
         assert differing_pairs(want, got) == [], name
     al.close()
 
+
+
+def _same_fastq(want, got):
+    names = ("bases", "quals", "offsets", "lens", "id_offsets", "id_lens", "front_clipped")
+    for n, a, b in zip(names, want[:7], got[:7]):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), n
+    assert want[7] == got[7], "bytes consumed"
+
+
+def test_fastq_ingest_matches_reference_reader(engine, small_cfg, reflib, golden_dir):
+    """snapgpu_fastq_parse vs FASTQReader::getReadFromBuffer + Read::clip: fixture, then fresh decorated text (CRLF, lower
+    case, '.', '#' heads/tails, comments, truncated last record), every clipping mode; and the parsed reads align exactly
+    like the same reads handed over directly."""
+    from snap_b200 import synth
+    g = np.load(os.path.join(golden_dir, "fastq_small.npz"))
+    fq = engine.FastqParser(max_bytes=64 << 20, max_reads=200000)
+    for clip in (0, 1, 2, 3):
+        got = fq.parse(g["text"], clip)
+        want = (g["bases%d" % clip], g["quals%d" % clip], g["offsets%d" % clip], g["lens%d" % clip], g["idoff%d" % clip], g["idlen%d" % clip],
+                g["front%d" % clip], int(g["used%d" % clip][0]))
+        _same_fastq(want, got)
+    rb = synth.make_reads(small_cfg.contigs, 30000, 150, seed=81, short_frac=0.1, n_run_frac=0.05)
+    text = synth.make_fastq_text(rb, 82, crlf_frac=0.1, lower_frac=0.2, dot_frac=0.1, hash_tail_frac=0.3, hash_head_frac=0.1, comment_frac=0.5,
+                                 plus_id_frac=0.2, truncate_last=True)
+    for clip in (2, 3, 0):
+        _same_fastq(reflib.fastq_parse(text, clip), fq.parse(text, clip))
+    # max_reads smaller than the buffer holds: stops after max_reads records, reports where
+    small = engine.FastqParser(max_bytes=64 << 20, max_reads=1000)
+    got = small.parse(text, 2)
+    want = reflib.fastq_parse(text, 2, max_reads=1000)
+    _same_fastq(want, got)
+    assert len(got[3]) == 1000
+    # empty buffer, buffer without a complete record
+    assert len(fq.parse(np.zeros(0, dtype=np.uint8), 2)[3]) == 0
+    assert fq.parse(np.frombuffer(b"@r\nACGT\n+\n", dtype=np.uint8), 2)[7] == 0
+    for bad in (b"@r\nACGT\n\nIIII\n", b"r\nACGT\n+\nIIII\n", b"@r\n1CGT\n+\nIIII\n", b"@r\nACGT\n-\nIIII\n"):
+        with pytest.raises(engine.SnapGpuError):
+            fq.parse(np.frombuffer(bad, dtype=np.uint8), 2)
+    # parsed reads == the reads: align both ways
+    plain = synth.make_fastq_text(rb, 83)
+    b, q, off, ln, *_ = fq.parse(plain, 2)
+    ix = engine.Index.open(small_cfg.idx)
+    al = engine.SingleAligner(ix, engine.default_params(maxDist=14), 1 << 15)
+    r1, _ = al.align(synth.ReadBatch(b, q, off, ln))
+    r2, _ = al.align(rb)
+    assert r1.tobytes() == r2.tobytes()
+    al.close(); ix.close(); fq.close(); small.close()

@@ -148,3 +148,29 @@ def test_port_probe_and_seed_match_reference(reflib, port, small_cfg):
             else:
                 assert want[d] >= 2
         assert total == want[4] + 2      # entries examined: first slot of each chain + the reference's extra-probe counter
+
+
+def test_fastq_reader_known_answers(reflib):
+    """The oracle's FASTQ path (the reference's own FASTQReader::getReadFromBuffer + Read::clip) on hand-checked records."""
+    txt = (b"@r1 comment\nACGTNacgt.\n+\nIIII#IIII#\n"        # lower case and '.', one '#' at the back
+           b"@r2\r\nGGGG\r\n+r2\r\n####\r\n"                   # CRLF; everything clipped by ClipBack
+           b"@r3\nGGAC\n+\n##II\n"                              # '#' qualities in front
+           b"@r4\nAC\n+\nI")                                    # incomplete: not consumed
+    t = np.frombuffer(txt, dtype=np.uint8)
+    b, q, off, ln, ido, idl, fc, used = reflib.fastq_parse(t, 2)
+    assert used == len(txt) - len(b"@r4\nAC\n+\nI") and list(ln) == [9, 0, 4]
+    assert bytes(b[:9]) == b"ACGTNACGT" and bytes(q[:9]) == b"IIII#IIII"
+    assert [bytes(t[int(o):int(o) + int(l)]) for o, l in zip(ido, idl)] == [b"r1", b"r2", b"r3"]
+    b, q, off, ln, ido, idl, fc, used = reflib.fastq_parse(t, 3)
+    assert list(ln) == [9, 0, 2] and list(fc) == [0, 0, 2] and bytes(b[9:11]) == b"AC"
+    b, q, off, ln, ido, idl, fc, used = reflib.fastq_parse(t, 0)
+    assert list(ln) == [10, 4, 4] and bytes(b[:10]) == b"ACGTNACGTN"
+
+
+def test_fastq_golden_fixture_matches_oracle(reflib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "fastq_small.npz"))
+    for clip in (0, 1, 2, 3):
+        b, q, off, ln, ido, idl, fc, used = reflib.fastq_parse(g["text"], clip)
+        assert np.array_equal(b, g["bases%d" % clip]) and np.array_equal(q, g["quals%d" % clip]) and np.array_equal(ln, g["lens%d" % clip])
+        assert np.array_equal(off, g["offsets%d" % clip]) and np.array_equal(ido, g["idoff%d" % clip]) and np.array_equal(idl, g["idlen%d" % clip])
+        assert np.array_equal(fc, g["front%d" % clip]) and used == int(g["used%d" % clip][0])
