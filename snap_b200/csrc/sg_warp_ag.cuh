@@ -16,9 +16,6 @@
 #include "sg_ag.h"
 #include "sg_warp_ag_packed.cuh"
 
-#ifndef SG_AG_REG_BLOCKS
-#define SG_AG_REG_BLOCKS 0        // > 1: keep up to that many blocks of a row in registers through the lazy-F passes (measured slower: spills + code size)
-#endif
 
 __device__ __forceinline__ int sg_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -211,99 +208,6 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                 continue;
             }
 
-#if SG_AG_REG_BLOCKS > 1
-            if (nBlocks <= SG_AG_REG_BLOCKS) {
-                // ---- up to 4*SG_AG_REG_BLOCKS vectors (pattern <= 160 columns unbanded): each lane keeps its cell of every
-                //      block in registers through the main pass and all lazy-F passes; H and the traceback byte are written once.
-                //      Same arithmetic, order and commit rule as the generic path below. ----
-                int hreg[SG_AG_REG_BLOCKS], areg[SG_AG_REG_BLOCKS];
-                #pragma unroll
-                for (int b = 0; b < SG_AG_REG_BLOCKS; b++) {
-                    hreg[b] = 0; areg[b] = 0;
-                    if (b < nBlocks) {
-                        const int k = 4 * b + q;
-                        const bool valid = k < nVecHere;
-                        const int idx = (vbase + k) * SG_VEC + l;
-                        int temp = 0, h1 = 0, act = 0;
-                        if (valid) {
-                            int hdiag;
-                            if (k == 0) hdiag = (l == 0) ? hInit : (int)Hptr[(vbase + numVec - 1) * SG_VEC + l - 1];
-                            else hdiag = Hptr[idx - SG_VEC];
-                            const int pv = profRow[idx];
-                            const int m = (hdiag > 0) ? sg_sat16(hdiag + (pv == -128 ? -32768 : pv)) : 0;
-                            const int e = E[idx];
-                            act = (e > m) ? 1 : 0;
-                            h1 = m > e ? m : e;
-                            const int e2 = sg_sat16(e - ext);
-                            temp = sg_sat16(m - open); if (temp < 0) temp = 0;
-                            if (e2 > temp) act |= 4;
-                            E[idx] = (int16_t)(e2 > temp ? e2 : temp);
-                        }
-                        const int t0 = sg_shfl(temp, l), t1 = sg_shfl(temp, 8 + l), t2 = sg_shfl(temp, 16 + l), t3 = sg_shfl(temp, 24 + l);
-                        int fin = fcarry - q * ext;
-                        if (q > 0) { int v = t0 - (q - 1) * ext; if (v > fin) fin = v; }
-                        if (q > 1) { int v = t1 - (q - 2) * ext; if (v > fin) fin = v; }
-                        if (q > 2) { int v = t2; if (v > fin) fin = v; }
-                        if (b > 0 || q > 0) { if (fin < 0) fin = 0; }
-                        if (valid) {
-                            if (fin > h1) { act |= 2; h1 = fin; }
-                            if (sg_sat16(fin - ext) > temp) act |= 32;
-                        }
-                        hreg[b] = h1; areg[b] = act;
-                        int nv = nVecHere - 4 * b; if (nv > 4) nv = 4;
-                        int c = fcarry - nv * ext;
-                        { int v = t0 - (nv - 1) * ext; if (nv > 0 && v > c) c = v; }
-                        { int v = t1 - (nv - 2) * ext; if (nv > 1 && v > c) c = v; }
-                        { int v = t2 - (nv - 3) * ext; if (nv > 2 && v > c) c = v; }
-                        { int v = t3 - (nv - 4) * ext; if (nv > 3 && v > c) c = v; }
-                        if (c < 0) c = 0;
-                        fcarry = c;
-                    }
-                }
-                int fl = fcarry;
-                bool converged = false;
-                #pragma unroll 1
-                for (int kk = 0; kk < passes && !converged; kk++) {
-                    if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
-                    { int up = sg_shfl(fl, (lane & 24) | ((l + 7) & 7)); fl = (l == 0) ? 0 : up; }
-                    #pragma unroll
-                    for (int b = 0; b < SG_AG_REG_BLOCKS; b++) {
-                        if (b < nBlocks && !converged) {
-                            const int v = 4 * b + q;
-                            const bool valid = v < nVecHere;
-                            int fv = fl - v * ext; if (fv < 0) fv = 0;
-                            const int h = hreg[b];
-                            const bool a2 = valid && fv > h;
-                            const int newh = a2 ? fv : h;
-                            int temp = newh - open; if (temp < 0) temp = 0;
-                            int fn = fv - ext; if (fn < 0) fn = 0;
-                            const bool live = valid && fn > temp;
-                            const unsigned liveMask = __ballot_sync(0xffffffffu, live);
-                            int nv = nVecHere - 4 * b; if (nv > 4) nv = 4;
-                            const unsigned zeroBytes = (liveMask - 0x01010101u) & ~liveMask & 0x80808080u & (nv >= 4 ? 0xffffffffu : ((1u << (8 * nv)) - 1u));
-                            const int firstConv = zeroBytes ? ((__ffs(zeroBytes) - 1) >> 3) : 4;
-                            if (q <= firstConv) { hreg[b] = newh; areg[b] |= (a2 ? 2 : 0) | (live ? 32 : 0); }
-                            if (firstConv < 4) converged = true;
-                        }
-                    }
-                    if (!converged) { fl = fl - nVecHere * ext; if (fl < 0) fl = 0; }
-                }
-                #pragma unroll
-                for (int b = 0; b < SG_AG_REG_BLOCKS; b++) {
-                    const int k = 4 * b + q;
-                    if (b < nBlocks && k < nVecHere) {
-                        const int idx = (vbase + k) * SG_VEC + l;
-                        const int col = j * segLen + l * numVec + k;
-                        const int h = hreg[b];
-                        if (h > myMax || (h == myMax && col > myMaxCol)) { myMax = h; myMaxCol = col; }
-                        Hm1ptr[idx] = (int16_t)h;
-                        btRow[idx] = (uint8_t)areg[b];
-                    }
-                }
-                __syncwarp();
-                continue;
-            }
-#endif
 
             // ---------------- main pass, 4 vectors per step ----------------
             for (int b = 0; b < nBlocks; b++) {
