@@ -19,6 +19,126 @@
 
 __device__ __forceinline__ int sg_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// The banded DP for bands of up to 32 columns (numVec <= 4, i.e. w <= 15: every `snap single -d 14` rescoring): each
+// (row, segment) is ONE block of 4 vectors, every lane owns one cell, which stays in registers through the main pass and all
+// lazy-F passes and is written once.  Exactly the nBlocks == 1 case of the general row loop in sg_warp_ag_compute, in a
+// function of its own so that its loop carries no state of the other cases (registers: the kernels run at 64 per thread,
+// and the general function spills inside its loops) and its code is one small contiguous piece.
+__device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int open, int ext, int dir, const uint8_t *text, int textLen, int patternLen,
+                                                     int w, int scoreInit, SgAgLayout &lay, uint8_t *bt, int lane, SgAgBests *res)
+{
+    const int numVec = lay.numVec, segLen = lay.segLen;
+    const int stride = lay.rowStride();
+    const int l = lane & 7, q = lane >> 3;
+    int16_t *Hptr = S.agH, *Hm1ptr = S.agHm1, *E = S.agE;
+    const int8_t *prof = S.agProf;
+    int bestG = -1, bestGT = -1, bestL = -1, bestLT = -1, bestLP = -1;
+    const int globalIdx = lay.cellIndex(patternLen - 1);
+    int segBegTrack = 0, segEndTrack = ((w < patternLen - 1) ? w : (patternLen - 1)) / segLen;
+    const int laneUp = (lane & 24) | ((l + 7) & 7);
+
+    #pragma unroll 1
+    for (int i = 0; i < textLen; i++) {
+        const uint32_t tb = sg_base_value(text[i * dir]);
+        uint8_t *btRow = bt + (size_t)i * stride;
+        const int8_t *profRow = prof + tb * stride;
+        int myMax = 0, myMaxCol = -1, X0 = 0;
+        const int bandBeg = (i - w) > 0 ? (i - w) : 0;
+        const int bandEnd = (i + w) < (patternLen - 1) ? (i + w) : (patternLen - 1);
+        while (bandBeg >= (segBegTrack + 1) * segLen) segBegTrack++;
+        while (bandEnd >= (segEndTrack + 1) * segLen) segEndTrack++;
+
+        #pragma unroll 1
+        for (int j = segBegTrack; j <= segEndTrack; j++) {
+            const int vbase = j * numVec;
+            int nVecHere = bandEnd - j * segLen + 1;
+            if (nVecHere > numVec) nVecHere = numVec;
+            if (nVecHere < 0) nVecHere = 0;
+            int hInit;
+            if (j == 0) {
+                hInit = scoreInit;
+                if (i > 0) { hInit = scoreInit - open - (i - 1) * ext; if (hInit < 0) hInit = 0; }
+            } else {
+                hInit = (bandBeg > j * segLen) ? 0 : (int)Hptr[(vbase - 1) * SG_VEC + (SG_VEC - 1)];
+            }
+            const int fcarry = (j > segBegTrack) ? (l == 0 ? X0 : 0) : 0;       // (X0, 0, ..., 0) passed on from the previous segment (:572)
+            const bool valid = q < nVecHere;
+            const int idx = (vbase + q) * SG_VEC + l;
+            int temp = 0, h = 0, act = 0;
+            if (valid) {
+                int hdiag;
+                if (q == 0) hdiag = (l == 0) ? hInit : (int)Hptr[(vbase + numVec - 1) * SG_VEC + l - 1];
+                else hdiag = Hptr[idx - SG_VEC];
+                const int pv = profRow[idx];
+                const int m = (hdiag > 0) ? sg_sat16(hdiag + (pv == -128 ? -32768 : pv)) : 0;
+                const int e = E[idx];
+                act = (e > m) ? 1 : 0;
+                h = m > e ? m : e;
+                const int e2 = sg_sat16(e - ext);
+                temp = sg_sat16(m - open); if (temp < 0) temp = 0;
+                if (e2 > temp) act |= 4;
+                E[idx] = (int16_t)(e2 > temp ? e2 : temp);
+            }
+            const int t0 = sg_shfl(temp, l), t1 = sg_shfl(temp, 8 + l), t2 = sg_shfl(temp, 16 + l), t3 = sg_shfl(temp, 24 + l);
+            int fin = fcarry - q * ext;
+            if (q > 0) { int v = t0 - (q - 1) * ext; if (v > fin) fin = v; }
+            if (q > 1) { int v = t1 - (q - 2) * ext; if (v > fin) fin = v; }
+            if (q > 2) { int v = t2; if (v > fin) fin = v; }
+            if (valid) {
+                if (fin > h) { act |= 2; h = fin; }
+                if (sg_sat16(fin - ext) > temp) act |= 32;
+            }
+            int fl = fcarry - nVecHere * ext;            // f register of SSE lane l after the main pass
+            { int v = t0 - (nVecHere - 1) * ext; if (nVecHere > 0 && v > fl) fl = v; }
+            { int v = t1 - (nVecHere - 2) * ext; if (nVecHere > 1 && v > fl) fl = v; }
+            { int v = t2 - (nVecHere - 3) * ext; if (nVecHere > 2 && v > fl) fl = v; }
+            { int v = t3 - (nVecHere - 4) * ext; if (nVecHere > 3 && v > fl) fl = v; }
+            if (fl < 0) fl = 0;
+            const unsigned validBytes = nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u);
+            #pragma unroll 1
+            for (int kk = 0; kk < SG_VEC - 1; kk++) {
+                { const int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
+                { const int up = sg_shfl(fl, laneUp); fl = (l == 0) ? 0 : up; }
+                int fv = fl - q * ext; if (fv < 0) fv = 0;
+                const bool a2 = valid && fv > h;
+                const int newh = a2 ? fv : h;
+                int tmp2 = newh - open; if (tmp2 < 0) tmp2 = 0;
+                int fn = fv - ext; if (fn < 0) fn = 0;
+                const bool live = valid && fn > tmp2;
+                const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+                const unsigned zb = (liveMask - 0x01010101u) & ~liveMask & 0x80808080u & validBytes;
+                const int firstConv = zb ? ((__ffs(zb) - 1) >> 3) : 4;
+                if (q <= firstConv) { h = newh; act |= (a2 ? 2 : 0) | (live ? 32 : 0); }
+                if (firstConv < 4) break;
+                fl = fl - nVecHere * ext; if (fl < 0) fl = 0;
+            }
+            if (valid) {
+                const int col = j * segLen + l * numVec + q;
+                if (h > myMax || (h == myMax && col > myMaxCol)) { myMax = h; myMaxCol = col; }
+                Hm1ptr[idx] = (int16_t)h;
+                btRow[idx] = (uint8_t)act;
+            }
+            __syncwarp();
+        }
+
+        const int maxScoreRow = __reduce_max_sync(0xffffffffu, myMax);
+        if (bandEnd == patternLen - 1) {
+            const int globalAlignmentScore = Hm1ptr[globalIdx];
+            if (globalAlignmentScore >= bestG) { bestG = globalAlignmentScore; bestGT = i; }
+        }
+        lay.nRows = i + 1;
+        if (maxScoreRow == 0) break;
+        if (maxScoreRow > bestL) {
+            bestL = maxScoreRow; bestLT = i;
+            bestLP = __reduce_max_sync(0xffffffffu, (myMax == maxScoreRow) ? myMaxCol : -1);
+        }
+        int16_t *tmp = Hm1ptr; Hm1ptr = Hptr; Hptr = tmp;
+    }
+    __syncwarp();
+    res->gScore = bestG; res->gText = bestGT; res->lScore = bestL; res->lText = bestLT; res->lPat = bestLP;
+}
+
+
 __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParams &P, int dir, bool banded,
                                                 const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
                                                 int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out, int lane)
@@ -93,6 +213,14 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         for (uint32_t t = 0; t < 5; t++) prof[t * stride + idx] = (pb == 5u) ? (int8_t)-128 : (int8_t)sg_ag_sub(P, t, pb);
     }
     __syncwarp();
+
+    if (banded && numVec <= 4) {
+        SgAgBests bb;
+        sg_warp_ag_rows_banded4(S, open, ext, dir, text, textLen, patternLen, w, scoreInit, lay, bt, lane, &bb);
+        sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
+                     bb.lScore, bb.lText, bb.lPat, bb.gScore, bb.gText, out);
+        return;
+    }
 
     int bestGlobalAlignmentScore = -1, bestGlobalAlignmentTextOffset = -1;
     int bestLocalAlignmentScore = -1, bestLocalAlignmentTextOffset = -1, bestLocalAlignmentPatternOffset = -1;
