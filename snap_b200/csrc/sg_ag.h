@@ -11,7 +11,8 @@
 
 struct SgAgParams {
     int matchReward, subPenalty /* negative */, gapOpenPenalty /* open+extend */, gapExtendPenalty, fivePrimeEndBonus, threePrimeEndBonus;
-    int usePacked;                   // device: take the packed s16x2 form for unbanded problems (results are identical either way)
+    int usePacked;                   // device: take the specialised forms (packed s16x2 for unbanded problems, sg_warp_ag_rows_banded4 for
+                                     // narrow bands); results are identical either way, which is faster depends on the kernel
 };
 
 SG_HD SgAgParams sg_ag_params(int matchReward, int subPenalty, int gapOpen, int gapExtend, int five, int three)

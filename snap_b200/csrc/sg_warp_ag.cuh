@@ -214,7 +214,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
     }
     __syncwarp();
 
-    if (banded && numVec <= 4) {
+    if (banded && numVec <= 4 && P.usePacked) {      // (same switch as the packed form: measured +10 % for pairs, -3 % for single-end)
         SgAgBests bb;
         sg_warp_ag_rows_banded4(S, open, ext, dir, text, textLen, patternLen, w, scoreInit, lay, bt, lane, &bb);
         sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
