@@ -238,6 +238,9 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a);
  * bases/quals: concatenated clipped views (Read::getData()/getQuality(), upper-cased), read i at
  * [offsets[i], offsets[i]+lens[i]).  HOST pointers; copies are done inside.  results[n] caller-owned.
  * counters may be NULL; when given it is *accumulated into*.
+ * Page-locked buffers (cudaHostAlloc / cudaHostRegister) are detected and used for DMA directly -- reads that sit back to
+ * back in pinned bases/quals skip the staging copy, pinned results are written in place; pageable memory works the same,
+ * through the handle's own pinned staging.
  */
 int  snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals,
                           const uint64_t *offsets, const uint32_t *lens,

@@ -1013,14 +1013,15 @@ int snapgpu_align_paired_device(snapgpu_aligner *a, int64_t nPairs, const char *
 }
 
 // Drains a pipeline slot: waits for its D2H copy and hands the results to the caller's buffer.
-static int drain_slot(snapgpu_aligner *a, int k, uint8_t *results, size_t resultBytesPerUnit)
+static int drain_slot(snapgpu_aligner *a, int k, uint8_t *results, size_t resultBytesPerUnit, bool resultsPinned)
 {
     snapgpu_aligner::Slot &sl = a->slot[k];
     if (sl.pendingCount == 0) return 0;
     SG_CUDA(cudaEventSynchronize(sl.evOut));
-    memcpy(results + (size_t)sl.pendingFirst * resultBytesPerUnit, sl.h_results, (size_t)sl.pendingCount * resultBytesPerUnit);
+    uint8_t *dst = results + (size_t)sl.pendingFirst * resultBytesPerUnit;
+    if (!resultsPinned) memcpy(dst, sl.h_results, (size_t)sl.pendingCount * resultBytesPerUnit);      // (pinned: the DMA wrote them in place)
     if (!a->paired) {
-        const snapgpu_single_result *r = (const snapgpu_single_result *)sl.h_results;
+        const snapgpu_single_result *r = (const snapgpu_single_result *)dst;
         for (int64_t i = 0; i < sl.pendingCount; i++) {
             if (r[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
         }
@@ -1038,12 +1039,21 @@ static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size
     const int64_t n = nUnits * readsPerUnit;
     SG_CUDA(cudaSetDevice(a->device));
     SG_CUDA(cudaMemsetAsync(a->d_counters, 0, sizeof(snapgpu_counters), a->stream));
+    bool callerPinned = false, resultsPinned = false;
+    {
+        cudaPointerAttributes pa, pq, pr;
+        if (cudaPointerGetAttributes(&pa, bases) == cudaSuccess && cudaPointerGetAttributes(&pq, quals) == cudaSuccess) {
+            callerPinned = pa.type == cudaMemoryTypeHost && pq.type == cudaMemoryTypeHost;
+        }
+        if (cudaPointerGetAttributes(&pr, results) == cudaSuccess) resultsPinned = pr.type == cudaMemoryTypeHost;
+        cudaGetLastError();          // an unregistered pointer is not an error for us
+    }
     int64_t done = 0;
     int c = 0;
     while (done < n) {
         const int k = c & 1;
         snapgpu_aligner::Slot &sl = a->slot[k];
-        if (drain_slot(a, k, results, resultBytesPerUnit)) return 1;                    // slot k was used by chunk c-2
+        if (drain_slot(a, k, results, resultBytesPerUnit, resultsPinned)) return 1;     // slot k was used by chunk c-2
         int64_t m = 0; size_t total = 0;
         while (done + m < n && m < a->chunkReads) {
             size_t unitBases = 0;
@@ -1062,9 +1072,13 @@ static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size
         if (m == 0) return sg_fail("a read does not fit the aligner's staging buffers");
         // reads that are back to back in the caller's buffers (the common case) are packed with one memcpy each way
         const uint64_t first = offsets[done];
+        const char *src_b = sl.h_bases, *src_q = sl.h_quals;
         bool contiguous = true;
         for (int64_t i = 0; i < m; i++) { if (offsets[done + i] != first + sl.h_offsets[i]) { contiguous = false; break; } }
-        if (contiguous) {
+        if (contiguous && callerPinned) {
+            // the caller's buffers are page-locked: DMA straight out of them, no staging copy
+            src_b = bases + first; src_q = quals + first;
+        } else if (contiguous) {
             memcpy(sl.h_bases, bases + first, total);
             memcpy(sl.h_quals, quals + first, total);
         } else {
@@ -1073,8 +1087,8 @@ static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size
                 memcpy(sl.h_quals + sl.h_offsets[i], quals + offsets[done + i], sl.h_lens[i]);
             }
         }
-        SG_CUDA(cudaMemcpyAsync(sl.d_bases, sl.h_bases, total, cudaMemcpyHostToDevice, a->streamIn));
-        SG_CUDA(cudaMemcpyAsync(sl.d_quals, sl.h_quals, total, cudaMemcpyHostToDevice, a->streamIn));
+        SG_CUDA(cudaMemcpyAsync(sl.d_bases, src_b, total, cudaMemcpyHostToDevice, a->streamIn));
+        SG_CUDA(cudaMemcpyAsync(sl.d_quals, src_q, total, cudaMemcpyHostToDevice, a->streamIn));
         SG_CUDA(cudaMemcpyAsync(sl.d_offsets, sl.h_offsets, (size_t)m * 8, cudaMemcpyHostToDevice, a->streamIn));
         SG_CUDA(cudaMemcpyAsync(sl.d_lens, sl.h_lens, (size_t)m * 4, cudaMemcpyHostToDevice, a->streamIn));
         SG_CUDA(cudaEventRecord(sl.evIn, a->streamIn));
@@ -1083,14 +1097,15 @@ static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size
         if (launch_align(a, units, sl.d_bases, sl.d_quals, sl.d_offsets, sl.d_lens, sl.d_results, a->d_counters, a->stream)) return 1;
         SG_CUDA(cudaEventRecord(sl.evKernel, a->stream));
         SG_CUDA(cudaStreamWaitEvent(a->streamOut, sl.evKernel, 0));
-        SG_CUDA(cudaMemcpyAsync(sl.h_results, sl.d_results, (size_t)units * resultBytesPerUnit, cudaMemcpyDeviceToHost, a->streamOut));
+        SG_CUDA(cudaMemcpyAsync(resultsPinned ? (void *)(results + (size_t)(done / readsPerUnit) * resultBytesPerUnit) : (void *)sl.h_results, sl.d_results,
+                                (size_t)units * resultBytesPerUnit, cudaMemcpyDeviceToHost, a->streamOut));
         SG_CUDA(cudaEventRecord(sl.evOut, a->streamOut));
         sl.pendingFirst = done / readsPerUnit; sl.pendingCount = units;
         done += m;
         c++;
     }
-    if (drain_slot(a, c & 1, results, resultBytesPerUnit)) return 1;
-    if (drain_slot(a, (c + 1) & 1, results, resultBytesPerUnit)) return 1;
+    if (drain_slot(a, c & 1, results, resultBytesPerUnit, resultsPinned)) return 1;
+    if (drain_slot(a, (c + 1) & 1, results, resultBytesPerUnit, resultsPinned)) return 1;
     SG_CUDA(cudaMemcpyAsync(a->h_counters, a->d_counters, sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, a->stream));
     SG_CUDA(cudaStreamSynchronize(a->stream));
     if (a->paired && snapgpu_aligner_check(a, nullptr)) return 1;

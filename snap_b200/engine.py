@@ -241,9 +241,10 @@ class SingleAligner:
         self.handle = h
         self.max_batch_reads = max_batch_reads
 
-    def align(self, batch):
-        """Host buffers in, host results out (copies inside): snapgpu_align_single."""
-        res = np.zeros(batch.n, dtype=RESULT_DTYPE)
+    def align(self, batch, out=None):
+        """Host buffers in, host results out (copies inside): snapgpu_align_single.  `out`: optional preallocated result
+        array (e.g. a view of page-locked memory, which the library then DMAs into directly)."""
+        res = np.zeros(batch.n, dtype=RESULT_DTYPE) if out is None else out[:batch.n]
         ctr = np.zeros(N_COUNTERS, dtype=np.int64)
         done = 0
         while done < batch.n:
@@ -282,10 +283,10 @@ class PairedAligner:
         self.handle = h
         self.max_batch_pairs = max_batch_pairs
 
-    def align(self, batch):
-        """Host buffers in, host results out (copies inside): snapgpu_align_paired."""
+    def align(self, batch, out=None):
+        """Host buffers in, host results out (copies inside): snapgpu_align_paired.  `out` as in SingleAligner.align."""
         n_pairs = batch.n // 2
-        res = np.zeros(n_pairs, dtype=PAIRED_RESULT_DTYPE)
+        res = np.zeros(n_pairs, dtype=PAIRED_RESULT_DTYPE) if out is None else out[:n_pairs]
         ctr = np.zeros(N_COUNTERS, dtype=np.int64)
         done = 0
         while done < n_pairs:

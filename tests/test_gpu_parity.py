@@ -418,3 +418,17 @@ def test_fastq_ingest_matches_reference_reader(engine, small_cfg, reflib, golden
     r2, _ = al.align(rb)
     assert r1.tobytes() == r2.tobytes()
     al.close(); ix.close(); fq.close(); small.close()
+
+
+def test_pinned_host_buffers_give_the_same_results(engine, gidx, small_cfg):
+    """Page-locked inputs / results are DMA'd directly (no staging copies): same records as the pageable path."""
+    import torch
+    from snap_b200 import synth
+    rb = synth.make_reads(small_cfg.contigs, 20000, 150, seed=88)
+    al = engine.SingleAligner(gidx, engine.default_params(maxDist=14), 1 << 15)
+    want, wc = al.align(rb)
+    pb = synth.ReadBatch(torch.from_numpy(rb.bases).pin_memory().numpy(), torch.from_numpy(rb.quals).pin_memory().numpy(), rb.offsets, rb.lens)
+    out = torch.empty((rb.n * engine.RESULT_DTYPE.itemsize,), dtype=torch.uint8).pin_memory().numpy().view(engine.RESULT_DTYPE)
+    got, gc = al.align(pb, out=out)
+    assert got.tobytes() == want.tobytes() and gc == wc
+    al.close()
