@@ -1,6 +1,6 @@
 """AG leaf micro-benchmark: realistic jobs (read tails vs the reference window), warp form, packed vs generic builds."""
 import os, sys
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests'))
 import numpy as np
 import jobs as J
 from snap_b200 import engine, synth
