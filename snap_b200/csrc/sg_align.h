@@ -188,6 +188,7 @@ struct SgAligner {
     int64_t invalidLocation;
     // candidatesForAffineGap of the Hamming pass (only the paired caller provides a buffer)
     snapgpu_single_result *agCands; int nAgCands, maxAgCands; int agCandsOverflow;
+    int deferred;                    // set by the DEFER instantiation when the read needs affine-gap scoring (see sg_align_read_t)
 
     // ---- weight lists: doubly linked FIFO per weight; link values are element indices or SG_SENTINEL+w ----
     SG_HD uint32_t getNext(uint32_t n) const { return (n & SG_SENTINEL) ? sc.listNext[n & ~SG_SENTINEL] : sc.pool[n].weightNext; }
@@ -322,8 +323,10 @@ struct SgCandScore {
     int basesClippedBefore, basesClippedAfter, agScore;
 };
 
-// HAM: the Hamming / gapless pass (AlignRead(..., useHamming = true)); a template parameter so that the stock pass carries none of its code
-template <bool HAM>
+// HAM: the Hamming / gapless pass (AlignRead(..., useHamming = true)); a template parameter so that the stock pass carries none of its code.
+// DEFER: an instantiation WITHOUT the affine-gap code: at the point where the reference would rescore with affine gap it sets
+// A.deferred and unwinds; the caller then aligns that read again from scratch with the full instantiation (two-pass launch).
+template <bool HAM, bool DEFER>
 SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLocationIn, int seedOffset, int scoreLimitForThisElement, SgCandScore *o)
 {
     const bool useHamming = HAM;
@@ -393,6 +396,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
         if (!useHamming && score1 != SG_SCORE_ABOVE_LIMIT && score2 != SG_SCORE_ABOVE_LIMIT) {
             // :1203
             if (pr.noEditDistance || (pr.useAffineGap && (score1 + score2 > maxKForSameAlignment && el.lowestPossibleScore <= (unsigned)A.all.bestScore))) {
+                if (DEFER) { A.deferred = 1; return; }
                 score1 = 0; score2 = 0; agScore1 = seedLen; agScore2 = 0;
                 usedAffineGapScoring = 1;
                 A.work.agCalls++;
@@ -447,7 +451,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
 }
 
 // BaseAligner::score (:917-1534).  Returns true iff a result was reached.
-template <bool HAM>
+template <bool HAM, bool DEFER>
 SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult)
 {
     const bool useHamming = HAM;
@@ -520,7 +524,8 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                 bool genomeLocationIsNonALT = (!pr.altAwareness) || !A.isALT(genomeLocation);
 
                 SgCandScore cs;
-                sg_score_candidate<HAM>(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, &cs);
+                sg_score_candidate<HAM, DEFER>(A, el, genomeLocation, (int)el.candSeedOffset[candidateIndexToScore], scoreLimitForThisElement, &cs);
+                if (DEFER && A.deferred) return true;
                 unsigned score = cs.score;
                 double matchProbability = cs.matchProbability;
                 genomeLocation = cs.genomeLocation;
@@ -609,7 +614,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
 
 // BaseAligner::AlignRead (:272-763) for one read with the stock loop's arguments (SingleAligner.cpp:250).
 // `result` must be caller-zeroed POD; on return it holds what the reference would have put in primaryResult.
-template <bool HAM>
+template <bool HAM, bool DEFER = false>
 SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult)
 {
     const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
@@ -638,6 +643,7 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
     A.popularSeedsSkipped = 0;
     A.nAddedToHashTable = 0;
     A.readLen = readLen;
+    if (DEFER) A.deferred = 0;
 
     if ((int)readLen < (int)seedLen) {
         return;                      // :360-366, "hopeless"
@@ -710,7 +716,7 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
         if (nextSeedToTest >= nPossibleSeeds) {
             A.wrapCount++;
             if (A.wrapCount >= seedLen) {
-                sg_score<HAM>(A, true, primaryResult);
+                sg_score<HAM, DEFER>(A, true, primaryResult);
                 primaryResult->scorePriorToClipping = primaryResult->score;     // finalizeSecondaryResults, :2442
                 return;
             }
@@ -771,13 +777,13 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
         nextSeedToTest += seedLen;
 
         if (appliedEitherSeed) {
-            if (sg_score<HAM>(A, false, primaryResult)) {
+            if (sg_score<HAM, DEFER>(A, false, primaryResult)) {
                 primaryResult->scorePriorToClipping = primaryResult->score;
                 return;
             }
         }
     }
-    sg_score<HAM>(A, true, primaryResult);
+    sg_score<HAM, DEFER>(A, true, primaryResult);
     primaryResult->scorePriorToClipping = primaryResult->score;
 }
 

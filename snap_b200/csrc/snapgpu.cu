@@ -62,6 +62,7 @@ struct snapgpu_aligner {
     // paired-end handle (snapgpu_paired_aligner_create): `params` drives the intersecting aligner, `paramsSingle` the
     // single-end fallback aligner; a worker's arena = [single scratch | paired scratch]
     bool paired = false;
+    bool twoPass = false;                // single-end: MODE 1 + MODE 2 launches of sg_align_kernel instead of one MODE 0
     SgParams paramsSingle;
     SgPairedParams pparams;
     size_t singleScratchBytes = 0;
@@ -77,6 +78,7 @@ struct snapgpu_aligner {
     int device = 0;
     int numSMs = 0;
     int warpsPerBlock = 8, blocksPerSM = 4;
+    int pass1BlocksPerSM = 4;            // resident CTAs per SM of the first (no affine gap) pass of the two-pass single-end launch
     int nWorkers = 0;
     size_t scratchBytesPerWorker = 0;
     uint8_t *d_scratch = nullptr;
@@ -164,12 +166,20 @@ sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_
 // and split the work inside the data-parallel leaves (hash-chain probing of both strands, ...).
 // The register budget (and with it the number of resident warps per SM) is a template parameter so that the host can
 // pick the occupancy that measures best: MB CTAs of 8 warps per SM.
-template <int MB>
+//
+// MODE 0: the whole of AlignRead for reads [0, n).
+// MODE 1 / MODE 2, the two-pass form used when affine gap is on: only ~1 read in 4 ever reaches the affine-gap rescoring, yet
+//   that code is most of the kernel's instruction footprint, and the kernel is bound by instruction supply.
+//   MODE 1 is an instantiation without the affine-gap code: it finishes the reads that never need it and appends the others,
+//   at the moment they first would, to deferList.  MODE 2 (full code) then aligns deferList[0, *deferCount) from scratch.
+//   Results are those of MODE 0 by construction (a deferred read's partial work is discarded, counters included).
+template <int MB, int MODE>
 __global__ void __launch_bounds__(256, MB)
 sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratchBase, size_t scratchBytesPerWorker,
                 long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
-                snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next)
+                snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next, unsigned long long *deferCount, uint32_t *deferList)
 {
+    if (MODE == 2) n = (long long)*deferCount;
     const int lane = threadIdx.x & 31;
     const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
@@ -189,12 +199,13 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
         if (lane == 0) i = atomicAdd(next, 1ULL);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= (unsigned long long)n) break;
+        if (MODE == 2) i = deferList[i];
         const uint8_t *rd = bases + offsets[i];
         const uint8_t *rq = quals + offsets[i];
         const uint32_t len = lens[i];
         snapgpu_single_result r;
         memset(&r, 0, sizeof(r));
-        cTotal++;
+        if (MODE != 2) cTotal++;
         uint32_t countOfNs = 0;
         #pragma unroll 1
         for (uint32_t k = lane; k < len; k += 32) countOfNs += (rd[k] == 'N');
@@ -208,7 +219,17 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
             if (lane == 0) results[i] = r;
             continue;
         }
-        sg_align_read(A, rd, rq, len, &r);
+        if (MODE == 1) {
+            const SgWork workBefore = A.work;
+            sg_align_read_t<false, true>(A, rd, rq, len, &r);
+            if (A.deferred) {
+                if (lane == 0) deferList[atomicAdd(deferCount, 1ULL)] = (uint32_t)i;
+                A.work = workBefore;
+                continue;
+            }
+        } else {
+            sg_align_read(A, rd, rq, len, &r);
+        }
         if (lane == 0) results[i] = r;
         if (r.status == SNAPGPU_SINGLE_HIT) cSingle++;
         else if (r.status == SNAPGPU_MULTIPLE_HITS) cMulti++;
@@ -459,7 +480,7 @@ static int require_device(int device)
     if (device < 0 || device >= n) return sg_fail("CUDA device ordinal out of range");
     SG_CUDA(cudaSetDevice(device));
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, sg_align_kernel<2>);
+    e = cudaFuncGetAttributes(&fa, sg_align_kernel<2, 0>);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return sg_fail(std::string("no sm_100a kernel image usable on this device: ") + cudaGetErrorString(e));
@@ -782,7 +803,10 @@ static int aligner_init_common(snapgpu_aligner *a, int64_t maxBatchReads, int64_
     if (const char *e = getenv(blocksEnv)) a->blocksPerSM = atoi(e) > 0 ? atoi(e) : defaultBlocksPerSM;
     if (a->blocksPerSM < 2) a->blocksPerSM = 2;
     if (a->blocksPerSM > 4) a->blocksPerSM = 4;
-    a->nWorkers = a->numSMs * a->blocksPerSM * a->warpsPerBlock;
+    a->pass1BlocksPerSM = 8;             // measured (M reads/s, 3 Gbp, 150 bp): 4 -> 13.49, 5 -> 13.66, 6 -> 13.75, 8 -> 13.94 (32 registers, no extra spills)
+    if (const char *e = getenv("SNAPGPU_PASS1_BLOCKS_PER_SM")) a->pass1BlocksPerSM = atoi(e);
+    if (a->pass1BlocksPerSM < 3 || a->pass1BlocksPerSM > 8 || a->pass1BlocksPerSM == 7 || readsPerUnit != 1) a->pass1BlocksPerSM = a->blocksPerSM;
+    a->nWorkers = a->numSMs * (a->blocksPerSM > a->pass1BlocksPerSM ? a->blocksPerSM : a->pass1BlocksPerSM) * a->warpsPerBlock;
     if ((int64_t)a->nWorkers > maxUnits) {
         int blocks = (int)((maxUnits + a->warpsPerBlock - 1) / a->warpsPerBlock);
         a->nWorkers = blocks * a->warpsPerBlock;
@@ -843,6 +867,18 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     if (!sg_derive_params(*params, idx->view.seedLen, env_max_read_len(), a->params, err)) { delete a; return sg_fail("snapgpu_aligner_create: " + err); }
     if (aligner_init_common(a, maxBatchReads, maxBatchReads, sg_align_up(sg_scratch_bytes(a->params), 256), sizeof(snapgpu_single_result), 1, 4,
                             "SNAPGPU_BLOCKS_PER_SM")) { snapgpu_aligner_destroy(a); return 1; }
+    // two-pass launch (see sg_align_kernel) whenever some reads can finish without affine gap: not under -ne (every
+    // candidate is rescored) ; without affine gap at all the first pass simply finishes everything.  SNAPGPU_TWO_PASS=0 turns it off.
+    a->twoPass = !a->params.noEditDistance;
+    if (const char *e = getenv("SNAPGPU_TWO_PASS")) a->twoPass = atoi(e) != 0;
+    if (a->twoPass) {
+        if (cudaMalloc((void **)&a->d_retryList, (size_t)maxBatchReads * 4) != cudaSuccess ||
+            cudaMalloc((void **)&a->d_retryCount, 8) != cudaSuccess || cudaMalloc((void **)&a->d_next2, 8) != cudaSuccess) {
+            std::string msg = std::string("snapgpu_aligner_create: deferred-read list: ") + cudaGetErrorString(cudaGetLastError());
+            snapgpu_aligner_destroy(a);
+            return sg_fail(msg);
+        }
+    }
     *out = a;
     return 0;
 }
@@ -934,15 +970,43 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
                         const uint32_t *d_lens, void *d_results, snapgpu_counters *d_counters, cudaStream_t st)
 {
     SG_CUDA(cudaMemsetAsync(a->d_next, 0, 8, st));
-    int64_t workers = a->nWorkers;
+    int64_t workers = (int64_t)a->numSMs * a->blocksPerSM * a->warpsPerBlock;
+    if (workers > a->nWorkers) workers = a->nWorkers;
     if (workers > n) workers = n;
     int blocks = (int)((workers + a->warpsPerBlock - 1) / a->warpsPerBlock);
     if (blocks < 1) blocks = 1;
     if (!a->paired) {
-#define SG_LAUNCH(MB) sg_align_kernel<MB><<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, \
+#define SG_LAUNCH(MB, MODE, GRID, NEXT) sg_align_kernel<MB, MODE><<<GRID, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, \
         a->d_scratch, a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, \
-        d_lens, (snapgpu_single_result *)d_results, d_counters, a->d_next)
-        if (a->blocksPerSM >= 4) SG_LAUNCH(4); else if (a->blocksPerSM == 3) SG_LAUNCH(3); else SG_LAUNCH(2);
+        d_lens, (snapgpu_single_result *)d_results, d_counters, NEXT, a->d_retryCount, a->d_retryList)
+#define SG_LAUNCH_MB(MODE, GRID, NEXT) if (a->blocksPerSM >= 4) SG_LAUNCH(4, MODE, GRID, NEXT); else if (a->blocksPerSM == 3) SG_LAUNCH(3, MODE, GRID, NEXT); \
+        else SG_LAUNCH(2, MODE, GRID, NEXT)
+        if (a->twoPass) {
+            SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));
+            SG_CUDA(cudaMemsetAsync(a->d_next2, 0, 8, st));
+            int64_t w1 = (int64_t)a->numSMs * a->pass1BlocksPerSM * a->warpsPerBlock;
+            if (w1 > n) w1 = n;
+            if (w1 > a->nWorkers) w1 = a->nWorkers;
+            int grid1 = (int)((w1 + a->warpsPerBlock - 1) / a->warpsPerBlock);
+            if (grid1 < 1) grid1 = 1;
+            switch (a->pass1BlocksPerSM) {
+                case 8: SG_LAUNCH(8, 1, grid1, a->d_next); break;
+                case 6: SG_LAUNCH(6, 1, grid1, a->d_next); break;
+                case 5: SG_LAUNCH(5, 1, grid1, a->d_next); break;
+                case 3: SG_LAUNCH(3, 1, grid1, a->d_next); break;
+                default: SG_LAUNCH(4, 1, grid1, a->d_next); break;
+            }
+            SG_CUDA(cudaGetLastError());
+            a->launches++;
+            int64_t w2 = (int64_t)a->numSMs * a->blocksPerSM * a->warpsPerBlock;
+            if (w2 > n) w2 = n;
+            int grid2 = (int)((w2 + a->warpsPerBlock - 1) / a->warpsPerBlock);
+            if (grid2 < 1) grid2 = 1;
+            SG_LAUNCH_MB(2, grid2, a->d_next2);
+        } else {
+            SG_LAUNCH_MB(0, blocks, a->d_next);
+        }
+#undef SG_LAUNCH_MB
 #undef SG_LAUNCH
     } else {
         SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));

@@ -24,6 +24,8 @@ struct HsAligner {
     SgTables tables;
     std::vector<uint8_t> scratch;
     SgAligner A;
+    bool twoPass = false;
+    int64_t deferredReads = 0;
 };
 
 static std::string g_err;
@@ -156,6 +158,8 @@ void *hs_aligner_create(void *vix, const snapgpu_params *params, uint32_t maxRea
 }
 
 void hs_aligner_destroy(void *v) { delete (HsAligner *)v; }
+void hs_aligner_set_two_pass(void *v, int on) { ((HsAligner *)v)->twoPass = on != 0; }
+int64_t hs_aligner_deferred(void *v) { return ((HsAligner *)v)->deferredReads; }
 
 // Same contract as snapgpu_align_single: pre-filter (SingleAligner.cpp:213), AlignRead, stats.
 int hs_align_single(void *v, int64_t n, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
@@ -177,7 +181,18 @@ int hs_align_single(void *v, int64_t n, const char *bases, const char *quals, co
             if (ctr) ctr->uselessReads++;
             continue;
         }
-        sg_align_read(a->A, rd, rq, lens[i], r);
+        if (a->twoPass) {
+            // the two-pass launch of sg_align_kernel: the instantiation without affine gap first, and the read again from scratch if it bailed out
+            const SgWork before = a->A.work;
+            sg_align_read_t<false, true>(a->A, rd, rq, lens[i], r);
+            if (a->A.deferred) {
+                a->A.work = before; a->deferredReads++;
+                memset(r, 0, sizeof(*r));
+                sg_align_read(a->A, rd, rq, lens[i], r);
+            }
+        } else {
+            sg_align_read(a->A, rd, rq, lens[i], r);
+        }
         if (ctr) {
             if (r->status == SNAPGPU_SINGLE_HIT) ctr->singleHits++;
             else if (r->status == SNAPGPU_MULTIPLE_HITS) ctr->multiHits++;

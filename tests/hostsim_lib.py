@@ -48,6 +48,9 @@ def lib():
         L.hs_aligner_create.restype = C.c_void_p
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
+        L.hs_aligner_set_two_pass.argtypes = [C.c_void_p, C.c_int]
+        L.hs_aligner_deferred.restype = C.c_int64
+        L.hs_aligner_deferred.argtypes = [C.c_void_p]
         L.hs_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.hs_paired_create.restype = C.c_void_p
         L.hs_paired_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -84,6 +87,13 @@ class HsAligner:
         self.handle = lib().hs_aligner_create(index.handle, ctypes.byref(params), max_read_len)
         if not self.handle:
             raise RuntimeError(lib().hs_last_error().decode())
+
+    def set_two_pass(self, on: bool):
+        lib().hs_aligner_set_two_pass(self.handle, 1 if on else 0)
+
+    @property
+    def deferred(self) -> int:
+        return lib().hs_aligner_deferred(self.handle)
 
     def align(self, batch, result_dtype, n_counters):
         res = np.zeros(batch.n, dtype=result_dtype)

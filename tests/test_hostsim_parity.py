@@ -117,6 +117,29 @@ def test_whole_reads_match_reference(reflib, small_cfg, opt):
             assert wctr[k] == g[k], (opt, name, k)
 
 
+@pytest.mark.parametrize("opt", ["default_d14", "ag_d20", "coverage", "esd3_ms2", "nobanded", "stopfirst", "noag_d14"])
+def test_two_pass_form_matches_reference(reflib, small_cfg, opt):
+    """sg_align_kernel's two-pass launch: the instantiation without the affine-gap code, then reads that bailed out of it
+    again from scratch.  ONE aligner is used for every read set, so a bail-out must also leave the scratch state clean."""
+    p = reflib.default_params(**OPTION_SETS[opt])
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    al = hs.HsAligner(hidx, p)
+    al.set_two_pass(True)
+    for name, rb in small_cfg.reads.items():
+        ral = reflib.RefSingleAligner(ridx, p)
+        want, wctr = ral.align(rb)
+        ral.close()
+        got, gctr = al.align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (opt, name)
+        g = reflib.counters_dict(gctr)
+        for k in ("totalReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "nHashEntriesProbed", "lvCalls", "affineGapCalls", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, name, k)
+    if opt == "noag_d14":
+        assert al.deferred == 0
+    else:
+        assert al.deferred > 0
+
+
 def test_large_index_gives_identical_results(reflib, small_cfg):
     p = reflib.default_params(maxDist=14)
     rb = small_cfg.reads["noisy150"]
