@@ -175,7 +175,6 @@ struct SgAligner {
     SgScratch          sc;
     SgAgParams         ag;
     SgWork             work;
-    int                lane;         // 0..31 on the device (all lanes run the state machine uniformly); -1 on the host
     uint32_t           maxK;         // BaseAligner::maxK: pr->maxK unless the paired caller lowered it (setMaxK, BaseAligner.h:118)
 
     // per-read state
@@ -290,14 +289,16 @@ struct SgAligner {
     // clearCandidates (:2331-2339), plus un-marking our lookup table
     SG_HD void clearCandidates() {
 #if defined(__CUDA_ARCH__)
-        if (lane >= 0) {
+        {
+            const uint32_t lane = (uint32_t)sg_lane(), nUsed = nUsedElements, nLists = pr->numWeightLists;
             #pragma unroll 1
-            for (uint32_t i = lane; i < nUsedElements; i += 32) sc.table[sc.pool[i].slot] = 0;
+            for (uint32_t i = lane; i < nUsed; i += 32) sc.table[sc.pool[i].slot] = 0;
             #pragma unroll 1
-            for (uint32_t i = 1 + lane; i < pr->numWeightLists; i += 32) {
+            for (uint32_t i = 1 + lane; i < nLists; i += 32) {
                 sc.listNext[i] = SG_SENTINEL | i;
                 sc.listPrev[i] = SG_SENTINEL | i;
             }
+            __syncwarp();                // (this object is shared by the warp's lanes: no lane may still be reading nUsedElements)
             nUsedElements = 0;
             highestUsedWeightList = 0;
             __syncwarp();
@@ -359,13 +360,13 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
         if (!useHamming) {
             SgLvResult lv;
             sg_lv_compute(T, A.sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart,
-                          scoreLimitForThisElement, &lv, A.lane);
+                          scoreLimitForThisElement, &lv, sg_lane());
             score1 = lv.score; matchProb1 = lv.matchProbability;
             agScore1 = (seedLen + readLen - tailStart - score1) * pr.matchReward - score1 * pr.subPenalty;
             if (score1 != SG_SCORE_ABOVE_LIMIT) {
                 int limitLeft = scoreLimitForThisElement - score1;
                 sg_lv_compute(T, A.sc, -1, data + seedOffset, seedOffset + SG_MAX_K, revRead + readLen - seedOffset, oppQual + readLen - seedOffset,
-                              seedOffset, limitLeft, &lv, A.lane);
+                              seedOffset, limitLeft, &lv, sg_lane());
                 score2 = lv.score; matchProb2 = lv.matchProbability; genomeLocationOffset = lv.netIndel;
                 agScore2 = (seedOffset - score2) * pr.matchReward - score2 * pr.subPenalty;
             }
@@ -406,7 +407,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
                     int patternLen = readLen - tailStart;
                     bool banded = (patternLen >= (3 * (2 * scoreLimitForThisElement + 1))) && !pr.noBandedAffineGap;
                     sg_ag_dispatch(T, A.sc, A.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart,
-                                   patternLen, scoreLimitForThisElement, readLen, dirn != 0, false, &ar, A.lane);
+                                   patternLen, scoreLimitForThisElement, readLen, dirn != 0, false, &ar, sg_lane());
                     agScore1 = ar.agScore; basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
                     agScore1 += (seedLen - readLen);
                 }
@@ -417,7 +418,7 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
                         bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
                         ar.textOffset = genomeLocationOffset; ar.patternOffset = basesClippedBefore; ar.matchProbability = matchProb2;
                         sg_ag_dispatch(T, A.sc, A.ag, -1, banded, data + seedOffset, seedOffset + limitLeft, revRead + readLen - seedOffset,
-                                       oppQual + readLen - seedOffset, seedOffset, limitLeft, readLen, dirn != 0, false, &ar, A.lane);
+                                       oppQual + readLen - seedOffset, seedOffset, limitLeft, readLen, dirn != 0, false, &ar, sg_lane());
                         agScore2 = ar.agScore; genomeLocationOffset = ar.textOffset; basesClippedBefore = ar.patternOffset;
                         score2 = ar.nEdits; matchProb2 = ar.matchProbability;
                         agScore2 -= readLen;
@@ -651,12 +652,12 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
 
     uint32_t countOfNs = 0;
 #if defined(__CUDA_ARCH__)
-    if (A.lane >= 0) {
+    if (sg_lane() >= 0) {
         // the four derived strings (:388-396) are built 32 bases per step; every lane reads all of them afterwards
         #pragma unroll 1
-        for (uint32_t i = A.lane; i < (readLen + 7) / 8; i += 32) A.sc.seedUsed[i] = 0;
+        for (uint32_t i = sg_lane(); i < (readLen + 7) / 8; i += 32) A.sc.seedUsed[i] = 0;
         #pragma unroll 1
-        for (uint32_t i = A.lane; i < readLen; i += 32) {
+        for (uint32_t i = sg_lane(); i < readLen; i += 32) {
             uint8_t baseByte = readData[i];
             uint8_t complement = sg_complement(baseByte);
             A.sc.rcRead[readLen - i - 1] = complement;
@@ -731,8 +732,8 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
         uint64_t sb, srcb;
         SgHits hits;
 #if defined(__CUDA_ARCH__)
-        if (!sg_warp_seed_pack(readData + nextSeedToTest, seedLen, A.lane, &sb, &srcb)) continue;
-        sg_warp_lookup_seed32(ix, sb, srcb, A.lane, &hits, &A.work.entriesProbed, &A.work.overflowWords);
+        if (!sg_warp_seed_pack(readData + nextSeedToTest, seedLen, sg_lane(), &sb, &srcb)) continue;
+        sg_warp_lookup_seed32(ix, sb, srcb, sg_lane(), &hits, &A.work.entriesProbed, &A.work.overflowWords);
 #else
         if (!sg_seed_pack(readData + nextSeedToTest, seedLen, &sb, &srcb)) continue;
         sg_lookup_seed32(ix, sb, srcb, &hits, &A.work.entriesProbed, &A.work.overflowWords);
@@ -820,7 +821,7 @@ SG_HDN void sg_single_score_location_ag(SgAligner &A, int direction, int64_t gen
         bool banded = (patternLen >= (3 * (2 * scoreLimit + 1))) && !pr.noBandedAffineGap;
         ar.textOffset = 0; ar.patternOffset = *basesClippedAfter; ar.nEdits = score1; ar.matchProbability = matchProb1; ar.agScore = -1;
         sg_ag_dispatch(T, A.sc, A.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, patternLen, scoreLimit, readLen,
-                       direction != 0, true, &ar, A.lane);
+                       direction != 0, true, &ar, sg_lane());
         agScore1 = ar.agScore; *basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
         agScore1 += (seedLen - readLen);
         A.work.agCalls++;
@@ -832,7 +833,7 @@ SG_HDN void sg_single_score_location_ag(SgAligner &A, int direction, int64_t gen
             bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
             ar.textOffset = *genomeLocationOffset; ar.patternOffset = *basesClippedBefore; ar.nEdits = score2; ar.matchProbability = matchProb2; ar.agScore = -1;
             sg_ag_dispatch(T, A.sc, A.ag, -1, banded, data + seedOffset, (int)seedOffset + limitLeft, A.sc.revRead[direction] + readLen - seedOffset,
-                           A.readQual[1 - direction] + readLen - seedOffset, patternLen, limitLeft, readLen, direction != 0, false, &ar, A.lane);
+                           A.readQual[1 - direction] + readLen - seedOffset, patternLen, limitLeft, readLen, direction != 0, false, &ar, sg_lane());
             agScore2 = ar.agScore; *genomeLocationOffset = ar.textOffset; *basesClippedBefore = ar.patternOffset; score2 = ar.nEdits; matchProb2 = ar.matchProbability;
             agScore2 -= readLen;
             if (score2 == SG_SCORE_ABOVE_LIMIT) { *score = SG_SCORE_ABOVE_LIMIT; *genomeLocationOffset = 0; *agScore = -1; }

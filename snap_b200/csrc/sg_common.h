@@ -13,6 +13,18 @@
 #define SG_HDN inline
 #endif
 
+// Lane of the calling thread within its warp on the device (all 32 lanes of a warp run one read's state machine uniformly and
+// split the work inside the leaves); -1 in a host build, where the scalar forms of the leaves are used.  The aligner state
+// itself is shared by the warp's lanes (one copy per warp), so the lane cannot be a member of it.
+SG_HD int sg_lane()
+{
+#if defined(__CUDA_ARCH__)
+    return (int)(threadIdx.x & 31u);
+#else
+    return -1;
+#endif
+}
+
 #define SG_MAX_K 127                 // reference LandauVishkin.h:11
 #define SG_N_PADDING 1000            // reference Genome.h:446
 #define SG_MAX_MERGE_DIST 48         // reference BaseAligner.h:177 (also hashTableElementSize, :213)

@@ -333,7 +333,6 @@ struct SgPairedAligner {
     const SgIndexView *ix; const SgParams *pr; const SgPairedParams *pp; const SgTables *tb;
     SgPairedScratch ps;
     SgAgParams ag;
-    int lane;
     int maxK;                        // IntersectingPairedEndAligner::maxK for this call
     const uint8_t *readData[2][2], *readQual[2][2];
     uint32_t readLen[2];
@@ -390,7 +389,7 @@ SG_HDN void sg_paired_score_location_ag(SgPairedAligner &P, uint32_t whichRead, 
         bool banded = (patternLen >= (3 * (2 * scoreLimit + 1))) && !pr.noBandedAffineGap;
         ar.textOffset = textRem; ar.patternOffset = *basesClippedAfter; ar.nEdits = score1; ar.matchProbability = matchProb1; ar.agScore = -1;
         sg_ag_dispatch(T, sc, P.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, patternLen, scoreLimit, readLen,
-                       direction != 0, P.pp->useSoftClip != 0, &ar, P.lane);
+                       direction != 0, P.pp->useSoftClip != 0, &ar, sg_lane());
         agScore1 = ar.agScore; textRem = ar.textOffset; *basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
         agScore1 += (seedLen - readLen);
         P.agCalls++;
@@ -403,7 +402,7 @@ SG_HDN void sg_paired_score_location_ag(SgPairedAligner &P, uint32_t whichRead, 
             ar.textOffset = *genomeLocationOffset; ar.patternOffset = *basesClippedBefore; ar.nEdits = score2; ar.matchProbability = matchProb2; ar.agScore = -1;
             sg_ag_dispatch(T, sc, P.ag, -1, banded, data + seedOffset, (int)seedOffset + limitLeft, P.ps.revRead[whichRead][direction] + readLen - seedOffset,
                            P.readQual[whichRead][1 - direction] + readLen - seedOffset, patternLen, limitLeft, readLen, direction != 0,
-                           P.pp->useSoftClip != 0, &ar, P.lane);
+                           P.pp->useSoftClip != 0, &ar, sg_lane());
             agScore2 = ar.agScore; *genomeLocationOffset = ar.textOffset; *basesClippedBefore = ar.patternOffset; score2 = ar.nEdits; matchProb2 = ar.matchProbability;
             agScore2 -= readLen;
             if (score2 == SG_SCORE_ABOVE_LIMIT) { *score = SG_SCORE_ABOVE_LIMIT; *genomeLocationOffset = 0; *agScore = -1; }
@@ -444,13 +443,13 @@ SG_HDN void sg_paired_score_location(SgPairedAligner &P, uint32_t whichRead, int
     const uint8_t *readToScore = P.readData[whichRead][direction], *qualToScore = P.readQual[whichRead][direction];
     P.lvCalls++;
     SgLvResult lv;
-    sg_lv_compute(T, P.single->sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart, scoreLimit, &lv, P.lane);
+    sg_lv_compute(T, P.single->sc, 1, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, readLen - tailStart, scoreLimit, &lv, sg_lane());
     score1 = lv.score; matchProb1 = lv.matchProbability; totalIndels1 = lv.totalIndels; textSpan1 = lv.textSpan;
     agScore1 = (seedLen + readLen - tailStart - score1) * pr.matchReward - score1 * pr.subPenalty;
     if (score1 != SG_SCORE_ABOVE_LIMIT) {
         int limitLeft = scoreLimit - score1;
         sg_lv_compute(T, P.single->sc, -1, data + seedOffset, (int)seedOffset + SG_MAX_K, P.ps.revRead[whichRead][direction] + readLen - seedOffset,
-                      P.readQual[whichRead][1 - direction] + readLen - seedOffset, (int)seedOffset, limitLeft, &lv, P.lane);
+                      P.readQual[whichRead][1 - direction] + readLen - seedOffset, (int)seedOffset, limitLeft, &lv, sg_lane());
         score2 = lv.score; matchProb2 = lv.matchProbability; *genomeLocationOffset = lv.netIndel; totalIndels2 = lv.totalIndels; textSpan2 = lv.textSpan;
         agScore2 = ((int)seedOffset - score2) * pr.matchReward - score2 * pr.subPenalty;
     }
@@ -614,7 +613,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
 #if defined(__CUDA_ARCH__)
         // the derived strings (:347-372) are built 32 bases per step; every lane reads all of them afterwards
         #pragma unroll 1
-        for (uint32_t i = (uint32_t)P.lane; i < lens[w]; i += 32) {
+        for (uint32_t i = (uint32_t)sg_lane(); i < lens[w]; i += 32) {
             const uint8_t b = readBases[w][i], c = sg_complement(b);
             ps.rcRead[w][lens[w] - i - 1] = c;
             ps.rcQual[w][lens[w] - i - 1] = readQuals[w][i];
@@ -648,7 +647,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
             const uint32_t ml = lens[0] > lens[1] ? lens[0] : lens[1];
 #if defined(__CUDA_ARCH__)
             __syncwarp();
-            for (uint32_t i = (uint32_t)P.lane; i < (ml + 7) / 8; i += 32) ps.seedUsed[i] = 0;
+            for (uint32_t i = (uint32_t)sg_lane(); i < (ml + 7) / 8; i += 32) ps.seedUsed[i] = 0;
             __syncwarp();
 #else
             for (uint32_t i = 0; i < (ml + 7) / 8; i++) ps.seedUsed[i] = 0;
@@ -668,8 +667,8 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
             uint64_t sb, srcb;
             SgHits hits;
 #if defined(__CUDA_ARCH__)
-            if (!sg_warp_seed_pack(readBases[w] + nextSeedToTest, seedLen, P.lane, &sb, &srcb)) { nextSeedToTest++; continue; }
-            sg_warp_lookup_seed32(ix, sb, srcb, P.lane, &hits, &P.single->work.entriesProbed, &P.single->work.overflowWords);
+            if (!sg_warp_seed_pack(readBases[w] + nextSeedToTest, seedLen, sg_lane(), &sb, &srcb)) { nextSeedToTest++; continue; }
+            sg_warp_lookup_seed32(ix, sb, srcb, sg_lane(), &hits, &P.single->work.entriesProbed, &P.single->work.overflowWords);
 #else
             if (!sg_seed_pack(readBases[w] + nextSeedToTest, seedLen, &sb, &srcb)) { nextSeedToTest++; continue; }
             sg_lookup_seed32(ix, sb, srcb, &hits, &P.single->work.entriesProbed, &P.single->work.overflowWords);

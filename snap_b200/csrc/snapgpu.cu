@@ -175,23 +175,36 @@ sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_
 //   Results are those of MODE 0 by construction (a deferred read's partial work is discarded, counters included).
 template <int MB, int MODE>
 __global__ void __launch_bounds__(256, MB)
-sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratchBase, size_t scratchBytesPerWorker,
-                long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
+sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_constant__ SgParams prParam, const SgTables *tb, uint8_t *scratchBase,
+                size_t scratchBytesPerWorker, long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
                 snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next, unsigned long long *deferCount, uint32_t *deferList)
 {
     if (MODE == 2) n = (long long)*deferCount;
     const int lane = threadIdx.x & 31;
     const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
-    SgAligner A;
+    // The aligner state is the same in all 32 lanes of a warp (they run the state machine uniformly), so it lives ONCE per warp in
+    // shared memory rather than 32 times in local memory: as per-thread stack it was 95 % of the kernel's L2 traffic and, with
+    // tens of KB of stack per warp times thousands of resident warps, most of its DRAM traffic (profiles/r01_twopass_*).
+    // Every lane stores the same value to the same word; the warp is converged wherever this state is updated.
+    __shared__ SgIndexView sIx;
+    __shared__ SgParams sPr;
+    __shared__ SgAligner sA[8];
+    __shared__ snapgpu_single_result sR[8];
+    if (threadIdx.x == 0) { sIx = ixParam; sPr = prParam; }
+    __syncthreads();
+    const SgIndexView &ix = sIx; const SgParams &pr = sPr;
+    SgAligner &A = sA[threadIdx.x >> 5];
+    snapgpu_single_result &r = sR[threadIdx.x >> 5];
     A.ix = &ix; A.pr = &pr; A.tb = tb;
-    A.lane = lane; A.maxK = pr.maxK;
+    A.maxK = pr.maxK;
     A.agCands = nullptr; A.nAgCands = 0; A.maxAgCands = 0; A.agCandsOverflow = 0;
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
     A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     A.nUsedElements = 0;         // the scratch lookup table is all-zero at creation and left clean after every read
     A.work.lookups = A.work.entriesProbed = A.work.overflowWords = A.work.lvCalls = A.work.agCalls = A.work.popularIgnored = 0;
+    __syncwarp();
     unsigned long long cTotal = 0, cUseless = 0, cSingle = 0, cMulti = 0, cNotFound = 0;
 
     for (;;) {
@@ -203,7 +216,6 @@ sg_align_kernel(SgIndexView ix, SgParams pr, const SgTables *tb, uint8_t *scratc
         const uint8_t *rd = bases + offsets[i];
         const uint8_t *rq = quals + offsets[i];
         const uint32_t len = lens[i];
-        snapgpu_single_result r;
         memset(&r, 0, sizeof(r));
         if (MODE != 2) cTotal++;
         uint32_t countOfNs = 0;
@@ -275,7 +287,7 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
 
     SgAligner S;
     S.ix = &ix; S.pr = &prSingle; S.tb = tb;
-    S.lane = lane; S.maxK = prSingle.maxK;
+    S.maxK = prSingle.maxK;
     S.agCands = nullptr; S.nAgCands = 0; S.maxAgCands = 0; S.agCandsOverflow = 0;
     sg_scratch_carve(prSingle, arena, &S.sc);
     S.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
@@ -287,7 +299,7 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
     SgPairedAligner P;
     P.single = &S; P.ix = &ix; P.pr = &pr; P.pp = &pp; P.tb = tb;
     sg_paired_scratch_carve(pr, pp, arena + singleScratchBytes, &P.ps);
-    P.ag = S.ag; P.lane = lane; P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    P.ag = S.ag; P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     P.lvCalls = P.agCalls = 0; P.error = 0; P.maxK = (int)pr.maxK;
     unsigned long long cTotal = 0, cUseless = 0, cSingle = 0, cMulti = 0, cNotFound = 0;
 

@@ -153,7 +153,7 @@ void *hs_aligner_create(void *vix, const snapgpu_params *params, uint32_t maxRea
                            params->fivePrimeEndBonus, params->threePrimeEndBonus);
     a->A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     a->A.nUsedElements = 0;
-    a->A.lane = -1; a->A.maxK = a->params.maxK;
+    a->A.maxK = a->params.maxK;
     return a;
 }
 
@@ -241,12 +241,12 @@ void *hs_paired_create(void *vix, const snapgpu_params *params, const snapgpu_pa
     a->S.ag = sg_ag_params(params->matchReward, params->subPenalty, params->gapOpenPenalty, params->gapExtendPenalty,
                            params->fivePrimeEndBonus, params->threePrimeEndBonus);
     a->S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
-    a->S.lane = -1; a->S.maxK = a->prSingle.maxK;
+    a->S.maxK = a->prSingle.maxK;
     memset(&a->P, 0, sizeof(a->P));
     a->pscratch.assign(sg_paired_scratch_bytes(a->pr, a->pp) + 256, 0);
     sg_paired_scratch_carve(a->pr, a->pp, (uint8_t *)(((uintptr_t)a->pscratch.data() + 255) & ~(uintptr_t)255), &a->P.ps);
     a->P.single = &a->S; a->P.ix = &ix->view; a->P.pr = &a->pr; a->P.pp = &a->pp; a->P.tb = &a->tables;
-    a->P.ag = a->S.ag; a->P.lane = -1; a->P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    a->P.ag = a->S.ag; a->P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     return a;
 }
 
