@@ -187,6 +187,7 @@ struct SgAligner {
     int64_t invalidLocation;
     // candidatesForAffineGap of the Hamming pass (only the paired caller provides a buffer)
     snapgpu_single_result *agCands; int nAgCands, maxAgCands; int agCandsOverflow;
+    SgScoreSet wsAll, wsNonAlt; snapgpu_single_result wsKey;     // working storage of alignAffineGap (stack objects in the reference)
     int deferred;                    // set by the DEFER instantiation when the read needs affine-gap scoring (see sg_align_read_t)
 
     // ---- weight lists: doubly linked FIFO per weight; link values are element indices or SG_SENTINEL+w ----
@@ -878,7 +879,7 @@ SG_HDN void sg_align_affine_gap(SgAligner &A, snapgpu_single_result *result, int
         result->agScore = SG_SCORE_ABOVE_LIMIT; result->seedOffset = 0; result->matchProbability = 0.0;
         return;
     }
-    SgScoreSet all, nonAlt;
+    SgScoreSet &all = A.wsAll, &nonAlt = A.wsNonAlt;
     nonAlt.init(A.invalidLocation);              // ScoreSet::ScoreSet() (default ctor calls init())
     const bool nonALTAlignment = (!pr.altAwareness) || !A.isALT(result->location);
     all.initFrom(result);
@@ -896,7 +897,8 @@ SG_HDN void sg_align_affine_gap(SgAligner &A, snapgpu_single_result *result, int
         scoreLimitForCandidate = ((int)A.maxK < bestScore ? (int)A.maxK : bestScore) + (int)pr.extraSearchDepth;
         // qsort(compareByScore): stable (glibc merge sort)
         for (int i = 1; i < nCands; i++) {
-            snapgpu_single_result key = cands[i];
+            snapgpu_single_result &key = A.wsKey;
+            key = cands[i];
             int j = i - 1;
             while (j >= 0 && cands[j].score > key.score) { cands[j + 1] = cands[j]; j--; }
             cands[j + 1] = key;

@@ -81,6 +81,7 @@ struct SgParams {
     uint32_t poolSize;               // hashTableElementPoolSize, BaseAligner.cpp:183
     uint32_t tableSlots;             // power of two >= 2*poolSize (our candidate lookup table)
     uint32_t maxReadLen;             // scratch sizing bound
+    int32_t  agSpecialised;          // device tuning knob (no effect on results): SgAgParams.usePacked of the single-end kernel's second pass
 };
 
 // One candidate-table element: reference BaseAligner::HashTableElement (BaseAligner.h:223-258), compacted.

@@ -343,6 +343,11 @@ struct SgPairedAligner {
     int64_t invalidLocation;
     uint32_t lvCalls, agCalls;       // nLocationsScoredLandauVishkin / AffineGap
     int error;                       // 1: a pool overflowed (the reference soft_exit()s there)
+    // working storage of align / alignLV / alignAffineGap (their stack objects in the reference): members, so that on the device
+    // they are part of the per-warp state rather than per-thread stack
+    SgPairScoreSet wsAll, wsNonAlt;
+    snapgpu_single_result wsSingle[2];
+    snapgpu_paired_result wsKey;
 
     SG_HD bool isALT(int64_t loc) const { return loc >= ix->altFirstLocation; }
     SG_HD bool isSeedUsed(int64_t i) const { return (ps.seedUsed[i / 8] & (1 << (i % 8))) != 0; }
@@ -596,7 +601,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
     P.lowestFreeScoringMateCandidate[0] = P.lowestFreeScoringMateCandidate[1] = 0;
     P.firstFreeMergeAnchor = 0;
 
-    SgPairScoreSet all, nonAlt;
+    SgPairScoreSet &all = P.wsAll, &nonAlt = P.wsNonAlt;
     all.init(P.invalidLocation); nonAlt.init(P.invalidLocation);
     uint32_t popularSeedsSkipped[2];
 
@@ -1007,7 +1012,7 @@ SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result
         return;
     }
 
-    SgPairScoreSet all, nonAlt;
+    SgPairScoreSet &all = P.wsAll, &nonAlt = P.wsNonAlt;
     nonAlt.init(P.invalidLocation);
     bool nonALTAlignment = (!pr.altAwareness) || !P.isALT(result->location[0]);
     all.initFrom(result);
@@ -1028,7 +1033,8 @@ SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result
         // (SURVEY 7.6); insertion sort keeps equal keys in order and n is small
         const int n = *nLVCandidatesForAffineGap;
         for (int i = 1; i < n; i++) {
-            snapgpu_paired_result key = ps.lvCandidates[i];
+            snapgpu_paired_result &key = P.wsKey;
+            key = ps.lvCandidates[i];
             int ks = key.score[0] + key.score[1];
             int j = i - 1;
             while (j >= 0 && (ps.lvCandidates[j].score[0] + ps.lvCandidates[j].score[1]) > ks) { ps.lvCandidates[j + 1] = ps.lvCandidates[j]; j--; }
@@ -1082,12 +1088,44 @@ SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result
     (void)pp;
 }
 
-// ChimericPairedEndAligner::align (ChimericPairedEndAligner.cpp:126-448) around IntersectingPairedEndAligner::align (:169-252).
-SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
-                            snapgpu_paired_result *result)
+// (re)derive the per-read strings and pointers alignLandauVishkin sets up (:347-372), for a worker that takes a pair over at the
+// stage boundary below
+SG_HDN void sg_paired_restore_reads(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2])
+{
+    SgPairedScratch &ps = P.ps;
+    for (uint32_t w = 0; w < 2; w++) {
+        P.readLen[w] = lens[w];
+        P.readData[w][0] = readBases[w]; P.readQual[w][0] = readQuals[w];
+        P.readData[w][1] = ps.rcRead[w]; P.readQual[w][1] = ps.rcQual[w];
+#if defined(__CUDA_ARCH__)
+        #pragma unroll 1
+        for (uint32_t i = (uint32_t)sg_lane(); i < lens[w]; i += 32) {
+#else
+        for (uint32_t i = 0; i < lens[w]; i++) {
+#endif
+            const uint8_t b = readBases[w][i], c = sg_complement(b);
+            ps.rcRead[w][lens[w] - i - 1] = c;
+            ps.rcQual[w][lens[w] - i - 1] = readQuals[w][i];
+            ps.revRead[w][0][lens[w] - i - 1] = b;
+            ps.revRead[w][1][i] = c;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+
+// ChimericPairedEndAligner::align (ChimericPairedEndAligner.cpp:126-448) around IntersectingPairedEndAligner::align (:169-252), cut in
+// two at the point where the seed / Landau-Vishkin phases (alignLandauVishkin, incl. the Hamming retry) are over and the
+// affine-gap phase and the single-end fallback begin.  What crosses the cut: `result`, the phase-4 candidate list
+// (P.ps.lvCandidates[0, nLVCand)) and the return value of stage 1.  sg_paired_align() is the two stages back to back; the
+// device may run them in different kernels (sg_align_paired_kernel) so that each kernel's code stays small.
+//   stage 1 returns 0: `result` is final (or P.error is set); 1: continue, both reads were long enough for the paired aligner;
+//   2: continue, one read is too short (single-end fallback only).
+SG_HDN int sg_paired_align_stage1(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
+                                  snapgpu_paired_result *result, int *nLVCand)
 {
     const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp;
-    SgAligner &S = *P.single;
     result->status[0] = result->status[1] = SNAPGPU_NOT_FOUND;
     result->usedAffineGapScoring[0] = result->usedAffineGapScoring[1] = 0;
     result->basesClippedBefore[0] = result->basesClippedBefore[1] = 0;
@@ -1097,29 +1135,39 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
     result->liftover[0] = result->liftover[1] = 0;
     result->agForcedSingleAlignerCall = 0;
     const uint32_t minReadLength = pr.minReadLength;
-    const int maxKSingleEnd = (int)(pr.maxK / 2), maxKPairedEnd = (int)pr.maxK;
+    *nLVCand = 0;
 
     if (lens[0] < minReadLength && lens[1] < minReadLength) {
         for (int w = 0; w < 2; w++) { result->location[w] = P.invalidLocation; result->mapq[w] = 0; result->score[w] = 0; result->status[w] = SNAPGPU_NOT_FOUND; }
         result->alignedAsPair = 0;
-        return;
+        return 0;
     }
+    if (lens[0] >= minReadLength && lens[1] >= minReadLength) {
+        P.maxK = (int)pr.maxK;
+        bool fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, nLVCand);
+        if (!fit || P.error) { P.error = P.error ? P.error : (pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2); return 0; }      // buffer growth + retry (PairedAligner.cpp:727-780) is not implemented
+        if (pr.useAffineGap && pp.useSoftClip && (result->status[0] == SNAPGPU_NOT_FOUND || result->status[1] == SNAPGPU_NOT_FOUND)) {
+            // IntersectingPairedEndAligner.cpp:220-233: try again with Hamming scoring that clips a poorly matching start / end
+            fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, nLVCand, true);
+            if (!fit || P.error) { P.error = P.error ? P.error : (pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2); return 0; }
+        }
+        return 1;
+    }
+    return 2;
+}
 
+SG_HDN void sg_paired_align_stage2(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
+                                   snapgpu_paired_result *result, int stage, int nLVCand)
+{
+    const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp;
+    SgAligner &S = *P.single;
+    const uint32_t minReadLength = pr.minReadLength;
+    const int maxKSingleEnd = (int)(pr.maxK / 2);
     int pairAGScore = 0, sumPairScore = 0;
     bool compareWithSingleEndAlignment = false;
-    if (lens[0] >= minReadLength && lens[1] >= minReadLength) {
-        P.maxK = maxKPairedEnd;
-        int nLVCand = 0;
-        bool fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, &nLVCand);
-        if (!fit || P.error) { P.error = P.error ? P.error : (pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2); return; }      // buffer growth + retry (PairedAligner.cpp:727-780) is not implemented
-        if (pr.useAffineGap) {
-            if (pp.useSoftClip && (result->status[0] == SNAPGPU_NOT_FOUND || result->status[1] == SNAPGPU_NOT_FOUND)) {
-                // IntersectingPairedEndAligner.cpp:220-233: try again with Hamming scoring that clips a poorly matching start / end
-                fit = sg_paired_align_lv(P, readBases, readQuals, lens, result, &nLVCand, true);
-                if (!fit || P.error) { P.error = P.error ? P.error : (pp.agCandCap < SG_MAX_AG_CANDIDATES ? 4 : 2); return; }
-            }
-            sg_paired_align_ag(P, result, &nLVCand);
-        }
+    if (stage == 1) {
+        P.maxK = (int)pr.maxK;
+        if (pr.useAffineGap) sg_paired_align_ag(P, result, &nLVCand);
         result->alignedAsPair = 1;
         if (pp.forceSpacing) {
             if (result->status[0] == SNAPGPU_NOT_FOUND) result->alignedAsPair = 0;
@@ -1139,8 +1187,8 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
         if (result->status[0] != SNAPGPU_NOT_FOUND && result->status[1] != SNAPGPU_NOT_FOUND) result->agForcedSingleAlignerCall = 1;
     }
 
-    snapgpu_single_result singleResult[2];
-    memset(singleResult, 0, sizeof(singleResult));
+    snapgpu_single_result *singleResult = P.wsSingle;
+    memset(singleResult, 0, 2 * sizeof(snapgpu_single_result));
     int singleEndAGScore = 0;
     bool chooseSingleEndMapq = true;
     int nSingleCandsFirstRead = 0;
@@ -1214,4 +1262,12 @@ SG_HDN void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2
         }
         result->alignedAsPair = 0;
     }
+}
+
+SG_HD void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
+                           snapgpu_paired_result *result)
+{
+    int nLVCand = 0;
+    const int stage = sg_paired_align_stage1(P, readBases, readQuals, lens, result, &nLVCand);
+    if (stage != 0) sg_paired_align_stage2(P, readBases, readQuals, lens, result, stage, nLVCand);
 }

@@ -97,7 +97,7 @@ __device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int ope
             const unsigned validBytes = nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u);
             #pragma unroll 1
             for (int kk = 0; kk < SG_VEC - 1; kk++) {
-                { const int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
+                if (j < segEndTrack) { const int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }      // X0 only feeds the next segment of this row
                 { const int up = sg_shfl(fl, laneUp); fl = (l == 0) ? 0 : up; }
                 int fv = fl - q * ext; if (fv < 0) fv = 0;
                 const bool a2 = valid && fv > h;
@@ -310,7 +310,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
                 const unsigned validBytes = nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u);
                 #pragma unroll 1
                 for (int kk = 0; kk < passes; kk++) {
-                    if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
+                    if (banded && j < segEnd) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }      // X0 only feeds the next segment of this row
                     { int up = sg_shfl(fl, (lane & 24) | ((l + 7) & 7)); fl = (l == 0) ? 0 : up; }
                     int fv = fl - k * ext; if (fv < 0) fv = 0;
                     const bool a2 = valid && fv > h;
@@ -392,7 +392,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
             int fl = fcarry;                 // f register of SSE lane l after the main pass
             bool converged = false;
             for (int kk = 0; kk < passes && !converged; kk++) {
-                if (banded) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
+                if (banded && j < segEnd) { int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }
                 { int up = sg_shfl(fl, (lane & 24) | ((l + 7) & 7)); fl = (l == 0) ? 0 : up; }      // f = f << one lane
                 for (int b = 0; b < nBlocks && !converged; b++) {
                     const int v = 4 * b + q;

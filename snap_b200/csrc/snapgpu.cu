@@ -75,6 +75,12 @@ struct snapgpu_aligner {
     uint8_t *d_bigScratch = nullptr;
     uint32_t *d_retryList = nullptr;     // [maxUnits]
     unsigned long long *d_retryCount = nullptr, *d_next2 = nullptr;
+    // staged paired launch (sg_align_paired_kernel STAGE 1 + STAGE 2): per-pair hand-off records and the pool of phase-4 candidates
+    bool staged = false;
+    void *d_handoff = nullptr;           // SgPairHandoff[maxUnits]
+    snapgpu_paired_result *d_candPool = nullptr;
+    unsigned long long candPoolCap = 0;
+    unsigned long long *d_candPoolUsed = nullptr, *d_next3 = nullptr;
     int device = 0;
     int numSMs = 0;
     int warpsPerBlock = 8, blocksPerSM = 4;
@@ -201,6 +207,7 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
     A.agCands = nullptr; A.nAgCands = 0; A.maxAgCands = 0; A.agCandsOverflow = 0;
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
+    if (MODE == 2) A.ag.usePacked = pr.agSpecialised;
     A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     A.nUsedElements = 0;         // the scratch lookup table is all-zero at creation and left clean after every read
     A.work.lookups = A.work.entriesProbed = A.work.overflowWords = A.work.lvCalls = A.work.agCalls = A.work.popularIgnored = 0;
@@ -271,12 +278,28 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
 // The paired-end kernel: same execution model, one warp per PAIR.  Worker arena = single-end scratch followed by the
 // paired scratch (hit sets, candidate pools, merge anchors, phase-4 candidate buffer, the second pair of affine-gap
 // traceback arrays).
-template <int MB>
+//
+// STAGE 0: sg_paired_align() whole (also the retry pass over workList with full-size pools).
+// STAGE 1 / STAGE 2, the staged launch: stage 1 runs the seed / Landau-Vishkin phases of every pair (sg_paired_align_stage1) and
+//   leaves `results[i]`, the phase-4 candidate list (copied to candPool) and an SgPairHandoff record; stage 2, another launch
+//   with its own instantiation, takes every unfinished pair over from there (affine-gap phase, single-end fallback).  Each
+//   kernel carries only its own phases' code -- the kernels are bound by instruction supply -- and the work of a
+//   pair stays attributed to the pair (SgPairHandoff::work) so that the counters do not depend on the launch form.
+struct SgPairHandoff {
+    int32_t stage;                   // 0: nothing left to do (final result written, or queued for the retry pass); else sg_paired_align_stage1's return value
+    int32_t nLVCand;                 // phase-4 candidates at candPool[candBase, +nLVCand)
+    unsigned long long candBase;
+    uint32_t work[8];                // stage 1's counters for this pair: lookups, entriesProbed, overflowWords, lvCalls, agCalls, popularIgnored, P.lvCalls, P.agCalls
+};
+
+template <int MB, int STAGE>
 __global__ void __launch_bounds__(256, MB)
-sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedParams pp, const SgTables *tb, uint8_t *scratchBase,
+sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_constant__ SgParams prParam, const __grid_constant__ SgParams prSingleParam,
+                       const __grid_constant__ SgPairedParams ppParam, const SgTables *tb, uint8_t *scratchBase,
                        size_t scratchBytesPerWorker, size_t singleScratchBytes, long long nPairs, const uint8_t *bases, const uint8_t *quals,
                        const unsigned long long *offsets, const uint32_t *lens, snapgpu_paired_result *results, snapgpu_counters *counters,
-                       unsigned long long *next, int *errorWord, const uint32_t *workList, unsigned long long *retryCount, uint32_t *retryList)
+                       unsigned long long *next, int *errorWord, const uint32_t *workList, unsigned long long *retryCount, uint32_t *retryList,
+                       SgPairHandoff *handoff, snapgpu_paired_result *candPool, unsigned long long candPoolCap, unsigned long long *candPoolUsed)
 {
     // workList == NULL: first pass over pairs [0, nPairs), pairs that outgrow this arena's caps go to retryList.
     // workList != NULL: retry pass over workList[0, *retryCount) with full-size pools.
@@ -285,7 +308,19 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
     const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t *arena = scratchBase + (size_t)worker * scratchBytesPerWorker;
 
-    SgAligner S;
+    // warp-uniform state: one copy per warp in shared memory (see sg_align_kernel)
+    __shared__ SgIndexView sIx;
+    __shared__ SgParams sPr, sPrSingle;
+    __shared__ SgPairedParams sPp;
+    __shared__ SgAligner sS[8];
+    __shared__ SgPairedAligner sP[8];
+    __shared__ snapgpu_paired_result sR[8];
+    if (threadIdx.x == 0) { sIx = ixParam; sPr = prParam; sPrSingle = prSingleParam; sPp = ppParam; }
+    __syncthreads();
+    const SgIndexView &ix = sIx; const SgParams &pr = sPr; const SgParams &prSingle = sPrSingle; const SgPairedParams &pp = sPp;
+    SgAligner &S = sS[threadIdx.x >> 5];
+    SgPairedAligner &P = sP[threadIdx.x >> 5];
+    snapgpu_paired_result &r = sR[threadIdx.x >> 5];
     S.ix = &ix; S.pr = &prSingle; S.tb = tb;
     S.maxK = prSingle.maxK;
     S.agCands = nullptr; S.nAgCands = 0; S.maxAgCands = 0; S.agCandsOverflow = 0;
@@ -296,7 +331,6 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
     S.nUsedElements = 0;
     S.work.lookups = S.work.entriesProbed = S.work.overflowWords = S.work.lvCalls = S.work.agCalls = S.work.popularIgnored = 0;
 
-    SgPairedAligner P;
     P.single = &S; P.ix = &ix; P.pr = &pr; P.pp = &pp; P.tb = tb;
     sg_paired_scratch_carve(pr, pp, arena + singleScratchBytes, &P.ps);
     P.ag = S.ag; P.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
@@ -310,9 +344,15 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
         if (i >= (unsigned long long)nPairs) break;
         const bool firstPass = workList == (const uint32_t *)0;
         if (!firstPass) i = workList[i];
+        SgPairHandoff h;
+        if (STAGE == 2) {
+            h = handoff[i];
+            if (h.stage == 0) continue;
+        }
         const uint8_t *rb[2], *rq[2]; uint32_t ln[2]; bool useful[2]; bool tooLong = false;
         for (int w = 0; w < 2; w++) {
             rb[w] = bases + offsets[2 * i + w]; rq[w] = quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w];
+            if (STAGE == 2) continue;
             uint32_t countOfNs = 0;
             #pragma unroll 1
             for (uint32_t k = lane; k < ln[w]; k += 32) countOfNs += (rb[w][k] == 'N');
@@ -320,24 +360,69 @@ sg_align_paired_kernel(SgIndexView ix, SgParams pr, SgParams prSingle, SgPairedP
             useful[w] = ln[w] >= pr.minReadLength && countOfNs <= pr.maxK;       // PairedAligner.cpp:669-676
             tooLong = tooLong || ln[w] > pr.maxReadLen;
         }
-        snapgpu_paired_result r;
-        memset(&r, 0, sizeof(r));
-        if (firstPass) cTotal += 2;
-        if (tooLong) { if (lane == 0) atomicMax(errorWord, 3); useful[0] = useful[1] = false; }
-        if (!useful[0] && !useful[1]) {
-            r.status[0] = r.status[1] = SNAPGPU_NOT_FOUND; r.location[0] = r.location[1] = P.invalidLocation;
-            cUseless += 2;
-            if (lane == 0) results[i] = r;
-            continue;
-        }
         P.error = 0;
         const SgWork workBefore = S.work; const uint32_t lvBefore = P.lvCalls, agBefore = P.agCalls;
-        sg_paired_align(P, rb, rq, ln, &r);
+        if (STAGE == 2) {
+            // take the pair over: result so far, derived strings, phase-4 candidates
+            __syncwarp();
+            for (uint32_t k = lane; k < sizeof(r) / 4; k += 32) ((uint32_t *)&r)[k] = ((const uint32_t *)&results[i])[k];
+            for (uint32_t k = lane; k < (uint32_t)h.nLVCand * (sizeof(r) / 4); k += 32) ((uint32_t *)P.ps.lvCandidates)[k] = ((const uint32_t *)(candPool + h.candBase))[k];
+            __syncwarp();
+            sg_paired_restore_reads(P, rb, rq, ln);
+            sg_paired_align_stage2(P, rb, rq, ln, &r, h.stage, h.nLVCand);
+        } else {
+            memset(&r, 0, sizeof(r));
+            if (firstPass) cTotal += 2;
+            if (tooLong) { if (lane == 0) atomicMax(errorWord, 3); useful[0] = useful[1] = false; }
+            if (!useful[0] && !useful[1]) {
+                r.status[0] = r.status[1] = SNAPGPU_NOT_FOUND; r.location[0] = r.location[1] = P.invalidLocation;
+                cUseless += 2;
+                if (lane == 0) { results[i] = r; if (STAGE == 1) handoff[i].stage = 0; }
+                continue;
+            }
+            if (STAGE == 1) {
+                int nLV = 0;
+                const int st = sg_paired_align_stage1(P, rb, rq, ln, &r, &nLV);
+                if (st != 0 && !P.error) {
+                    // hand the pair over to stage 2
+                    unsigned long long base = 0;
+                    if (nLV > 0) {
+                        if (lane == 0) base = atomicAdd(candPoolUsed, (unsigned long long)nLV);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (base + (unsigned long long)nLV > candPoolCap) P.error = 4;       // hand-off pool exhausted: the retry pass does the pair whole
+                    }
+                    if (!P.error) {
+                        __syncwarp();
+                        for (uint32_t k = lane; k < (uint32_t)nLV * (sizeof(r) / 4); k += 32) ((uint32_t *)(candPool + base))[k] = ((const uint32_t *)P.ps.lvCandidates)[k];
+                        for (uint32_t k = lane; k < sizeof(r) / 4; k += 32) ((uint32_t *)&results[i])[k] = ((const uint32_t *)&r)[k];
+                        if (lane == 0) {
+                            SgPairHandoff o;
+                            o.stage = st; o.nLVCand = nLV; o.candBase = base;
+                            o.work[0] = S.work.lookups - workBefore.lookups; o.work[1] = S.work.entriesProbed - workBefore.entriesProbed;
+                            o.work[2] = S.work.overflowWords - workBefore.overflowWords; o.work[3] = S.work.lvCalls - workBefore.lvCalls;
+                            o.work[4] = S.work.agCalls - workBefore.agCalls; o.work[5] = S.work.popularIgnored - workBefore.popularIgnored;
+                            o.work[6] = P.lvCalls - lvBefore; o.work[7] = P.agCalls - agBefore;
+                            handoff[i] = o;
+                        }
+                        __syncwarp();
+                        S.work = workBefore; P.lvCalls = lvBefore; P.agCalls = agBefore;       // (they travel with the pair)
+                        continue;
+                    }
+                }
+                if (lane == 0) handoff[i].stage = 0;
+            } else {
+                sg_paired_align(P, rb, rq, ln, &r);
+            }
+        }
         if (P.error == 4 && firstPass) {
             // this arena's pools are too small for the pair: hand it to the retry pass (and do not count the aborted work)
             if (lane == 0) retryList[atomicAdd(retryCount, 1ULL)] = (uint32_t)i;
             S.work = workBefore; P.lvCalls = lvBefore; P.agCalls = agBefore;
             continue;
+        }
+        if (STAGE == 2) {
+            S.work.lookups += h.work[0]; S.work.entriesProbed += h.work[1]; S.work.overflowWords += h.work[2]; S.work.lvCalls += h.work[3];
+            S.work.agCalls += h.work[4]; S.work.popularIgnored += h.work[5]; P.lvCalls += h.work[6]; P.agCalls += h.work[7];
         }
         if (P.error) {
             if (lane == 0) atomicMax(errorWord, P.error);
@@ -881,6 +966,8 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
                             "SNAPGPU_BLOCKS_PER_SM")) { snapgpu_aligner_destroy(a); return 1; }
     // two-pass launch (see sg_align_kernel) whenever some reads can finish without affine gap: not under -ne (every
     // candidate is rescored) ; without affine gap at all the first pass simply finishes everything.  SNAPGPU_TWO_PASS=0 turns it off.
+    a->params.agSpecialised = 1;         // second pass: narrow-band / packed affine-gap forms (measured 16.61 -> 17.18 M reads/s; they cost throughput in the one-launch form)
+    if (const char *e = getenv("SNAPGPU_SINGLE_AG_SPECIALISED")) a->params.agSpecialised = atoi(e) != 0;
     a->twoPass = !a->params.noEditDistance;
     if (const char *e = getenv("SNAPGPU_TWO_PASS")) a->twoPass = atoi(e) != 0;
     if (a->twoPass) {
@@ -951,6 +1038,20 @@ int snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params
         snapgpu_aligner_destroy(a);
         return sg_fail(msg);
     }
+    a->staged = true;
+    if (const char *e = getenv("SNAPGPU_PAIRED_STAGED")) a->staged = atoi(e) != 0;
+    if (a->staged) {
+        unsigned long long perPair = 4;      // hand-off candidate records per pair of the batch (a pair that finds the pool full is done whole by the retry pass)
+        if (const char *e = getenv("SNAPGPU_PAIRED_HANDOFF_PER_PAIR")) perPair = atoll(e) > 0 ? (unsigned long long)atoll(e) : perPair;
+        a->candPoolCap = perPair * (unsigned long long)maxBatchPairs;
+        if (cudaMalloc(&a->d_handoff, (size_t)maxBatchPairs * sizeof(SgPairHandoff)) != cudaSuccess ||
+            cudaMalloc((void **)&a->d_candPool, (size_t)a->candPoolCap * sizeof(snapgpu_paired_result)) != cudaSuccess ||
+            cudaMalloc((void **)&a->d_candPoolUsed, 8) != cudaSuccess || cudaMalloc((void **)&a->d_next3, 8) != cudaSuccess) {
+            std::string msg = std::string("snapgpu_paired_aligner_create: hand-off buffers: ") + cudaGetErrorString(cudaGetLastError());
+            snapgpu_aligner_destroy(a);
+            return sg_fail(msg);
+        }
+    }
     *out = a;
     return 0;
 }
@@ -965,6 +1066,7 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
     if (a->streamOut) cudaStreamDestroy(a->streamOut);
     cudaFree(a->d_scratch); cudaFree(a->d_next); cudaFree(a->d_error);
     cudaFree(a->d_bigScratch); cudaFree(a->d_retryList); cudaFree(a->d_retryCount); cudaFree(a->d_next2);
+    cudaFree(a->d_handoff); cudaFree(a->d_candPool); cudaFree(a->d_candPoolUsed); cudaFree(a->d_next3);
     for (int k = 0; k < 2; k++) {
         snapgpu_aligner::Slot &sl = a->slot[k];
         cudaFreeHost(sl.h_bases); cudaFreeHost(sl.h_quals); cudaFreeHost(sl.h_offsets); cudaFreeHost(sl.h_lens); cudaFreeHost(sl.h_results);
@@ -1023,18 +1125,28 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
     } else {
         SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));
         SG_CUDA(cudaMemsetAsync(a->d_next2, 0, 8, st));
-#define SG_LAUNCH(MB, GRID, PP, SCRATCH, BYTES, NEXT, LIST) sg_align_paired_kernel<MB><<<GRID, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, \
+#define SG_LAUNCH(MB, STAGE, GRID, PP, SCRATCH, BYTES, NEXT, LIST) sg_align_paired_kernel<MB, STAGE><<<GRID, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, \
         a->paramsSingle, PP, a->index->d_tables_prob, SCRATCH, BYTES, a->singleScratchBytes, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, \
-        (const unsigned long long *)d_offsets, d_lens, (snapgpu_paired_result *)d_results, d_counters, NEXT, a->d_error, LIST, a->d_retryCount, a->d_retryList)
-#define SG_LAUNCH_MB(GRID, PP, SCRATCH, BYTES, NEXT, LIST) \
-        if (a->blocksPerSM >= 4) SG_LAUNCH(4, GRID, PP, SCRATCH, BYTES, NEXT, LIST); else if (a->blocksPerSM == 3) SG_LAUNCH(3, GRID, PP, SCRATCH, BYTES, NEXT, LIST); \
-        else SG_LAUNCH(2, GRID, PP, SCRATCH, BYTES, NEXT, LIST)
-        SG_LAUNCH_MB(blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
+        (const unsigned long long *)d_offsets, d_lens, (snapgpu_paired_result *)d_results, d_counters, NEXT, a->d_error, LIST, a->d_retryCount, a->d_retryList, \
+        (SgPairHandoff *)a->d_handoff, a->d_candPool, a->candPoolCap, a->d_candPoolUsed)
+#define SG_LAUNCH_MB(STAGE, GRID, PP, SCRATCH, BYTES, NEXT, LIST) \
+        if (a->blocksPerSM >= 4) SG_LAUNCH(4, STAGE, GRID, PP, SCRATCH, BYTES, NEXT, LIST); else if (a->blocksPerSM == 3) SG_LAUNCH(3, STAGE, GRID, PP, SCRATCH, BYTES, NEXT, LIST); \
+        else SG_LAUNCH(2, STAGE, GRID, PP, SCRATCH, BYTES, NEXT, LIST)
+        if (a->staged) {
+            SG_CUDA(cudaMemsetAsync(a->d_candPoolUsed, 0, 8, st));
+            SG_CUDA(cudaMemsetAsync(a->d_next3, 0, 8, st));
+            SG_LAUNCH_MB(1, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
+            SG_CUDA(cudaGetLastError());
+            a->launches++;
+            SG_LAUNCH_MB(2, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next3, (const uint32_t *)nullptr);
+        } else {
+            SG_LAUNCH_MB(0, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
+        }
         SG_CUDA(cudaGetLastError());
         a->launches++;
-        if (a->pparams.poolCap < a->pparamsBig.poolCap || a->pparams.agCandCap < a->pparamsBig.agCandCap) {
+        if (a->staged || a->pparams.poolCap < a->pparamsBig.poolCap || a->pparams.agCandCap < a->pparamsBig.agCandCap) {
             // retry pass: exits at once when the list is empty
-            SG_LAUNCH_MB(a->nBigWorkers / a->warpsPerBlock, a->pparamsBig, a->d_bigScratch, a->bigScratchBytesPerWorker, a->d_next2, (const uint32_t *)a->d_retryList);
+            SG_LAUNCH_MB(0, a->nBigWorkers / a->warpsPerBlock, a->pparamsBig, a->d_bigScratch, a->bigScratchBytesPerWorker, a->d_next2, (const uint32_t *)a->d_retryList);
             SG_CUDA(cudaGetLastError());
             a->launches++;
         }

@@ -219,6 +219,7 @@ struct HsPaired {
     SgPairedAligner P;
     HsPaired *big = nullptr;         // full-size fallback when this one runs with reduced pool caps (mirrors the GPU retry pass)
     int64_t retried = 0;
+    bool staged = false;             // mirror of the CUDA path's staged launch: stage 1 of every pair first, then stage 2 of every pair
 };
 
 // poolCap / candCap: 0 = the reference's sizes; otherwise this aligner's pools are capped and a pair that needs more is
@@ -252,6 +253,7 @@ void *hs_paired_create(void *vix, const snapgpu_params *params, const snapgpu_pa
 
 void hs_paired_destroy(void *v) { HsPaired *a = (HsPaired *)v; if (a->big) hs_paired_destroy(a->big); delete a; }
 int64_t hs_paired_retried(void *v) { return ((HsPaired *)v)->retried; }
+void hs_paired_set_staged(void *v, int on) { ((HsPaired *)v)->staged = on != 0; }
 
 // Same contract as oracle ref_paired_align: pair i = reads 2i, 2i+1; the pre-filter of PairedAligner.cpp:669-707.
 int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
@@ -260,6 +262,8 @@ int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *qual
     HsPaired *a = (HsPaired *)v;
     a->P.lvCalls = a->P.agCalls = 0;
     memset(&a->S.work, 0, sizeof(a->S.work));
+    struct Handoff { int stage = 0; int nLVCand = 0; std::vector<snapgpu_paired_result> cands; };
+    std::vector<Handoff> hand(a->staged ? (size_t)nPairs : 0);
     for (int64_t i = 0; i < nPairs; i++) {
         snapgpu_paired_result *r = &results[i];
         memset(r, 0, sizeof(*r));
@@ -276,7 +280,38 @@ int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *qual
             continue;
         }
         a->P.error = 0;
-        sg_paired_align(a->P, rb, rq, ln, r);
+        if (a->staged) {
+            Handoff &h = hand[i];
+            h.stage = sg_paired_align_stage1(a->P, rb, rq, ln, r, &h.nLVCand);
+            if (a->P.error == 0 && h.stage != 0) {
+                h.cands.assign(a->P.ps.lvCandidates, a->P.ps.lvCandidates + h.nLVCand);
+                continue;
+            }
+            h.stage = 0;
+        } else {
+            sg_paired_align(a->P, rb, rq, ln, r);
+        }
+        if (a->P.error == 4 && a->big) {
+            a->retried++;
+            memset(r, 0, sizeof(*r));
+            a->big->P.error = 0;
+            sg_paired_align(a->big->P, rb, rq, ln, r);
+            if (a->big->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
+            continue;
+        }
+        if (a->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
+    }
+    for (int64_t i = 0; a->staged && i < nPairs; i++) {
+        Handoff &h = hand[i];
+        if (h.stage == 0) continue;
+        snapgpu_paired_result *r = &results[i];
+        const uint8_t *rb[2], *rq[2]; uint32_t ln[2];
+        for (int w = 0; w < 2; w++) { rb[w] = (const uint8_t *)bases + offsets[2 * i + w]; rq[w] = (const uint8_t *)quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w]; }
+        // by now the aligner's scratch has been through every other pair of the batch
+        sg_paired_restore_reads(a->P, rb, rq, ln);
+        for (int k = 0; k < h.nLVCand; k++) a->P.ps.lvCandidates[k] = h.cands[k];
+        a->P.error = 0;
+        sg_paired_align_stage2(a->P, rb, rq, ln, r, h.stage, h.nLVCand);
         if (a->P.error == 4 && a->big) {
             a->retried++;
             memset(r, 0, sizeof(*r));

@@ -57,6 +57,7 @@ def lib():
         L.hs_paired_retried.restype = C.c_int64
         L.hs_paired_retried.argtypes = [C.c_void_p]
         L.hs_paired_destroy.argtypes = [C.c_void_p]
+        L.hs_paired_set_staged.argtypes = [C.c_void_p, C.c_int]
         L.hs_align_paired.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         _lib = L
     return _lib
@@ -124,6 +125,9 @@ class HsPairedAligner:
 
     def retried(self) -> int:
         return int(lib().hs_paired_retried(self.handle))
+
+    def set_staged(self, on: bool):
+        lib().hs_paired_set_staged(self.handle, 1 if on else 0)
 
     def __del__(self):
         if getattr(self, "handle", None):

@@ -210,6 +210,30 @@ def test_pairs_match_reference(reflib, small_cfg, opt):
             assert int(want["usedGaplessClipping"].sum()) > 0 and int((want["basesClippedBefore"] + want["basesClippedAfter"] > 0).sum()) > 0
 
 
+@pytest.mark.parametrize("opt", ["default_d14", "default_d27", "default_no_eh", "hc_d14", "hc_noag", "hc_forcespacing", "hc_h20_H50"])
+def test_pairs_staged_form_matches_reference(reflib, small_cfg, opt):
+    """sg_align_paired_kernel's staged launch: sg_paired_align_stage1 of every pair of the batch first, then
+    sg_paired_align_stage2 of every pair from the hand-off (result so far + phase-4 candidates), the aligner's scratch having
+    been through all the other pairs in between.  With and without reduced pool caps (a pair may also abort in stage 2)."""
+    kw, pkw = PAIRED_OPTION_SETS[opt]
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for name, pb in small_cfg.pairs.items():
+        ral = reflib.RefPairedAligner(ridx, p, pp)
+        want, _ = ral.align(pb)
+        ral.close()
+        ref_lv, ref_ag = None, None
+        for caps in ((0, 0), (64, 8)):
+            plain = hs.HsPairedAligner(hidx, p, pp, pool_cap=caps[0], cand_cap=caps[1])
+            _, lv0, ag0 = plain.align(pb, reflib.PAIRED_RESULT_DTYPE)
+            al = hs.HsPairedAligner(hidx, p, pp, pool_cap=caps[0], cand_cap=caps[1])
+            al.set_staged(True)
+            got, lv1, ag1 = al.align(pb, reflib.PAIRED_RESULT_DTYPE)
+            assert differing_pairs(want, got) == [], (opt, name, caps)
+            if caps == (0, 0):
+                assert (lv0, ag0) == (lv1, ag1), (opt, name)
+
+
 def test_pairs_large_index(reflib, small_cfg):
     kw, pkw = PAIRED_OPTION_SETS["default_d14"]
     p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
