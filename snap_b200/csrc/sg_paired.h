@@ -1156,14 +1156,12 @@ SG_HDN int sg_paired_align_stage1(SgPairedAligner &P, const uint8_t *const readB
     return 2;
 }
 
-SG_HDN void sg_paired_align_stage2(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
-                                   snapgpu_paired_result *result, int stage, int nLVCand)
+// stage 2 (the affine-gap phase of the intersecting aligner) returns 0: `result` is final; 1: continue with the single-end
+// aligner on both reads (stage 3); 2: the same, comparing its result with the pair's (compareWithSingleEndAlignment).
+// Only `result` and that value cross this cut.
+SG_HDN int sg_paired_align_stage2(SgPairedAligner &P, snapgpu_paired_result *result, int stage, int nLVCand)
 {
     const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp;
-    SgAligner &S = *P.single;
-    const uint32_t minReadLength = pr.minReadLength;
-    const int maxKSingleEnd = (int)(pr.maxK / 2);
-    int pairAGScore = 0, sumPairScore = 0;
     bool compareWithSingleEndAlignment = false;
     if (stage == 1) {
         P.maxK = (int)pr.maxK;
@@ -1171,15 +1169,28 @@ SG_HDN void sg_paired_align_stage2(SgPairedAligner &P, const uint8_t *const read
         result->alignedAsPair = 1;
         if (pp.forceSpacing) {
             if (result->status[0] == SNAPGPU_NOT_FOUND) result->alignedAsPair = 0;
-            return;
+            return 0;
         }
         int maxScore = result->score[0] > result->score[1] ? result->score[0] : result->score[1];
-        sumPairScore = result->score[0] + result->score[1];
         result->mapq[0] = result->mapq[0] <= pp.flattenMAPQAtOrBelow ? 0 : result->mapq[0];
         result->mapq[1] = result->mapq[1] <= pp.flattenMAPQAtOrBelow ? 0 : result->mapq[1];
         if ((result->usedAffineGapScoring[0] || result->usedAffineGapScoring[1]) && maxScore >= pp.minScoreRealignment) compareWithSingleEndAlignment = true;
-        if (result->status[0] != SNAPGPU_NOT_FOUND && result->status[1] != SNAPGPU_NOT_FOUND && !compareWithSingleEndAlignment) return;
+        if (result->status[0] != SNAPGPU_NOT_FOUND && result->status[1] != SNAPGPU_NOT_FOUND && !compareWithSingleEndAlignment) return 0;
     }
+    return compareWithSingleEndAlignment ? 2 : 1;
+}
+
+// stage 3: ChimericPairedEndAligner.cpp:268-448, the single-end aligner on each read and the choice between its result and the pair's
+SG_HDN void sg_paired_align_stage3(SgPairedAligner &P, const uint8_t *const readBases[2], const uint8_t *const readQuals[2], const uint32_t lens[2],
+                                   snapgpu_paired_result *result, int stage)
+{
+    const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp;
+    SgAligner &S = *P.single;
+    const uint32_t minReadLength = pr.minReadLength;
+    const int maxKSingleEnd = (int)(pr.maxK / 2);
+    const bool compareWithSingleEndAlignment = stage == 2;
+    int pairAGScore = 0;
+    const int sumPairScore = compareWithSingleEndAlignment ? result->score[0] + result->score[1] : 0;
 
     int scoreLimitLeft = maxKSingleEnd;
     if (compareWithSingleEndAlignment) {
@@ -1269,5 +1280,7 @@ SG_HD void sg_paired_align(SgPairedAligner &P, const uint8_t *const readBases[2]
 {
     int nLVCand = 0;
     const int stage = sg_paired_align_stage1(P, readBases, readQuals, lens, result, &nLVCand);
-    if (stage != 0) sg_paired_align_stage2(P, readBases, readQuals, lens, result, stage, nLVCand);
+    if (stage == 0) return;
+    const int stage3 = sg_paired_align_stage2(P, result, stage, nLVCand);
+    if (stage3 != 0) sg_paired_align_stage3(P, readBases, readQuals, lens, result, stage3);
 }

@@ -345,14 +345,14 @@ sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid
         const bool firstPass = workList == (const uint32_t *)0;
         if (!firstPass) i = workList[i];
         SgPairHandoff h;
-        if (STAGE == 2) {
+        if (STAGE >= 2) {
             h = handoff[i];
             if (h.stage == 0) continue;
         }
         const uint8_t *rb[2], *rq[2]; uint32_t ln[2]; bool useful[2]; bool tooLong = false;
         for (int w = 0; w < 2; w++) {
             rb[w] = bases + offsets[2 * i + w]; rq[w] = quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w];
-            if (STAGE == 2) continue;
+            if (STAGE >= 2) continue;
             uint32_t countOfNs = 0;
             #pragma unroll 1
             for (uint32_t k = lane; k < ln[w]; k += 32) countOfNs += (rb[w][k] == 'N');
@@ -362,14 +362,21 @@ sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid
         }
         P.error = 0;
         const SgWork workBefore = S.work; const uint32_t lvBefore = P.lvCalls, agBefore = P.agCalls;
-        if (STAGE == 2) {
-            // take the pair over: result so far, derived strings, phase-4 candidates
+        int nextStage = 0;               // staged launch: the pair goes on to the next kernel with this stage value
+        int nLV = 0;
+        if (STAGE >= 2) {
+            // take the pair over: the result so far (+ for stage 2 the derived strings and the phase-4 candidates)
             __syncwarp();
             for (uint32_t k = lane; k < sizeof(r) / 4; k += 32) ((uint32_t *)&r)[k] = ((const uint32_t *)&results[i])[k];
-            for (uint32_t k = lane; k < (uint32_t)h.nLVCand * (sizeof(r) / 4); k += 32) ((uint32_t *)P.ps.lvCandidates)[k] = ((const uint32_t *)(candPool + h.candBase))[k];
-            __syncwarp();
-            sg_paired_restore_reads(P, rb, rq, ln);
-            sg_paired_align_stage2(P, rb, rq, ln, &r, h.stage, h.nLVCand);
+            if (STAGE == 2) {
+                for (uint32_t k = lane; k < (uint32_t)h.nLVCand * (sizeof(r) / 4); k += 32) ((uint32_t *)P.ps.lvCandidates)[k] = ((const uint32_t *)(candPool + h.candBase))[k];
+                __syncwarp();
+                sg_paired_restore_reads(P, rb, rq, ln);
+                nextStage = sg_paired_align_stage2(P, &r, h.stage, h.nLVCand);
+            } else {
+                __syncwarp();
+                sg_paired_align_stage3(P, rb, rq, ln, &r, h.stage);
+            }
         } else {
             memset(&r, 0, sizeof(r));
             if (firstPass) cTotal += 2;
@@ -381,46 +388,49 @@ sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid
                 continue;
             }
             if (STAGE == 1) {
-                int nLV = 0;
-                const int st = sg_paired_align_stage1(P, rb, rq, ln, &r, &nLV);
-                if (st != 0 && !P.error) {
-                    // hand the pair over to stage 2
-                    unsigned long long base = 0;
-                    if (nLV > 0) {
-                        if (lane == 0) base = atomicAdd(candPoolUsed, (unsigned long long)nLV);
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (base + (unsigned long long)nLV > candPoolCap) P.error = 4;       // hand-off pool exhausted: the retry pass does the pair whole
-                    }
-                    if (!P.error) {
-                        __syncwarp();
-                        for (uint32_t k = lane; k < (uint32_t)nLV * (sizeof(r) / 4); k += 32) ((uint32_t *)(candPool + base))[k] = ((const uint32_t *)P.ps.lvCandidates)[k];
-                        for (uint32_t k = lane; k < sizeof(r) / 4; k += 32) ((uint32_t *)&results[i])[k] = ((const uint32_t *)&r)[k];
-                        if (lane == 0) {
-                            SgPairHandoff o;
-                            o.stage = st; o.nLVCand = nLV; o.candBase = base;
-                            o.work[0] = S.work.lookups - workBefore.lookups; o.work[1] = S.work.entriesProbed - workBefore.entriesProbed;
-                            o.work[2] = S.work.overflowWords - workBefore.overflowWords; o.work[3] = S.work.lvCalls - workBefore.lvCalls;
-                            o.work[4] = S.work.agCalls - workBefore.agCalls; o.work[5] = S.work.popularIgnored - workBefore.popularIgnored;
-                            o.work[6] = P.lvCalls - lvBefore; o.work[7] = P.agCalls - agBefore;
-                            handoff[i] = o;
-                        }
-                        __syncwarp();
-                        S.work = workBefore; P.lvCalls = lvBefore; P.agCalls = agBefore;       // (they travel with the pair)
-                        continue;
-                    }
-                }
-                if (lane == 0) handoff[i].stage = 0;
+                nextStage = sg_paired_align_stage1(P, rb, rq, ln, &r, &nLV);
+                if (STAGE == 1) { h.candBase = 0; for (int k = 0; k < 8; k++) h.work[k] = 0; }
             } else {
                 sg_paired_align(P, rb, rq, ln, &r);
             }
         }
+        if ((STAGE == 1 || STAGE == 2) && nextStage != 0 && !P.error) {
+            // hand the pair over to the next stage's kernel; its work so far travels with it
+            if (STAGE == 1 && nLV > 0) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(candPoolUsed, (unsigned long long)nLV);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + (unsigned long long)nLV > candPoolCap) P.error = 4;       // hand-off pool exhausted: the retry pass does the pair whole
+                h.candBase = base;
+            }
+            if (!P.error) {
+                __syncwarp();
+                if (STAGE == 1) {
+                    for (uint32_t k = lane; k < (uint32_t)nLV * (sizeof(r) / 4); k += 32) ((uint32_t *)(candPool + h.candBase))[k] = ((const uint32_t *)P.ps.lvCandidates)[k];
+                }
+                for (uint32_t k = lane; k < sizeof(r) / 4; k += 32) ((uint32_t *)&results[i])[k] = ((const uint32_t *)&r)[k];
+                if (lane == 0) {
+                    SgPairHandoff o;
+                    o.stage = nextStage; o.nLVCand = nLV; o.candBase = h.candBase;
+                    o.work[0] = h.work[0] + (S.work.lookups - workBefore.lookups); o.work[1] = h.work[1] + (S.work.entriesProbed - workBefore.entriesProbed);
+                    o.work[2] = h.work[2] + (S.work.overflowWords - workBefore.overflowWords); o.work[3] = h.work[3] + (S.work.lvCalls - workBefore.lvCalls);
+                    o.work[4] = h.work[4] + (S.work.agCalls - workBefore.agCalls); o.work[5] = h.work[5] + (S.work.popularIgnored - workBefore.popularIgnored);
+                    o.work[6] = h.work[6] + (P.lvCalls - lvBefore); o.work[7] = h.work[7] + (P.agCalls - agBefore);
+                    handoff[i] = o;
+                }
+                __syncwarp();
+                S.work = workBefore; P.lvCalls = lvBefore; P.agCalls = agBefore;
+                continue;
+            }
+        }
+        if (STAGE == 1 || STAGE == 2) { if (lane == 0) handoff[i].stage = 0; }      // final here (or queued for the retry pass)
         if (P.error == 4 && firstPass) {
             // this arena's pools are too small for the pair: hand it to the retry pass (and do not count the aborted work)
             if (lane == 0) retryList[atomicAdd(retryCount, 1ULL)] = (uint32_t)i;
             S.work = workBefore; P.lvCalls = lvBefore; P.agCalls = agBefore;
             continue;
         }
-        if (STAGE == 2) {
+        if (STAGE >= 2) {
             S.work.lookups += h.work[0]; S.work.entriesProbed += h.work[1]; S.work.overflowWords += h.work[2]; S.work.lvCalls += h.work[3];
             S.work.agCalls += h.work[4]; S.work.popularIgnored += h.work[5]; P.lvCalls += h.work[6]; P.agCalls += h.work[7];
         }
@@ -1046,7 +1056,7 @@ int snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params
         a->candPoolCap = perPair * (unsigned long long)maxBatchPairs;
         if (cudaMalloc(&a->d_handoff, (size_t)maxBatchPairs * sizeof(SgPairHandoff)) != cudaSuccess ||
             cudaMalloc((void **)&a->d_candPool, (size_t)a->candPoolCap * sizeof(snapgpu_paired_result)) != cudaSuccess ||
-            cudaMalloc((void **)&a->d_candPoolUsed, 8) != cudaSuccess || cudaMalloc((void **)&a->d_next3, 8) != cudaSuccess) {
+            cudaMalloc((void **)&a->d_candPoolUsed, 8) != cudaSuccess || cudaMalloc((void **)&a->d_next3, 16) != cudaSuccess) {
             std::string msg = std::string("snapgpu_paired_aligner_create: hand-off buffers: ") + cudaGetErrorString(cudaGetLastError());
             snapgpu_aligner_destroy(a);
             return sg_fail(msg);
@@ -1134,11 +1144,14 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
         else SG_LAUNCH(2, STAGE, GRID, PP, SCRATCH, BYTES, NEXT, LIST)
         if (a->staged) {
             SG_CUDA(cudaMemsetAsync(a->d_candPoolUsed, 0, 8, st));
-            SG_CUDA(cudaMemsetAsync(a->d_next3, 0, 8, st));
+            SG_CUDA(cudaMemsetAsync(a->d_next3, 0, 16, st));
             SG_LAUNCH_MB(1, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
             SG_CUDA(cudaGetLastError());
             a->launches++;
             SG_LAUNCH_MB(2, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next3, (const uint32_t *)nullptr);
+            SG_CUDA(cudaGetLastError());
+            a->launches++;
+            SG_LAUNCH_MB(3, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next3 + 1, (const uint32_t *)nullptr);
         } else {
             SG_LAUNCH_MB(0, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
         }

@@ -311,7 +311,27 @@ int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *qual
         sg_paired_restore_reads(a->P, rb, rq, ln);
         for (int k = 0; k < h.nLVCand; k++) a->P.ps.lvCandidates[k] = h.cands[k];
         a->P.error = 0;
-        sg_paired_align_stage2(a->P, rb, rq, ln, r, h.stage, h.nLVCand);
+        h.stage = sg_paired_align_stage2(a->P, r, h.stage, h.nLVCand);
+        if (a->P.error == 0 && h.stage != 0) continue;          // on to stage 3
+        h.stage = 0;
+        if (a->P.error == 4 && a->big) {
+            a->retried++;
+            memset(r, 0, sizeof(*r));
+            a->big->P.error = 0;
+            sg_paired_align(a->big->P, rb, rq, ln, r);
+            if (a->big->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
+            continue;
+        }
+        if (a->P.error) { g_err = "paired candidate pool / buffer overflow"; return 2; }
+    }
+    for (int64_t i = 0; a->staged && i < nPairs; i++) {
+        Handoff &h = hand[i];
+        if (h.stage == 0) continue;
+        snapgpu_paired_result *r = &results[i];
+        const uint8_t *rb[2], *rq[2]; uint32_t ln[2];
+        for (int w = 0; w < 2; w++) { rb[w] = (const uint8_t *)bases + offsets[2 * i + w]; rq[w] = (const uint8_t *)quals + offsets[2 * i + w]; ln[w] = lens[2 * i + w]; }
+        a->P.error = 0;
+        sg_paired_align_stage3(a->P, rb, rq, ln, r, h.stage);
         if (a->P.error == 4 && a->big) {
             a->retried++;
             memset(r, 0, sizeof(*r));

@@ -290,7 +290,7 @@ def test_pairs_large_index_and_split_batches(engine, small_cfg, reflib):
     assert differing_pairs(want, got) == []
     small = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 100)
     got2, c2 = small.align(pb)
-    assert differing_pairs(want, got2) == [] and c1["lvCalls"] == c2["lvCalls"] and small.launch_count() == 3 * ((pb.n // 2 + 99) // 100)      # stage 1 + stage 2 + retry launch per batch
+    assert differing_pairs(want, got2) == [] and c1["lvCalls"] == c2["lvCalls"] and small.launch_count() == 4 * ((pb.n // 2 + 99) // 100)      # three stages + retry launch per batch
     big.close(); small.close(); ix.close()
 
 
