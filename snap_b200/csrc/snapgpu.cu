@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <new>
 
 #define SG_WITH_PAIRED 1
@@ -85,6 +86,7 @@ struct snapgpu_aligner {
     int numSMs = 0;
     int warpsPerBlock = 8, blocksPerSM = 4;
     int pass1BlocksPerSM = 4;            // resident CTAs per SM of the first (no affine gap) pass of the two-pass single-end launch
+    int stageBlocks[4] = {4, 8, 4, 8};   // paired staged launch: resident CTAs per SM of stage 1, 2, 3 ([0] unused)
     int nWorkers = 0;
     size_t scratchBytesPerWorker = 0;
     uint8_t *d_scratch = nullptr;
@@ -913,7 +915,16 @@ static int aligner_init_common(snapgpu_aligner *a, int64_t maxBatchReads, int64_
     a->pass1BlocksPerSM = 8;             // measured (M reads/s, 3 Gbp, 150 bp): 4 -> 13.49, 5 -> 13.66, 6 -> 13.75, 8 -> 13.94 (32 registers, no extra spills)
     if (const char *e = getenv("SNAPGPU_PASS1_BLOCKS_PER_SM")) a->pass1BlocksPerSM = atoi(e);
     if (a->pass1BlocksPerSM < 3 || a->pass1BlocksPerSM > 8 || a->pass1BlocksPerSM == 7 || readsPerUnit != 1) a->pass1BlocksPerSM = a->blocksPerSM;
-    a->nWorkers = a->numSMs * (a->blocksPerSM > a->pass1BlocksPerSM ? a->blocksPerSM : a->pass1BlocksPerSM) * a->warpsPerBlock;
+    int maxBlocks = a->blocksPerSM > a->pass1BlocksPerSM ? a->blocksPerSM : a->pass1BlocksPerSM;
+    if (readsPerUnit == 2) {
+        // measured (stock snap paired, M reads/s): 4,4,4 -> 7.71; 8,4,4 -> 8.08; 8,4,8 -> 8.42; 8,6,8 -> 8.46
+        if (const char *e = getenv("SNAPGPU_PAIRED_STAGE_BLOCKS")) sscanf(e, "%d,%d,%d", &a->stageBlocks[1], &a->stageBlocks[2], &a->stageBlocks[3]);
+        for (int k = 1; k <= 3; k++) {
+            if (a->stageBlocks[k] != 6 && a->stageBlocks[k] != 8) a->stageBlocks[k] = 4;
+            if (a->stageBlocks[k] > maxBlocks) maxBlocks = a->stageBlocks[k];
+        }
+    }
+    a->nWorkers = a->numSMs * maxBlocks * a->warpsPerBlock;
     if ((int64_t)a->nWorkers > maxUnits) {
         int blocks = (int)((maxUnits + a->warpsPerBlock - 1) / a->warpsPerBlock);
         a->nWorkers = blocks * a->warpsPerBlock;
@@ -1104,7 +1115,7 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
         a->d_scratch, a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, \
         d_lens, (snapgpu_single_result *)d_results, d_counters, NEXT, a->d_retryCount, a->d_retryList)
 #define SG_LAUNCH_MB(MODE, GRID, NEXT) if (a->blocksPerSM >= 4) SG_LAUNCH(4, MODE, GRID, NEXT); else if (a->blocksPerSM == 3) SG_LAUNCH(3, MODE, GRID, NEXT); \
-        else SG_LAUNCH(2, MODE, GRID, NEXT)
+        else SG_LAUNCH(2, MODE, GRID, NEXT)      /* second pass measured the same at 4, 5 and 6 CTAs/SM (17.2 M reads/s) */
         if (a->twoPass) {
             SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));
             SG_CUDA(cudaMemsetAsync(a->d_next2, 0, 8, st));
@@ -1145,13 +1156,20 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
         if (a->staged) {
             SG_CUDA(cudaMemsetAsync(a->d_candPoolUsed, 0, 8, st));
             SG_CUDA(cudaMemsetAsync(a->d_next3, 0, 16, st));
-            SG_LAUNCH_MB(1, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
+#define SG_GRID(K) ((int)((std::min<int64_t>(std::min<int64_t>((int64_t)a->numSMs * a->stageBlocks[K] * a->warpsPerBlock, a->nWorkers), n) + a->warpsPerBlock - 1) / a->warpsPerBlock))
+#define SG_LAUNCH_STAGE(K, NEXT) \
+            if (a->stageBlocks[K] == 8) SG_LAUNCH(8, K, SG_GRID(K), a->pparams, a->d_scratch, a->scratchBytesPerWorker, NEXT, (const uint32_t *)nullptr); \
+            else if (a->stageBlocks[K] == 6) SG_LAUNCH(6, K, SG_GRID(K), a->pparams, a->d_scratch, a->scratchBytesPerWorker, NEXT, (const uint32_t *)nullptr); \
+            else SG_LAUNCH(4, K, SG_GRID(K), a->pparams, a->d_scratch, a->scratchBytesPerWorker, NEXT, (const uint32_t *)nullptr)
+            SG_LAUNCH_STAGE(1, a->d_next);
             SG_CUDA(cudaGetLastError());
             a->launches++;
-            SG_LAUNCH_MB(2, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next3, (const uint32_t *)nullptr);
+            SG_LAUNCH_STAGE(2, a->d_next3);
             SG_CUDA(cudaGetLastError());
             a->launches++;
-            SG_LAUNCH_MB(3, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next3 + 1, (const uint32_t *)nullptr);
+            SG_LAUNCH_STAGE(3, a->d_next3 + 1);
+#undef SG_LAUNCH_STAGE
+#undef SG_GRID
         } else {
             SG_LAUNCH_MB(0, blocks, a->pparams, a->d_scratch, a->scratchBytesPerWorker, a->d_next, (const uint32_t *)nullptr);
         }
