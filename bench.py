@@ -7,7 +7,8 @@ A "step" is one pass of the hot path (seed lookup + LV / affine-gap scoring, Bas
 one batch of synthetic reads.  `value` = reads of all ranks per second with the inputs already resident in HBM,
 timed with CUDA events around exactly K steps (max over ranks).  `e2e` = the same metric through the C ABI call a
 SNAP extension makes (snapgpu_align_single) with HOST buffers: host->device copies of the reads and device->host
-copy of the results inside the timed region.  `roofline` is for the dominant kernel (sg_align_kernel);
+copy of the results inside the timed region.  `roofline` is for the step's alignment launches taken together (two for
+sg_align_kernel's two-pass form, four for the staged sg_align_paired_kernel), timed with CUDA events on their stream;
 `seed_phase` is the seed-lookup kernel run in isolation over every seed of the batch (BASELINE's second metric).
 `cpu_baseline` / `--impl reference` time the UNMODIFIED reference (oracle/_ref, compiled from /root/reference) on the
 host cores, on a bounded sample of the same workload, against the same index written out in the reference's own
@@ -61,7 +62,7 @@ def parse_args():
 
 
 def measured_traffic(workload, batch_reads, genome_mbp):
-    """DRAM bytes of ONE launch of the alignment kernel from the committed `ncu --set full` capture of this same workload
+    """DRAM bytes of ONE step's alignment launches (summed) from the committed `ncu --set full` capture of this same workload
     (profiles/traffic.json, written by profiles/extract_traffic.py); None when the capture is of another configuration."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -258,16 +259,19 @@ def run_ours(args):
     e2e_s = shard.max_over_ranks(e2e_s, device) if world > 1 else e2e_s
     e2e_value = n_e2e * world / e2e_s
 
-    # ---- roofline of the dominant kernel (one sg_align_kernel launch per step) ----
+    # ---- roofline of the step's alignment kernels (sg_align_kernel: pass 1 + pass 2 launches; sg_align_paired_kernel: three
+    #      stage launches + the retry launch), timed together with CUDA events: algorithmic bytes of the step / its duration ----
     peak, peak_src = measured_peaks()
     per_launch = 1.0 / (K * world)
     alg_bytes = (c["nHashEntriesProbed"] * 8 + c["nOverflowWordsRead"] * 4 + (c["lvCalls"] + c["affineGapCalls"]) * ALG_BYTES_PER_CANDIDATE
                  + c["totalReads"] * (2 * READ_LEN + result_bytes_per_read)) * per_launch
     kernel_ms_avg = float(np.mean(kernel_ms))
     achieved = alg_bytes / (kernel_ms_avg / 1e3) / 1e9
-    roofline = {"kernel": "sg_align_paired_kernel" if paired else "sg_align_kernel", "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": ("sg_align_paired_kernel<.,1..3> (staged launch: seed/LV, affine gap, single-end fallback) + retry pass" if paired else
+                           "sg_align_kernel<.,1> + <.,2> (two-pass launch: without affine gap, then the deferred reads)"),
+                "launches_per_step": round(launches / K, 2), "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 6), "traffic": measured_traffic(args.workload, B, args.genome_mbp), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(kernel_ms_avg, 3),
+                "algorithmic_bytes_per_step": int(alg_bytes), "avg_step_ms": round(kernel_ms_avg, 3),
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
 
     out = {

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Pull dram__bytes_read.sum + dram__bytes_write.sum (one launch, `ncu --set full`) out of .ncu-rep files and record them in
-profiles/traffic.json, which bench.py quotes as roofline.traffic when it runs the same workload.
+"""Pull dram__bytes_read.sum + dram__bytes_write.sum (`ncu --set full`) out of .ncu-rep files and record them in
+profiles/traffic.json, which bench.py quotes as roofline.traffic when it runs the same workload.  A report holds the launches of
+ONE step (two for the single-end two-pass launch, four for the staged paired launch); their bytes are summed.
 usage: extract_traffic.py KEY REPORT.ncu-rep "description of the captured command" [KEY REPORT DESC ...]"""
 import csv, io, json, os, subprocess, sys
 
@@ -20,13 +21,22 @@ def main():
         key, rep, desc = args[k], args[k + 1], args[k + 2]
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
-        hdr, units, vals = rows[0], rows[1], rows[2]
+        hdr, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(hdr)}
-        rd = to_bytes(vals[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
-        wr = to_bytes(vals[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-        dur = vals[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]]
-        data[key] = {"dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr), "kernel": vals[col["Kernel Name"]][:60],
-                     "duration_under_ncu": dur, "captured_with": desc, "report": os.path.basename(rep)}
+        rd = wr = 0.0
+        per_launch = []
+        for vals in rows[2:]:
+            if len(vals) != len(hdr):
+                continue
+            r = to_bytes(vals[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
+            w = to_bytes(vals[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+            if r != r or w != w:          # a launch too short for the DRAM counters (e.g. the empty retry pass)
+                r = w = 0.0
+            rd += r; wr += w
+            per_launch.append({"kernel": vals[col["Kernel Name"]][:40], "dram_bytes": int(r + w),
+                               "duration_under_ncu": vals[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]]})
+        data[key] = {"dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr), "launches": per_launch,
+                     "captured_with": desc, "report": os.path.basename(rep)}
         print(key, data[key])
     json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
 
