@@ -372,6 +372,75 @@ def test_pairs_tiny_pool_caps_take_the_retry_pass(engine, gidx, small_cfg, refli
     al.close()
 
 
+_CTR_KEYS = ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "nHashEntriesProbed", "nOverflowWordsRead",
+             "lvCalls", "affineGapCalls", "nHitsIgnoredBecauseOfTooHighPopularity", "mapqHistogram")
+
+
+@pytest.mark.parametrize("opt", ["default_d14", "ag_d20", "noag_d14", "ne_d20", "stopfirst"])
+def test_single_launch_forms_agree(engine, gidx, small_cfg, reflib, monkeypatch, opt):
+    """The two-pass launch (first pass without the affine-gap code, deferred reads again from scratch) and the one-launch
+    form give the same records AND the same counters; with affine gap off the second pass has nothing to do, under -ne
+    (where the library would not choose the two-pass form itself) every read is deferred."""
+    p = engine.default_params(**OPTION_SETS[opt])
+    rb = small_cfg.reads["noisy150"]
+    want, wctr = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params(**OPTION_SETS[opt])).align(rb)
+    out = {}
+    for form in ("1", "0"):
+        monkeypatch.setenv("SNAPGPU_TWO_PASS", form)
+        al = engine.SingleAligner(gidx, p, 4096)
+        got, ctr = al.align(rb)
+        out[form] = (got, ctr, al.launch_count())
+        al.close()
+        assert differing(want, got) == [], (opt, form)
+        for k in ("totalReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "lvCalls", "affineGapCalls", "mapqHistogram"):
+            assert wctr[k] == ctr[k], (opt, form, k)
+    for k in _CTR_KEYS:
+        assert out["1"][1][k] == out["0"][1][k], (opt, k)
+    assert out["0"][2] == 1 and out["1"][2] == 2
+
+
+@pytest.mark.parametrize("opt", ["default_d27", "hc_d14", "hc_noag", "hc_forcespacing"])
+def test_paired_launch_forms_agree(engine, gidx, small_cfg, reflib, monkeypatch, opt):
+    """Staged launch (three stage kernels + retry pass) vs the one-launch form: same records, same counters."""
+    kw, pkw = PAIRED_OPTION_SETS[opt]
+    p, pp = engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw)
+    out = {}
+    for form in ("1", "0"):
+        monkeypatch.setenv("SNAPGPU_PAIRED_STAGED", form)
+        al = engine.PairedAligner(gidx, p, pp, 2048)
+        res = [al.align(small_cfg.pairs[name]) for name in ("noisy150", "clipped150")]
+        out[form] = res
+        al.close()
+    for (a, ca), (b, cb) in zip(out["1"], out["0"]):
+        assert differing_pairs(a, b) == [], opt
+        for k in _CTR_KEYS:
+            assert ca[k] == cb[k], (opt, k)
+
+
+@pytest.mark.parametrize("per_pair,cand_cap", [("1", "512"), ("4", "8")])
+def test_paired_handoff_pool_exhaustion_takes_the_retry_pass(engine, gidx, small_cfg, reflib, monkeypatch, per_pair, cand_cap):
+    """Stage 1 hands its phase-4 candidates over through a pool of `per_pair` records per pair of the batch.  A batch sized
+    1 gives a pool too small for almost any pair with candidates: those pairs must come back, unchanged, from the retry pass
+    (which runs the whole function); so must pairs that overflow a small candidate buffer in stage 3."""
+    monkeypatch.setenv("SNAPGPU_PAIRED_HANDOFF_PER_PAIR", per_pair)
+    monkeypatch.setenv("SNAPGPU_PAIRED_CAND_CAP", cand_cap)
+    kw, pkw = PAIRED_OPTION_SETS["default_d14"]
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    pb = small_cfg.pairs["clipped150"]
+    want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), p, pp).align(pb)
+    n_batch = 1 if per_pair == "1" else 2048
+    al = engine.PairedAligner(gidx, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), n_batch)
+    if n_batch == 1:
+        from snap_b200 import synth
+        sub = pb.slice(0, 120)
+        got = np.concatenate([al.align(sub.slice(2 * i, 2 * i + 2))[0] for i in range(sub.n // 2)])
+        assert differing_pairs(want[:sub.n // 2], got) == []
+    else:
+        got, _ = al.align(pb)
+        assert differing_pairs(want, got) == []
+    al.close()
+
+
 
 def _same_fastq(want, got):
     names = ("bases", "quals", "offsets", "lens", "id_offsets", "id_lens", "front_clipped")
