@@ -15,13 +15,14 @@
 #endif
 
 // Affine-gap leaf dispatch: on the device with a converged warp (lane >= 0) the rows are spread over the lanes.
+template <int AGM = 0>
 SG_HD void sg_ag_dispatch(const SgTables &T, const SgScratch &S, const SgAgParams &P, int dir, bool banded,
                           const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
                           int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out, int lane)
 {
 #if defined(__CUDA_ARCH__)
     // every device caller is a converged warp (lane >= 0); the scalar form is not compiled into the kernels
-    sg_warp_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out, lane);
+    sg_warp_ag_compute<AGM>(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out, lane);
 #else
     (void)lane;
     sg_ag_compute(T, S, P, dir, banded, text, textLen, pattern, quality, patternLen, w, scoreInit, isRC, useClippingOptimizations, out);

@@ -26,6 +26,7 @@ struct SgPairedParams {
     // capacities of THIS worker's arena (<= the reference's poolSize / 4096): a pair that needs more is retried by a worker
     // with full-size pools (error code 4) -- results do not depend on the caps
     uint32_t poolCap, agCandCap;
+    int32_t  stage2Packed;              // device tuning knob (no effect on results): SgAgParams.usePacked of stage 2 (1 loop-compact, 2 unrolled)
 };
 
 struct SgHitLookup {                 // HashTableLookup<unsigned>, IntersectingPairedEndAligner.h
@@ -366,6 +367,7 @@ struct SgPairedAligner {
 };
 
 // IntersectingPairedEndAligner::scoreLocationWithAffineGap (:3119-3282).  useAltLiftover is always false here.
+template <int AGM = 0>
 SG_HDN void sg_paired_score_location_ag(SgPairedAligner &P, uint32_t whichRead, int direction, int64_t genomeLocation, uint32_t seedOffset, int scoreLimit,
                                         int *score, double *matchProbability, int *genomeLocationOffset, int *basesClippedBefore, int *basesClippedAfter,
                                         int *agScore, int *genomeSpan)
@@ -393,7 +395,7 @@ SG_HDN void sg_paired_score_location_ag(SgPairedAligner &P, uint32_t whichRead, 
         int patternLen = readLen - tailStart;
         bool banded = (patternLen >= (3 * (2 * scoreLimit + 1))) && !pr.noBandedAffineGap;
         ar.textOffset = textRem; ar.patternOffset = *basesClippedAfter; ar.nEdits = score1; ar.matchProbability = matchProb1; ar.agScore = -1;
-        sg_ag_dispatch(T, sc, P.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, patternLen, scoreLimit, readLen,
+        sg_ag_dispatch<AGM>(T, sc, P.ag, 1, banded, data + tailStart, textLen, readToScore + tailStart, qualToScore + tailStart, patternLen, scoreLimit, readLen,
                        direction != 0, P.pp->useSoftClip != 0, &ar, sg_lane());
         agScore1 = ar.agScore; textRem = ar.textOffset; *basesClippedAfter = ar.patternOffset; score1 = ar.nEdits; matchProb1 = ar.matchProbability;
         agScore1 += (seedLen - readLen);
@@ -405,7 +407,7 @@ SG_HDN void sg_paired_score_location_ag(SgPairedAligner &P, uint32_t whichRead, 
             int patternLen = (int)seedOffset;
             bool banded = (patternLen >= (3 * (2 * limitLeft + 1))) && !pr.noBandedAffineGap;
             ar.textOffset = *genomeLocationOffset; ar.patternOffset = *basesClippedBefore; ar.nEdits = score2; ar.matchProbability = matchProb2; ar.agScore = -1;
-            sg_ag_dispatch(T, sc, P.ag, -1, banded, data + seedOffset, (int)seedOffset + limitLeft, P.ps.revRead[whichRead][direction] + readLen - seedOffset,
+            sg_ag_dispatch<AGM>(T, sc, P.ag, -1, banded, data + seedOffset, (int)seedOffset + limitLeft, P.ps.revRead[whichRead][direction] + readLen - seedOffset,
                            P.readQual[whichRead][1 - direction] + readLen - seedOffset, patternLen, limitLeft, readLen, direction != 0,
                            P.pp->useSoftClip != 0, &ar, sg_lane());
             agScore2 = ar.agScore; *genomeLocationOffset = ar.textOffset; *basesClippedBefore = ar.patternOffset; score2 = ar.nEdits; matchProb2 = ar.matchProbability;
@@ -966,6 +968,7 @@ SG_HDN bool sg_paired_align_lv(SgPairedAligner &P, const uint8_t *const readBase
 }
 
 // IntersectingPairedEndAligner::alignAffineGap (:2489-2969), phase 4.  No ALT contigs => firstALTResult is always NotFound.
+template <int AGM = 0>
 SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result, int *nLVCandidatesForAffineGap)
 {
     const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp; const SgTables &T = *P.tb;
@@ -986,7 +989,7 @@ SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result
         if (result->usedGaplessClipping[r] || result->score[r] > maxKForSameAlignment) {
             result->usedAffineGapScoring[r] = 1;
             if (!result->usedGaplessClipping[r]) scoreLimit = scoreLimit > result->score[r] ? scoreLimit : result->score[r];
-            sg_paired_score_location_ag(P, (uint32_t)r, result->direction[r], result->origLocation[r], (uint32_t)result->seedOffset[r], scoreLimit, &result->score[r],
+            sg_paired_score_location_ag<AGM>(P, (uint32_t)r, result->direction[r], result->origLocation[r], (uint32_t)result->seedOffset[r], scoreLimit, &result->score[r],
                                         &result->matchProbability[r], &genomeOffset[r], &result->basesClippedBefore[r], &result->basesClippedAfter[r],
                                         &result->agScore[r], &result->refSpan[r]);
             if (result->score[r] != SG_SCORE_ABOVE_LIMIT) {
@@ -1052,7 +1055,7 @@ SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result
                 if (!skipAffineGap[0]) {
                     lv->usedAffineGapScoring[0] = 1;
                     if (!lv->usedGaplessClipping[0]) scoreLimit = scoreLimit > lv->score[0] ? scoreLimit : lv->score[0];
-                    sg_paired_score_location_ag(P, 0, lv->direction[0], lv->origLocation[0], (uint32_t)lv->seedOffset[0], scoreLimit, &lv->score[0], &lv->matchProbability[0],
+                    sg_paired_score_location_ag<AGM>(P, 0, lv->direction[0], lv->origLocation[0], (uint32_t)lv->seedOffset[0], scoreLimit, &lv->score[0], &lv->matchProbability[0],
                                                 &genomeOffset[0], &lv->basesClippedBefore[0], &lv->basesClippedAfter[0], &lv->agScore[0], &lv->refSpan[0]);
                 }
                 if ((lv->score[0] != SG_SCORE_ABOVE_LIMIT) && (lv->score[0] <= SG_MAX_K - 1)) {
@@ -1061,7 +1064,7 @@ SG_HDN void sg_paired_align_ag(SgPairedAligner &P, snapgpu_paired_result *result
                         lv->usedAffineGapScoring[1] = 1;
                         scoreLimit = scoreLimit - lv->score[0];
                         if (!lv->usedGaplessClipping[1]) scoreLimit = scoreLimit > lv->score[1] ? scoreLimit : lv->score[1];
-                        sg_paired_score_location_ag(P, 1, lv->direction[1], lv->origLocation[1], (uint32_t)lv->seedOffset[1], scoreLimit, &lv->score[1], &lv->matchProbability[1],
+                        sg_paired_score_location_ag<AGM>(P, 1, lv->direction[1], lv->origLocation[1], (uint32_t)lv->seedOffset[1], scoreLimit, &lv->score[1], &lv->matchProbability[1],
                                                     &genomeOffset[1], &lv->basesClippedBefore[1], &lv->basesClippedAfter[1], &lv->agScore[1], &lv->refSpan[1]);
                     }
                     if ((lv->score[1] != SG_SCORE_ABOVE_LIMIT) && (lv->score[1] <= SG_MAX_K - 1)) {
@@ -1159,13 +1162,14 @@ SG_HDN int sg_paired_align_stage1(SgPairedAligner &P, const uint8_t *const readB
 // stage 2 (the affine-gap phase of the intersecting aligner) returns 0: `result` is final; 1: continue with the single-end
 // aligner on both reads (stage 3); 2: the same, comparing its result with the pair's (compareWithSingleEndAlignment).
 // Only `result` and that value cross this cut.
+template <int AGM = 0>
 SG_HDN int sg_paired_align_stage2(SgPairedAligner &P, snapgpu_paired_result *result, int stage, int nLVCand)
 {
     const SgParams &pr = *P.pr; const SgPairedParams &pp = *P.pp;
     bool compareWithSingleEndAlignment = false;
     if (stage == 1) {
         P.maxK = (int)pr.maxK;
-        if (pr.useAffineGap) sg_paired_align_ag(P, result, &nLVCand);
+        if (pr.useAffineGap) sg_paired_align_ag<AGM>(P, result, &nLVCand);
         result->alignedAsPair = 1;
         if (pp.forceSpacing) {
             if (result->status[0] == SNAPGPU_NOT_FOUND) result->alignedAsPair = 0;

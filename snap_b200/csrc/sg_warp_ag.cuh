@@ -139,6 +139,8 @@ __device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int ope
 }
 
 
+// AGM: 2 = the caller's kernel may take the unrolled packed instantiation (only stage 2 of the paired launch carries that code)
+template <int AGM = 0>
 __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParams &P, int dir, bool banded,
                                                 const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
                                                 int w, int scoreInit, bool isRC, bool useClippingOptimizations, SgAgResult *out, int lane)
@@ -198,7 +200,8 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         // unbanded, up to 192 columns: the packed (two cells per lane, DPX s16x2) register-resident form
         __syncwarp();
         SgAgBests bb;
-        sg_warp_ag_rows_packed(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
+        if (AGM == 2 && P.usePacked == 2) sg_warp_ag_rows_packed<true>(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
+        else sg_warp_ag_rows_packed<false>(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
         sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
                      bb.lScore, bb.lText, bb.lPat, bb.gScore, bb.gText, out);
         return;

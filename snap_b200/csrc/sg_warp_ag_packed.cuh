@@ -30,10 +30,14 @@ __device__ __forceinline__ unsigned sg_nzmask2(unsigned x)
 }
 __device__ __forceinline__ unsigned sg_relu2(unsigned x) { return __vimax_s16x2_relu(x, x); }
 
+// UNROLLED: the three block loops unrolled with the blocks in fixed registers (fewer instructions, ~3x the loop code); used where
+// this function is nearly all a kernel runs (stage 2 of the paired launch, which is issue-bound).  Otherwise loop-compact.
+template <bool UNROLLED>
 __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const SgAgParams &P, int dir, const uint8_t *text, int textLen,
                                                     const uint8_t *pattern, int patternLen, int scoreInit, SgAgLayout &lay, uint8_t *bt,
                                                     int lane, SgAgBests *res)
 {
+    constexpr int kBlockUnroll = UNROLLED ? SG_AGP_BLOCKS : 1;
     const int numVec = lay.numVec;
     const int strideW = numVec * 4;                  // 32-bit words per row (8 int16 per vector)
     const int nBlocks = (numVec + 7) >> 3;
@@ -71,10 +75,13 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
         // cache: the kernel is fetch-bound) the block loops are NOT unrolled: each iteration works on (h0, a0) and then rotates
         // (h0,h1,h2) <- (h1,h2,h0); every loop makes exactly SG_AGP_BLOCKS rotations, so the registers end up in place again.
         unsigned h0 = 0, h1r = 0, h2 = 0, a0 = 0, a1 = 0, a2r = 0;
+        unsigned hreg[SG_AGP_BLOCKS], areg[SG_AGP_BLOCKS];          // UNROLLED form: block b in (hreg[b], areg[b])
+        #define SG_HB (*(UNROLLED ? &hreg[b] : &h0))
+        #define SG_AB (*(UNROLLED ? &areg[b] : &a0))
         unsigned fcarry = 0;                         // F entering the next vector of SSE lanes (2a, 2a+1); identical for all qq
 
         // ---------------- main pass: 8 vectors per step ----------------
-        #pragma unroll 1
+        #pragma unroll kBlockUnroll
         for (int b = 0; b < SG_AGP_BLOCKS; b++) {
             unsigned hnew = 0, anew = 0;
             if (b < nBlocks) {
@@ -117,8 +124,11 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
                 const unsigned gl = __shfl_sync(0xffffffffu, g, (nv - 1) * 4 + a);
                 fcarry = __vimax_s16x2_relu(gl, __vadd2(fcarry, sg_pk2(-nv * ext)));
             }
-            h0 = h1r; h1r = h2; h2 = hnew;           // rotate: after the loop (h0,h1r,h2) = blocks (0,1,2)
-            a0 = a1; a1 = a2r; a2r = anew;
+            if (UNROLLED) { hreg[b] = hnew; areg[b] = anew; }
+            else {
+                h0 = h1r; h1r = h2; h2 = hnew;       // rotate: after the loop (h0,h1r,h2) = blocks (0,1,2)
+                a0 = a1; a1 = a2r; a2r = anew;
+            }
         }
 
         // ---------------- lazy F (:1080-1112): whole blocks evaluated at once, committed up to the first vector at which
@@ -129,14 +139,14 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
         for (int kk = 0; kk < SG_VEC && !converged; kk++) {
             const unsigned below = __shfl_up_sync(0xffffffffu, fl, 1);
             fl = (fl << 16) | (a == 0 ? 0u : (below >> 16));                       // f = f << one SSE lane
-            #pragma unroll 1
+            #pragma unroll kBlockUnroll
             for (int b = 0; b < SG_AGP_BLOCKS; b++) {
                 if (b < nBlocks && !converged) {
                     const int k = 8 * b + qq;
                     const bool valid = k < numVec;
                     bool hgeHi, hgeLo, tgeHi, tgeLo;
                     const unsigned fv = __viaddmax_s16x2_relu(fl, sg_pk2(-k * ext), 0u);
-                    const unsigned newh = __vibmax_s16x2(h0, fv, &hgeHi, &hgeLo);                  // f > h
+                    const unsigned newh = __vibmax_s16x2(SG_HB, fv, &hgeHi, &hgeLo);               // f > h
                     const unsigned temp = __viaddmax_s16x2_relu(newh, nOpen2, 0u);
                     const unsigned fn = __viaddmax_s16x2_relu(fv, nExt2, 0u);
                     (void)__vibmax_s16x2(temp, fn, &tgeHi, &tgeLo);                                // f - ext > h - open
@@ -146,8 +156,8 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
                     const unsigned z = (liveMask - 0x11111111u) & ~liveMask & 0x88888888u & (nv >= 8 ? 0xffffffffu : ((1u << (4 * nv)) - 1u));
                     const int firstConv = z ? ((__ffs(z) - 1) >> 2) : 8;
                     if (valid && qq <= firstConv) {
-                        h0 = newh;
-                        a0 |= ((hgeLo ? 0u : 2u) | (tgeLo ? 0u : 32u)) | (((hgeHi ? 0u : 2u) | (tgeHi ? 0u : 32u)) << 8);
+                        SG_HB = newh;
+                        SG_AB |= ((hgeLo ? 0u : 2u) | (tgeLo ? 0u : 32u)) | (((hgeHi ? 0u : 2u) | (tgeHi ? 0u : 32u)) << 8);
                     }
                     if (firstConv < 8) converged = true;
                 }
@@ -159,15 +169,15 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
 
         // ---------------- write the row once; per-lane row maximum and the largest column holding it ----------------
         unsigned rmax = 0; int kLo = -1, kHi = -1;
-        #pragma unroll 1
+        #pragma unroll kBlockUnroll
         for (int b = 0; b < SG_AGP_BLOCKS; b++) {
             const int k = 8 * b + qq;
             if (b < nBlocks && k < numVec) {
                 const int w = k * 4 + a;
-                Hm[w] = h0;
-                *(uint16_t *)(btRow + 2 * w) = (uint16_t)a0;
+                Hm[w] = SG_HB;
+                *(uint16_t *)(btRow + 2 * w) = (uint16_t)SG_AB;
                 bool geHi, geLo;
-                rmax = __vibmax_s16x2(h0, rmax, &geHi, &geLo);
+                rmax = __vibmax_s16x2(SG_HB, rmax, &geHi, &geLo);
                 if (geLo) kLo = k;
                 if (geHi) kHi = k;
             }
@@ -193,5 +203,7 @@ __device__ __noinline__ void sg_warp_ag_rows_packed(const SgScratch &S, const Sg
         unsigned *tmp = Hm; Hm = Hp; Hp = tmp;
     }
     __syncwarp();
+    #undef SG_HB
+    #undef SG_AB
     res->gScore = bestG; res->gText = bestGT; res->lScore = bestL; res->lText = bestLT; res->lPat = bestLP;
 }

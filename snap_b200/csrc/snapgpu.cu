@@ -328,7 +328,7 @@ sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid
     S.agCands = nullptr; S.nAgCands = 0; S.maxAgCands = 0; S.agCandsOverflow = 0;
     sg_scratch_carve(prSingle, arena, &S.sc);
     S.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
-    S.ag.usePacked = 1;          // `snap paired` rescoring is mostly unbanded (wide score limits): the packed form pays here, not in sg_align_kernel
+    S.ag.usePacked = (STAGE == 2) ? pp.stage2Packed : 1;      // `snap paired` rescoring is mostly unbanded (wide score limits): the packed form pays here
     S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     S.nUsedElements = 0;
     S.work.lookups = S.work.entriesProbed = S.work.overflowWords = S.work.lvCalls = S.work.agCalls = S.work.popularIgnored = 0;
@@ -374,7 +374,7 @@ sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid
                 for (uint32_t k = lane; k < (uint32_t)h.nLVCand * (sizeof(r) / 4); k += 32) ((uint32_t *)P.ps.lvCandidates)[k] = ((const uint32_t *)(candPool + h.candBase))[k];
                 __syncwarp();
                 sg_paired_restore_reads(P, rb, rq, ln);
-                nextStage = sg_paired_align_stage2(P, &r, h.stage, h.nLVCand);
+                nextStage = sg_paired_align_stage2<2>(P, &r, h.stage, h.nLVCand);
             } else {
                 __syncwarp();
                 sg_paired_align_stage3(P, rb, rq, ln, &r, h.stage);
@@ -540,7 +540,7 @@ __global__ void sg_test_ag_warp_kernel(const SgTables *tb, SgParams pr, SgAgPara
     for (long long j = wid; j < nJobs; j += nW) {
         SgAgResult r;
         r.agScore = -1; r.textOffset = 0; r.patternOffset = 0; r.nEdits = 0; r.matchProbability = 0.0;
-        sg_warp_ag_compute(*tb, s, P, jobs[j].dir, jobs[j].banded != 0, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff,
+        sg_warp_ag_compute<2>(*tb, s, P, jobs[j].dir, jobs[j].banded != 0, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff,
                            qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].w, jobs[j].scoreInit, jobs[j].isRC != 0,
                            jobs[j].useClippingOptimizations != 0, &r, lane);
         __syncwarp();
@@ -988,7 +988,7 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     // two-pass launch (see sg_align_kernel) whenever some reads can finish without affine gap: not under -ne (every
     // candidate is rescored) ; without affine gap at all the first pass simply finishes everything.  SNAPGPU_TWO_PASS=0 turns it off.
     a->params.agSpecialised = 1;         // second pass: narrow-band / packed affine-gap forms (measured 16.61 -> 17.18 M reads/s; they cost throughput in the one-launch form)
-    if (const char *e = getenv("SNAPGPU_SINGLE_AG_SPECIALISED")) a->params.agSpecialised = atoi(e) != 0;
+    if (const char *e = getenv("SNAPGPU_SINGLE_AG_SPECIALISED")) a->params.agSpecialised = atoi(e);       // 0 off, 1 on, 2 on with the unrolled packed form
     a->twoPass = !a->params.noEditDistance;
     if (const char *e = getenv("SNAPGPU_TWO_PASS")) a->twoPass = atoi(e) != 0;
     if (a->twoPass) {
@@ -1060,6 +1060,9 @@ int snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params
         return sg_fail(msg);
     }
     a->staged = true;
+    a->pparamsBig.stage2Packed = 1;
+    a->pparams.stage2Packed = 2;         // stage 2 is ~90 % this one function and issue-bound: the unrolled instantiation measured 8.36 -> 8.98 M reads/s
+    if (const char *e = getenv("SNAPGPU_PAIRED_STAGE2_PACKED")) a->pparams.stage2Packed = atoi(e) == 2 ? 2 : 1;
     if (const char *e = getenv("SNAPGPU_PAIRED_STAGED")) a->staged = atoi(e) != 0;
     if (a->staged) {
         unsigned long long perPair = 4;      // hand-off candidate records per pair of the batch (a pair that finds the pool full is done whole by the retry pass)
@@ -1550,7 +1553,7 @@ static int test_ag_impl(int device, const snapgpu_ag_params *ap, const char *tex
     if (leaf_scratch(device, &p, &threads, &d_scratch, &bytes, &d_tb)) return 1;
     SgAgParams P = sg_ag_params(ap->matchReward, ap->subPenalty, ap->gapOpenPenalty, ap->gapExtendPenalty, ap->fivePrimeEndBonus, ap->threePrimeEndBonus);
     P.usePacked = 1;                 // leaf tests: the packed form unless SNAPGPU_TEST_AG_PACKED=0 (the tests run both)
-    if (const char *e = getenv("SNAPGPU_TEST_AG_PACKED")) P.usePacked = atoi(e) != 0;
+    if (const char *e = getenv("SNAPGPU_TEST_AG_PACKED")) P.usePacked = atoi(e);        // 0 int form, 1 packed loop-compact, 2 packed unrolled
     uint8_t *d_text, *d_pat, *d_qual; snapgpu_ag_job *d_jobs; snapgpu_ag_out *d_out;
     SG_CUDA(cudaMalloc((void **)&d_text, textBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_pat, patBytes + 16)); SG_CUDA(cudaMalloc((void **)&d_qual, patBytes + 16));
     SG_CUDA(cudaMalloc((void **)&d_jobs, (size_t)nJobs * sizeof(*jobs) + 16)); SG_CUDA(cudaMalloc((void **)&d_out, (size_t)nJobs * sizeof(*out) + 16));

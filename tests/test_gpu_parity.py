@@ -91,9 +91,9 @@ def test_warp_leaves_golden(engine, golden_dir):
         assert (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
 
-@pytest.mark.parametrize("packed", ["1", "0"])
+@pytest.mark.parametrize("packed", ["1", "0", "2"])
 def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib, monkeypatch, packed):
-    """packed = 1: unbanded jobs take the s16x2 (DPX) form used by the paired kernel; 0: the int form used by sg_align_kernel."""
+    """packed = 1: unbanded jobs take the s16x2 (DPX) form used by the paired kernel (2: its unrolled instantiation); 0: the int form."""
     monkeypatch.setenv("SNAPGPU_TEST_AG_PACKED", packed)
     for seed in (301, 302):
         t, p, q, jb = J.lv_jobs(3000, seed)
