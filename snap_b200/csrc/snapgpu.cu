@@ -924,6 +924,18 @@ static int aligner_init_common(snapgpu_aligner *a, int64_t maxBatchReads, int64_
             if (a->stageBlocks[k] > maxBlocks) maxBlocks = a->stageBlocks[k];
         }
     }
+    // The arenas of the extra (more than blocksPerSM) CTAs per SM are a throughput option, not a need: give them up when they
+    // would take more than half of the free HBM (long maximum read lengths make the arenas large).
+    {
+        size_t freeB = 0, totalB = 0;
+        SG_CUDA(cudaMemGetInfo(&freeB, &totalB));
+        while (maxBlocks > a->blocksPerSM && scratchBytesPerWorker * (size_t)a->numSMs * maxBlocks * a->warpsPerBlock > freeB / 2) {
+            maxBlocks -= 2;
+            if (maxBlocks < a->blocksPerSM) maxBlocks = a->blocksPerSM;
+            if (a->pass1BlocksPerSM > maxBlocks) a->pass1BlocksPerSM = maxBlocks == 6 ? 6 : a->blocksPerSM;
+            for (int k = 1; k <= 3; k++) if (a->stageBlocks[k] > maxBlocks) a->stageBlocks[k] = maxBlocks == 6 ? 6 : 4;
+        }
+    }
     a->nWorkers = a->numSMs * maxBlocks * a->warpsPerBlock;
     if ((int64_t)a->nWorkers > maxUnits) {
         int blocks = (int)((maxUnits + a->warpsPerBlock - 1) / a->warpsPerBlock);

@@ -441,6 +441,19 @@ def test_paired_handoff_pool_exhaustion_takes_the_retry_pass(engine, gidx, small
     al.close()
 
 
+def test_large_arenas_fall_back_to_fewer_resident_warps(engine, gidx, small_cfg, reflib, monkeypatch):
+    """With the longest supported reads the per-warp arenas are ~4x larger; the extra CTAs per SM of the first pass are then
+    given up rather than taking most of the HBM.  Results unchanged."""
+    monkeypatch.setenv("SNAPGPU_MAX_READ_LEN", "1000")
+    p = engine.default_params(maxDist=14)
+    al = engine.SingleAligner(gidx, p, 1 << 16)
+    rb = small_cfg.reads["noisy150"]
+    want, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params(maxDist=14)).align(rb)
+    got, _ = al.align(rb)
+    assert differing(want, got) == []
+    al.close()
+
+
 
 def _same_fastq(want, got):
     names = ("bases", "quals", "offsets", "lens", "id_offsets", "id_lens", "front_clipped")
