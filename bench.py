@@ -326,7 +326,7 @@ def run_ours(args):
             out["cpu_baseline"] = {"error": str(e)[:300]}
 
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
     al.close()
     idx.close()
     if world > 1:
@@ -551,13 +551,29 @@ def run_reference(args):
                "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "aligned_frac": round(aligned / (n * K), 5),
                "note": "unmodified amplab/snap aligner (BaseAligner::AlignRead / ChimericPairedEndAligner::align) via oracle/_ref on host cores; index = GPU-built, exported to SNAP's format"}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The one JSON line goes to the process's real stdout; everything else any library prints (NCCL's version banner, for one,
+    goes to fd 1 at communicator creation whatever NCCL_DEBUG says short of unset) has been routed to stderr by main()."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                      # C-level stdout of this process (and its children) -> stderr
+    sys.stdout = sys.stderr
     if args.impl == "reference":
         run_reference(args)
     else:
