@@ -24,6 +24,17 @@ SG_HD SgAgParams sg_ag_params(int matchReward, int subPenalty, int gapOpen, int 
     return p;
 }
 
+// The specialised device forms (packed s16x2 rows, narrow-band rows) do plain 16-bit arithmetic where the reference saturates, and
+// the packed one pads with -16384 instead of INT16_MIN.  That is exact as long as no cell value can come near either: true for any
+// sane scoring scheme, checked here so that an exotic one falls back to the general form (which saturates like the reference).
+SG_HD bool sg_ag_small_scores(const SgAgParams &P, uint32_t maxReadLen)
+{
+    const long long top = (long long)(P.matchReward > 0 ? P.matchReward : 0) * ((long long)maxReadLen + SG_MAX_K + 1)
+                          + (P.fivePrimeEndBonus > P.threePrimeEndBonus ? P.fivePrimeEndBonus : P.threePrimeEndBonus);
+    const long long step = (long long)(-P.subPenalty > P.gapOpenPenalty ? -P.subPenalty : P.gapOpenPenalty);
+    return P.matchReward >= 0 && P.subPenalty <= 0 && P.gapOpenPenalty >= 0 && P.gapExtendPenalty >= 0 && top < 12000 && step < 4000;
+}
+
 struct SgAgResult {
     int agScore, textOffset, patternOffset, nEdits;
     double matchProbability;

@@ -70,12 +70,12 @@ __device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int ope
                 if (q == 0) hdiag = (l == 0) ? hInit : (int)Hptr[(vbase + numVec - 1) * SG_VEC + l - 1];
                 else hdiag = Hptr[idx - SG_VEC];
                 const int pv = profRow[idx];
-                const int m = (hdiag > 0) ? sg_sat16(hdiag + (pv == -128 ? -32768 : pv)) : 0;
+                const int m = (hdiag > 0) ? hdiag + (pv == -128 ? -32768 : pv) : 0;      // (no saturation can occur here: sg_ag_small_scores)
                 const int e = E[idx];
                 act = (e > m) ? 1 : 0;
                 h = m > e ? m : e;
-                const int e2 = sg_sat16(e - ext);
-                temp = sg_sat16(m - open); if (temp < 0) temp = 0;
+                const int e2 = e - ext;
+                temp = m - open; if (temp < 0) temp = 0;
                 if (e2 > temp) act |= 4;
                 E[idx] = (int16_t)(e2 > temp ? e2 : temp);
             }
@@ -86,7 +86,7 @@ __device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int ope
             if (q > 2) { int v = t2; if (v > fin) fin = v; }
             if (valid) {
                 if (fin > h) { act |= 2; h = fin; }
-                if (sg_sat16(fin - ext) > temp) act |= 32;
+                if (fin - ext > temp) act |= 32;
             }
             int fl = fcarry - nVecHere * ext;            // f register of SSE lane l after the main pass
             { int v = t0 - (nVecHere - 1) * ext; if (nVecHere > 0 && v > fl) fl = v; }

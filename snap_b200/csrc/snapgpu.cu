@@ -209,7 +209,7 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
     A.agCands = nullptr; A.nAgCands = 0; A.maxAgCands = 0; A.agCandsOverflow = 0;
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
-    if (MODE == 2) A.ag.usePacked = pr.agSpecialised;
+    if (MODE == 2) A.ag.usePacked = sg_ag_small_scores(A.ag, pr.maxReadLen) ? pr.agSpecialised : 0;
     A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     A.nUsedElements = 0;         // the scratch lookup table is all-zero at creation and left clean after every read
     A.work.lookups = A.work.entriesProbed = A.work.overflowWords = A.work.lvCalls = A.work.agCalls = A.work.popularIgnored = 0;
@@ -328,7 +328,7 @@ sg_align_paired_kernel(const __grid_constant__ SgIndexView ixParam, const __grid
     S.agCands = nullptr; S.nAgCands = 0; S.maxAgCands = 0; S.agCandsOverflow = 0;
     sg_scratch_carve(prSingle, arena, &S.sc);
     S.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
-    S.ag.usePacked = (STAGE == 2) ? pp.stage2Packed : 1;      // `snap paired` rescoring is mostly unbanded (wide score limits): the packed form pays here
+    S.ag.usePacked = !sg_ag_small_scores(S.ag, pr.maxReadLen) ? 0 : (STAGE == 2) ? pp.stage2Packed : 1;      // `snap paired` rescoring is mostly unbanded (wide score limits): the packed form pays here
     S.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
     S.nUsedElements = 0;
     S.work.lookups = S.work.entriesProbed = S.work.overflowWords = S.work.lvCalls = S.work.agCalls = S.work.popularIgnored = 0;
