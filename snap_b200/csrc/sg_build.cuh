@@ -34,13 +34,24 @@ __global__ void sg_build_emit_kernel(const uint8_t *bases /* location 0 */, long
     }
 }
 
-// pass 1: per run head, count unique seeds per table and overflow words
-__global__ void sg_build_count_kernel(const unsigned long long *keys, long long n, uint32_t keyBits, uint32_t seedLen,
+// pass 1: per run head, count unique seeds per table and overflow words.  The keys are sorted, so a thread sees the same table
+// for long stretches: counts are kept in registers, flushed to a per-block shared histogram when the table changes, and each
+// block adds its totals to the global counters once (one atomic per seed on three hot words cost 2 s at 3 Gbp).
+__global__ void sg_build_count_kernel(const unsigned long long *keys, long long n, uint32_t keyBits, uint32_t seedLen, uint32_t nTables, int hist,
                                       unsigned long long *tableUsed, unsigned long long *overflowWords, unsigned long long *nValid)
 {
+    // shared per-block histogram when the tables fit (seed length <= 22); for more tables the per-thread run counts go straight to
+    // the global histogram (still one atomic per run of equal tables, not per seed)
+    extern __shared__ unsigned long long sUsed[];       // [nTables or 0] + nValid + overflowWords
+    const bool sharedHist = hist == 1;
+    const uint32_t nShared = sharedHist ? nTables : 0;
+    for (uint32_t t = threadIdx.x; t < nShared + 2; t += blockDim.x) sUsed[t] = 0;
+    __syncthreads();
     const unsigned long long SG_BUILD_INVALID_KEY = 1ULL << (2 * seedLen);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    uint32_t curTable = 0xffffffffu;
+    unsigned long long curUsed = 0, valid = 0, over = 0;
     for (; i < n; i += stride) {
         unsigned long long k = keys[i];
         if (k & SG_BUILD_INVALID_KEY) continue;
@@ -48,9 +59,23 @@ __global__ void sg_build_count_kernel(const unsigned long long *keys, long long 
         long long e = i + 1;
         while (e < n && keys[e] == k) e++;
         unsigned long long count = (unsigned long long)(e - i);
-        atomicAdd(&tableUsed[(uint32_t)(k >> keyBits)], 1ULL);
-        atomicAdd(nValid, count);
-        if (count > 1) atomicAdd(overflowWords, count + 1);
+        const uint32_t table = (uint32_t)(k >> keyBits);
+        if (table != curTable) {
+            if (curUsed) atomicAdd(sharedHist ? &sUsed[curTable] : &tableUsed[curTable], curUsed);
+            curTable = table; curUsed = 0;
+        }
+        curUsed++;
+        valid += count;
+        if (count > 1) over += count + 1;
+    }
+    if (curUsed) atomicAdd(sharedHist ? &sUsed[curTable] : &tableUsed[curTable], curUsed);
+    if (valid) atomicAdd(&sUsed[nShared], valid);
+    if (over) atomicAdd(&sUsed[nShared + 1], over);
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < nShared; t += blockDim.x) if (sUsed[t]) atomicAdd(&tableUsed[t], sUsed[t]);
+    if (threadIdx.x == 0) {
+        if (sUsed[nShared]) atomicAdd(nValid, sUsed[nShared]);
+        if (sUsed[nShared + 1]) atomicAdd(overflowWords, sUsed[nShared + 1]);
     }
 }
 

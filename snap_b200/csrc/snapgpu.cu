@@ -679,7 +679,11 @@ static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const i
 
     SG_CUDA(cudaMalloc((void **)&d_stats, (size_t)(nTables + 3) * 8));
     SG_CUDA(cudaMemset(d_stats, 0, (size_t)(nTables + 3) * 8));
-    sg_build_count_kernel<<<grid, 256>>>(sk, nPos, keyBits, seedLen, d_stats, d_stats + nTables, d_stats + nTables + 1);
+    {
+        int hist = nTables <= 4096 ? 1 : 0;
+        if (const char *e = getenv("SNAPGPU_BUILD_SHARED_HIST")) hist = (atoi(e) != 0 && nTables <= 4096) ? 1 : 0;      // (test hook for the many-tables form)
+        sg_build_count_kernel<<<grid, 256, (size_t)((hist ? nTables : 0) + 2) * 8>>>(sk, nPos, keyBits, seedLen, nTables, hist, d_stats, d_stats + nTables, d_stats + nTables + 1);
+    }
     SG_CUDA(cudaGetLastError());
     std::vector<unsigned long long> stats(nTables + 3);
     SG_CUDA(cudaMemcpy(stats.data(), d_stats, (size_t)(nTables + 3) * 8, cudaMemcpyDeviceToHost));

@@ -126,9 +126,12 @@ def test_lookup_matches_reference(engine, gidx, small_cfg, reflib):
             assert a[4] + 2 == probes[i]
 
 
-def test_device_built_index_equals_reference_index(engine, gidx, small_cfg):
+@pytest.mark.parametrize("shared_hist", ["1", "0"])
+def test_device_built_index_equals_reference_index(engine, gidx, small_cfg, monkeypatch, shared_hist):
     """snapgpu_index_build: same hit sets in the same (descending) order as the reference-built directory, for every
-    seed of a few hundred reads and their reverse complements; and whole-read results identical."""
+    seed of a few hundred reads and their reverse complements; and whole-read results identical.  (shared_hist: the two forms
+    of the counting pass -- per-block shared histogram, or straight to the global one when there are too many tables.)"""
+    monkeypatch.setenv("SNAPGPU_BUILD_SHARED_HIST", shared_hist)
     bases, starts = small_cfg.padded_bases()
     bix = engine.Index.build(bases, starts, seed_len=20, chromosome_padding=2000)
     a, b = gidx.info(), bix.info()
