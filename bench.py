@@ -319,7 +319,8 @@ def run_ours(args):
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_baseline(args, idx, host_batches[0], check_against=None)
+            got0, _ = al.align(host_batches[0])          # the engine's records for the reads the reference is about to be timed on
+            out["cpu_baseline"] = cpu_baseline(args, idx, host_batches[0], check_against=got0)
             if paired:
                 out["per_read"]["aligned_as_pair_frac"] = out["cpu_baseline"].pop("aligned_as_pair_frac", None)
         except Exception as e:  # pragma: no cover
@@ -458,8 +459,28 @@ def export_index_for_reference(idx):
     return d
 
 
+def count_differing(want, got, paired):
+    """Result records of the engine vs the reference's for the same reads, bytewise (doubles bit for bit), vectorised.  Same
+    exclusions as tests/conftest.py: single-end records both sides report NotFound (the reference leaves the rest
+    uninitialised on its early returns); mapq / scorePriorToClipping of a paired end reported NotFound (copied from an
+    unwritten stack object by ChimericPairedEndAligner)."""
+    w, g = want.copy(), np.asarray(got).view(want.dtype).copy()
+    if paired:
+        for arr in (w, g):
+            nf = arr["status"] == 0
+            arr["mapq"][nf] = 0
+            arr["scorePriorToClipping"][nf] = 0
+        skip = np.zeros(len(w), dtype=bool)
+    else:
+        skip = (w["status"] == 0) & (g["status"] == 0)
+    wb = w.view(np.uint8).reshape(len(w), -1)
+    gb = g.view(np.uint8).reshape(len(g), -1)
+    return int(((wb != gb).any(axis=1) & ~skip).sum())
+
+
 def cpu_baseline(args, idx, host_batch, check_against):
-    """oracle/_ref (the compiled, unmodified reference) on all host cores over a bounded sample of the same reads."""
+    """oracle/_ref (the compiled, unmodified reference) on all host cores over a bounded sample of the same reads.  The
+    reference's records for the sample are also compared with the engine's (`check_against`): full-size parity evidence."""
     from oracle import reflib
     if not reflib.available():
         return {"error": "oracle/_ref not built"}
@@ -477,7 +498,8 @@ def cpu_baseline(args, idx, host_batch, check_against):
             p, pp = reflib.default_params(**PAIRED_KW), reflib.default_paired_params(**PAIRED_PKW)
             reflib.paired_align_mt(ridx, p, pp, sample.slice(0, min(n, 20000)), cores)
             res, ctr, secs = reflib.paired_align_mt(ridx, p, pp, sample, cores)
-            return {"value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
+            parity = None if check_against is None else {"pairs_compared": n // 2, "differing": count_differing(res, check_against[:n // 2], True)}
+            return {"parity_vs_reference": parity, "value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
                     "sample": "%d of the step's %d pairs, %d threads, oracle/_ref ChimericPairedEndAligner(IntersectingPairedEndAligner)::align "
                               "(aligner only, no SAM output); index = ours exported to SNAP's directory format (load %.1fs)"
                               % (n // 2, host_batch.n // 2, cores, load_s),
@@ -485,7 +507,8 @@ def cpu_baseline(args, idx, host_batch, check_against):
         p = reflib.default_params(maxDist=MAX_DIST)
         reflib.align_mt(ridx, p, sample.slice(0, min(n, 20000)), cores)          # warm the page cache / TLB
         res, ctr, secs = reflib.align_mt(ridx, p, sample, cores)
-        return {"value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
+        parity = None if check_against is None else {"reads_compared": n, "differing": count_differing(res, check_against[:n], False)}
+        return {"parity_vs_reference": parity, "value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
                 "sample": "%d of the step's %d reads, %d threads, oracle/_ref BaseAligner::AlignRead (aligner only, no SAM output); "
                           "index = ours exported to SNAP's directory format (load %.1fs)" % (n, host_batch.n, cores, load_s),
                 "seconds": round(secs, 3), "lv_per_read": round(ctr["lvCalls"] / n, 3), "ag_per_read": round(ctr["affineGapCalls"] / n, 3)}
