@@ -29,6 +29,7 @@
 #include "Tables.h"
 #include "FASTQ.h"
 #include "DataReader.h"
+#include "Bam.h"
 
 #include <pthread.h>
 #include <string.h>
@@ -154,6 +155,40 @@ void ref_lv_batch(const char *textBuf, const char *patBuf, const char *qualBuf, 
         o->score = ref_lv(b->dir, textBuf + b->textOff, b->textLen, patBuf + b->patOff, qualBuf + b->patOff, b->patternLen, b->k,
                           &o->matchProbability, &o->netIndel, &o->totalIndels, &o->textSpan);
     }
+}
+
+/*
+ * LandauVishkinWithCigar::computeEditDistance / computeEditDistanceNormalized (LandauVishkin.cpp:141-505 / :507-650) with
+ * BAM_CIGAR_OPS output: the oracle for snap_b200/csrc/sg_lv_cigar.h (output stage).  POD job / out records are
+ * test-local (mirrored in tests/hostsim and oracle/reflib.py), not part of include/snapgpu.h.
+ */
+struct RefLvCigarJob { unsigned long long textOff, patOff; int textLen, patternLen, k, useM; };
+struct RefLvCigarOut { int score, nOps, textUsed, netIndel, normalizedScore, addFrontClipping; unsigned ops[32]; };
+
+void ref_lv_cigar_batch(const char *textBuf, const char *patBuf, const RefLvCigarJob *jobs, _int64 nJobs, RefLvCigarOut *out)
+{
+    static LandauVishkinWithCigar *lvc = NULL;
+    if (lvc == NULL) lvc = new LandauVishkinWithCigar();
+    for (_int64 j = 0; j < nJobs; j++) {
+        const RefLvCigarJob *b = &jobs[j];
+        RefLvCigarOut *o = &out[j];
+        memset(o, 0, sizeof(*o));
+        int used = 0, textUsed = 0, netIndel = 0;
+        o->score = lvc->computeEditDistance(textBuf + b->textOff, b->textLen, patBuf + b->patOff, b->patternLen, b->k, (char *)o->ops, (int)sizeof(o->ops),
+                                            b->useM != 0, BAM_CIGAR_OPS, &used, &textUsed, &netIndel);
+        o->nOps = o->score >= 0 ? used / 4 : 0; o->textUsed = o->score >= 0 ? textUsed : 0; o->netIndel = o->score >= 0 ? netIndel : 0;
+        if (o->score < 0) memset(o->ops, 0, sizeof(o->ops));
+        unsigned ops2[32]; int used2 = 0, clip = 0, netIndel2 = 0;
+        o->normalizedScore = lvc->computeEditDistanceNormalized(textBuf + b->textOff, b->textLen, patBuf + b->patOff, b->patternLen, b->k, (char *)ops2,
+                                                                (int)sizeof(ops2), b->useM != 0, BAM_CIGAR_OPS, &used2, &clip, &netIndel2);
+        o->addFrontClipping = o->normalizedScore >= 0 ? clip : 0;
+    }
+}
+
+// the SAM text form of BAM operations (BAMAlignment::decodeCigar, Bam.cpp:345-375), for the known-answer vectors
+int ref_decode_cigar(const unsigned *ops, int nOps, char *buf, int bufLen)
+{
+    return BAMAlignment::decodeCigar(buf, bufLen, (_uint32 *)ops, nOps) ? 1 : 0;
 }
 
 /*

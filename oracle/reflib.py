@@ -117,6 +117,9 @@ def lib():
         L.ref_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ref_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
         L.ref_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.ref_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+        L.ref_decode_cigar.restype = C.c_int
+        L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_init()
         _lib = L
@@ -279,6 +282,26 @@ def lv_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarr
     out = np.zeros(jobs.size, dtype=LV_OUT_DTYPE)
     lib().ref_lv_batch(_p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out))
     return out
+
+
+# LandauVishkinWithCigar (output stage): test-local POD records, see oracle/ref_harness.cpp
+LVC_JOB_DTYPE = np.dtype([("textOff", "<u8"), ("patOff", "<u8"), ("textLen", "<i4"), ("patternLen", "<i4"), ("k", "<i4"), ("useM", "<i4")])
+LVC_OUT_DTYPE = np.dtype([("score", "<i4"), ("nOps", "<i4"), ("textUsed", "<i4"), ("netIndel", "<i4"), ("normalizedScore", "<i4"),
+                          ("addFrontClipping", "<i4"), ("ops", "<u4", (32,))])
+
+
+def lv_cigar_batch(text: np.ndarray, pat: np.ndarray, jobs: np.ndarray) -> np.ndarray:
+    out = np.zeros(jobs.size, dtype=LVC_OUT_DTYPE)
+    lib().ref_lv_cigar_batch(_p(text), _p(pat), _p(np.ascontiguousarray(jobs, dtype=LVC_JOB_DTYPE)), jobs.size, _p(out))
+    return out
+
+
+def decode_cigar(ops: np.ndarray, n_ops: int) -> str:
+    buf = C.create_string_buffer(512)
+    ops = np.ascontiguousarray(ops, dtype=np.uint32)
+    ok = lib().ref_decode_cigar(_p(ops), int(n_ops), buf, 512)
+    assert ok
+    return buf.value.decode()
 
 
 def ag_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray, params=AG_PARAMS_DEFAULT) -> np.ndarray:

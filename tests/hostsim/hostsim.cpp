@@ -12,6 +12,7 @@
 #include "../../snap_b200/csrc/sg_align.h"
 #include "../../snap_b200/csrc/sg_paired.h"
 #include "../../snap_b200/csrc/sg_host.h"
+#include "../../snap_b200/csrc/sg_lv_cigar.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -345,6 +346,33 @@ int hs_align_paired(void *v, int64_t nPairs, const char *bases, const char *qual
     if (nLV) *nLV = a->P.lvCalls + a->S.work.lvCalls;
     if (nAG) *nAG = a->P.agCalls + a->S.work.agCalls;
     return 0;
+}
+
+// LandauVishkinWithCigar restated (sg_lv_cigar.h) over the same test-local job / out records as oracle ref_lv_cigar_batch
+struct HsLvCigarJob { unsigned long long textOff, patOff; int textLen, patternLen, k, useM; };
+struct HsLvCigarOut { int score, nOps, textUsed, netIndel, normalizedScore, addFrontClipping; unsigned ops[32]; };
+
+void hs_lv_cigar_batch(const char *textBuf, const char *patBuf, const HsLvCigarJob *jobs, int64_t nJobs, HsLvCigarOut *out)
+{
+    const int kmax = SG_MAX_K - 1;
+    std::vector<int> L(sg_lv_cigar_scratch_ints(kmax)), TI(sg_lv_cigar_scratch_ints(kmax)), btM(kmax + 2), btD(kmax + 2);
+    std::vector<uint8_t> A(sg_lv_cigar_scratch_ints(kmax)), btA(kmax + 2);
+    SgLvCigarScratch S;
+    S.L = L.data(); S.totalIndels = TI.data(); S.A = A.data(); S.btAction = btA.data(); S.btMatched = btM.data(); S.btD = btD.data(); S.kmax = kmax;
+    for (int64_t j = 0; j < nJobs; j++) {
+        const HsLvCigarJob &b = jobs[j];
+        HsLvCigarOut &o = out[j];
+        memset(&o, 0, sizeof(o));
+        SgLvCigarOut r;
+        sg_lv_cigar_compute(S, (const uint8_t *)textBuf + b.textOff, b.textLen, (const uint8_t *)patBuf + b.patOff, b.patternLen, b.k, o.ops, 32, b.useM != 0, &r);
+        o.score = r.score;
+        if (r.score >= 0) { o.nOps = r.nOps; o.textUsed = r.textUsed; o.netIndel = r.netIndel; } else memset(o.ops, 0, sizeof(o.ops));
+        unsigned ops2[32]; int clip = 0;
+        SgLvCigarOut r2;
+        o.normalizedScore = sg_lv_cigar_normalized(S, (const uint8_t *)textBuf + b.textOff, b.textLen, (const uint8_t *)patBuf + b.patOff, b.patternLen, b.k, ops2, 32,
+                                                   b.useM != 0, &r2, &clip);
+        o.addFrontClipping = o.normalizedScore >= 0 ? clip : 0;
+    }
 }
 
 } // extern "C"

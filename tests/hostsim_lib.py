@@ -45,6 +45,7 @@ def lib():
         L.hs_mapq.argtypes = [C.c_double, C.c_double, C.c_int]
         L.hs_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
         L.hs_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
+        L.hs_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.hs_aligner_create.restype = C.c_void_p
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
@@ -133,6 +134,12 @@ class HsPairedAligner:
         if getattr(self, "handle", None):
             lib().hs_paired_destroy(self.handle)
             self.handle = None
+
+
+def lv_cigar_batch(text, pat, jobs, out_dtype):
+    out = np.zeros(jobs.size, dtype=out_dtype)
+    lib().hs_lv_cigar_batch(_p(text), _p(pat), _p(np.ascontiguousarray(jobs)), jobs.size, _p(out))
+    return out
 
 
 def tables(seed_len=20, n_indel=1200, n_perfect=1001):
