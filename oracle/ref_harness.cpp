@@ -13,6 +13,10 @@
  */
 #include "stdafx.h"
 #include "Compat.h"
+// SAMFormat::computeCigarString is a private static member; this harness is its only outside caller (test infrastructure)
+#define private public
+#include "SAM.h"
+#undef private
 #include "BigAlloc.h"
 #include "Genome.h"
 #include "GenomeIndex.h"
@@ -189,6 +193,38 @@ void ref_lv_cigar_batch(const char *textBuf, const char *patBuf, const RefLvCiga
 int ref_decode_cigar(const unsigned *ops, int nOps, char *buf, int bufLen)
 {
     return BAMAlignment::decodeCigar(buf, bufLen, (_uint32 *)ops, nOps) ? 1 : 0;
+}
+
+/*
+ * SAMFormat::computeCigarString, LandauVishkinWithCigar overload (SAM.cpp:2595-2671, around computeCigar :2354-2468): the oracle
+ * for snap_b200/csrc/sg_cigar.h.  kind: 0 = NULL (caller retries with addFrontClipping), 1 = "*", 2 = a CIGAR string.
+ */
+struct RefCigarJob { unsigned long long dataOff; long long location; int dataLength, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter,
+                     frontHardClipping, backHardClipping, direction, useM; };
+struct RefCigarOut { int kind, editDistance, addFrontClipping, refSpan; char cigar[240]; };
+
+void ref_cigar_lv_batch(void *vidx, const char *dataBuf, const RefCigarJob *jobs, _int64 nJobs, RefCigarOut *out)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    static LandauVishkinWithCigar *lvc = NULL;
+    if (lvc == NULL) lvc = new LandauVishkinWithCigar();
+    const int bufSize = MAX_READ_LENGTH * 2;
+    char *cigarBuf = new char[bufSize], *withClipping = new char[bufSize + 32];
+    for (_int64 j = 0; j < nJobs; j++) {
+        const RefCigarJob *b = &jobs[j];
+        RefCigarOut *o = &out[j];
+        memset(o, 0, sizeof(*o));
+        int editDistance = -1, addFrontClipping = 0, refSpan = 0;
+        const char *c = SAMFormat::computeCigarString(index->getGenome(), lvc, cigarBuf, bufSize, withClipping, bufSize + 32, dataBuf + b->dataOff, b->dataLength,
+                                                      (unsigned)b->basesClippedBefore, (GenomeDistance)b->extraBasesClippedBefore, (unsigned)b->basesClippedAfter,
+                                                      (unsigned)b->frontHardClipping, (unsigned)b->backHardClipping, GenomeLocation(b->location),
+                                                      b->direction ? RC : FORWARD, b->useM != 0, &editDistance, &addFrontClipping, &refSpan);
+        o->editDistance = editDistance; o->addFrontClipping = addFrontClipping;
+        if (c == NULL) { o->kind = 0; }
+        else if (c[0] == '*') { o->kind = 1; }
+        else { o->kind = 2; o->refSpan = refSpan; strncpy(o->cigar, c, sizeof(o->cigar) - 1); }
+    }
+    delete[] cigarBuf; delete[] withClipping;
 }
 
 /*

@@ -118,6 +118,7 @@ def lib():
         L.ref_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
         L.ref_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+        L.ref_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.ref_decode_cigar.restype = C.c_int
         L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -302,6 +303,18 @@ def decode_cigar(ops: np.ndarray, n_ops: int) -> str:
     ok = lib().ref_decode_cigar(_p(ops), int(n_ops), buf, 512)
     assert ok
     return buf.value.decode()
+
+
+# SAMFormat::computeCigarString (LV overload): test-local POD records, see oracle/ref_harness.cpp
+CIGAR_JOB_DTYPE = np.dtype([("dataOff", "<u8"), ("location", "<i8"), ("dataLength", "<i4"), ("basesClippedBefore", "<i4"), ("extraBasesClippedBefore", "<i4"),
+                            ("basesClippedAfter", "<i4"), ("frontHardClipping", "<i4"), ("backHardClipping", "<i4"), ("direction", "<i4"), ("useM", "<i4")])
+CIGAR_REF_OUT_DTYPE = np.dtype([("kind", "<i4"), ("editDistance", "<i4"), ("addFrontClipping", "<i4"), ("refSpan", "<i4"), ("cigar", "S240")])
+
+
+def cigar_lv_batch(index, data: np.ndarray, jobs: np.ndarray) -> np.ndarray:
+    out = np.zeros(jobs.size, dtype=CIGAR_REF_OUT_DTYPE)
+    lib().ref_cigar_lv_batch(index.handle, _p(data), _p(np.ascontiguousarray(jobs, dtype=CIGAR_JOB_DTYPE)), jobs.size, _p(out))
+    return out
 
 
 def ag_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray, params=AG_PARAMS_DEFAULT) -> np.ndarray:

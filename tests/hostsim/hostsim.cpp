@@ -13,6 +13,7 @@
 #include "../../snap_b200/csrc/sg_paired.h"
 #include "../../snap_b200/csrc/sg_host.h"
 #include "../../snap_b200/csrc/sg_lv_cigar.h"
+#include "../../snap_b200/csrc/sg_cigar.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -372,6 +373,31 @@ void hs_lv_cigar_batch(const char *textBuf, const char *patBuf, const HsLvCigarJ
         o.normalizedScore = sg_lv_cigar_normalized(S, (const uint8_t *)textBuf + b.textOff, b.textLen, (const uint8_t *)patBuf + b.patOff, b.patternLen, b.k, ops2, 32,
                                                    b.useM != 0, &r2, &clip);
         o.addFrontClipping = o.normalizedScore >= 0 ? clip : 0;
+    }
+}
+
+// sg_cigar.h (SAMFormat::computeCigarString, LV overload) over the same job records as oracle ref_cigar_lv_batch
+struct HsCigarJob { unsigned long long dataOff; long long location; int dataLength, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter,
+                    frontHardClipping, backHardClipping, direction, useM; };
+struct HsCigarOut { int kind, editDistance, addFrontClipping, refSpan, nOps; unsigned ops[40]; };
+
+void hs_cigar_lv_batch(void *vix, const char *dataBuf, const HsCigarJob *jobs, int64_t nJobs, HsCigarOut *out)
+{
+    HsIndex *ix = (HsIndex *)vix;
+    const int kmax = SG_MAX_K - 1;
+    std::vector<int> L(sg_lv_cigar_scratch_ints(kmax)), TI(sg_lv_cigar_scratch_ints(kmax)), btM(kmax + 2), btD(kmax + 2);
+    std::vector<uint8_t> A(sg_lv_cigar_scratch_ints(kmax)), btA(kmax + 2);
+    SgLvCigarScratch S;
+    S.L = L.data(); S.totalIndels = TI.data(); S.A = A.data(); S.btAction = btA.data(); S.btMatched = btM.data(); S.btD = btD.data(); S.kmax = kmax;
+    for (int64_t j = 0; j < nJobs; j++) {
+        const HsCigarJob &b = jobs[j];
+        HsCigarOut &o = out[j];
+        memset(&o, 0, sizeof(o));
+        SgCigarOut r;
+        sg_cigar_lv(ix->view, S, (const uint8_t *)dataBuf + b.dataOff, b.dataLength, (uint32_t)b.basesClippedBefore, b.extraBasesClippedBefore,
+                    (uint32_t)b.basesClippedAfter, (uint32_t)b.frontHardClipping, (uint32_t)b.backHardClipping, b.location, b.useM != 0, o.ops, 40, &r);
+        o.kind = r.kind; o.editDistance = r.editDistance; o.addFrontClipping = r.addFrontClipping;
+        if (r.kind == 2) { o.refSpan = r.refSpan; o.nOps = r.nOps; } else memset(o.ops, 0, sizeof(o.ops));
     }
 }
 

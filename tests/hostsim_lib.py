@@ -46,6 +46,7 @@ def lib():
         L.hs_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
         L.hs_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
         L.hs_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+        L.hs_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.hs_aligner_create.restype = C.c_void_p
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
@@ -139,6 +140,15 @@ class HsPairedAligner:
 def lv_cigar_batch(text, pat, jobs, out_dtype):
     out = np.zeros(jobs.size, dtype=out_dtype)
     lib().hs_lv_cigar_batch(_p(text), _p(pat), _p(np.ascontiguousarray(jobs)), jobs.size, _p(out))
+    return out
+
+
+CIGAR_OUT_DTYPE = np.dtype([("kind", "<i4"), ("editDistance", "<i4"), ("addFrontClipping", "<i4"), ("refSpan", "<i4"), ("nOps", "<i4"), ("ops", "<u4", (40,))])
+
+
+def cigar_lv_batch(index, data, jobs):
+    out = np.zeros(jobs.size, dtype=CIGAR_OUT_DTYPE)
+    lib().hs_cigar_lv_batch(index.handle, _p(data), _p(np.ascontiguousarray(jobs)), jobs.size, _p(out))
     return out
 
 

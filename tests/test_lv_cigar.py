@@ -101,3 +101,81 @@ def test_restatement_equals_reference(reflib, seed):
     solved = want["score"] >= 0
     assert 0.5 < solved.mean() < 1.0                      # both outcomes occur
     assert (want["netIndel"] != 0).sum() > 100 and (want["addFrontClipping"] != 0).sum() > 10
+
+
+_CODES = "MIDNSHP=X"
+
+
+def _ops_to_text(ops, n):
+    return "".join("%d%s" % (int(o) >> 4, _CODES[int(o) & 15]) for o in ops[:n])
+
+
+def _record_jobs(reflib, small_cfg, seed):
+    """Reads at the locations the (affine-gap-free) reference aligner put them, in alignment direction; reads placed by hand
+    across contig ends (with and without indels), starts shifted by a few bases (leading insertion / deletion => the
+    front-clipping retry protocol), soft and hard clips."""
+    from snap_b200 import synth
+    rng = np.random.default_rng(seed)
+    bases, starts = small_cfg.padded_bases()
+    data = []; jobs = []; off = 0
+
+    def add(read, loc, direction, cb=0, xb=0, ca=0, fh=0, bh=0, use_m=0):
+        nonlocal off
+        data.append(np.asarray(read, dtype=np.uint8)); data.append(np.zeros(16, dtype=np.uint8))
+        jobs.append((off + cb, loc, len(read) - cb - ca, cb, xb, ca, fh, bh, direction, use_m))
+        off += len(read) + 16
+
+    ridx = reflib.RefIndex(small_cfg.idx)
+    p = reflib.default_params(maxDist=14, useAffineGap=0)
+    for name in ("noisy150", "indel100", "long250"):
+        rb = small_cfg.reads[name]
+        res, _ = reflib.RefSingleAligner(ridx, p).align(rb)
+        for i in range(rb.n):
+            if res[i]["status"] == 0:
+                continue
+            b, _q = rb.read(i)
+            r = np.frombuffer(b, dtype=np.uint8)
+            if res[i]["direction"] == 1:
+                r = synth.revcomp(r)
+            shift = int(rng.choice([0, 0, 0, 0, 0, 1, -1, 2, -3]))
+            cb = int(rng.choice([0, 0, 0, 3, 7])); ca = int(rng.choice([0, 0, 0, 2, 9]))
+            add(r, int(res[i]["location"]) + cb + shift, int(res[i]["direction"]), cb=cb, ca=ca,
+                fh=int(rng.choice([0, 0, 0, 5])), bh=int(rng.choice([0, 0, 0, 4])), use_m=int(rng.integers(0, 2)))
+    # reads hanging over a contig's end by 1..40 bases, clean / with a deletion / with an insertion near the end
+    for c, contig in enumerate(small_cfg.contigs):
+        end_loc = int(starts[c]) + contig.size
+        for over in (1, 2, 5, 17, 40):
+            for kind in ("clean", "del", "ins", "sub"):
+                src = contig[contig.size - 150 + over - 8: contig.size].copy()
+                if kind == "del":
+                    src = np.delete(src, [100, 101])
+                elif kind == "ins":
+                    src = np.insert(src, 90, [ord("A"), ord("C"), ord("A")])
+                elif kind == "sub":
+                    src[60] = ord("A") if src[60] != ord("A") else ord("C")
+                tail = np.frombuffer(bytes(rng.choice(list(b"ACGT"), size=over)), dtype=np.uint8)
+                read = np.concatenate([src, tail])
+                loc = end_loc - (150 - over + 8) if kind != "del" else end_loc - (150 - over + 8)
+                add(read, loc, 0, use_m=int(rng.integers(0, 2)))
+                add(read, loc, 0, xb=3, use_m=int(rng.integers(0, 2)))
+    return (np.concatenate(data), np.array(jobs, dtype=reflib.CIGAR_JOB_DTYPE), ridx)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_record_cigars_equal_reference(reflib, small_cfg, seed):
+    """sg_cigar.h vs SAMFormat::computeCigarString (LV overload) on the reference's own alignments and on hand-placed reads
+    that hang over contig ends: kind (retry / '*' / CIGAR), the CIGAR text incl. soft and hard clips, edit distance, the
+    front-clipping verdict and the reference span."""
+    data, jobs, ridx = _record_jobs(reflib, small_cfg, seed)
+    want = reflib.cigar_lv_batch(ridx, data, jobs)
+    got = hs.cigar_lv_batch(hs.HsIndex(small_cfg.idx), data, jobs)
+    for f in ("kind", "addFrontClipping"):
+        bad = np.nonzero(want[f] != got[f])[0]
+        assert bad.size == 0, (f, int(bad[0]), jobs[int(bad[0])], want[int(bad[0])], got[int(bad[0])])
+    ok = want["kind"] == 2
+    for i in np.nonzero(ok)[0]:
+        assert want[i]["cigar"].decode() == _ops_to_text(got[i]["ops"], int(got[i]["nOps"])), (int(i), jobs[i])
+    assert (want["editDistance"][ok] == got["editDistance"][ok]).all() and (want["refSpan"][ok] == got["refSpan"][ok]).all()
+    assert ok.sum() > 1500 and (want["kind"] == 0).sum() > 50
+    texts = [w.decode() for w in want["cigar"][ok]]
+    assert sum("S" in t for t in texts) > 300 and sum("H" in t for t in texts) > 100 and sum("D" in t or "I" in t for t in texts) > 100
