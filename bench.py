@@ -72,6 +72,16 @@ def measured_traffic(workload, batch_reads, genome_mbp):
         return None
 
 
+def measured_instructions(workload, batch_reads, genome_mbp):
+    """Warp instructions one step's alignment launches execute (smsp__inst_executed.sum of the same committed capture)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s_%dreads_%dmbp" % (workload, batch_reads, genome_mbp)
+        return int(t[key]["warp_instructions_per_step"]) if key in t and "warp_instructions_per_step" in t[key] else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -273,6 +283,16 @@ def run_ours(args):
                 "frac": round(achieved / peak, 6), "traffic": measured_traffic(args.workload, B, args.genome_mbp), "peak_source": peak_src,
                 "algorithmic_bytes_per_step": int(alg_bytes), "avg_step_ms": round(kernel_ms_avg, 3),
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
+
+    # what actually bounds these kernels is instruction issue, so that utilisation is reported beside the (required) HBM roofline:
+    # warp instructions per step (from the committed ncu capture of this workload) / step time, against SMs x 4 schedulers x SM clock
+    n_inst = measured_instructions(args.workload, B, args.genome_mbp)
+    if n_inst is not None and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        issue_peak = sms * 4 * float(clocks["sm_mhz"]) * 1e6
+        issue_ach = n_inst / (kernel_ms_avg / 1e3)
+        roofline["issue_slots"] = {"warp_instructions_per_step": n_inst, "achieved_per_s": round(issue_ach, 1), "peak_per_s": round(issue_peak, 1),
+                                   "frac": round(issue_ach / issue_peak, 4), "source": "profiles/traffic.json (ncu smsp__inst_executed.sum)"}
 
     out = {
         "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
