@@ -228,6 +228,35 @@ void ref_cigar_lv_batch(void *vidx, const char *dataBuf, const RefCigarJob *jobs
 }
 
 /*
+ * AffineGapVectorizedWithCigar::computeGlobalScore (AffineGapVectorized.cpp:159-518) with BAM_CIGAR_OPS output: the oracle for
+ * snap_b200/csrc/sg_ag_cigar.h.  The object holds __m128i members => 64-byte aligned storage, init() instead of a constructor.
+ */
+struct RefAgCigarJob { unsigned long long textOff, patOff; int textLen, patternLen, w, useM; };
+struct RefAgCigarOut { int score, nOps, netDel, tailIns; unsigned ops[64]; };
+
+void ref_ag_cigar_global_batch(const int *params /* match, sub, open, extend */, const char *textBuf, const char *patBuf, const char *qualBuf,
+                               const RefAgCigarJob *jobs, _int64 nJobs, RefAgCigarOut *out)
+{
+    static AffineGapVectorizedWithCigar *agc = NULL;
+    if (agc == NULL) {
+        void *m = NULL;
+        if (posix_memalign(&m, 64, sizeof(AffineGapVectorizedWithCigar))) abort();
+        memset(m, 0, sizeof(AffineGapVectorizedWithCigar));
+        agc = (AffineGapVectorizedWithCigar *)m;
+    }
+    agc->init(params[0], params[1], params[2], params[3]);
+    for (_int64 j = 0; j < nJobs; j++) {
+        const RefAgCigarJob *b = &jobs[j];
+        RefAgCigarOut *o = &out[j];
+        memset(o, 0, sizeof(*o));
+        int used = 0, netDel = 0, tailIns = 0;
+        o->score = agc->computeGlobalScore(textBuf + b->textOff, b->textLen, patBuf + b->patOff, qualBuf + b->patOff, b->patternLen, b->w, (char *)o->ops,
+                                           (int)sizeof(o->ops), b->useM != 0, BAM_CIGAR_OPS, &used, &netDel, &tailIns);
+        if (o->score >= 0) { o->nOps = used / 4; o->netDel = netDel; o->tailIns = tailIns; } else memset(o->ops, 0, sizeof(o->ops));
+    }
+}
+
+/*
  * AffineGapVectorized<dir>::computeScore / computeScoreBanded (AffineGapVectorized.h:821 / 256).
  * The objects hold __m128i members => allocate 16-byte aligned.
  */

@@ -119,6 +119,7 @@ def lib():
         L.ref_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.ref_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+        L.ref_ag_cigar_global_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_decode_cigar.restype = C.c_int
         L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -314,6 +315,18 @@ CIGAR_REF_OUT_DTYPE = np.dtype([("kind", "<i4"), ("editDistance", "<i4"), ("addF
 def cigar_lv_batch(index, data: np.ndarray, jobs: np.ndarray) -> np.ndarray:
     out = np.zeros(jobs.size, dtype=CIGAR_REF_OUT_DTYPE)
     lib().ref_cigar_lv_batch(index.handle, _p(data), _p(np.ascontiguousarray(jobs, dtype=CIGAR_JOB_DTYPE)), jobs.size, _p(out))
+    return out
+
+
+# AffineGapVectorizedWithCigar::computeGlobalScore: test-local POD records, see oracle/ref_harness.cpp
+AGC_JOB_DTYPE = np.dtype([("textOff", "<u8"), ("patOff", "<u8"), ("textLen", "<i4"), ("patternLen", "<i4"), ("w", "<i4"), ("useM", "<i4")])
+AGC_OUT_DTYPE = np.dtype([("score", "<i4"), ("nOps", "<i4"), ("netDel", "<i4"), ("tailIns", "<i4"), ("ops", "<u4", (64,))])
+
+
+def ag_cigar_global_batch(text, pat, qual, jobs, params=(1, 4, 6, 1)) -> np.ndarray:
+    out = np.zeros(jobs.size, dtype=AGC_OUT_DTYPE)
+    prm = np.ascontiguousarray(params, dtype=np.int32)
+    lib().ref_ag_cigar_global_batch(_p(prm), _p(text), _p(pat), _p(qual), _p(np.ascontiguousarray(jobs, dtype=AGC_JOB_DTYPE)), jobs.size, _p(out))
     return out
 
 

@@ -14,6 +14,7 @@
 #include "../../snap_b200/csrc/sg_host.h"
 #include "../../snap_b200/csrc/sg_lv_cigar.h"
 #include "../../snap_b200/csrc/sg_cigar.h"
+#include "../../snap_b200/csrc/sg_ag_cigar.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -398,6 +399,33 @@ void hs_cigar_lv_batch(void *vix, const char *dataBuf, const HsCigarJob *jobs, i
                     (uint32_t)b.basesClippedAfter, (uint32_t)b.frontHardClipping, (uint32_t)b.backHardClipping, b.location, b.useM != 0, o.ops, 40, &r);
         o.kind = r.kind; o.editDistance = r.editDistance; o.addFrontClipping = r.addFrontClipping;
         if (r.kind == 2) { o.refSpan = r.refSpan; o.nOps = r.nOps; } else memset(o.ops, 0, sizeof(o.ops));
+    }
+}
+
+// sg_ag_cigar.h (AffineGapVectorizedWithCigar::computeGlobalScore) over the same job records as oracle ref_ag_cigar_global_batch
+struct HsAgCigarJob { unsigned long long textOff, patOff; int textLen, patternLen, w, useM; };
+struct HsAgCigarOut { int score, nOps, netDel, tailIns; unsigned ops[64]; };
+
+void hs_ag_cigar_global_batch(const int *params, const char *textBuf, const char *patBuf, const char *qualBuf, const HsAgCigarJob *jobs, int64_t nJobs,
+                              HsAgCigarOut *out)
+{
+    const int numVecMax = (1000 + 7) / 8, rowsMax = 1000 + SG_MAX_K + 8, resMax = 2 * rowsMax;
+    std::vector<int16_t> H(numVecMax * 8), Hm1(numVecMax * 8), E(numVecMax * 8), prof(5 * numVecMax * 8);
+    std::vector<uint8_t> bt((size_t)rowsMax * numVecMax * 8), ra(resMax);
+    std::vector<int> rc(resMax);
+    SgAgCigarScratch S;
+    S.H = H.data(); S.Hm1 = Hm1.data(); S.E = E.data(); S.prof = prof.data(); S.bt = bt.data(); S.resAction = ra.data(); S.resCount = rc.data();
+    S.numVecMax = numVecMax; S.rowsMax = rowsMax; S.resMax = resMax;
+    SgAgParams P = sg_ag_params(params[0], params[1], params[2], params[3], 0, 0);
+    for (int64_t j = 0; j < nJobs; j++) {
+        const HsAgCigarJob &b = jobs[j];
+        HsAgCigarOut &o = out[j];
+        memset(&o, 0, sizeof(o));
+        SgAgCigarOut r;
+        sg_ag_cigar_global(P, S, (const uint8_t *)textBuf + b.textOff, b.textLen, (const uint8_t *)patBuf + b.patOff, (const uint8_t *)qualBuf + b.patOff, b.patternLen,
+                           o.ops, 64, b.useM != 0, &r);
+        o.score = r.score;
+        if (r.score >= 0) { o.nOps = r.nOps; o.netDel = r.netDel; o.tailIns = r.tailIns; } else memset(o.ops, 0, sizeof(o.ops));
     }
 }
 

@@ -179,3 +179,57 @@ def test_record_cigars_equal_reference(reflib, small_cfg, seed):
     assert ok.sum() > 1500 and (want["kind"] == 0).sum() > 50
     texts = [w.decode() for w in want["cigar"][ok]]
     assert sum("S" in t for t in texts) > 300 and sum("H" in t for t in texts) > 100 and sum("D" in t or "I" in t for t in texts) > 100
+
+
+def _agc_jobs(reflib, n, seed):
+    """Global affine-gap problems: patterns cut from random text with substitutions / insertions / deletions (incl. runs, near the
+    ends, homopolymer neighbourhoods for the 'flip' heuristics), text = the window the SAM writer would pass (pattern + slack),
+    low and high qualities (the heuristics look at quality < 65)."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    text = alphabet[rng.integers(0, 4, size=300000)].copy()
+    # homopolymer-rich stretches
+    for _ in range(3000):
+        p = int(rng.integers(0, text.size - 10)); text[p:p + int(rng.integers(2, 6))] = text[p]
+    pats = []; quals = []; jobs = []; off = 0
+    for _ in range(n):
+        plen = int(rng.integers(12, 260))
+        start = int(rng.integers(100, text.size - 700))
+        src = text[start:start + plen + 60].tolist()
+        out = []; si = 0
+        n_edit = int(rng.choice([0, 1, 1, 2, 3, 5, 8]))
+        edits = set(int(x) for x in rng.integers(0, plen, size=n_edit))
+        while len(out) < plen:
+            pos = len(out)
+            if pos in edits:
+                kind = int(rng.integers(0, 4))
+                if kind <= 1:
+                    out.append(int(alphabet[(int(np.searchsorted(alphabet, src[si])) + 1 + int(rng.integers(0, 3))) % 4])); si += 1
+                elif kind == 2:
+                    for _k in range(int(rng.integers(1, 4))):
+                        out.append(int(alphabet[rng.integers(0, 4)]))
+                else:
+                    si += int(rng.integers(1, 5)); out.append(src[si]); si += 1
+                edits.discard(pos)
+            else:
+                out.append(src[si]); si += 1
+        pats.append(np.array(out[:plen], dtype=np.uint8)); pats.append(np.zeros(16, dtype=np.uint8))
+        q = rng.integers(40, 75, size=plen).astype(np.uint8)
+        quals.append(q); quals.append(np.zeros(16, dtype=np.uint8))
+        slack = int(rng.choice([0, 3, 10, 27, 127]))
+        jobs.append((start + int(rng.choice([0, 0, 0, 1, 2])), off, plen + slack, plen, int(rng.choice([5, 15, 27, 60])), int(rng.integers(0, 2))))
+        off += plen + 16
+    return text, np.concatenate(pats), np.concatenate(quals), np.array(jobs, dtype=reflib.AGC_JOB_DTYPE)
+
+
+@pytest.mark.parametrize("seed,params", [(21, (1, 4, 6, 1)), (22, (1, 4, 6, 1)), (23, (2, 3, 4, 2))])
+def test_affine_gap_global_cigar_equals_reference(reflib, seed, params):
+    """sg_ag_cigar.h vs AffineGapVectorizedWithCigar::computeGlobalScore: BAM operations, edit count, net deletions, tail insertions."""
+    text, pat, qual, jobs = _agc_jobs(reflib, 3000, seed)
+    want = reflib.ag_cigar_global_batch(text, pat, qual, jobs, params)
+    got = hs.ag_cigar_global_batch(text, pat, qual, jobs, reflib.AGC_OUT_DTYPE, params)
+    for f in ("score", "nOps", "netDel", "tailIns"):
+        bad = np.nonzero(want[f] != got[f])[0]
+        assert bad.size == 0, (f, int(bad[0]), jobs[int(bad[0])], want[int(bad[0])], got[int(bad[0])])
+    assert (want["ops"] == got["ops"]).all()
+    assert (want["score"] >= 0).mean() > 0.9 and (want["netDel"] > 0).sum() > 100 and (want["tailIns"] > 0).sum() > 20
