@@ -256,6 +256,32 @@ void ref_ag_cigar_global_batch(const int *params /* match, sub, open, extend */,
     }
 }
 
+// computeGlobalScoreNormalized (:1043-1128): banded / unbanded dispatch + front-clipping verdict.  `out->score` = its return value.
+struct RefAgCigarNormOut { int score, nOps, netDel, tailIns, addFrontClipping; unsigned ops[64]; };
+
+void ref_ag_cigar_norm_batch(const int *params, const char *textBuf, const char *patBuf, const char *qualBuf, const RefAgCigarJob *jobs, _int64 nJobs,
+                             RefAgCigarNormOut *out)
+{
+    static AffineGapVectorizedWithCigar *agc = NULL;
+    if (agc == NULL) {
+        void *m = NULL;
+        if (posix_memalign(&m, 64, sizeof(AffineGapVectorizedWithCigar))) abort();
+        memset(m, 0, sizeof(AffineGapVectorizedWithCigar));
+        agc = (AffineGapVectorizedWithCigar *)m;
+    }
+    agc->init(params[0], params[1], params[2], params[3]);
+    for (_int64 j = 0; j < nJobs; j++) {
+        const RefAgCigarJob *b = &jobs[j];
+        RefAgCigarNormOut *o = &out[j];
+        memset(o, 0, sizeof(*o));
+        int used = 0, netDel = 0, tailIns = 0, clip = 0;
+        o->score = agc->computeGlobalScoreNormalized(textBuf + b->textOff, b->textLen, patBuf + b->patOff, qualBuf + b->patOff, b->patternLen, b->w, (char *)o->ops,
+                                                     (int)sizeof(o->ops), b->useM != 0, BAM_CIGAR_OPS, &used, &clip, &netDel, &tailIns);
+        o->netDel = netDel; o->tailIns = tailIns; o->addFrontClipping = clip;
+        if (o->score > 0 || (o->score == 0 && clip == 0)) o->nOps = used / 4; else memset(o->ops, 0, sizeof(o->ops));
+    }
+}
+
 /*
  * AffineGapVectorized<dir>::computeScore / computeScoreBanded (AffineGapVectorized.h:821 / 256).
  * The objects hold __m128i members => allocate 16-byte aligned.

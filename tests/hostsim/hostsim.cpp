@@ -429,4 +429,31 @@ void hs_ag_cigar_global_batch(const int *params, const char *textBuf, const char
     }
 }
 
+struct HsAgCigarNormOut { int score, nOps, netDel, tailIns, addFrontClipping; unsigned ops[64]; };
+
+// one persistent scratch, like the reference object's members: the banded form's traceback can read what earlier calls left
+void hs_ag_cigar_norm_batch(const int *params, const char *textBuf, const char *patBuf, const char *qualBuf, const HsAgCigarJob *jobs, int64_t nJobs,
+                            HsAgCigarNormOut *out)
+{
+    const int numVecMax = (1000 + 7) / 8 + 16, rowsMax = 1000 + SG_MAX_K + 8, resMax = 2 * rowsMax;
+    static std::vector<int16_t> H(numVecMax * 8), Hm1(numVecMax * 8), E(numVecMax * 8), prof(5 * numVecMax * 8);
+    static std::vector<uint8_t> bt((size_t)rowsMax * numVecMax * 8), ra(resMax);
+    static std::vector<int> rc(resMax);
+    SgAgCigarScratch S;
+    S.H = H.data(); S.Hm1 = Hm1.data(); S.E = E.data(); S.prof = prof.data(); S.bt = bt.data(); S.resAction = ra.data(); S.resCount = rc.data();
+    S.numVecMax = numVecMax; S.rowsMax = rowsMax; S.resMax = resMax;
+    SgAgParams P = sg_ag_params(params[0], params[1], params[2], params[3], 0, 0);
+    for (int64_t j = 0; j < nJobs; j++) {
+        const HsAgCigarJob &b = jobs[j];
+        HsAgCigarNormOut &o = out[j];
+        memset(&o, 0, sizeof(o));
+        SgAgCigarOut r; int clip = 0;
+        o.score = sg_ag_cigar_normalized(P, S, (const uint8_t *)textBuf + b.textOff, b.textLen, (const uint8_t *)patBuf + b.patOff, (const uint8_t *)qualBuf + b.patOff,
+                                         b.patternLen, b.w, o.ops, 64, b.useM != 0, &r, &clip);
+        o.netDel = r.netDel; o.tailIns = r.tailIns; o.addFrontClipping = clip;
+        if (o.score > 0 || (o.score == 0 && clip == 0)) o.nOps = r.nOps; else memset(o.ops, 0, sizeof(o.ops));
+        for (int q = o.nOps; q < 64; q++) o.ops[q] = 0;       // (the banded attempt may have left operations behind the fall-back's)
+    }
+}
+
 } // extern "C"

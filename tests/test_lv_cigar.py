@@ -233,3 +233,21 @@ def test_affine_gap_global_cigar_equals_reference(reflib, seed, params):
         assert bad.size == 0, (f, int(bad[0]), jobs[int(bad[0])], want[int(bad[0])], got[int(bad[0])])
     assert (want["ops"] == got["ops"]).all()
     assert (want["score"] >= 0).mean() > 0.9 and (want["netDel"] > 0).sum() > 100 and (want["tailIns"] > 0).sum() > 20
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_affine_gap_normalized_cigar_equals_reference(reflib, seed):
+    """computeGlobalScoreNormalized: the banded form (scores shifted by MAX_READ_LENGTH) with its fall-back to the unbanded one, and
+    the front-clipping verdict.  One job sequence through one reference object and one restatement scratch: where the banded
+    traceback steps onto cells the call did not write, both read what the same earlier calls left."""
+    text, pat, qual, jobs = _agc_jobs(reflib, 3000, seed)
+    jobs = jobs.copy()
+    jobs["w"] = np.random.default_rng(seed).choice([3, 8, 14, 27], size=jobs.size)       # k: small enough that most patterns take the banded form
+    want = reflib.ag_cigar_norm_batch(text, pat, qual, jobs)
+    got = hs.ag_cigar_norm_batch(text, pat, qual, jobs, reflib.AGC_NORM_OUT_DTYPE)
+    for f in ("score", "addFrontClipping", "nOps", "netDel", "tailIns"):
+        bad = np.nonzero(want[f] != got[f])[0]
+        assert bad.size == 0, (f, int(bad[0]), bad.size, jobs[int(bad[0])], want[int(bad[0])], got[int(bad[0])])
+    assert (want["ops"] == got["ops"]).all()
+    banded = jobs["patternLen"] >= 3 * (2 * jobs["w"] + 1)
+    assert banded.mean() > 0.5 and (want["score"] > 0).sum() > 1000 and (want["addFrontClipping"] != 0).sum() > 10
