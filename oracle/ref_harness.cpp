@@ -282,6 +282,40 @@ void ref_ag_cigar_norm_batch(const int *params, const char *textBuf, const char 
     }
 }
 
+// SAMFormat::computeCigarString, AffineGapVectorizedWithCigar overload (SAM.cpp:2677-2766 around computeCigar :2470-2592)
+struct RefCigarAgJob { unsigned long long dataOff; long long location; int dataLength, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter,
+                       frontHardClipping, backHardClipping, direction, useM, score, pad; };
+
+void ref_cigar_ag_batch(void *vidx, const int *params, const char *dataBuf, const char *qualBuf, const RefCigarAgJob *jobs, _int64 nJobs, RefCigarOut *out)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    static AffineGapVectorizedWithCigar *agc = NULL;
+    if (agc == NULL) {
+        void *m = NULL;
+        if (posix_memalign(&m, 64, sizeof(AffineGapVectorizedWithCigar))) abort();
+        memset(m, 0, sizeof(AffineGapVectorizedWithCigar));
+        agc = (AffineGapVectorizedWithCigar *)m;
+    }
+    agc->init(params[0], params[1], params[2], params[3]);
+    const int bufSize = MAX_READ_LENGTH * 2;
+    char *cigarBuf = new char[bufSize], *withClipping = new char[bufSize + 32];
+    for (_int64 j = 0; j < nJobs; j++) {
+        const RefCigarAgJob *b = &jobs[j];
+        RefCigarOut *o = &out[j];
+        memset(o, 0, sizeof(*o));
+        int editDistance = -1, addFrontClipping = 0, refSpan = 0;
+        const char *c = SAMFormat::computeCigarString(index->getGenome(), agc, cigarBuf, bufSize, withClipping, bufSize + 32, dataBuf + b->dataOff, qualBuf + b->dataOff,
+                                                      b->dataLength, b->score, (unsigned)b->basesClippedBefore, (GenomeDistance)b->extraBasesClippedBefore,
+                                                      (unsigned)b->basesClippedAfter, (unsigned)b->frontHardClipping, (unsigned)b->backHardClipping,
+                                                      GenomeLocation(b->location), b->direction ? RC : FORWARD, b->useM != 0, &editDistance, &addFrontClipping, &refSpan);
+        o->editDistance = editDistance; o->addFrontClipping = addFrontClipping;
+        if (c == NULL) { o->kind = 0; }
+        else if (c[0] == '*') { o->kind = 1; }
+        else { o->kind = 2; o->refSpan = refSpan; strncpy(o->cigar, c, sizeof(o->cigar) - 1); }
+    }
+    delete[] cigarBuf; delete[] withClipping;
+}
+
 /*
  * AffineGapVectorized<dir>::computeScore / computeScoreBanded (AffineGapVectorized.h:821 / 256).
  * The objects hold __m128i members => allocate 16-byte aligned.

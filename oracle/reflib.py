@@ -121,6 +121,7 @@ def lib():
         L.ref_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.ref_ag_cigar_global_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.ref_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_decode_cigar.restype = C.c_int
         L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -338,6 +339,16 @@ def ag_cigar_norm_batch(text, pat, qual, jobs, params=(1, 4, 6, 1)) -> np.ndarra
     out = np.zeros(jobs.size, dtype=AGC_NORM_OUT_DTYPE)
     prm = np.ascontiguousarray(params, dtype=np.int32)
     lib().ref_ag_cigar_norm_batch(_p(prm), _p(text), _p(pat), _p(qual), _p(np.ascontiguousarray(jobs, dtype=AGC_JOB_DTYPE)), jobs.size, _p(out))
+    return out
+
+
+CIGAR_AG_JOB_DTYPE = np.dtype(CIGAR_JOB_DTYPE.descr + [("score", "<i4"), ("pad", "<i4")])
+
+
+def cigar_ag_batch(index, data: np.ndarray, qual: np.ndarray, jobs: np.ndarray, params=(1, 4, 6, 1)) -> np.ndarray:
+    out = np.zeros(jobs.size, dtype=CIGAR_REF_OUT_DTYPE)
+    prm = np.ascontiguousarray(params, dtype=np.int32)
+    lib().ref_cigar_ag_batch(index.handle, _p(prm), _p(data), _p(qual), _p(np.ascontiguousarray(jobs, dtype=CIGAR_AG_JOB_DTYPE)), jobs.size, _p(out))
     return out
 
 

@@ -456,4 +456,31 @@ void hs_ag_cigar_norm_batch(const int *params, const char *textBuf, const char *
     }
 }
 
+struct HsCigarAgJob { unsigned long long dataOff; long long location; int dataLength, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter,
+                      frontHardClipping, backHardClipping, direction, useM, score, pad; };
+
+void hs_cigar_ag_batch(void *vix, const int *params, const char *dataBuf, const char *qualBuf, const HsCigarAgJob *jobs, int64_t nJobs, HsCigarOut *out)
+{
+    HsIndex *ix = (HsIndex *)vix;
+    const int numVecMax = (1000 + 7) / 8 + 16, rowsMax = 1000 + SG_MAX_K + 8, resMax = 2 * rowsMax;
+    static std::vector<int16_t> H(numVecMax * 8), Hm1(numVecMax * 8), E(numVecMax * 8), prof(5 * numVecMax * 8);
+    static std::vector<uint8_t> bt((size_t)rowsMax * numVecMax * 8), ra(resMax);
+    static std::vector<int> rc(resMax);
+    SgAgCigarScratch S;
+    S.H = H.data(); S.Hm1 = Hm1.data(); S.E = E.data(); S.prof = prof.data(); S.bt = bt.data(); S.resAction = ra.data(); S.resCount = rc.data();
+    S.numVecMax = numVecMax; S.rowsMax = rowsMax; S.resMax = resMax;
+    SgAgParams P = sg_ag_params(params[0], params[1], params[2], params[3], 0, 0);
+    for (int64_t j = 0; j < nJobs; j++) {
+        const HsCigarAgJob &b = jobs[j];
+        HsCigarOut &o = out[j];
+        memset(&o, 0, sizeof(o));
+        SgCigarOut r;
+        sg_cigar_ag(ix->view, P, S, (const uint8_t *)dataBuf + b.dataOff, (const uint8_t *)qualBuf + b.dataOff, b.dataLength, b.score, (uint32_t)b.basesClippedBefore,
+                    b.extraBasesClippedBefore, (uint32_t)b.basesClippedAfter, (uint32_t)b.frontHardClipping, (uint32_t)b.backHardClipping, b.location, b.useM != 0,
+                    o.ops, 40, &r);
+        o.kind = r.kind; o.editDistance = r.editDistance; o.addFrontClipping = r.addFrontClipping;
+        if (r.kind == 2) { o.refSpan = r.refSpan; o.nOps = r.nOps; for (int q = o.nOps; q < 40; q++) o.ops[q] = 0; } else memset(o.ops, 0, sizeof(o.ops));
+    }
+}
+
 } // extern "C"

@@ -49,6 +49,7 @@ def lib():
         L.hs_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.hs_ag_cigar_global_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.hs_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.hs_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.hs_aligner_create.restype = C.c_void_p
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
@@ -165,6 +166,13 @@ def ag_cigar_norm_batch(text, pat, qual, jobs, out_dtype, params=(1, 4, 6, 1)):
     out = np.zeros(jobs.size, dtype=out_dtype)
     prm = np.ascontiguousarray(params, dtype=np.int32)
     lib().hs_ag_cigar_norm_batch(_p(prm), _p(text), _p(pat), _p(qual), _p(np.ascontiguousarray(jobs)), jobs.size, _p(out))
+    return out
+
+
+def cigar_ag_batch(index, data, qual, jobs, params=(1, 4, 6, 1)):
+    out = np.zeros(jobs.size, dtype=CIGAR_OUT_DTYPE)
+    prm = np.ascontiguousarray(params, dtype=np.int32)
+    lib().hs_cigar_ag_batch(index.handle, _p(prm), _p(data), _p(qual), _p(np.ascontiguousarray(jobs)), jobs.size, _p(out))
     return out
 
 

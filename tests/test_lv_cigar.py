@@ -251,3 +251,72 @@ def test_affine_gap_normalized_cigar_equals_reference(reflib, seed):
     assert (want["ops"] == got["ops"]).all()
     banded = jobs["patternLen"] >= 3 * (2 * jobs["w"] + 1)
     assert banded.mean() > 0.5 and (want["score"] > 0).sum() > 1000 and (want["addFrontClipping"] != 0).sum() > 10
+
+
+def _record_jobs_ag(reflib, small_cfg, seed):
+    """Reads the reference aligner rescored with affine gap, at its locations with its clip counts and scores; starts shifted now and
+    then; reads hanging over contig ends."""
+    from snap_b200 import synth
+    rng = np.random.default_rng(seed)
+    bases, starts = small_cfg.padded_bases()
+    data = []; qual = []; jobs = []; off = 0
+
+    def add(read, q, loc, direction, score, cb=0, xb=0, ca=0, fh=0, bh=0, use_m=0):
+        nonlocal off
+        data.append(np.asarray(read, dtype=np.uint8)); data.append(np.zeros(16, dtype=np.uint8))
+        qual.append(np.asarray(q, dtype=np.uint8)); qual.append(np.zeros(16, dtype=np.uint8))
+        jobs.append((off + cb, loc, len(read) - cb - ca, cb, xb, ca, fh, bh, direction, use_m, score, 0))
+        off += len(read) + 16
+
+    ridx = reflib.RefIndex(small_cfg.idx)
+    p = reflib.default_params(maxDist=14)
+    for name in ("noisy150", "indel100", "long250"):
+        rb = small_cfg.reads[name]
+        res, _ = reflib.RefSingleAligner(ridx, p).align(rb)
+        for i in range(rb.n):
+            if res[i]["status"] == 0 or res[i]["usedAffineGapScoring"] == 0:
+                continue
+            b, q = rb.read(i)
+            r = np.frombuffer(b, dtype=np.uint8); qq = np.frombuffer(q, dtype=np.uint8)
+            if res[i]["direction"] == 1:
+                r = synth.revcomp(r); qq = qq[::-1]
+            shift = int(rng.choice([0, 0, 0, 0, 0, 0, 1, -1, 2]))
+            add(r, qq, int(res[i]["location"]) + shift, int(res[i]["direction"]), int(res[i]["score"]) + int(rng.choice([0, 0, 1, 3])),
+                cb=int(res[i]["basesClippedBefore"]), ca=int(res[i]["basesClippedAfter"]),
+                fh=int(rng.choice([0, 0, 0, 5])), bh=int(rng.choice([0, 0, 0, 4])), use_m=int(rng.integers(0, 2)))
+    for c, contig in enumerate(small_cfg.contigs):
+        end_loc = int(starts[c]) + contig.size
+        for over in (1, 2, 5, 17, 40):
+            for kind in ("clean", "del", "ins", "sub"):
+                src = contig[contig.size - 150 + over - 8: contig.size].copy()
+                if kind == "del":
+                    src = np.delete(src, [100, 101])
+                elif kind == "ins":
+                    src = np.insert(src, 90, [ord("A"), ord("C"), ord("A")])
+                elif kind == "sub":
+                    src[60] = ord("A") if src[60] != ord("A") else ord("C")
+                tail = np.frombuffer(bytes(rng.choice(list(b"ACGT"), size=over)), dtype=np.uint8)
+                read = np.concatenate([src, tail])
+                q = rng.integers(40, 75, size=read.size).astype(np.uint8)
+                loc = end_loc - (150 - over + 8)
+                for score in (4, 10, 25):
+                    add(read, q, loc, 0, score, use_m=int(rng.integers(0, 2)))
+    return (np.concatenate(data), np.concatenate(qual), np.array(jobs, dtype=reflib.CIGAR_AG_JOB_DTYPE), ridx)
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_record_cigars_affine_gap_equal_reference(reflib, small_cfg, seed):
+    """sg_cigar_ag vs SAMFormat::computeCigarString (affine-gap overload) on the reference aligner's own affine-gap results and on
+    hand-placed reads across contig ends."""
+    data, qual, jobs, ridx = _record_jobs_ag(reflib, small_cfg, seed)
+    want = reflib.cigar_ag_batch(ridx, data, qual, jobs)
+    got = hs.cigar_ag_batch(hs.HsIndex(small_cfg.idx), data, qual, jobs)
+    for f in ("kind", "addFrontClipping"):
+        bad = np.nonzero(want[f] != got[f])[0]
+        assert bad.size == 0, (f, int(bad[0]), bad.size, jobs[int(bad[0])], want[int(bad[0])], got[int(bad[0])])
+    ok = want["kind"] == 2
+    for i in np.nonzero(ok)[0]:
+        assert want[i]["cigar"].decode() == _ops_to_text(got[i]["ops"], int(got[i]["nOps"])), (int(i), jobs[i], want[i], got[i])
+    assert (want["editDistance"][ok] == got["editDistance"][ok]).all() and (want["refSpan"][ok] == got["refSpan"][ok]).all()
+    texts = [w.decode() for w in want["cigar"][ok]]
+    assert ok.sum() > 500 and sum("D" in t or "I" in t for t in texts) > 150 and sum("S" in t for t in texts) > 50
