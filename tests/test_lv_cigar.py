@@ -320,3 +320,29 @@ def test_record_cigars_affine_gap_equal_reference(reflib, small_cfg, seed):
     assert (want["editDistance"][ok] == got["editDistance"][ok]).all() and (want["refSpan"][ok] == got["refSpan"][ok]).all()
     texts = [w.decode() for w in want["cigar"][ok]]
     assert ok.sum() > 500 and sum("D" in t or "I" in t for t in texts) > 150 and sum("S" in t for t in texts) > 50
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("indel100", []), ("std150", ["-=" ]), ("noisy150", ["-G-"])])
+def test_sam_records_equal_reference_binary(reflib, small_cfg, tmp_path, name, extra):
+    """End to end for the output stage: the SAM file `snap-aligner single ... -o out.sam -t 1` writes vs sg_sam.h run over the
+    result records of the same reads (record for record, byte for byte, headers aside).  `-=`: =/X CIGARs instead of M;
+    `-G-`: affine gap off (every CIGAR from the Landau-Vishkin routine)."""
+    import subprocess
+    rb = small_cfg.reads[name]
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.sam")
+    rb.write_fastq(fq)
+    r = subprocess.run([reflib.SNAP_ALIGNER, "single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"] + extra, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    want = [l for l in open(out, "rb").read().split(b"\n") if l and not l.startswith(b"@")]
+    use_ag = "-G-" not in extra
+    p = reflib.default_params(maxDist=14, useAffineGap=1 if use_ag else 0)
+    res, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), p).align(rb)
+    text = hs.sam_single(hs.HsIndex(small_cfg.idx), rb, [b"r%d" % i for i in range(rb.n)], res, use_m=("-=" not in extra), use_affine_gap=use_ag)
+    got = [l for l in text.split(b"\n") if l]
+    assert len(want) == len(got) == rb.n
+    bad = [i for i in range(rb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+    cig = [l.split(b"\t")[5] for l in want]
+    assert sum(b"I" in c or b"D" in c for c in cig) > 20
+    if name == "noisy150":
+        assert sum(c == b"*" for c in cig) >= 1                # unaligned reads are written too
