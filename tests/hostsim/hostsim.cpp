@@ -487,7 +487,7 @@ void hs_cigar_ag_batch(void *vix, const int *params, const char *dataBuf, const 
 // sg_sam.h: one SAM record per read from the result records, text appended to `out` (returns the bytes written, -1 if `outCap` is too small)
 int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAffineGap, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
                             const uint32_t *lens, const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results,
-                            char *out, int64_t outCap)
+                            const snapgpu_paired_result *pairedResults, char *out, int64_t outCap)
 {
     HsIndex *ix = (HsIndex *)vix;
     const int kmax = SG_MAX_K - 1;
@@ -508,7 +508,31 @@ int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAff
     C.agS.H = H.data(); C.agS.Hm1 = Hm1.data(); C.agS.E = E.data(); C.agS.prof = prof.data(); C.agS.bt = bt.data(); C.agS.resAction = ra.data(); C.agS.resCount = rc.data();
     C.agS.numVecMax = numVecMax; C.agS.rowsMax = rowsMax; C.agS.resMax = resMax;
     C.data = data.data(); C.quality = quality.data();
+    std::vector<uint8_t> data2(1024), quality2(1024);
+    C.data2 = data2.data(); C.quality2 = quality2.data();
     int64_t used = 0;
+    if (pairedResults != NULL) {
+        for (int64_t i = 0; i < n / 2; i++) {
+            if (lens[2 * i] > 1000 || lens[2 * i + 1] > 1000 || used + 8192 > outCap) return -1;
+            SgSamRead R[2];
+            for (int w = 0; w < 2; w++) {
+                const int64_t k = 2 * i + w;
+                R[w].unclippedData = (const uint8_t *)bases + offsets[k]; R[w].unclippedQuality = (const uint8_t *)quals + offsets[k]; R[w].unclippedLength = lens[k];
+                R[w].frontClipped = 0; R[w].dataLength = lens[k]; R[w].id = (const uint8_t *)ids + idOffsets[k]; R[w].idLength = idLens[k];
+                R[w].additionalFrontClipping = 0; R[w].additionalBackClipping = 0;
+            }
+            const snapgpu_paired_result &r = pairedResults[i];
+            SgSamPairResult pr;
+            for (int w = 0; w < 2; w++) {
+                pr.status[w] = r.status[w]; pr.location[w] = r.location[w]; pr.direction[w] = r.direction[w]; pr.mapq[w] = r.mapq[w]; pr.score[w] = r.score[w];
+                pr.usedAffineGapScoring[w] = r.usedAffineGapScoring[w]; pr.basesClippedBefore[w] = r.basesClippedBefore[w]; pr.basesClippedAfter[w] = r.basesClippedAfter[w];
+                pr.clippingForReadAdjustment[w] = r.clippingForReadAdjustment[w];
+            }
+            pr.alignedAsPair = r.alignedAsPair;
+            used += sg_sam_write_pair(C, R[0], R[1], pr, out + used);
+        }
+        return used;
+    }
     for (int64_t i = 0; i < n; i++) {
         if (lens[i] > 1000 || used + 4096 > outCap) return -1;
         SgSamRead R;

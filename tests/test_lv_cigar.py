@@ -9,6 +9,10 @@ import pytest
 
 import hostsim_lib as hs
 
+# `snap paired` stock options (-d 27, soft clipping on) and `-hc` (soft clipping off: end bonuses 5/5, minAGScoreImprovement 15)
+PAIRED_DEFAULT = (dict(maxDist=27), dict())
+PAIRED_HC = (dict(maxDist=27, fivePrimeEndBonus=5, threePrimeEndBonus=5), dict(useSoftClipping=0, minAGScoreImprovement=15))
+
 # (text, pattern, k, cigar with =/X, cigar with M) -- reference tests/LandauVishkinTest.cpp:38-128
 KNOWN = [
     ("abcde", "abcde", 2, "5=", "5M"),
@@ -346,3 +350,30 @@ def test_sam_records_equal_reference_binary(reflib, small_cfg, tmp_path, name, e
     assert sum(b"I" in c or b"D" in c for c in cig) > 20
     if name == "noisy150":
         assert sum(c == b"*" for c in cig) >= 1                # unaligned reads are written too
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("clipped150", []), ("std150", ["-="]), ("len100", ["-hc"])])
+def test_sam_pair_records_equal_reference_binary(reflib, small_cfg, tmp_path, name, extra):
+    """The same for pairs: `snap-aligner paired ... -o out.sam -t 1` vs sg_sam_write_pair over the pair result records (mate
+    fields, template length, write order, QS)."""
+    import subprocess
+    pb = small_cfg.pairs[name]
+    f1 = str(tmp_path / "p1.fq"); f2 = str(tmp_path / "p2.fq"); out = str(tmp_path / "o.sam")
+    with open(f1, "wb") as a, open(f2, "wb") as b:
+        for i in range(pb.n // 2):
+            x, q = pb.read(2 * i); a.write(b"@p%d/1\n%s\n+\n%s\n" % (i, x, q))
+            x, q = pb.read(2 * i + 1); b.write(b"@p%d/2\n%s\n+\n%s\n" % (i, x, q))
+    r = subprocess.run([reflib.SNAP_ALIGNER, "paired", small_cfg.idx, f1, f2, "-o", out, "-t", "1"] + extra, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    want = [l for l in open(out, "rb").read().split(b"\n") if l and not l.startswith(b"@")]
+    kw, pkw = PAIRED_DEFAULT if "-hc" not in extra else PAIRED_HC
+    p, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    res, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), p, pp).align(pb)
+    ids = []
+    for i in range(pb.n // 2):
+        ids += [b"p%d/1" % i, b"p%d/2" % i]
+    text = hs.sam_single(hs.HsIndex(small_cfg.idx), pb, ids, res, use_m=("-=" not in extra), use_affine_gap=True, paired=True)
+    got = [l for l in text.split(b"\n") if l]
+    assert len(want) == len(got) == pb.n
+    bad = [i for i in range(pb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
