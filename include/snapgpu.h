@@ -319,6 +319,28 @@ int  snapgpu_fastq_parse(snapgpu_fastq *f, const char *text, int64_t nBytes, int
                          uint64_t *idOffsets, uint32_t *idLens, uint32_t *frontClipped,
                          int64_t *nReads, int64_t *bytesConsumed);
 
+/*
+ * Output stage: SAM records from result records, formatted on the device.
+ * snapgpu_sam_format_single replaces, for one batch, SimpleReadWriter::writeReads (reference SNAPLib/ReadWriter.cpp:170-330) ->
+ * SAMFormat::writeRead (SAM.cpp:1897-2352) -> createSAMLine (:1423-1573) and computeCigarString (:2595-2766) with
+ * LandauVishkinWithCigar (LandauVishkin.cpp:141-650) / AffineGapVectorizedWithCigar (AffineGapVectorized.cpp:159-1128);
+ * snapgpu_sam_format_paired replaces SimpleReadWriter::writePairs (ReadWriter.cpp:362-560) -> SAMFormat::writePairs
+ * (SAM.cpp:1574-1896) and fillMateInfo (:1308-1422): two records per pair, in genome order, with mate fields and QS.
+ * Primary alignments, default tags (PG, NM, the default read group line); the header lines are the caller's.
+ * reads / ids / results are HOST arrays in the layout of snapgpu_align_single / _paired (ids: concatenated, idOffsets / idLens per
+ * read, at most 255 characters each); `text` receives the records back to back, *textBytes their total length.
+ * `useM`: M instead of = / X operations (SNAP's default, -M).  Scoring parameters and useAffineGap are taken from `params`.
+ */
+typedef struct snapgpu_sam snapgpu_sam;
+int  snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, int32_t useM, int64_t maxBatchReads, snapgpu_sam **out);
+void snapgpu_sam_destroy(snapgpu_sam *s);
+int  snapgpu_sam_format_single(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
+                               const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results,
+                               char *text, int64_t textCapacity, int64_t *textBytes);
+int  snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
+                               const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_paired_result *results,
+                               char *text, int64_t textCapacity, int64_t *textBytes);
+
 /* Number of kernel launches issued through this aligner since creation (bench.py's gpu_launches). */
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a);
 

@@ -18,6 +18,7 @@
 #include "sg_host.h"
 #include "sg_build.cuh"
 #include "sg_fastq.cuh"
+#include "sg_sam.h"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -1377,6 +1378,241 @@ int snapgpu_align_paired(snapgpu_aligner *a, int64_t nPairs, const char *bases, 
 // ------------------------------------------------------------------------------------------------
 // FASTQ ingest
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Output stage: SAM records on the device.  First form: ONE THREAD PER READ (pair) running the scalar
+// restatements of sg_lv_cigar.h / sg_ag_cigar.h / sg_cigar.h / sg_sam.h -- the code the host tests pin against the
+// reference binary's SAM file -- each into its own fixed-size slot; the host wrapper packs the slots.
+// ------------------------------------------------------------------------------------------------
+struct SgSamScratchLayout { size_t lvInts, agVec, agRows, agRes, perThread; uint32_t maxReadLen; };
+
+static SgSamScratchLayout sam_layout(uint32_t maxReadLen)
+{
+    SgSamScratchLayout l;
+    l.maxReadLen = maxReadLen;
+    l.lvInts = sg_lv_cigar_scratch_ints(SG_MAX_K - 1);
+    l.agVec = (size_t)maxReadLen / 8 + 48;
+    l.agRows = (size_t)maxReadLen + SG_MAX_K + 8;
+    l.agRes = 2 * l.agRows;
+    size_t b = 0;
+    b += sg_align_up(l.lvInts * 4, 256) * 2 + sg_align_up(l.lvInts, 256);                 // L, totalIndels, A
+    b += sg_align_up((SG_MAX_K + 2) * 4, 256) * 2 + sg_align_up(SG_MAX_K + 2, 256);      // btMatched, btD, btAction
+    b += sg_align_up(l.agVec * 8 * 2, 256) * 3 + sg_align_up(5 * l.agVec * 8 * 2, 256);  // H, Hm1, E, prof
+    b += sg_align_up(l.agRows * l.agVec * 8, 256);                                        // bt
+    b += sg_align_up(l.agRes, 256) + sg_align_up(l.agRes * 4, 256);                       // resAction, resCount
+    b += sg_align_up((size_t)maxReadLen + 16, 256) * 4;                                   // data, quality x2
+    l.perThread = b;
+    return l;
+}
+
+__device__ static void sam_carve(const SgSamScratchLayout &l, uint8_t *q, SgSamContext *C)
+{
+    C->lv.kmax = SG_MAX_K - 1;
+    C->lv.L = (int *)q; q += sg_align_up(l.lvInts * 4, 256);
+    C->lv.totalIndels = (int *)q; q += sg_align_up(l.lvInts * 4, 256);
+    C->lv.A = q; q += sg_align_up(l.lvInts, 256);
+    C->lv.btMatched = (int *)q; q += sg_align_up((SG_MAX_K + 2) * 4, 256);
+    C->lv.btD = (int *)q; q += sg_align_up((SG_MAX_K + 2) * 4, 256);
+    C->lv.btAction = q; q += sg_align_up(SG_MAX_K + 2, 256);
+    C->agS.numVecMax = (int)l.agVec; C->agS.rowsMax = (int)l.agRows; C->agS.resMax = (int)l.agRes;
+    C->agS.H = (int16_t *)q; q += sg_align_up(l.agVec * 8 * 2, 256);
+    C->agS.Hm1 = (int16_t *)q; q += sg_align_up(l.agVec * 8 * 2, 256);
+    C->agS.E = (int16_t *)q; q += sg_align_up(l.agVec * 8 * 2, 256);
+    C->agS.prof = (int16_t *)q; q += sg_align_up(5 * l.agVec * 8 * 2, 256);
+    C->agS.bt = q; q += sg_align_up(l.agRows * l.agVec * 8, 256);
+    C->agS.resAction = q; q += sg_align_up(l.agRes, 256);
+    C->agS.resCount = (int *)q; q += sg_align_up(l.agRes * 4, 256);
+    C->data = q; q += sg_align_up((size_t)l.maxReadLen + 16, 256);
+    C->quality = q; q += sg_align_up((size_t)l.maxReadLen + 16, 256);
+    C->data2 = q; q += sg_align_up((size_t)l.maxReadLen + 16, 256);
+    C->quality2 = q;
+}
+
+__global__ void __launch_bounds__(64)
+sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, uint8_t *scratch, const char *const *contigNames, const char *readGroupAux,
+              SgAgParams ag, int useM, int useAffineGap, long long nUnits, int paired, const uint8_t *bases, const uint8_t *quals,
+              const unsigned long long *offsets, const uint32_t *lens, const uint8_t *ids, const unsigned long long *idOffsets, const uint32_t *idLens,
+              const snapgpu_single_result *single, const snapgpu_paired_result *pairs, char *slots, uint32_t slotBytes, uint32_t *recordBytes)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nT = (long long)gridDim.x * blockDim.x;
+    SgSamContext C;
+    C.ix = &ix; C.contigName = contigNames; C.ag = ag; C.readGroupAux = readGroupAux; C.useM = useM != 0; C.useAffineGap = useAffineGap != 0;
+    sam_carve(lay, scratch + (size_t)t * lay.perThread, &C);
+    for (long long u = t; u < nUnits; u += nT) {
+        char *out = slots + (size_t)u * slotBytes;
+        if (!paired) {
+            SgSamRead R;
+            R.unclippedData = bases + offsets[u]; R.unclippedQuality = quals + offsets[u]; R.unclippedLength = lens[u];
+            R.frontClipped = 0; R.dataLength = lens[u]; R.id = ids + idOffsets[u]; R.idLength = idLens[u];
+            R.additionalFrontClipping = 0; R.additionalBackClipping = 0;
+            const snapgpu_single_result &r = single[u];
+            SgSamResult sr;
+            sr.status = r.status; sr.location = r.status == SNAPGPU_NOT_FOUND ? -1 : r.location; sr.direction = r.direction; sr.mapq = r.mapq; sr.score = r.score;
+            sr.scorePriorToClipping = r.scorePriorToClipping; sr.usedAffineGapScoring = r.usedAffineGapScoring; sr.basesClippedBefore = r.basesClippedBefore;
+            sr.basesClippedAfter = r.basesClippedAfter; sr.clippingForReadAdjustment = r.clippingForReadAdjustment;
+            recordBytes[u] = (uint32_t)sg_sam_write_single(C, R, sr, out);
+        } else {
+            SgSamRead R[2];
+            for (int w = 0; w < 2; w++) {
+                const long long k = 2 * u + w;
+                R[w].unclippedData = bases + offsets[k]; R[w].unclippedQuality = quals + offsets[k]; R[w].unclippedLength = lens[k];
+                R[w].frontClipped = 0; R[w].dataLength = lens[k]; R[w].id = ids + idOffsets[k]; R[w].idLength = idLens[k];
+                R[w].additionalFrontClipping = 0; R[w].additionalBackClipping = 0;
+            }
+            const snapgpu_paired_result &r = pairs[u];
+            SgSamPairResult pr;
+            for (int w = 0; w < 2; w++) {
+                pr.status[w] = r.status[w]; pr.location[w] = r.location[w]; pr.direction[w] = r.direction[w]; pr.mapq[w] = r.mapq[w]; pr.score[w] = r.score[w];
+                pr.usedAffineGapScoring[w] = r.usedAffineGapScoring[w]; pr.basesClippedBefore[w] = r.basesClippedBefore[w]; pr.basesClippedAfter[w] = r.basesClippedAfter[w];
+                pr.clippingForReadAdjustment[w] = r.clippingForReadAdjustment[w];
+            }
+            pr.alignedAsPair = r.alignedAsPair;
+            recordBytes[u] = (uint32_t)sg_sam_write_pair(C, R[0], R[1], pr, out);
+        }
+    }
+}
+
+struct snapgpu_sam {
+    const snapgpu_index *index = nullptr;
+    int device = 0;
+    SgSamScratchLayout lay;
+    SgAgParams ag;
+    int useM = 1, useAffineGap = 1;
+    int64_t maxBatchReads = 0;
+    int nThreads = 0;
+    uint32_t slotBytes = 0;
+    uint8_t *d_scratch = nullptr;
+    char *d_names = nullptr; const char **d_namePtrs = nullptr; char *d_rgAux = nullptr;
+    // staging of the host-buffer call
+    uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_ids = nullptr, *d_results = nullptr;
+    unsigned long long *d_offsets = nullptr, *d_idOffsets = nullptr;
+    uint32_t *d_lens = nullptr, *d_idLens = nullptr, *d_recordBytes = nullptr;
+    char *d_slots = nullptr;
+    std::vector<char> h_slots; std::vector<uint32_t> h_recordBytes;
+    cudaStream_t stream = nullptr;
+};
+
+void snapgpu_sam_destroy(snapgpu_sam *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    cudaFree(s->d_scratch); cudaFree(s->d_names); cudaFree((void *)s->d_namePtrs); cudaFree(s->d_rgAux); cudaFree(s->d_bases); cudaFree(s->d_quals); cudaFree(s->d_ids);
+    cudaFree(s->d_results); cudaFree(s->d_offsets); cudaFree(s->d_idOffsets); cudaFree(s->d_lens); cudaFree(s->d_idLens); cudaFree(s->d_recordBytes); cudaFree(s->d_slots);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+#define SG_SAM_MAX_ID 256
+
+int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, int32_t useM, int64_t maxBatchReads, snapgpu_sam **out)
+{
+    if (!idx || !params || !out) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(idx->device)) return 1;
+    if (maxBatchReads <= 0) return sg_fail("maxBatchReads must be positive");
+    snapgpu_sam *s = new (std::nothrow) snapgpu_sam;
+    if (!s) return sg_fail("out of memory");
+    s->index = idx; s->device = idx->device; s->maxBatchReads = maxBatchReads;
+    s->lay = sam_layout(env_max_read_len());
+    s->ag = sg_ag_params(params->matchReward, params->subPenalty, params->gapOpenPenalty, params->gapExtendPenalty, 0, 0);
+    s->useM = useM != 0; s->useAffineGap = params->useAffineGap != 0;
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, s->device));
+    int64_t threads = (int64_t)prop.multiProcessorCount * 64;
+    if (threads > maxBatchReads) threads = (maxBatchReads + 63) / 64 * 64;
+    s->nThreads = (int)threads;
+    s->slotBytes = 2 * (2 * s->lay.maxReadLen + SG_SAM_MAX_ID + 512);          // room for the two records of a pair
+    // contig names and the default read group line (ReaderContext::defaultReadGroupAux for the default read group "FASTQ")
+    std::string blob; std::vector<size_t> off;
+    for (size_t c = 0; c < idx->h_contigName.size(); c++) { off.push_back(blob.size()); blob += idx->h_contigName[c]; blob.push_back('\0'); }
+    const char rg[] = "\tRG:Z:FASTQ\tPL:Z:Illumina\tPU:Z:pu\tLB:Z:lb\tSM:Z:sm";
+    bool ok = cudaMalloc((void **)&s->d_names, blob.size() + 16) == cudaSuccess && cudaMalloc((void **)&s->d_namePtrs, (off.size() + 1) * sizeof(char *)) == cudaSuccess &&
+              cudaMalloc((void **)&s->d_rgAux, sizeof(rg)) == cudaSuccess && cudaMalloc((void **)&s->d_scratch, s->lay.perThread * (size_t)s->nThreads) == cudaSuccess;
+    const size_t nb = (size_t)maxBatchReads * s->lay.maxReadLen;
+    ok = ok && cudaMalloc((void **)&s->d_bases, nb + 16) == cudaSuccess && cudaMalloc((void **)&s->d_quals, nb + 16) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_ids, (size_t)maxBatchReads * SG_SAM_MAX_ID + 16) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_results, (size_t)maxBatchReads * sizeof(snapgpu_paired_result)) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_offsets, (size_t)maxBatchReads * 8) == cudaSuccess && cudaMalloc((void **)&s->d_idOffsets, (size_t)maxBatchReads * 8) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_lens, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_idLens, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_recordBytes, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_slots, (size_t)maxBatchReads * s->slotBytes) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) {
+        std::string msg = std::string("snapgpu_sam_create: ") + cudaGetErrorString(cudaGetLastError());
+        snapgpu_sam_destroy(s);
+        return sg_fail(msg);
+    }
+    std::vector<const char *> ptrs;
+    for (size_t c = 0; c < off.size(); c++) ptrs.push_back(s->d_names + off[c]);
+    SG_CUDA(cudaMemcpy(s->d_names, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    if (!ptrs.empty()) SG_CUDA(cudaMemcpy((void *)s->d_namePtrs, ptrs.data(), ptrs.size() * sizeof(char *), cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(s->d_rgAux, rg, sizeof(rg), cudaMemcpyHostToDevice));
+    s->h_slots.resize((size_t)maxBatchReads * s->slotBytes);
+    s->h_recordBytes.resize((size_t)maxBatchReads);
+    *out = s;
+    return 0;
+}
+
+static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens, const char *ids,
+                      const uint64_t *idOffsets, const uint32_t *idLens, const void *results, char *text, int64_t textCapacity, int64_t *textBytes)
+{
+    if (!s || !bases || !quals || !offsets || !lens || !ids || !idOffsets || !idLens || !results || !text || !textBytes) return sg_fail("null argument");
+    if (nReads < 0 || nReads > s->maxBatchReads || (paired && (nReads & 1))) return sg_fail("snapgpu_sam_format: bad read count");
+    *textBytes = 0;
+    if (nReads == 0) return 0;
+    SG_CUDA(cudaSetDevice(s->device));
+    size_t totalBases = 0, totalIds = 0;
+    for (int64_t i = 0; i < nReads; i++) {
+        if (lens[i] > s->lay.maxReadLen) return sg_fail("a read is longer than the configured maximum (SNAPGPU_MAX_READ_LEN)");
+        if (idLens[i] >= SG_SAM_MAX_ID) return sg_fail("a read id is longer than 255 characters");
+        if (offsets[i] + lens[i] > totalBases) totalBases = (size_t)(offsets[i] + lens[i]);
+        if (idOffsets[i] + idLens[i] > totalIds) totalIds = (size_t)(idOffsets[i] + idLens[i]);
+    }
+    if (totalBases > (size_t)s->maxBatchReads * s->lay.maxReadLen || totalIds > (size_t)s->maxBatchReads * SG_SAM_MAX_ID) return sg_fail("snapgpu_sam_format: input buffers larger than the handle was sized for");
+    cudaStream_t st = s->stream;
+    const int64_t nUnits = paired ? nReads / 2 : nReads;
+    SG_CUDA(cudaMemcpyAsync(s->d_bases, bases, totalBases, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_quals, quals, totalBases, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_ids, ids, totalIds, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_offsets, offsets, (size_t)nReads * 8, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_idOffsets, idOffsets, (size_t)nReads * 8, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_lens, lens, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_idLens, idLens, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(s->d_results, results, (size_t)nUnits * (paired ? sizeof(snapgpu_paired_result) : sizeof(snapgpu_single_result)), cudaMemcpyHostToDevice, st));
+    int64_t threads = s->nThreads < nUnits ? s->nThreads : (nUnits + 63) / 64 * 64;
+    sg_sam_kernel<<<(int)(threads / 64), 64, 0, st>>>(s->index->view, s->lay, s->d_scratch, s->d_namePtrs, s->d_rgAux, s->ag, s->useM, s->useAffineGap, nUnits, paired,
+                                                      s->d_bases, s->d_quals, s->d_offsets, s->d_lens, s->d_ids, s->d_idOffsets, s->d_idLens,
+                                                      paired ? nullptr : (const snapgpu_single_result *)s->d_results, paired ? (const snapgpu_paired_result *)s->d_results : nullptr,
+                                                      s->d_slots, s->slotBytes, s->d_recordBytes);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(s->h_recordBytes.data(), s->d_recordBytes, (size_t)nUnits * 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(s->h_slots.data(), s->d_slots, (size_t)nUnits * s->slotBytes, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    int64_t used = 0;
+    for (int64_t u = 0; u < nUnits; u++) {
+        const uint32_t n = s->h_recordBytes[u];
+        if (n == 0 || n > s->slotBytes) return sg_fail("snapgpu_sam_format: a record could not be formatted");
+        if (used + n > textCapacity) return sg_fail("snapgpu_sam_format: text buffer too small");
+        memcpy(text + used, s->h_slots.data() + (size_t)u * s->slotBytes, n);
+        used += n;
+    }
+    *textBytes = used;
+    return 0;
+}
+
+int snapgpu_sam_format_single(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens, const char *ids,
+                              const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
+{
+    return sam_format(s, 0, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, results, text, textCapacity, textBytes);
+}
+
+int snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens, const char *ids,
+                              const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_paired_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
+{
+    return sam_format(s, 1, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, results, text, textCapacity, textBytes);
+}
+
 struct snapgpu_fastq {
     int device = 0;
     int64_t maxBytes = 0, maxReads = 0, nTilesMax = 0;

@@ -84,7 +84,7 @@ EXPORTS = [
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
-    "snapgpu_fastq_parse", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 _lib = None
@@ -120,6 +120,10 @@ def lib():
         L.snapgpu_aligner_check.argtypes = [C.c_void_p, C.c_void_p]
         L.snapgpu_fastq_create.argtypes = [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
         L.snapgpu_fastq_destroy.argtypes = [C.c_void_p]
+        L.snapgpu_sam_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]
+        L.snapgpu_sam_destroy.argtypes = [C.c_void_p]
+        L.snapgpu_sam_format_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64, C.POINTER(C.c_int64)]
+        L.snapgpu_sam_format_paired.argtypes = L.snapgpu_sam_format_single.argtypes
         L.snapgpu_fastq_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.snapgpu_fastq_parse_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_aligner_launch_count.restype = C.c_int64
@@ -312,6 +316,36 @@ class PairedAligner:
     def close(self):
         if self.handle:
             lib().snapgpu_aligner_destroy(self.handle)
+            self.handle = None
+
+
+class SamFormatter:
+    """SAM records of a batch from its result records (SimpleReadWriter::writeReads / writePairs + SAMFormat for a whole batch)."""
+
+    def __init__(self, index, params, max_batch_reads: int, use_m: bool = True):
+        h = C.c_void_p()
+        _check(lib().snapgpu_sam_create(index.handle, C.byref(params), 1 if use_m else 0, max_batch_reads, C.byref(h)))
+        self.handle = h
+        self.max_batch_reads = max_batch_reads
+
+    def format(self, batch, ids, results, paired: bool = False) -> bytes:
+        """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one
+        per pair with paired=True)."""
+        id_buf = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
+        id_lens = np.array([len(x) for x in ids], dtype=np.uint32)
+        id_offs = np.concatenate([[0], np.cumsum(id_lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+        cap = int(batch.n) * (2 * int(batch.lens.max()) + 1024) + 4096
+        text = np.zeros(cap, dtype=np.uint8)
+        used = C.c_int64(0)
+        res = np.ascontiguousarray(results)
+        fn = lib().snapgpu_sam_format_paired if paired else lib().snapgpu_sam_format_single
+        _check(fn(self.handle, batch.n, _p(np.ascontiguousarray(batch.bases)), _p(np.ascontiguousarray(batch.quals)), _p(np.ascontiguousarray(batch.offsets)),
+                  _p(np.ascontiguousarray(batch.lens)), _p(id_buf), _p(id_offs), _p(id_lens), _p(res), _p(text), cap, C.byref(used)))
+        return text[:used.value].tobytes()
+
+    def close(self):
+        if self.handle:
+            lib().snapgpu_sam_destroy(self.handle)
             self.handle = None
 
 

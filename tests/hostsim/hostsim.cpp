@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 #define SG_WITH_PAIRED 1
 #include "../../snap_b200/csrc/sg_align.h"
 #include "../../snap_b200/csrc/sg_paired.h"
@@ -512,7 +513,9 @@ int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAff
     C.data2 = data2.data(); C.quality2 = quality2.data();
     int64_t used = 0;
     if (pairedResults != NULL) {
+        const bool scrubP = getenv("HS_SAM_SCRUB") != NULL;
         for (int64_t i = 0; i < n / 2; i++) {
+            if (scrubP) memset(bt.data(), 0x2a + (int)(i % 7), bt.size());
             if (lens[2 * i] > 1000 || lens[2 * i + 1] > 1000 || used + 8192 > outCap) return -1;
             SgSamRead R[2];
             for (int w = 0; w < 2; w++) {
@@ -533,8 +536,10 @@ int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAff
         }
         return used;
     }
+    const bool scrub = getenv("HS_SAM_SCRUB") != NULL;      // fill the never-cleared action array with junk before every read: does any record depend on call history?
     for (int64_t i = 0; i < n; i++) {
         if (lens[i] > 1000 || used + 4096 > outCap) return -1;
+        if (scrub) memset(bt.data(), 0x2a + (int)(i % 7), bt.size());
         SgSamRead R;
         R.unclippedData = (const uint8_t *)bases + offsets[i]; R.unclippedQuality = (const uint8_t *)quals + offsets[i]; R.unclippedLength = lens[i];
         R.frontClipped = 0; R.dataLength = lens[i]; R.id = (const uint8_t *)ids + idOffsets[i]; R.idLength = idLens[i];

@@ -517,3 +517,54 @@ def test_pinned_host_buffers_give_the_same_results(engine, gidx, small_cfg):
     got, gc = al.align(pb, out=out)
     assert got.tobytes() == want.tobytes() and gc == wc
     al.close()
+
+
+def _reference_sam_lines(reflib, argv):
+    import subprocess
+    r = subprocess.run([reflib.SNAP_ALIGNER] + argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    return [l for l in open(argv[argv.index("-o") + 1], "rb").read().split(b"\n") if l and not l.startswith(b"@")]
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("indel100", ["-="]), ("noisy150", ["-G-"])])
+def test_sam_records_from_the_device_equal_reference_binary(engine, gidx, small_cfg, reflib, tmp_path, name, extra):
+    """Output stage on the device (snapgpu_sam_format_single over the engine's own result records) vs the SAM file
+    `snap-aligner single ... -o out.sam -t 1` writes for the same reads: record for record, byte for byte."""
+    rb = small_cfg.reads[name]
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.sam")
+    rb.write_fastq(fq)
+    want = _reference_sam_lines(reflib, ["single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"] + extra)
+    p = engine.default_params(maxDist=14, useAffineGap=0 if "-G-" in extra else 1)
+    al = engine.SingleAligner(gidx, p, 4096)
+    res, _ = al.align(rb)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096, use_m=("-=" not in extra))
+    got = [l for l in fmt.format(rb, [b"r%d" % i for i in range(rb.n)], res).split(b"\n") if l]
+    fmt.close()
+    assert len(want) == len(got) == rb.n
+    bad = [i for i in range(rb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("clipped150", ["-="])])
+def test_sam_pair_records_from_the_device_equal_reference_binary(engine, gidx, small_cfg, reflib, tmp_path, name, extra):
+    """The same for pairs (snapgpu_sam_format_paired): write order, mate fields, template length, QS."""
+    pb = small_cfg.pairs[name]
+    f1 = str(tmp_path / "p1.fq"); f2 = str(tmp_path / "p2.fq"); out = str(tmp_path / "o.sam")
+    ids = []
+    with open(f1, "wb") as a, open(f2, "wb") as b:
+        for i in range(pb.n // 2):
+            x, q = pb.read(2 * i); a.write(b"@p%d/1\n%s\n+\n%s\n" % (i, x, q))
+            x, q = pb.read(2 * i + 1); b.write(b"@p%d/2\n%s\n+\n%s\n" % (i, x, q))
+            ids += [b"p%d/1" % i, b"p%d/2" % i]
+    want = _reference_sam_lines(reflib, ["paired", small_cfg.idx, f1, f2, "-o", out, "-t", "1"] + extra)
+    p, pp = engine.default_params(maxDist=27, numSeedsFromCommandLine=8), engine.default_paired_params()
+    al = engine.PairedAligner(gidx, p, pp, 2048)
+    res, _ = al.align(pb)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096, use_m=("-=" not in extra))
+    got = [l for l in fmt.format(pb, ids, res, paired=True).split(b"\n") if l]
+    fmt.close()
+    assert len(want) == len(got) == pb.n
+    bad = [i for i in range(pb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
