@@ -330,6 +330,7 @@ int  snapgpu_fastq_parse(snapgpu_fastq *f, const char *text, int64_t nBytes, int
  * reads / ids / results are HOST arrays in the layout of snapgpu_align_single / _paired (ids: concatenated, idOffsets / idLens per
  * read, at most 255 characters each); `text` receives the records back to back, *textBytes their total length.
  * `useM`: M instead of = / X operations (SNAP's default, -M).  Scoring parameters and useAffineGap are taken from `params`.
+ * First form: the reads are taken to be unclipped (no quality clipping in effect); one thread per read, not yet optimised.
  */
 typedef struct snapgpu_sam snapgpu_sam;
 int  snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, int32_t useM, int64_t maxBatchReads, snapgpu_sam **out);
