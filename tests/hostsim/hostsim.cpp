@@ -488,7 +488,7 @@ void hs_cigar_ag_batch(void *vix, const int *params, const char *dataBuf, const 
 // sg_sam.h: one SAM record per read from the result records, text appended to `out` (returns the bytes written, -1 if `outCap` is too small)
 int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAffineGap, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
                             const uint32_t *lens, const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results,
-                            const snapgpu_paired_result *pairedResults, char *out, int64_t outCap)
+                            const snapgpu_paired_result *pairedResults, const uint32_t *frontClipped, const uint32_t *clippedLens, char *out, int64_t outCap)
 {
     HsIndex *ix = (HsIndex *)vix;
     const int kmax = SG_MAX_K - 1;
@@ -542,7 +542,8 @@ int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAff
         if (scrub) memset(bt.data(), 0x2a + (int)(i % 7), bt.size());
         SgSamRead R;
         R.unclippedData = (const uint8_t *)bases + offsets[i]; R.unclippedQuality = (const uint8_t *)quals + offsets[i]; R.unclippedLength = lens[i];
-        R.frontClipped = 0; R.dataLength = lens[i]; R.id = (const uint8_t *)ids + idOffsets[i]; R.idLength = idLens[i];
+        R.frontClipped = frontClipped ? frontClipped[i] : 0; R.dataLength = clippedLens ? clippedLens[i] : lens[i];      // quality clipping (Read::clip)
+        R.id = (const uint8_t *)ids + idOffsets[i]; R.idLength = idLens[i];
         R.additionalFrontClipping = 0; R.additionalBackClipping = 0;
         const snapgpu_single_result &r = results[i];
         SgSamResult sr;

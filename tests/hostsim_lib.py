@@ -51,7 +51,7 @@ def lib():
         L.hs_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.hs_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.hs_sam_single_batch.restype = C.c_int64
-        L.hs_sam_single_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 10 + [C.c_int64]
+        L.hs_sam_single_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 12 + [C.c_int64]
         L.hs_aligner_create.restype = C.c_void_p
         L.hs_aligner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.hs_aligner_destroy.argtypes = [C.c_void_p]
@@ -178,7 +178,7 @@ def cigar_ag_batch(index, data, qual, jobs, params=(1, 4, 6, 1)):
     return out
 
 
-def sam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1), paired=False) -> bytes:
+def sam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1), paired=False, front_clipped=None, clipped_lens=None) -> bytes:
     """SAM records (text) of a batch from its result records; ids: list of bytes (one per read).  paired: results are pair records."""
     prm = np.ascontiguousarray(params, dtype=np.int32)
     id_buf = np.frombuffer(b"".join(ids), dtype=np.uint8).copy()
@@ -188,7 +188,9 @@ def sam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, para
     out = np.zeros(cap, dtype=np.uint8)
     res = np.ascontiguousarray(results)
     n = lib().hs_sam_single_batch(index.handle, _p(prm), 1 if use_m else 0, 1 if use_affine_gap else 0, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
-                                  _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), None if paired else _p(res), _p(res) if paired else None, _p(out), cap)
+                                  _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), None if paired else _p(res), _p(res) if paired else None,
+                                  None if front_clipped is None else _p(np.ascontiguousarray(front_clipped, dtype=np.uint32)),
+                                  None if clipped_lens is None else _p(np.ascontiguousarray(clipped_lens, dtype=np.uint32)), _p(out), cap)
     assert n >= 0
     return out[:n].tobytes()
 

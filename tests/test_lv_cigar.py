@@ -386,3 +386,40 @@ def test_sam_records_do_not_depend_on_call_history(reflib, small_cfg, tmp_path, 
     monkeypatch.setenv("HS_SAM_SCRUB", "1")
     test_sam_records_equal_reference_binary(reflib, small_cfg, tmp_path, "noisy150", [])
     test_sam_pair_records_equal_reference_binary(reflib, small_cfg, tmp_path, "noisy150", [])
+
+
+@pytest.mark.parametrize("clip", ["back", "both"])
+def test_sam_records_with_quality_clipping_equal_reference_binary(reflib, small_cfg, tmp_path, clip):
+    """Reads with '#' quality tails (and heads): the aligner sees the clipped view (Read::clip, default -C-+ = back only; -C++ = both
+    ends), the SAM record carries the whole read with S operations."""
+    import subprocess
+    from snap_b200 import synth
+    rng = np.random.default_rng(5)
+    rb = small_cfg.reads["noisy150"]
+    reads = []; fronts = []; clens = []
+    for i in range(600):
+        b, q = rb.read(i)
+        q = bytearray(q)
+        tail = int(rng.choice([0, 0, 3, 11, 40])); head = int(rng.choice([0, 0, 0, 5])) if clip == "both" else 0
+        if len(b) < 70:
+            tail = head = 0
+        for k in range(tail):
+            q[len(q) - 1 - k] = ord("#")
+        for k in range(head):
+            q[k] = ord("#")
+        reads.append((b, bytes(q))); fronts.append(head); clens.append(len(b) - head - tail)
+    full = synth.ReadBatch.from_lists(reads)
+    clipped = synth.ReadBatch.from_lists([(b[f:f + n], q[f:f + n]) for (b, q), f, n in zip(reads, fronts, clens)])
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.sam")
+    full.write_fastq(fq)
+    argv = [reflib.SNAP_ALIGNER, "single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"] + (["-C++"] if clip == "both" else [])
+    r = subprocess.run(argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    want = [l for l in open(out, "rb").read().split(b"\n") if l and not l.startswith(b"@")]
+    res, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params(maxDist=14)).align(clipped)
+    text = hs.sam_single(hs.HsIndex(small_cfg.idx), full, [b"r%d" % i for i in range(full.n)], res, front_clipped=fronts, clipped_lens=clens)
+    got = [l for l in text.split(b"\n") if l]
+    assert len(want) == len(got) == full.n
+    bad = [i for i in range(full.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+    assert sum(b"S" in l.split(b"\t")[5] for l in want) > 200
