@@ -2,7 +2,7 @@
 // (reference SNAPLib/AffineGapVectorized.cpp): computeGlobalScore (:159-518), computeGlobalScoreBanded (:520-943),
 // computeFinalCigarString (:945-1041) and the dispatch computeGlobalScoreNormalized (:1043-1128) -- what SAMFormat::computeCigar
 // (SAM.cpp:2470-2592) runs on every read that WAS rescored with affine gap.  Third piece of the output stage.
-// STATUS: verified on the host against the compiled reference (tests/test_lv_cigar.py); no device entry point yet, nothing in
+// STATUS: verified on the host against the compiled reference (tests/test_output_stage.py); no device entry point yet, nothing in
 // include/snapgpu.h refers to this file.
 //
 // Like the scoring kernels (sg_ag.h) this keeps the reference's striped coordinates -- cell (vector j, SSE lane l) holds pattern

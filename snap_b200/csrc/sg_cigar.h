@@ -1,7 +1,7 @@
 // sg_cigar.h -- CIGAR of one aligned read: SAMFormat::computeCigar inside SAMFormat::computeCigarString, as BAM operations.  sg_cigar_lv:
 // the LandauVishkinWithCigar overloads (reference SNAPLib/SAM.cpp:2354-2468, :2595-2671) for results that were not rescored with
 // affine gap; sg_cigar_ag: the AffineGapVectorizedWithCigar overloads (:2470-2592, :2677-2766) for those that were.  Second piece of the output stage; same status as sg_lv_cigar.h: verified on the host against
-// the compiled reference (tests/test_lv_cigar.py), no device entry point yet.
+// the compiled reference (tests/test_output_stage.py), no device entry point yet.
 //
 // What it adds to the LV routine: soft clipping of a read that hangs over the end of its contig (re-run until the clip and the
 // alignment's net indel agree), the front-clipping verdict that makes the caller move the alignment start and try again, the

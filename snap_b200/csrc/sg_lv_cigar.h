@@ -1,7 +1,7 @@
 // sg_lv_cigar.h -- Landau-Vishkin with CIGAR output: literal restatement of LandauVishkinWithCigar::computeEditDistance
 // (reference SNAPLib/LandauVishkin.cpp:141-505) and computeEditDistanceNormalized (:507-650), the routine SAMFormat::computeCigar
 // (SAM.cpp:2354-2468) runs for every aligned read that was NOT rescored with affine gap.  First piece of the output stage
-// (SURVEY 8f row N1).  STATUS: verified on the host against the compiled reference (tests/test_lv_cigar.py, incl. the 30 known
+// (SURVEY 8f row N1).  STATUS: verified on the host against the compiled reference (tests/test_output_stage.py, incl. the 30 known
 // answers of the reference's tests/LandauVishkinTest.cpp:34-129); no device entry point yet, nothing in include/snapgpu.h refers to it.
 //
 // Output is BAM cigar operations, (count << 4) | code with codes "MIDNSHP=X" (Bam.cpp:268) -- the form

@@ -1,7 +1,7 @@
 // sg_sam.h -- one SAM record of an unpaired read: SimpleReadWriter::writeReads' per-result loop (reference SNAPLib/ReadWriter.cpp:
 // 170-330) around SAMFormat::writeRead (SAM.cpp:1897-2112 for Landau-Vishkin results, :2113-2352 for affine-gap ones) and
 // SAMFormat::createSAMLine (:1423-1573).  Fourth piece of the output stage; same status as sg_cigar.h: verified on
-// the host (tests/test_lv_cigar.py: against the SAM file the reference binary writes for the same reads), no device entry point
+// the host (tests/test_output_stage.py: against the SAM file the reference binary writes for the same reads), no device entry point
 // yet, nothing in include/snapgpu.h refers to it.  Primary alignments only (no secondary results), default tags (PG, NM, the default
 // read group line, QS for pairs); sg_sam_write_pair adds SimpleReadWriter::writePairs (ReadWriter.cpp:362-560) around
 // SAMFormat::writePairs (SAM.cpp:1574-1896) and fillMateInfo (:1308-1422).
