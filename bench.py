@@ -336,6 +336,14 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             out["ingest_phase"] = {"error": str(e)[:200]}
 
+    # ---- output stage in isolation (rank 0, N=1; SURVEY 8f N1, first device form) ----
+    if rank == 0 and world == 1 and not args.no_seed_phase:
+        try:
+            got_s, _ = al.align(host_batches[0])
+            out["sam_phase"] = sam_phase(args, idx, host_batches[0], got_s, paired)
+        except Exception as e:  # pragma: no cover
+            out["sam_phase"] = {"error": str(e)[:300]}
+
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample (rank 0, N=1 only) ----
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -470,6 +478,86 @@ def ingest_phase(args, host_batch, device, peak, peak_src):
         out["cpu_reference_error"] = str(e)[:100]
     fq.close()
     return out
+
+
+def sam_phase(args, idx, host_batch, results, paired):
+    """Output stage, first device form: snapgpu_sam_format_single / _paired over a bounded sample of the step's reads
+    and the engine's own result records, through the host-buffer C ABI (copies and the host-side packing of the records inside the
+    timed region).  Beside it the reference's routine for the same job, SAMFormat::computeCigarString, on ONE host thread over a
+    smaller sample (oracle/_ref; the reference's writer is single-threaded per output buffer)."""
+    from snap_b200 import engine, synth
+    n = min(131072, host_batch.n)
+    n -= n % 2
+    sample = host_batch.slice(0, n)
+    res = np.ascontiguousarray(results[:n // 2] if paired else results[:n])
+    ids = [(b"p%d/%d" % (i // 2, 1 + i % 2)) if paired else (b"r%d" % i) for i in range(n)]
+    p = engine.default_params(**PAIRED_KW) if paired else engine.default_params(maxDist=MAX_DIST)
+    fmt = engine.SamFormatter(idx, p, n, use_m=True)
+    try:
+        id_buf, id_offs, id_lens = fmt.pack_ids(ids)
+        sb = synth.ReadBatch(np.ascontiguousarray(sample.bases), np.ascontiguousarray(sample.quals), np.ascontiguousarray(sample.offsets), np.ascontiguousarray(sample.lens))
+        buf, used = fmt.format_arrays(sb, id_buf, id_offs, id_lens, res, paired)          # warm-up (and the text buffer)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            buf, used = fmt.format_arrays(sb, id_buf, id_offs, id_lens, res, paired, text=buf)
+        dt = (time.perf_counter() - t0) / reps
+        text = buf[:used].tobytes()
+    finally:
+        fmt.close()
+    out = {"kernel": "sg_sam_kernel (one thread per read; first form, not optimised)", "reads": int(n), "ms": round(dt * 1e3, 3),
+           "reads_per_s": round(n / dt, 1), "text_bytes": len(text), "text_gbs": round(len(text) / dt / 1e9, 3),
+           "records_ok": text.count(b"\n") == n}
+    try:
+        out["cpu_reference_1thread_reads_per_s"] = sam_cpu_reference(idx, sample, res, paired)
+    except Exception as e:  # pragma: no cover
+        out["cpu_reference_error"] = str(e)[:200]
+    return out
+
+
+def sam_cpu_reference(idx, sample, res, paired, n_cpu=20000):
+    """reads/s of the reference's SAMFormat::computeCigarString (both overloads; the dominant cost of its writer) on one host thread."""
+    from oracle import reflib
+    from snap_b200 import synth
+    if not reflib.available():
+        return None
+    d = export_index_for_reference(idx)
+    try:
+        ridx = reflib.RefIndex(d)
+        m = min(n_cpu, sample.n)
+        data = []; qual = []; jl = []; ja = []; off = 0
+        for i in range(m):
+            if paired:
+                r = res[i // 2]; w = i % 2
+                status, loc, direction, used_ag, score, cb, ca = (int(r["status"][w]), int(r["location"][w]), int(r["direction"][w]), int(r["usedAffineGapScoring"][w]),
+                                                                   int(r["score"][w]), int(r["basesClippedBefore"][w]), int(r["basesClippedAfter"][w]))
+            else:
+                r = res[i]
+                status, loc, direction, used_ag, score, cb, ca = (int(r["status"]), int(r["location"]), int(r["direction"]), int(r["usedAffineGapScoring"]), int(r["score"]),
+                                                                   int(r["basesClippedBefore"]), int(r["basesClippedAfter"]))
+            if status == 0:
+                continue
+            b, q = sample.read(i)
+            x = np.frombuffer(b, dtype=np.uint8); y = np.frombuffer(q, dtype=np.uint8)
+            if direction == 1:
+                x = synth.revcomp(x); y = y[::-1]
+            data.append(x); data.append(np.zeros(16, dtype=np.uint8)); qual.append(y); qual.append(np.zeros(16, dtype=np.uint8))
+            if used_ag or score > 0:
+                ja.append((off + cb, loc, len(b) - cb - ca, cb, 0, ca, 0, 0, direction, 1, score, 0))
+            else:
+                jl.append((off, loc, len(b), 0, 0, 0, 0, 0, direction, 1))
+            off += len(b) + 16
+        data = np.concatenate(data); qual = np.concatenate(qual)
+        jl = np.array(jl, dtype=reflib.CIGAR_JOB_DTYPE); ja = np.array(ja, dtype=reflib.CIGAR_AG_JOB_DTYPE)
+        t0 = time.perf_counter()
+        if jl.size:
+            reflib.cigar_lv_batch(ridx, data, jl)
+        if ja.size:
+            reflib.cigar_ag_batch(ridx, data, qual, ja)
+        dt = time.perf_counter() - t0
+        return round((jl.size + ja.size) / dt, 1)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def export_index_for_reference(idx):

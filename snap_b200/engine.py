@@ -328,20 +328,31 @@ class SamFormatter:
         self.handle = h
         self.max_batch_reads = max_batch_reads
 
-    def format(self, batch, ids, results, paired: bool = False) -> bytes:
-        """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one
-        per pair with paired=True)."""
+    @staticmethod
+    def pack_ids(ids):
+        """ids (one bytes object per read) -> (concatenated uint8 array, offsets, lengths) as the C ABI takes them."""
         id_buf = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
         id_lens = np.array([len(x) for x in ids], dtype=np.uint32)
         id_offs = np.concatenate([[0], np.cumsum(id_lens[:-1], dtype=np.uint64)]).astype(np.uint64)
-        cap = int(batch.n) * (2 * int(batch.lens.max()) + 1024) + 4096
-        text = np.zeros(cap, dtype=np.uint8)
+        return id_buf, id_offs, id_lens
+
+    def format_arrays(self, batch, id_buf, id_offs, id_lens, results, paired: bool = False, text=None):
+        """The C ABI call itself (snapgpu_sam_format_single / _paired); returns (text buffer, bytes used)."""
+        if text is None:
+            text = np.zeros(int(batch.n) * (2 * int(batch.lens.max()) + 1024) + 4096, dtype=np.uint8)
         used = C.c_int64(0)
-        res = np.ascontiguousarray(results)
         fn = lib().snapgpu_sam_format_paired if paired else lib().snapgpu_sam_format_single
-        _check(fn(self.handle, batch.n, _p(np.ascontiguousarray(batch.bases)), _p(np.ascontiguousarray(batch.quals)), _p(np.ascontiguousarray(batch.offsets)),
-                  _p(np.ascontiguousarray(batch.lens)), _p(id_buf), _p(id_offs), _p(id_lens), _p(res), _p(text), cap, C.byref(used)))
-        return text[:used.value].tobytes()
+        _check(fn(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), _p(results),
+                  _p(text), text.size, C.byref(used)))
+        return text, used.value
+
+    def format(self, batch, ids, results, paired: bool = False) -> bytes:
+        """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one
+        per pair with paired=True)."""
+        id_buf, id_offs, id_lens = self.pack_ids(ids)
+        b = type(batch)(np.ascontiguousarray(batch.bases), np.ascontiguousarray(batch.quals), np.ascontiguousarray(batch.offsets), np.ascontiguousarray(batch.lens))
+        text, used = self.format_arrays(b, id_buf, id_offs, id_lens, np.ascontiguousarray(results), paired)
+        return text[:used].tobytes()
 
     def close(self):
         if self.handle:
