@@ -17,6 +17,7 @@
 #include "../../snap_b200/csrc/sg_cigar.h"
 #include "../../snap_b200/csrc/sg_ag_cigar.h"
 #include "../../snap_b200/csrc/sg_sam.h"
+#include "../../snap_b200/csrc/sg_bam.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -551,6 +552,50 @@ int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAff
         sr.scorePriorToClipping = r.scorePriorToClipping; sr.usedAffineGapScoring = r.usedAffineGapScoring; sr.basesClippedBefore = r.basesClippedBefore;
         sr.basesClippedAfter = r.basesClippedAfter; sr.clippingForReadAdjustment = r.clippingForReadAdjustment;
         used += sg_sam_write_single(C, R, sr, out + used);
+    }
+    return used;
+}
+
+// sg_bam.h: one BAM record per read (unpaired), appended to `out`
+int64_t hs_bam_single_batch(void *vix, const int *agParams, int useM, int useAffineGap, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
+                            const uint32_t *lens, const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results,
+                            char *out, int64_t outCap)
+{
+    HsIndex *ix = (HsIndex *)vix;
+    const int kmax = SG_MAX_K - 1;
+    std::vector<int> L(sg_lv_cigar_scratch_ints(kmax)), TI(sg_lv_cigar_scratch_ints(kmax)), btM(kmax + 2), btD(kmax + 2);
+    std::vector<uint8_t> A(sg_lv_cigar_scratch_ints(kmax)), btA(kmax + 2);
+    const int numVecMax = (1000 + 7) / 8 + 16, rowsMax = 1000 + SG_MAX_K + 8, resMax = 2 * rowsMax;
+    std::vector<int16_t> H(numVecMax * 8), Hm1(numVecMax * 8), E(numVecMax * 8), prof(5 * numVecMax * 8);
+    std::vector<uint8_t> bt((size_t)rowsMax * numVecMax * 8), ra(resMax), data(1024), quality(1024), data2(1024), quality2(1024);
+    std::vector<int> rc(resMax);
+    std::vector<const char *> names;
+    for (size_t c = 0; c < ix->host.contigName.size(); c++) names.push_back(ix->host.contigName[c].c_str());
+    SgSamContext C;
+    C.ix = &ix->view; C.contigName = names.data();
+    C.ag = sg_ag_params(agParams[0], agParams[1], agParams[2], agParams[3], 0, 0);
+    C.readGroupAux = "";
+    C.useM = useM != 0; C.useAffineGap = useAffineGap != 0;
+    C.lv.L = L.data(); C.lv.totalIndels = TI.data(); C.lv.A = A.data(); C.lv.btAction = btA.data(); C.lv.btMatched = btM.data(); C.lv.btD = btD.data(); C.lv.kmax = kmax;
+    C.agS.H = H.data(); C.agS.Hm1 = Hm1.data(); C.agS.E = E.data(); C.agS.prof = prof.data(); C.agS.bt = bt.data(); C.agS.resAction = ra.data(); C.agS.resCount = rc.data();
+    C.agS.numVecMax = numVecMax; C.agS.rowsMax = rowsMax; C.agS.resMax = resMax;
+    C.data = data.data(); C.quality = quality.data(); C.data2 = data2.data(); C.quality2 = quality2.data();
+    static const char rg[] = "RGZFASTQ\0PLZIllumina\0PUZpu\0LBZlb\0SMZsm";       // + the terminating NUL of the literal = the last tag's
+    SgBamContext B;
+    B.readGroupAux = (const uint8_t *)rg; B.readGroupAuxLen = (int)sizeof(rg);
+    int64_t used = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (lens[i] > 1000 || used + 4096 > outCap) return -1;
+        SgSamRead R;
+        R.unclippedData = (const uint8_t *)bases + offsets[i]; R.unclippedQuality = (const uint8_t *)quals + offsets[i]; R.unclippedLength = lens[i];
+        R.frontClipped = 0; R.dataLength = lens[i]; R.id = (const uint8_t *)ids + idOffsets[i]; R.idLength = idLens[i];
+        R.additionalFrontClipping = 0; R.additionalBackClipping = 0;
+        const snapgpu_single_result &r = results[i];
+        SgSamResult sr;
+        sr.status = r.status; sr.location = r.location; sr.direction = r.direction; sr.mapq = r.mapq; sr.score = r.score;
+        sr.scorePriorToClipping = r.scorePriorToClipping; sr.usedAffineGapScoring = r.usedAffineGapScoring; sr.basesClippedBefore = r.basesClippedBefore;
+        sr.basesClippedAfter = r.basesClippedAfter; sr.clippingForReadAdjustment = r.clippingForReadAdjustment;
+        used += sg_bam_write_single(C, B, R, sr, (uint8_t *)out + used);
     }
     return used;
 }

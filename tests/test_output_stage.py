@@ -423,3 +423,43 @@ def test_sam_records_with_quality_clipping_equal_reference_binary(reflib, small_
     bad = [i for i in range(full.n) if want[i] != got[i]]
     assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
     assert sum(b"S" in l.split(b"\t")[5] for l in want) > 200
+
+
+def _bam_records(path):
+    """The alignment records of a BAM file (BGZF blocks inflated, header and reference table skipped), as a list of bytes."""
+    import gzip, struct
+    raw = gzip.open(path, "rb").read()
+    assert raw[:4] == b"BAM\x01"
+    p = 8 + struct.unpack("<i", raw[4:8])[0]
+    n_ref = struct.unpack("<i", raw[p:p + 4])[0]; p += 4
+    for _ in range(n_ref):
+        l = struct.unpack("<i", raw[p:p + 4])[0]; p += 8 + l
+    recs = []
+    while p < len(raw):
+        b = struct.unpack("<i", raw[p:p + 4])[0]
+        recs.append(raw[p:p + 4 + b]); p += 4 + b
+    return recs
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("indel100", ["-="]), ("noisy150", ["-G-"])])
+def test_bam_records_equal_reference_binary(reflib, small_cfg, tmp_path, name, extra):
+    """`snap-aligner single ... -o out.bam -t 1` vs sg_bam.h over the result records of the same reads: every record, byte for
+    byte (fixed fields, bin, CIGAR words, 4-bit sequence, qualities, the binary tags)."""
+    import subprocess
+    rb = small_cfg.reads[name]
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.bam")
+    rb.write_fastq(fq)
+    r = subprocess.run([reflib.SNAP_ALIGNER, "single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"] + extra, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    want = _bam_records(out)
+    use_ag = "-G-" not in extra
+    res, _ = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params(maxDist=14, useAffineGap=1 if use_ag else 0)).align(rb)
+    blob = hs.bam_single(hs.HsIndex(small_cfg.idx), rb, [b"r%d" % i for i in range(rb.n)], res, use_m=("-=" not in extra), use_affine_gap=use_ag)
+    import struct
+    got = []; p = 0
+    while p < len(blob):
+        b = struct.unpack("<i", blob[p:p + 4])[0]
+        got.append(blob[p:p + 4 + b]); p += 4 + b
+    assert len(want) == len(got) == rb.n
+    bad = [i for i in range(rb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
