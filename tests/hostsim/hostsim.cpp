@@ -559,7 +559,7 @@ int64_t hs_sam_single_batch(void *vix, const int *agParams, int useM, int useAff
 // sg_bam.h: one BAM record per read (unpaired), appended to `out`
 int64_t hs_bam_single_batch(void *vix, const int *agParams, int useM, int useAffineGap, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,
                             const uint32_t *lens, const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results,
-                            char *out, int64_t outCap)
+                            const snapgpu_paired_result *pairedResults, char *out, int64_t outCap)
 {
     HsIndex *ix = (HsIndex *)vix;
     const int kmax = SG_MAX_K - 1;
@@ -584,6 +584,28 @@ int64_t hs_bam_single_batch(void *vix, const int *agParams, int useM, int useAff
     SgBamContext B;
     B.readGroupAux = (const uint8_t *)rg; B.readGroupAuxLen = (int)sizeof(rg);
     int64_t used = 0;
+    if (pairedResults != NULL) {
+        for (int64_t i = 0; i < n / 2; i++) {
+            if (lens[2 * i] > 1000 || lens[2 * i + 1] > 1000 || used + 8192 > outCap) return -1;
+            SgSamRead R[2];
+            for (int w = 0; w < 2; w++) {
+                const int64_t k = 2 * i + w;
+                R[w].unclippedData = (const uint8_t *)bases + offsets[k]; R[w].unclippedQuality = (const uint8_t *)quals + offsets[k]; R[w].unclippedLength = lens[k];
+                R[w].frontClipped = 0; R[w].dataLength = lens[k]; R[w].id = (const uint8_t *)ids + idOffsets[k]; R[w].idLength = idLens[k];
+                R[w].additionalFrontClipping = 0; R[w].additionalBackClipping = 0;
+            }
+            const snapgpu_paired_result &r = pairedResults[i];
+            SgSamPairResult pr;
+            for (int w = 0; w < 2; w++) {
+                pr.status[w] = r.status[w]; pr.location[w] = r.location[w]; pr.direction[w] = r.direction[w]; pr.mapq[w] = r.mapq[w]; pr.score[w] = r.score[w];
+                pr.usedAffineGapScoring[w] = r.usedAffineGapScoring[w]; pr.basesClippedBefore[w] = r.basesClippedBefore[w]; pr.basesClippedAfter[w] = r.basesClippedAfter[w];
+                pr.clippingForReadAdjustment[w] = r.clippingForReadAdjustment[w];
+            }
+            pr.alignedAsPair = r.alignedAsPair;
+            used += sg_bam_write_pair(C, B, R[0], R[1], pr, out + used);
+        }
+        return used;
+    }
     for (int64_t i = 0; i < n; i++) {
         if (lens[i] > 1000 || used + 4096 > outCap) return -1;
         SgSamRead R;

@@ -51,7 +51,7 @@ def lib():
         L.hs_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.hs_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.hs_bam_single_batch.restype = C.c_int64
-        L.hs_bam_single_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64]
+        L.hs_bam_single_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 10 + [C.c_int64]
         L.hs_sam_single_batch.restype = C.c_int64
         L.hs_sam_single_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 12 + [C.c_int64]
         L.hs_aligner_create.restype = C.c_void_p
@@ -197,7 +197,7 @@ def sam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, para
     return out[:n].tobytes()
 
 
-def bam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1)) -> bytes:
+def bam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1), paired=False) -> bytes:
     """BAM records (binary, back to back, no header) of an unpaired batch from its result records."""
     prm = np.ascontiguousarray(params, dtype=np.int32)
     id_buf = np.frombuffer(b"".join(ids), dtype=np.uint8).copy()
@@ -207,7 +207,7 @@ def bam_single(index, batch, ids, results, use_m=True, use_affine_gap=True, para
     out = np.zeros(cap, dtype=np.uint8)
     res = np.ascontiguousarray(results)
     n = lib().hs_bam_single_batch(index.handle, _p(prm), 1 if use_m else 0, 1 if use_affine_gap else 0, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
-                                  _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), _p(res), _p(out), cap)
+                                  _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), None if paired else _p(res), _p(res) if paired else None, _p(out), cap)
     assert n >= 0
     return out[:n].tobytes()
 

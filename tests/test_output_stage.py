@@ -463,3 +463,31 @@ def test_bam_records_equal_reference_binary(reflib, small_cfg, tmp_path, name, e
     assert len(want) == len(got) == rb.n
     bad = [i for i in range(rb.n) if want[i] != got[i]]
     assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("clipped150", ["-="]), ("std150", [])])
+def test_bam_pair_records_equal_reference_binary(reflib, small_cfg, tmp_path, name, extra):
+    """`snap-aligner paired ... -o out.bam -t 1` vs sg_bam_write_pair: both records of every pair, byte for byte (mate fields, bin of an
+    unmapped end at its mate's position, template length, QS)."""
+    import subprocess, struct
+    pb = small_cfg.pairs[name]
+    f1 = str(tmp_path / "p1.fq"); f2 = str(tmp_path / "p2.fq"); out = str(tmp_path / "o.bam")
+    ids = []
+    with open(f1, "wb") as a, open(f2, "wb") as b:
+        for i in range(pb.n // 2):
+            x, q = pb.read(2 * i); a.write(b"@p%d/1\n%s\n+\n%s\n" % (i, x, q))
+            x, q = pb.read(2 * i + 1); b.write(b"@p%d/2\n%s\n+\n%s\n" % (i, x, q))
+            ids += [b"p%d/1" % i, b"p%d/2" % i]
+    r = subprocess.run([reflib.SNAP_ALIGNER, "paired", small_cfg.idx, f1, f2, "-o", out, "-t", "1"] + extra, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    want = _bam_records(out)
+    kw, pkw = PAIRED_DEFAULT
+    res, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)).align(pb)
+    blob = hs.bam_single(hs.HsIndex(small_cfg.idx), pb, ids, res, use_m=("-=" not in extra), paired=True)
+    got = []; p = 0
+    while p < len(blob):
+        b = struct.unpack("<i", blob[p:p + 4])[0]
+        got.append(blob[p:p + 4 + b]); p += 4 + b
+    assert len(want) == len(got) == pb.n
+    bad = [i for i in range(pb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
