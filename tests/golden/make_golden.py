@@ -9,6 +9,8 @@
 2. e2e_small.npz -- a seeded synthetic genome + reads and the reference's SingleAlignmentResult for each read under
    three option sets, produced by the compiled reference (oracle/_ref/libsnapref.so).
 3. leaf_lv.npz / leaf_ag.npz -- random LV / affine-gap jobs (tests/jobs.py) with the reference's outputs.
+4. output_small.json.gz (`make_golden.py output`) -- the reference unit test's 30 CIGAR known answers and the SAM / BAM records the
+   reference binary writes for the reads of e2e_small.npz.
 The GPU box has no /root/reference; the `-m gpu` tests compare the CUDA path against these files (and, when the
 prebuilt oracle/_ref travelled along, against it directly).
 """
@@ -97,8 +99,53 @@ def fastq_small():
     return out
 
 
+def output_small():
+    """Output stage: (1) the CIGAR known answers of the reference's own unit test (tests/LandauVishkinTest.cpp:34-129), parsed
+    out of its source; (2) for the reads of e2e_small.npz, the alignment records of the SAM and BAM files the reference BINARY writes
+    (`snap-aligner single <idx> r.fq -o out.sam|out.bam -t 1 -d 14`; BAM records as hex, BGZF inflated)."""
+    import gzip, struct, subprocess, tempfile
+    src = open(os.path.join(REF, "tests", "LandauVishkinTest.cpp")).read()
+    vec = []
+    for m in re.finditer(r'lvc\.computeEditDistance\("([^"]*)", (\d+), "([^"]*)", (\d+), (\d+), cigarBuf, bufLen, (true|false)\);\s*ASSERT_STREQ\("([^"]*)", cigarBuf\);', src):
+        vec.append(dict(text=m.group(1), textLen=int(m.group(2)), pattern=m.group(3), patternLen=int(m.group(4)), k=int(m.group(5)), useM=m.group(6) == "true",
+                        cigar=m.group(7)))
+    assert len(vec) == 30, len(vec)
+    g = np.load(os.path.join(HERE, "e2e_small.npz"))
+    reads = synth.ReadBatch(g["bases"], g["quals"], g["offsets"], g["lens"])
+    out = {"source": "amplab/snap tests/LandauVishkinTest.cpp:34-129; snap-aligner single -d 14 -t 1 over the reads of e2e_small.npz", "lv_cigar": vec}
+    with tempfile.TemporaryDirectory() as tmp:
+        fa = os.path.join(tmp, "ref.fa"); synth.write_fasta(fa, [g["contig0"], g["contig1"]])
+        idx = os.path.join(tmp, "idx"); synth.build_reference_index(reflib.SNAP_ALIGNER, fa, idx)
+        fq = os.path.join(tmp, "r.fq"); reads.write_fastq(fq)
+        for ext in ("sam", "bam"):
+            o = os.path.join(tmp, "o." + ext)
+            r = subprocess.run([reflib.SNAP_ALIGNER, "single", idx, fq, "-o", o, "-t", "1", "-d", "14"], capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
+            if ext == "sam":
+                out["sam"] = [l for l in open(o).read().split("\n") if l and not l.startswith("@")]
+            else:
+                raw = gzip.open(o, "rb").read()
+                p = 8 + struct.unpack("<i", raw[4:8])[0]
+                n_ref = struct.unpack("<i", raw[p:p + 4])[0]; p += 4
+                for _ in range(n_ref):
+                    p += 8 + struct.unpack("<i", raw[p:p + 4])[0]
+                recs = []
+                while p < len(raw):
+                    b = struct.unpack("<i", raw[p:p + 4])[0]
+                    recs.append(raw[p:p + 4 + b].hex()); p += 4 + b
+                out["bam"] = recs
+    assert len(out["sam"]) == len(out["bam"]) == reads.n
+    return out
+
+
 def main():
     import tempfile
+    if len(sys.argv) > 1 and sys.argv[1] == "output":          # only the output-stage fixture (the others are left as committed)
+        import gzip
+        with gzip.open(os.path.join(HERE, "output_small.json.gz"), "wt") as f:
+            json.dump(output_small(), f)
+        print("output_small.json.gz %d bytes" % os.path.getsize(os.path.join(HERE, "output_small.json.gz")))
+        return
     with open(os.path.join(HERE, "ref_unit_vectors.json"), "w") as f:
         json.dump(unit_vectors(), f, indent=1)
     with tempfile.TemporaryDirectory() as tmp:

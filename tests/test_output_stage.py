@@ -13,48 +13,56 @@ import hostsim_lib as hs
 PAIRED_DEFAULT = (dict(maxDist=27), dict())
 PAIRED_HC = (dict(maxDist=27, fivePrimeEndBonus=5, threePrimeEndBonus=5), dict(useSoftClipping=0, minAGScoreImprovement=15))
 
-# (text, pattern, k, cigar with =/X, cigar with M) -- reference tests/LandauVishkinTest.cpp:38-128
-KNOWN = [
-    ("abcde", "abcde", 2, "5=", "5M"),
-    ("abcdef", "abcde", 2, "5=", "5M"),
-    ("abcde", "abcdX", 2, "4=1X", "5M"),
-    ("abcde", "Xbcde", 2, "1X4=", "5M"),
-    ("abcde", "abde", 2, "2=1D2=", "2M1D2M"),
-    ("abcde", "bcde", 2, "1D4=", "1D4M"),
-    ("abcde", "abcXde", 2, "3=1I2=", "3M1I2M"),
-    ("abcde", "abXXe", 2, "2=2X1=", "5M"),
-    ("abcde", "abcXXde", 3, "3=2I2=", "3M2I2M"),
-    ("ttttc", "tttc", 3, "3=1X", "4M"),
-    ("tttcc", "ttttc", 3, "3=1X1=", "5M"),
-    ("tttcc", "tttaa", 3, "3=2X", "5M"),
-    ("atctcag", "acttcag", 3, "1=2X4=", "7M"),
-    ("abc", "abcde", 3, "3=2X", "5M"),
-    ("abc", "abXde", 3, "2=3X", "5M"),
-]
+def _fixture(golden_dir):
+    import gzip, json, os
+    return json.load(gzip.open(os.path.join(golden_dir, "output_small.json.gz"), "rt"))
 
 
-def _known_jobs(reflib):
+def _known_jobs(reflib, known):
     # C string literals: NUL after the last character, as in the reference's test (the routine looks one character past the ends)
     text = bytearray(); pat = bytearray(); jobs = []
-    for t, p, k, _, _ in KNOWN:
-        for use_m in (0, 1):
-            jobs.append((len(text), len(pat), len(t), len(p), k, use_m))
-        text += t.encode() + b"\0" * 16
-        pat += p.encode() + b"\0" * 16
+    for v in known:
+        jobs.append((len(text), len(pat), v["textLen"], v["patternLen"], v["k"], 1 if v["useM"] else 0))
+        text += v["text"].encode() + b"\0" * 16
+        pat += v["pattern"].encode() + b"\0" * 16
     return (np.frombuffer(bytes(text), dtype=np.uint8).copy(), np.frombuffer(bytes(pat), dtype=np.uint8).copy(),
             np.array(jobs, dtype=reflib.LVC_JOB_DTYPE))
 
 
 @pytest.mark.parametrize("impl", ["reference", "restatement"])
-def test_known_cigars(reflib, impl):
-    text, pat, jobs = _known_jobs(reflib)
+def test_known_cigars(reflib, golden_dir, impl):
+    """The 30 CIGAR known answers of the reference's own unit test (tests/golden/output_small.json.gz, parsed out of
+    tests/LandauVishkinTest.cpp:34-129 by make_golden.py) through the compiled reference and through the restatement."""
+    known = _fixture(golden_dir)["lv_cigar"]
+    assert len(known) == 30
+    text, pat, jobs = _known_jobs(reflib, known)
     out = reflib.lv_cigar_batch(text, pat, jobs) if impl == "reference" else hs.lv_cigar_batch(text, pat, jobs, reflib.LVC_OUT_DTYPE)
-    i = 0
-    for t, p, k, eqx, m in KNOWN:
-        for want in (eqx, m):
-            assert out[i]["score"] >= 0, (t, p)
-            assert reflib.decode_cigar(out[i]["ops"], int(out[i]["nOps"])) == want, (t, p, want)
-            i += 1
+    for i, v in enumerate(known):
+        assert out[i]["score"] >= 0, v
+        assert reflib.decode_cigar(out[i]["ops"], int(out[i]["nOps"])) == v["cigar"], v
+
+
+def test_committed_sam_and_bam_records(reflib, golden_dir, tmp_path):
+    """Committed fixture: the SAM and BAM records the reference binary wrote for the reads of e2e_small.npz (made by
+    tests/golden/make_golden.py output) vs sg_sam.h / sg_bam.h over that fixture's committed result records."""
+    import os, struct
+    from snap_b200 import synth
+    fx = _fixture(golden_dir)
+    g = np.load(os.path.join(golden_dir, "e2e_small.npz"))
+    synth.write_fasta(str(tmp_path / "ref.fa"), [g["contig0"], g["contig1"]])
+    synth.build_reference_index(reflib.SNAP_ALIGNER, str(tmp_path / "ref.fa"), str(tmp_path / "idx"))
+    reads = synth.ReadBatch(g["bases"], g["quals"], g["offsets"], g["lens"])
+    hidx = hs.HsIndex(str(tmp_path / "idx"))
+    ids = [b"r%d" % i for i in range(reads.n)]
+    res = g["res_default_d14"]
+    got = [l for l in hs.sam_single(hidx, reads, ids, res).decode().split("\n") if l]
+    assert got == fx["sam"]
+    blob = hs.bam_single(hidx, reads, ids, res)
+    recs = []; p = 0
+    while p < len(blob):
+        b = struct.unpack("<i", blob[p:p + 4])[0]
+        recs.append(blob[p:p + 4 + b].hex()); p += 4 + b
+    assert recs == fx["bam"]
 
 
 def _fuzz_jobs(reflib, n, seed):
