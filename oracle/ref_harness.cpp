@@ -33,6 +33,7 @@
 #include "Tables.h"
 #include "FASTQ.h"
 #include "DataReader.h"
+#include "DataWriter.h"
 #include "Bam.h"
 
 #include <pthread.h>
@@ -314,6 +315,63 @@ void ref_cigar_ag_batch(void *vidx, const int *params, const char *dataBuf, cons
         else { o->kind = 2; o->refSpan = refSpan; strncpy(o->cigar, c, sizeof(o->cigar) - 1); }
     }
     delete[] cigarBuf; delete[] withClipping;
+}
+
+/*
+ * SimpleReadWriter::writeReads (ReadWriter.cpp:170-360) into memory: the oracle for sg_sam_write_single's retry loop (the loop that
+ * applies the CIGAR routines' front-clipping verdicts), which real alignments hardly ever enter.  The DataWriter below hands out one
+ * big buffer; the ReadWriter comes from the reference's own factory with the SAM format object.
+ */
+class RefMemWriter : public DataWriter {
+public:
+    RefMemWriter(char *b, size_t c) : DataWriter(NULL), buf(b), cap(c), used(0) {}
+    virtual bool getBuffer(char **o_buffer, size_t *o_size) { *o_buffer = buf + used; *o_size = cap - used; return true; }
+    virtual void advance(_int64 bytes, GenomeLocation location = 0) { used += (size_t)bytes; }
+    virtual bool getBatch(int relative, char **o_buffer, size_t *o_size = NULL, size_t *o_used = NULL, size_t *o_offset = NULL, size_t *o_logicalUsed = 0,
+                          size_t *o_logicalOffset = NULL) { return false; }
+    virtual bool nextBatch(bool lastBatch = false) { return true; }
+    virtual void close() {}
+    char *buf; size_t cap, used;
+};
+class RefMemSupplier : public DataWriterSupplier {
+public:
+    RefMemSupplier(RefMemWriter *i_w) : w(i_w) {}
+    virtual DataWriter *getWriter() { return w; }
+    virtual void close() {}
+    RefMemWriter *w;
+};
+
+_int64 ref_write_reads_batch(void *vidx, const int *agParams, int useM, int useAffineGap, _int64 n, const char *bases, const char *quals, const _uint64 *offsets,
+                             const unsigned *lens, const char *ids, const _uint64 *idOffsets, const unsigned *idLens, const snapgpu_single_result *results,
+                             char *out, _int64 outCap)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    RefMemWriter *mw = new RefMemWriter(out, (size_t)outCap);
+    RefMemSupplier *ms = new RefMemSupplier(mw);
+    ReadWriterSupplier *rws = ReadWriterSupplier::create(FileFormat::SAM[useM ? 1 : 0], ms, index->getGenome(), false, false, (char *)"", false,
+                                                        agParams[0], agParams[1], agParams[2], agParams[3], false);
+    ReadWriter *rw = rws->getWriter();
+    ReaderContext ctx;
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.genome = index->getGenome();
+    ctx.defaultReadGroup = "FASTQ";
+    static const char rg[] = "\tRG:Z:FASTQ\tPL:Z:Illumina\tPU:Z:pu\tLB:Z:lb\tSM:Z:sm";
+    ctx.defaultReadGroupAux = rg; ctx.defaultReadGroupAuxLen = (int)strlen(rg);
+    ctx.headerMatchesIndex = false;
+    for (_int64 i = 0; i < n; i++) {
+        Read read;
+        read.init(ids + idOffsets[i], idLens[i], bases + offsets[i], quals + offsets[i], lens[i], NULL, 0);
+        read.setReadGroup(ctx.defaultReadGroup);
+        const snapgpu_single_result &r = results[i];
+        SingleAlignmentResult sr;
+        memset(&sr, 0, sizeof(sr));
+        sr.status = (AlignmentResult)r.status; sr.location = r.status == 0 ? InvalidGenomeLocation : GenomeLocation(r.location); sr.origLocation = sr.location;
+        sr.direction = r.direction ? RC : FORWARD; sr.score = r.score; sr.scorePriorToClipping = r.scorePriorToClipping; sr.mapq = r.mapq;
+        sr.clippingForReadAdjustment = r.clippingForReadAdjustment; sr.usedAffineGapScoring = r.usedAffineGapScoring != 0;
+        sr.basesClippedBefore = r.basesClippedBefore; sr.basesClippedAfter = r.basesClippedAfter; sr.agScore = r.agScore; sr.supplementary = false;
+        if (!rw->writeReads(ctx, &read, &sr, 1, true, useAffineGap != 0)) return -1;
+    }
+    return (_int64)mw->used;
 }
 
 /*

@@ -122,6 +122,8 @@ def lib():
         L.ref_ag_cigar_global_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+        L.ref_write_reads_batch.restype = C.c_int64
+        L.ref_write_reads_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64]
         L.ref_decode_cigar.restype = C.c_int
         L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -350,6 +352,21 @@ def cigar_ag_batch(index, data: np.ndarray, qual: np.ndarray, jobs: np.ndarray, 
     prm = np.ascontiguousarray(params, dtype=np.int32)
     lib().ref_cigar_ag_batch(index.handle, _p(prm), _p(data), _p(qual), _p(np.ascontiguousarray(jobs, dtype=CIGAR_AG_JOB_DTYPE)), jobs.size, _p(out))
     return out
+
+
+def write_reads(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1)) -> bytes:
+    """SimpleReadWriter::writeReads (SAM) for every read of the batch with the given result records; returns the text."""
+    prm = np.ascontiguousarray(params, dtype=np.int32)
+    id_buf = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
+    id_lens = np.array([len(x) for x in ids], dtype=np.uint32)
+    id_offs = np.concatenate([[0], np.cumsum(id_lens[:-1], dtype=np.uint64)]).astype(np.uint64)
+    cap = int(batch.n) * 4096 + 8192
+    out = np.zeros(cap, dtype=np.uint8)
+    res = np.ascontiguousarray(results)
+    n = lib().ref_write_reads_batch(index.handle, _p(prm), 1 if use_m else 0, 1 if use_affine_gap else 0, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
+                                    _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), _p(res), _p(out), cap)
+    assert n >= 0
+    return out[:n].tobytes()
 
 
 def ag_batch(text: np.ndarray, pat: np.ndarray, qual: np.ndarray, jobs: np.ndarray, params=AG_PARAMS_DEFAULT) -> np.ndarray:

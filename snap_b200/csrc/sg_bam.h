@@ -47,16 +47,16 @@ SG_HDN int sg_bam_format(const SgSamContext &C, const SgBamContext &B, const SgS
     const int64_t loc = status == SNAPGPU_NOT_FOUND ? SG_SAM_INVALID_LOCATION : genomeLocation;
     sg_sam_create_line(ix, R, status, loc, direction, mapQuality, bpClippedBefore, bpClippedAfter, C.data, C.quality, &line);
     const bool mapped = loc != SG_SAM_INVALID_LOCATION;
-    uint32_t ops[48];
+    uint32_t ops[SG_SAM_MAX_OPS];
     SgCigarOut co;
     co.kind = 1; co.editDistance = -1; co.nOps = 0;
     int editDistance = -1;
     if (affineGap && line.extraBasesClippedBefore != 0) { *addFrontClipping = (int)line.extraBasesClippedBefore; return 0; }       // (:1892-1895)
     if (mapped) {
         if (affineGap) sg_cigar_ag(ix, C.ag, C.agS, line.clippedData, line.clippedQuality, line.clippedLength, score, line.basesClippedBefore, line.extraBasesClippedBefore,
-                                   line.basesClippedAfter, 0, 0, loc, C.useM, ops, 48, &co);
+                                   line.basesClippedAfter, 0, 0, loc, C.useM, ops, SG_SAM_MAX_OPS, &co);
         else sg_cigar_lv(ix, C.lv, line.clippedData, line.clippedLength, line.basesClippedBefore, line.extraBasesClippedBefore, line.basesClippedAfter, 0, 0, loc, C.useM,
-                         ops, 48, &co);
+                         ops, SG_SAM_MAX_OPS, &co);
         editDistance = co.editDistance;
         if (co.addFrontClipping != 0) { *addFrontClipping = co.addFrontClipping; return 0; }
     }
@@ -167,7 +167,7 @@ SG_HDN int sg_bam_write_pair(const SgSamContext &C, const SgBamContext &B, SgSam
         if (locations[0] <= locations[1]) { writeOrder[0] = 0; writeOrder[1] = 1; } else { writeOrder[0] = 1; writeOrder[1] = 0; }
         // ---- SAMFormat::writePairs (:1628-1716): line fields and CIGAR of each read, in write order ----
         SgSamLine line[2];
-        uint32_t ops[2][48];
+        uint32_t ops[2][SG_SAM_MAX_OPS];
         SgCigarOut co[2];
         int editDistance[2] = {-1, -1}, refSpan[2] = {0, 0};
         for (int fs = 0; fs < 2; fs++) {
@@ -181,9 +181,9 @@ SG_HDN int sg_bam_write_pair(const SgSamContext &C, const SgBamContext &B, SgSam
                 if (locations[w] != SG_SAM_INVALID_LOCATION) {
                     const bool ag = C.useAffineGap && (res.usedAffineGapScoring[w] || res.score[w] > 0);
                     if (ag) sg_cigar_ag(ix, C.ag, C.agS, line[w].clippedData, line[w].clippedQuality, line[w].clippedLength, res.score[w], line[w].basesClippedBefore,
-                                        line[w].extraBasesClippedBefore, line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], 48, &co[w]);
+                                        line[w].extraBasesClippedBefore, line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], SG_SAM_MAX_OPS, &co[w]);
                     else sg_cigar_lv(ix, C.lv, line[w].clippedData, line[w].clippedLength, line[w].basesClippedBefore, line[w].extraBasesClippedBefore,
-                                     line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], 48, &co[w]);
+                                     line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], SG_SAM_MAX_OPS, &co[w]);
                     editDistance[w] = co[w].editDistance; refSpan[w] = co[w].kind == 2 ? co[w].refSpan : 0;
                     addFrontClipping = co[w].addFrontClipping;
                     if (addFrontClipping != 0) {

@@ -12,6 +12,10 @@
 #pragma once
 #include "sg_cigar.h"
 
+// CIGAR operations one record can carry: an alignment with e edits has at most 2e + 1 operations (e <= MAX_K - 1 = 126), plus two
+// soft / hard clips on either side.  (The reference formats into a 2000-character buffer, which is never the limit.)
+#define SG_SAM_MAX_OPS 264
+
 struct SgSamRead {                   // the Read object's view of one read (Read.h:412-560)
     const uint8_t *unclippedData, *unclippedQuality;
     uint32_t unclippedLength;
@@ -115,7 +119,7 @@ SG_HDN int sg_sam_format(const SgSamContext &C, const SgSamRead &R, int status, 
         mapQuality = 0;
     }
     // ---- writeRead: the CIGAR (:1976-1983 / :2194-2204) ----
-    uint32_t ops[48];
+    uint32_t ops[SG_SAM_MAX_OPS];
     SgCigarOut co;
     co.kind = 1; co.editDistance = -1; co.nOps = 0;
     int editDistance = -1;
@@ -125,8 +129,8 @@ SG_HDN int sg_sam_format(const SgSamContext &C, const SgSamRead &R, int status, 
         //  which is the caller's original one: pass that)
         const int64_t locForCigar = genomeLocation - extraBasesClippedBefore;
         if (affineGap) sg_cigar_ag(ix, C.ag, C.agS, clippedData, clippedQuality, clippedLength, score, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter, 0, 0,
-                                   locForCigar, C.useM, ops, 48, &co);
-        else sg_cigar_lv(ix, C.lv, clippedData, clippedLength, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter, 0, 0, locForCigar, C.useM, ops, 48, &co);
+                                   locForCigar, C.useM, ops, SG_SAM_MAX_OPS, &co);
+        else sg_cigar_lv(ix, C.lv, clippedData, clippedLength, basesClippedBefore, extraBasesClippedBefore, basesClippedAfter, 0, 0, locForCigar, C.useM, ops, SG_SAM_MAX_OPS, &co);
         editDistance = co.editDistance;
         if (co.addFrontClipping != 0) { *addFrontClipping = co.addFrontClipping; return 0; }
     }
@@ -274,7 +278,7 @@ SG_HDN int sg_sam_write_pair(const SgSamContext &C, SgSamRead R0, SgSamRead R1, 
         if (locations[0] <= locations[1]) { writeOrder[0] = 0; writeOrder[1] = 1; } else { writeOrder[0] = 1; writeOrder[1] = 0; }
         // ---- SAMFormat::writePairs (:1628-1716): line fields and CIGAR of each read, in write order ----
         SgSamLine line[2];
-        uint32_t ops[2][48];
+        uint32_t ops[2][SG_SAM_MAX_OPS];
         SgCigarOut co[2];
         int editDistance[2] = {-1, -1}, refSpan[2] = {0, 0};
         for (int fs = 0; fs < 2; fs++) {
@@ -288,9 +292,9 @@ SG_HDN int sg_sam_write_pair(const SgSamContext &C, SgSamRead R0, SgSamRead R1, 
                 if (locations[w] != SG_SAM_INVALID_LOCATION) {
                     const bool ag = C.useAffineGap && (res.usedAffineGapScoring[w] || res.score[w] > 0);
                     if (ag) sg_cigar_ag(ix, C.ag, C.agS, line[w].clippedData, line[w].clippedQuality, line[w].clippedLength, res.score[w], line[w].basesClippedBefore,
-                                        line[w].extraBasesClippedBefore, line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], 48, &co[w]);
+                                        line[w].extraBasesClippedBefore, line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], SG_SAM_MAX_OPS, &co[w]);
                     else sg_cigar_lv(ix, C.lv, line[w].clippedData, line[w].clippedLength, line[w].basesClippedBefore, line[w].extraBasesClippedBefore,
-                                     line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], 48, &co[w]);
+                                     line[w].basesClippedAfter, 0, 0, locations[w], C.useM, ops[w], SG_SAM_MAX_OPS, &co[w]);
                     editDistance[w] = co[w].editDistance; refSpan[w] = co[w].kind == 2 ? co[w].refSpan : 0;
                     addFrontClipping = co[w].addFrontClipping;
                     if (addFrontClipping != 0) {

@@ -1522,7 +1522,7 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     int64_t threads = (int64_t)prop.multiProcessorCount * 64;
     if (threads > maxBatchReads) threads = (maxBatchReads + 63) / 64 * 64;
     s->nThreads = (int)threads;
-    s->slotBytes = 2 * (2 * s->lay.maxReadLen + SG_SAM_MAX_ID + 512);          // room for the two records of a pair
+    s->slotBytes = 2 * (2 * s->lay.maxReadLen + SG_SAM_MAX_ID + 256 + 5 * SG_SAM_MAX_OPS);      // room for the two records of a pair (CIGAR: <= 5 characters per operation)
     // contig names and the default read group line (ReaderContext::defaultReadGroupAux for the default read group "FASTQ")
     std::string blob; std::vector<size_t> off;
     for (size_t c = 0; c < idx->h_contigName.size(); c++) { off.push_back(blob.size()); blob += idx->h_contigName[c]; blob.push_back('\0'); }
