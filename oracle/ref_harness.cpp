@@ -374,6 +374,48 @@ _int64 ref_write_reads_batch(void *vidx, const int *agParams, int useM, int useA
     return (_int64)mw->used;
 }
 
+// SimpleReadWriter::writePairs (ReadWriter.cpp:362-560) into memory, same set-up as ref_write_reads_batch: the oracle for sg_sam_write_pair
+_int64 ref_write_pairs_batch(void *vidx, const int *agParams, int useM, int useAffineGap, _int64 nReads, const char *bases, const char *quals, const _uint64 *offsets,
+                             const unsigned *lens, const char *ids, const _uint64 *idOffsets, const unsigned *idLens, const snapgpu_paired_result *results,
+                             char *out, _int64 outCap)
+{
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    RefMemWriter *mw = new RefMemWriter(out, (size_t)outCap);
+    RefMemSupplier *ms = new RefMemSupplier(mw);
+    ReadWriterSupplier *rws = ReadWriterSupplier::create(FileFormat::SAM[useM ? 1 : 0], ms, index->getGenome(), false, false, (char *)"", false,
+                                                        agParams[0], agParams[1], agParams[2], agParams[3], false);
+    ReadWriter *rw = rws->getWriter();
+    ReaderContext ctx;
+    memset(&ctx, 0, sizeof(ctx));
+    ctx.genome = index->getGenome();
+    ctx.defaultReadGroup = "FASTQ";
+    static const char rg[] = "\tRG:Z:FASTQ\tPL:Z:Illumina\tPU:Z:pu\tLB:Z:lb\tSM:Z:sm";
+    ctx.defaultReadGroupAux = rg; ctx.defaultReadGroupAuxLen = (int)strlen(rg);
+    ctx.paired = true;
+    for (_int64 i = 0; i < nReads / 2; i++) {
+        Read r0, r1;
+        Read *reads[2] = {&r0, &r1};
+        for (int w = 0; w < 2; w++) {
+            const _int64 k = 2 * i + w;
+            reads[w]->init(ids + idOffsets[k], idLens[k], bases + offsets[k], quals + offsets[k], lens[k], NULL, 0);
+            reads[w]->setReadGroup(ctx.defaultReadGroup);
+        }
+        const snapgpu_paired_result &r = results[i];
+        PairedAlignmentResult pr;
+        memset(&pr, 0, sizeof(pr));
+        for (int w = 0; w < 2; w++) {
+            pr.status[w] = (AlignmentResult)r.status[w]; pr.location[w] = r.status[w] == 0 ? InvalidGenomeLocation : GenomeLocation(r.location[w]);
+            pr.origLocation[w] = pr.location[w]; pr.direction[w] = r.direction[w] ? RC : FORWARD; pr.score[w] = r.score[w];
+            pr.scorePriorToClipping[w] = r.scorePriorToClipping[w]; pr.mapq[w] = r.mapq[w]; pr.clippingForReadAdjustment[w] = r.clippingForReadAdjustment[w];
+            pr.usedAffineGapScoring[w] = r.usedAffineGapScoring[w] != 0; pr.basesClippedBefore[w] = r.basesClippedBefore[w]; pr.basesClippedAfter[w] = r.basesClippedAfter[w];
+            pr.agScore[w] = r.agScore[w];
+        }
+        pr.alignedAsPair = r.alignedAsPair != 0;
+        if (!rw->writePairs(ctx, reads, &pr, 1, NULL, NULL, true, useAffineGap != 0)) return -1;
+    }
+    return (_int64)mw->used;
+}
+
 /*
  * AffineGapVectorized<dir>::computeScore / computeScoreBanded (AffineGapVectorized.h:821 / 256).
  * The objects hold __m128i members => allocate 16-byte aligned.

@@ -124,6 +124,8 @@ def lib():
         L.ref_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         L.ref_write_reads_batch.restype = C.c_int64
         L.ref_write_reads_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64]
+        L.ref_write_pairs_batch.restype = C.c_int64
+        L.ref_write_pairs_batch.argtypes = L.ref_write_reads_batch.argtypes
         L.ref_decode_cigar.restype = C.c_int
         L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -354,7 +356,7 @@ def cigar_ag_batch(index, data: np.ndarray, qual: np.ndarray, jobs: np.ndarray, 
     return out
 
 
-def write_reads(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1)) -> bytes:
+def write_reads(index, batch, ids, results, use_m=True, use_affine_gap=True, params=(1, 4, 6, 1), paired=False) -> bytes:
     """SimpleReadWriter::writeReads (SAM) for every read of the batch with the given result records; returns the text."""
     prm = np.ascontiguousarray(params, dtype=np.int32)
     id_buf = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
@@ -363,7 +365,8 @@ def write_reads(index, batch, ids, results, use_m=True, use_affine_gap=True, par
     cap = int(batch.n) * 4096 + 8192
     out = np.zeros(cap, dtype=np.uint8)
     res = np.ascontiguousarray(results)
-    n = lib().ref_write_reads_batch(index.handle, _p(prm), 1 if use_m else 0, 1 if use_affine_gap else 0, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
+    fn = lib().ref_write_pairs_batch if paired else lib().ref_write_reads_batch
+    n = fn(index.handle, _p(prm), 1 if use_m else 0, 1 if use_affine_gap else 0, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
                                     _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), _p(res), _p(out), cap)
     assert n >= 0
     return out[:n].tobytes()

@@ -535,3 +535,37 @@ def test_write_reads_retry_loop_equals_reference(reflib, small_cfg, use_ag):
     flags = [int(l.split(b"\t")[1]) for l in want]
     gave_up = sum(1 for i in range(rb.n) if res[i]["status"] != 0 and (flags[i] & 4))
     assert gave_up > 5                                                       # reads given up at a contig boundary
+
+
+def test_write_pairs_retry_loops_equal_reference(reflib, small_cfg):
+    """The same for pairs: SimpleReadWriter::writePairs itself (into memory) vs sg_sam_write_pair, with one or both ends of the
+    reference aligner's placements shifted, moved to a contig end, or put before a contig (re-ordering of the two records, ends given
+    up, mates pointing at each other)."""
+    rng = np.random.default_rng(78)
+    pb = small_cfg.pairs["noisy150"]
+    bases, starts = small_cfg.padded_bases()
+    ridx = reflib.RefIndex(small_cfg.idx)
+    kw, pkw = PAIRED_DEFAULT
+    res, _ = reflib.RefPairedAligner(ridx, reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)).align(pb)
+    res = res.copy()
+    for i in range(pb.n // 2):
+        for w in range(2):
+            if res[i]["status"][w] == 0:
+                continue
+            how = int(rng.integers(0, 8))
+            if how <= 2:
+                res[i]["location"][w] += int(rng.choice([-3, -2, -1, 1, 2, 3, 5]))
+            elif how == 3:
+                c = int(rng.integers(0, len(starts)))
+                res[i]["location"][w] = int(starts[c]) + small_cfg.contigs[c].size - int(rng.integers(1, 150))
+            elif how == 4:
+                c = int(rng.integers(0, len(starts)))
+                res[i]["location"][w] = int(starts[c]) - int(rng.integers(1, 40))
+    ids = []
+    for i in range(pb.n // 2):
+        ids += [b"p%d/1" % i, b"p%d/2" % i]
+    want = [l for l in reflib.write_reads(ridx, pb, ids, res, paired=True).split(b"\n") if l]
+    got = [l for l in hs.sam_single(hs.HsIndex(small_cfg.idx), pb, ids, res, paired=True).split(b"\n") if l]
+    assert len(want) == len(got) == pb.n
+    bad = [i for i in range(pb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), res[bad[0] // 2], want[bad[0]], got[bad[0]])
