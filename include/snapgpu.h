@@ -330,17 +330,22 @@ int  snapgpu_fastq_parse(snapgpu_fastq *f, const char *text, int64_t nBytes, int
  * reads / ids / results are HOST arrays in the layout of snapgpu_align_single / _paired (ids: concatenated, idOffsets / idLens per
  * read, at most 255 characters each); `text` receives the records back to back, *textBytes their total length.
  * `useM`: M instead of = / X operations (SNAP's default, -M).  Scoring parameters and useAffineGap are taken from `params`.
- * First form: the reads are taken to be unclipped (no quality clipping in effect); one thread per read, not yet optimised.
+ * Quality clipping (Read::clip, reference SNAPLib/Read.h:567-619): hand over the UNCLIPPED reads plus, per read, frontClipped[i] (bases clipped
+ * at the front) and clippedLens[i] (length of the view that was aligned) -- e.g. snapgpu_fastq_parse's frontClipped and lens outputs next to
+ * the text's own sequence lines -- or NULL for both when nothing was clipped.  The records then carry the whole read with S operations,
+ * like stock SNAP's.  First form: one thread per read, not yet optimised.
  */
 typedef struct snapgpu_sam snapgpu_sam;
 int  snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, int32_t useM, int64_t maxBatchReads, snapgpu_sam **out);
 void snapgpu_sam_destroy(snapgpu_sam *s);
 int  snapgpu_sam_format_single(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
-                               const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results,
-                               char *text, int64_t textCapacity, int64_t *textBytes);
+                               const char *ids, const uint64_t *idOffsets, const uint32_t *idLens,
+                               const uint32_t *frontClipped, const uint32_t *clippedLens,
+                               const snapgpu_single_result *results, char *text, int64_t textCapacity, int64_t *textBytes);
 int  snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
-                               const char *ids, const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_paired_result *results,
-                               char *text, int64_t textCapacity, int64_t *textBytes);
+                               const char *ids, const uint64_t *idOffsets, const uint32_t *idLens,
+                               const uint32_t *frontClipped, const uint32_t *clippedLens,
+                               const snapgpu_paired_result *results, char *text, int64_t textCapacity, int64_t *textBytes);
 
 /* Number of kernel launches issued through this aligner since creation (bench.py's gpu_launches). */
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a);

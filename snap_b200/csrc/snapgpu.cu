@@ -1431,7 +1431,8 @@ __global__ void __launch_bounds__(64)
 sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, uint8_t *scratch, const char *const *contigNames, const char *readGroupAux,
               SgAgParams ag, int useM, int useAffineGap, long long nUnits, int paired, const uint8_t *bases, const uint8_t *quals,
               const unsigned long long *offsets, const uint32_t *lens, const uint8_t *ids, const unsigned long long *idOffsets, const uint32_t *idLens,
-              const snapgpu_single_result *single, const snapgpu_paired_result *pairs, char *slots, uint32_t slotBytes, uint32_t *recordBytes)
+              const snapgpu_single_result *single, const snapgpu_paired_result *pairs, const uint32_t *frontClipped, const uint32_t *clippedLens,
+              char *slots, uint32_t slotBytes, uint32_t *recordBytes)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nT = (long long)gridDim.x * blockDim.x;
@@ -1443,7 +1444,8 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
         if (!paired) {
             SgSamRead R;
             R.unclippedData = bases + offsets[u]; R.unclippedQuality = quals + offsets[u]; R.unclippedLength = lens[u];
-            R.frontClipped = 0; R.dataLength = lens[u]; R.id = ids + idOffsets[u]; R.idLength = idLens[u];
+            R.frontClipped = frontClipped ? frontClipped[u] : 0u; R.dataLength = clippedLens ? clippedLens[u] : lens[u];      // quality clipping (Read::clip), if any
+            R.id = ids + idOffsets[u]; R.idLength = idLens[u];
             R.additionalFrontClipping = 0; R.additionalBackClipping = 0;
             const snapgpu_single_result &r = single[u];
             SgSamResult sr;
@@ -1456,7 +1458,8 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
             for (int w = 0; w < 2; w++) {
                 const long long k = 2 * u + w;
                 R[w].unclippedData = bases + offsets[k]; R[w].unclippedQuality = quals + offsets[k]; R[w].unclippedLength = lens[k];
-                R[w].frontClipped = 0; R[w].dataLength = lens[k]; R[w].id = ids + idOffsets[k]; R[w].idLength = idLens[k];
+                R[w].frontClipped = frontClipped ? frontClipped[k] : 0u; R[w].dataLength = clippedLens ? clippedLens[k] : lens[k];
+                R[w].id = ids + idOffsets[k]; R[w].idLength = idLens[k];
                 R[w].additionalFrontClipping = 0; R[w].additionalBackClipping = 0;
             }
             const snapgpu_paired_result &r = pairs[u];
@@ -1486,7 +1489,7 @@ struct snapgpu_sam {
     // staging of the host-buffer call
     uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_ids = nullptr, *d_results = nullptr;
     unsigned long long *d_offsets = nullptr, *d_idOffsets = nullptr;
-    uint32_t *d_lens = nullptr, *d_idLens = nullptr, *d_recordBytes = nullptr;
+    uint32_t *d_lens = nullptr, *d_idLens = nullptr, *d_recordBytes = nullptr, *d_front = nullptr, *d_clippedLens = nullptr;
     char *d_slots = nullptr;
     std::vector<char> h_slots; std::vector<uint32_t> h_recordBytes;
     cudaStream_t stream = nullptr;
@@ -1498,7 +1501,7 @@ void snapgpu_sam_destroy(snapgpu_sam *s)
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
     cudaFree(s->d_scratch); cudaFree(s->d_names); cudaFree((void *)s->d_namePtrs); cudaFree(s->d_rgAux); cudaFree(s->d_bases); cudaFree(s->d_quals); cudaFree(s->d_ids);
-    cudaFree(s->d_results); cudaFree(s->d_offsets); cudaFree(s->d_idOffsets); cudaFree(s->d_lens); cudaFree(s->d_idLens); cudaFree(s->d_recordBytes); cudaFree(s->d_slots);
+    cudaFree(s->d_results); cudaFree(s->d_offsets); cudaFree(s->d_idOffsets); cudaFree(s->d_lens); cudaFree(s->d_idLens); cudaFree(s->d_recordBytes); cudaFree(s->d_front); cudaFree(s->d_clippedLens); cudaFree(s->d_slots);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1536,6 +1539,7 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
          cudaMalloc((void **)&s->d_offsets, (size_t)maxBatchReads * 8) == cudaSuccess && cudaMalloc((void **)&s->d_idOffsets, (size_t)maxBatchReads * 8) == cudaSuccess &&
          cudaMalloc((void **)&s->d_lens, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_idLens, (size_t)maxBatchReads * 4) == cudaSuccess &&
          cudaMalloc((void **)&s->d_recordBytes, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_front, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_clippedLens, (size_t)maxBatchReads * 4) == cudaSuccess &&
          cudaMalloc((void **)&s->d_slots, (size_t)maxBatchReads * s->slotBytes) == cudaSuccess &&
          cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
@@ -1555,10 +1559,12 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
 }
 
 static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens, const char *ids,
-                      const uint64_t *idOffsets, const uint32_t *idLens, const void *results, char *text, int64_t textCapacity, int64_t *textBytes)
+                      const uint64_t *idOffsets, const uint32_t *idLens, const uint32_t *frontClipped, const uint32_t *clippedLens, const void *results, char *text,
+                      int64_t textCapacity, int64_t *textBytes)
 {
     if (!s || !bases || !quals || !offsets || !lens || !ids || !idOffsets || !idLens || !results || !text || !textBytes) return sg_fail("null argument");
     if (nReads < 0 || nReads > s->maxBatchReads || (paired && (nReads & 1))) return sg_fail("snapgpu_sam_format: bad read count");
+    if ((frontClipped == nullptr) != (clippedLens == nullptr)) return sg_fail("snapgpu_sam_format: frontClipped and clippedLens go together (both or neither)");
     *textBytes = 0;
     if (nReads == 0) return 0;
     SG_CUDA(cudaSetDevice(s->device));
@@ -1566,6 +1572,7 @@ static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *ba
     for (int64_t i = 0; i < nReads; i++) {
         if (lens[i] > s->lay.maxReadLen) return sg_fail("a read is longer than the configured maximum (SNAPGPU_MAX_READ_LEN)");
         if (idLens[i] >= SG_SAM_MAX_ID) return sg_fail("a read id is longer than 255 characters");
+        if (frontClipped && (uint64_t)frontClipped[i] + clippedLens[i] > lens[i]) return sg_fail("snapgpu_sam_format: clipped view outside the read");
         if (offsets[i] + lens[i] > totalBases) totalBases = (size_t)(offsets[i] + lens[i]);
         if (idOffsets[i] + idLens[i] > totalIds) totalIds = (size_t)(idOffsets[i] + idLens[i]);
     }
@@ -1579,12 +1586,16 @@ static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *ba
     SG_CUDA(cudaMemcpyAsync(s->d_idOffsets, idOffsets, (size_t)nReads * 8, cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMemcpyAsync(s->d_lens, lens, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMemcpyAsync(s->d_idLens, idLens, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
+    if (frontClipped) {
+        SG_CUDA(cudaMemcpyAsync(s->d_front, frontClipped, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(s->d_clippedLens, clippedLens, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
+    }
     SG_CUDA(cudaMemcpyAsync(s->d_results, results, (size_t)nUnits * (paired ? sizeof(snapgpu_paired_result) : sizeof(snapgpu_single_result)), cudaMemcpyHostToDevice, st));
     int64_t threads = s->nThreads < nUnits ? s->nThreads : (nUnits + 63) / 64 * 64;
     sg_sam_kernel<<<(int)(threads / 64), 64, 0, st>>>(s->index->view, s->lay, s->d_scratch, s->d_namePtrs, s->d_rgAux, s->ag, s->useM, s->useAffineGap, nUnits, paired,
                                                       s->d_bases, s->d_quals, s->d_offsets, s->d_lens, s->d_ids, s->d_idOffsets, s->d_idLens,
                                                       paired ? nullptr : (const snapgpu_single_result *)s->d_results, paired ? (const snapgpu_paired_result *)s->d_results : nullptr,
-                                                      s->d_slots, s->slotBytes, s->d_recordBytes);
+                                                      frontClipped ? s->d_front : nullptr, frontClipped ? s->d_clippedLens : nullptr, s->d_slots, s->slotBytes, s->d_recordBytes);
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaMemcpyAsync(s->h_recordBytes.data(), s->d_recordBytes, (size_t)nUnits * 4, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(s->h_slots.data(), s->d_slots, (size_t)nUnits * s->slotBytes, cudaMemcpyDeviceToHost, st));
@@ -1602,15 +1613,17 @@ static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *ba
 }
 
 int snapgpu_sam_format_single(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens, const char *ids,
-                              const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_single_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
+                              const uint64_t *idOffsets, const uint32_t *idLens, const uint32_t *frontClipped, const uint32_t *clippedLens,
+                              const snapgpu_single_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
 {
-    return sam_format(s, 0, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, results, text, textCapacity, textBytes);
+    return sam_format(s, 0, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, frontClipped, clippedLens, results, text, textCapacity, textBytes);
 }
 
 int snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens, const char *ids,
-                              const uint64_t *idOffsets, const uint32_t *idLens, const snapgpu_paired_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
+                              const uint64_t *idOffsets, const uint32_t *idLens, const uint32_t *frontClipped, const uint32_t *clippedLens,
+                              const snapgpu_paired_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
 {
-    return sam_format(s, 1, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, results, text, textCapacity, textBytes);
+    return sam_format(s, 1, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, frontClipped, clippedLens, results, text, textCapacity, textBytes);
 }
 
 struct snapgpu_fastq {

@@ -122,7 +122,7 @@ def lib():
         L.snapgpu_fastq_destroy.argtypes = [C.c_void_p]
         L.snapgpu_sam_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]
         L.snapgpu_sam_destroy.argtypes = [C.c_void_p]
-        L.snapgpu_sam_format_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64, C.POINTER(C.c_int64)]
+        L.snapgpu_sam_format_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 11 + [C.c_int64, C.POINTER(C.c_int64)]
         L.snapgpu_sam_format_paired.argtypes = L.snapgpu_sam_format_single.argtypes
         L.snapgpu_fastq_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.snapgpu_fastq_parse_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
@@ -336,22 +336,24 @@ class SamFormatter:
         id_offs = np.concatenate([[0], np.cumsum(id_lens[:-1], dtype=np.uint64)]).astype(np.uint64)
         return id_buf, id_offs, id_lens
 
-    def format_arrays(self, batch, id_buf, id_offs, id_lens, results, paired: bool = False, text=None):
+    def format_arrays(self, batch, id_buf, id_offs, id_lens, results, paired: bool = False, text=None, front_clipped=None, clipped_lens=None):
         """The C ABI call itself (snapgpu_sam_format_single / _paired); returns (text buffer, bytes used)."""
         if text is None:
             text = np.zeros(int(batch.n) * (2 * int(batch.lens.max()) + 1024) + 4096, dtype=np.uint8)
         used = C.c_int64(0)
         fn = lib().snapgpu_sam_format_paired if paired else lib().snapgpu_sam_format_single
-        _check(fn(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), _p(results),
-                  _p(text), text.size, C.byref(used)))
+        fc = None if front_clipped is None else _p(np.ascontiguousarray(front_clipped, dtype=np.uint32))
+        cl = None if clipped_lens is None else _p(np.ascontiguousarray(clipped_lens, dtype=np.uint32))
+        _check(fn(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), fc, cl,
+                  _p(results), _p(text), text.size, C.byref(used)))
         return text, used.value
 
-    def format(self, batch, ids, results, paired: bool = False) -> bytes:
+    def format(self, batch, ids, results, paired: bool = False, front_clipped=None, clipped_lens=None) -> bytes:
         """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one
         per pair with paired=True)."""
         id_buf, id_offs, id_lens = self.pack_ids(ids)
         b = type(batch)(np.ascontiguousarray(batch.bases), np.ascontiguousarray(batch.quals), np.ascontiguousarray(batch.offsets), np.ascontiguousarray(batch.lens))
-        text, used = self.format_arrays(b, id_buf, id_offs, id_lens, np.ascontiguousarray(results), paired)
+        text, used = self.format_arrays(b, id_buf, id_offs, id_lens, np.ascontiguousarray(results), paired, front_clipped=front_clipped, clipped_lens=clipped_lens)
         return text[:used].tobytes()
 
     def close(self):

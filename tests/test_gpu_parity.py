@@ -568,3 +568,34 @@ def test_sam_pair_records_from_the_device_equal_reference_binary(engine, gidx, s
     assert len(want) == len(got) == pb.n
     bad = [i for i in range(pb.n) if want[i] != got[i]]
     assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+
+
+def test_sam_records_of_quality_clipped_reads_from_the_device(engine, gidx, small_cfg, reflib, tmp_path):
+    """Reads with '#' quality tails: the aligner gets the clipped view (Read::clip, default -C-+), snapgpu_sam_format_single the whole
+    read plus the clip counts; the records (whole read, S operations) must be the reference binary's."""
+    from snap_b200 import synth
+    rng = np.random.default_rng(5)
+    rb = small_cfg.reads["noisy150"]
+    reads = []; fronts = []; clens = []
+    for i in range(600):
+        b, q = rb.read(i)
+        q = bytearray(q)
+        tail = int(rng.choice([0, 0, 3, 11, 40])) if len(b) >= 70 else 0
+        for k in range(tail):
+            q[len(q) - 1 - k] = ord("#")
+        reads.append((b, bytes(q))); fronts.append(0); clens.append(len(b) - tail)
+    full = synth.ReadBatch.from_lists(reads)
+    clipped = synth.ReadBatch.from_lists([(b[:n], q[:n]) for (b, q), n in zip(reads, clens)])
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.sam")
+    full.write_fastq(fq)
+    want = _reference_sam_lines(reflib, ["single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"])
+    p = engine.default_params(maxDist=14)
+    al = engine.SingleAligner(gidx, p, 4096)
+    res, _ = al.align(clipped)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096)
+    got = [l for l in fmt.format(full, [b"r%d" % i for i in range(full.n)], res, front_clipped=fronts, clipped_lens=clens).split(b"\n") if l]
+    fmt.close()
+    assert len(want) == len(got) == full.n
+    bad = [i for i in range(full.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
