@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on the reference's headline workload (BASELINE.json):
 aligned reads/s for `snap single`, 150 bp synthetic reads vs a 3 Gbp hg-sized synthetic reference, seed 20,
-maxDist 14 (configs[1]), read-sharded over N GPUs.
+maxDist 14 (configs[1]), read-sharded over N GPUs -- and, in the same line, the other configs to the same bar.
 
 A "step" is one pass of the hot path (seed lookup + LV / affine-gap scoring, BaseAligner::AlignRead semantics) over
 one batch of synthetic reads.  `value` = reads of all ranks per second with the inputs already resident in HBM,
 timed with CUDA events around exactly K steps (max over ranks).  `e2e` = the same metric through the C ABI call a
 SNAP extension makes (snapgpu_align_single) with HOST buffers: host->device copies of the reads and device->host
-copy of the results inside the timed region.  `roofline` is for the step's alignment launches taken together (two for
-sg_align_kernel's two-pass form, four for the staged sg_align_paired_kernel), timed with CUDA events on their stream;
+copy of the results inside the timed region (aligner only: no FASTQ parsing, no SAM formatting).  `roofline` is for the
+step's alignment launches taken together, timed with CUDA events on their stream.
+`paired_phase` = BASELINE configs[2] (stock `snap paired`; at N > 1 this is configs[4]'s read-sharded shape),
+`ag_forced_phase` = configs[3] (`-G -d 20` and `-ne -d 20`): each with its own value / e2e / roofline and, at N = 1, a
+`cpu_baseline` whose `parity_vs_reference` compares the engine's records with the UNMODIFIED reference's on ~1 M reads
+(0.5 M pairs) at the full 3 Gbp size.  Any `differing != 0`, and any exception in those legs, makes the run exit 3
+after the line is printed.
 `seed_phase` is the seed-lookup kernel run in isolation over every seed of the batch (BASELINE's second metric).
 `cpu_baseline` / `--impl reference` time the UNMODIFIED reference (oracle/_ref, compiled from /root/reference) on the
 host cores, on a bounded sample of the same workload, against the same index written out in the reference's own
-directory format.
+directory format into tmpfs with its pages interleaved over the NUMA nodes (the protocol of BASELINE.md 3: threads started
+before the clock, >= 5 s timed, stock flags and -march=x86-64-v3, 1-thread and all-thread rates, a stock-CLI cross-check).
 """
 from __future__ import annotations
 
@@ -55,32 +61,15 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-seed-phase", action="store_true")
-    ap.add_argument("--workload", default=os.environ.get("SNAPGPU_BENCH_WORKLOAD", "single"), choices=["single", "paired"],
-                    help="single = BASELINE configs[1] (the default, headline); paired = configs[2] shape: stock `snap paired`, "
-                         "--batch-reads/2 FR pairs per step, insert N(400,40)")
-    ap.add_argument("--phase", default="", choices=["", "sam"], help=argparse.SUPPRESS)      # child-process mode of run_ours' sam_phase leg
+    ap.add_argument("--workload", default=os.environ.get("SNAPGPU_BENCH_WORKLOAD", "single"), choices=["single", "paired", "ag_d20", "ne_d20"],
+                    help="the HEADLINE workload (timed over exactly --steps): single = BASELINE configs[1] (default); paired = configs[2]; "
+                         "ag_d20 / ne_d20 = configs[3].  The others still run, as paired_phase / ag_forced_phase, unless --only-headline")
+    ap.add_argument("--only-headline", action="store_true", help="skip the other configs' phases (profiling runs)")
+    ap.add_argument("--no-sam-phase", action="store_true")
+    ap.add_argument("--no-cli-crosscheck", action="store_true")
+    ap.add_argument("--repeat-frac", type=float, default=float(os.environ.get("SNAPGPU_BENCH_REPEAT_FRAC", "0")),
+                    help="SURVEY 8d stress variant: this fraction of the reference is drawn from a 10 kbp repeat library at 0-5 %% divergence")
     return ap.parse_args()
-
-
-def measured_traffic(workload, batch_reads, genome_mbp):
-    """DRAM bytes of ONE step's alignment launches (summed) from the committed `ncu --set full` capture of this same workload
-    (profiles/traffic.json, written by profiles/extract_traffic.py); None when the capture is of another configuration."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_%dreads_%dmbp" % (workload, batch_reads, genome_mbp)
-        return int(t[key]["dram_bytes_per_launch"]) if key in t else None
-    except Exception:
-        return None
-
-
-def measured_instructions(workload, batch_reads, genome_mbp):
-    """Warp instructions one step's alignment launches execute (smsp__inst_executed.sum of the same committed capture)."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_%dreads_%dmbp" % (workload, batch_reads, genome_mbp)
-        return int(t[key]["warp_instructions_per_step"]) if key in t and "warp_instructions_per_step" in t[key] else None
-    except Exception:
-        return None
 
 
 def measured_peaks():
@@ -142,87 +131,154 @@ class ClockSampler:
         return out
 
 
-def build_workload(args, device, rank, world):
-    """Genome + index in this rank's HBM (replicated) and W+K batches of reads for this rank's shard."""
+
+# ---- the workloads of BASELINE.json's configs (SURVEY 8d command lines) ----
+WORKLOADS = {
+    # configs[1]: `snap single idx r150.fq -d 14` -- the headline
+    "single": dict(kind="single", kw=dict(maxDist=MAX_DIST), pkw=None, max_dist=MAX_DIST, config="BASELINE configs[1]",
+                   cli="snap-aligner single idx3G r150.fq -d 14"),
+    # configs[2] (and, sharded, configs[4]): stock `snap paired`
+    "paired": dict(kind="paired", kw=PAIRED_KW, pkw=PAIRED_PKW, max_dist=PAIRED_MAX_DIST, config="BASELINE configs[2] (configs[4] when sharded over N GPUs)",
+                   cli="snap-aligner paired idx3G r1.fq r2.fq   (stock options: -d 27 -n 8 -H 4000 -s 0 1000, soft clipping on)"),
+    # configs[3]: the same reads, maxDist 20, affine gap "forced": -G re-asserts the default (AlignerOptions.cpp:696-701) ...
+    "ag_d20": dict(kind="single", kw=dict(maxDist=20, useAffineGap=1), pkw=None, max_dist=20, config="BASELINE configs[3], -G",
+                   cli="snap-aligner single idx3G r150.fq -d 20 -G"),
+    # ... and -ne is what rescores EVERY candidate with affine gap (AlignerOptions.cpp:964-967; it also clears useAffineGap)
+    "ne_d20": dict(kind="single", kw=dict(maxDist=20, noEditDistance=1, useAffineGap=0), pkw=None, max_dist=20, config="BASELINE configs[3], -ne",
+                   cli="snap-aligner single idx3G r150.fq -d 20 -ne"),
+}
+
+
+def csrc_sha16():
+    """Hash of the kernel sources: profiles/traffic.json records the one its ncu capture was taken at, and the line only quotes
+    `traffic` / `issue_slots` from a capture of THESE sources."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "snap_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def traffic_entry(workload, batch_reads, genome_mbp):
+    """(entry or None, why-not).  The entry is ONE step's alignment launches from `ncu --set full` (profiles/refresh_traffic.sh)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "profiles/traffic.json unreadable"
+    key = "%s_%dreads_%dmbp" % (workload, batch_reads, genome_mbp)
+    if key not in t:
+        return None, "no capture of this workload"
+    if t[key].get("csrc_sha16") != csrc_sha16():
+        return None, "capture is of other kernel sources (csrc_sha16 %s, now %s): refresh with profiles/refresh_traffic.sh" % (t[key].get("csrc_sha16"), csrc_sha16())
+    return t[key], None
+
+
+class Ctx:
+    """Everything the workloads share on one rank: device, the genome and index in HBM, the reads, rank / world."""
+    pass
+
+
+def build_context(args):
     import torch
+    import torch.distributed as dist
     from snap_b200 import engine, synth_device
+    c = Ctx()
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if c.world != args.gpus and c.world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, c.world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    c.device = torch.device("cuda", c.local_rank)
+    torch.cuda.set_device(c.device)
+    if c.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=c.device)
     n_contigs = 24
-    contig_len = args.genome_mbp * 1_000_000 // n_contigs
+    c.contig_len = args.genome_mbp * 1_000_000 // n_contigs
     t0 = time.time()
-    bases, starts = synth_device.make_genome(n_contigs, contig_len, seed=20260924, device=device)
+    c.bases, c.starts = synth_device.make_genome(n_contigs, c.contig_len, seed=20260924, device=c.device)
+    if args.repeat_frac > 0:
+        synth_device.plant_repeats(c.bases, c.starts, c.contig_len, args.repeat_frac, seed=77)
     torch.cuda.synchronize()
     t1 = time.time()
-    idx = engine.Index.build_device(bases.data_ptr(), bases.numel(), starts, seed_len=SEED_LEN, chromosome_padding=2000, device=device.index or 0)
+    c.idx = engine.Index.build_device(c.bases.data_ptr(), c.bases.numel(), c.starts, seed_len=SEED_LEN, chromosome_padding=2000, device=c.device.index or 0)
     torch.cuda.synchronize()
     t2 = time.time()
-    batches = []
-    nb = args.warmup + args.steps
-    for b in range(nb):
-        # every (rank, step) gets its own reads: the global batch of step b is the concatenation over ranks
-        if args.workload == "paired":
-            batches.append(synth_device.make_pairs(bases, starts, contig_len, args.batch_reads // 2, READ_LEN, seed=1000 + b * 64 + rank))
+    info = c.idx.info()
+    c.setup = {"genome_s": round(t1 - t0, 2), "index_build_s": round(t2 - t1, 2), "index_hbm_gb": round(info.hbmBytes / 1e9, 2),
+               "overflow_words": int(info.overflowTableSize)}
+    c.peak, c.peak_src = measured_peaks()
+    c.ref = None
+    return c
+
+
+def make_batches(c, args, kind, n):
+    """n batches of this rank's shard: every (rank, step) has its own reads; the global batch of a step is the concatenation over ranks."""
+    from snap_b200 import synth_device
+    out = []
+    for b in range(n):
+        seed = 1000 + b * 64 + c.rank
+        if kind == "paired":
+            out.append(synth_device.make_pairs(c.bases, c.starts, c.contig_len, args.batch_reads // 2, READ_LEN, seed=seed))
         else:
-            batches.append(synth_device.make_reads(bases, starts, contig_len, args.batch_reads, READ_LEN, seed=1000 + b * 64 + rank))
-    torch.cuda.synchronize()
-    t3 = time.time()
-    info = idx.info()
-    setup = {"genome_s": round(t1 - t0, 2), "index_build_s": round(t2 - t1, 2), "reads_s": round(t3 - t2, 2),
-             "index_hbm_gb": round(info.hbmBytes / 1e9, 2), "overflow_words": int(info.overflowTableSize)}
-    return bases, starts, contig_len, idx, batches, setup
+            out.append(synth_device.make_reads(c.bases, c.starts, c.contig_len, args.batch_reads, READ_LEN, seed=seed))
+    return out
 
 
-def run_ours(args):
+def to_host_batch(dev_batch, pinned=True):
+    from snap_b200 import synth
+    rb, rq, ro, rl = dev_batch[:4]
+    if pinned:
+        return synth.ReadBatch(rb.cpu().pin_memory().numpy(), rq.cpu().pin_memory().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32))
+    return synth.ReadBatch(rb.cpu().numpy(), rq.cpu().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32))
+
+
+def run_workload(c, args, name, batches, W, K, sample_clocks=False):
+    """One workload on this rank (all ranks call it together): device-resident timing over exactly K steps after W warm-ups, then the
+    same through the C ABI with host buffers.  Returns the workload's object; ["_records"] holds the engine's records for batches[0]
+    (rank 0, for the parity leg), ["_host0"] those reads on the host."""
     import torch
     import torch.distributed as dist
     from snap_b200 import engine, shard
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=device)
-    W, K, B = args.warmup, args.steps, args.batch_reads
-    bases, starts, contig_len, idx, batches, setup = build_workload(args, device, rank, world)
-    paired = args.workload == "paired"
+    wl = WORKLOADS[name]
+    paired = wl["kind"] == "paired"
+    B = (args.batch_reads // 2) * 2 if paired else args.batch_reads
+    n_units = B // 2 if paired else B
+    device, world, rank = c.device, c.world, c.rank
     if paired:
-        B = args.batch_reads = (B // 2) * 2
-        al = engine.PairedAligner(idx, engine.default_params(**PAIRED_KW), engine.default_paired_params(**PAIRED_PKW), max_batch_pairs=B // 2)
-        result_bytes_per_read = engine.PAIRED_RESULT_DTYPE.itemsize // 2
+        al = engine.PairedAligner(c.idx, engine.default_params(**wl["kw"]), engine.default_paired_params(**wl["pkw"]), max_batch_pairs=n_units)
+        res_dtype = engine.PAIRED_RESULT_DTYPE
     else:
-        al = engine.SingleAligner(idx, engine.default_params(maxDist=MAX_DIST), max_batch_reads=B)
-        result_bytes_per_read = engine.RESULT_DTYPE.itemsize
+        al = engine.SingleAligner(c.idx, engine.default_params(**wl["kw"]), max_batch_reads=B)
+        res_dtype = engine.RESULT_DTYPE
+    result_bytes_per_read = res_dtype.itemsize // (2 if paired else 1)
     # a dedicated (non-default) stream: the kernels are launched on it through the C ABI and the CUDA events that time
     # them are recorded on the same stream (a NULL stream argument would mean "the aligner's own stream")
     stream = torch.cuda.Stream(device)
     assert stream.cuda_stream != 0
-    res = torch.empty((B, result_bytes_per_read), dtype=torch.uint8, device=device)
+    res = torch.empty((n_units, res_dtype.itemsize), dtype=torch.uint8, device=device)
     d_ctr = torch.zeros((engine.N_COUNTERS,), dtype=torch.int64, device=device)
 
     def step(b):
-        rb, rq, ro, rl = batches[b][0], batches[b][1], batches[b][2], batches[b][3]
-        al.align_device(B // 2 if paired else B, rb.data_ptr(), rq.data_ptr(), ro.data_ptr(), rl.data_ptr(), res.data_ptr(), d_ctr.data_ptr(),
-                        stream.cuda_stream)
+        rb, rq, ro, rl = batches[b][:4]
+        al.align_device(n_units, rb.data_ptr(), rq.data_ptr(), ro.data_ptr(), rl.data_ptr(), res.data_ptr(), d_ctr.data_ptr(), stream.cuda_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: W warm-ups, then exactly K steps between barriers, CUDA events on the launch stream ----
+    # ---- device-resident timing ----
     for b in range(W):
         step(b)
     barrier()
     d_ctr.zero_()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(c.local_rank)
+    if sample_clocks and rank == 0:
         sampler.start()
     launches0 = al.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
@@ -232,7 +288,7 @@ def run_ours(args):
         step(W + k)
         ev[k + 1].record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else {}
+    clocks = sampler.stop() if (sample_clocks and rank == 0) else {}
     ms_total = ev[0].elapsed_time(ev[K])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
     launches = al.launch_count() - launches0
@@ -241,27 +297,18 @@ def run_ours(args):
     ctr = d_ctr.cpu().numpy()
     ms_max = shard.max_over_ranks(ms_total, device) if world > 1 else ms_total
     ctr_all = shard.allreduce_counters(ctr, device) if world > 1 else ctr
-    c = engine.counters_dict(ctr_all)
-    reads_total = B * K * world
-    value = reads_total / (ms_max / 1e3)
+    cd = engine.counters_dict(ctr_all)
+    value = B * K * world / (ms_max / 1e3)
 
-    # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) ----
-    host_batches = []
-    from snap_b200 import synth
-    for b in range(min(2, W + K)):
-        rb, rq, ro, rl = batches[b][:4]
-        # inputs of the end-to-end leg live in pinned host memory (the C ABI then DMAs straight out of them)
-        hb = synth.ReadBatch(rb.cpu().pin_memory().numpy(), rq.cpu().pin_memory().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32))
-        host_batches.append(hb)
-    # ... and so does the result array (torch is only used to get page-locked memory)
-    res_dtype = engine.PAIRED_RESULT_DTYPE if paired else engine.RESULT_DTYPE
-    n_units = B // 2 if paired else B
+    # ---- end to end through the C ABI: reads in pinned HOST memory, records back in pinned host memory, copies inside the clock ----
+    host_batches = [to_host_batch(batches[b]) for b in range(min(3, W + K))]
     res_host = torch.empty((n_units * res_dtype.itemsize,), dtype=torch.uint8).pin_memory().numpy().view(res_dtype)
-    al.align(host_batches[0], out=res_host)         # warm-up
+    for b in range(2):
+        al.align(host_batches[b % len(host_batches)], out=res_host)         # warm-ups
     barrier()
+    e2e_steps = max(3, min(K, 10))
     t0 = time.perf_counter()
     n_e2e = 0
-    e2e_steps = max(1, min(K, 3))
     for k in range(e2e_steps):
         r, _ = al.align(host_batches[k % len(host_batches)], out=res_host)
         n_e2e += len(r) * (2 if paired else 1)
@@ -269,107 +316,144 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     e2e_s = shard.max_over_ranks(e2e_s, device) if world > 1 else e2e_s
     e2e_value = n_e2e * world / e2e_s
+    records0 = None
+    if rank == 0 and world == 1:
+        records0, _ = al.align(host_batches[0])
+        records0 = records0.copy()
 
-    # ---- roofline of the step's alignment kernels (sg_align_kernel: pass 1 + pass 2 launches; sg_align_paired_kernel: three
-    #      stage launches + the retry launch), timed together with CUDA events: algorithmic bytes of the step / its duration ----
-    peak, peak_src = measured_peaks()
-    per_launch = 1.0 / (K * world)
-    alg_bytes = (c["nHashEntriesProbed"] * 8 + c["nOverflowWordsRead"] * 4 + (c["lvCalls"] + c["affineGapCalls"]) * ALG_BYTES_PER_CANDIDATE
-                 + c["totalReads"] * (2 * READ_LEN + result_bytes_per_read)) * per_launch
+    # ---- roofline of the step's alignment launches taken together (algorithmic bytes of the step / its duration) ----
+    per_step = 1.0 / (K * world)
+    alg_cand = READ_LEN - SEED_LEN + 2 * (wl["max_dist"] + 1)
+    alg_bytes = (cd["nHashEntriesProbed"] * 8 + cd["nOverflowWordsRead"] * 4 + (cd["lvCalls"] + cd["affineGapCalls"]) * alg_cand
+                 + cd["totalReads"] * (2 * READ_LEN + result_bytes_per_read)) * per_step
     kernel_ms_avg = float(np.mean(kernel_ms))
     achieved = alg_bytes / (kernel_ms_avg / 1e3) / 1e9
+    entry, why = traffic_entry(name, B, args.genome_mbp)
     roofline = {"kernel": ("sg_align_paired_kernel<.,1..3> (staged launch: seed/LV, affine gap, single-end fallback) + retry pass" if paired else
-                           "sg_align_kernel<.,1> + <.,2> (two-pass launch: without affine gap, then the deferred reads)"),
-                "launches_per_step": round(launches / K, 2), "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 6), "traffic": measured_traffic(args.workload, B, args.genome_mbp), "peak_source": peak_src,
+                           "sg_align_kernel<.,1> + <.,2> (two-pass launch)" if not wl["kw"].get("noEditDistance") else "sg_align_kernel<.,0> (one launch: every candidate is rescored)"),
+                "launches_per_step": round(launches / K, 2), "bound": "hbm", "achieved": round(achieved, 3), "peak": c.peak, "unit": "GB/s",
+                "frac": round(achieved / c.peak, 6), "traffic": int(entry["dram_bytes_per_launch"]) if entry else None, "peak_source": c.peak_src,
                 "algorithmic_bytes_per_step": int(alg_bytes), "avg_step_ms": round(kernel_ms_avg, 3),
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
+    if entry:
+        roofline["traffic_over_algorithmic"] = round(entry["dram_bytes_per_launch"] / max(1.0, alg_bytes), 2)
+        roofline["traffic_source"] = "profiles/traffic.json, ncu --set full of these kernel sources (csrc_sha16 %s)" % entry["csrc_sha16"]
+        n_inst = entry.get("warp_instructions_per_step")
+        sm_mhz = clocks.get("sm_mhz") or c.__dict__.get("sm_mhz")
+        if n_inst and sm_mhz:
+            sms = torch.cuda.get_device_properties(device).multi_processor_count
+            issue_peak = sms * 4 * float(sm_mhz) * 1e6
+            issue_ach = n_inst / (kernel_ms_avg / 1e3)
+            roofline["issue_slots"] = {"warp_instructions_per_step": int(n_inst), "achieved_per_s": round(issue_ach, 1), "peak_per_s": round(issue_peak, 1),
+                                       "frac": round(issue_ach / issue_peak, 4)}
+    else:
+        roofline["traffic_note"] = why
+    if clocks.get("sm_mhz"):
+        c.sm_mhz = clocks["sm_mhz"]
 
-    # what actually bounds these kernels is instruction issue, so that utilisation is reported beside the (required) HBM roofline:
-    # warp instructions per step (from the committed ncu capture of this workload) / step time, against SMs x 4 schedulers x SM clock
-    n_inst = measured_instructions(args.workload, B, args.genome_mbp)
-    if n_inst is not None and clocks.get("sm_mhz"):
-        sms = torch.cuda.get_device_properties(device).multi_processor_count
-        issue_peak = sms * 4 * float(clocks["sm_mhz"]) * 1e6
-        issue_ach = n_inst / (kernel_ms_avg / 1e3)
-        roofline["issue_slots"] = {"warp_instructions_per_step": n_inst, "achieved_per_s": round(issue_ach, 1), "peak_per_s": round(issue_peak, 1),
-                                   "frac": round(issue_ach / issue_peak, 4), "source": "profiles/traffic.json (ncu smsp__inst_executed.sum)"}
+    out = {"workload": wl["cli"], "config": wl["config"], "value": round(value, 1), "unit": "reads/s", "steps": K, "warmup": W,
+           "ms_per_step": round(ms_max / K, 3), "reads_per_step": B * world,
+           "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(B * (2 * READ_LEN + 12)),
+                   "d2h_bytes_per_step": int(B * result_bytes_per_read + engine.N_COUNTERS * 8), "steps": e2e_steps,
+                   "scope": "aligner only, through snapgpu_align_%s with host buffers (reads already parsed, no SAM formatting)" % ("paired" if paired else "single")},
+           "gpu_launches": int(launches), "roofline": roofline,
+           "per_read": {"lookups": round(cd["nHashTableLookups"] / max(1, cd["totalReads"]), 3),
+                        "hash_entries_per_lookup": round(cd["nHashEntriesProbed"] / max(1, cd["nHashTableLookups"]), 3),
+                        "overflow_words": round(cd["nOverflowWordsRead"] / max(1, cd["totalReads"]), 3),
+                        "lv_locations": round(cd["lvCalls"] / max(1, cd["totalReads"]), 3),
+                        "ag_locations": round(cd["affineGapCalls"] / max(1, cd["totalReads"]), 3),
+                        "aligned_frac": round((cd["singleHits"] + cd["multiHits"]) / max(1, cd["totalReads"]), 5)},
+           "_clocks": clocks, "_records": records0, "_host0": host_batches[0], "_host_batches": host_batches}
+    al.close()
+    del res, res_host
+    torch.cuda.empty_cache()
+    return out
 
-    out = {
-        "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": round(ms_max / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
-        "config": {"workload": ("snap paired (stock options), 2 x %d x %d bp synthetic FR pairs (insert N(400,40)) per step per GPU vs %d Mbp "
-                                "synthetic reference (24 contigs), seed %d, maxDist %d, IntersectingPairedEndAligner + chimeric single-end fallback "
-                                "(BASELINE configs[2] shape)" % (B // 2, READ_LEN, args.genome_mbp, SEED_LEN, PAIRED_MAX_DIST)) if paired else
-                               ("snap single, %d x %d bp synthetic reads per step per GPU vs %d Mbp synthetic reference (24 contigs), "
-                                "seed %d, maxDist %d, affine gap on (BASELINE configs[1] shape)" % (B, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)),
-                   "reads_per_step": B * world, "read_len": READ_LEN, "genome_mbp": args.genome_mbp, "seed_len": SEED_LEN,
-                   "max_dist": PAIRED_MAX_DIST if paired else MAX_DIST,
-                   "parallelism": "read-sharded x%d, index replicated per GPU" % world,
-                   "l2": "each step uses fresh reads (%.0f MB/step > L2) against a %.1f GB index" % (B * 2 * READ_LEN / 1e6, setup["index_hbm_gb"])},
-        "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(B * (2 * READ_LEN + 12)),
-                "d2h_bytes_per_step": int(B * result_bytes_per_read + engine.N_COUNTERS * 8), "steps": e2e_steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "per_read": {"lookups": round(c["nHashTableLookups"] / max(1, c["totalReads"]), 3),
-                     "hash_entries_per_lookup": round(c["nHashEntriesProbed"] / max(1, c["nHashTableLookups"]), 3),
-                     "lv_locations": round(c["lvCalls"] / max(1, c["totalReads"]), 3),
-                     "ag_locations": round(c["affineGapCalls"] / max(1, c["totalReads"]), 3),
-                     "aligned_frac": round((c["singleHits"] + c["multiHits"]) / max(1, c["totalReads"]), 5)},
-        "setup": setup,
-    }
 
-    # ---- seed-lookup phase in isolation (rank 0, N=1) ----
+class RefContext:
+    """The unmodified reference (oracle/_ref) over the same index, written out once in SNAP's own directory format into tmpfs with its
+    pages interleaved over the NUMA nodes, and mapped (GenomeIndex::loadFromDirectory(map = true), what stock `-map` does)."""
+
+    def __init__(self, idx):
+        from oracle import reflib
+        self.reflib = reflib
+        self.nodes = reflib.numa_interleave()
+        t0 = time.time()
+        self.dir = export_index_for_reference(idx)
+        self.export_s = time.time() - t0
+        t0 = time.time()
+        self.ridx = {"stock": reflib.RefIndex(self.dir, "stock", map_files=True, prefetch=False)}
+        self.load_s = time.time() - t0
+        if reflib.available_v3():
+            self.ridx["v3"] = reflib.RefIndex(self.dir, "v3", map_files=True, prefetch=False)
+        self.cores = os.cpu_count() or 1
+
+    def host(self):
+        sockets = set()
+        model = ""
+        try:
+            for l in open("/proc/cpuinfo"):
+                if l.startswith("physical id"):
+                    sockets.add(l.split(":")[1].strip())
+                elif l.startswith("model name") and not model:
+                    model = l.split(":")[1].strip()
+        except Exception:
+            pass
+        return {"cpu": model, "hw_threads": self.cores, "sockets": max(1, len(sockets)), "numa_nodes_interleaved": self.nodes,
+                "pinning": "none (threads unpinned; index pages interleaved over the memory nodes with MPOL_INTERLEAVE, = numactl --interleave=all)",
+                "index": "ours, exported to SNAP's directory format in tmpfs (%.0f s), mapped like stock -map (%.1f s)" % (self.export_s, self.load_s)}
+
+    def run(self, name, batch, threads, build="stock", reps=1):
+        """(records, counters, seconds for `reps` passes)"""
+        wl = WORKLOADS[name]
+        rl = self.reflib
+        if wl["kind"] == "paired":
+            p, pp = rl.default_params(**wl["kw"]), rl.default_paired_params(**wl["pkw"])
+            return rl.paired_align_mt(self.ridx[build], p, pp, batch, threads, reps)
+        return rl.align_mt(self.ridx[build], rl.default_params(**wl["kw"]), batch, threads, reps)
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def cpu_leg(ref, args, name, host_batch, records, min_seconds=3.0, builds=("stock",), one_thread=False):
+    """The reference on all host threads over a bounded sample of the step's reads: its rate, and its records against the engine's
+    for the same reads (full-size parity: 3 Gbp index, ~1 M reads / 0.5 M pairs)."""
+    wl = WORKLOADS[name]
+    paired = wl["kind"] == "paired"
+    n = min(args.cpu_sample_reads, host_batch.n)
+    n -= n % 2
+    sample = host_batch.slice(0, n)
+    units = n // 2 if paired else n
+    ref.run(name, sample.slice(0, min(n, 20000)), ref.cores)               # warm the page cache / TLB
+    want, ctr, secs1 = ref.run(name, sample, ref.cores)
+    reps = int(max(1, min(40, np.ceil(min_seconds / max(secs1, 1e-3)))))
+    _, _, secs = ref.run(name, sample, ref.cores, reps=reps) if reps > 1 else (None, None, secs1)
+    out = {"value": round(n * reps / secs, 1), "unit": "reads/s", "cores": ref.cores, "kind": "reference",
+           "sample": "%d of the step's %d %s x %d passes = %.1f s, %d threads started before the clock, oracle/_ref %s (aligner only, no SAM output)"
+                     % (units, host_batch.n // (2 if paired else 1), "pairs" if paired else "reads", reps, secs, ref.cores,
+                        "ChimericPairedEndAligner(IntersectingPairedEndAligner)::align" if paired else "BaseAligner::AlignRead"),
+           "seconds": round(secs, 3), "build": "-O3 -std=c++98 -msse (the reference Makefile's flags)",
+           "lv_per_read": round(ctr["lvCalls"] / n, 3), "ag_per_read": round(ctr["affineGapCalls"] / n, 3)}
+    if "v3" in builds and "v3" in ref.ridx:
+        ref.run(name, sample.slice(0, min(n, 20000)), ref.cores, build="v3")
+        _, _, s3 = ref.run(name, sample, ref.cores, build="v3", reps=reps)
+        out["value_march_x86_64_v3"] = round(n * reps / s3, 1)
+        out["build_v3"] = "-O3 -march=x86-64-v3 (stands in for -march=native: the build host is not the bench host)"
+    if one_thread:
+        m = min(n, 20000)
+        _, _, s1 = ref.run(name, sample.slice(0, m), 1)
+        out["value_1thread"] = round(m / s1, 1)
     if paired:
-        out["per_read"]["aligned_as_pair_frac"] = None
-    if rank == 0 and not args.no_seed_phase and not paired:
-        try:
-            out["seed_phase"] = seed_phase(args, idx, batches, device, peak, peak_src)
-        except Exception as e:  # pragma: no cover
-            out["seed_phase"] = {"error": str(e)[:200]}
-
-    # ---- FASTQ ingest in isolation (rank 0) ----
-    if rank == 0 and not args.no_seed_phase and not paired:
-        try:
-            out["ingest_phase"] = ingest_phase(args, host_batches[0], device, peak, peak_src)
-        except Exception as e:  # pragma: no cover
-            out["ingest_phase"] = {"error": str(e)[:200]}
-
-    # ---- CPU baseline: the unmodified reference on the host cores, bounded sample (rank 0, N=1 only) ----
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            got0, _ = al.align(host_batches[0])          # the engine's records for the reads the reference is about to be timed on
-            out["cpu_baseline"] = cpu_baseline(args, idx, host_batches[0], check_against=got0)
-            if paired:
-                out["per_read"]["aligned_as_pair_frac"] = out["cpu_baseline"].pop("aligned_as_pair_frac", None)
-        except Exception as e:  # pragma: no cover
-            out["cpu_baseline"] = {"error": str(e)[:300]}
-
-    # ---- output stage in isolation (rank 0, N=1; SURVEY 8f N1, first device form).  The formatter was verified on the GPU in the
-    #      last minutes of its round and has not been through a full-size run yet, so it gets a process of its own: whatever happens
-    #      there, this process still prints its line.  (Our aligner's arena is released first to leave the child room in HBM.) ----
-    if rank == 0 and world == 1 and not args.no_seed_phase:
-        try:
-            al.close()
-            cmd = [sys.executable, os.path.abspath(__file__), "--phase", "sam", "--workload", args.workload, "--genome-mbp", str(args.genome_mbp),
-                   "--batch-reads", str(args.batch_reads), "--steps", "1", "--warmup", "0"]
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-            lines = [l for l in r.stdout.strip().split("\n") if l.startswith("{")]
-            out["sam_phase"] = json.loads(lines[-1]) if lines else {"error": "child exited %d: %s" % (r.returncode, r.stderr[-300:])}
-        except Exception as e:  # pragma: no cover
-            out["sam_phase"] = {"error": str(e)[:300]}
-
-    if rank == 0:
-        emit(json.dumps(out))
-    try:
-        al.close()
-        idx.close()
-    except Exception:  # pragma: no cover
-        pass
-    if world > 1:
-        dist.destroy_process_group()
+        out["aligned_as_pair_frac"] = round(float(want["alignedAsPair"].mean()), 5)
+    parity = None
+    if records is not None:
+        differing, skipped = count_differing(want, records[:units], paired)
+        parity = {("pairs_compared" if paired else "reads_compared"): units, "differing": differing, "n_skipped": skipped,
+                  "skip_rule": ("none; mapq / scorePriorToClipping of ends reported NotFound are zeroed on both sides (uninitialised in the reference)" if paired else
+                                "records BOTH sides report NotFound (the reference leaves their other fields uninitialised)")}
+    out["parity_vs_reference"] = parity
+    return out
 
 
 def seed_phase(args, idx, batches, device, peak, peak_src):
@@ -531,27 +615,6 @@ def sam_phase(args, idx, host_batch, results, paired):
     return out
 
 
-def run_sam_phase_child(args):
-    """`bench.py --phase sam`: builds the same workload, aligns one batch and prints sam_phase's JSON object (parent: run_ours)."""
-    import torch
-    from snap_b200 import engine, synth
-    device = torch.device("cuda", 0)
-    torch.cuda.set_device(device)
-    bases, starts, contig_len, idx, batches, setup = build_workload(args, device, 0, 1)
-    paired = args.workload == "paired"
-    B = args.batch_reads
-    if paired:
-        B = (B // 2) * 2
-        al = engine.PairedAligner(idx, engine.default_params(**PAIRED_KW), engine.default_paired_params(**PAIRED_PKW), max_batch_pairs=B // 2)
-    else:
-        al = engine.SingleAligner(idx, engine.default_params(maxDist=MAX_DIST), max_batch_reads=B)
-    rb, rq, ro, rl = batches[0][:4]
-    hb = synth.ReadBatch(rb.cpu().numpy(), rq.cpu().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32))
-    got, _ = al.align(hb)
-    al.close()
-    emit(json.dumps(sam_phase(args, idx, hb, got, paired)))
-
-
 def sam_cpu_reference(idx, sample, res, paired, n_cpu=20000):
     """reads/s of the reference's SAMFormat::computeCigarString (both overloads; the dominant cost of its writer) on one host thread."""
     from oracle import reflib
@@ -597,6 +660,7 @@ def sam_cpu_reference(idx, sample, res, paired, n_cpu=20000):
         shutil.rmtree(d, ignore_errors=True)
 
 
+
 def export_index_for_reference(idx):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     d = tempfile.mkdtemp(prefix="snapidx_", dir=base)
@@ -605,10 +669,10 @@ def export_index_for_reference(idx):
 
 
 def count_differing(want, got, paired):
-    """Result records of the engine vs the reference's for the same reads, bytewise (doubles bit for bit), vectorised.  Same
-    exclusions as tests/conftest.py: single-end records both sides report NotFound (the reference leaves the rest
-    uninitialised on its early returns); mapq / scorePriorToClipping of a paired end reported NotFound (copied from an
-    unwritten stack object by ChimericPairedEndAligner)."""
+    """(differing, skipped): result records of the engine vs the reference's for the same reads, bytewise (doubles bit for bit),
+    vectorised.  Same exclusions as tests/conftest.py: single-end records BOTH sides report NotFound are skipped (the reference leaves
+    the rest uninitialised on its early returns) and counted; mapq / scorePriorToClipping of a paired end reported NotFound are zeroed
+    on both sides (copied from an unwritten stack object by ChimericPairedEndAligner), nothing is skipped."""
     w, g = want.copy(), np.asarray(got).view(want.dtype).copy()
     if paired:
         for arr in (w, g):
@@ -620,45 +684,52 @@ def count_differing(want, got, paired):
         skip = (w["status"] == 0) & (g["status"] == 0)
     wb = w.view(np.uint8).reshape(len(w), -1)
     gb = g.view(np.uint8).reshape(len(g), -1)
-    return int(((wb != gb).any(axis=1) & ~skip).sum())
+    return int(((wb != gb).any(axis=1) & ~skip).sum()), int(skip.sum())
 
 
-def cpu_baseline(args, idx, host_batch, check_against):
-    """oracle/_ref (the compiled, unmodified reference) on all host cores over a bounded sample of the same reads.  The
-    reference's records for the sample are also compared with the engine's (`check_against`): full-size parity evidence."""
+def fastq_text(host_batch, prefix=b"r"):
+    """FASTQ text of a batch of fixed-length reads, vectorised (ids r00000000 ...)."""
+    n = host_batch.n
+    L = READ_LEN
+    rec = 2 + 8 + 1 + L + 3 + L + 1
+    txt = np.empty((n, rec), dtype=np.uint8)
+    txt[:, 0] = ord("@"); txt[:, 1] = prefix[0]
+    ids = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        txt[:, 2 + 7 - d] = (ids // 10 ** d % 10 + 48).astype(np.uint8)
+    txt[:, 10] = 10
+    txt[:, 11:11 + L] = host_batch.bases.reshape(n, L)
+    txt[:, 11 + L] = 10; txt[:, 12 + L] = ord("+"); txt[:, 13 + L] = 10
+    txt[:, 14 + L:14 + 2 * L] = host_batch.quals.reshape(n, L)
+    txt[:, 14 + 2 * L] = 10
+    return txt.reshape(-1)
+
+
+def cli_crosscheck(ref, host_batches, max_dist, threads):
+    """Stock `oracle/_ref/snap-aligner single <index> reads.fq -t N -d D` (no -o) over the same reads as a FASTQ file in tmpfs:
+    the reference's own "Reads/s" (AlignerContext::printStats, AlignerContext.cpp:491-540; excludes the index load, :420)."""
+    import re
     from oracle import reflib
-    if not reflib.available():
-        return {"error": "oracle/_ref not built"}
-    d = export_index_for_reference(idx)
-    try:
-        t0 = time.time()
-        ridx = reflib.RefIndex(d)
-        load_s = time.time() - t0
-        cores = os.cpu_count() or 1
-        n = min(args.cpu_sample_reads, host_batch.n)
-        sample = host_batch.slice(0, n)
-        if args.workload == "paired":
-            n -= n % 2
-            sample = host_batch.slice(0, n)
-            p, pp = reflib.default_params(**PAIRED_KW), reflib.default_paired_params(**PAIRED_PKW)
-            reflib.paired_align_mt(ridx, p, pp, sample.slice(0, min(n, 20000)), cores)
-            res, ctr, secs = reflib.paired_align_mt(ridx, p, pp, sample, cores)
-            parity = None if check_against is None else {"pairs_compared": n // 2, "differing": count_differing(res, check_against[:n // 2], True)}
-            return {"parity_vs_reference": parity, "value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
-                    "sample": "%d of the step's %d pairs, %d threads, oracle/_ref ChimericPairedEndAligner(IntersectingPairedEndAligner)::align "
-                              "(aligner only, no SAM output); index = ours exported to SNAP's directory format (load %.1fs)"
-                              % (n // 2, host_batch.n // 2, cores, load_s),
-                    "seconds": round(secs, 3), "aligned_as_pair_frac": round(float(res["alignedAsPair"].mean()), 5)}
-        p = reflib.default_params(maxDist=MAX_DIST)
-        reflib.align_mt(ridx, p, sample.slice(0, min(n, 20000)), cores)          # warm the page cache / TLB
-        res, ctr, secs = reflib.align_mt(ridx, p, sample, cores)
-        parity = None if check_against is None else {"reads_compared": n, "differing": count_differing(res, check_against[:n], False)}
-        return {"parity_vs_reference": parity, "value": round(n / secs, 1), "unit": "reads/s", "cores": cores, "kind": "reference",
-                "sample": "%d of the step's %d reads, %d threads, oracle/_ref BaseAligner::AlignRead (aligner only, no SAM output); "
-                          "index = ours exported to SNAP's directory format (load %.1fs)" % (n, host_batch.n, cores, load_s),
-                "seconds": round(secs, 3), "lv_per_read": round(ctr["lvCalls"] / n, 3), "ag_per_read": round(ctr["affineGapCalls"] / n, 3)}
-    finally:
-        shutil.rmtree(d, ignore_errors=True)
+    fq = os.path.join(ref.dir, "reads.fq")
+    with open(fq, "wb") as f:
+        for hb in host_batches:
+            f.write(fastq_text(hb).tobytes())
+    n = sum(hb.n for hb in host_batches)
+    cmd = [reflib.SNAP_ALIGNER, "single", ref.dir, fq, "-t", str(threads), "-d", str(max_dist)]
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    wall = time.time() - t0
+    os.unlink(fq)
+    if r.returncode != 0:
+        return {"error": "snap-aligner exited %d: %s" % (r.returncode, (r.stdout + r.stderr)[-300:])}
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    k = [i for i, l in enumerate(lines) if "Reads/s" in l]
+    if not k or k[-1] + 1 >= len(lines):
+        return {"error": "no stats line in snap-aligner's output", "tail": r.stdout[-300:]}
+    toks = [t for t in re.sub(r"\([^)]*\)", " ", lines[k[-1] + 1]).split() if re.fullmatch(r"[0-9,]+", t)]
+    return {"command": " ".join(["snap-aligner"] + cmd[1:]).replace(ref.dir, "<index>"), "reads": n, "reads_per_s": int(toks[-2].replace(",", "")),
+            "time_in_aligner_s": int(toks[-1].replace(",", "")), "total_reads_reported": int(toks[0].replace(",", "")), "wall_s_incl_index_load": round(wall, 1),
+            "note": "includes FASTQ reading by the reference's own supplier threads; harness rate above is aligner only"}
 
 
 def run_reference(args):
@@ -667,61 +738,194 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    from snap_b200 import engine, synth
-    from oracle import reflib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl reference: the workload's index is generated on the GPU; no CUDA device")
-    device = torch.device("cuda", 0)
-    torch.cuda.set_device(device)
     W, K = args.warmup, args.steps
     n = args.cpu_sample_reads
     saved = args.batch_reads
     args.batch_reads = n
-    bases, starts, contig_len, idx, batches, setup = build_workload(args, device, 0, 1)
+    os.environ.pop("WORLD_SIZE", None); os.environ["RANK"] = "0"; os.environ["LOCAL_RANK"] = "0"      # rank 0 alone: no process group
+    c = build_context(args)
+    name = args.workload
+    wl = WORKLOADS[name]
+    paired = wl["kind"] == "paired"
+    dev_batches = make_batches(c, args, wl["kind"], W + K)
+    hb = [to_host_batch(b, pinned=False) for b in dev_batches]
+    del dev_batches
     args.batch_reads = saved
-    d = export_index_for_reference(idx)
-    idx.close()
-    del bases
+    ref = RefContext(c.idx)
+    c.idx.close()
+    del c.bases
     torch.cuda.empty_cache()
     try:
-        ridx = reflib.RefIndex(d)
-        cores = os.cpu_count() or 1
-        p = reflib.default_params(maxDist=MAX_DIST)
-        hb = []
-        for b in range(W + K):
-            rb, rq, ro, rl = batches[b][:4]
-            hb.append(synth.ReadBatch(rb.cpu().numpy(), rq.cpu().numpy(), ro.cpu().numpy().astype(np.uint64), rl.cpu().numpy().astype(np.uint32)))
-        paired = args.workload == "paired"
-        if paired:
-            p, pp = reflib.default_params(**PAIRED_KW), reflib.default_paired_params(**PAIRED_PKW)
-            run = lambda batch: reflib.paired_align_mt(ridx, p, pp, batch, cores)
-        else:
-            run = lambda batch: reflib.align_mt(ridx, p, batch, cores)
+        cores = ref.cores
         for b in range(W):
-            run(hb[b])
+            ref.run(name, hb[b], cores)
         total_s = 0.0
         aligned = 0
         for k in range(K):
-            res, ctr, secs = run(hb[W + k])
+            res, ctr, secs = ref.run(name, hb[W + k], cores)
             total_s += secs
             aligned += int((res["status"] != 0).sum())
         value = n * K / total_s
-        sample = "%d reads per step (bounded sample of the %d-read step), %d threads" % (n, saved, cores)
+        extra = {}
+        if "v3" in ref.ridx:
+            ref.run(name, hb[0], cores, build="v3")
+            s3 = sum(ref.run(name, hb[W + k], cores, build="v3")[2] for k in range(min(K, 5)))
+            extra["value_march_x86_64_v3"] = round(n * min(K, 5) / s3, 1)
+        m = min(n, 20000)
+        extra["value_1thread"] = round(m / ref.run(name, hb[0].slice(0, m), 1)[2], 1)
+        if not paired and not args.no_cli_crosscheck:
+            try:
+                extra["cli_crosscheck"] = cli_crosscheck(ref, hb[W:W + min(K, 4)], wl["max_dist"], cores)
+            except Exception as e:
+                extra["cli_crosscheck"] = {"error": str(e)[:200]}
+        sample = ("%d %s per step (bounded sample of the %d-read step), %d threads started before the clock, stock build (-O3 -msse)"
+                  % (n // 2 if paired else n, "pairs" if paired else "reads", saved, cores))
         out = {"impl": "reference", "metric": "aligned reads/s", "value": round(value, 1), "unit": "reads/s", "n_gpus": args.gpus, "steps": K,
                "warmup": W, "ms_per_step": round(total_s / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
                "config": {"workload": ("snap paired (stock options), 2 x %d x %d bp synthetic FR pairs per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
                                        % (n // 2, READ_LEN, args.genome_mbp, SEED_LEN, PAIRED_MAX_DIST)) if paired else
                                       ("snap single, %d x %d bp synthetic reads per step vs %d Mbp synthetic reference (24 contigs), seed %d, maxDist %d"
-                                       % (n, READ_LEN, args.genome_mbp, SEED_LEN, MAX_DIST)), "read_len": READ_LEN, "genome_mbp": args.genome_mbp,
-                          "seed_len": SEED_LEN, "max_dist": MAX_DIST},
-               "cpu_baseline": {"value": round(value, 1), "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample},
+                                       % (n, READ_LEN, args.genome_mbp, SEED_LEN, wl["max_dist"])), "read_len": READ_LEN, "genome_mbp": args.genome_mbp,
+                          "seed_len": SEED_LEN, "max_dist": wl["max_dist"]},
+               "cpu_baseline": dict({"value": round(value, 1), "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample, "host": ref.host()}, **extra),
                "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "aligned_frac": round(aligned / (n * K), 5),
                "note": "unmodified amplab/snap aligner (BaseAligner::AlignRead / ChimericPairedEndAligner::align) via oracle/_ref on host cores; index = GPU-built, exported to SNAP's format"}
         emit(json.dumps(out))
     finally:
-        shutil.rmtree(d, ignore_errors=True)
+        ref.close()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    c = build_context(args)
+    rank, world = c.rank, c.world
+    W, K = args.warmup, args.steps
+    headline = args.workload
+    failures = []
+
+    # ---- the headline workload: exactly K timed steps after W warm-ups ----
+    kind = WORKLOADS[headline]["kind"]
+    t0 = time.time()
+    batches = {kind: make_batches(c, args, kind, W + K)}
+    torch.cuda.synchronize()
+    c.setup["reads_s"] = round(time.time() - t0, 2)
+    head = run_workload(c, args, headline, batches[kind], W, K, sample_clocks=True)
+    clocks = head.pop("_clocks")
+
+    # ---- the other BASELINE configs, each to the same bar (device-resident + e2e + roofline; parity below): configs[2] / [4] paired,
+    #      configs[3] -G -d 20 and -ne -d 20.  Bounded step counts of their own so the default run stays within minutes. ----
+    phases = {}
+    if not args.only_headline:
+        Wp, Kp = 3, max(3, min(K, 5))
+        for name in ("paired", "ag_d20", "ne_d20", "single"):
+            if name == headline:
+                continue
+            k2 = WORKLOADS[name]["kind"]
+            if k2 not in batches:
+                batches[k2] = make_batches(c, args, k2, Wp + Kp)
+            elif len(batches[k2]) < Wp + Kp:
+                batches[k2] += make_batches(c, args, k2, Wp + Kp)[len(batches[k2]):]
+            phases[name] = run_workload(c, args, name, batches[k2], Wp, Kp)
+            phases[name].pop("_clocks")
+    batch0 = {k: v[0] for k, v in batches.items()}
+    del batches
+    torch.cuda.empty_cache()
+
+    paired = kind == "paired"
+    B = args.batch_reads
+    out = {
+        "metric": "aligned reads/s", "value": head["value"], "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 (+f64 match probabilities)", "data": "synthetic",
+        "config": {"workload": ("snap paired (stock options), 2 x %d x %d bp synthetic FR pairs (insert N(400,40)) per step per GPU vs %d Mbp "
+                                "synthetic reference (24 contigs), seed %d, maxDist %d, IntersectingPairedEndAligner + chimeric single-end fallback "
+                                "(BASELINE configs[2] shape)" % (B // 2, READ_LEN, args.genome_mbp, SEED_LEN, PAIRED_MAX_DIST)) if paired else
+                               ("snap single, %d x %d bp synthetic reads per step per GPU vs %d Mbp synthetic reference (24 contigs), "
+                                "seed %d, maxDist %d, affine gap on (BASELINE configs[1] shape)" % (B, READ_LEN, args.genome_mbp, SEED_LEN, WORKLOADS[headline]["max_dist"])),
+                   "reads_per_step": B * world, "read_len": READ_LEN, "genome_mbp": args.genome_mbp, "seed_len": SEED_LEN,
+                   "max_dist": WORKLOADS[headline]["max_dist"], "repeat_frac": args.repeat_frac,
+                   "parallelism": "read-sharded x%d, index replicated per GPU" % world,
+                   "l2": "each step uses fresh reads (%.0f MB/step > L2) against a %.1f GB index" % (B * 2 * READ_LEN / 1e6, c.setup["index_hbm_gb"])},
+        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "roofline": head["roofline"], "per_read": head["per_read"],
+        "setup": c.setup, "csrc_sha16": csrc_sha16(),
+    }
+    for name, ph in phases.items():
+        key = {"paired": "paired_phase", "single": "single_phase"}.get(name)
+        if key:
+            out[key] = ph
+        else:
+            out.setdefault("ag_forced_phase", {})[name] = ph
+
+    # ---- seed-lookup phase and FASTQ ingest in isolation (rank 0) ----
+    if rank == 0 and not args.no_seed_phase:
+        single_batch = batch0.get("single")
+        if single_batch is not None:
+            try:
+                out["seed_phase"] = seed_phase(args, c.idx, [single_batch], c.device, c.peak, c.peak_src)
+            except Exception as e:
+                out["seed_phase"] = {"error": str(e)[:300]}
+                failures.append("seed_phase: " + str(e)[:200])
+            try:
+                out["ingest_phase"] = ingest_phase(args, to_host_batch(single_batch, pinned=False), c.device, c.peak, c.peak_src)
+            except Exception as e:
+                out["ingest_phase"] = {"error": str(e)[:300]}
+                failures.append("ingest_phase: " + str(e)[:200])
+
+    # ---- CPU reference: rate on the host cores AND full-size parity of every workload above (rank 0, N=1 only).  A mismatch or an
+    #      exception here fails the run (exit code 3 after the line is printed). ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = None
+        try:
+            ref = RefContext(c.idx)
+            out["cpu_baseline"] = cpu_leg(ref, args, headline, head["_host0"], head["_records"], min_seconds=5.0, builds=("stock", "v3"), one_thread=True)
+            out["cpu_baseline"]["host"] = ref.host()
+            for name, ph in phases.items():
+                ph["cpu_baseline"] = cpu_leg(ref, args, name, ph["_host0"], ph["_records"], min_seconds=2.0)
+            for name, leg in [(headline, out["cpu_baseline"])] + [(n2, p2["cpu_baseline"]) for n2, p2 in phases.items()]:
+                par = leg.get("parity_vs_reference")
+                if not par or par["differing"] != 0:
+                    failures.append("parity: workload %s: %s" % (name, par))
+            if "paired" in phases:
+                phases["paired"]["per_read"]["aligned_as_pair_frac"] = phases["paired"]["cpu_baseline"].pop("aligned_as_pair_frac", None)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            out.setdefault("cpu_baseline", {})["error"] = str(e)[:300]
+            failures.append("cpu_baseline: " + str(e)[:200])
+        finally:
+            if ref is not None:
+                ref.close()
+    # ---- output stage in isolation (rank 0, N=1): the headline's first batch and the engine's own records for it ----
+    if rank == 0 and world == 1 and not args.no_seed_phase and not args.no_sam_phase and head.get("_records") is not None:
+        try:
+            out["sam_phase"] = sam_phase(args, c.idx, head["_host0"], head["_records"], paired)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            out["sam_phase"] = {"error": str(e)[:300]}
+            failures.append("sam_phase: " + str(e)[:200])
+
+    for ph in [head] + list(phases.values()):
+        for k in ("_records", "_host0", "_host_batches"):
+            ph.pop(k, None)
+    if failures:
+        out["failures"] = failures
+    if rank == 0:
+        emit(json.dumps(out))
+    try:
+        c.idx.close()
+    except Exception:  # pragma: no cover
+        pass
+    if world > 1:
+        dist.destroy_process_group()
+    if failures:
+        sys.stderr.write("bench.py: FAILED: %s\n" % "; ".join(failures))
+        sys.exit(3)
 
 
 _REAL_STDOUT = None
@@ -742,9 +946,7 @@ def main():
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)                      # C-level stdout of this process (and its children) -> stderr
     sys.stdout = sys.stderr
-    if args.phase == "sam":
-        run_sam_phase_child(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

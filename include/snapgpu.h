@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SNAPGPU_ABI_VERSION 1
+#define SNAPGPU_ABI_VERSION 2   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results` */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };

@@ -40,6 +40,8 @@
 #include <string.h>
 #include <stdio.h>
 #include <time.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 #include "../include/snapgpu.h"
 
@@ -60,14 +62,57 @@ int ref_init(void)
     return 0;
 }
 
-void *ref_index_load(const char *dir)
+void *ref_index_load_ex(const char *dir, int map, int prefetch)
 {
     ref_init();
-    GenomeIndex *index = GenomeIndex::loadFromDirectory((char *)dir, /*map*/false, /*prefetch*/false);
+    GenomeIndex *index = GenomeIndex::loadFromDirectory((char *)dir, map != 0, prefetch != 0);
     if (NULL != index) {
         g_index = index;
     }
     return index;
+}
+
+void *ref_index_load(const char *dir)
+{
+    return ref_index_load_ex(dir, /*map*/0, /*prefetch*/0);
+}
+
+/*
+ * Page placement for the CPU baseline.  The index is tens of GB touched at random by every thread; written (tmpfs) or read in
+ * (BigAlloc) by ONE thread it lands on that thread's NUMA node and all other sockets go through the interconnect -- measured
+ * 0.67 vs 3.1 M reads/s on two boxes with the same binary.  MPOL_INTERLEAVE on the calling thread (inherited by the threads it
+ * creates; obeyed by tmpfs pages it instantiates) spreads the pages round-robin, which is what `numactl --interleave=all
+ * snap-aligner ...` does.  Returns the number of memory nodes interleaved over (1 = nothing to do), or -1 if the kernel refused.
+ */
+int ref_numa_interleave(void)
+{
+    int nNodes = 0;
+    for (int i = 0; i < 64; i++) {
+        char path[64];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/meminfo", i);
+        FILE *f = fopen(path, "r");
+        if (!f) continue;
+        fclose(f);
+        nNodes = i + 1;
+    }
+    if (nNodes <= 1) return 1;
+    unsigned long mask = 0;
+    int n = 0;
+    for (int i = 0; i < nNodes; i++) {
+        char path[64];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/meminfo", i);
+        FILE *f = fopen(path, "r");
+        if (!f) continue;
+        // nodes without memory (MemTotal 0) must not be in the mask
+        char line[256]; unsigned long long kb = 0; int node = 0;
+        while (fgets(line, sizeof(line), f)) { if (2 == sscanf(line, "Node %d MemTotal: %llu", &node, &kb)) break; }
+        fclose(f);
+        if (kb > 0) { mask |= 1UL << i; n++; }
+    }
+    if (n <= 1) return 1;
+    const int MPOL_INTERLEAVE_ = 3;
+    long rc = syscall(SYS_set_mempolicy, MPOL_INTERLEAVE_, &mask, (unsigned long)(8 * sizeof(mask) + 1));
+    return rc == 0 ? n : -1;
 }
 
 int ref_index_info(void *vidx, snapgpu_index_info *info)
@@ -605,22 +650,31 @@ struct MTArg {
     RefSingle *rs; _int64 begin, end;
     const char *bases; const char *quals; const _uint64 *offsets; const unsigned *lens;
     snapgpu_single_result *results; snapgpu_counters ctr;
+    pthread_barrier_t *start; int reps;
 };
 
 static void *mt_main(void *v)
 {
     MTArg *a = (MTArg *)v;
-    align_range(a->rs, a->begin, a->end, a->bases, a->quals, a->offsets, a->lens, a->results, &a->ctr);
+    pthread_barrier_wait(a->start);              // the clock starts when every thread exists and is waiting here
+    for (int r = 0; r < a->reps; r++) {
+        if (r > 0) memset(&a->ctr, 0, sizeof(a->ctr));
+        align_range(a->rs, a->begin, a->end, a->bases, a->quals, a->offsets, a->lens, a->results, &a->ctr);
+    }
     return NULL;
 }
 
-double ref_single_align_mt(void *vidx, const snapgpu_params *p, int nThreads, _int64 n, const char *bases, const char *quals,
-                           const _uint64 *offsets, const unsigned *lens, snapgpu_single_result *results, snapgpu_counters *counters)
+double ref_single_align_mt_reps(void *vidx, const snapgpu_params *p, int nThreads, int reps, _int64 n, const char *bases, const char *quals,
+                                const _uint64 *offsets, const unsigned *lens, snapgpu_single_result *results, snapgpu_counters *counters)
 {
     if (nThreads < 1) nThreads = 1;
+    if (reps < 1) reps = 1;
     MTArg *args = new MTArg[nThreads];
     pthread_t *threads = new pthread_t[nThreads];
+    pthread_barrier_t start;
+    pthread_barrier_init(&start, NULL, nThreads + 1);
     for (int t = 0; t < nThreads; t++) {
+        args[t].start = &start; args[t].reps = reps;
         args[t].rs = (RefSingle *)ref_single_create(vidx, p);
         args[t].begin = n * t / nThreads;
         args[t].end = n * (t + 1) / nThreads;
@@ -629,10 +683,12 @@ double ref_single_align_mt(void *vidx, const snapgpu_params *p, int nThreads, _i
         memset(&args[t].ctr, 0, sizeof(args[t].ctr));
     }
     struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < nThreads; t++) pthread_create(&threads[t], NULL, mt_main, &args[t]);
+    pthread_barrier_wait(&start);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < nThreads; t++) pthread_join(threads[t], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    pthread_barrier_destroy(&start);
     for (int t = 0; t < nThreads; t++) {
         if (counters) {
             _int64 *dst = (_int64 *)counters;
@@ -644,6 +700,12 @@ double ref_single_align_mt(void *vidx, const snapgpu_params *p, int nThreads, _i
     delete[] args;
     delete[] threads;
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+double ref_single_align_mt(void *vidx, const snapgpu_params *p, int nThreads, _int64 n, const char *bases, const char *quals,
+                           const _uint64 *offsets, const unsigned *lens, snapgpu_single_result *results, snapgpu_counters *counters)
+{
+    return ref_single_align_mt_reps(vidx, p, nThreads, 1, n, bases, quals, offsets, lens, results, counters);
 }
 
 /*
@@ -774,23 +836,32 @@ struct MTPairedArg {
     void *rp; _int64 begin, end;
     const char *bases; const char *quals; const _uint64 *offsets; const unsigned *lens;
     snapgpu_paired_result *results; _int64 nLV, nAG; int rc;
+    pthread_barrier_t *start; int reps;
 };
 
 static void *mt_paired_main(void *v)
 {
     MTPairedArg *a = (MTPairedArg *)v;
-    a->rc = ref_paired_align(a->rp, a->end - a->begin, a->bases, a->quals, a->offsets + 2 * a->begin, a->lens + 2 * a->begin,
-                             a->results + a->begin, &a->nLV, &a->nAG);
+    pthread_barrier_wait(a->start);
+    for (int r = 0; r < a->reps && !a->rc; r++) {
+        a->nLV = a->nAG = 0;
+        a->rc = ref_paired_align(a->rp, a->end - a->begin, a->bases, a->quals, a->offsets + 2 * a->begin, a->lens + 2 * a->begin,
+                                 a->results + a->begin, &a->nLV, &a->nAG);
+    }
     return NULL;
 }
 
-double ref_paired_align_mt(void *vidx, const snapgpu_params *p, const snapgpu_paired_params *pp, int nThreads, _int64 nPairs, const char *bases,
-                           const char *quals, const _uint64 *offsets, const unsigned *lens, snapgpu_paired_result *results, _int64 *nLV, _int64 *nAG)
+double ref_paired_align_mt_reps(void *vidx, const snapgpu_params *p, const snapgpu_paired_params *pp, int nThreads, int reps, _int64 nPairs, const char *bases,
+                                const char *quals, const _uint64 *offsets, const unsigned *lens, snapgpu_paired_result *results, _int64 *nLV, _int64 *nAG)
 {
     if (nThreads < 1) nThreads = 1;
+    if (reps < 1) reps = 1;
     MTPairedArg *args = new MTPairedArg[nThreads];
     pthread_t *threads = new pthread_t[nThreads];
+    pthread_barrier_t start;
+    pthread_barrier_init(&start, NULL, nThreads + 1);
     for (int t = 0; t < nThreads; t++) {
+        args[t].start = &start; args[t].reps = reps;
         args[t].rp = ref_paired_create(vidx, p, pp);
         args[t].begin = nPairs * t / nThreads;
         args[t].end = nPairs * (t + 1) / nThreads;
@@ -798,10 +869,12 @@ double ref_paired_align_mt(void *vidx, const snapgpu_params *p, const snapgpu_pa
         args[t].results = results; args[t].nLV = args[t].nAG = 0; args[t].rc = 0;
     }
     struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < nThreads; t++) pthread_create(&threads[t], NULL, mt_paired_main, &args[t]);
+    pthread_barrier_wait(&start);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < nThreads; t++) pthread_join(threads[t], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    pthread_barrier_destroy(&start);
     double secs = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     for (int t = 0; t < nThreads; t++) {
         if (nLV) *nLV += args[t].nLV;
@@ -812,6 +885,12 @@ double ref_paired_align_mt(void *vidx, const snapgpu_params *p, const snapgpu_pa
     delete[] args;
     delete[] threads;
     return secs;
+}
+
+double ref_paired_align_mt(void *vidx, const snapgpu_params *p, const snapgpu_paired_params *pp, int nThreads, _int64 nPairs, const char *bases,
+                           const char *quals, const _uint64 *offsets, const unsigned *lens, snapgpu_paired_result *results, _int64 *nLV, _int64 *nAG)
+{
+    return ref_paired_align_mt_reps(vidx, p, pp, nThreads, 1, nPairs, bases, quals, offsets, lens, results, nLV, nAG);
 }
 
 

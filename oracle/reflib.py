@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_SO = os.path.join(HERE, "_ref", "libsnapref.so")
+REF_SO = os.path.join(HERE, "_ref", "libsnapref.so")                # the reference's own flags (-O3 -msse)
+REF_SO_V3 = os.path.join(HERE, "_ref", "libsnapref_v3.so")          # -O3 -march=x86-64-v3 (second build of the CPU baseline)
 SNAP_ALIGNER = os.path.join(HERE, "_ref", "snap-aligner")
 
 
@@ -93,45 +94,87 @@ def available() -> bool:
 
 
 _lib = None
+_libs = {}
 
 
-def lib():
+def available_v3() -> bool:
+    """The AVX2 build exists and this host can run it."""
+    if not os.path.exists(REF_SO_V3):
+        return False
+    try:
+        flags = open("/proc/cpuinfo").read()
+        return all(f in flags for f in (" avx2", " bmi2", " fma"))
+    except Exception:
+        return False
+
+
+def lib(build: str = "stock"):
+    """build: "stock" (the reference's own flags) or "v3" (-march=x86-64-v3).  Each is its own shared object with its own globals."""
     global _lib
+    if build == "v3":
+        if "v3" not in _libs:
+            if not available_v3():
+                raise RuntimeError("oracle/_ref/libsnapref_v3.so missing or this CPU lacks AVX2")
+            _libs["v3"] = _load(REF_SO_V3)
+        return _libs["v3"]
     if _lib is None:
         if not available():
             raise RuntimeError("oracle/_ref/libsnapref.so missing: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(REF_SO)
-        L.ref_index_load.restype = C.c_void_p
-        L.ref_index_load.argtypes = [C.c_char_p]
-        L.ref_single_create.restype = C.c_void_p
-        L.ref_single_create.argtypes = [C.c_void_p, C.POINTER(Params)]
-        L.ref_single_destroy.argtypes = [C.c_void_p]
-        L.ref_single_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
-        L.ref_single_align_mt.restype = C.c_double
-        L.ref_single_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int64] + [C.c_void_p] * 6
-        L.ref_lookup_seed.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
-        L.ref_wrapped_seed.restype = C.c_uint
-        L.ref_wrapped_seed.argtypes = [C.c_uint, C.c_uint]
-        L.ref_mapq.restype = C.c_int
-        L.ref_mapq.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
-        L.ref_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-        L.ref_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
-        L.ref_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
-        L.ref_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
-        L.ref_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
-        L.ref_ag_cigar_global_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
-        L.ref_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
-        L.ref_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
-        L.ref_write_reads_batch.restype = C.c_int64
-        L.ref_write_reads_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64]
-        L.ref_write_pairs_batch.restype = C.c_int64
-        L.ref_write_pairs_batch.argtypes = L.ref_write_reads_batch.argtypes
-        L.ref_decode_cigar.restype = C.c_int
-        L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
-        L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
-        L.ref_init()
-        _lib = L
+        _lib = _load(REF_SO)
     return _lib
+
+
+def _load(path):
+    L = C.CDLL(path)
+    L.ref_index_load.restype = C.c_void_p
+    L.ref_index_load.argtypes = [C.c_char_p]
+    L.ref_single_create.restype = C.c_void_p
+    L.ref_single_create.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.ref_single_destroy.argtypes = [C.c_void_p]
+    L.ref_single_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    L.ref_single_align_mt.restype = C.c_double
+    L.ref_single_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int64] + [C.c_void_p] * 6
+    L.ref_lookup_seed.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+    L.ref_wrapped_seed.restype = C.c_uint
+    L.ref_wrapped_seed.argtypes = [C.c_uint, C.c_uint]
+    L.ref_mapq.restype = C.c_int
+    L.ref_mapq.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+    L.ref_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.ref_lv_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+    L.ref_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+    L.ref_lv_cigar_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+    L.ref_cigar_lv_batch.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+    L.ref_ag_cigar_global_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+    L.ref_ag_cigar_norm_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+    L.ref_cigar_ag_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+    L.ref_write_reads_batch.restype = C.c_int64
+    L.ref_write_reads_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 9 + [C.c_int64]
+    L.ref_write_pairs_batch.restype = C.c_int64
+    L.ref_write_pairs_batch.argtypes = L.ref_write_reads_batch.argtypes
+    L.ref_decode_cigar.restype = C.c_int
+    L.ref_decode_cigar.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    L.ref_index_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_index_load_ex.restype = C.c_void_p
+    L.ref_index_load_ex.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.ref_numa_interleave.restype = C.c_int
+    L.ref_single_align_mt_reps.restype = C.c_double
+    L.ref_single_align_mt_reps.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 6
+    L.ref_paired_align_mt_reps.restype = C.c_double
+    L.ref_paired_align_mt_reps.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams), C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 7
+    L.ref_paired_create.restype = C.c_void_p
+    L.ref_paired_create.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams)]
+    L.ref_paired_destroy.argtypes = [C.c_void_p]
+    L.ref_paired_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    L.ref_paired_align_mt.restype = C.c_double
+    L.ref_paired_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams), C.c_int, C.c_int64] + [C.c_void_p] * 7
+    L.ref_init()
+    return L
+
+
+def numa_interleave() -> int:
+    """MPOL_INTERLEAVE over all memory nodes for this thread and the threads it creates (see ref_numa_interleave): memory nodes
+    interleaved over, 1 when there is a single node, -1 if refused."""
+    return int(lib().ref_numa_interleave())
 
 
 def _p(a: np.ndarray):
@@ -139,8 +182,11 @@ def _p(a: np.ndarray):
 
 
 class RefIndex:
-    def __init__(self, directory: str):
-        self.handle = lib().ref_index_load(directory.encode())
+    def __init__(self, directory: str, build: str = "stock", map_files: bool = False, prefetch: bool = False):
+        """map_files / prefetch: GenomeIndex::loadFromDirectory's own arguments (stock SNAP defaults to -map -pre)."""
+        self.build = build
+        self.L = lib(build)
+        self.handle = self.L.ref_index_load_ex(directory.encode(), 1 if map_files else 0, 1 if prefetch else 0)
         if not self.handle:
             raise RuntimeError("reference failed to load index " + directory)
         self.directory = directory
@@ -173,11 +219,13 @@ class RefSingleAligner:
             self.handle = None
 
 
-def align_mt(index: RefIndex, params: Params, batch, threads: int):
+def align_mt(index: RefIndex, params: Params, batch, threads: int, reps: int = 1):
+    """All-threads run: the threads exist and wait at a barrier before the clock starts; `reps` passes over the batch inside the
+    timed region (seconds returned are for all of them; counters are those of one pass)."""
     res = np.zeros(batch.n, dtype=RESULT_DTYPE)
     ctr = np.zeros(N_COUNTERS, dtype=np.int64)
-    secs = lib().ref_single_align_mt(index.handle, C.byref(params), threads, batch.n, _p(batch.bases), _p(batch.quals),
-                                     _p(batch.offsets), _p(batch.lens), _p(res), _p(ctr))
+    secs = index.L.ref_single_align_mt_reps(index.handle, C.byref(params), threads, reps, batch.n, _p(batch.bases), _p(batch.quals),
+                                            _p(batch.offsets), _p(batch.lens), _p(res), _p(ctr))
     return res, counters_dict(ctr), float(secs)
 
 
@@ -228,11 +276,7 @@ assert PAIRED_RESULT_DTYPE.itemsize == 200
 
 class RefPairedAligner:
     def __init__(self, index: RefIndex, params: Params, pparams: PairedParams):
-        L = lib()
-        L.ref_paired_create.restype = C.c_void_p
-        L.ref_paired_create.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams)]
-        L.ref_paired_destroy.argtypes = [C.c_void_p]
-        L.ref_paired_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        L = index.L
         self.index = index
         self.handle = L.ref_paired_create(index.handle, C.byref(params), C.byref(pparams))
 
@@ -252,16 +296,13 @@ class RefPairedAligner:
             self.handle = None
 
 
-def paired_align_mt(index: RefIndex, params: Params, pparams: PairedParams, batch, n_threads: int):
-    """All-cores paired run (one aligner stack per thread): (results, {lvCalls, affineGapCalls}, seconds)."""
-    L = lib()
-    L.ref_paired_align_mt.restype = C.c_double
-    L.ref_paired_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams), C.c_int, C.c_int64] + [C.c_void_p] * 7
+def paired_align_mt(index: RefIndex, params: Params, pparams: PairedParams, batch, n_threads: int, reps: int = 1):
+    """All-cores paired run (one aligner stack per thread): (results, {lvCalls, affineGapCalls}, seconds).  `reps` as in align_mt."""
     n = batch.n // 2
     res = np.zeros(n, dtype=PAIRED_RESULT_DTYPE)
     lvag = np.zeros(2, dtype=np.int64)
-    secs = L.ref_paired_align_mt(index.handle, C.byref(params), C.byref(pparams), n_threads, n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
-                                 _p(batch.lens), _p(res), C.c_void_p(lvag.ctypes.data), C.c_void_p(lvag.ctypes.data + 8))
+    secs = index.L.ref_paired_align_mt_reps(index.handle, C.byref(params), C.byref(pparams), n_threads, reps, n, _p(batch.bases), _p(batch.quals), _p(batch.offsets),
+                                            _p(batch.lens), _p(res), C.c_void_p(lvag.ctypes.data), C.c_void_p(lvag.ctypes.data + 8))
     if secs < 0:
         raise RuntimeError("ref_paired_align_mt failed")
     return res, {"lvCalls": int(lvag[0]), "affineGapCalls": int(lvag[1])}, float(secs)
@@ -385,3 +426,16 @@ def tables(n_indel: int = 1200, n_perfect: int = 1001):
     perfect = np.zeros(n_perfect)
     lib().ref_tables(_p(phred), _p(indel), n_indel, _p(perfect), n_perfect)
     return phred, indel, perfect
+
+
+def build_reference_index(snap_aligner: str, fasta: str, out_dir: str, seed_len: int = 20, large: bool = False,
+                          threads: int = 8) -> None:
+    """Runs the stock reference CLI `snap-aligner index` (oracle/_ref/snap-aligner). Test infrastructure only."""
+    import subprocess
+    os.makedirs(out_dir, exist_ok=True)
+    cmd = [snap_aligner, "index", fasta, out_dir, "-s", str(seed_len), "-t%d" % threads]
+    if large:
+        cmd.append("-large")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0 or not os.path.exists(os.path.join(out_dir, "GenomeIndexHash")):
+        raise RuntimeError("snap-aligner index failed:\n" + res.stdout)

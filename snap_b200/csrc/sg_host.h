@@ -91,6 +91,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
             while (q < nl && spaces < 7) { if (*q == ' ') spaces++; q++; }
             ix.contigStart.push_back(start);
             ix.contigIsAlt.push_back((cflags & 1) ? 1 : 0);
+            if (nameLen < 0 || (long long)nameLen > (long long)(nl - q)) { err = "Genome contig line: name length runs past the line"; return false; }
             ix.contigName.push_back(std::string(q, (size_t)nameLen));
             p = nl + 1;
         }
@@ -125,6 +126,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
             memcpy(&ks, &buf[off + 20], 4); memcpy(&vs, &buf[off + 24], 4); memcpy(&vc, &buf[off + 28], 4);
             if (magic != 0xb111b010u) { err = "hash table magic mismatch"; return false; }      // HashTable.cpp:343
             if (vs != 4 || vc != valueCount || ks != ix.keyBytes) { err = "hash table key/value geometry unsupported"; return false; }
+            if (tsz == 0 || tsz > (buf.size() - off) / ix.entryBytes) { err = "hash table size field is zero or runs past the file"; return false; }
             memcpy(&inval, &buf[off + 32], 4);
             ix.invalidValue = inval;
             ix.tableStart[t] = slots; ix.tableSize[t] = tsz; ix.tableUsed[t] = used;

@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <errno.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -785,8 +788,17 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
     if (ix->view.entryBytes != 8 && ix->view.entryBytes != 12) return sg_fail("snapgpu_index_save: unsupported entry geometry");
     SG_CUDA(cudaSetDevice(ix->device));
     std::string dir(directory);
-    std::string cmd = "mkdir -p '" + dir + "'";
-    if (system(cmd.c_str()) != 0) return sg_fail("snapgpu_index_save: cannot create directory");
+    {
+        // mkdir -p without a shell (a directory name is data, not a command line)
+        for (size_t p = 1; p <= dir.size(); p++) {
+            if (p == dir.size() || dir[p] == '/') {
+                const std::string part = dir.substr(0, p);
+                if (mkdir(part.c_str(), 0777) != 0 && errno != EEXIST) return sg_fail("snapgpu_index_save: cannot create directory " + part);
+            }
+        }
+        struct stat sb;
+        if (stat(dir.c_str(), &sb) != 0 || !S_ISDIR(sb.st_mode)) return sg_fail("snapgpu_index_save: not a directory: " + dir);
+    }
     const size_t CH = (size_t)256 << 20;
     std::vector<uint8_t> buf(CH);
     // Genome
@@ -795,8 +807,10 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
         if (!f) return sg_fail("snapgpu_index_save: cannot write Genome");
         fprintf(f, "%lld %d %d\n", (long long)ix->view.nBases, (int)ix->h_contigStart.size(), 1);
         for (size_t c = 0; c < ix->h_contigStart.size(); c++) {
+            std::string name = ix->h_contigName[c];
+            for (size_t k = 0; k < name.size(); k++) if (name[k] == ' ') name[k] = '_';      // Genome::saveToFile does the same (Genome.cpp:230-236): the line is space-separated
             fprintf(f, "%lld %x %d %lld %x %d %d %s %s\n", (long long)ix->h_contigStart[c], ix->h_contigIsAlt[c] ? 1 : 0, (int)c, 0LL, 0,
-                    (int)ix->h_contigName[c].size(), 1, ix->h_contigName[c].c_str(), "*");
+                    (int)name.size(), 1, name.c_str(), "*");
         }
         for (size_t off = 0; off < (size_t)ix->view.nBases; off += CH) {
             size_t m = (size_t)ix->view.nBases - off < CH ? (size_t)ix->view.nBases - off : CH;
@@ -1233,6 +1247,7 @@ int snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bas
     if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results) return sg_fail("null argument");
     if (a->paired) return sg_fail("snapgpu_align_single_device called on a paired-end aligner handle");
     if (n < 0) return sg_fail("negative read count");
+    if (n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads (the deferred-read list and arenas are sized from it)");
     if (n == 0) return 0;
     SG_CUDA(cudaSetDevice(a->device));
     cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : a->stream;
@@ -1245,6 +1260,7 @@ int snapgpu_align_paired_device(snapgpu_aligner *a, int64_t nPairs, const char *
     if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results) return sg_fail("null argument");
     if (!a->paired) return sg_fail("snapgpu_align_paired_device called on a single-end aligner handle");
     if (nPairs < 0) return sg_fail("negative pair count");
+    if (2 * nPairs > a->maxBatchReads) return sg_fail("pair count exceeds maxBatchPairs (the retry list, hand-off records and candidate pool are sized from it)");
     if (nPairs == 0) return 0;
     SG_CUDA(cudaSetDevice(a->device));
     cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : a->stream;
@@ -1258,22 +1274,23 @@ static int drain_slot(snapgpu_aligner *a, int k, uint8_t *results, size_t result
     if (sl.pendingCount == 0) return 0;
     SG_CUDA(cudaEventSynchronize(sl.evOut));
     uint8_t *dst = results + (size_t)sl.pendingFirst * resultBytesPerUnit;
-    if (!resultsPinned) memcpy(dst, sl.h_results, (size_t)sl.pendingCount * resultBytesPerUnit);      // (pinned: the DMA wrote them in place)
+    const int64_t count = sl.pendingCount;
+    sl.pendingCount = 0;             // whatever happens below, the slot is free again
+    if (!resultsPinned) memcpy(dst, sl.h_results, (size_t)count * resultBytesPerUnit);      // (pinned: the DMA wrote them in place)
     if (!a->paired) {
         const snapgpu_single_result *r = (const snapgpu_single_result *)dst;
-        for (int64_t i = 0; i < sl.pendingCount; i++) {
+        for (int64_t i = 0; i < count; i++) {
             if (r[i].reserved == 1) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
         }
     }
-    sl.pendingCount = 0;
     return 0;
 }
 
 // Host-buffer path shared by snapgpu_align_single / snapgpu_align_paired.  nUnits units of readsPerUnit reads each.
 // Software pipeline over chunks of reads, two slots: pack chunk c+1 into pinned staging on the host and copy it in
 // while the GPU aligns chunk c and chunk c-1's results stream out.  Kernels stay on one stream (they share the arenas).
-static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size_t resultBytesPerUnit, const char *bases, const char *quals,
-                      const uint64_t *offsets, const uint32_t *lens, uint8_t *results, snapgpu_counters *counters)
+static int align_host_impl(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size_t resultBytesPerUnit, const char *bases, const char *quals,
+                           const uint64_t *offsets, const uint32_t *lens, uint8_t *results, snapgpu_counters *counters)
 {
     const int64_t n = nUnits * readsPerUnit;
     SG_CUDA(cudaSetDevice(a->device));
@@ -1353,6 +1370,24 @@ static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size
         for (size_t k2 = 0; k2 < sizeof(snapgpu_counters) / 8; k2++) dst[k2] += src[k2];
     }
     return 0;
+}
+
+// A call that fails part-way (an over-long read, a CUDA error) must not leave work of its own behind: the slots' pending results
+// belong to THIS call's buffers, and a D2H copy may still be in flight into them.  Quiesce the three streams and free both slots,
+// so the next call on the handle starts clean (it would otherwise drain the stale slot into its own, possibly smaller, buffer).
+static int align_host(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit, size_t resultBytesPerUnit, const char *bases, const char *quals,
+                      const uint64_t *offsets, const uint32_t *lens, uint8_t *results, snapgpu_counters *counters)
+{
+    a->slot[0].pendingCount = a->slot[1].pendingCount = 0;
+    const int rc = align_host_impl(a, nUnits, readsPerUnit, resultBytesPerUnit, bases, quals, offsets, lens, results, counters);
+    if (rc) {
+        const std::string keep = g_lastError;
+        cudaStreamSynchronize(a->streamIn); cudaStreamSynchronize(a->stream); cudaStreamSynchronize(a->streamOut);
+        cudaGetLastError();
+        a->slot[0].pendingCount = a->slot[1].pendingCount = 0;
+        g_lastError = keep;
+    }
+    return rc;
 }
 
 int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals, const uint64_t *offsets,

@@ -87,6 +87,7 @@ EXPORTS = [
     "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
+ABI_VERSION = 2          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
 _lib = None
 
 
@@ -99,6 +100,9 @@ def lib():
                                "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         L.snapgpu_last_error.restype = C.c_char_p
+        if L.snapgpu_abi_version() != ABI_VERSION:
+            raise SnapGpuError("%s has ABI version %d, this mirror expects %d: rebuild (python -c 'import __graft_entry__ as g; g.build()')"
+                               % (LIB_PATH, L.snapgpu_abi_version(), ABI_VERSION))
         L.snapgpu_params_default.argtypes = [C.POINTER(Params)]
         L.snapgpu_index_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.snapgpu_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,

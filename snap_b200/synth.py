@@ -175,19 +175,6 @@ def make_reads(contigs: list[np.ndarray], n: int, read_len: int, seed: int, sub_
     return rb
 
 
-def build_reference_index(snap_aligner: str, fasta: str, out_dir: str, seed_len: int = 20, large: bool = False,
-                          threads: int = 8) -> None:
-    """Runs the stock reference CLI `snap-aligner index` (oracle/_ref/snap-aligner). Test infrastructure only."""
-    import subprocess
-    os.makedirs(out_dir, exist_ok=True)
-    cmd = [snap_aligner, "index", fasta, out_dir, "-s", str(seed_len), "-t%d" % threads]
-    if large:
-        cmd.append("-large")
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0 or not os.path.exists(os.path.join(out_dir, "GenomeIndexHash")):
-        raise RuntimeError("snap-aligner index failed:\n" + res.stdout)
-
-
 def make_pairs(contigs: list[np.ndarray], n_pairs: int, read_len: int, seed: int, insert_mean: float = 400.0, insert_sd: float = 40.0,
                sub_rate: float = 0.01, ins_rate: float = 0.0005, del_rate: float = 0.0005, chimeric_frac: float = 0.0,
                n_run_frac: float = 0.0, short_frac: float = 0.0) -> ReadBatch:

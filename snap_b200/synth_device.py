@@ -30,6 +30,41 @@ def make_genome(n_contigs: int, contig_len: int, seed: int, device) -> tuple[tor
     return bases, np.array(starts, dtype=np.int64)
 
 
+def plant_repeats(bases: torch.Tensor, contig_starts: np.ndarray, contig_len: int, frac: float, seed: int, unit_len: int = 10_000,
+                  n_units: int = 32, max_div: float = 0.05, tandem_frac: float = 0.1) -> None:
+    """SURVEY 8d's stress variant, in place: `frac` of the bases are overwritten with copies of a small library of `unit_len`-bp
+    repeat units at 0..max_div divergence per copy (dispersed repeats: overflow lists, maxHits skips, merge logic), a tenth of
+    them as short tandem arrays of a 2-50 bp motif."""
+    device = bases.device
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    starts = torch.from_numpy(contig_starts).to(device)
+    n_contigs = len(contig_starts)
+    lib = lut[torch.randint(0, 4, (n_units, unit_len), generator=g, device=device)]
+    n_tandem = max(1, n_units // 8)
+    for t in range(n_tandem):                     # tandem units: a short motif repeated over the whole unit
+        m = int(torch.randint(2, 51, (1,), generator=g, device=device).item())
+        motif = lib[t, :m].clone()
+        lib[t] = motif.repeat((unit_len + m - 1) // m)[:unit_len]
+    n_copies = int(frac * n_contigs * contig_len / unit_len)
+    ar = torch.arange(unit_len, device=device, dtype=torch.int64)[None, :]
+    chunk = 2048
+    for o in range(0, n_copies, chunk):
+        m = min(chunk, n_copies - o)
+        tandem = torch.rand((m,), generator=g, device=device) < tandem_frac
+        u = torch.where(tandem, torch.randint(0, n_tandem, (m,), generator=g, device=device),
+                        torch.randint(n_tandem, n_units, (m,), generator=g, device=device))
+        ci = torch.randint(0, n_contigs, (m,), generator=g, device=device)
+        pos = torch.randint(0, contig_len - unit_len, (m,), generator=g, device=device)
+        div = torch.rand((m, 1), generator=g, device=device) * max_div
+        copy = lib[u]
+        mut = torch.rand((m, unit_len), generator=g, device=device) < div
+        copy = torch.where(mut, lut[torch.randint(0, 4, (m, unit_len), generator=g, device=device)], copy)
+        dst = (starts[ci] + pos)[:, None] + ar
+        bases[dst.reshape(-1)] = copy.reshape(-1)
+
+
 _COMP = None
 
 

@@ -68,8 +68,8 @@ class SmallCfg:
         synth.write_fasta(self.fasta, self.contigs)
         self.idx = os.path.join(self.dir, "idx")
         self.idx_large = os.path.join(self.dir, "idxL")
-        synth.build_reference_index(reflib.SNAP_ALIGNER, self.fasta, self.idx)
-        synth.build_reference_index(reflib.SNAP_ALIGNER, self.fasta, self.idx_large, large=True)
+        reflib.build_reference_index(reflib.SNAP_ALIGNER, self.fasta, self.idx)
+        reflib.build_reference_index(reflib.SNAP_ALIGNER, self.fasta, self.idx_large, large=True)
         self.reads = {
             "std150": synth.make_reads(self.contigs, 1500, 150, seed=32),
             "noisy150": synth.make_reads(self.contigs, 1500, 150, seed=33, sub_rate=0.04, ins_rate=0.006, del_rate=0.006,

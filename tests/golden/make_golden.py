@@ -66,7 +66,7 @@ def e2e_small(tmp):
     contigs = synth.make_contigs(2, 60_000, seed=101, repeat_frac=0.25)
     fasta = os.path.join(tmp, "ref.fa")
     synth.write_fasta(fasta, contigs)
-    synth.build_reference_index(reflib.SNAP_ALIGNER, fasta, os.path.join(tmp, "idx"))
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fasta, os.path.join(tmp, "idx"))
     sets = [
         synth.make_reads(contigs, 250, 150, seed=102),
         synth.make_reads(contigs, 250, 150, seed=103, sub_rate=0.03, ins_rate=0.004, del_rate=0.004, n_run_frac=0.1, short_frac=0.1, random_frac=0.05),
@@ -115,7 +115,7 @@ def output_small():
     out = {"source": "amplab/snap tests/LandauVishkinTest.cpp:34-129; snap-aligner single -d 14 -t 1 over the reads of e2e_small.npz", "lv_cigar": vec}
     with tempfile.TemporaryDirectory() as tmp:
         fa = os.path.join(tmp, "ref.fa"); synth.write_fasta(fa, [g["contig0"], g["contig1"]])
-        idx = os.path.join(tmp, "idx"); synth.build_reference_index(reflib.SNAP_ALIGNER, fa, idx)
+        idx = os.path.join(tmp, "idx"); reflib.build_reference_index(reflib.SNAP_ALIGNER, fa, idx)
         fq = os.path.join(tmp, "r.fq"); reads.write_fastq(fq)
         for ext in ("sam", "bam"):
             o = os.path.join(tmp, "o." + ext)

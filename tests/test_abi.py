@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libsnapgpu.so does not export " + n
     assert sorted(engine.EXPORTS) == names
-    assert L.snapgpu_abi_version() == 1
+    assert L.snapgpu_abi_version() == engine.ABI_VERSION
 
 
 def test_struct_sizes_match_header():
@@ -55,5 +55,5 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
-                assert "oracle" not in src.replace("oracle/_ref/snap-aligner", "").lower() or f == "synth.py", f
+                assert "oracle" not in src.lower(), f
                 assert "hostsim" not in src.lower(), f

@@ -157,7 +157,7 @@ def test_golden_e2e_fixture(golden_dir, tmp_path, reflib):
     g = np.load(os.path.join(golden_dir, "e2e_small.npz"))
     contigs = [g["contig0"], g["contig1"]]
     synth.write_fasta(str(tmp_path / "ref.fa"), contigs)
-    synth.build_reference_index(reflib.SNAP_ALIGNER, str(tmp_path / "ref.fa"), str(tmp_path / "idx"))
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, str(tmp_path / "ref.fa"), str(tmp_path / "idx"))
     reads = synth.ReadBatch(g["bases"], g["quals"], g["offsets"], g["lens"])
     hidx = hs.HsIndex(str(tmp_path / "idx"))
     for name in ("default_d14", "noag_d14", "ne_d20"):

@@ -75,7 +75,7 @@ def test_reference_datatest_end_to_end(vectors, reflib, tmp_path):
     fasta = str(tmp_path / "ref.fa")
     with open(fasta, "w") as f:
         f.write(">%s\n%s\n" % (d["contig_name"], d["contig"]))
-    synth.build_reference_index(reflib.SNAP_ALIGNER, fasta, str(tmp_path / "idx"))
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fasta, str(tmp_path / "idx"))
     reads = synth.ReadBatch.from_lists([(r["bases"].encode(), r["quals"].encode()) for r in d["reads"]])
     # the FASTQ reader clips trailing '#' qualities (FASTQ.cpp:294); these reads have none
     idx = reflib.RefIndex(str(tmp_path / "idx"))

@@ -50,7 +50,7 @@ def test_committed_sam_and_bam_records(reflib, golden_dir, tmp_path):
     fx = _fixture(golden_dir)
     g = np.load(os.path.join(golden_dir, "e2e_small.npz"))
     synth.write_fasta(str(tmp_path / "ref.fa"), [g["contig0"], g["contig1"]])
-    synth.build_reference_index(reflib.SNAP_ALIGNER, str(tmp_path / "ref.fa"), str(tmp_path / "idx"))
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, str(tmp_path / "ref.fa"), str(tmp_path / "idx"))
     reads = synth.ReadBatch(g["bases"], g["quals"], g["offsets"], g["lens"])
     hidx = hs.HsIndex(str(tmp_path / "idx"))
     ids = [b"r%d" % i for i in range(reads.n)]
