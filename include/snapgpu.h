@@ -180,6 +180,10 @@ typedef struct snapgpu_index   snapgpu_index;   /* opaque: hash tables + overflo
 typedef struct snapgpu_aligner snapgpu_aligner; /* opaque: per-host-thread stream, scratch arenas, staging */
 
 const char *snapgpu_last_error(void);            /* thread-local, never NULL */
+/* Page-locked host memory for callers that do not link CUDA themselves (the align calls DMA straight out of / into such buffers);
+ * NULL on failure. */
+void *snapgpu_host_alloc(size_t bytes);
+void  snapgpu_host_free(void *p);
 int  snapgpu_abi_version(void);
 int  snapgpu_device_count(void);                 /* 0 if no usable CUDA device */
 void snapgpu_params_default(snapgpu_params *p);  /* `snap single` 2.0.5 defaults, AlignerOptions.cpp:39-121 */
@@ -206,6 +210,12 @@ int  snapgpu_index_build_device(const char *d_bases, int64_t nBases, const int64
  * SURVEY 8a-F) so stock SNAP can load an index built on the device. */
 int  snapgpu_index_save(const snapgpu_index *idx, const char *directory);
 int  snapgpu_index_info_get(const snapgpu_index *idx, snapgpu_index_info *info);
+/*
+ * Second, third ... copy of an HBM-resident index on another device of the same process ("replicate the full index image in
+ * every GPU's HBM ... index upload can be done once"): device-to-device copies over NVLink / NVSwitch peer access instead of
+ * N uploads from the host.  The copy is an independent index (close each one).
+ */
+int  snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index **out);
 void snapgpu_index_close(snapgpu_index *idx);
 
 /*

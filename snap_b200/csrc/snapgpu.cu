@@ -563,6 +563,15 @@ extern "C" {
 const char *snapgpu_last_error(void) { return g_lastError.c_str(); }
 int snapgpu_abi_version(void) { return SNAPGPU_ABI_VERSION; }
 
+void *snapgpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); g_lastError = "snapgpu_host_alloc: cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+
+void snapgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int snapgpu_device_count(void)
 {
     int n = 0;
@@ -861,6 +870,52 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
                 (int)ix->view.chromosomePadding, (int)ix->view.keyBytes, (long long)hashBytes, ix->view.large ? 0 : 1, 4);
         fclose(f);
     }
+    return 0;
+}
+
+// A copy of `src` on `device`: every array of the image is copied device to device (cudaMemcpyPeer: NVLink / NVSwitch when peer
+// access is possible, staged through the host by the driver otherwise).
+int snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index **out)
+{
+    if (!src || !out) return sg_fail("null argument");
+    *out = nullptr;
+    if (require_device(device)) return 1;
+    if (device != src->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            cudaGetLastError();
+        }
+    }
+    snapgpu_index *ix = new (std::nothrow) snapgpu_index;
+    if (!ix) return sg_fail("out of memory");
+    ix->device = device;
+    const SgIndexView &sv = src->view;
+    const size_t tableBytes = (size_t)src->info.hashTableSlots * sv.entryBytes + 16;
+    const size_t nT = sv.nTables;
+    size_t hbm = 0;
+    #define DUP(dst, srcp, bytes) do { size_t b__ = (bytes); if (b__ == 0) b__ = 16; SG_CUDA(cudaMalloc((void **)&(dst), b__)); \
+        if ((bytes) > 0) SG_CUDA(cudaMemcpyPeer((dst), device, (srcp), src->device, (bytes))); hbm += b__; } while (0)
+    DUP(ix->d_tables, src->d_tables, tableBytes);
+    DUP(ix->d_tableStart, src->d_tableStart, nT * 8);
+    DUP(ix->d_tableSize, src->d_tableSize, nT * 8);
+    DUP(ix->d_tableMagic, src->d_tableMagic, nT * 8);
+    DUP(ix->d_overflow, src->d_overflow, (size_t)(sv.overflowSize + 1) * 4);
+    DUP(ix->d_basesPadded, src->d_basesPadded, (size_t)sv.nBases + 2 * SG_N_PADDING);
+    DUP(ix->d_contigStart, src->d_contigStart, (size_t)sv.nContigs * 8);
+    DUP(ix->d_tables_prob, src->d_tables_prob, sizeof(SgTables));
+    #undef DUP
+    SG_CUDA(cudaDeviceSynchronize());
+    SgIndexView v = sv;
+    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.tableMagic = ix->d_tableMagic; v.overflow = ix->d_overflow;
+    v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart;
+    ix->view = v;
+    ix->info = src->info; ix->info.hbmBytes = hbm;
+    ix->h_tables_prob = src->h_tables_prob;
+    ix->h_tableStart = src->h_tableStart; ix->h_tableSize = src->h_tableSize; ix->h_tableUsed = src->h_tableUsed;
+    ix->h_contigStart = src->h_contigStart; ix->h_contigName = src->h_contigName; ix->h_contigIsAlt = src->h_contigIsAlt;
+    *out = ix;
     return 0;
 }
 

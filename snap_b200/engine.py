@@ -80,7 +80,7 @@ N_COUNTERS = len(COUNTER_FIELDS) + 71
 # every symbol include/snapgpu.h declares
 EXPORTS = [
     "snapgpu_last_error", "snapgpu_abi_version", "snapgpu_device_count", "snapgpu_params_default",
-    "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close",
+    "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close", "snapgpu_index_replicate", "snapgpu_host_alloc", "snapgpu_host_free",
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
@@ -112,6 +112,10 @@ def lib():
         L.snapgpu_index_save.argtypes = [C.c_void_p, C.c_char_p]
         L.snapgpu_index_info_get.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
         L.snapgpu_index_close.argtypes = [C.c_void_p]
+        L.snapgpu_index_replicate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.snapgpu_host_alloc.restype = C.c_void_p
+        L.snapgpu_host_alloc.argtypes = [C.c_size_t]
+        L.snapgpu_host_free.argtypes = [C.c_void_p]
         L.snapgpu_lookup_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.snapgpu_aligner_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.POINTER(C.c_void_p)]
         L.snapgpu_aligner_destroy.argtypes = [C.c_void_p]
@@ -214,6 +218,12 @@ class Index:
     def lookup_seeds_device(self, d_seeds: int, n: int, d_nhits: int, d_hits: int = 0, d_probes: int = 0, max_hits: int = 0, stream: int = 0):
         _check(lib().snapgpu_lookup_seeds_device(self.handle, C.c_void_p(d_seeds), n, max_hits, C.c_void_p(d_nhits), C.c_void_p(d_hits),
                                                  C.c_void_p(d_probes), C.c_void_p(stream)))
+
+    def replicate(self, device: int) -> "Index":
+        """A copy of this index on another device of the same process (device-to-device copies)."""
+        h = C.c_void_p()
+        _check(lib().snapgpu_index_replicate(self.handle, device, C.byref(h)))
+        return Index(h, device)
 
     def save(self, directory: str) -> None:
         """Writes a reference-format index directory (loadable by stock `snap-aligner`)."""
