@@ -228,6 +228,14 @@ void snapgpu_index_close(snapgpu_index *idx);
 int  snapgpu_lookup_seeds(const snapgpu_index *idx, const char *seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,
                           int64_t *nHits, uint32_t *hits, uint32_t *probes);
 
+/*
+ * Measurement utility (the denominator of bench.py's seed_phase; on no product path): the device's random-access ceiling.  nAccesses
+ * aligned 32-byte sector reads at pseudo-random places of a scratch table of tableBytes, one independent read in flight per thread
+ * (best of three launches, CUDA events).  A hash probe is exactly this access, so sector reads per second is the roofline of the
+ * seed-lookup phase: lookups/s <= rate / sectors per lookup.
+ */
+int  snapgpu_measure_random_sector_rate(int device, uint64_t tableBytes, uint64_t nAccesses, double *sectorsPerSecond);
+
 /* Same with DEVICE pointers (d_hits / d_probes may be NULL), enqueued on `cudaStream` without synchronising:
  * the seed-lookup phase in isolation, for its roofline measurement. */
 int  snapgpu_lookup_seeds_device(const snapgpu_index *idx, const char *d_seeds, int64_t nSeeds, uint32_t maxHitsPerSeed,

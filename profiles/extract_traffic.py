@@ -3,7 +3,7 @@
 profiles/traffic.json, which bench.py quotes as roofline.traffic when it runs the same workload.  A report holds the launches of
 ONE step (two for the single-end two-pass launch, four for the staged paired launch); their bytes are summed.
 usage: extract_traffic.py KEY REPORT.ncu-rep "description of the captured command" [KEY REPORT DESC ...]"""
-import csv, io, json, os, subprocess, sys
+import csv, hashlib, io, json, os, subprocess, sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "traffic.json")
@@ -12,6 +12,16 @@ OUT = os.path.join(HERE, "traffic.json")
 def to_bytes(v, unit):
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     return float(v.replace(",", "")) * mult[unit]
+
+
+def csrc_sha16():
+    """Same hash as bench.py's: the kernel sources a capture was taken of."""
+    h = hashlib.sha256()
+    d = os.path.join(os.path.dirname(HERE), "snap_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def main():
@@ -23,7 +33,7 @@ def main():
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(hdr)}
-        rd = wr = 0.0
+        rd = wr = inst = 0.0
         per_launch = []
         for vals in rows[2:]:
             if len(vals) != len(hdr):
@@ -33,10 +43,14 @@ def main():
             if r != r or w != w:          # a launch too short for the DRAM counters (e.g. the empty retry pass)
                 r = w = 0.0
             rd += r; wr += w
+            try:
+                inst += float(vals[col["smsp__inst_executed.sum"]].replace(",", ""))
+            except Exception:
+                pass
             per_launch.append({"kernel": vals[col["Kernel Name"]][:40], "dram_bytes": int(r + w),
                                "duration_under_ncu": vals[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]]})
         data[key] = {"dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr), "launches": per_launch,
-                     "captured_with": desc, "report": os.path.basename(rep)}
+                     "warp_instructions_per_step": int(inst), "csrc_sha16": csrc_sha16(), "captured_with": desc, "report": os.path.basename(rep)}
         print(key, data[key])
     json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
 

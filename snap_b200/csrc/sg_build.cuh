@@ -79,10 +79,82 @@ __global__ void sg_build_count_kernel(const unsigned long long *keys, long long 
     }
 }
 
-// pass 2: insert run heads
+// Sector-bucket insertion (sg_bucket.h) with atomics: claims the first empty slot of the home bucket, or of the next bucket with room,
+// setting the "continue" flag (bit 63 of slot 0) of every full bucket it passes.  Slot 0 can change under us in two ways -- another
+// key claims it, or a passer-by sets its flag -- hence the compare-and-swap retry.
+__device__ __forceinline__ bool sg_bucket_insert_atomic(unsigned long long *buckets, unsigned long long nBuckets, uint32_t bits, unsigned long long canonical,
+                                                        uint32_t orient, uint32_t value)
+{
+    const unsigned long long h = sg_bucket_mix(canonical, bits);
+    unsigned long long b = sg_bucket_home(h, bits, nBuckets);
+    const unsigned long long slot = sg_bucket_slot_make(h, orient, value);
+    for (int disp = 0; disp <= SG_BUCKET_MAX_DISP; disp++) {
+        unsigned long long *p = buckets + b * SG_BUCKET_SLOTS;
+        #pragma unroll 1
+        for (int k = 0; k < SG_BUCKET_SLOTS; k++) {
+            unsigned long long old = ((volatile unsigned long long *)p)[k];
+            while ((uint32_t)old == 0xffffffffu) {
+                const unsigned long long desired = slot | (k == 0 ? (old & SG_BUCKET_FLAG) : 0ULL);
+                const unsigned long long prev = atomicCAS(&p[k], old, desired);
+                if (prev == old) return true;
+                old = prev;
+            }
+        }
+        atomicOr(&p[0], SG_BUCKET_FLAG);
+        b = (b + 1 == nBuckets) ? 0 : b + 1;
+    }
+    return false;
+}
+
+// Re-lays the reference's tables (as uploaded from an index directory: 8-byte default or 12-byte -large entries) into sector buckets.
+__global__ void sg_build_relayout_kernel(const uint8_t *tables, const uint64_t *tableStart, const uint64_t *tableSize, uint32_t nTables, uint32_t entryBytes,
+                                         uint32_t large, uint32_t keyBits, uint32_t seedLen, uint32_t invalidValue, unsigned long long *buckets,
+                                         unsigned long long nBuckets, int *failed)
+{
+    const uint32_t nv = large ? 2u : 1u, bits = 2 * seedLen;
+    for (uint32_t t = blockIdx.y; t < nTables; t += gridDim.y) {
+        const uint64_t size = tableSize[t], base = tableStart[t];
+        for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < size; k += (uint64_t)gridDim.x * blockDim.x) {
+            const uint8_t *p = tables + (base + k) * entryBytes;
+            const uint32_t v0 = *(const uint32_t *)p, v1 = nv == 2 ? *(const uint32_t *)(p + 4) : 0xfffffffeu, key = *(const uint32_t *)(p + 4 * nv);
+            if (v0 == invalidValue) continue;
+            const unsigned long long seed = ((unsigned long long)t << keyBits) | key;
+            bool ok = true;
+            if (large) {
+                if (v0 != 0xfffffffeu) ok = sg_bucket_insert_atomic(buckets, nBuckets, bits, seed, 0, v0);
+                if (ok && v1 != 0xfffffffeu) ok = sg_bucket_insert_atomic(buckets, nBuckets, bits, seed, 1, v1);
+            } else {
+                const unsigned long long rc = sg_seed_revcomp(seed, seedLen);
+                const unsigned long long c = seed < rc ? seed : rc;
+                ok = sg_bucket_insert_atomic(buckets, nBuckets, bits, c, seed == c ? 0u : 1u, v0);
+            }
+            if (!ok) *failed = 1;
+        }
+    }
+}
+
+// counts the used values of the reference's tables (= bucket slots needed)
+__global__ void sg_build_count_values_kernel(const uint8_t *tables, unsigned long long totalSlots, uint32_t entryBytes, uint32_t large, uint32_t invalidValue,
+                                             unsigned long long *count)
+{
+    unsigned long long local = 0;
+    const uint32_t nv = large ? 2u : 1u;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < totalSlots; k += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t *p = tables + k * entryBytes;
+        for (uint32_t j = 0; j < nv; j++) {
+            const uint32_t v = *(const uint32_t *)(p + 4 * j);
+            if (v != invalidValue && v != 0xfffffffeu) local++;
+        }
+    }
+    local = __reduce_add_sync(0xffffffffu, (unsigned)local) ;
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+// pass 2: insert run heads.  buckets != NULL: into sector buckets (sg_bucket.h); else into the reference's table layout.
 __global__ void sg_build_insert_kernel(const unsigned long long *keys, const uint32_t *locs, long long n, uint32_t keyBits, uint32_t seedLen,
                                        const uint64_t *tableStart, const uint64_t *tableSize, unsigned long long *tables,
-                                       uint32_t *overflow, unsigned long long *overflowCursor, long long nBases, int *failed)
+                                       uint32_t *overflow, unsigned long long *overflowCursor, long long nBases, int *failed,
+                                       unsigned long long *buckets, unsigned long long nBuckets)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -103,6 +175,12 @@ __global__ void sg_build_insert_kernel(const unsigned long long *keys, const uin
             overflow[off] = (uint32_t)count;
             for (unsigned long long c = 0; c < count; c++) overflow[off + 1 + c] = locs[i + c];   // already descending
             value = (uint32_t)((unsigned long long)nBases + off);
+        }
+        if (buckets) {
+            const unsigned long long rc = sg_seed_revcomp(k, seedLen);
+            const unsigned long long c = k < rc ? k : rc;
+            if (!sg_bucket_insert_atomic(buckets, nBuckets, 2 * seedLen, c, k == c ? 0u : 1u, value)) *failed = 1;
+            continue;
         }
         const uint32_t table = (uint32_t)(k >> keyBits);
         const unsigned long long low = k & ((1ULL << keyBits) - 1);

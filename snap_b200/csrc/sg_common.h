@@ -57,7 +57,14 @@ struct SgIndexView {
     uint32_t entryBytes;             // 4*valueCount + keyBytes
     uint32_t chromosomePadding;
     uint32_t invalidValue;           // 0xffffffff
+    // layout 1 (sg_bucket.h): sector buckets keyed by the canonical seed; `tables` etc. are then unused (NULL)
+    uint32_t layout;                 // 0: the reference's tables (8 / 12-byte entries, quadratic probing); 1: 32-byte sector buckets
+    uint32_t pad0;
+    const uint64_t *buckets;         // [nBuckets * 4]
+    uint64_t nBuckets;
 };
+#define SG_LAYOUT_SNAP 0
+#define SG_LAYOUT_BUCKET 1
 
 // Probability / schedule tables (host-computed with the host libm so doubles are bit-identical to the reference's).
 struct SgTables {

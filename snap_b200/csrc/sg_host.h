@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include "sg_common.h"
+#include "sg_seed.h"
 
 struct SgHostIndex {
     std::vector<uint8_t>  tables;        // repacked: entries of all tables back to back (+8 bytes slack)
@@ -22,6 +23,10 @@ struct SgHostIndex {
     uint32_t seedLen = 0, keyBytes = 0, nTables = 0, large = 0, entryBytes = 0, chromosomePadding = 0, locationSize = 4;
     uint32_t invalidValue = 0xffffffffu;
     uint64_t overflowSize = 0, totalSlots = 0;
+    // sector-bucket layout (sg_bucket.h), filled by sg_host_relayout(); layout says which one view() hands out
+    uint32_t layout = SG_LAYOUT_SNAP;
+    std::vector<uint64_t> buckets;
+    uint64_t nBuckets = 0;
 
     SgIndexView view() const {           // host-memory view (test build); the CUDA library builds a device one
         SgIndexView v;
@@ -30,6 +35,7 @@ struct SgHostIndex {
         v.nBases = nBases; v.altFirstLocation = altFirstLocation; v.overflowSize = overflowSize;
         v.nContigs = (uint32_t)contigStart.size(); v.seedLen = seedLen; v.keyBytes = keyBytes; v.nTables = nTables;
         v.large = large; v.entryBytes = entryBytes; v.chromosomePadding = chromosomePadding; v.invalidValue = invalidValue;
+        v.layout = layout; v.pad0 = 0; v.buckets = buckets.empty() ? (const uint64_t *)0 : buckets.data(); v.nBuckets = nBuckets;
         return v;
     }
 };
@@ -149,6 +155,66 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
         }
     }
     return true;
+}
+
+// Number of 32-byte buckets for nEntries (seed, orientation) entries at the given load (entries per slot).
+static inline uint64_t sg_bucket_count_for(uint64_t nEntries, uint32_t seedLen, double load)
+{
+    if (load < 0.05) load = 0.05;
+    if (load > 0.9) load = 0.9;
+    uint64_t n = (uint64_t)((double)nEntries / (SG_BUCKET_SLOTS * load)) + 1;
+    const uint64_t mn = sg_bucket_min_count(2 * seedLen);
+    return n < mn ? mn : n;
+}
+
+static inline double sg_bucket_default_load()
+{
+    double load = 0.6;
+    if (const char *e = getenv("SNAPGPU_BUCKET_LOAD")) { double v = atof(e); if (v > 0.0) load = v; }
+    return load;
+}
+
+// Re-lays a loaded reference-format index (default or -large tables) into sector buckets on the host: every used value of every
+// table entry becomes one (canonical seed, orientation) -> value slot.  Sequential; the CUDA library does the same on the device
+// (sg_build.cuh), this form serves the host-side tests.
+static inline bool sg_host_relayout(SgHostIndex &ix, double load, std::string &err)
+{
+    if (ix.keyBytes != 4 || ix.seedLen < 16 || ix.seedLen > 24) { err = "bucket layout needs 4-byte keys (seed length 16..24)"; return false; }
+    const uint32_t nv = ix.large ? 2u : 1u, keyBits = ix.keyBytes * 8, bits = 2 * ix.seedLen;
+    uint64_t nEntries = 0;
+    for (uint64_t s = 0; s < ix.totalSlots; s++) {
+        const uint8_t *p = ix.tables.data() + (size_t)s * ix.entryBytes;
+        for (uint32_t j = 0; j < nv; j++) {
+            uint32_t v; memcpy(&v, p + 4 * j, 4);
+            if (v != ix.invalidValue && v != 0xfffffffeu) nEntries++;
+        }
+    }
+    for (int attempt = 0; attempt < 4; attempt++, load *= 0.7) {
+        ix.nBuckets = sg_bucket_count_for(nEntries, ix.seedLen, load);
+        ix.buckets.assign((size_t)ix.nBuckets * SG_BUCKET_SLOTS, SG_BUCKET_EMPTY);
+        bool ok = true;
+        for (uint32_t t = 0; t < ix.nTables && ok; t++) {
+            for (uint64_t k = 0; k < ix.tableSize[t] && ok; k++) {
+                const uint8_t *p = ix.tables.data() + (size_t)(ix.tableStart[t] + k) * ix.entryBytes;
+                uint32_t v[2] = {0xfffffffeu, 0xfffffffeu}; uint32_t key;
+                memcpy(&v[0], p, 4); if (nv == 2) memcpy(&v[1], p + 4, 4);
+                memcpy(&key, p + 4 * nv, 4);
+                if (v[0] == ix.invalidValue) continue;
+                const uint64_t seed = ((uint64_t)t << keyBits) | key;
+                if (ix.large) {
+                    for (uint32_t o = 0; o < 2 && ok; o++)
+                        if (v[o] != 0xfffffffeu) ok = sg_bucket_insert_seq(ix.buckets.data(), ix.nBuckets, bits, seed, o, v[o]);
+                } else {
+                    const uint64_t rc = sg_seed_revcomp(seed, ix.seedLen);
+                    const uint64_t c = seed < rc ? seed : rc;
+                    ok = sg_bucket_insert_seq(ix.buckets.data(), ix.nBuckets, bits, c, seed == c ? 0u : 1u, v[0]);
+                }
+            }
+        }
+        if (ok) { ix.layout = SG_LAYOUT_BUCKET; return true; }
+    }
+    err = "bucket layout: a key landed too far from home even at low load";
+    return false;
 }
 
 // ---- probability tables (reference LandauVishkin.cpp:715-763), MAPQ thresholds (mapq.h:54), wrap table ----

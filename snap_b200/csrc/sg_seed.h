@@ -1,6 +1,7 @@
 // sg_seed.h -- seed packing, index hash probe, lookupSeed32, genome substring.  Scalar form, host+device.
 #pragma once
 #include "sg_common.h"
+#include "sg_bucket.h"
 
 // BASE_VALUE, reference Tables.cpp:52-58: A=0 G=1 C=2 T=3, everything else 4.
 SG_HD uint32_t sg_base_value(uint8_t c)
@@ -34,6 +35,19 @@ SG_HD bool sg_seed_pack(const uint8_t *text, uint32_t seedLen, uint64_t *bases, 
     *bases = b;
     *rc = r;
     return ok;
+}
+
+// The packed reverse complement of a packed seed (both in the `bases` convention of sg_seed_pack: first base most significant):
+// reverse the order of the 2-bit digits and complement each (v ^ 3, Seed.h:40-53).
+SG_HD uint64_t sg_seed_revcomp(uint64_t bases, uint32_t seedLen)
+{
+    uint64_t x = ~bases;                                       // complement every digit
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0f0f0f0f0f0f0f0fULL) | ((x & 0x0f0f0f0f0f0f0f0fULL) << 4);
+    x = ((x >> 8) & 0x00ff00ff00ff00ffULL) | ((x & 0x00ff00ff00ff00ffULL) << 8);
+    x = ((x >> 16) & 0x0000ffff0000ffffULL) | ((x & 0x0000ffff0000ffffULL) << 16);
+    x = (x >> 32) | (x << 32);                                 // all 32 digits reversed
+    return x >> (64 - 2 * seedLen);
 }
 
 // SNAPHashTable::hash: MurmurHash3 fmix64 (reference HashTable.h:72-85).
@@ -132,6 +146,10 @@ SG_HD void sg_fill_hits(const SgIndexView &ix, const uint32_t *subEntry, uint32_
 // GenomeIndex::lookupSeed32 (reference GenomeIndex.cpp:2095-2157).  `bases`/`rc` from sg_seed_pack.
 SG_HD void sg_lookup_seed32(const SgIndexView &ix, uint64_t bases, uint64_t rc, SgHits *out, uint32_t *examined, uint32_t *overflowWords)
 {
+    if (ix.layout == SG_LAYOUT_BUCKET) {
+        sg_bucket_lookup_seed32(ix, bases, rc, out->nHits, out->hits, examined, overflowWords);
+        return;
+    }
     const uint32_t keyBits = ix.keyBytes * 8;
     out->nHits[0] = out->nHits[1] = 0;
     out->hits[0] = out->hits[1] = ix.overflow;

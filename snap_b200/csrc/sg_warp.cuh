@@ -46,6 +46,12 @@ __device__ __forceinline__ uint32_t sg_probe_offset(uint32_t k)
 __device__ __forceinline__ void sg_warp_lookup_seed32(const SgIndexView &ix, uint64_t bases, uint64_t rc, int lane, SgHits *out,
                                                       uint32_t *examined, uint32_t *overflowWords)
 {
+    if (ix.layout == SG_LAYOUT_BUCKET) {
+        // one sector resolves the lookup: every lane loads the same 32 bytes (one request) and resolves it redundantly -- there is
+        // nothing to spread over the lanes
+        sg_bucket_lookup_seed32(ix, bases, rc, out->nHits, out->hits, examined, overflowWords);
+        return;
+    }
     const uint32_t keyBits = ix.keyBytes * 8;
     out->nHits[0] = out->nHits[1] = 0;
     out->hits[0] = out->hits[1] = ix.overflow;

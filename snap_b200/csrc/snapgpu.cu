@@ -46,7 +46,9 @@ struct snapgpu_index {
     int device = 0;
     SgIndexView view;                    // device pointers
     snapgpu_index_info info;
-    uint8_t  *d_tables = nullptr;
+    uint8_t  *d_tables = nullptr;        // the reference's table layout (SG_LAYOUT_SNAP); NULL for a sector-bucket index
+    uint64_t *d_buckets = nullptr;       // sector buckets (SG_LAYOUT_BUCKET, sg_bucket.h)
+    bool builtOnDevice = false;          // bases -> index on the device (such an index can be re-built in the reference's layout for saving)
     uint64_t *d_tableStart = nullptr, *d_tableSize = nullptr, *d_tableMagic = nullptr;
     uint32_t *d_overflow = nullptr;
     uint8_t  *d_basesPadded = nullptr;
@@ -168,6 +170,33 @@ sg_lookup_kernel(SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_
                     uint32_t n = h.nHits[d] < maxHitsPerSeed ? h.nHits[d] : maxHitsPerSeed;
                     for (uint32_t k = lane; k < n; k += 32) hits[(2 * i + d) * (long long)maxHitsPerSeed + k] = h.hits[d][k];
                 }
+            }
+        }
+    }
+}
+
+// The same entry on a sector-bucket index (sg_bucket.h): ONE THREAD per seed -- a lookup is one 32-byte sector (two 16-byte loads of
+// the same sector), there is nothing for a warp to share, and what the phase needs is as many independent sector requests in flight as
+// the memory system takes (2048 threads per SM, one request each; the random-sector gather ceiling is reached at that depth,
+// profiles/r02_random_gather_peak.jsonl).
+__global__ void __launch_bounds__(256, 8)
+sg_lookup_bucket_kernel(const __grid_constant__ SgIndexView ix, const uint8_t *seeds, long long nSeeds, uint32_t maxHitsPerSeed,
+                        long long *nHits, uint32_t *hits, uint32_t *probes)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nSeeds; i += stride) {
+        uint64_t b, rc;
+        SgHits h;
+        uint32_t examined = 0, ow = 0;
+        h.nHits[0] = h.nHits[1] = 0; h.hits[0] = h.hits[1] = ix.overflow;
+        if (sg_seed_pack(seeds + i * ix.seedLen, ix.seedLen, &b, &rc)) sg_bucket_lookup_seed32(ix, b, rc, h.nHits, h.hits, &examined, &ow);
+        nHits[2 * i] = h.nHits[0];
+        nHits[2 * i + 1] = h.nHits[1];
+        if (probes) probes[i] = examined;
+        if (hits) {
+            for (int d = 0; d < 2; d++) {
+                const uint32_t n = h.nHits[d] < maxHitsPerSeed ? h.nHits[d] : maxHitsPerSeed;
+                for (uint32_t k = 0; k < n; k++) hits[(2 * i + d) * (long long)maxHitsPerSeed + k] = h.hits[d][k];
             }
         }
     }
@@ -610,6 +639,52 @@ static int require_device(int device)
     return 0;
 }
 
+// Which layout the lookup structure gets in HBM: sector buckets (default) or the reference's own tables (SNAPGPU_INDEX_LAYOUT=snap;
+// kept for probe-for-probe parity tests of GetFirstValueForKey and as the form an index is written out in).
+static uint32_t wanted_layout()
+{
+    if (const char *e = getenv("SNAPGPU_INDEX_LAYOUT")) { if (!strcmp(e, "snap") || !strcmp(e, "0")) return SG_LAYOUT_SNAP; }
+    return SG_LAYOUT_BUCKET;
+}
+
+// Sector buckets from the reference-layout tables already in HBM (ix->d_tables ...); frees those tables on success.
+static int relayout_on_device(snapgpu_index *ix, size_t *hbm)
+{
+    SgIndexView &v = ix->view;
+    if (v.keyBytes != 4 || v.seedLen < 16 || v.seedLen > 24) return 0;          // other key geometries keep the reference layout
+    unsigned long long *d_count = nullptr; int *d_failed = nullptr;
+    SG_CUDA(cudaMalloc((void **)&d_count, 8)); SG_CUDA(cudaMemset(d_count, 0, 8));
+    SG_CUDA(cudaMalloc((void **)&d_failed, 4));
+    sg_build_count_values_kernel<<<148 * 8, 256>>>(v.tables, (unsigned long long)ix->info.hashTableSlots, v.entryBytes, v.large, v.invalidValue, d_count);
+    unsigned long long nEntries = 0;
+    SG_CUDA(cudaMemcpy(&nEntries, d_count, 8, cudaMemcpyDeviceToHost));
+    double load = sg_bucket_default_load();
+    bool done = false;
+    for (int attempt = 0; attempt < 4 && !done; attempt++, load *= 0.7) {
+        const uint64_t nBuckets = sg_bucket_count_for(nEntries, v.seedLen, load);
+        if (ix->d_buckets) { cudaFree(ix->d_buckets); ix->d_buckets = nullptr; }
+        SG_CUDA(cudaMalloc((void **)&ix->d_buckets, (size_t)nBuckets * 32 + 64));
+        sg_build_fill_kernel<<<148 * 8, 256>>>((unsigned long long *)ix->d_buckets, (long long)nBuckets * SG_BUCKET_SLOTS + 8, SG_BUCKET_EMPTY);
+        SG_CUDA(cudaMemset(d_failed, 0, 4));
+        dim3 grid(148 * 4, v.nTables < 64 ? v.nTables : 64);
+        sg_build_relayout_kernel<<<grid, 256>>>(v.tables, v.tableStart, v.tableSize, v.nTables, v.entryBytes, v.large, v.keyBytes * 8, v.seedLen, v.invalidValue,
+                                                (unsigned long long *)ix->d_buckets, nBuckets, d_failed);
+        SG_CUDA(cudaGetLastError());
+        int failed = 0;
+        SG_CUDA(cudaMemcpy(&failed, d_failed, 4, cudaMemcpyDeviceToHost));
+        if (!failed) { v.nBuckets = nBuckets; done = true; }
+    }
+    cudaFree(d_count); cudaFree(d_failed);
+    if (!done) return sg_fail("bucket layout: a key landed too far from its home bucket even at low load");
+    *hbm -= (size_t)ix->info.hashTableSlots * v.entryBytes;
+    cudaFree(ix->d_tables); ix->d_tables = nullptr;
+    v.tables = nullptr; v.layout = SG_LAYOUT_BUCKET; v.buckets = ix->d_buckets;
+    *hbm += (size_t)v.nBuckets * 32;
+    ix->info.hashTableSlots = v.nBuckets * SG_BUCKET_SLOTS;
+    ix->info.reserved = SG_LAYOUT_BUCKET;
+    return 0;
+}
+
 static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
 {
     if (require_device(device)) return 1;
@@ -640,6 +715,11 @@ static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
     ix->info.overflowTableSize = h.overflowSize; ix->info.hashTableSlots = h.totalSlots; ix->info.hbmBytes = hbm;
     ix->h_tableStart = h.tableStart; ix->h_tableSize = h.tableSize; ix->h_tableUsed = h.tableUsed;
     ix->h_contigStart = h.contigStart; ix->h_contigName = h.contigName; ix->h_contigIsAlt = h.contigIsAlt;
+    ix->view.layout = SG_LAYOUT_SNAP; ix->view.pad0 = 0; ix->view.buckets = nullptr; ix->view.nBuckets = 0;
+    if (wanted_layout() == SG_LAYOUT_BUCKET) {
+        if (relayout_on_device(ix, &hbm)) { snapgpu_index_close(ix); return 1; }
+        ix->info.hbmBytes = hbm;
+    }
     *out = ix;
     return 0;
 }
@@ -658,7 +738,7 @@ int snapgpu_index_open(const char *directory, int device, snapgpu_index **out)
 // Device-side index construction (kernels in sg_build.cuh).  d_basesPadded: SG_N_PADDING 'n', the nBases bases,
 // SG_N_PADDING 'n' -- ownership passes to the index on success.
 static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const int64_t *contigStarts, uint32_t nContigs,
-                                 uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out)
+                                 uint32_t seedLen, uint32_t chromosomePadding, int device, snapgpu_index **out, uint32_t layout)
 {
     if (seedLen < 16 || seedLen > 24) return sg_fail("snapgpu_index_build: seed length must be in [16, 24]");
     if (nBases <= (int64_t)seedLen + 2 || nBases > 0xffffffffLL - 16) return sg_fail("snapgpu_index_build: genome size unsupported for 4-byte locations");
@@ -705,31 +785,58 @@ static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const i
 
     // table sizes: the reference sizes tables at (1 + slack) x expected content with slack 0.3 (GenomeIndex.cpp:1084-1100)
     std::vector<uint64_t> tstart(nTables), tsize(nTables), tmagic(nTables);
-    uint64_t slots = 0;
+    uint64_t slots = 0, distinct = 0;
     for (uint32_t t = 0; t < nTables; t++) {
         uint64_t sz = (uint64_t)((double)stats[t] * 1.3) + 1;
         if (sz < 100) sz = 100;
         tstart[t] = slots; tsize[t] = sz; tmagic[t] = ~0ULL / sz; slots += sz;
+        distinct += stats[t];
     }
     size_t hbm = 0;
-    SG_CUDA(cudaMalloc((void **)&ix->d_tables, slots * 8 + 16)); hbm += slots * 8 + 16;
-    sg_build_fill_kernel<<<grid, 256>>>((unsigned long long *)ix->d_tables, (long long)slots + 2, 0x00000000ffffffffULL);
-    SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaMalloc((void **)&ix->d_tableStart, nTables * 8)); SG_CUDA(cudaMalloc((void **)&ix->d_tableSize, nTables * 8));
     SG_CUDA(cudaMalloc((void **)&ix->d_tableMagic, nTables * 8));
     SG_CUDA(cudaMemcpy(ix->d_tableMagic, tmagic.data(), nTables * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(ix->d_tableStart, tstart.data(), nTables * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(ix->d_tableSize, tsize.data(), nTables * 8, cudaMemcpyHostToDevice));
     SG_CUDA(cudaMalloc((void **)&ix->d_overflow, (size_t)(overflowWords + 4) * 4)); hbm += (size_t)(overflowWords + 4) * 4;
-    SG_CUDA(cudaMemset(ix->d_overflow, 0, (size_t)(overflowWords + 4) * 4));
-    SG_CUDA(cudaMalloc((void **)&d_failed, 4)); SG_CUDA(cudaMemset(d_failed, 0, 4));
-    sg_build_insert_kernel<<<grid, 256>>>(sk, sv, nPos, keyBits, seedLen, ix->d_tableStart, ix->d_tableSize, (unsigned long long *)ix->d_tables,
-                                          ix->d_overflow, d_stats + nTables + 2, nBases, d_failed);
-    SG_CUDA(cudaGetLastError());
-    int failed = 0;
-    SG_CUDA(cudaMemcpy(&failed, d_failed, 4, cudaMemcpyDeviceToHost));
-    cudaFree((void *)sk); cudaFree((void *)sv); cudaFree(d_stats); cudaFree(d_failed);
-    if (failed) return sg_fail("snapgpu_index_build: hash table overflow during insertion");
+    SG_CUDA(cudaMalloc((void **)&d_failed, 4));
+    uint64_t nBuckets = 0;
+    if (layout == SG_LAYOUT_BUCKET) {
+        // sector buckets keyed by the canonical seed (sg_bucket.h): every distinct seed is one slot
+        double load = sg_bucket_default_load();
+        bool done = false;
+        for (int attempt = 0; attempt < 4 && !done; attempt++, load *= 0.7) {
+            nBuckets = sg_bucket_count_for(distinct, seedLen, load);
+            if (ix->d_buckets) { cudaFree(ix->d_buckets); ix->d_buckets = nullptr; }
+            SG_CUDA(cudaMalloc((void **)&ix->d_buckets, (size_t)nBuckets * 32 + 64));
+            sg_build_fill_kernel<<<grid, 256>>>((unsigned long long *)ix->d_buckets, (long long)nBuckets * SG_BUCKET_SLOTS + 8, SG_BUCKET_EMPTY);
+            SG_CUDA(cudaMemset(ix->d_overflow, 0, (size_t)(overflowWords + 4) * 4));
+            SG_CUDA(cudaMemset(d_failed, 0, 4));
+            SG_CUDA(cudaMemset(d_stats + nTables + 2, 0, 8));
+            sg_build_insert_kernel<<<grid, 256>>>(sk, sv, nPos, keyBits, seedLen, ix->d_tableStart, ix->d_tableSize, nullptr, ix->d_overflow, d_stats + nTables + 2,
+                                                  nBases, d_failed, (unsigned long long *)ix->d_buckets, nBuckets);
+            SG_CUDA(cudaGetLastError());
+            int failed = 0;
+            SG_CUDA(cudaMemcpy(&failed, d_failed, 4, cudaMemcpyDeviceToHost));
+            done = !failed;
+        }
+        cudaFree((void *)sk); cudaFree((void *)sv); cudaFree(d_stats); cudaFree(d_failed);
+        if (!done) return sg_fail("snapgpu_index_build: bucket layout: a key landed too far from its home bucket even at low load");
+        hbm += (size_t)nBuckets * 32 + 64;
+    } else {
+        SG_CUDA(cudaMalloc((void **)&ix->d_tables, slots * 8 + 16)); hbm += slots * 8 + 16;
+        sg_build_fill_kernel<<<grid, 256>>>((unsigned long long *)ix->d_tables, (long long)slots + 2, 0x00000000ffffffffULL);
+        SG_CUDA(cudaGetLastError());
+        SG_CUDA(cudaMemset(ix->d_overflow, 0, (size_t)(overflowWords + 4) * 4));
+        SG_CUDA(cudaMemset(d_failed, 0, 4));
+        sg_build_insert_kernel<<<grid, 256>>>(sk, sv, nPos, keyBits, seedLen, ix->d_tableStart, ix->d_tableSize, (unsigned long long *)ix->d_tables,
+                                              ix->d_overflow, d_stats + nTables + 2, nBases, d_failed, nullptr, 0);
+        SG_CUDA(cudaGetLastError());
+        int failed = 0;
+        SG_CUDA(cudaMemcpy(&failed, d_failed, 4, cudaMemcpyDeviceToHost));
+        cudaFree((void *)sk); cudaFree((void *)sv); cudaFree(d_stats); cudaFree(d_failed);
+        if (failed) return sg_fail("snapgpu_index_build: hash table overflow during insertion");
+    }
 
     SG_CUDA(cudaMalloc((void **)&ix->d_contigStart, (size_t)nContigs * 8 + 16));
     SG_CUDA(cudaMemcpy(ix->d_contigStart, contigStarts, (size_t)nContigs * 8, cudaMemcpyHostToDevice));
@@ -744,11 +851,14 @@ static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const i
     v.bases = d_bases; v.contigStart = ix->d_contigStart; v.nBases = nBases; v.altFirstLocation = LLONG_MAX;
     v.overflowSize = overflowWords; v.nContigs = nContigs; v.seedLen = seedLen; v.keyBytes = keyBytes; v.nTables = nTables;
     v.large = 0; v.entryBytes = 8; v.chromosomePadding = chromosomePadding; v.invalidValue = 0xffffffffu;
+    v.layout = layout; v.pad0 = 0; v.buckets = ix->d_buckets; v.nBuckets = nBuckets;
     ix->view = v;
+    ix->builtOnDevice = true;
     memset(&ix->info, 0, sizeof(ix->info));
     ix->info.countOfBases = nBases; ix->info.seedLen = seedLen; ix->info.hashTableKeySize = keyBytes; ix->info.nHashTables = nTables;
     ix->info.locationSize = 4; ix->info.largeHashTable = 0; ix->info.chromosomePadding = chromosomePadding; ix->info.nContigs = nContigs;
-    ix->info.overflowTableSize = overflowWords; ix->info.hashTableSlots = slots; ix->info.hbmBytes = hbm;
+    ix->info.overflowTableSize = overflowWords; ix->info.hashTableSlots = layout == SG_LAYOUT_BUCKET ? nBuckets * SG_BUCKET_SLOTS : slots; ix->info.hbmBytes = hbm;
+    ix->info.reserved = layout;
     ix->h_tableStart = tstart; ix->h_tableSize = tsize;
     ix->h_tableUsed.assign(stats.begin(), stats.begin() + nTables);
     ix->h_contigStart.assign(contigStarts, contigStarts + nContigs);
@@ -767,7 +877,7 @@ int snapgpu_index_build(const char *bases, int64_t nBases, const int64_t *contig
     SG_CUDA(cudaMalloc((void **)&d_padded, (size_t)nBases + 2 * SG_N_PADDING));
     SG_CUDA(cudaMemset(d_padded, 'n', (size_t)nBases + 2 * SG_N_PADDING));
     SG_CUDA(cudaMemcpy(d_padded + SG_N_PADDING, bases, (size_t)nBases, cudaMemcpyHostToDevice));
-    int rc = build_index_on_device(d_padded, nBases, contigStarts, nContigs, seedLen, chromosomePadding, device, out);
+    int rc = build_index_on_device(d_padded, nBases, contigStarts, nContigs, seedLen, chromosomePadding, device, out, wanted_layout());
     if (rc) cudaFree(d_padded);
     return rc;
 }
@@ -783,7 +893,7 @@ int snapgpu_index_build_device(const char *d_bases, int64_t nBases, const int64_
     SG_CUDA(cudaMalloc((void **)&d_padded, (size_t)nBases + 2 * SG_N_PADDING));
     SG_CUDA(cudaMemset(d_padded, 'n', (size_t)nBases + 2 * SG_N_PADDING));
     SG_CUDA(cudaMemcpy(d_padded + SG_N_PADDING, d_bases, (size_t)nBases, cudaMemcpyDeviceToDevice));
-    int rc = build_index_on_device(d_padded, nBases, contigStarts, nContigs, seedLen, chromosomePadding, device, out);
+    int rc = build_index_on_device(d_padded, nBases, contigStarts, nContigs, seedLen, chromosomePadding, device, out, wanted_layout());
     if (rc) cudaFree(d_padded);
     return rc;
 }
@@ -796,6 +906,23 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
     if (!ix || !directory) return sg_fail("null argument");
     if (ix->view.entryBytes != 8 && ix->view.entryBytes != 12) return sg_fail("snapgpu_index_save: unsupported entry geometry");
     SG_CUDA(cudaSetDevice(ix->device));
+    if (ix->view.layout == SG_LAYOUT_BUCKET) {
+        // The reference's directory format holds the reference's tables.  An index built on the device is built once more, in that
+        // layout, from the same bases (same hit sets, same order), written out and dropped; an index that was re-laid from a directory
+        // has that directory.
+        if (!ix->builtOnDevice) return sg_fail("snapgpu_index_save: this index was loaded from a reference-format directory (copy that), or open it with SNAPGPU_INDEX_LAYOUT=snap");
+        uint8_t *d_padded = nullptr;
+        const size_t nb = (size_t)ix->view.nBases + 2 * SG_N_PADDING;
+        SG_CUDA(cudaMalloc((void **)&d_padded, nb));
+        SG_CUDA(cudaMemcpy(d_padded, ix->d_basesPadded, nb, cudaMemcpyDeviceToDevice));
+        snapgpu_index *tmp = nullptr;
+        if (build_index_on_device(d_padded, ix->view.nBases, ix->h_contigStart.data(), (uint32_t)ix->h_contigStart.size(), ix->view.seedLen,
+                                  ix->view.chromosomePadding, ix->device, &tmp, SG_LAYOUT_SNAP)) { cudaFree(d_padded); return 1; }
+        tmp->h_contigName = ix->h_contigName; tmp->h_contigIsAlt = ix->h_contigIsAlt;
+        const int rc = snapgpu_index_save(tmp, directory);
+        snapgpu_index_close(tmp);
+        return rc;
+    }
     std::string dir(directory);
     {
         // mkdir -p without a shell (a directory name is data, not a command line)
@@ -892,12 +1019,13 @@ int snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index 
     if (!ix) return sg_fail("out of memory");
     ix->device = device;
     const SgIndexView &sv = src->view;
-    const size_t tableBytes = (size_t)src->info.hashTableSlots * sv.entryBytes + 16;
+    const size_t tableBytes = sv.layout == SG_LAYOUT_BUCKET ? 0 : (size_t)src->info.hashTableSlots * sv.entryBytes + 16;
     const size_t nT = sv.nTables;
     size_t hbm = 0;
     #define DUP(dst, srcp, bytes) do { size_t b__ = (bytes); if (b__ == 0) b__ = 16; SG_CUDA(cudaMalloc((void **)&(dst), b__)); \
         if ((bytes) > 0) SG_CUDA(cudaMemcpyPeer((dst), device, (srcp), src->device, (bytes))); hbm += b__; } while (0)
-    DUP(ix->d_tables, src->d_tables, tableBytes);
+    if (sv.layout == SG_LAYOUT_BUCKET) { DUP(ix->d_buckets, src->d_buckets, (size_t)sv.nBuckets * 32 + 64); }
+    else { DUP(ix->d_tables, src->d_tables, tableBytes); }
     DUP(ix->d_tableStart, src->d_tableStart, nT * 8);
     DUP(ix->d_tableSize, src->d_tableSize, nT * 8);
     DUP(ix->d_tableMagic, src->d_tableMagic, nT * 8);
@@ -909,8 +1037,9 @@ int snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index 
     SG_CUDA(cudaDeviceSynchronize());
     SgIndexView v = sv;
     v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.tableMagic = ix->d_tableMagic; v.overflow = ix->d_overflow;
-    v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart;
+    v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart; v.buckets = ix->d_buckets;
     ix->view = v;
+    ix->builtOnDevice = src->builtOnDevice;
     ix->info = src->info; ix->info.hbmBytes = hbm;
     ix->h_tables_prob = src->h_tables_prob;
     ix->h_tableStart = src->h_tableStart; ix->h_tableSize = src->h_tableSize; ix->h_tableUsed = src->h_tableUsed;
@@ -930,7 +1059,7 @@ void snapgpu_index_close(snapgpu_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    cudaFree(ix->d_tables); cudaFree(ix->d_tableStart); cudaFree(ix->d_tableSize); cudaFree(ix->d_tableMagic); cudaFree(ix->d_overflow);
+    cudaFree(ix->d_tables); cudaFree(ix->d_buckets); cudaFree(ix->d_tableStart); cudaFree(ix->d_tableSize); cudaFree(ix->d_tableMagic); cudaFree(ix->d_overflow);
     cudaFree(ix->d_basesPadded); cudaFree(ix->d_contigStart); cudaFree(ix->d_tables_prob);
     delete ix;
 }
@@ -950,6 +1079,10 @@ int snapgpu_lookup_seeds(const snapgpu_index *idx, const char *seeds, int64_t nS
     SG_CUDA(cudaMemcpy(d_seeds, seeds, sb, cudaMemcpyHostToDevice));
     int blocks = (int)((nSeeds * 32 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    if (idx->view.layout == SG_LAYOUT_BUCKET) {
+        int bb = (int)((nSeeds + 255) / 256); if (bb > 148 * 8) bb = 148 * 8;
+        sg_lookup_bucket_kernel<<<bb, 256>>>(idx->view, d_seeds, nSeeds, maxHitsPerSeed, d_nHits, d_hits, d_probes);
+    } else
     sg_lookup_kernel<<<blocks, 256>>>(idx->view, d_seeds, nSeeds, maxHitsPerSeed, d_nHits, d_hits, d_probes);
     SG_CUDA(cudaGetLastError());
     SG_CUDA(cudaDeviceSynchronize());
@@ -957,6 +1090,50 @@ int snapgpu_lookup_seeds(const snapgpu_index *idx, const char *seeds, int64_t nS
     if (hits) SG_CUDA(cudaMemcpy(hits, d_hits, (size_t)nSeeds * 2 * maxHitsPerSeed * 4, cudaMemcpyDeviceToHost));
     if (probes) SG_CUDA(cudaMemcpy(probes, d_probes, (size_t)nSeeds * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_seeds); cudaFree(d_nHits); cudaFree(d_hits); cudaFree(d_probes);
+    return 0;
+}
+
+// Random 32-byte sector reads (see the header): the ceiling hash probing is measured against.
+__global__ void __launch_bounds__(256, 8)
+sg_random_sector_kernel(const uint8_t *tbl, unsigned long long nSectors, unsigned long long nAccess, unsigned long long salt, unsigned long long *sink)
+{
+    const unsigned long long nT = (unsigned long long)gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nAccess; i += nT) {
+        const unsigned long long unit = __umul64hi(sg_fmix64(i ^ salt), nSectors);
+        const uint4 *p = (const uint4 *)(tbl + unit * 32);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        acc += a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1ULL);
+}
+
+int snapgpu_measure_random_sector_rate(int device, uint64_t tableBytes, uint64_t nAccesses, double *sectorsPerSecond)
+{
+    if (!sectorsPerSecond || tableBytes < 4096 || nAccesses == 0) return sg_fail("bad argument");
+    if (require_device(device)) return 1;
+    uint8_t *tbl = nullptr; unsigned long long *sink = nullptr;
+    tableBytes = tableBytes / 4096 * 4096;
+    SG_CUDA(cudaMalloc((void **)&tbl, tableBytes));
+    SG_CUDA(cudaMalloc((void **)&sink, 8));
+    SG_CUDA(cudaMemset(tbl, 1, tableBytes));
+    SG_CUDA(cudaMemset(sink, 0, 8));
+    cudaEvent_t e0, e1;
+    SG_CUDA(cudaEventCreate(&e0)); SG_CUDA(cudaEventCreate(&e1));
+    sg_random_sector_kernel<<<148 * 8, 256>>>(tbl, tableBytes / 32, nAccesses / 8 + 1, 1, sink);
+    SG_CUDA(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        SG_CUDA(cudaEventRecord(e0));
+        sg_random_sector_kernel<<<148 * 8, 256>>>(tbl, tableBytes / 32, nAccesses, 77 + r, sink);
+        SG_CUDA(cudaEventRecord(e1));
+        SG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0; SG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(tbl); cudaFree(sink);
+    *sectorsPerSecond = (double)nAccesses / ((double)best * 1e-3);
     return 0;
 }
 
@@ -968,6 +1145,11 @@ int snapgpu_lookup_seeds_device(const snapgpu_index *idx, const char *d_seeds, i
     if (nSeeds <= 0) return 0;
     int blocks = (int)((nSeeds * 32 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    if (idx->view.layout == SG_LAYOUT_BUCKET) {
+        int bb = (int)((nSeeds + 255) / 256); if (bb > 148 * 8) bb = 148 * 8;
+        sg_lookup_bucket_kernel<<<bb, 256, 0, (cudaStream_t)cudaStream>>>(idx->view, (const uint8_t *)d_seeds, nSeeds, maxHitsPerSeed,
+                                                                        (long long *)d_nHits, d_hits, d_probes);
+    } else
     sg_lookup_kernel<<<blocks, 256, 0, (cudaStream_t)cudaStream>>>(idx->view, (const uint8_t *)d_seeds, nSeeds, maxHitsPerSeed,
                                                                    (long long *)d_nHits, d_hits, d_probes);
     SG_CUDA(cudaGetLastError());

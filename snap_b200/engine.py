@@ -81,7 +81,7 @@ N_COUNTERS = len(COUNTER_FIELDS) + 71
 EXPORTS = [
     "snapgpu_last_error", "snapgpu_abi_version", "snapgpu_device_count", "snapgpu_params_default",
     "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close", "snapgpu_index_replicate", "snapgpu_host_alloc", "snapgpu_host_free",
-    "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
+    "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
     "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
@@ -117,6 +117,7 @@ def lib():
         L.snapgpu_host_alloc.argtypes = [C.c_size_t]
         L.snapgpu_host_free.argtypes = [C.c_void_p]
         L.snapgpu_lookup_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_measure_random_sector_rate.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
         L.snapgpu_aligner_create.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.POINTER(C.c_void_p)]
         L.snapgpu_aligner_destroy.argtypes = [C.c_void_p]
         L.snapgpu_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
@@ -417,6 +418,13 @@ class FastqParser:
         if self.handle:
             lib().snapgpu_fastq_destroy(self.handle)
             self.handle = None
+
+
+def measure_random_sector_rate(table_bytes: int, n_accesses: int = 1 << 26, device: int = 0) -> float:
+    """Random 32-byte sector reads per second over a table of table_bytes (the roofline of hash probing)."""
+    r = C.c_double(0.0)
+    _check(lib().snapgpu_measure_random_sector_rate(device, table_bytes, n_accesses, C.byref(r)))
+    return r.value
 
 
 def test_lv(text, pat, qual, jobs, out_dtype, device=0, warps=0):

@@ -50,6 +50,15 @@ void *hs_index_open(const char *dir)
 
 void hs_index_close(void *v) { delete (HsIndex *)v; }
 
+// switches the index to the sector-bucket layout (sg_bucket.h), built on the host from the loaded reference-format tables
+int hs_index_relayout(void *v, double load)
+{
+    HsIndex *ix = (HsIndex *)v;
+    if (!sg_host_relayout(ix->host, load > 0 ? load : sg_bucket_default_load(), g_err)) return 1;
+    ix->view = ix->host.view();
+    return 0;
+}
+
 int hs_index_info(void *v, snapgpu_index_info *info)
 {
     HsIndex *ix = (HsIndex *)v;
@@ -57,7 +66,8 @@ int hs_index_info(void *v, snapgpu_index_info *info)
     info->countOfBases = ix->host.nBases; info->seedLen = ix->host.seedLen; info->hashTableKeySize = ix->host.keyBytes;
     info->nHashTables = ix->host.nTables; info->locationSize = 4; info->largeHashTable = ix->host.large;
     info->chromosomePadding = ix->host.chromosomePadding; info->nContigs = (uint32_t)ix->host.contigStart.size();
-    info->overflowTableSize = ix->host.overflowSize; info->hashTableSlots = ix->host.totalSlots;
+    info->overflowTableSize = ix->host.overflowSize; info->hashTableSlots = ix->host.layout == SG_LAYOUT_BUCKET ? ix->host.nBuckets * SG_BUCKET_SLOTS : ix->host.totalSlots;
+    info->reserved = ix->host.layout;
     return 0;
 }
 

@@ -39,6 +39,7 @@ def lib():
         L.hs_index_open.restype = C.c_void_p
         L.hs_index_open.argtypes = [C.c_char_p]
         L.hs_index_close.argtypes = [C.c_void_p]
+        L.hs_index_relayout.argtypes = [C.c_void_p, C.c_double]
         L.hs_lookup_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_tables.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_mapq.restype = C.c_int
@@ -81,6 +82,12 @@ class HsIndex:
         self.handle = lib().hs_index_open(directory.encode())
         if not self.handle:
             raise RuntimeError(lib().hs_last_error().decode())
+
+    def relayout(self, load: float = 0.0) -> "HsIndex":
+        """Switches to the sector-bucket layout (snap_b200/csrc/sg_bucket.h), built from the loaded reference-format tables."""
+        if lib().hs_index_relayout(self.handle, load) != 0:
+            raise RuntimeError(lib().hs_last_error().decode())
+        return self
 
     def lookup(self, seeds: np.ndarray, n: int, max_hits: int = 512):
         nh = np.zeros(2 * n, dtype=np.int64)

@@ -22,7 +22,27 @@ def engine():
 
 @pytest.fixture(scope="module")
 def gidx(engine, small_cfg):
+    """The reference-built index directory in HBM, in the library's default layout: 32-byte sector buckets (sg_bucket.h)."""
     ix = engine.Index.open(small_cfg.idx)
+    assert ix.info().reserved == 1
+    yield ix
+    ix.close()
+
+
+@pytest.fixture(scope="module")
+def gidx_snap(engine, small_cfg):
+    """The same directory kept in the reference's own table layout (SNAPGPU_INDEX_LAYOUT=snap): probe-for-probe parity of
+    SNAPHashTable::GetFirstValueForKey."""
+    old = os.environ.get("SNAPGPU_INDEX_LAYOUT")
+    os.environ["SNAPGPU_INDEX_LAYOUT"] = "snap"
+    try:
+        ix = engine.Index.open(small_cfg.idx)
+    finally:
+        if old is None:
+            del os.environ["SNAPGPU_INDEX_LAYOUT"]
+        else:
+            os.environ["SNAPGPU_INDEX_LAYOUT"] = old
+    assert ix.info().reserved == 0
     yield ix
     ix.close()
 
@@ -108,7 +128,11 @@ def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib, monkeypatch, p
         assert (want["agScore"] == got["agScore"]).all() and (want["textOffset"] == got["textOffset"]).all()
 
 
-def test_lookup_matches_reference(engine, gidx, small_cfg, reflib):
+@pytest.mark.parametrize("layout", ["bucket", "snap"])
+def test_lookup_matches_reference(engine, gidx, gidx_snap, small_cfg, reflib, layout):
+    """Hit sets (and their order) of both layouts against the reference's lookupSeed32; on the reference layout also the number of
+    entries examined, probe for probe."""
+    ix = gidx if layout == "bucket" else gidx_snap
     ridx = reflib.RefIndex(small_cfg.idx)
     rb = small_cfg.reads["noisy150"]
     seeds = []
@@ -116,14 +140,60 @@ def test_lookup_matches_reference(engine, gidx, small_cfg, reflib):
         b = rb.read(i)[0]
         if len(b) >= 60:
             seeds += [b[0:20], b[37:57]]
+    from snap_b200 import synth
+    c = small_cfg.contigs[1]
+    seeds += [c[o:o + 20].tobytes() for o in range(0, 4000)] + [synth.revcomp(c[o:o + 20]).tobytes() for o in range(0, 4000, 3)]
     arr = np.frombuffer(b"".join(seeds), dtype=np.uint8)
-    nh, hits, probes = gidx.lookup_seeds(arr, len(seeds), 512)
+    nh, hits, probes = ix.lookup_seeds(arr, len(seeds), 512)
     for i, s in enumerate(seeds):
         a = ridx.lookup(s, 512)
         assert (a[0], a[1]) == (nh[i, 0], nh[i, 1]), (i, s)
         assert np.array_equal(a[2], hits[i, 0, :min(a[0], 512)]) and np.array_equal(a[3], hits[i, 1, :min(a[1], 512)])
         if b"N" not in s:
-            assert a[4] + 2 == probes[i]
+            if layout == "snap":
+                assert a[4] + 2 == probes[i]
+            else:
+                assert probes[i] >= 4 and probes[i] % 4 == 0          # whole 32-byte buckets
+    if layout == "bucket":
+        assert np.mean(probes[probes > 0]) < 6.0                     # ~1.1 sectors per lookup at the default load
+
+
+def test_reference_layout_counts_entries_like_the_reference(engine, gidx_snap, small_cfg, reflib):
+    """On the reference's own table layout the work counters match the reference's probe for probe (nHashEntriesProbed included)."""
+    for opt in ("default_d14", "ne_d20"):
+        kw = OPTION_SETS[opt]
+        al = engine.SingleAligner(gidx_snap, engine.default_params(**kw), 4096)
+        ridx = reflib.RefIndex(small_cfg.idx)
+        for name in ("std150", "noisy150"):
+            rb = small_cfg.reads[name]
+            want, wctr = reflib.RefSingleAligner(ridx, reflib.default_params(**kw)).align(rb)
+            got, g = al.align(rb)
+            assert differing(want, got) == [], (opt, name)
+            for k in ("totalReads", "nHashTableLookups", "nHashEntriesProbed", "lvCalls", "affineGapCalls", "mapqHistogram"):
+                assert wctr[k] == g[k], (opt, name, k)
+        al.close()
+
+
+def test_device_built_bucket_index_saves_in_the_reference_format(engine, small_cfg, reflib, tmp_path):
+    """snapgpu_index_save of a device-built sector-bucket index: the directory is the reference's own format (its tables), loadable by
+    the unmodified reference, with the same hit sets."""
+    bases, starts = small_cfg.padded_bases()
+    bix = engine.Index.build(bases, starts, seed_len=20, chromosome_padding=2000)
+    assert bix.info().reserved == 1
+    d = str(tmp_path / "saved")
+    bix.save(d)
+    ridx, r0 = reflib.RefIndex(d), reflib.RefIndex(small_cfg.idx)
+    rb = small_cfg.reads["std150"]
+    for i in range(0, 300):
+        b = rb.read(i)[0]
+        for o in (0, 41, 120):
+            a, w = ridx.lookup(b[o:o + 20], 256), r0.lookup(b[o:o + 20], 256)
+            assert a[0] == w[0] and a[1] == w[1] and np.array_equal(a[2], w[2]) and np.array_equal(a[3], w[3])
+    p = reflib.default_params(maxDist=14)
+    want, _ = reflib.RefSingleAligner(r0, p).align(small_cfg.reads["noisy150"])
+    got, _ = reflib.RefSingleAligner(ridx, p).align(small_cfg.reads["noisy150"])
+    assert differing(want, got) == []
+    bix.close()
 
 
 @pytest.mark.parametrize("shared_hist", ["1", "0"])
@@ -164,7 +234,7 @@ def test_whole_reads_match_reference(engine, gidx, small_cfg, reflib, opt):
         ral.close()
         got, g = al.align(rb)
         assert differing(want, got) == [], (opt, name)
-        for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "nHashEntriesProbed",
+        for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups",
                   "lvCalls", "affineGapCalls", "nHitsIgnoredBecauseOfTooHighPopularity", "mapqHistogram"):
             assert wctr[k] == g[k], (opt, name, k)
     assert al.launch_count() >= len(small_cfg.reads)

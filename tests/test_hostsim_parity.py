@@ -101,6 +101,96 @@ def test_ag_fuzz(reflib, seed):
         assert (want[f] == got[f]).all(), f
 
 
+@pytest.mark.parametrize("which,load", [("idx", 0.0), ("idx_large", 0.0), ("idx", 0.9)])
+def test_bucket_layout_lookup_matches_reference(reflib, small_cfg, which, load):
+    """The sector-bucket re-layout (sg_bucket.h) of a reference-built index, default and -large: every seed returns the reference's hit
+    set in the reference's order, for seeds of reads (present, absent, both strands) and for the seeds with the longest hit lists."""
+    d = getattr(small_cfg, which)
+    ridx, hidx = reflib.RefIndex(d), hs.HsIndex(d).relayout(load)
+    seeds = []
+    for name in ("noisy150", "std150"):
+        rb = small_cfg.reads[name]
+        for i in range(0, 700):
+            b = rb.read(i)[0]
+            for o in range(0, len(b) - 20, 13):
+                seeds.append(b[o:o + 20])
+    seeds += [b"ACGT" * 5, b"A" * 20, b"AC" * 10, b"ACGTACGTACGTACGTAAAC"]        # palindromes / low complexity
+    for c in small_cfg.contigs:                                                     # every seed of a stretch of the genome itself
+        seeds += [c[o:o + 20].tobytes() for o in range(0, 3000)]
+    arr = np.frombuffer(b"".join(seeds), dtype=np.uint8)
+    nh, hits, probes = hidx.lookup(arr, len(seeds), 512)
+    multi = both = 0
+    for i, s in enumerate(seeds):
+        a = ridx.lookup(s, 512)
+        assert (a[0], a[1]) == (nh[i, 0], nh[i, 1]), (i, s)
+        assert np.array_equal(a[2], hits[i, 0, :min(a[0], 512)]) and np.array_equal(a[3], hits[i, 1, :min(a[1], 512)]), (i, s)
+        multi += a[0] > 1
+        both += a[0] > 0 and a[1] > 0
+    assert multi > 10
+    assert np.all(probes % 4 == 0) and (probes > 0).sum() > 0.9 * len(seeds)      # whole buckets (sectors) are examined; 0 = a seed with an N
+    if load == 0.9:
+        assert probes.max() > 4                                   # a crowded table does spill into neighbouring buckets
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_bucket_layout_both_strands_and_palindromes(reflib, tmp_path, large):
+    """Seeds that occur on BOTH strands (two slots of one canonical key), own-reverse-complement seeds (one slot serves both
+    directions, GenomeIndex.cpp:2131) and seeds repeated on both strands (two overflow lists)."""
+    from snap_b200 import synth
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    rnd = lambda n: acgt[rng.integers(0, 4, size=n)]
+    seg = rnd(300)
+    pal = np.frombuffer(b"ACGTACGTACGTACGTACGT", dtype=np.uint8)           # its own reverse complement
+    pal2 = np.frombuffer(b"AACCGGTTAACCGGTTAACC", dtype=np.uint8)
+    pal2 = np.concatenate([pal2[:10], synth.revcomp(pal2[:10])])
+    contig = np.concatenate([rnd(4000), seg, rnd(3000), synth.revcomp(seg), rnd(2000), pal, rnd(500), pal, rnd(800), pal2, rnd(1500),
+                             seg[:100], rnd(700), synth.revcomp(seg[:100]), rnd(2500)])
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, [contig, rnd(6000)])
+    d = str(tmp_path / "idx")
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fa, d, large=large)
+    ridx, hidx = reflib.RefIndex(d), hs.HsIndex(d).relayout()
+    seeds = [contig[o:o + 20].tobytes() for o in range(0, contig.size - 20)] + [synth.revcomp(contig[o:o + 20]).tobytes() for o in range(0, contig.size - 20, 7)]
+    arr = np.frombuffer(b"".join(seeds), dtype=np.uint8)
+    nh, hits, _ = hidx.lookup(arr, len(seeds), 64)
+    both = pals = 0
+    for i, s in enumerate(seeds):
+        a = ridx.lookup(s, 64)
+        assert (a[0], a[1]) == (nh[i, 0], nh[i, 1]), (i, s)
+        assert np.array_equal(a[2], hits[i, 0, :a[0]]) and np.array_equal(a[3], hits[i, 1, :a[1]]), (i, s)
+        both += a[0] > 0 and a[1] > 0
+        pals += s == synth.revcomp(np.frombuffer(s, dtype=np.uint8)).tobytes()
+    assert both > 300 and pals >= 3
+
+
+@pytest.mark.parametrize("opt", ["default_d14", "d8_h20", "ag_d20", "ne_d20"])
+def test_whole_reads_on_bucket_layout_match_reference(reflib, small_cfg, opt):
+    """Results do not depend on the index layout: same records, same work counters except the entries examined."""
+    p = reflib.default_params(**OPTION_SETS[opt])
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx).relayout()
+    for name, rb in small_cfg.reads.items():
+        ral = reflib.RefSingleAligner(ridx, p)
+        want, wctr = ral.align(rb)
+        ral.close()
+        got, gctr = hs.HsAligner(hidx, p).align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (opt, name)
+        g = reflib.counters_dict(gctr)
+        for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "lvCalls", "affineGapCalls",
+                  "nHitsIgnoredBecauseOfTooHighPopularity", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, name, k)
+
+
+def test_pairs_on_bucket_layout_match_reference(reflib, small_cfg):
+    rp, pp = reflib.default_params_paired(maxDist=27), reflib.default_paired_params()
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx_large).relayout()
+    for name in ("std150", "clipped150"):
+        pairs = small_cfg.pairs[name]
+        want, _ = reflib.RefPairedAligner(ridx, rp, pp).align(pairs)
+        got, _, _ = hs.HsPairedAligner(hidx, rp, pp).align(pairs, reflib.PAIRED_RESULT_DTYPE)
+        assert differing_pairs(want, got) == [], name
+
+
 @pytest.mark.parametrize("opt", list(OPTION_SETS))
 def test_whole_reads_match_reference(reflib, small_cfg, opt):
     p = reflib.default_params(**OPTION_SETS[opt])
