@@ -66,6 +66,7 @@ def parse_args():
                          "ag_d20 / ne_d20 = configs[3].  The others still run, as paired_phase / ag_forced_phase, unless --only-headline")
     ap.add_argument("--only-headline", action="store_true", help="skip the other configs' phases (profiling runs)")
     ap.add_argument("--no-sam-phase", action="store_true")
+    ap.add_argument("--no-stress-phase", action="store_true")
     ap.add_argument("--no-cli-crosscheck", action="store_true")
     ap.add_argument("--repeat-frac", type=float, default=float(os.environ.get("SNAPGPU_BENCH_REPEAT_FRAC", "0")),
                     help="SURVEY 8d stress variant: this fraction of the reference is drawn from a 10 kbp repeat library at 0-5 %% divergence")
@@ -180,11 +181,14 @@ class Ctx:
     pass
 
 
-def build_context(args):
+def build_context(args, repeat_frac=None, like=None):
+    """like: an existing context whose rank / device / process group this one shares (the stress genome's context)."""
     import torch
     import torch.distributed as dist
     from snap_b200 import engine, synth_device
     c = Ctx()
+    if repeat_frac is None:
+        repeat_frac = args.repeat_frac
     c.rank = int(os.environ.get("RANK", "0"))
     c.world = int(os.environ.get("WORLD_SIZE", "1"))
     c.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -194,15 +198,15 @@ def build_context(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     c.device = torch.device("cuda", c.local_rank)
     torch.cuda.set_device(c.device)
-    if c.world > 1:
+    if c.world > 1 and like is None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=c.device)
     n_contigs = 24
     c.contig_len = args.genome_mbp * 1_000_000 // n_contigs
     t0 = time.time()
     c.bases, c.starts = synth_device.make_genome(n_contigs, c.contig_len, seed=20260924, device=c.device)
-    if args.repeat_frac > 0:
-        synth_device.plant_repeats(c.bases, c.starts, c.contig_len, args.repeat_frac, seed=77)
+    if repeat_frac > 0:
+        synth_device.plant_repeats(c.bases, c.starts, c.contig_len, repeat_frac, seed=77)
     torch.cuda.synchronize()
     t1 = time.time()
     c.idx = engine.Index.build_device(c.bases.data_ptr(), c.bases.numel(), c.starts, seed_len=SEED_LEN, chromosome_padding=2000, device=c.device.index or 0)
@@ -213,6 +217,7 @@ def build_context(args):
                "overflow_words": int(info.overflowTableSize)}
     c.peak, c.peak_src = measured_peaks()
     c.ref = None
+    c.repeat_frac = repeat_frac
     return c
 
 
@@ -401,8 +406,8 @@ class RefContext:
             pass
         return {"cpu": model, "hw_threads": self.cores, "sockets": max(1, len(sockets)), "numa_nodes_interleaved": self.nodes,
                 "threads_used": getattr(self, "threads", self.cores), "thread_sweep_reads_per_s": getattr(self, "thread_sweep", None),
-                "thread_sweep_note": "fastest thread count of the sweep is used: the reference adds to one process-wide counter per probe chain (HashTable.h:109-110), which stops it scaling across sockets",
-                "pinning": "none (threads unpinned; index pages interleaved over the memory nodes with MPOL_INTERLEAVE, = numactl --interleave=all)",
+                "thread_sweep_note": "fastest (thread count, pinning) of the sweep is used: the reference adds to one process-wide counter per probe chain (HashTable.h:109-110), which stops it scaling across sockets",
+                "pinning": ("thread t pinned to logical CPU t (stock -b)" if getattr(self, "pinned", False) else "threads unpinned") + "; index pages interleaved over the memory nodes with MPOL_INTERLEAVE (= numactl --interleave=all)",
                 "index": "ours, exported to SNAP's directory format in tmpfs (%.0f s), mapped like stock -map (%.1f s)" % (self.export_s, self.load_s)}
 
     def run(self, name, batch, threads, build="stock", reps=1):
@@ -420,15 +425,22 @@ class RefContext:
         thread count (stock -t) is swept on a small sample and the FASTEST is what the baseline is quoted at."""
         if getattr(self, "threads", None):
             return self.threads
-        m = min(batch.n, 200000) // 2 * 2
+        m = min(batch.n, 500000) // 2 * 2
         sample = batch.slice(0, m)
         sweep = {}
         cands = sorted(set(t for t in (self.cores // 8, self.cores // 4, self.cores // 2, self.cores) if t >= 1))
         self.run(name, sample, self.cores)
-        for t in cands:
-            sweep[t] = round(m / min(self.run(name, sample, t)[2] for _ in range(2)), 1)
+        best = (0.0, self.cores, False)
+        for pin in (False, True):
+            self.reflib.set_thread_pinning(pin, builds=tuple(self.ridx))
+            for t in cands:
+                rate = round(m / self.run(name, sample, t)[2], 1)
+                sweep["%d%s" % (t, " pinned" if pin else "")] = rate
+                if rate > best[0]:
+                    best = (rate, t, pin)
         self.thread_sweep = sweep
-        self.threads = max(sweep, key=lambda t: sweep[t])
+        self.threads, self.pinned = best[1], best[2]
+        self.reflib.set_thread_pinning(self.pinned, builds=tuple(self.ridx))
         return self.threads
 
     def close(self):
@@ -827,6 +839,35 @@ def run_reference(args):
         ref.close()
 
 
+def stress_phase(args, c_main, failures):
+    import torch
+    c = build_context(args, repeat_frac=0.05, like=c_main)
+    W, K = 2, 3
+    batches = make_batches(c, args, "single", W + K)
+    res = run_workload(c, args, "single", batches, W, K)
+    res.pop("_clocks")
+    out = {"reference_genome": "%d Mbp, 5 %% of the bases overwritten with copies of 32 repeat units of 10 kbp at 0-5 %% divergence (a tenth of them tandem arrays of a 2-50 bp motif)" % args.genome_mbp,
+           "index_overflow_words": c.setup["overflow_words"], "index_build_s": c.setup["index_build_s"]}
+    for k in ("workload", "value", "unit", "steps", "warmup", "ms_per_step", "e2e", "gpu_launches", "per_read"):
+        out[k] = res[k]
+    if not args.no_cpu_baseline:
+        ref = RefContext(c.idx)
+        try:
+            ref.threads, ref.pinned = getattr(c_main, "ref_threads", (ref.cores, False))
+            ref.reflib.set_thread_pinning(ref.pinned, builds=tuple(ref.ridx))
+            saved = args.cpu_sample_reads
+            args.cpu_sample_reads = min(saved, 250000)
+            out["cpu_baseline"] = cpu_leg(ref, args, "single", res["_host0"], res["_records"], min_seconds=1.0)
+            args.cpu_sample_reads = saved
+            par = out["cpu_baseline"].get("parity_vs_reference")
+            if not par or par["differing"] != 0:
+                failures.append("parity: stress genome: %s" % par)
+        finally:
+            ref.close()
+    c.idx.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -912,6 +953,7 @@ def run_ours(args):
             ref = RefContext(c.idx)
             out["cpu_baseline"] = cpu_leg(ref, args, headline, head["_host0"], head["_records"], min_seconds=5.0, builds=("stock", "v3"), one_thread=True)
             out["cpu_baseline"]["host"] = ref.host()
+            c.ref_threads = (ref.threads, ref.pinned)
             for name, ph in phases.items():
                 ph["cpu_baseline"] = cpu_leg(ref, args, name, ph["_host0"], ph["_records"], min_seconds=2.0)
             for name, leg in [(headline, out["cpu_baseline"])] + [(n2, p2["cpu_baseline"]) for n2, p2 in phases.items()]:
@@ -941,12 +983,27 @@ def run_ours(args):
     for ph in [head] + list(phases.values()):
         for k in ("_records", "_host0", "_host_batches"):
             ph.pop(k, None)
+
+    # ---- SURVEY 8d's stress variant (rank 0, N=1): the same shape on a repeat-bearing reference (5 % of the bases from a 10 kbp repeat
+    #      library at 0-5 % divergence + tandem arrays), where overflow lists, maxHits skips and the merge logic actually run ----
+    if rank == 0 and world == 1 and not args.no_stress_phase and not args.only_headline and args.repeat_frac == 0:
+        try:
+            c.idx.close(); c.idx = None
+            del c.bases
+            torch.cuda.empty_cache()
+            out["stress_phase"] = stress_phase(args, c, failures)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            out["stress_phase"] = {"error": str(e)[:300]}
+            failures.append("stress_phase: " + str(e)[:200])
     if failures:
         out["failures"] = failures
     if rank == 0:
         emit(json.dumps(out))
     try:
-        c.idx.close()
+        if c.idx is not None:
+            c.idx.close()
     except Exception:  # pragma: no cover
         pass
     if world > 1:

@@ -40,7 +40,11 @@
 #include <string.h>
 #include <stdio.h>
 #include <time.h>
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <unistd.h>
+#include <sched.h>
 #include <sys/syscall.h>
 
 #include "../include/snapgpu.h"
@@ -646,8 +650,24 @@ int ref_single_align(void *v, _int64 n, const char *bases, const char *quals, co
  * way ParallelTask.h:40-120 runs SingleAlignerContext::runIterationThread.  Used for the CPU baseline.
  * Returns wall seconds spent aligning (aligner construction excluded, like AlignerContext.cpp:420).
  */
+/* Thread pinning for the multi-threaded baselines (stock SNAP's -b): thread t -> logical CPU t, so that a 32-thread run sits on the
+ * physical cores of one socket and a 64-thread run on the physical cores of both (the usual Linux numbering: SMT siblings last). */
+static int g_pin_threads = 0;
+void ref_set_thread_pinning(int on) { g_pin_threads = on; }
+
+static void pin_self(int t)
+{
+    if (!g_pin_threads) return;
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    if (n < 1) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET((int)(t % n), &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+}
+
 struct MTArg {
-    RefSingle *rs; _int64 begin, end;
+    RefSingle *rs; _int64 begin, end; int threadNo;
     const char *bases; const char *quals; const _uint64 *offsets; const unsigned *lens;
     snapgpu_single_result *results; snapgpu_counters ctr;
     pthread_barrier_t *start; int reps;
@@ -656,6 +676,7 @@ struct MTArg {
 static void *mt_main(void *v)
 {
     MTArg *a = (MTArg *)v;
+    pin_self(a->threadNo);
     pthread_barrier_wait(a->start);              // the clock starts when every thread exists and is waiting here
     for (int r = 0; r < a->reps; r++) {
         if (r > 0) memset(&a->ctr, 0, sizeof(a->ctr));
@@ -674,7 +695,7 @@ double ref_single_align_mt_reps(void *vidx, const snapgpu_params *p, int nThread
     pthread_barrier_t start;
     pthread_barrier_init(&start, NULL, nThreads + 1);
     for (int t = 0; t < nThreads; t++) {
-        args[t].start = &start; args[t].reps = reps;
+        args[t].start = &start; args[t].reps = reps; args[t].threadNo = t;
         args[t].rs = (RefSingle *)ref_single_create(vidx, p);
         args[t].begin = n * t / nThreads;
         args[t].end = n * (t + 1) / nThreads;
@@ -836,12 +857,13 @@ struct MTPairedArg {
     void *rp; _int64 begin, end;
     const char *bases; const char *quals; const _uint64 *offsets; const unsigned *lens;
     snapgpu_paired_result *results; _int64 nLV, nAG; int rc;
-    pthread_barrier_t *start; int reps;
+    pthread_barrier_t *start; int reps; int threadNo;
 };
 
 static void *mt_paired_main(void *v)
 {
     MTPairedArg *a = (MTPairedArg *)v;
+    pin_self(a->threadNo);
     pthread_barrier_wait(a->start);
     for (int r = 0; r < a->reps && !a->rc; r++) {
         a->nLV = a->nAG = 0;
@@ -861,7 +883,7 @@ double ref_paired_align_mt_reps(void *vidx, const snapgpu_params *p, const snapg
     pthread_barrier_t start;
     pthread_barrier_init(&start, NULL, nThreads + 1);
     for (int t = 0; t < nThreads; t++) {
-        args[t].start = &start; args[t].reps = reps;
+        args[t].start = &start; args[t].reps = reps; args[t].threadNo = t;
         args[t].rp = ref_paired_create(vidx, p, pp);
         args[t].begin = nPairs * t / nThreads;
         args[t].end = nPairs * (t + 1) / nThreads;

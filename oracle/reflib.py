@@ -171,6 +171,13 @@ def _load(path):
     return L
 
 
+def set_thread_pinning(on: bool, builds=("stock", "v3")) -> None:
+    """Stock SNAP's -b for the harness's multi-threaded runs: thread t -> logical CPU t (see ref_set_thread_pinning)."""
+    for b in builds:
+        if b == "stock" or (b in _libs):
+            lib(b).ref_set_thread_pinning(1 if on else 0)
+
+
 def numa_interleave() -> int:
     """MPOL_INTERLEAVE over all memory nodes for this thread and the threads it creates (see ref_numa_interleave): memory nodes
     interleaved over, 1 when there is a single node, -1 if refused."""

@@ -127,6 +127,11 @@ struct SgScratch {
     uint8_t  *agBt[2];               // [agRows*agCols] traceback bits; [0] forward object, [1] reverse object; PERSISTENT across calls
     int8_t   *agProf;                // [5*agCols] striped query profile of the current affine-gap call (device warp form)
     uint32_t agCols, agRows;
+    // Small copies in SHARED memory (the alignment kernels set them per warp; NULL / 0 elsewhere): Landau-Vishkin needs (k+1)(2k+1)
+    // cells of L and A for the k it is called with and k+1 backtrace entries -- a few hundred bytes at the usual k <= 15 -- and
+    // arrays that small must not live in (and be written back to) HBM.
+    int16_t  *lvLs;  uint8_t *lvAs;  uint32_t lvSmallCells;
+    int16_t  *lvBtMatchedS, *lvBtDS; uint8_t *lvBtActionS; uint32_t lvBtSmall;
 };
 
 SG_HD size_t sg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -177,7 +182,22 @@ SG_HD void sg_scratch_carve(const SgParams &p, uint8_t *base, SgScratch *s)
     s->agProf = (int8_t *)q;          q += sg_align_up(5 * agCols, 256);
     s->agCols = (uint32_t)agCols;
     s->agRows = (uint32_t)agRows;
+    s->lvLs = (int16_t *)0; s->lvAs = (uint8_t *)0; s->lvSmallCells = 0;
+    s->lvBtMatchedS = (int16_t *)0; s->lvBtDS = (int16_t *)0; s->lvBtActionS = (uint8_t *)0; s->lvBtSmall = 0;
 }
+
+// The per-warp block of shared memory behind those small copies and the four derived strings of a short read.
+#define SG_SMALL_LV_CELLS 512        // (k+1)(2k+1) <= 512  <=>  k <= 15
+#define SG_SMALL_BT 32
+#define SG_SMALL_READ_LEN 152
+struct SgWarpSmall {
+    int16_t lvL[SG_SMALL_LV_CELLS];
+    uint8_t lvA[SG_SMALL_LV_CELLS];
+    int16_t btMatched[SG_SMALL_BT], btD[SG_SMALL_BT];
+    uint8_t btAction[SG_SMALL_BT];
+    uint8_t str[4][SG_SMALL_READ_LEN + 16];  // rcRead, rcQual, revRead[0], revRead[1] (16 bytes of slack each, like the arena's)
+    uint8_t seedUsed[32];
+};
 
 // Per-read work counters accumulated by a worker (flushed with atomics at the end).
 struct SgWork {

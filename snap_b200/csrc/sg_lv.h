@@ -64,7 +64,8 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
     if (dir == -1) text--;
 
     SgLvState st;
-    st.L = S.lvL; st.A = S.lvA; st.kmax = k; st.stride = 2 * k + 1;
+    const bool smallLA = (uint32_t)((k + 1) * (2 * k + 1)) <= S.lvSmallCells;      // the cells of this call fit the shared-memory copy
+    st.L = smallLA ? S.lvLs : S.lvL; st.A = smallLA ? S.lvAs : S.lvA; st.kmax = k; st.stride = 2 * k + 1;
 
     int end = patternLen < textLen ? patternLen : textLen;
     int L00 = end > 0 ? sg_lv_cpm(pattern, 0, text, 0, dir, end, lane) : 0;      // countPerfectMatch(p, t, end) with end >= 0
@@ -126,7 +127,9 @@ SG_HDN void sg_lv_compute(const SgTables &T, const SgScratch &S, int dir, const 
 
     // Backtrace (LandauVishkin.h:286-304).  On the 'X' finish path L(e, lastBestD) was not written: the reference
     // then reads a stale cell into backtraceMatched[e], which only feeds `offset` after its last use.  We use 0.
-    int16_t *btMatched = S.lvBtMatched; int16_t *btD = S.lvBtD; uint8_t *btAction = S.lvBtAction;
+    const bool smallBt = (uint32_t)(k + 2) <= S.lvBtSmall;
+    int16_t *btMatched = smallBt ? S.lvBtMatchedS : S.lvBtMatched; int16_t *btD = smallBt ? S.lvBtDS : S.lvBtD;
+    uint8_t *btAction = smallBt ? S.lvBtActionS : S.lvBtAction;
     int curD = lastBestD;
     for (int curE = e; curE >= 1; curE--) {
         uint8_t a = st.getA(curE, curD);

@@ -232,15 +232,20 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
     __shared__ SgParams sPr;
     __shared__ SgAligner sA[8];
     __shared__ snapgpu_single_result sR[8];
+    __shared__ SgWarpSmall sW[8];        // small hot arrays of the warp: Landau-Vishkin cells, the derived strings of a short read
     if (threadIdx.x == 0) { sIx = ixParam; sPr = prParam; }
     __syncthreads();
     const SgIndexView &ix = sIx; const SgParams &pr = sPr;
     SgAligner &A = sA[threadIdx.x >> 5];
     snapgpu_single_result &r = sR[threadIdx.x >> 5];
+    SgWarpSmall &W = sW[threadIdx.x >> 5];
     A.ix = &ix; A.pr = &pr; A.tb = tb;
     A.maxK = pr.maxK;
     A.agCands = nullptr; A.nAgCands = 0; A.maxAgCands = 0; A.agCandsOverflow = 0;
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
+    A.sc.lvLs = W.lvL; A.sc.lvAs = W.lvA; A.sc.lvSmallCells = SG_SMALL_LV_CELLS;
+    A.sc.lvBtMatchedS = W.btMatched; A.sc.lvBtDS = W.btD; A.sc.lvBtActionS = W.btAction; A.sc.lvBtSmall = SG_SMALL_BT;
+    uint8_t *const arenaStr[5] = {A.sc.rcRead, A.sc.rcQual, A.sc.revRead[0], A.sc.revRead[1], A.sc.seedUsed};
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
     if (MODE == 2) A.ag.usePacked = sg_ag_small_scores(A.ag, pr.maxReadLen) ? pr.agSpecialised : 0;
     A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
@@ -272,6 +277,14 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
             cUseless++;
             if (lane == 0) results[i] = r;
             continue;
+        }
+        {
+            // the four derived strings (and the seed-used bits) of a short read live in shared memory, of a longer one in the arena
+            const bool shortRead = len <= SG_SMALL_READ_LEN;
+            A.sc.rcRead = shortRead ? W.str[0] : arenaStr[0]; A.sc.rcQual = shortRead ? W.str[1] : arenaStr[1];
+            A.sc.revRead[0] = shortRead ? W.str[2] : arenaStr[2]; A.sc.revRead[1] = shortRead ? W.str[3] : arenaStr[3];
+            A.sc.seedUsed = shortRead ? W.seedUsed : arenaStr[4];
+            __syncwarp();
         }
         if (MODE == 1) {
             const SgWork workBefore = A.work;
