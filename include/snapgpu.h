@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SNAPGPU_ABI_VERSION 2   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results` */
+#define SNAPGPU_ABI_VERSION 3   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
@@ -217,6 +217,22 @@ int  snapgpu_index_info_get(const snapgpu_index *idx, snapgpu_index_info *info);
  */
 int  snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index **out);
 void snapgpu_index_close(snapgpu_index *idx);
+
+/*
+ * A group of CUDA devices driven by ONE process -- the SNAP extension runs one feeder thread per device -- with an NCCL communicator
+ * per device (ncclCommInitAll; NCCL is loaded with dlopen at this call, not linked).  The path has exactly two collectives
+ * (SURVEY 8e): the index broadcast at start-up (one upload from the index directory, then ncclBroadcast over NVLink / NVSwitch instead
+ * of N uploads) and the all-reduce of the statistics at the end (AlignerStats.h:41-84; AlignerContext::finishThread adds the
+ * per-thread stats on the host in the reference, AlignerContext.cpp:241-245).  Reads shard across the devices without any exchange.
+ */
+typedef struct snapgpu_group snapgpu_group;
+int  snapgpu_group_create(const int *devices, int nDevices, snapgpu_group **out);
+void snapgpu_group_destroy(snapgpu_group *g);
+int  snapgpu_group_size(const snapgpu_group *g);
+/* src lives on the group's first device; out[nDevices]: out[0] = src itself, out[k] = an independent copy on device k (close each). */
+int  snapgpu_index_broadcast(snapgpu_group *g, snapgpu_index *src, snapgpu_index **out);
+/* counters[nDevices] (HOST): each entry is replaced by the sum over the group (ncclAllReduce(SUM) on the devices). */
+int  snapgpu_counters_allreduce(snapgpu_group *g, snapgpu_counters *counters);
 
 /*
  * Batched GenomeIndex::lookupSeed32 (reference SNAPLib/GenomeIndex.cpp:2095-2157).

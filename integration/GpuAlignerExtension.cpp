@@ -59,6 +59,8 @@ struct GpuEngine {
 
 struct GpuShared {
     pthread_mutex_t  lock;
+    snapgpu_group   *group;          // NCCL communicators over the devices (index broadcast, statistics all-reduce)
+    snapgpu_counters *counters;      // [nDevices] work counters of each device's batches
     int              nDevices;
     GpuEngine       *engines;
     int              nextThread;     // worker threads are numbered in the order they arrive
@@ -221,6 +223,7 @@ public:
     {
         pthread_mutex_init(&shared->lock, NULL);
         shared->nDevices = 0; shared->engines = NULL; shared->nextThread = 0; shared->opened = false; shared->refs = 1;
+        shared->group = NULL; shared->counters = NULL;
         shared->batchReads = 65536;
         if (const char *e = getenv("SNAPGPU_EXT_BATCH_READS")) { if (atoll(e) >= 2) shared->batchReads = atoll(e) / 2 * 2; }
     }
@@ -240,6 +243,8 @@ public:
                 pthread_mutex_destroy(&shared->engines[d].lock);
             }
             delete[] shared->engines;
+            delete[] shared->counters;
+            if (shared->group) snapgpu_group_destroy(shared->group);
             pthread_mutex_destroy(&shared->lock);
             delete shared;
         }
@@ -251,9 +256,29 @@ public:
     virtual bool runIterationThread(ReadSupplier *supplier, AlignerContext *context);
     virtual bool runIterationThread(PairedReadSupplier *supplier, AlignerContext *context);
 
+    // AlignerContext::printStats (AlignerContext.cpp:670): the engine's own work counters, summed over the devices with ncclAllReduce
+    virtual void printStats()
+    {
+        if (!shared->opened) return;
+        if (shared->group != NULL && snapgpu_counters_allreduce(shared->group, shared->counters)) gpuFatal("reducing the counters");
+        const snapgpu_counters &c = shared->counters[0];
+        WriteStatusMessage("snap-aligner-gpu: %d device%s: %lld hash lookups (%.1f slots examined each), %lld locations scored with Landau-Vishkin, %lld with affine gap\n",
+                           shared->nDevices, shared->nDevices == 1 ? "" : "s", (long long)c.nHashTableLookups,
+                           c.nHashTableLookups ? (double)c.nHashEntriesProbed / (double)c.nHashTableLookups : 0.0, (long long)c.lvCalls, (long long)c.affineGapCalls);
+    }
+
 private:
     GpuShared *shared;
     int        threadNo;
+
+    void addCounters(GpuEngine *engine, const snapgpu_counters &c)
+    {
+        pthread_mutex_lock(&shared->lock);
+        _int64 *dst = (_int64 *)&shared->counters[engine->device];
+        const _int64 *src = (const _int64 *)&c;
+        for (size_t k = 0; k < sizeof(snapgpu_counters) / sizeof(_int64); k++) dst[k] += src[k];
+        pthread_mutex_unlock(&shared->lock);
+    }
 
     // Opens the index image on every device on first use (AlignerExtension::initialize() gets no context, so this is where the
     // index directory is first known) and creates this thread's device's aligner handle.  Returns the thread's engine.
@@ -281,10 +306,18 @@ GpuEngine *GpuAlignerExtension::engineForThisThread(AlignerContext *context, boo
             shared->engines[d].device = d; shared->engines[d].index = NULL; shared->engines[d].aligner = NULL;
             pthread_mutex_init(&shared->engines[d].lock, NULL);
         }
-        // one upload from the index directory, then device-to-device replication over NVLink
+        // one upload from the index directory, then ncclBroadcast to the other devices over NVLink / NVSwitch
         if (snapgpu_index_open(context->options->indexDir, 0, &shared->engines[0].index)) gpuFatal("loading the index onto device 0");
-        for (int d = 1; d < nDev; d++) {
-            if (snapgpu_index_replicate(shared->engines[0].index, d, &shared->engines[d].index)) gpuFatal("replicating the index");
+        shared->counters = new snapgpu_counters[nDev];
+        memset(shared->counters, 0, sizeof(snapgpu_counters) * nDev);
+        if (nDev > 1) {
+            int *devs = new int[nDev];
+            snapgpu_index **copies = new snapgpu_index *[nDev];
+            for (int d = 0; d < nDev; d++) devs[d] = d;
+            if (snapgpu_group_create(devs, nDev, &shared->group)) gpuFatal("creating the device group (NCCL)");
+            if (snapgpu_index_broadcast(shared->group, shared->engines[0].index, copies)) gpuFatal("broadcasting the index");
+            for (int d = 1; d < nDev; d++) shared->engines[d].index = copies[d];
+            delete[] devs; delete[] copies;
         }
         shared->nDevices = nDev;
         shared->opened = true;
@@ -407,6 +440,7 @@ bool GpuAlignerExtension::runIterationThread(ReadSupplier *supplier, AlignerCont
     }
     stats->lvCalls = counters.lvCalls;
     stats->affineGapCalls = counters.affineGapCalls;
+    addCounters(engine, counters);
     batch.destroy();
     snapgpu_host_free(results);
     return true;             // this thread's share is consumed: the stock loop is skipped (SingleAligner.cpp:102-105)
@@ -512,6 +546,7 @@ bool GpuAlignerExtension::runIterationThread(PairedReadSupplier *supplier, Align
     }
     stats->lvCalls = counters.lvCalls;
     stats->affineGapCalls = counters.affineGapCalls;
+    addCounters(engine, counters);
     batch.destroy();
     snapgpu_host_free(results);
     return true;

@@ -751,9 +751,29 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
                 uint32_t offset = (direction == 0) ? nextSeedToTest : (readLen - seedLen - nextSeedToTest);
                 uint32_t limit = hits.nHits[direction] < pr.maxHits ? hits.nHits[direction] : pr.maxHits;
                 A.work.overflowWords += (hits.nHits[direction] > 1) ? limit : 0;
+                const uint32_t *hitList = hits.hits[direction];
+#if defined(__CUDA_ARCH__)
+                // long lists go through shared memory, one bulk asynchronous copy (TMA) per chunk (sg_warp_stage_hits)
+                const bool stageHits = pr.tmaMinHits != 0 && limit >= pr.tmaMinHits && A.sc.hitStageWords != 0;
+                uint32_t stagedFrom = 0, stagedN = 0, stagedLead = 0;
+#endif
                 #pragma unroll 1
                 for (uint32_t i = 0; i < limit; i++) {
-                    uint32_t genomeLocationOfThisHit = hits.hits[direction][i] - offset;       // 32-bit wrap like the reference
+#if defined(__CUDA_ARCH__)
+                    uint32_t hitWord;
+                    if (stageHits) {
+                        if (i >= stagedFrom + stagedN) {
+                            stagedFrom = i;
+                            stagedN = sg_warp_stage_hits(A.sc, hitList + i, limit - i, sg_lane(), &stagedLead);
+                        }
+                        hitWord = A.sc.hitStage[stagedLead + (i - stagedFrom)];
+                    } else {
+                        hitWord = hitList[i];
+                    }
+                    uint32_t genomeLocationOfThisHit = hitWord - offset;
+#else
+                    uint32_t genomeLocationOfThisHit = hitList[i] - offset;       // 32-bit wrap like the reference
+#endif
                     uint32_t ei = A.findElement(genomeLocationOfThisHit, direction);
                     if (ei != ~0u) {
                         // findCandidate (:1873-1878)

@@ -89,6 +89,7 @@ struct SgParams {
     uint32_t tableSlots;             // power of two >= 2*poolSize (our candidate lookup table)
     uint32_t maxReadLen;             // scratch sizing bound
     int32_t  agSpecialised;          // device tuning knob (no effect on results): SgAgParams.usePacked of the single-end kernel's second pass
+    uint32_t tmaMinHits;             // device tuning knob (no effect on results): hit lists of at least this many locations are staged through shared memory with bulk copies; 0 = never
 };
 
 // One candidate-table element: reference BaseAligner::HashTableElement (BaseAligner.h:223-258), compacted.
@@ -132,6 +133,10 @@ struct SgScratch {
     // arrays that small must not live in (and be written back to) HBM.
     int16_t  *lvLs;  uint8_t *lvAs;  uint32_t lvSmallCells;
     int16_t  *lvBtMatchedS, *lvBtDS; uint8_t *lvBtActionS; uint32_t lvBtSmall;
+    // Hit-list staging (device): long overflow lists are copied into shared memory with one bulk asynchronous copy (TMA,
+    // cp.async.bulk + mbarrier) per chunk instead of being read word by word from HBM.  hitStage: 16-byte aligned, hitStageWords
+    // words (it is the Landau-Vishkin cell block, idle while hits are filed); hitBar: the warp's mbarrier; 0 words = off.
+    uint32_t *hitStage; uint32_t hitStageWords; unsigned long long *hitBar; uint32_t hitPhase;
 };
 
 SG_HD size_t sg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -184,19 +189,25 @@ SG_HD void sg_scratch_carve(const SgParams &p, uint8_t *base, SgScratch *s)
     s->agRows = (uint32_t)agRows;
     s->lvLs = (int16_t *)0; s->lvAs = (uint8_t *)0; s->lvSmallCells = 0;
     s->lvBtMatchedS = (int16_t *)0; s->lvBtDS = (int16_t *)0; s->lvBtActionS = (uint8_t *)0; s->lvBtSmall = 0;
+    s->hitStage = (uint32_t *)0; s->hitStageWords = 0; s->hitBar = (unsigned long long *)0; s->hitPhase = 0;
 }
 
 // The per-warp block of shared memory behind those small copies and the four derived strings of a short read.
 #define SG_SMALL_LV_CELLS 512        // (k+1)(2k+1) <= 512  <=>  k <= 15
 #define SG_SMALL_BT 32
 #define SG_SMALL_READ_LEN 152
-struct SgWarpSmall {
-    int16_t lvL[SG_SMALL_LV_CELLS];
+struct
+#if defined(__CUDACC__)
+__align__(16)
+#endif
+SgWarpSmall {
+    int16_t lvL[SG_SMALL_LV_CELLS];      // (doubles as the hit-list staging buffer: 1024 bytes, 16-byte aligned)
     uint8_t lvA[SG_SMALL_LV_CELLS];
     int16_t btMatched[SG_SMALL_BT], btD[SG_SMALL_BT];
     uint8_t btAction[SG_SMALL_BT];
     uint8_t str[4][SG_SMALL_READ_LEN + 16];  // rcRead, rcQual, revRead[0], revRead[1] (16 bytes of slack each, like the arena's)
     uint8_t seedUsed[32];
+    unsigned long long hitBar;           // mbarrier of the warp's bulk copies
 };
 
 // Per-read work counters accumulated by a worker (flushed with atomics at the end).

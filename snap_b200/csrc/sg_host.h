@@ -113,7 +113,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
     // --- OverflowTable: raw u32[]
     if (!sg_read_file(dir + "/OverflowTable", buf, err)) return false;
     if (buf.size() != ix.overflowSize * 4) { err = "OverflowTable size mismatch"; return false; }
-    ix.overflow.assign((size_t)ix.overflowSize + 1, 0);
+    ix.overflow.assign((size_t)ix.overflowSize + 8, 0);
     if (!buf.empty()) memcpy(ix.overflow.data(), buf.data(), buf.size());
 
     // --- GenomeIndexHash: per table {u32 magic, u64 tableSize, u64 used, u32 keySize, u32 valueSize, u32 valueCount, valueSize bytes invalid} + data

@@ -209,3 +209,48 @@ __device__ __forceinline__ bool sg_warp_probe_finish(const SgIndexView &ix, cons
     }
     return true;
 }
+
+
+// ---- hit-list staging: one bulk asynchronous copy (TMA: cp.async.bulk, completion on an mbarrier) of up to SgScratch::hitStageWords
+//      words of an overflow list into the warp's shared-memory buffer.  `src` need only be 4-byte aligned: the copy starts at the
+//      16-byte boundary below it and *lead (0..3) says how many words precede the first wanted one.  All 32 lanes call this converged;
+//      lane 0 issues, every lane waits on the barrier (which also makes the data visible to it). ----
+__device__ __forceinline__ void sg_warp_hits_barrier_init(SgScratch &sc, int lane)
+{
+    if (sc.hitBar == (unsigned long long *)0) return;
+    if (lane == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sc.hitBar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t sg_warp_stage_hits(SgScratch &sc, const uint32_t *src, uint32_t nWords, int lane, uint32_t *lead)
+{
+    const uintptr_t a = (uintptr_t)src;
+    const uint32_t ld = (uint32_t)((a & 15u) >> 2);
+    uint32_t words = nWords + ld;
+    if (words > sc.hitStageWords) words = sc.hitStageWords;
+    const uint32_t bytes = ((words * 4u) + 15u) & ~15u;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sc.hitBar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sc.hitStage);
+    const uint32_t phase = sc.hitPhase;
+    __syncwarp();                    // nobody is still reading the previous chunk (or the phase)
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the buffer was last touched through the generic proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"((unsigned long long)(a & ~(uintptr_t)15)), "r"(bytes), "r"(bar) : "memory");
+    }
+    const uint32_t parity = phase & 1u;
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    sc.hitPhase = phase ^ 1u;        // (shared by the warp's lanes: every lane stores the same value, all of them read it before the first __syncwarp)
+    __syncwarp();
+    *lead = ld;
+    return words - ld;               // wanted words now at hitStage[ld ...]
+}

@@ -4,6 +4,8 @@
 // fallback anywhere in this file: every entry point that needs the device fails with an error when no
 // usable CUDA device / kernel image is present.
 #include <cuda_runtime.h>
+#include <nccl.h>                    // types only: NCCL is dlopen'ed, never linked (see snapgpu_group_create)
+#include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -245,6 +247,9 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
     sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
     A.sc.lvLs = W.lvL; A.sc.lvAs = W.lvA; A.sc.lvSmallCells = SG_SMALL_LV_CELLS;
     A.sc.lvBtMatchedS = W.btMatched; A.sc.lvBtDS = W.btD; A.sc.lvBtActionS = W.btAction; A.sc.lvBtSmall = SG_SMALL_BT;
+    A.sc.hitStage = (uint32_t *)W.lvL; A.sc.hitStageWords = SG_SMALL_LV_CELLS * 2 / 4; A.sc.hitBar = &W.hitBar; A.sc.hitPhase = 0;
+    __syncwarp();
+    sg_warp_hits_barrier_init(A.sc, lane);
     uint8_t *const arenaStr[5] = {A.sc.rcRead, A.sc.rcQual, A.sc.revRead[0], A.sc.revRead[1], A.sc.seedUsed};
     A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
     if (MODE == 2) A.ag.usePacked = sg_ag_small_scores(A.ag, pr.maxReadLen) ? pr.agSpecialised : 0;
@@ -711,7 +716,7 @@ static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
     UP(ix->d_tableStart, h.tableStart.data(), h.tableStart.size() * 8);
     UP(ix->d_tableSize, h.tableSize.data(), h.tableSize.size() * 8);
     UP(ix->d_tableMagic, h.tableMagic.data(), h.tableMagic.size() * 8);
-    UP(ix->d_overflow, h.overflow.data(), h.overflow.size() * 4);
+    UP(ix->d_overflow, h.overflow.data(), h.overflow.size() * 4);          // (sg_load_index_directory leaves 8 words of slack: bulk copies round up to 16 bytes)
     UP(ix->d_basesPadded, h.basesPadded.data(), h.basesPadded.size());
     UP(ix->d_contigStart, h.contigStart.data(), h.contigStart.size() * 8);
     sg_init_tables(ix->h_tables_prob, h.seedLen);
@@ -1013,6 +1018,46 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
     return 0;
 }
 
+// ---- copies of an index on other devices of the same process ----
+struct SgCloneCopy { void *dst; const void *src; size_t bytes; };
+
+// Allocates, on `device`, every array of `src`'s image and lists the copies that fill them; the caller performs the copies
+// (cudaMemcpyPeer, or one ncclBroadcast per array) and then calls clone_finish().
+static int clone_alloc(const snapgpu_index *src, int device, snapgpu_index **out, std::vector<SgCloneCopy> &copies)
+{
+    if (require_device(device)) return 1;
+    snapgpu_index *ix = new (std::nothrow) snapgpu_index;
+    if (!ix) return sg_fail("out of memory");
+    ix->device = device;
+    const SgIndexView &sv = src->view;
+    const size_t tableBytes = sv.layout == SG_LAYOUT_BUCKET ? 0 : (size_t)src->info.hashTableSlots * sv.entryBytes + 16;
+    const size_t nT = sv.nTables;
+    size_t hbm = 0;
+    #define DUP(dst, srcp, bytes) do { size_t b__ = (bytes); if (b__ == 0) b__ = 16; SG_CUDA(cudaMalloc((void **)&(dst), b__)); \
+        if ((bytes) > 0) { SgCloneCopy c__ = {(void *)(dst), (const void *)(srcp), (size_t)(bytes)}; copies.push_back(c__); } hbm += b__; } while (0)
+    if (sv.layout == SG_LAYOUT_BUCKET) { DUP(ix->d_buckets, src->d_buckets, (size_t)sv.nBuckets * 32 + 64); }
+    else { DUP(ix->d_tables, src->d_tables, tableBytes); }
+    DUP(ix->d_tableStart, src->d_tableStart, nT * 8);
+    DUP(ix->d_tableSize, src->d_tableSize, nT * 8);
+    DUP(ix->d_tableMagic, src->d_tableMagic, nT * 8);
+    DUP(ix->d_overflow, src->d_overflow, (size_t)(sv.overflowSize + 4) * 4);
+    DUP(ix->d_basesPadded, src->d_basesPadded, (size_t)sv.nBases + 2 * SG_N_PADDING);
+    DUP(ix->d_contigStart, src->d_contigStart, (size_t)sv.nContigs * 8);
+    DUP(ix->d_tables_prob, src->d_tables_prob, sizeof(SgTables));
+    #undef DUP
+    SgIndexView v = sv;
+    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.tableMagic = ix->d_tableMagic; v.overflow = ix->d_overflow;
+    v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart; v.buckets = ix->d_buckets;
+    ix->view = v;
+    ix->builtOnDevice = src->builtOnDevice;
+    ix->info = src->info; ix->info.hbmBytes = hbm;
+    ix->h_tables_prob = src->h_tables_prob;
+    ix->h_tableStart = src->h_tableStart; ix->h_tableSize = src->h_tableSize; ix->h_tableUsed = src->h_tableUsed;
+    ix->h_contigStart = src->h_contigStart; ix->h_contigName = src->h_contigName; ix->h_contigIsAlt = src->h_contigIsAlt;
+    *out = ix;
+    return 0;
+}
+
 // A copy of `src` on `device`: every array of the image is copied device to device (cudaMemcpyPeer: NVLink / NVSwitch when peer
 // access is possible, staged through the host by the driver otherwise).
 int snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index **out)
@@ -1028,36 +1073,154 @@ int snapgpu_index_replicate(const snapgpu_index *src, int device, snapgpu_index 
             cudaGetLastError();
         }
     }
-    snapgpu_index *ix = new (std::nothrow) snapgpu_index;
-    if (!ix) return sg_fail("out of memory");
-    ix->device = device;
-    const SgIndexView &sv = src->view;
-    const size_t tableBytes = sv.layout == SG_LAYOUT_BUCKET ? 0 : (size_t)src->info.hashTableSlots * sv.entryBytes + 16;
-    const size_t nT = sv.nTables;
-    size_t hbm = 0;
-    #define DUP(dst, srcp, bytes) do { size_t b__ = (bytes); if (b__ == 0) b__ = 16; SG_CUDA(cudaMalloc((void **)&(dst), b__)); \
-        if ((bytes) > 0) SG_CUDA(cudaMemcpyPeer((dst), device, (srcp), src->device, (bytes))); hbm += b__; } while (0)
-    if (sv.layout == SG_LAYOUT_BUCKET) { DUP(ix->d_buckets, src->d_buckets, (size_t)sv.nBuckets * 32 + 64); }
-    else { DUP(ix->d_tables, src->d_tables, tableBytes); }
-    DUP(ix->d_tableStart, src->d_tableStart, nT * 8);
-    DUP(ix->d_tableSize, src->d_tableSize, nT * 8);
-    DUP(ix->d_tableMagic, src->d_tableMagic, nT * 8);
-    DUP(ix->d_overflow, src->d_overflow, (size_t)(sv.overflowSize + 1) * 4);
-    DUP(ix->d_basesPadded, src->d_basesPadded, (size_t)sv.nBases + 2 * SG_N_PADDING);
-    DUP(ix->d_contigStart, src->d_contigStart, (size_t)sv.nContigs * 8);
-    DUP(ix->d_tables_prob, src->d_tables_prob, sizeof(SgTables));
-    #undef DUP
+    std::vector<SgCloneCopy> copies;
+    snapgpu_index *ix = nullptr;
+    if (clone_alloc(src, device, &ix, copies)) { if (ix) snapgpu_index_close(ix); return 1; }
+    for (size_t k = 0; k < copies.size(); k++) {
+        if (cudaMemcpyPeer(copies[k].dst, device, copies[k].src, src->device, copies[k].bytes) != cudaSuccess) {
+            std::string msg = std::string("snapgpu_index_replicate: cudaMemcpyPeer: ") + cudaGetErrorString(cudaGetLastError());
+            snapgpu_index_close(ix);
+            return sg_fail(msg);
+        }
+    }
     SG_CUDA(cudaDeviceSynchronize());
-    SgIndexView v = sv;
-    v.tables = ix->d_tables; v.tableStart = ix->d_tableStart; v.tableSize = ix->d_tableSize; v.tableMagic = ix->d_tableMagic; v.overflow = ix->d_overflow;
-    v.bases = ix->d_basesPadded + SG_N_PADDING; v.contigStart = ix->d_contigStart; v.buckets = ix->d_buckets;
-    ix->view = v;
-    ix->builtOnDevice = src->builtOnDevice;
-    ix->info = src->info; ix->info.hbmBytes = hbm;
-    ix->h_tables_prob = src->h_tables_prob;
-    ix->h_tableStart = src->h_tableStart; ix->h_tableSize = src->h_tableSize; ix->h_tableUsed = src->h_tableUsed;
-    ix->h_contigStart = src->h_contigStart; ix->h_contigName = src->h_contigName; ix->h_contigIsAlt = src->h_contigIsAlt;
     *out = ix;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A group of devices driven by ONE process (the SNAP extension: one feeder thread per device): NCCL communicators over them,
+// for the two collectives the path has -- the index broadcast at start-up and the statistics all-reduce at the end.
+// NCCL is loaded at run time (dlopen), not linked: a process that already carries an NCCL (PyTorch ships its own) keeps using that
+// one, and a single-device user of this library needs none.
+// ------------------------------------------------------------------------------------------------
+typedef ncclResult_t (*sg_ncclCommInitAll_t)(ncclComm_t *, int, const int *);
+typedef ncclResult_t (*sg_ncclCommDestroy_t)(ncclComm_t);
+typedef ncclResult_t (*sg_ncclGroup_t)(void);
+typedef ncclResult_t (*sg_ncclBroadcast_t)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*sg_ncclAllReduce_t)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+typedef const char *(*sg_ncclGetErrorString_t)(ncclResult_t);
+
+struct SgNccl {
+    void *lib = nullptr;
+    sg_ncclCommInitAll_t CommInitAll = nullptr; sg_ncclCommDestroy_t CommDestroy = nullptr; sg_ncclGroup_t GroupStart = nullptr, GroupEnd = nullptr;
+    sg_ncclBroadcast_t Broadcast = nullptr; sg_ncclAllReduce_t AllReduce = nullptr; sg_ncclGetErrorString_t GetErrorString = nullptr;
+};
+static SgNccl g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (int k = 0; k < 2 && !h; k++) h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return sg_fail(std::string("NCCL is not loadable (libnccl.so.2): ") + (dlerror() ? dlerror() : ""));
+    SgNccl n; n.lib = h;
+    n.CommInitAll = (sg_ncclCommInitAll_t)dlsym(h, "ncclCommInitAll"); n.CommDestroy = (sg_ncclCommDestroy_t)dlsym(h, "ncclCommDestroy");
+    n.GroupStart = (sg_ncclGroup_t)dlsym(h, "ncclGroupStart"); n.GroupEnd = (sg_ncclGroup_t)dlsym(h, "ncclGroupEnd");
+    n.Broadcast = (sg_ncclBroadcast_t)dlsym(h, "ncclBroadcast"); n.AllReduce = (sg_ncclAllReduce_t)dlsym(h, "ncclAllReduce");
+    n.GetErrorString = (sg_ncclGetErrorString_t)dlsym(h, "ncclGetErrorString");
+    if (!n.CommInitAll || !n.CommDestroy || !n.GroupStart || !n.GroupEnd || !n.Broadcast || !n.AllReduce || !n.GetErrorString) return sg_fail("libnccl.so.2 lacks a needed symbol");
+    g_nccl = n;
+    return 0;
+}
+
+#define SG_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return sg_fail(std::string(#call) + ": " + g_nccl.GetErrorString(r__)); } while (0)
+
+struct snapgpu_group {
+    std::vector<int> devices;
+    std::vector<ncclComm_t> comms;
+    std::vector<cudaStream_t> streams;
+    std::vector<snapgpu_counters *> d_counters;
+};
+
+int snapgpu_group_create(const int *devices, int nDevices, snapgpu_group **out)
+{
+    if (!devices || !out || nDevices < 1) return sg_fail("bad argument");
+    *out = nullptr;
+    for (int k = 0; k < nDevices; k++) if (require_device(devices[k])) return 1;
+    if (load_nccl()) return 1;
+    snapgpu_group *g = new (std::nothrow) snapgpu_group;
+    if (!g) return sg_fail("out of memory");
+    g->devices.assign(devices, devices + nDevices);
+    g->comms.assign(nDevices, (ncclComm_t)nullptr);
+    g->streams.assign(nDevices, (cudaStream_t)nullptr);
+    g->d_counters.assign(nDevices, (snapgpu_counters *)nullptr);
+    ncclResult_t r = g_nccl.CommInitAll(g->comms.data(), nDevices, devices);
+    if (r != ncclSuccess) { delete g; return sg_fail(std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r)); }
+    for (int k = 0; k < nDevices; k++) {
+        SG_CUDA(cudaSetDevice(devices[k]));
+        SG_CUDA(cudaStreamCreateWithFlags(&g->streams[k], cudaStreamNonBlocking));
+        SG_CUDA(cudaMalloc((void **)&g->d_counters[k], sizeof(snapgpu_counters)));
+    }
+    *out = g;
+    return 0;
+}
+
+void snapgpu_group_destroy(snapgpu_group *g)
+{
+    if (!g) return;
+    for (size_t k = 0; k < g->devices.size(); k++) {
+        cudaSetDevice(g->devices[k]);
+        if (g->comms[k]) g_nccl.CommDestroy(g->comms[k]);
+        if (g->streams[k]) cudaStreamDestroy(g->streams[k]);
+        cudaFree(g->d_counters[k]);
+    }
+    delete g;
+}
+
+int snapgpu_group_size(const snapgpu_group *g) { return g ? (int)g->devices.size() : 0; }
+
+// One upload, then ncclBroadcast of every array of the image from the group's first device: out[0] = src, out[k] = the copy on device k.
+int snapgpu_index_broadcast(snapgpu_group *g, snapgpu_index *src, snapgpu_index **out)
+{
+    if (!g || !src || !out) return sg_fail("null argument");
+    const int n = (int)g->devices.size();
+    if (src->device != g->devices[0]) return sg_fail("snapgpu_index_broadcast: the source index must live on the group's first device");
+    std::vector<std::vector<SgCloneCopy> > copies(n);
+    out[0] = src;
+    for (int k = 1; k < n; k++) {
+        out[k] = nullptr;
+        if (clone_alloc(src, g->devices[k], &out[k], copies[k])) return 1;
+    }
+    if (n == 1) return 0;
+    const size_t nArrays = copies[1].size();
+    for (size_t a = 0; a < nArrays; a++) {
+        SG_NCCL(g_nccl.GroupStart());
+        for (int k = 0; k < n; k++) {
+            const void *srcp = copies[1][a].src;
+            void *dst = k == 0 ? (void *)srcp : copies[k][a].dst;
+            ncclResult_t r = g_nccl.Broadcast(srcp, dst, copies[1][a].bytes, ncclUint8, 0, g->comms[k], g->streams[k]);
+            if (r != ncclSuccess) { g_nccl.GroupEnd(); return sg_fail(std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r)); }
+        }
+        SG_NCCL(g_nccl.GroupEnd());
+    }
+    for (int k = 0; k < n; k++) { SG_CUDA(cudaSetDevice(g->devices[k])); SG_CUDA(cudaStreamSynchronize(g->streams[k])); }
+    return 0;
+}
+
+// AlignerStats reduction (AlignerStats.h:41-84, AlignerContext.cpp:241-245): counters[k] = the HOST counters of device k's feeder; each
+// is replaced by the sum over the group, computed by ncclAllReduce(SUM) over the devices.
+int snapgpu_counters_allreduce(snapgpu_group *g, snapgpu_counters *counters)
+{
+    if (!g || !counters) return sg_fail("null argument");
+    const int n = (int)g->devices.size();
+    const size_t words = sizeof(snapgpu_counters) / 8;
+    for (int k = 0; k < n; k++) {
+        SG_CUDA(cudaSetDevice(g->devices[k]));
+        SG_CUDA(cudaMemcpyAsync(g->d_counters[k], &counters[k], sizeof(snapgpu_counters), cudaMemcpyHostToDevice, g->streams[k]));
+    }
+    SG_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < n; k++) {
+        ncclResult_t r = g_nccl.AllReduce(g->d_counters[k], g->d_counters[k], words, ncclInt64, ncclSum, g->comms[k], g->streams[k]);
+        if (r != ncclSuccess) { g_nccl.GroupEnd(); return sg_fail(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r)); }
+    }
+    SG_NCCL(g_nccl.GroupEnd());
+    for (int k = 0; k < n; k++) {
+        SG_CUDA(cudaSetDevice(g->devices[k]));
+        SG_CUDA(cudaMemcpyAsync(&counters[k], g->d_counters[k], sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, g->streams[k]));
+        SG_CUDA(cudaStreamSynchronize(g->streams[k]));
+    }
     return 0;
 }
 
@@ -1270,6 +1433,8 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     // candidate is rescored) ; without affine gap at all the first pass simply finishes everything.  SNAPGPU_TWO_PASS=0 turns it off.
     a->params.agSpecialised = 1;         // second pass: narrow-band / packed affine-gap forms (measured 16.61 -> 17.18 M reads/s; they cost throughput in the one-launch form)
     if (const char *e = getenv("SNAPGPU_SINGLE_AG_SPECIALISED")) a->params.agSpecialised = atoi(e);       // 0 off, 1 on, 2 on with the unrolled packed form
+    a->params.tmaMinHits = 0;            // hit-list staging through shared memory (bulk copies): measured on the repeat-bearing genome, see DESIGN.md
+    if (const char *e = getenv("SNAPGPU_TMA_MIN_HITS")) a->params.tmaMinHits = (uint32_t)atoi(e);
     a->twoPass = !a->params.noEditDistance;
     if (const char *e = getenv("SNAPGPU_TWO_PASS")) a->twoPass = atoi(e) != 0;
     if (a->twoPass) {

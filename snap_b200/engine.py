@@ -81,13 +81,14 @@ N_COUNTERS = len(COUNTER_FIELDS) + 71
 EXPORTS = [
     "snapgpu_last_error", "snapgpu_abi_version", "snapgpu_device_count", "snapgpu_params_default",
     "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close", "snapgpu_index_replicate", "snapgpu_host_alloc", "snapgpu_host_free",
+    "snapgpu_group_create", "snapgpu_group_destroy", "snapgpu_group_size", "snapgpu_index_broadcast", "snapgpu_counters_allreduce",
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
     "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
-ABI_VERSION = 2          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
+ABI_VERSION = 3          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
 _lib = None
 
 
@@ -113,6 +114,11 @@ def lib():
         L.snapgpu_index_info_get.argtypes = [C.c_void_p, C.POINTER(IndexInfo)]
         L.snapgpu_index_close.argtypes = [C.c_void_p]
         L.snapgpu_index_replicate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.snapgpu_group_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.snapgpu_group_destroy.argtypes = [C.c_void_p]
+        L.snapgpu_group_size.argtypes = [C.c_void_p]
+        L.snapgpu_index_broadcast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_counters_allreduce.argtypes = [C.c_void_p, C.c_void_p]
         L.snapgpu_host_alloc.restype = C.c_void_p
         L.snapgpu_host_alloc.argtypes = [C.c_size_t]
         L.snapgpu_host_free.argtypes = [C.c_void_p]
@@ -246,6 +252,34 @@ class Index:
     def close(self):
         if self.handle:
             lib().snapgpu_index_close(self.handle)
+            self.handle = None
+
+
+class Group:
+    """The devices one process drives, with NCCL communicators over them (snapgpu_group_create): index broadcast + counters all-reduce."""
+
+    def __init__(self, devices):
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _check(lib().snapgpu_group_create(arr, len(self.devices), C.byref(h)))
+        self.handle = h
+
+    def broadcast_index(self, index: Index):
+        out = (C.c_void_p * len(self.devices))()
+        _check(lib().snapgpu_index_broadcast(self.handle, index.handle, out))
+        return [index] + [Index(C.c_void_p(out[k]), self.devices[k]) for k in range(1, len(self.devices))]
+
+    def allreduce_counters(self, counters: np.ndarray) -> np.ndarray:
+        """counters: int64 [nDevices, N_COUNTERS] (host); returns the array with every row replaced by the column sums."""
+        c = np.ascontiguousarray(counters, dtype=np.int64).copy()
+        assert c.shape == (len(self.devices), N_COUNTERS)
+        _check(lib().snapgpu_counters_allreduce(self.handle, _p(c)))
+        return c
+
+    def close(self):
+        if self.handle:
+            lib().snapgpu_group_destroy(self.handle)
             self.handle = None
 
 

@@ -241,6 +241,61 @@ def test_whole_reads_match_reference(engine, gidx, small_cfg, reflib, opt):
     al.close()
 
 
+@pytest.mark.parametrize("min_hits", ["2", "8", "300"])
+def test_hit_lists_staged_with_bulk_copies_give_the_same_results(engine, gidx, small_cfg, reflib, monkeypatch, min_hits):
+    """SNAPGPU_TMA_MIN_HITS: overflow lists of at least that many hits are staged into shared memory with cp.async.bulk + mbarrier
+    (sg_warp_stage_hits) instead of being read from HBM word by word -- lists that start at any 4-byte offset, longer than the
+    staging buffer (chunked), and every list of a repeat-rich read set.  Records and counters must not change."""
+    monkeypatch.setenv("SNAPGPU_TMA_MIN_HITS", min_hits)
+    ridx = reflib.RefIndex(small_cfg.idx)
+    for opt in ("default_d14", "d8_h20"):
+        kw = OPTION_SETS[opt]
+        if min_hits == "300":
+            kw = dict(kw, maxHits=2000)          # lists longer than the 256-word staging buffer
+        al = engine.SingleAligner(gidx, engine.default_params(**kw), 4096)
+        for name in ("std150", "noisy150"):
+            rb = small_cfg.reads[name]
+            want, wctr = reflib.RefSingleAligner(ridx, reflib.default_params(**kw)).align(rb)
+            got, g = al.align(rb)
+            assert differing(want, got) == [], (opt, name)
+            for k in ("nHashTableLookups", "lvCalls", "affineGapCalls", "nHitsIgnoredBecauseOfTooHighPopularity", "mapqHistogram"):
+                assert wctr[k] == g[k], (opt, name, k)
+        al.close()
+
+
+def test_hit_lists_longer_than_the_staging_buffer(engine, reflib, tmp_path, monkeypatch):
+    """600 copies of a 150 bp unit: every seed of a read from the unit has a 600-entry overflow list, which -h 2000 lets through and
+    the bulk-copy staging takes in three chunks (the buffer holds 256 words); compared with the reference and with staging off."""
+    from snap_b200 import synth
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    unit = acgt[rng.integers(0, 4, size=150)]
+    parts = []
+    for i in range(600):
+        parts.append(acgt[rng.integers(0, 4, size=int(rng.integers(40, 90)))])
+        parts.append(unit)
+    contig = np.concatenate(parts + [acgt[rng.integers(0, 4, size=5000)]])
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, [contig])
+    d = str(tmp_path / "idx")
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fa, d)
+    reads = synth.make_reads([contig], 300, 100, seed=3)
+    kw = dict(maxDist=8, maxHits=2000)
+    want, wctr = reflib.RefSingleAligner(reflib.RefIndex(d), reflib.default_params(**kw)).align(reads)
+    ix = engine.Index.open(d)
+    out = {}
+    for tma in ("0", "16"):
+        monkeypatch.setenv("SNAPGPU_TMA_MIN_HITS", tma)
+        al = engine.SingleAligner(ix, engine.default_params(**kw), 1024)
+        got, g = al.align(reads)
+        al.close()
+        assert differing(want, got) == [], tma
+        out[tma] = g
+        assert g["lvCalls"] == wctr["lvCalls"] and g["nHashTableLookups"] == wctr["nHashTableLookups"]
+    assert out["0"]["nOverflowWordsRead"] == out["16"]["nOverflowWordsRead"] > 300 * 600
+    ix.close()
+
+
 def test_large_index(engine, small_cfg, reflib):
     ix = engine.Index.open(small_cfg.idx_large)
     assert ix.info().largeHashTable == 1

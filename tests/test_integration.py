@@ -22,7 +22,7 @@ def test_binding_is_built_and_links_the_product_library():
     assert "libsnapgpu.so" in out and "not found" not in out, out
     assert "libsnapref" not in out            # the oracle shim is not part of the drop-in
     src = open(os.path.join(ROOT, "integration", "GpuAlignerExtension.cpp")).read()
-    for sym in ("snapgpu_align_single", "snapgpu_align_paired", "snapgpu_index_open", "snapgpu_index_replicate", "snapgpu_aligner_create",
+    for sym in ("snapgpu_align_single", "snapgpu_align_paired", "snapgpu_index_open", "snapgpu_index_broadcast", "snapgpu_counters_allreduce", "snapgpu_aligner_create",
                 "snapgpu_paired_aligner_create"):
         assert sym in src
 
