@@ -139,6 +139,95 @@ SG_HDN void sg_agc_finish(const SgAgCigarScratch &S, const uint8_t *text, const 
     out->score = sg_ag_cigar_final(S, text, pattern, n_res, min_i, ops, maxOps, useM, &out->nOps, &out->netDel);
 }
 
+// ---- The 8 x int16 vector of the reference (__m128i), in two bodies with one interface.
+//   * host build: eight values, every operation a loop over them (what the CPU-side tests diff against the compiled reference);
+//   * device build: ONE value per thread -- the eight threads of an aligned "octet" of a warp (lanes 8q .. 8q+7) are the eight SSE lanes of
+//     one read's vectors (thread l holds element l), lane shifts are shuffles inside the octet and the lazy-F loop's joint "is any lane
+//     still live" test is a vote over the octet.  Four reads per warp; everything that is not a vector operation (the traceback, the
+//     heuristics, the text of the record) is executed identically by the eight threads of the octet, like the alignment kernels'
+//     warp-uniform state machine.  The DP functions below are written once, against this interface.
+#if defined(__CUDA_ARCH__)
+struct SgV8 {
+    int v;
+    __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 7u); }
+    __device__ __forceinline__ static unsigned mask() { return 0xffu << (threadIdx.x & 24u); }
+    __device__ __forceinline__ static SgV8 splat(int x) { SgV8 r; r.v = x; return r; }
+    template <class F> __device__ __forceinline__ static SgV8 gen(F f) { SgV8 r; r.v = f(lane()); return r; }                 // element l = f(l)
+    template <class F> __device__ __forceinline__ void each(F f) const { f(lane(), v); }                                      // f(l, element l)
+    __device__ __forceinline__ static SgV8 load16(const int16_t *p) { SgV8 r; r.v = p[lane()]; return r; }
+    __device__ __forceinline__ static SgV8 load8(const uint8_t *p) { SgV8 r; r.v = p[lane()]; return r; }
+    __device__ __forceinline__ void store16(int16_t *p) const { p[lane()] = (int16_t)v; }
+    __device__ __forceinline__ void store8(uint8_t *p) const { p[lane()] = (uint8_t)v; }
+    __device__ __forceinline__ SgV8 shiftUp(int fill) const { SgV8 r; const int up = __shfl_sync(mask(), v, (int)((threadIdx.x & 24u) | ((threadIdx.x + 7u) & 7u))); r.v = lane() == 0 ? fill : up; return r; }
+    __device__ __forceinline__ int elem(int l) const { return __shfl_sync(mask(), v, (int)((threadIdx.x & 24u) | (unsigned)l)); }
+    __device__ __forceinline__ bool any() const { return (__ballot_sync(mask(), v != 0) & mask()) != 0u; }
+    __device__ __forceinline__ static void sync() { __syncwarp(mask()); }
+};
+#define SG_V8_OP(expr) { SgV8 r; { const int a = x.v, b = y.v; (void)a; (void)b; r.v = (expr); } return r; }
+#else
+struct SgV8 {
+    int v[SG_VEC];
+    static SgV8 splat(int x) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = x; return r; }
+    template <class F> static SgV8 gen(F f) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = f(l); return r; }
+    template <class F> void each(F f) const { for (int l = 0; l < SG_VEC; l++) f(l, v[l]); }
+    static SgV8 load16(const int16_t *p) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = p[l]; return r; }
+    static SgV8 load8(const uint8_t *p) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = p[l]; return r; }
+    void store16(int16_t *p) const { for (int l = 0; l < SG_VEC; l++) p[l] = (int16_t)v[l]; }
+    void store8(uint8_t *p) const { for (int l = 0; l < SG_VEC; l++) p[l] = (uint8_t)v[l]; }
+    SgV8 shiftUp(int fill) const { SgV8 r; for (int l = SG_VEC - 1; l >= 1; l--) r.v[l] = v[l - 1]; r.v[0] = fill; return r; }
+    int elem(int l) const { return v[l]; }
+    bool any() const { for (int l = 0; l < SG_VEC; l++) if (v[l] != 0) return true; return false; }
+    static void sync() {}
+};
+#define SG_V8_OP(expr) { SgV8 r; for (int l = 0; l < SG_VEC; l++) { const int a = x.v[l], b = y.v[l]; (void)a; (void)b; r.v[l] = (expr); } return r; }
+#endif
+SG_HD SgV8 sg_v8_adds(const SgV8 &x, const SgV8 &y) SG_V8_OP(sg_sat16(a + b))         // _mm_adds_epi16
+SG_HD SgV8 sg_v8_subs(const SgV8 &x, const SgV8 &y) SG_V8_OP(sg_sat16(a - b))         // _mm_subs_epi16
+SG_HD SgV8 sg_v8_max(const SgV8 &x, const SgV8 &y) SG_V8_OP(a > b ? a : b)
+SG_HD SgV8 sg_v8_gt(const SgV8 &x, const SgV8 &y) SG_V8_OP(a > b ? 1 : 0)
+SG_HD SgV8 sg_v8_or(const SgV8 &x, const SgV8 &y) SG_V8_OP(a | b)
+SG_HD SgV8 sg_v8_bit(const SgV8 &x, const SgV8 &y) SG_V8_OP(a ? b : 0)                // x ? y : 0 (action bits under a comparison mask)
+
+// One DP vector step, shared by the main passes of the unbanded and the banded recurrence (:262-311 / :681-731): h = H of the diagonal
+// neighbours, f = the running horizontal gap.  Returns the vector's action bits; updates E, f, Hm1.
+SG_HD void sg_agc_vector_step(const int16_t *prow, int16_t *Eptr, int16_t *Hm1, const int16_t *Hptr, uint8_t *btRow, int idx8, SgV8 &h, SgV8 &f, const SgV8 &vOpen,
+                              const SgV8 &vExt)
+{
+    const SgV8 m = sg_v8_adds(h, SgV8::load16(prow + idx8));
+    SgV8 e = SgV8::load16(Eptr + idx8);
+    SgV8 act = sg_v8_gt(e, m);                                                  // bit 0
+    SgV8 hh = sg_v8_max(m, e);
+    act = sg_v8_or(act, sg_v8_bit(sg_v8_gt(f, hh), SgV8::splat(2)));
+    hh = sg_v8_max(hh, f);
+    hh.store16(Hm1 + idx8);
+    e = sg_v8_subs(e, vExt);
+    const SgV8 temp = sg_v8_subs(m, vOpen);
+    act = sg_v8_or(act, sg_v8_bit(sg_v8_gt(e, temp), SgV8::splat(4)));
+    e = sg_v8_max(e, temp);
+    e.store16(Eptr + idx8);
+    SgV8 ff = sg_v8_subs(f, vExt);
+    act = sg_v8_or(act, sg_v8_bit(sg_v8_gt(ff, temp), SgV8::splat(32)));
+    f = sg_v8_max(ff, temp);
+    act.store8(btRow + idx8);
+    h = SgV8::load16(Hptr + idx8);
+}
+
+// One lazy-F vector step (:325-347 / :747-770): returns whether any lane is still live.
+SG_HD bool sg_agc_lazy_step(int16_t *Hm1, uint8_t *btRow, int idx8, SgV8 &f, const SgV8 &vOpen, const SgV8 &vExt)
+{
+    SgV8 hh = SgV8::load16(Hm1 + idx8);
+    SgV8 act = SgV8::load8(btRow + idx8);
+    act = sg_v8_or(act, sg_v8_bit(sg_v8_gt(f, hh), SgV8::splat(2)));
+    hh = sg_v8_max(hh, f);
+    hh.store16(Hm1 + idx8);
+    const SgV8 temp = sg_v8_subs(hh, vOpen);
+    f = sg_v8_subs(f, vExt);
+    const SgV8 live = sg_v8_gt(f, temp);
+    act = sg_v8_or(act, sg_v8_bit(live, SgV8::splat(32)));
+    act.store8(btRow + idx8);
+    return live.any();
+}
+
 // AffineGapVectorizedWithCigar::computeGlobalScore with format == BAM_CIGAR_OPS.  P: sg_ag_params() of the scoring scheme
 // (gapOpenPenalty = open + extend, subPenalty negative), as in the reference's init (:64-92).
 SG_HDN void sg_ag_cigar_global(const SgAgParams &P, const SgAgCigarScratch &S, const uint8_t *text, int textLen, const uint8_t *pattern,
@@ -150,76 +239,37 @@ SG_HDN void sg_ag_cigar_global(const SgAgParams &P, const SgAgCigarScratch &S, c
     const int numVec = (patternLen + SG_VEC - 1) / SG_VEC;
     const int stride = numVec * SG_VEC;
     if (numVec > S.numVecMax || textLen > S.rowsMax) { out->score = -2; return; }
+    const SgV8 vOpen = SgV8::splat(open), vExt = SgV8::splat(ext);
     // query profile (:186-203) and first row (:222-239), striped: index j * 8 + l  <->  column l * numVec + j
     for (uint32_t t = 0; t < 5; t++) {
         for (int j = 0; j < numVec; j++) {
-            for (int l = 0; l < SG_VEC; l++) {
-                const int k = l * numVec + j;
-                S.prof[t * stride + j * SG_VEC + l] = (k < patternLen) ? (int16_t)sg_ag_sub(P, t, sg_base_value(pattern[k])) : (int16_t)-32768;
-            }
+            SgV8::gen([&](int l) { const int k = l * numVec + j; return (k < patternLen) ? (int)sg_ag_sub(P, t, sg_base_value(pattern[k])) : -32768; })
+                .store16(S.prof + t * stride + j * SG_VEC);
         }
     }
     for (int j = 0; j < numVec; j++) {
-        for (int l = 0; l < SG_VEC; l++) {
-            const int k = l * numVec + j;
-            S.H[j * SG_VEC + l] = (k < patternLen) ? (int16_t)(-(open + k * ext)) : (int16_t)-32768;
-            S.E[j * SG_VEC + l] = (int16_t)-32768;
-        }
+        SgV8::gen([&](int l) { const int k = l * numVec + j; return (k < patternLen) ? -(open + k * ext) : -32768; }).store16(S.H + j * SG_VEC);
+        SgV8::splat(-32768).store16(S.E + j * SG_VEC);
     }
+    SgV8::sync();
     int score = -32768, textUsed = -1;
     int16_t *Hptr = S.H, *Hm1 = S.Hm1;
     for (int i = 0; i < textLen; i++) {
         const int16_t *prow = S.prof + sg_base_value(text[i]) * stride;
         uint8_t *btRow = S.bt + (size_t)i * stride;
-        int f[SG_VEC], h[SG_VEC];
-        for (int l = 0; l < SG_VEC; l++) f[l] = -32768;
+        SgV8 f = SgV8::splat(-32768);
         const int hInit = (i > 0) ? -(open + (i - 1) * ext) : 0;
-        for (int l = SG_VEC - 1; l >= 1; l--) h[l] = Hptr[(numVec - 1) * SG_VEC + l - 1];      // h << one lane, lane 0 <- hInit
-        h[0] = (int16_t)hInit;
-        for (int j = 0; j < numVec; ++j) {
-            for (int l = 0; l < SG_VEC; l++) {
-                const int idx = j * SG_VEC + l;
-                const int m = sg_agc_adds(h[l], prow[idx]);
-                int e = S.E[idx];
-                int act = (e > m) ? 1 : 0;
-                int hh = m > e ? m : e;
-                if (f[l] > hh) act |= 2;
-                if (f[l] > hh) hh = f[l];
-                Hm1[idx] = (int16_t)hh;
-                e = sg_sat16(e - ext);
-                const int temp = sg_sat16(m - open);
-                if (e > temp) act |= 4;
-                if (temp > e) e = temp;
-                S.E[idx] = (int16_t)e;
-                int ff = sg_sat16(f[l] - ext);
-                if (ff > temp) act |= 32;
-                if (temp > ff) ff = temp;
-                f[l] = ff;
-                btRow[idx] = (uint8_t)act;
-                h[l] = Hptr[idx];
-            }
-        }
+        SgV8 h = SgV8::load16(Hptr + (numVec - 1) * SG_VEC).shiftUp((int)(int16_t)hInit);      // h << one lane, lane 0 <- hInit
+        for (int j = 0; j < numVec; ++j) sg_agc_vector_step(prow, S.E, Hm1, Hptr, btRow, j * SG_VEC, h, f, vOpen, vExt);
         // lazy F (:317-349)
         bool converged = false;
         for (int k = 0; k < SG_VEC - 1 && !converged; k++) {
-            for (int l = SG_VEC - 1; l >= 1; l--) f[l] = f[l - 1];
-            f[0] = -32768;
+            f = f.shiftUp(-32768);
             for (int j = 0; j < numVec && !converged; j++) {
-                bool any = false;
-                for (int l = 0; l < SG_VEC; l++) {
-                    const int idx = j * SG_VEC + l;
-                    int hh = Hm1[idx];
-                    int act = btRow[idx];
-                    if (f[l] > hh) { act |= 2; hh = f[l]; }
-                    Hm1[idx] = (int16_t)hh;
-                    const int temp = sg_sat16(hh - open);
-                    f[l] = sg_sat16(f[l] - ext);
-                    if (f[l] > temp) { act |= 32; any = true; }
-                    btRow[idx] = (uint8_t)act;
-                }
-                if (!any) converged = true;
+                if (!sg_agc_lazy_step(Hm1, btRow, j * SG_VEC, f, vOpen, vExt)) converged = true;
             }
         }
+        SgV8::sync();
         const int g = Hm1[((patternLen - 1) % numVec) * SG_VEC + (patternLen - 1) / numVec];
         if (g >= score) { score = g; textUsed = i; }
         int16_t *tmp = Hm1; Hm1 = Hptr; Hptr = tmp;
@@ -247,34 +297,37 @@ SG_HDN void sg_ag_cigar_banded(const SgAgParams &P, const SgAgCigarScratch &S, c
     const int numSeg = (patternLen + segLen - 1) / segLen;
     const int stride = numVec * numSeg * SG_VEC;
     if (numVec * numSeg > S.numVecMax || textLen > S.rowsMax) { out->score = -2; return; }
+    const SgV8 vOpen = SgV8::splat(open), vExt = SgV8::splat(ext);
     for (uint32_t t = 0; t < 5; t++) {
-        for (int sgi = 0; sgi < numSeg; sgi++) for (int j = 0; j < numVec; j++) for (int l = 0; l < SG_VEC; l++) {
-            const int idx = sgi * segLen + l * numVec + j;
-            S.prof[t * stride + (sgi * numVec + j) * SG_VEC + l] = (idx < patternLen) ? (int16_t)sg_ag_sub(P, t, sg_base_value(pattern[idx])) : (int16_t)-32768;
+        for (int sgi = 0; sgi < numSeg; sgi++) for (int j = 0; j < numVec; j++) {
+            SgV8::gen([&](int l) { const int idx = sgi * segLen + l * numVec + j; return (idx < patternLen) ? (int)sg_ag_sub(P, t, sg_base_value(pattern[idx])) : -32768; })
+                .store16(S.prof + t * stride + (sgi * numVec + j) * SG_VEC);
         }
     }
     {   // first row (:611-627): scoreFirstRow[] is declared outside the loops and only assigned for columns inside the pattern, so a
         // padding lane repeats the value its lane had in the previous vector
-        int16_t scoreFirstRow[SG_VEC] = {0, 0, 0, 0, 0, 0, 0, 0};
+        SgV8 scoreFirstRow = SgV8::splat(0);
         for (int sgi = 0; sgi < numSeg; sgi++) for (int j = 0; j < numVec; j++) {
-            for (int l = 0; l < SG_VEC; l++) {
+            const SgV8 prev = scoreFirstRow;
+            int lanePrev[SG_VEC];
+            prev.each([&](int l, int v) { lanePrev[l] = v; });
+            scoreFirstRow = SgV8::gen([&](int l) {
                 const int idx = sgi * segLen + l * numVec + j;
-                if (idx < patternLen) { int v = scoreInit - (open + idx * ext); scoreFirstRow[l] = (int16_t)(v > 0 ? v : 0); }
-            }
-            for (int l = 0; l < SG_VEC; l++) {
-                S.H[(sgi * numVec + j) * SG_VEC + l] = scoreFirstRow[l];
-                S.Hm1[(sgi * numVec + j) * SG_VEC + l] = 0;
-                S.E[(sgi * numVec + j) * SG_VEC + l] = 0;
-            }
+                if (idx < patternLen) { const int v = scoreInit - (open + idx * ext); return (int)(int16_t)(v > 0 ? v : 0); }
+                return lanePrev[l];
+            });
+            scoreFirstRow.store16(S.H + (sgi * numVec + j) * SG_VEC);
+            SgV8::splat(0).store16(S.Hm1 + (sgi * numVec + j) * SG_VEC);
+            SgV8::splat(0).store16(S.E + (sgi * numVec + j) * SG_VEC);
         }
     }
+    SgV8::sync();
     int score = scoreInit, textUsed = -1;
     int16_t *Hptr = S.H, *Hm1 = S.Hm1;
     for (int i = 0; i < textLen; i++) {
         const int16_t *prow = S.prof + sg_base_value(text[i]) * stride;
         uint8_t *btRow = S.bt + (size_t)i * stride;
-        int f[SG_VEC], h[SG_VEC];
-        for (int l = 0; l < SG_VEC; l++) f[l] = 0;
+        SgV8 f = SgV8::splat(0);
         int X0 = 0;
         const int bandBeg = (i - w) > 0 ? (i - w) : 0;
         const int bandEnd = (i + w) < (patternLen - 1) ? (i + w) : (patternLen - 1);
@@ -288,54 +341,19 @@ SG_HDN void sg_ag_cigar_banded(const SgAgParams &P, const SgAgCigarScratch &S, c
             } else {
                 hInit = (bandBeg > j * segLen) ? 0 : (int)Hptr[(j * numVec - 1) * SG_VEC + (SG_VEC - 1)];
             }
-            for (int l = SG_VEC - 1; l >= 1; l--) h[l] = Hptr[(j * numVec + numVec - 1) * SG_VEC + l - 1];
-            h[0] = hInit;
-            for (int k = 0; (k < numVec) && (j * segLen + k) <= bandEnd; k++) {
-                for (int l = 0; l < SG_VEC; l++) {
-                    const int idx = (j * numVec + k) * SG_VEC + l;
-                    const int m = sg_agc_adds(h[l], prow[idx]);
-                    int e = S.E[idx];
-                    int act = (e > m) ? 1 : 0;
-                    int hh = m > e ? m : e;
-                    if (f[l] > hh) { act |= 2; hh = f[l]; }
-                    Hm1[idx] = (int16_t)hh;
-                    e = sg_sat16(e - ext);
-                    const int temp = sg_sat16(m - open);
-                    if (e > temp) act |= 4;
-                    if (temp > e) e = temp;
-                    S.E[idx] = (int16_t)e;
-                    int ff = sg_sat16(f[l] - ext);
-                    if (ff > temp) act |= 32;
-                    if (temp > ff) ff = temp;
-                    f[l] = ff;
-                    btRow[idx] = (uint8_t)act;
-                    h[l] = Hptr[idx];
-                }
-            }
+            SgV8 h = SgV8::load16(Hptr + (j * numVec + numVec - 1) * SG_VEC).shiftUp(hInit);
+            for (int k = 0; (k < numVec) && (j * segLen + k) <= bandEnd; k++) sg_agc_vector_step(prow, S.E, Hm1, Hptr, btRow, (j * numVec + k) * SG_VEC, h, f, vOpen, vExt);
             bool converged = false;
             for (int k = 0; k < SG_VEC - 1 && !converged; k++) {
-                if (f[SG_VEC - 1] > X0) X0 = f[SG_VEC - 1];          // X = max(X, f >> 7 lanes)
-                for (int l = SG_VEC - 1; l >= 1; l--) f[l] = f[l - 1];
-                f[0] = 0;
+                { const int f7 = f.elem(SG_VEC - 1); if (f7 > X0) X0 = f7; }          // X = max(X, f >> 7 lanes)
+                f = f.shiftUp(0);
                 for (int v = 0; (v < numVec) && (j * segLen + v) <= bandEnd && !converged; v++) {
-                    bool any = false;
-                    for (int l = 0; l < SG_VEC; l++) {
-                        const int idx = (j * numVec + v) * SG_VEC + l;
-                        int hh = Hm1[idx];
-                        int act = btRow[idx];
-                        if (f[l] > hh) { act |= 2; hh = f[l]; }
-                        Hm1[idx] = (int16_t)hh;
-                        const int temp = sg_sat16(hh - open);
-                        f[l] = sg_sat16(f[l] - ext);
-                        if (f[l] > temp) { act |= 32; any = true; }
-                        btRow[idx] = (uint8_t)act;
-                    }
-                    if (!any) converged = true;
+                    if (!sg_agc_lazy_step(Hm1, btRow, (j * numVec + v) * SG_VEC, f, vOpen, vExt)) converged = true;
                 }
             }
-            f[0] = X0;                                               // f = X: (X0, 0, ..., 0)
-            for (int l = 1; l < SG_VEC; l++) f[l] = 0;
+            { const int x0 = X0; f = SgV8::gen([&](int l) { return l == 0 ? x0 : 0; }); }      // f = X: (X0, 0, ..., 0)
         }
+        SgV8::sync();
         if (bandEnd == patternLen - 1) {
             const int vecIdx = (bandEnd / segLen) * numVec + ((bandEnd % segLen) % numVec), elemIdx = (bandEnd % segLen) / numVec;
             const int g = Hm1[vecIdx * SG_VEC + elemIdx];
