@@ -612,45 +612,91 @@ def ingest_phase(args, host_batch, device, peak, peak_src):
     return out
 
 
-def sam_phase(args, idx, host_batch, results, paired):
-    """Output stage, first device form: snapgpu_sam_format_single / _paired over a bounded sample of the step's reads
-    and the engine's own result records, through the host-buffer C ABI (copies and the host-side packing of the records inside the
-    timed region).  Beside it the reference's routine for the same job, SAMFormat::computeCigarString, on ONE host thread over a
-    smaller sample (oracle/_ref; the reference's writer is single-threaded per output buffer)."""
+def sam_phase(args, c, host_batch, paired):
+    """Output stage on the headline's first batch, single-end: (1) the formatter alone with everything resident in HBM
+    (snapgpu_sam_format_single_device: reads as parsed on the device, the engine's own records, packed SAM text left in HBM; CUDA events);
+    (2) the same through the host-buffer ABI; (3) `e2e_with_output`: FASTQ text in pinned host memory -> H2D -> parse (device) -> align
+    (device) -> SAM records (device) -> D2H of the text, one batch after the other, wall clock."""
+    import torch
     from snap_b200 import engine, synth
-    n = min(131072, host_batch.n)
-    n -= n % 2
-    sample = host_batch.slice(0, n)
-    res = np.ascontiguousarray(results[:n // 2] if paired else results[:n])
-    ids = [(b"p%d/%d" % (i // 2, 1 + i % 2)) if paired else (b"r%d" % i) for i in range(n)]
-    p = engine.default_params(**PAIRED_KW) if paired else engine.default_params(maxDist=MAX_DIST)
-    fmt = engine.SamFormatter(idx, p, n, use_m=True)
+    device = c.device
+    if paired:
+        return {"note": "measured for the single-end headline only"}
+    n = host_batch.n
+    L = READ_LEN
+    text = fastq_text(host_batch)
+    h_text = torch.from_numpy(text).pin_memory()
+    p = engine.default_params(maxDist=MAX_DIST)
+    al = engine.SingleAligner(c.idx, p, max_batch_reads=n)
+    fq = engine.FastqParser(max_bytes=int(text.size) + 64, max_reads=n + 8, device=device.index or 0)
+    fmt = engine.SamFormatter(c.idx, p, n, use_m=True)
+    st = torch.cuda.Stream(device)
+    d_text = torch.empty((text.size + 64,), dtype=torch.uint8, device=device)
+    d_b = torch.empty((text.size // 2 + 64,), dtype=torch.uint8, device=device); d_q = torch.empty_like(d_b)
+    d_off = torch.empty((n + 8,), dtype=torch.int64, device=device); d_len = torch.empty((n + 8,), dtype=torch.int32, device=device)
+    d_ido = torch.empty((n + 8,), dtype=torch.int64, device=device); d_idl = torch.empty((n + 8,), dtype=torch.int32, device=device)
+    d_fc = torch.empty((n + 8,), dtype=torch.int32, device=device)
+    d_res = torch.empty((n, engine.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=device)
+    cap = n * (2 * L + 256)
+    d_sam = torch.empty((cap,), dtype=torch.uint8, device=device)
+    h_sam = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+
+    def pipeline(copy_back=True):
+        with torch.cuda.stream(st):
+            d_text[:text.size].copy_(h_text, non_blocking=True)
+        nr, used = fq.parse_device(d_text.data_ptr(), int(text.size), 2, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_ido.data_ptr(),
+                                   d_idl.data_ptr(), d_fc.data_ptr(), st.cuda_stream)
+        al.align_device(nr, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr(), 0, st.cuda_stream)
+        nbytes = fmt.format_device(nr, L, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_text.data_ptr(), d_ido.data_ptr(), d_idl.data_ptr(),
+                                   d_res.data_ptr(), d_sam.data_ptr(), cap, stream=st.cuda_stream)
+        if copy_back:
+            with torch.cuda.stream(st):
+                h_sam[:nbytes].copy_(d_sam[:nbytes], non_blocking=True)
+            st.synchronize()
+        return nr, nbytes
+
     try:
-        id_buf, id_offs, id_lens = fmt.pack_ids(ids)
-        sb = synth.ReadBatch(np.ascontiguousarray(sample.bases), np.ascontiguousarray(sample.quals), np.ascontiguousarray(sample.offsets), np.ascontiguousarray(sample.lens))
-        buf, used = fmt.format_arrays(sb, id_buf, id_offs, id_lens, res, paired)          # warm-up (and the text buffer)
-        t0 = time.perf_counter()
+        nr, nbytes = pipeline()                                   # warm-up: sizes the formatter's scratch
+        torch.cuda.synchronize()
+        ok = bool(nr == n and int((h_sam[:nbytes] == 10).sum().item()) == n)
+        # (1) the formatter alone, device-resident
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
+        e0.record(st)
         for _ in range(reps):
-            buf, used = fmt.format_arrays(sb, id_buf, id_offs, id_lens, res, paired, text=buf)
-        dt = (time.perf_counter() - t0) / reps
-        text = buf[:used].tobytes()
+            fmt.format_device(n, L, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_text.data_ptr(), d_ido.data_ptr(), d_idl.data_ptr(),
+                              d_res.data_ptr(), d_sam.data_ptr(), cap, stream=st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        # (3) FASTQ text on the host -> SAM text on the host
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pipeline()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / reps
+        # (2) host-buffer ABI
+        res_host = np.ascontiguousarray(d_res.cpu().numpy().view(engine.RESULT_DTYPE).reshape(-1))
+        ids = [b"r%08d" % i for i in range(n)]
+        id_buf, id_offs, id_lens = fmt.pack_ids(ids)
+        sb = synth.ReadBatch(np.ascontiguousarray(host_batch.bases), np.ascontiguousarray(host_batch.quals), np.ascontiguousarray(host_batch.offsets), np.ascontiguousarray(host_batch.lens))
+        buf, used = fmt.format_arrays(sb, id_buf, id_offs, id_lens, res_host, False)
+        t0 = time.perf_counter()
+        buf, used = fmt.format_arrays(sb, id_buf, id_offs, id_lens, res_host, False, text=buf)
+        host_s = time.perf_counter() - t0
+        same = bool(used == nbytes and np.array_equal(buf[:used], h_sam[:nbytes].numpy()))
     finally:
-        fmt.close()
-    out = {"kernel": "sg_sam_kernel (one thread per read; first form, not optimised)", "reads": int(n), "ms": round(dt * 1e3, 3),
-           "reads_per_s": round(n / dt, 1), "text_bytes": len(text), "text_gbs": round(len(text) / dt / 1e9, 3),
-           "records_ok": text.count(b"\n") == n}
-    if args.genome_mbp <= 300:
-        # (needs the index written out in the reference's format: only worth a second export for small genomes; the routine's cost
-        #  per read does not depend on the genome -- 0.11 M reads/s on one thread measured on the 0.36 Mbp test genome, DESIGN.md 8)
-        try:
-            out["cpu_reference_1thread_reads_per_s"] = sam_cpu_reference(idx, sample, res, paired)
-        except Exception as e:  # pragma: no cover
-            out["cpu_reference_error"] = str(e)[:200]
-    else:
-        out["cpu_reference_1thread_reads_per_s"] = None
-        out["cpu_reference_note"] = "SAMFormat::computeCigarString on one host thread: 0.107-0.112 M reads/s (measured on the test genome; not re-timed at this genome size)"
-    return out
+        fmt.close(); fq.close(); al.close()
+    alg = nbytes + n * (2 * L + engine.RESULT_DTYPE.itemsize + 10)          # the text written + the reads, ids and records read
+    return {"kernel": "sg_sam_kernel (one octet of threads per read: the 8 SSE lanes of the CIGAR DP) + scan + sg_sam_pack_kernel", "reads": int(n),
+            "ms": round(ms, 3), "reads_per_s": round(n / (ms / 1e3), 1), "text_bytes": int(nbytes), "text_gbs": round(nbytes / (ms / 1e3) / 1e9, 3),
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms / 1e3) / 1e9, 2), "peak": c.peak, "unit": "GB/s", "frac": round(alg / (ms / 1e3) / 1e9 / c.peak, 5),
+                         "note": "algorithmic bytes = SAM text written + reads, ids and result records read; the kernel is latency / issue bound (integer DP per read), not bandwidth bound"},
+            "host_buffer_abi_reads_per_s": round(n / host_s, 1), "records_ok": ok, "device_and_host_paths_agree": same,
+            "e2e_with_output": {"value": round(n / e2e_s, 1), "unit": "reads/s", "scope": "FASTQ text in pinned host memory -> H2D -> snapgpu_fastq_parse_device -> snapgpu_align_single_device -> "
+                                "snapgpu_sam_format_single_device -> D2H of the SAM text; batches one after the other (no overlap between batches)",
+                                "h2d_bytes_per_step": int(text.size), "d2h_bytes_per_step": int(nbytes), "ms_per_batch": round(e2e_s * 1e3, 2)},
+            "cpu_reference_note": "SAMFormat::computeCigarString on one host thread: 0.107-0.112 M reads/s (round 1, test genome)"}
 
 
 def sam_cpu_reference(idx, sample, res, paired, n_cpu=20000):
@@ -973,7 +1019,9 @@ def run_ours(args):
     # ---- output stage in isolation (rank 0, N=1): the headline's first batch and the engine's own records for it ----
     if rank == 0 and world == 1 and not args.no_seed_phase and not args.no_sam_phase and head.get("_records") is not None:
         try:
-            out["sam_phase"] = sam_phase(args, c.idx, head["_host0"], head["_records"], paired)
+            out["sam_phase"] = sam_phase(args, c, head["_host0"], paired)
+            if not out["sam_phase"].get("records_ok", True) or not out["sam_phase"].get("device_and_host_paths_agree", True):
+                failures.append("sam_phase: records malformed or the device-resident and host-buffer paths disagree")
         except Exception as e:
             import traceback
             traceback.print_exc()

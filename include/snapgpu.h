@@ -367,7 +367,7 @@ int  snapgpu_fastq_parse(snapgpu_fastq *f, const char *text, int64_t nBytes, int
  * Quality clipping (Read::clip, reference SNAPLib/Read.h:567-619): hand over the UNCLIPPED reads plus, per read, frontClipped[i] (bases clipped
  * at the front) and clippedLens[i] (length of the view that was aligned) -- e.g. snapgpu_fastq_parse's frontClipped and lens outputs next to
  * the text's own sequence lines -- or NULL for both when nothing was clipped.  The records then carry the whole read with S operations,
- * like stock SNAP's.  First form: one thread per read, not yet optimised.
+ * like stock SNAP's.  One octet of threads per read: the eight threads are the eight lanes of the reference's SSE vectors in the CIGAR DP.
  */
 typedef struct snapgpu_sam snapgpu_sam;
 int  snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, int32_t useM, int64_t maxBatchReads, snapgpu_sam **out);
@@ -380,6 +380,29 @@ int  snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases
                                const char *ids, const uint64_t *idOffsets, const uint32_t *idLens,
                                const uint32_t *frontClipped, const uint32_t *clippedLens,
                                const snapgpu_paired_result *results, char *text, int64_t textCapacity, int64_t *textBytes);
+
+/* SNAPGPU_FORMAT_BAM: the format calls write uncompressed BAM alignment records (block_size, the fixed fields, bin, CIGAR words, 4-bit
+ * sequence, qualities, the default tags: BAMFormat::writeRead / writePairs, reference SNAPLib/Bam.cpp:1033-1310, 1312-1509, 1812-2031) back
+ * to back instead of SAM text; snapgpu_bgzf_device wraps such a stream (or a header) into BGZF members, which is what a .bam file is made of. */
+enum { SNAPGPU_FORMAT_SAM = 0, SNAPGPU_FORMAT_BAM = 1 };
+int  snapgpu_sam_set_format(snapgpu_sam *s, int format);
+/* BGZF members (reference SNAPLib/GzipDataWriter.cpp; SAM spec 4.1) over nBytes of DEVICE data, written to d_out: members of up to 65280
+ * payload bytes, each ONE STORED deflate block with its CRC-32 -- valid BGZF that inflates to exactly the payload (no compressor runs on
+ * the device; the reference compresses, so files differ in size, not in content).  outCapacity >= nBytes + 31 per member.  Asynchronous on `cudaStream`. */
+int  snapgpu_bgzf_device(const char *d_in, int64_t nBytes, char *d_out, int64_t outCapacity, int64_t *outBytes, void *cudaStream);
+
+/* Device-resident forms: every array, and the text buffer, is a DEVICE pointer -- the reads as parsed by snapgpu_fastq_parse_device, the
+ * records as left by snapgpu_align_*_device -- so a batch goes from FASTQ text to SAM text without its reads or results visiting the
+ * host.  maxReadLen = the longest read of the batch; ids: concatenated, idOffsets / idLens per read.  The packed text is left in d_text;
+ * the call synchronises `cudaStream` (NULL = the handle's own) once, to learn *textBytes. */
+int  snapgpu_sam_format_single_device(snapgpu_sam *s, int64_t nReads, uint32_t maxReadLen, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                                      const uint32_t *d_lens, const char *d_ids, const uint64_t *d_idOffsets, const uint32_t *d_idLens,
+                                      const uint32_t *d_frontClipped, const uint32_t *d_clippedLens, const snapgpu_single_result *d_results,
+                                      char *d_text, int64_t textCapacity, int64_t *textBytes, void *cudaStream);
+int  snapgpu_sam_format_paired_device(snapgpu_sam *s, int64_t nReads, uint32_t maxReadLen, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                                      const uint32_t *d_lens, const char *d_ids, const uint64_t *d_idOffsets, const uint32_t *d_idLens,
+                                      const uint32_t *d_frontClipped, const uint32_t *d_clippedLens, const snapgpu_paired_result *d_results,
+                                      char *d_text, int64_t textCapacity, int64_t *textBytes, void *cudaStream);
 
 /* Number of kernel launches issued through this aligner since creation (bench.py's gpu_launches). */
 int64_t snapgpu_aligner_launch_count(const snapgpu_aligner *a);

@@ -28,6 +28,57 @@ struct SgAgCigarOut {
     int nOps, netDel, tailIns;
 };
 
+// ---- The 8 x int16 vector of the reference (__m128i), in two bodies with one interface.
+//   * host build: eight values, every operation a loop over them (what the CPU-side tests diff against the compiled reference);
+//   * device build: ONE value per thread -- the eight threads of an aligned "octet" of a warp (lanes 8q .. 8q+7) are the eight SSE lanes of
+//     one read's vectors (thread l holds element l), lane shifts are shuffles inside the octet and the lazy-F loop's joint "is any lane
+//     still live" test is a vote over the octet.  Four reads per warp; everything that is not a vector operation (the traceback, the
+//     heuristics, the text of the record) is executed identically by the eight threads of the octet, like the alignment kernels'
+//     warp-uniform state machine.  The DP functions below are written once, against this interface.
+#if defined(__CUDA_ARCH__)
+struct SgV8 {
+    int v;
+    __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 7u); }
+    __device__ __forceinline__ static unsigned mask() { return 0xffu << (threadIdx.x & 24u); }
+    __device__ __forceinline__ static SgV8 splat(int x) { SgV8 r; r.v = x; return r; }
+    template <class F> __device__ __forceinline__ static SgV8 gen(F f) { SgV8 r; r.v = f(lane()); return r; }                 // element l = f(l)
+    template <class F> __device__ __forceinline__ void each(F f) const { f(lane(), v); }                                      // f(l, element l)
+    __device__ __forceinline__ static SgV8 load16(const int16_t *p) { SgV8 r; r.v = p[lane()]; return r; }
+    __device__ __forceinline__ static SgV8 load8(const uint8_t *p) { SgV8 r; r.v = p[lane()]; return r; }
+    __device__ __forceinline__ void store16(int16_t *p) const { p[lane()] = (int16_t)v; }
+    __device__ __forceinline__ void store8(uint8_t *p) const { p[lane()] = (uint8_t)v; }
+    __device__ __forceinline__ SgV8 shiftUp(int fill) const { SgV8 r; const int up = __shfl_sync(mask(), v, (int)((threadIdx.x & 24u) | ((threadIdx.x + 7u) & 7u))); r.v = lane() == 0 ? fill : up; return r; }
+    __device__ __forceinline__ int elem(int l) const { return __shfl_sync(mask(), v, (int)((threadIdx.x & 24u) | (unsigned)l)); }
+    __device__ __forceinline__ bool any() const { return (__ballot_sync(mask(), v != 0) & mask()) != 0u; }
+    __device__ __forceinline__ static void sync() { __syncwarp(mask()); }
+    __device__ __forceinline__ static bool first() { return lane() == 0; }
+};
+#define SG_V8_OP(expr) { SgV8 r; { const int a = x.v, b = y.v; (void)a; (void)b; r.v = (expr); } return r; }
+#else
+struct SgV8 {
+    int v[SG_VEC];
+    static SgV8 splat(int x) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = x; return r; }
+    template <class F> static SgV8 gen(F f) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = f(l); return r; }
+    template <class F> void each(F f) const { for (int l = 0; l < SG_VEC; l++) f(l, v[l]); }
+    static SgV8 load16(const int16_t *p) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = p[l]; return r; }
+    static SgV8 load8(const uint8_t *p) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = p[l]; return r; }
+    void store16(int16_t *p) const { for (int l = 0; l < SG_VEC; l++) p[l] = (int16_t)v[l]; }
+    void store8(uint8_t *p) const { for (int l = 0; l < SG_VEC; l++) p[l] = (uint8_t)v[l]; }
+    SgV8 shiftUp(int fill) const { SgV8 r; for (int l = SG_VEC - 1; l >= 1; l--) r.v[l] = v[l - 1]; r.v[0] = fill; return r; }
+    int elem(int l) const { return v[l]; }
+    bool any() const { for (int l = 0; l < SG_VEC; l++) if (v[l] != 0) return true; return false; }
+    static void sync() {}
+    static bool first() { return true; }
+};
+#define SG_V8_OP(expr) { SgV8 r; for (int l = 0; l < SG_VEC; l++) { const int a = x.v[l], b = y.v[l]; (void)a; (void)b; r.v[l] = (expr); } return r; }
+#endif
+SG_HD SgV8 sg_v8_adds(const SgV8 &x, const SgV8 &y) SG_V8_OP(sg_sat16(a + b))         // _mm_adds_epi16
+SG_HD SgV8 sg_v8_subs(const SgV8 &x, const SgV8 &y) SG_V8_OP(sg_sat16(a - b))         // _mm_subs_epi16
+SG_HD SgV8 sg_v8_max(const SgV8 &x, const SgV8 &y) SG_V8_OP(a > b ? a : b)
+SG_HD SgV8 sg_v8_gt(const SgV8 &x, const SgV8 &y) SG_V8_OP(a > b ? 1 : 0)
+SG_HD SgV8 sg_v8_or(const SgV8 &x, const SgV8 &y) SG_V8_OP(a | b)
+SG_HD SgV8 sg_v8_bit(const SgV8 &x, const SgV8 &y) SG_V8_OP(a ? b : 0)                // x ? y : 0 (action bits under a comparison mask)
+
 SG_HD int sg_agc_adds(int a, int b) { return sg_sat16(a + b); }
 
 // computeFinalCigarString with format == BAM_CIGAR_OPS
@@ -106,87 +157,44 @@ SG_HDN void sg_agc_finish(const SgAgCigarScratch &S, const uint8_t *text, const 
     int min_i = 0;
     if (S.resAction[0] == 2) { min_i = 1; out->tailIns = S.resCount[0]; }
 
-    // "flip order of insertions followed by substitutions" (:454-476)
-    rowIdx = 0; colIdx = 0;
-    for (int i = n_res - 1; i >= min_i; --i) {
-        if (S.resAction[i] == 0) { rowIdx += S.resCount[i]; colIdx += S.resCount[i]; }
-        else if (S.resAction[i] == 1) { rowIdx += S.resCount[i]; }
-        else {
-            if (i > 0 && rowIdx < textUsed && colIdx < patternLen - 1) {
-                if ((pattern[colIdx + 1] == pattern[colIdx]) && (pattern[colIdx + 1] != text[rowIdx]) && (quality[colIdx] < 65)) {
-                    if ((i + 1 <= n_res - 1) && S.resAction[i + 1] == 0 && S.resCount[i - 1] > 1) { S.resCount[i + 1] += 1; rowIdx++; colIdx++; }
-                    if (S.resAction[i - 1] == 0 && S.resCount[i - 1] > 1) S.resCount[i - 1] -= 1;
+    // The two heuristics below read-modify-write the shared result arrays: on the device ONE thread of the octet does them (the eight
+    // run the rest of this function identically, storing the same values, which is harmless; an increment is not).
+    SgV8::sync();
+    if (SgV8::first()) {
+        // "flip order of insertions followed by substitutions" (:454-476)
+        rowIdx = 0; colIdx = 0;
+        for (int i = n_res - 1; i >= min_i; --i) {
+            if (S.resAction[i] == 0) { rowIdx += S.resCount[i]; colIdx += S.resCount[i]; }
+            else if (S.resAction[i] == 1) { rowIdx += S.resCount[i]; }
+            else {
+                if (i > 0 && rowIdx < textUsed && colIdx < patternLen - 1) {
+                    if ((pattern[colIdx + 1] == pattern[colIdx]) && (pattern[colIdx + 1] != text[rowIdx]) && (quality[colIdx] < 65)) {
+                        if ((i + 1 <= n_res - 1) && S.resAction[i + 1] == 0 && S.resCount[i - 1] > 1) { S.resCount[i + 1] += 1; rowIdx++; colIdx++; }
+                        if (S.resAction[i - 1] == 0 && S.resCount[i - 1] > 1) S.resCount[i - 1] -= 1;
+                    }
                 }
+                colIdx += S.resCount[i];
             }
-            colIdx += S.resCount[i];
+        }
+        // "flip order of insertions and substitution with match in between" (:478-502)
+        rowIdx = 0; colIdx = 0;
+        for (int i = n_res - 1; i >= min_i; --i) {
+            if (S.resAction[i] == 0) { rowIdx += S.resCount[i]; colIdx += S.resCount[i]; }
+            else if (S.resAction[i] == 1) { rowIdx += S.resCount[i]; }
+            else {
+                if (i > 0 && rowIdx + 1 < textUsed && colIdx + S.resCount[i] < patternLen - 1) {
+                    if ((pattern[colIdx + S.resCount[i]] == pattern[colIdx]) && (pattern[colIdx + S.resCount[i] + 1] != text[rowIdx + 1]) && (quality[colIdx] < 65)) {
+                        if ((i + 1 <= n_res - 1) && S.resAction[i + 1] == 0 && S.resCount[i - 1] > 2) { S.resCount[i + 1] += 2; rowIdx += 2; colIdx += 2; }
+                        if (S.resAction[i - 1] == 0 && S.resCount[i - 1] > 2) S.resCount[i - 1] -= 2;
+                    }
+                }
+                colIdx += S.resCount[i];
+            }
         }
     }
-    // "flip order of insertions and substitution with match in between" (:478-502)
-    rowIdx = 0; colIdx = 0;
-    for (int i = n_res - 1; i >= min_i; --i) {
-        if (S.resAction[i] == 0) { rowIdx += S.resCount[i]; colIdx += S.resCount[i]; }
-        else if (S.resAction[i] == 1) { rowIdx += S.resCount[i]; }
-        else {
-            if (i > 0 && rowIdx + 1 < textUsed && colIdx + S.resCount[i] < patternLen - 1) {
-                if ((pattern[colIdx + S.resCount[i]] == pattern[colIdx]) && (pattern[colIdx + S.resCount[i] + 1] != text[rowIdx + 1]) && (quality[colIdx] < 65)) {
-                    if ((i + 1 <= n_res - 1) && S.resAction[i + 1] == 0 && S.resCount[i - 1] > 2) { S.resCount[i + 1] += 2; rowIdx += 2; colIdx += 2; }
-                    if (S.resAction[i - 1] == 0 && S.resCount[i - 1] > 2) S.resCount[i - 1] -= 2;
-                }
-            }
-            colIdx += S.resCount[i];
-        }
-    }
+    SgV8::sync();
     out->score = sg_ag_cigar_final(S, text, pattern, n_res, min_i, ops, maxOps, useM, &out->nOps, &out->netDel);
 }
-
-// ---- The 8 x int16 vector of the reference (__m128i), in two bodies with one interface.
-//   * host build: eight values, every operation a loop over them (what the CPU-side tests diff against the compiled reference);
-//   * device build: ONE value per thread -- the eight threads of an aligned "octet" of a warp (lanes 8q .. 8q+7) are the eight SSE lanes of
-//     one read's vectors (thread l holds element l), lane shifts are shuffles inside the octet and the lazy-F loop's joint "is any lane
-//     still live" test is a vote over the octet.  Four reads per warp; everything that is not a vector operation (the traceback, the
-//     heuristics, the text of the record) is executed identically by the eight threads of the octet, like the alignment kernels'
-//     warp-uniform state machine.  The DP functions below are written once, against this interface.
-#if defined(__CUDA_ARCH__)
-struct SgV8 {
-    int v;
-    __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & 7u); }
-    __device__ __forceinline__ static unsigned mask() { return 0xffu << (threadIdx.x & 24u); }
-    __device__ __forceinline__ static SgV8 splat(int x) { SgV8 r; r.v = x; return r; }
-    template <class F> __device__ __forceinline__ static SgV8 gen(F f) { SgV8 r; r.v = f(lane()); return r; }                 // element l = f(l)
-    template <class F> __device__ __forceinline__ void each(F f) const { f(lane(), v); }                                      // f(l, element l)
-    __device__ __forceinline__ static SgV8 load16(const int16_t *p) { SgV8 r; r.v = p[lane()]; return r; }
-    __device__ __forceinline__ static SgV8 load8(const uint8_t *p) { SgV8 r; r.v = p[lane()]; return r; }
-    __device__ __forceinline__ void store16(int16_t *p) const { p[lane()] = (int16_t)v; }
-    __device__ __forceinline__ void store8(uint8_t *p) const { p[lane()] = (uint8_t)v; }
-    __device__ __forceinline__ SgV8 shiftUp(int fill) const { SgV8 r; const int up = __shfl_sync(mask(), v, (int)((threadIdx.x & 24u) | ((threadIdx.x + 7u) & 7u))); r.v = lane() == 0 ? fill : up; return r; }
-    __device__ __forceinline__ int elem(int l) const { return __shfl_sync(mask(), v, (int)((threadIdx.x & 24u) | (unsigned)l)); }
-    __device__ __forceinline__ bool any() const { return (__ballot_sync(mask(), v != 0) & mask()) != 0u; }
-    __device__ __forceinline__ static void sync() { __syncwarp(mask()); }
-};
-#define SG_V8_OP(expr) { SgV8 r; { const int a = x.v, b = y.v; (void)a; (void)b; r.v = (expr); } return r; }
-#else
-struct SgV8 {
-    int v[SG_VEC];
-    static SgV8 splat(int x) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = x; return r; }
-    template <class F> static SgV8 gen(F f) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = f(l); return r; }
-    template <class F> void each(F f) const { for (int l = 0; l < SG_VEC; l++) f(l, v[l]); }
-    static SgV8 load16(const int16_t *p) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = p[l]; return r; }
-    static SgV8 load8(const uint8_t *p) { SgV8 r; for (int l = 0; l < SG_VEC; l++) r.v[l] = p[l]; return r; }
-    void store16(int16_t *p) const { for (int l = 0; l < SG_VEC; l++) p[l] = (int16_t)v[l]; }
-    void store8(uint8_t *p) const { for (int l = 0; l < SG_VEC; l++) p[l] = (uint8_t)v[l]; }
-    SgV8 shiftUp(int fill) const { SgV8 r; for (int l = SG_VEC - 1; l >= 1; l--) r.v[l] = v[l - 1]; r.v[0] = fill; return r; }
-    int elem(int l) const { return v[l]; }
-    bool any() const { for (int l = 0; l < SG_VEC; l++) if (v[l] != 0) return true; return false; }
-    static void sync() {}
-};
-#define SG_V8_OP(expr) { SgV8 r; for (int l = 0; l < SG_VEC; l++) { const int a = x.v[l], b = y.v[l]; (void)a; (void)b; r.v[l] = (expr); } return r; }
-#endif
-SG_HD SgV8 sg_v8_adds(const SgV8 &x, const SgV8 &y) SG_V8_OP(sg_sat16(a + b))         // _mm_adds_epi16
-SG_HD SgV8 sg_v8_subs(const SgV8 &x, const SgV8 &y) SG_V8_OP(sg_sat16(a - b))         // _mm_subs_epi16
-SG_HD SgV8 sg_v8_max(const SgV8 &x, const SgV8 &y) SG_V8_OP(a > b ? a : b)
-SG_HD SgV8 sg_v8_gt(const SgV8 &x, const SgV8 &y) SG_V8_OP(a > b ? 1 : 0)
-SG_HD SgV8 sg_v8_or(const SgV8 &x, const SgV8 &y) SG_V8_OP(a | b)
-SG_HD SgV8 sg_v8_bit(const SgV8 &x, const SgV8 &y) SG_V8_OP(a ? b : 0)                // x ? y : 0 (action bits under a comparison mask)
 
 // One DP vector step, shared by the main passes of the unbanded and the banded recurrence (:262-311 / :681-731): h = H of the diagonal
 // neighbours, f = the running horizontal gap.  Returns the vector's action bits; updates E, f, Hm1.

@@ -24,6 +24,7 @@
 #include "sg_build.cuh"
 #include "sg_fastq.cuh"
 #include "sg_sam.h"
+#include "sg_bam.h"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -1829,18 +1830,22 @@ int snapgpu_align_paired(snapgpu_aligner *a, int64_t nPairs, const char *bases, 
 // FASTQ ingest
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
-// Output stage: SAM records on the device.  First form: ONE THREAD PER READ (pair) running the scalar
-// restatements of sg_lv_cigar.h / sg_ag_cigar.h / sg_cigar.h / sg_sam.h -- the code the host tests pin against the
-// reference binary's SAM file -- each into its own fixed-size slot; the host wrapper packs the slots.
+// Output stage: SAM records on the device.
+// ONE OCTET OF THREADS PER READ (pair): the eight threads of an aligned octet of a warp are the eight SSE lanes of the reference's
+// AffineGapVectorizedWithCigar vectors (sg_ag_cigar.h: SgV8) -- the DP that regenerates the CIGAR of every read with a mismatch is the
+// bulk of the writer's work -- and run everything else of SAMFormat::writeRead / writePairs (sg_lv_cigar.h, sg_cigar.h, sg_sam.h)
+// identically, storing the same values.  Four reads per warp.  Each record goes into a slot; a scan of the record lengths and a
+// warp-per-record copy then pack the slots into contiguous text on the device, so only the text crosses the bus.
 // ------------------------------------------------------------------------------------------------
-struct SgSamScratchLayout { size_t lvInts, agVec, agRows, agRes, perThread; uint32_t maxReadLen; };
+struct SgSamScratchLayout { size_t lvInts, agVec, agRows, agRes, perOctet; uint32_t maxReadLen; };
 
 static SgSamScratchLayout sam_layout(uint32_t maxReadLen)
 {
     SgSamScratchLayout l;
     l.maxReadLen = maxReadLen;
     l.lvInts = sg_lv_cigar_scratch_ints(SG_MAX_K - 1);
-    l.agVec = (size_t)maxReadLen / 8 + 48;
+    // vectors per row: unbanded ceil(P/8); banded numSeg * numVec < P/8 + numVec with numVec <= ceil(P/24) (banded only when P >= 3(2k+1))
+    l.agVec = (size_t)maxReadLen / 8 + (size_t)maxReadLen / 24 + 4;
     l.agRows = (size_t)maxReadLen + SG_MAX_K + 8;
     l.agRes = 2 * l.agRows;
     size_t b = 0;
@@ -1850,7 +1855,7 @@ static SgSamScratchLayout sam_layout(uint32_t maxReadLen)
     b += sg_align_up(l.agRows * l.agVec * 8, 256);                                        // bt
     b += sg_align_up(l.agRes, 256) + sg_align_up(l.agRes * 4, 256);                       // resAction, resCount
     b += sg_align_up((size_t)maxReadLen + 16, 256) * 4;                                   // data, quality x2
-    l.perThread = b;
+    l.perOctet = b;
     return l;
 }
 
@@ -1877,20 +1882,26 @@ __device__ static void sam_carve(const SgSamScratchLayout &l, uint8_t *q, SgSamC
     C->quality2 = q;
 }
 
-__global__ void __launch_bounds__(64)
+// MB = resident CTAs (of 256 threads = 32 octets) per SM the instantiation is compiled for: the kernel is bound by the latency of each
+// read's serial chain, so more resident octets win as long as the register cap does not cost more in spills (measured: DESIGN.md 8).
+extern "C++" {
+template <int MB>
+__global__ void __launch_bounds__(256, MB)
 sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, uint8_t *scratch, const char *const *contigNames, const char *readGroupAux,
               SgAgParams ag, int useM, int useAffineGap, long long nUnits, int paired, const uint8_t *bases, const uint8_t *quals,
               const unsigned long long *offsets, const uint32_t *lens, const uint8_t *ids, const unsigned long long *idOffsets, const uint32_t *idLens,
               const snapgpu_single_result *single, const snapgpu_paired_result *pairs, const uint32_t *frontClipped, const uint32_t *clippedLens,
-              char *slots, uint32_t slotBytes, uint32_t *recordBytes)
+              char *slots, uint32_t slotBytes, uint32_t *recordBytes, int bam, const uint8_t *rgAuxBam, int rgAuxBamLen)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nT = (long long)gridDim.x * blockDim.x;
+    SgBamContext Bc; Bc.readGroupAux = rgAuxBam; Bc.readGroupAuxLen = rgAuxBamLen;
+    const long long octet = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long nOctets = ((long long)gridDim.x * blockDim.x) >> 3;
     SgSamContext C;
     C.ix = &ix; C.contigName = contigNames; C.ag = ag; C.readGroupAux = readGroupAux; C.useM = useM != 0; C.useAffineGap = useAffineGap != 0;
-    sam_carve(lay, scratch + (size_t)t * lay.perThread, &C);
-    for (long long u = t; u < nUnits; u += nT) {
+    sam_carve(lay, scratch + (size_t)octet * lay.perOctet, &C);
+    for (long long u = octet; u < nUnits; u += nOctets) {
         char *out = slots + (size_t)u * slotBytes;
+        uint32_t n;
         if (!paired) {
             SgSamRead R;
             R.unclippedData = bases + offsets[u]; R.unclippedQuality = quals + offsets[u]; R.unclippedLength = lens[u];
@@ -1902,7 +1913,7 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
             sr.status = r.status; sr.location = r.status == SNAPGPU_NOT_FOUND ? -1 : r.location; sr.direction = r.direction; sr.mapq = r.mapq; sr.score = r.score;
             sr.scorePriorToClipping = r.scorePriorToClipping; sr.usedAffineGapScoring = r.usedAffineGapScoring; sr.basesClippedBefore = r.basesClippedBefore;
             sr.basesClippedAfter = r.basesClippedAfter; sr.clippingForReadAdjustment = r.clippingForReadAdjustment;
-            recordBytes[u] = (uint32_t)sg_sam_write_single(C, R, sr, out);
+            n = bam ? (uint32_t)sg_bam_write_single(C, Bc, R, sr, (uint8_t *)out) : (uint32_t)sg_sam_write_single(C, R, sr, out);
         } else {
             SgSamRead R[2];
             for (int w = 0; w < 2; w++) {
@@ -1920,8 +1931,28 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
                 pr.clippingForReadAdjustment[w] = r.clippingForReadAdjustment[w];
             }
             pr.alignedAsPair = r.alignedAsPair;
-            recordBytes[u] = (uint32_t)sg_sam_write_pair(C, R[0], R[1], pr, out);
+            n = bam ? (uint32_t)sg_bam_write_pair(C, Bc, R[0], R[1], pr, out) : (uint32_t)sg_sam_write_pair(C, R[0], R[1], pr, out);
         }
+        recordBytes[u] = n > slotBytes ? 0u : n;
+        __syncwarp(0xffu << (threadIdx.x & 24u));        // the octet leaves its scratch together
+    }
+}
+
+}   // extern "C++"
+
+// packs the slots: warp per record (pair of records)
+__global__ void sg_sam_pack_kernel(const char *slots, uint32_t slotBytes, const uint32_t *recordBytes, const unsigned long long *recordOffsets, long long nUnits, char *text,
+                                   unsigned long long textCapacity, int *overflow)
+{
+    const int lane = threadIdx.x & 31;
+    const long long nW = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < nUnits; u += nW) {
+        const uint32_t n = recordBytes[u];
+        const unsigned long long off = recordOffsets[u];
+        if (n == 0) { if (lane == 0) atomicMax(overflow, 1); continue; }                 // a record that could not be formatted
+        if (off + n > textCapacity) { if (lane == 0) atomicMax(overflow, 2); continue; }
+        const char *src = slots + (size_t)u * slotBytes;
+        for (uint32_t k = lane; k < n; k += 32) text[off + k] = src[k];
     }
 }
 
@@ -1932,16 +1963,24 @@ struct snapgpu_sam {
     SgAgParams ag;
     int useM = 1, useAffineGap = 1;
     int64_t maxBatchReads = 0;
-    int nThreads = 0;
+    int64_t nOctets = 0;
+    int format = SNAPGPU_FORMAT_SAM;
+    uint8_t *d_rgAuxBam = nullptr; int rgAuxBamLen = 0;
+    int ctasPerSM = 4;
     uint32_t slotBytes = 0;
-    uint8_t *d_scratch = nullptr;
+    size_t stageBases = 0;
+    uint8_t *d_scratch = nullptr; size_t scratchBytes = 0;
     char *d_names = nullptr; const char **d_namePtrs = nullptr; char *d_rgAux = nullptr;
+    uint32_t maxNameLen = 0;
     // staging of the host-buffer call
     uint8_t *d_bases = nullptr, *d_quals = nullptr, *d_ids = nullptr, *d_results = nullptr;
-    unsigned long long *d_offsets = nullptr, *d_idOffsets = nullptr;
+    unsigned long long *d_offsets = nullptr, *d_idOffsets = nullptr, *d_recordOffsets = nullptr;
     uint32_t *d_lens = nullptr, *d_idLens = nullptr, *d_recordBytes = nullptr, *d_front = nullptr, *d_clippedLens = nullptr;
-    char *d_slots = nullptr;
-    std::vector<char> h_slots; std::vector<uint32_t> h_recordBytes;
+    char *d_slots = nullptr; size_t slotsBytes = 0;
+    char *d_text = nullptr; size_t textBytes = 0;
+    void *d_cub = nullptr; size_t cubBytes = 0;
+    int *d_overflow = nullptr;
+    unsigned long long *h_meta = nullptr;        // pinned: [0] last offset, [1] last length (low word), [2] overflow
     cudaStream_t stream = nullptr;
 };
 
@@ -1952,6 +1991,7 @@ void snapgpu_sam_destroy(snapgpu_sam *s)
     cudaDeviceSynchronize();
     cudaFree(s->d_scratch); cudaFree(s->d_names); cudaFree((void *)s->d_namePtrs); cudaFree(s->d_rgAux); cudaFree(s->d_bases); cudaFree(s->d_quals); cudaFree(s->d_ids);
     cudaFree(s->d_results); cudaFree(s->d_offsets); cudaFree(s->d_idOffsets); cudaFree(s->d_lens); cudaFree(s->d_idLens); cudaFree(s->d_recordBytes); cudaFree(s->d_front); cudaFree(s->d_clippedLens); cudaFree(s->d_slots);
+    cudaFree(s->d_recordOffsets); cudaFree(s->d_text); cudaFree(s->d_cub); cudaFree(s->d_overflow); cudaFreeHost(s->h_meta); cudaFree(s->d_rgAuxBam);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1967,30 +2007,33 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     snapgpu_sam *s = new (std::nothrow) snapgpu_sam;
     if (!s) return sg_fail("out of memory");
     s->index = idx; s->device = idx->device; s->maxBatchReads = maxBatchReads;
-    s->lay = sam_layout(env_max_read_len());
     s->ag = sg_ag_params(params->matchReward, params->subPenalty, params->gapOpenPenalty, params->gapExtendPenalty, 0, 0);
     s->useM = useM != 0; s->useAffineGap = params->useAffineGap != 0;
     cudaDeviceProp prop;
     SG_CUDA(cudaGetDeviceProperties(&prop, s->device));
-    int64_t threads = (int64_t)prop.multiProcessorCount * 64;
-    if (threads > maxBatchReads) threads = (maxBatchReads + 63) / 64 * 64;
-    s->nThreads = (int)threads;
-    s->slotBytes = 2 * (2 * s->lay.maxReadLen + SG_SAM_MAX_ID + 256 + 5 * SG_SAM_MAX_OPS);      // room for the two records of a pair (CIGAR: <= 5 characters per operation)
+    s->ctasPerSM = 4;                    // measured (M reads/s, 1 M x 150 bp): 2 -> 10.5, 4 -> 14.8, 6 -> 14.6, 8 -> 13.7 (profiles/r02_sam_occupancy.txt)
+    if (const char *e = getenv("SNAPGPU_SAM_CTAS_PER_SM")) { const int v = atoi(e); if (v == 2 || v == 3 || v == 4 || v == 6 || v == 8) s->ctasPerSM = v; }
+    s->nOctets = (int64_t)prop.multiProcessorCount * s->ctasPerSM * 256 / 8;
     // contig names and the default read group line (ReaderContext::defaultReadGroupAux for the default read group "FASTQ")
     std::string blob; std::vector<size_t> off;
-    for (size_t c = 0; c < idx->h_contigName.size(); c++) { off.push_back(blob.size()); blob += idx->h_contigName[c]; blob.push_back('\0'); }
+    for (size_t c = 0; c < idx->h_contigName.size(); c++) {
+        off.push_back(blob.size()); blob += idx->h_contigName[c]; blob.push_back('\0');
+        if (idx->h_contigName[c].size() > s->maxNameLen) s->maxNameLen = (uint32_t)idx->h_contigName[c].size();
+    }
     const char rg[] = "\tRG:Z:FASTQ\tPL:Z:Illumina\tPU:Z:pu\tLB:Z:lb\tSM:Z:sm";
+    size_t c1 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, c1, (uint32_t *)nullptr, (unsigned long long *)nullptr, (int)maxBatchReads);
+    s->cubBytes = c1 + 256;
     bool ok = cudaMalloc((void **)&s->d_names, blob.size() + 16) == cudaSuccess && cudaMalloc((void **)&s->d_namePtrs, (off.size() + 1) * sizeof(char *)) == cudaSuccess &&
-              cudaMalloc((void **)&s->d_rgAux, sizeof(rg)) == cudaSuccess && cudaMalloc((void **)&s->d_scratch, s->lay.perThread * (size_t)s->nThreads) == cudaSuccess;
-    const size_t nb = (size_t)maxBatchReads * s->lay.maxReadLen;
-    ok = ok && cudaMalloc((void **)&s->d_bases, nb + 16) == cudaSuccess && cudaMalloc((void **)&s->d_quals, nb + 16) == cudaSuccess &&
-         cudaMalloc((void **)&s->d_ids, (size_t)maxBatchReads * SG_SAM_MAX_ID + 16) == cudaSuccess &&
+              cudaMalloc((void **)&s->d_rgAux, sizeof(rg)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&s->d_ids, (size_t)maxBatchReads * SG_SAM_MAX_ID + 16) == cudaSuccess &&
          cudaMalloc((void **)&s->d_results, (size_t)maxBatchReads * sizeof(snapgpu_paired_result)) == cudaSuccess &&
          cudaMalloc((void **)&s->d_offsets, (size_t)maxBatchReads * 8) == cudaSuccess && cudaMalloc((void **)&s->d_idOffsets, (size_t)maxBatchReads * 8) == cudaSuccess &&
          cudaMalloc((void **)&s->d_lens, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_idLens, (size_t)maxBatchReads * 4) == cudaSuccess &&
-         cudaMalloc((void **)&s->d_recordBytes, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_recordBytes, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_recordOffsets, (size_t)maxBatchReads * 8) == cudaSuccess &&
          cudaMalloc((void **)&s->d_front, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_clippedLens, (size_t)maxBatchReads * 4) == cudaSuccess &&
-         cudaMalloc((void **)&s->d_slots, (size_t)maxBatchReads * s->slotBytes) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_cub, s->cubBytes) == cudaSuccess && cudaMalloc((void **)&s->d_overflow, sizeof(int)) == cudaSuccess &&
+         cudaMallocHost((void **)&s->h_meta, 4 * sizeof(unsigned long long)) == cudaSuccess &&
          cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
         std::string msg = std::string("snapgpu_sam_create: ") + cudaGetErrorString(cudaGetLastError());
@@ -2002,9 +2045,137 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     SG_CUDA(cudaMemcpy(s->d_names, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     if (!ptrs.empty()) SG_CUDA(cudaMemcpy((void *)s->d_namePtrs, ptrs.data(), ptrs.size() * sizeof(char *), cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(s->d_rgAux, rg, sizeof(rg), cudaMemcpyHostToDevice));
-    s->h_slots.resize((size_t)maxBatchReads * s->slotBytes);
-    s->h_recordBytes.resize((size_t)maxBatchReads);
+    // the same read group line as BAM tags (ReaderContext::defaultReadGroupAux for a BAM writer): the literal's terminating NUL ends the last tag
+    static const char rgBam[] = "RGZFASTQ\0PLZIllumina\0PUZpu\0LBZlb\0SMZsm";
+    s->rgAuxBamLen = (int)sizeof(rgBam);
+    SG_CUDA(cudaMalloc((void **)&s->d_rgAuxBam, sizeof(rgBam)));
+    SG_CUDA(cudaMemcpy(s->d_rgAuxBam, rgBam, sizeof(rgBam), cudaMemcpyHostToDevice));
     *out = s;
+    return 0;
+}
+
+int snapgpu_sam_set_format(snapgpu_sam *s, int format)
+{
+    if (!s) return sg_fail("null argument");
+    if (format != SNAPGPU_FORMAT_SAM && format != SNAPGPU_FORMAT_BAM) return sg_fail("snapgpu_sam_set_format: unknown format");
+    s->format = format;
+    return 0;
+}
+
+// ---- BGZF (the container of a BAM file; reference SNAPLib/GzipDataWriter.cpp + Bam.cpp): the payload cut into members of at most 0xff00 bytes,
+//      each a gzip member with the 'BC' extra field carrying its size.  The deflate stream of a member is ONE STORED block (BTYPE = 00): valid
+//      BGZF that any BAM reader inflates to exactly the payload, without a compressor on the device.  One CTA per member: the threads copy
+//      the payload while thread 0 runs the CRC-32 (table in shared memory). ----
+#define SG_BGZF_PAYLOAD 0xff00u
+__global__ void __launch_bounds__(256)
+sg_bgzf_kernel(const uint8_t *in, unsigned long long nBytes, uint8_t *out, unsigned long long nBlocks)
+{
+    __shared__ uint32_t table[256];
+    {
+        uint32_t c = threadIdx.x;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (0xedb88320u ^ (c >> 1)) : (c >> 1);
+        table[threadIdx.x] = c;
+    }
+    __syncthreads();
+    for (unsigned long long b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        const unsigned long long off = b * SG_BGZF_PAYLOAD;
+        const uint32_t len = (uint32_t)((nBytes - off) < SG_BGZF_PAYLOAD ? (nBytes - off) : SG_BGZF_PAYLOAD);
+        uint8_t *o = out + b * (unsigned long long)(SG_BGZF_PAYLOAD + 31u);      // members are laid at a fixed pitch; the host (or a scan) closes the gaps
+        const uint8_t *src = in + off;
+        for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) o[23 + k] = src[k];
+        if (threadIdx.x == 0) {
+            uint32_t crc = 0xffffffffu;
+            for (uint32_t k = 0; k < len; k++) crc = table[(crc ^ src[k]) & 0xffu] ^ (crc >> 8);
+            crc ^= 0xffffffffu;
+            const uint32_t total = len + 31u;
+            const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1u) & 0xffu), (uint8_t)((total - 1u) >> 8)};
+            for (int k = 0; k < 18; k++) o[k] = hdr[k];
+            o[18] = 1; o[19] = (uint8_t)(len & 0xffu); o[20] = (uint8_t)(len >> 8); o[21] = (uint8_t)(~len & 0xffu); o[22] = (uint8_t)((~len >> 8) & 0xffu);
+            uint8_t *t = o + 23 + len;
+            t[0] = (uint8_t)crc; t[1] = (uint8_t)(crc >> 8); t[2] = (uint8_t)(crc >> 16); t[3] = (uint8_t)(crc >> 24);
+            t[4] = (uint8_t)len; t[5] = (uint8_t)(len >> 8); t[6] = 0; t[7] = 0;
+        }
+    }
+}
+
+// All but the last member are full (pitch = their size), so the output is already contiguous: nBlocks - 1 full members + the last one.
+int snapgpu_bgzf_device(const char *d_in, int64_t nBytes, char *d_out, int64_t outCapacity, int64_t *outBytes, void *cudaStream)
+{
+    if (!d_in || !d_out || !outBytes || nBytes < 0) return sg_fail("bad argument");
+    *outBytes = 0;
+    if (nBytes == 0) return 0;
+    const unsigned long long nBlocks = ((unsigned long long)nBytes + SG_BGZF_PAYLOAD - 1) / SG_BGZF_PAYLOAD;
+    const unsigned long long total = (unsigned long long)nBytes + nBlocks * 31ull;
+    if ((unsigned long long)outCapacity < total) return sg_fail("snapgpu_bgzf: output buffer too small (payload + 31 bytes per 65280-byte member)");
+    const unsigned grid = (unsigned)(nBlocks < 148ull * 8 ? nBlocks : 148ull * 8);
+    sg_bgzf_kernel<<<grid, 256, 0, (cudaStream_t)cudaStream>>>((const uint8_t *)d_in, (unsigned long long)nBytes, (uint8_t *)d_out, nBlocks);
+    SG_CUDA(cudaGetLastError());
+    *outBytes = (int64_t)total;
+    return 0;
+}
+
+// (Re)sizes the octets' scratch and the record slots for reads of up to maxLen bases.
+static int sam_reserve(snapgpu_sam *s, uint32_t maxLen, int64_t nUnits, int paired)
+{
+    if (maxLen < 32) maxLen = 32;
+    maxLen = (maxLen + 31u) / 32u * 32u;
+    if (s->d_scratch == nullptr || maxLen > s->lay.maxReadLen) {
+        const SgSamScratchLayout lay = sam_layout(maxLen);
+        const size_t need = lay.perOctet * (size_t)s->nOctets;
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_scratch); s->d_scratch = nullptr;
+        SG_CUDA(cudaMalloc((void **)&s->d_scratch, need));
+        SG_CUDA(cudaMemsetAsync(s->d_scratch, 0, need, s->stream));
+        s->lay = lay; s->scratchBytes = need;
+    }
+    // one record: QNAME, the fixed fields and RNAME / RNEXT, a CIGAR of up to SG_SAM_MAX_OPS operations (<= 6 characters each from 10000
+    // bases on), SEQ and QUAL, the tags
+    const uint32_t opChars = maxLen >= 10000 ? 6u : (maxLen >= 1000 ? 5u : 4u);
+    const uint32_t one = 2 * maxLen + SG_SAM_MAX_ID + 2 * s->maxNameLen + 256 + (opChars + 1) * SG_SAM_MAX_OPS;
+    const uint32_t slot = (paired ? 2 * one : one + 0u);
+    const size_t need = (size_t)slot * (size_t)nUnits;
+    if (slot > s->slotBytes || need > s->slotsBytes) {
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(s->d_slots); s->d_slots = nullptr;
+        const size_t cap = (size_t)(slot > s->slotBytes ? slot : s->slotBytes) * (size_t)(paired ? (s->maxBatchReads + 1) / 2 : s->maxBatchReads);
+        SG_CUDA(cudaMalloc((void **)&s->d_slots, cap));
+        s->slotBytes = slot > s->slotBytes ? slot : s->slotBytes; s->slotsBytes = cap;
+    }
+    return 0;
+}
+
+// The device-resident core: every array already in HBM; the packed text is left in d_text (capacity textCapacity), *textBytes says how much.
+static int sam_format_device(snapgpu_sam *s, int paired, int64_t nReads, uint32_t maxLen, const uint8_t *d_bases, const uint8_t *d_quals, const unsigned long long *d_offsets,
+                             const uint32_t *d_lens, const uint8_t *d_ids, const unsigned long long *d_idOffsets, const uint32_t *d_idLens, const uint32_t *d_front,
+                             const uint32_t *d_clippedLens, const void *d_results, char *d_text, int64_t textCapacity, int64_t *textBytes, cudaStream_t st)
+{
+    const int64_t nUnits = paired ? nReads / 2 : nReads;
+    if (sam_reserve(s, maxLen, nUnits, paired)) return 1;
+    int64_t octets = s->nOctets < nUnits ? s->nOctets : nUnits;
+    int blocks = (int)((octets * 8 + 255) / 256);
+    SG_CUDA(cudaMemsetAsync(s->d_overflow, 0, sizeof(int), st));
+#define SG_SAM_LAUNCH(MB) sg_sam_kernel<MB><<<blocks, 256, 0, st>>>(s->index->view, s->lay, s->d_scratch, s->d_namePtrs, s->d_rgAux, s->ag, s->useM, s->useAffineGap, nUnits, paired, \
+                                          d_bases, d_quals, d_offsets, d_lens, d_ids, d_idOffsets, d_idLens, \
+                                          paired ? nullptr : (const snapgpu_single_result *)d_results, paired ? (const snapgpu_paired_result *)d_results : nullptr, \
+                                          d_front, d_clippedLens, s->d_slots, s->slotBytes, s->d_recordBytes, s->format == SNAPGPU_FORMAT_BAM, s->d_rgAuxBam, s->rgAuxBamLen)
+    if (s->ctasPerSM == 8) SG_SAM_LAUNCH(8); else if (s->ctasPerSM == 6) SG_SAM_LAUNCH(6); else if (s->ctasPerSM == 4) SG_SAM_LAUNCH(4);
+    else if (s->ctasPerSM == 3) SG_SAM_LAUNCH(3); else SG_SAM_LAUNCH(2);
+#undef SG_SAM_LAUNCH
+    SG_CUDA(cudaGetLastError());
+    size_t cb = s->cubBytes;
+    SG_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, cb, s->d_recordBytes, s->d_recordOffsets, (int)nUnits, st));
+    long long warps = nUnits < 148LL * 64 ? nUnits : 148LL * 64;
+    sg_sam_pack_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(s->d_slots, s->slotBytes, s->d_recordBytes, s->d_recordOffsets, nUnits, d_text,
+                                                                            (unsigned long long)textCapacity, s->d_overflow);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[0], s->d_recordOffsets + (nUnits - 1), 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[1], s->d_recordBytes + (nUnits - 1), 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[2], s->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    const int ov = (int)(s->h_meta[2] & 0xffffffffu);
+    if (ov == 1) return sg_fail("snapgpu_sam_format: a record could not be formatted");
+    if (ov == 2) return sg_fail("snapgpu_sam_format: text buffer too small");
+    *textBytes = (int64_t)(s->h_meta[0] + (s->h_meta[1] & 0xffffffffu));
     return 0;
 }
 
@@ -2019,16 +2190,31 @@ static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *ba
     if (nReads == 0) return 0;
     SG_CUDA(cudaSetDevice(s->device));
     size_t totalBases = 0, totalIds = 0;
+    uint32_t maxLen = 0;
     for (int64_t i = 0; i < nReads; i++) {
-        if (lens[i] > s->lay.maxReadLen) return sg_fail("a read is longer than the configured maximum (SNAPGPU_MAX_READ_LEN)");
+        if (lens[i] > SNAPGPU_MAX_READ_LENGTH) return sg_fail("a read is longer than MAX_READ_LENGTH");
         if (idLens[i] >= SG_SAM_MAX_ID) return sg_fail("a read id is longer than 255 characters");
         if (frontClipped && (uint64_t)frontClipped[i] + clippedLens[i] > lens[i]) return sg_fail("snapgpu_sam_format: clipped view outside the read");
         if (offsets[i] + lens[i] > totalBases) totalBases = (size_t)(offsets[i] + lens[i]);
         if (idOffsets[i] + idLens[i] > totalIds) totalIds = (size_t)(idOffsets[i] + idLens[i]);
+        if (lens[i] > maxLen) maxLen = lens[i];
     }
-    if (totalBases > (size_t)s->maxBatchReads * s->lay.maxReadLen || totalIds > (size_t)s->maxBatchReads * SG_SAM_MAX_ID) return sg_fail("snapgpu_sam_format: input buffers larger than the handle was sized for");
+    if (totalIds > (size_t)s->maxBatchReads * SG_SAM_MAX_ID) return sg_fail("snapgpu_sam_format: id buffer larger than the handle was sized for");
     cudaStream_t st = s->stream;
-    const int64_t nUnits = paired ? nReads / 2 : nReads;
+    // the staging of the reads and of the text grows with the batches seen
+    if (s->d_text == nullptr || (size_t)textCapacity > s->textBytes) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s->d_text); s->d_text = nullptr;
+        SG_CUDA(cudaMalloc((void **)&s->d_text, (size_t)textCapacity + 16));
+        s->textBytes = (size_t)textCapacity;
+    }
+    if (s->d_bases == nullptr || totalBases + 16 > s->stageBases) {
+        SG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s->d_bases); cudaFree(s->d_quals); s->d_bases = s->d_quals = nullptr;
+        SG_CUDA(cudaMalloc((void **)&s->d_bases, totalBases + 16));
+        SG_CUDA(cudaMalloc((void **)&s->d_quals, totalBases + 16));
+        s->stageBases = totalBases + 16;
+    }
     SG_CUDA(cudaMemcpyAsync(s->d_bases, bases, totalBases, cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMemcpyAsync(s->d_quals, quals, totalBases, cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMemcpyAsync(s->d_ids, ids, totalIds, cudaMemcpyHostToDevice, st));
@@ -2040,24 +2226,13 @@ static int sam_format(snapgpu_sam *s, int paired, int64_t nReads, const char *ba
         SG_CUDA(cudaMemcpyAsync(s->d_front, frontClipped, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
         SG_CUDA(cudaMemcpyAsync(s->d_clippedLens, clippedLens, (size_t)nReads * 4, cudaMemcpyHostToDevice, st));
     }
+    const int64_t nUnits = paired ? nReads / 2 : nReads;
     SG_CUDA(cudaMemcpyAsync(s->d_results, results, (size_t)nUnits * (paired ? sizeof(snapgpu_paired_result) : sizeof(snapgpu_single_result)), cudaMemcpyHostToDevice, st));
-    int64_t threads = s->nThreads < nUnits ? s->nThreads : (nUnits + 63) / 64 * 64;
-    sg_sam_kernel<<<(int)(threads / 64), 64, 0, st>>>(s->index->view, s->lay, s->d_scratch, s->d_namePtrs, s->d_rgAux, s->ag, s->useM, s->useAffineGap, nUnits, paired,
-                                                      s->d_bases, s->d_quals, s->d_offsets, s->d_lens, s->d_ids, s->d_idOffsets, s->d_idLens,
-                                                      paired ? nullptr : (const snapgpu_single_result *)s->d_results, paired ? (const snapgpu_paired_result *)s->d_results : nullptr,
-                                                      frontClipped ? s->d_front : nullptr, frontClipped ? s->d_clippedLens : nullptr, s->d_slots, s->slotBytes, s->d_recordBytes);
-    SG_CUDA(cudaGetLastError());
-    SG_CUDA(cudaMemcpyAsync(s->h_recordBytes.data(), s->d_recordBytes, (size_t)nUnits * 4, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaMemcpyAsync(s->h_slots.data(), s->d_slots, (size_t)nUnits * s->slotBytes, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
     int64_t used = 0;
-    for (int64_t u = 0; u < nUnits; u++) {
-        const uint32_t n = s->h_recordBytes[u];
-        if (n == 0 || n > s->slotBytes) return sg_fail("snapgpu_sam_format: a record could not be formatted");
-        if (used + n > textCapacity) return sg_fail("snapgpu_sam_format: text buffer too small");
-        memcpy(text + used, s->h_slots.data() + (size_t)u * s->slotBytes, n);
-        used += n;
-    }
+    if (sam_format_device(s, paired, nReads, maxLen, s->d_bases, s->d_quals, s->d_offsets, s->d_lens, s->d_ids, s->d_idOffsets, s->d_idLens,
+                          frontClipped ? s->d_front : nullptr, frontClipped ? s->d_clippedLens : nullptr, s->d_results, s->d_text, textCapacity, &used, st)) return 1;
+    SG_CUDA(cudaMemcpyAsync(text, s->d_text, (size_t)used, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
     *textBytes = used;
     return 0;
 }
@@ -2074,6 +2249,42 @@ int snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases,
                               const snapgpu_paired_result *results, char *text, int64_t textCapacity, int64_t *textBytes)
 {
     return sam_format(s, 1, nReads, bases, quals, offsets, lens, ids, idOffsets, idLens, frontClipped, clippedLens, results, text, textCapacity, textBytes);
+}
+
+// Device-resident forms: every array (and the text buffer) is a DEVICE pointer, so the records of a batch aligned with snapgpu_align_*_device
+// are formatted without their results ever visiting the host; maxReadLen = the longest read of the batch.  Synchronises `cudaStream` once.
+int snapgpu_sam_format_single_device(snapgpu_sam *s, int64_t nReads, uint32_t maxReadLen, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                                     const uint32_t *d_lens, const char *d_ids, const uint64_t *d_idOffsets, const uint32_t *d_idLens, const uint32_t *d_frontClipped,
+                                     const uint32_t *d_clippedLens, const snapgpu_single_result *d_results, char *d_text, int64_t textCapacity, int64_t *textBytes,
+                                     void *cudaStream)
+{
+    if (!s || !d_bases || !d_quals || !d_offsets || !d_lens || !d_ids || !d_idOffsets || !d_idLens || !d_results || !d_text || !textBytes) return sg_fail("null argument");
+    if (nReads < 0 || nReads > s->maxBatchReads) return sg_fail("snapgpu_sam_format: bad read count");
+    if ((d_frontClipped == nullptr) != (d_clippedLens == nullptr)) return sg_fail("snapgpu_sam_format: frontClipped and clippedLens go together (both or neither)");
+    if (maxReadLen == 0 || maxReadLen > SNAPGPU_MAX_READ_LENGTH) return sg_fail("snapgpu_sam_format: maxReadLen out of range");
+    *textBytes = 0;
+    if (nReads == 0) return 0;
+    SG_CUDA(cudaSetDevice(s->device));
+    return sam_format_device(s, 0, nReads, maxReadLen, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, d_lens, (const uint8_t *)d_ids,
+                             (const unsigned long long *)d_idOffsets, d_idLens, d_frontClipped, d_clippedLens, d_results, d_text, textCapacity, textBytes,
+                             cudaStream ? (cudaStream_t)cudaStream : s->stream);
+}
+
+int snapgpu_sam_format_paired_device(snapgpu_sam *s, int64_t nReads, uint32_t maxReadLen, const char *d_bases, const char *d_quals, const uint64_t *d_offsets,
+                                     const uint32_t *d_lens, const char *d_ids, const uint64_t *d_idOffsets, const uint32_t *d_idLens, const uint32_t *d_frontClipped,
+                                     const uint32_t *d_clippedLens, const snapgpu_paired_result *d_results, char *d_text, int64_t textCapacity, int64_t *textBytes,
+                                     void *cudaStream)
+{
+    if (!s || !d_bases || !d_quals || !d_offsets || !d_lens || !d_ids || !d_idOffsets || !d_idLens || !d_results || !d_text || !textBytes) return sg_fail("null argument");
+    if (nReads < 0 || nReads > s->maxBatchReads || (nReads & 1)) return sg_fail("snapgpu_sam_format: bad read count");
+    if ((d_frontClipped == nullptr) != (d_clippedLens == nullptr)) return sg_fail("snapgpu_sam_format: frontClipped and clippedLens go together (both or neither)");
+    if (maxReadLen == 0 || maxReadLen > SNAPGPU_MAX_READ_LENGTH) return sg_fail("snapgpu_sam_format: maxReadLen out of range");
+    *textBytes = 0;
+    if (nReads == 0) return 0;
+    SG_CUDA(cudaSetDevice(s->device));
+    return sam_format_device(s, 1, nReads, maxReadLen, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, d_lens, (const uint8_t *)d_ids,
+                             (const unsigned long long *)d_idOffsets, d_idLens, d_frontClipped, d_clippedLens, d_results, d_text, textCapacity, textBytes,
+                             cudaStream ? (cudaStream_t)cudaStream : s->stream);
 }
 
 struct snapgpu_fastq {

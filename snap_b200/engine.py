@@ -85,7 +85,7 @@ EXPORTS = [
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
-    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 ABI_VERSION = 3          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
@@ -139,6 +139,10 @@ def lib():
         L.snapgpu_sam_destroy.argtypes = [C.c_void_p]
         L.snapgpu_sam_format_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 11 + [C.c_int64, C.POINTER(C.c_int64)]
         L.snapgpu_sam_format_paired.argtypes = L.snapgpu_sam_format_single.argtypes
+        L.snapgpu_sam_format_single_device.argtypes = [C.c_void_p, C.c_int64, C.c_uint32] + [C.c_void_p] * 11 + [C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.snapgpu_sam_format_paired_device.argtypes = L.snapgpu_sam_format_single_device.argtypes
+        L.snapgpu_sam_set_format.argtypes = [C.c_void_p, C.c_int]
+        L.snapgpu_bgzf_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_fastq_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.snapgpu_fastq_parse_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_aligner_launch_count.restype = C.c_int64
@@ -377,6 +381,10 @@ class SamFormatter:
         self.handle = h
         self.max_batch_reads = max_batch_reads
 
+    def set_format(self, bam: bool) -> None:
+        """False: SAM text (default); True: uncompressed BAM alignment records (snapgpu_sam_set_format)."""
+        _check(lib().snapgpu_sam_set_format(self.handle, 1 if bam else 0))
+
     @staticmethod
     def pack_ids(ids):
         """ids (one bytes object per read) -> (concatenated uint8 array, offsets, lengths) as the C ABI takes them."""
@@ -396,6 +404,16 @@ class SamFormatter:
         _check(fn(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(id_buf), _p(id_offs), _p(id_lens), fc, cl,
                   _p(results), _p(text), text.size, C.byref(used)))
         return text, used.value
+
+    def format_device(self, n_reads, max_read_len, d_bases, d_quals, d_offsets, d_lens, d_ids, d_id_offsets, d_id_lens, d_results, d_text, text_capacity,
+                      paired: bool = False, d_front=0, d_clipped_lens=0, stream=0) -> int:
+        """Device pointers (ints) in, packed SAM text left in d_text; returns the bytes used (snapgpu_sam_format_*_device)."""
+        used = C.c_int64(0)
+        fn = lib().snapgpu_sam_format_paired_device if paired else lib().snapgpu_sam_format_single_device
+        _check(fn(self.handle, n_reads, max_read_len, C.c_void_p(d_bases), C.c_void_p(d_quals), C.c_void_p(d_offsets), C.c_void_p(d_lens), C.c_void_p(d_ids),
+                  C.c_void_p(d_id_offsets), C.c_void_p(d_id_lens), C.c_void_p(d_front), C.c_void_p(d_clipped_lens), C.c_void_p(d_results), C.c_void_p(d_text),
+                  text_capacity, C.byref(used), C.c_void_p(stream)))
+        return used.value
 
     def format(self, batch, ids, results, paired: bool = False, front_clipped=None, clipped_lens=None) -> bytes:
         """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one
@@ -452,6 +470,13 @@ class FastqParser:
         if self.handle:
             lib().snapgpu_fastq_destroy(self.handle)
             self.handle = None
+
+
+def bgzf_device(d_in: int, n_bytes: int, d_out: int, out_capacity: int, stream: int = 0) -> int:
+    """BGZF members (stored deflate blocks + CRC-32) over device data; returns the bytes written to d_out (snapgpu_bgzf_device)."""
+    used = C.c_int64(0)
+    _check(lib().snapgpu_bgzf_device(C.c_void_p(d_in), n_bytes, C.c_void_p(d_out), out_capacity, C.byref(used), C.c_void_p(stream)))
+    return used.value
 
 
 def measure_random_sector_rate(table_bytes: int, n_accesses: int = 1 << 26, device: int = 0) -> float:

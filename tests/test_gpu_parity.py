@@ -695,6 +695,139 @@ def test_sam_pair_records_from_the_device_equal_reference_binary(engine, gidx, s
     assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
 
 
+def test_fastq_text_to_sam_text_without_leaving_the_device(engine, gidx, small_cfg, reflib, tmp_path):
+    """The whole chain resident in HBM: FASTQ text -> snapgpu_fastq_parse_device -> snapgpu_align_single_device ->
+    snapgpu_sam_format_single_device (ids taken from the FASTQ text itself, records from the aligner's device buffer, packed on the device);
+    the text that comes out is the record set of the SAM file the reference binary writes for that FASTQ file."""
+    import torch
+    from snap_b200 import synth
+    rb = small_cfg.reads["indel100"]
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.sam")
+    rb.write_fastq(fq)
+    want = _reference_sam_lines(reflib, ["single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"])
+    text = np.frombuffer(open(fq, "rb").read(), dtype=np.uint8)
+    dev = torch.device("cuda", 0)
+    n = rb.n
+    d_text = torch.from_numpy(text.copy()).to(dev)
+    d_b = torch.empty((text.size // 2 + 64,), dtype=torch.uint8, device=dev); d_q = torch.empty_like(d_b)
+    d_off = torch.empty((n + 8,), dtype=torch.int64, device=dev); d_len = torch.empty((n + 8,), dtype=torch.int32, device=dev)
+    d_ido = torch.empty((n + 8,), dtype=torch.int64, device=dev); d_idl = torch.empty((n + 8,), dtype=torch.int32, device=dev)
+    d_fc = torch.empty((n + 8,), dtype=torch.int32, device=dev)
+    d_res = torch.empty((n, engine.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    cap = n * 1024
+    d_sam = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    p = engine.default_params(maxDist=14)
+    fqp = engine.FastqParser(max_bytes=int(text.size) + 64, max_reads=n + 8)
+    al = engine.SingleAligner(gidx, p, n)
+    fmt = engine.SamFormatter(gidx, p, n)
+    st = torch.cuda.Stream(dev)
+    nr, used = fqp.parse_device(d_text.data_ptr(), int(text.size), 2, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_ido.data_ptr(),
+                                d_idl.data_ptr(), d_fc.data_ptr(), st.cuda_stream)
+    assert nr == n and used == text.size
+    al.align_device(nr, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_res.data_ptr(), 0, st.cuda_stream)
+    nbytes = fmt.format_device(nr, 100, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_text.data_ptr(), d_ido.data_ptr(), d_idl.data_ptr(),
+                               d_res.data_ptr(), d_sam.data_ptr(), cap, stream=st.cuda_stream)
+    got = [l for l in d_sam[:nbytes].cpu().numpy().tobytes().split(b"\n") if l]
+    fmt.close(); al.close(); fqp.close()
+    assert len(want) == len(got) == n
+    bad = [i for i in range(n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+    # a text buffer that is too small is reported, not overrun
+    fmt2 = engine.SamFormatter(gidx, p, n)
+    with pytest.raises(engine.SnapGpuError):
+        fmt2.format_device(nr, 100, d_b.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_text.data_ptr(), d_ido.data_ptr(), d_idl.data_ptr(),
+                           d_res.data_ptr(), d_sam.data_ptr(), 1000, stream=st.cuda_stream)
+    fmt2.close()
+
+
+def _split_bam(blob):
+    import struct
+    out, p = [], 0
+    while p < len(blob):
+        b = struct.unpack("<i", blob[p:p + 4])[0]
+        out.append(blob[p:p + 4 + b]); p += 4 + b
+    return out
+
+
+def _reference_bam_records(reflib, argv, out):
+    """The alignment records of the BAM file the reference binary writes (BGZF inflated, header and reference table skipped)."""
+    import gzip, struct, subprocess
+    r = subprocess.run([reflib.SNAP_ALIGNER] + argv, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    raw = gzip.open(out, "rb").read()
+    assert raw[:4] == b"BAM\x01"
+    p = 8 + struct.unpack("<i", raw[4:8])[0]
+    n_ref = struct.unpack("<i", raw[p:p + 4])[0]; p += 4
+    for _ in range(n_ref):
+        l = struct.unpack("<i", raw[p:p + 4])[0]; p += 8 + l
+    return _split_bam(raw[p:])
+
+
+@pytest.mark.parametrize("name,extra", [("noisy150", []), ("indel100", ["-="]), ("noisy150", ["-G-"])])
+def test_bam_records_from_the_device_equal_reference_binary(engine, gidx, small_cfg, reflib, tmp_path, name, extra):
+    """SNAPGPU_FORMAT_BAM: the uncompressed BAM alignment records formatted on the device vs the records of the .bam file
+    `snap-aligner single ... -o out.bam -t 1` writes (its BGZF blocks inflated): every record, byte for byte."""
+    rb = small_cfg.reads[name]
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "o.bam")
+    rb.write_fastq(fq)
+    want = _reference_bam_records(reflib, ["single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14"] + extra, out)
+    p = engine.default_params(maxDist=14, useAffineGap=0 if "-G-" in extra else 1)
+    al = engine.SingleAligner(gidx, p, 4096)
+    res, _ = al.align(rb)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096, use_m=("-=" not in extra))
+    fmt.set_format(bam=True)
+    got = _split_bam(fmt.format(rb, [b"r%d" % i for i in range(rb.n)], res))
+    fmt.close()
+    assert len(want) == len(got) == rb.n
+    bad = [i for i in range(rb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+
+
+def test_bam_pair_records_from_the_device_and_bgzf(engine, gidx, small_cfg, reflib, tmp_path):
+    """Pairs as BAM records on the device (mate fields, bins, template lengths, QS) vs the reference binary's .bam; then the record stream
+    wrapped into BGZF members on the device (snapgpu_bgzf_device: stored deflate blocks + CRC-32) inflates, with the standard gzip reader, to
+    exactly that stream."""
+    import gzip, io
+    import torch
+    pb = small_cfg.pairs["noisy150"]
+    f1 = str(tmp_path / "p1.fq"); f2 = str(tmp_path / "p2.fq"); out = str(tmp_path / "o.bam")
+    ids = []
+    with open(f1, "wb") as a, open(f2, "wb") as b:
+        for i in range(pb.n // 2):
+            x, q = pb.read(2 * i); a.write(b"@p%d/1\n%s\n+\n%s\n" % (i, x, q))
+            x, q = pb.read(2 * i + 1); b.write(b"@p%d/2\n%s\n+\n%s\n" % (i, x, q))
+            ids += [b"p%d/1" % i, b"p%d/2" % i]
+    want = _reference_bam_records(reflib, ["paired", small_cfg.idx, f1, f2, "-o", out, "-t", "1"], out)
+    p, pp = engine.default_params(maxDist=27, numSeedsFromCommandLine=8), engine.default_paired_params()
+    al = engine.PairedAligner(gidx, p, pp, 2048)
+    res, _ = al.align(pb)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096)
+    fmt.set_format(bam=True)
+    blob = fmt.format(pb, ids, res, paired=True)
+    fmt.close()
+    got = _split_bam(blob)
+    assert len(want) == len(got) == pb.n
+    bad = [i for i in range(pb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+    # BGZF on the device: several members (the stream is > 65280 bytes), the last one short
+    dev = torch.device("cuda", 0)
+    payload = np.frombuffer(blob, dtype=np.uint8)
+    assert payload.size > 2 * 65280
+    d_in = torch.from_numpy(payload.copy()).to(dev)
+    cap = payload.size + 31 * (payload.size // 65280 + 2)
+    d_out = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    used = engine.bgzf_device(d_in.data_ptr(), payload.size, d_out.data_ptr(), cap)
+    torch.cuda.synchronize()
+    z = d_out[:used].cpu().numpy().tobytes()
+    assert used == payload.size + 31 * ((payload.size + 65279) // 65280)
+    assert z[:4] == b"\x1f\x8b\x08\x04" and z[12:14] == b"BC"
+    assert gzip.GzipFile(fileobj=io.BytesIO(z)).read() == blob
+    with pytest.raises(engine.SnapGpuError):
+        engine.bgzf_device(d_in.data_ptr(), payload.size, d_out.data_ptr(), payload.size)
+
+
 def test_sam_records_of_quality_clipped_reads_from_the_device(engine, gidx, small_cfg, reflib, tmp_path):
     """Reads with '#' quality tails: the aligner gets the clipped view (Read::clip, default -C-+), snapgpu_sam_format_single the whole
     read plus the clip counts; the records (whole read, S operations) must be the reference binary's."""
