@@ -514,7 +514,11 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
             uint64_t candidatesMask = el.candidatesUsed;
             while (candidatesMask != 0) {
                 uint32_t candidateIndexToScore = 0;
+#if defined(__CUDA_ARCH__)
+                candidateIndexToScore = (uint32_t)(__ffsll((long long)candidatesMask) - 1);                       // _BitScanForward64
+#else
                 { uint64_t m = candidatesMask; while (!(m & 1)) { m >>= 1; candidateIndexToScore++; } }   // _BitScanForward64
+#endif
                 uint64_t candidateBit = (uint64_t)1 << candidateIndexToScore;
                 candidatesMask &= ~candidateBit;
                 if ((el.candidatesScored & candidateBit) != 0) continue;

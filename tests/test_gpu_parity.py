@@ -79,7 +79,10 @@ def test_leaf_golden_ag(engine, golden_dir):
     g = np.load(os.path.join(golden_dir, "leaf_ag.npz"))
     got = engine.test_ag(g["text"], g["pat"], g["qual"], g["jobs"], J.AG_OUT, [1, 4, 6, 1, 10, 7])
     same = J.same_out(g["out"], got)
-    assert (~same).sum() <= 0.01 * same.size
+    # exactly the history-dependent jobs may differ (flagged by the scalar restatement's poison check), nothing else
+    hist = _history_dependent(g["text"], g["pat"], g["qual"], g["jobs"], [1, 4, 6, 1, 10, 7])
+    assert hist.sum() <= 0.01 * hist.size
+    assert same[~hist].all()
     assert (g["out"]["agScore"] == got["agScore"]).all()
     assert (g["out"]["textOffset"] == got["textOffset"]).all() and (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
