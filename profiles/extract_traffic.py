@@ -29,7 +29,8 @@ def main():
     args = sys.argv[1:]
     for k in range(0, len(args), 3):
         key, rep, desc = args[k], args[k + 1], args[k + 2]
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # REPORT: a .ncu-rep, or the CSV `ncu -i REPORT --page raw --csv` printed (profiles/refresh_traffic.sh leaves those in gpurun_out/)
+        raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(hdr)}
@@ -44,7 +45,9 @@ def main():
                 r = w = 0.0
             rd += r; wr += w
             try:
-                inst += float(vals[col["smsp__inst_executed.sum"]].replace(",", ""))
+                v = float(vals[col["smsp__inst_executed.sum"]].replace(",", ""))
+                if v == v:
+                    inst += v
             except Exception:
                 pass
             per_launch.append({"kernel": vals[col["Kernel Name"]][:40], "dram_bytes": int(r + w),

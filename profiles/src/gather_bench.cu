@@ -58,6 +58,11 @@ static void run(const uint8_t *tbl, uint64_t tableBytes, uint64_t nAccess, unsig
 
 int main(int argc, char **argv)
 {
+    if (argc > 3) {          // L2 fetch granularity hint (bytes): 32, 64 or 128
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[3]));
+        size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("{\"l2_fetch_granularity_requested\": %d, \"set_rc\": %d, \"now\": %zu}\n", atoi(argv[3]), (int)e, got);
+    }
     double gib = argc > 1 ? atof(argv[1]) : 32.0;
     uint64_t tableBytes = (uint64_t)(gib * 1073741824.0) / 4096 * 4096;
     uint64_t nAccess = argc > 2 ? strtoull(argv[2], 0, 10) : (1ULL << 26);

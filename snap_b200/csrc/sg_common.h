@@ -193,7 +193,9 @@ SG_HD void sg_scratch_carve(const SgParams &p, uint8_t *base, SgScratch *s)
 }
 
 // The per-warp block of shared memory behind those small copies and the four derived strings of a short read.
+#ifndef SG_SMALL_LV_CELLS
 #define SG_SMALL_LV_CELLS 512        // (k+1)(2k+1) <= 512  <=>  k <= 15
+#endif
 #define SG_SMALL_BT 32
 #define SG_SMALL_READ_LEN 152
 struct
