@@ -15,6 +15,7 @@
 #pragma once
 #include "sg_ag.h"
 #include "sg_warp_ag_packed.cuh"
+#include "sg_warp_ag_duo.cuh"
 
 
 __device__ __forceinline__ int sg_shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -94,23 +95,41 @@ __device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int ope
             { int v = t2 - (nVecHere - 3) * ext; if (nVecHere > 2 && v > fl) fl = v; }
             { int v = t3 - (nVecHere - 4) * ext; if (nVecHere > 3 && v > fl) fl = v; }
             if (fl < 0) fl = 0;
-            const unsigned validBytes = nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u);
+            // lazy F (:534-569).  Measured on `snap single -d 14` (profiles/r02_duo_*): 4.4 rounds per (row, segment) -- with gap-extend 1
+            // against gap-open 7 the cells right of the diagonal stay within reach of F round after round -- so the round is kept to
+            // the bone: a lane outside the unit holds an H nothing beats (no `valid` tests), "my vector is at or before the first one
+            // with no live lane" is one mask test on the vote, and X (:572) is taken after the loop in closed form -- lane 7 holds SSE
+            // lane 7-r's f, r rounds decayed, at the top of round r -- instead of by a shuffle per round.
+            const unsigned stopBits = 0x80808080u & (nVecHere >= 4 ? 0xffffffffu : ((1u << (8 * nVecHere)) - 1u));
+            const unsigned beforeMe = 0x80808080u & ((1u << (8 * q)) - 1u);
+            const int dRound = nVecHere * ext, fl0 = fl;
+            if (!valid) h = 0x3fff;
+            int nRounds = 0;
             #pragma unroll 1
             for (int kk = 0; kk < SG_VEC - 1; kk++) {
-                if (j < segEndTrack) { const int f7 = sg_shfl(fl, 7); if (f7 > X0) X0 = f7; }      // X0 only feeds the next segment of this row
+                nRounds++;
                 { const int up = sg_shfl(fl, laneUp); fl = (l == 0) ? 0 : up; }
                 int fv = fl - q * ext; if (fv < 0) fv = 0;
-                const bool a2 = valid && fv > h;
-                const int newh = a2 ? fv : h;
+                const int newh = fv > h ? fv : h;
                 int tmp2 = newh - open; if (tmp2 < 0) tmp2 = 0;
                 int fn = fv - ext; if (fn < 0) fn = 0;
-                const bool live = valid && fn > tmp2;
+                const bool live = fn > tmp2;
                 const unsigned liveMask = __ballot_sync(0xffffffffu, live);
-                const unsigned zb = (liveMask - 0x01010101u) & ~liveMask & 0x80808080u & validBytes;
-                const int firstConv = zb ? ((__ffs(zb) - 1) >> 3) : 4;
-                if (q <= firstConv) { h = newh; act |= (a2 ? 2 : 0) | (live ? 32 : 0); }
-                if (firstConv < 4) break;
-                fl = fl - nVecHere * ext; if (fl < 0) fl = 0;
+                // lowest all-zero byte of the ballot among the unit's vectors = first vector at which no lane is live
+                const unsigned zb = (liveMask - 0x01010101u) & ~liveMask & stopBits;
+                if (!(zb & beforeMe)) {
+                    if (fv > h) act |= 2;
+                    if (live) act |= 32;
+                    h = newh;
+                }
+                if (zb) break;
+                fl = fl - dRound; if (fl < 0) fl = 0;
+            }
+            if (j < segEndTrack) {        // X only feeds the next segment of this row
+                int v = fl0 - (7 - l) * dRound;
+                if (v < 0 || (7 - l) >= nRounds) v = 0;
+                v = __reduce_max_sync(0xffffffffu, v);
+                if (v > X0) X0 = v;
             }
             if (valid) {
                 const int col = j * segLen + l * numVec + q;
@@ -139,7 +158,8 @@ __device__ __noinline__ void sg_warp_ag_rows_banded4(const SgScratch &S, int ope
 }
 
 
-// AGM: 2 = the caller's kernel may take the unrolled packed instantiation (only stage 2 of the paired launch carries that code)
+// AGM: 2 = the caller's kernel may take the unrolled packed instantiation (only stage 2 of the paired launch carries that code);
+//      3 = 2 + the experimental narrow-band form of sg_warp_ag_duo.cuh when SgAgParams.usePacked has bit 2 set (leaf tests only)
 template <int AGM = 0>
 __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScratch &S, const SgAgParams &P, int dir, bool banded,
                                                 const uint8_t *text, int textLen, const uint8_t *pattern, const uint8_t *quality, int patternLen,
@@ -196,17 +216,29 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
         }
     }
 #ifndef SG_AG_NO_PACKED
-    if (!banded && numVec <= SG_AGP_MAX_VEC && P.usePacked) {
+    if (!banded && numVec <= SG_AGP_MAX_VEC && (P.usePacked & 3)) {
         // unbanded, up to 192 columns: the packed (two cells per lane, DPX s16x2) register-resident form
         __syncwarp();
         SgAgBests bb;
-        if (AGM == 2 && P.usePacked == 2) sg_warp_ag_rows_packed<true>(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
+        if (AGM >= 2 && (P.usePacked & 3) == 2) sg_warp_ag_rows_packed<true>(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
         else sg_warp_ag_rows_packed<false>(S, P, dir, text, textLen, pattern, patternLen, scoreInit, lay, bt, lane, &bb);
         sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
                      bb.lScore, bb.lText, bb.lPat, bb.gScore, bb.gText, out);
         return;
     }
 #endif
+    if (AGM == 3 && banded && numVec <= 4 && (P.usePacked & 3) && (P.usePacked & 4)) {
+        // bands of up to 32 columns, the experimental form: two (row, segment) units per step, two cells per lane, lazy F without
+        // its loop (sg_warp_ag_duo.cuh).  Same results; 12 % fewer instructions than the one-cell-per-lane form below but 4 % slower
+        // in the single-end kernel and 10 % in the paired one (instruction-fetch stalls: its step is 530 instructions of straight-line
+        // code against a 6 KB L0), so only the leaf-test kernel (AGM 3) and the SIMT emulator of the CPU suite instantiate it.
+        __syncwarp();
+        SgAgBests bb;
+        sg_warp_ag_rows_banded_duo(S, P, dir, text, textLen, pattern, patternLen, w, scoreInit, lay, bt, lane, &bb);
+        sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,
+                     bb.lScore, bb.lText, bb.lPat, bb.gScore, bb.gText, out);
+        return;
+    }
     // striped query profile (the reference's qProfile, :921-935 / :348-365) as int8, -128 standing for the INT16_MIN padding
     int8_t *prof = S.agProf;
     for (int idx = lane; idx < stride; idx += 32) {
@@ -217,7 +249,7 @@ __device__ __noinline__ void sg_warp_ag_compute(const SgTables &T, const SgScrat
     }
     __syncwarp();
 
-    if (banded && numVec <= 4 && P.usePacked) {      // (same switch as the packed form: measured +10 % for pairs, -3 % for single-end)
+    if (banded && numVec <= 4 && (P.usePacked & 3)) {      // (same switch as the packed form: measured +10 % for pairs, -3 % for single-end)
         SgAgBests bb;
         sg_warp_ag_rows_banded4(S, open, ext, dir, text, textLen, patternLen, w, scoreInit, lay, bt, lane, &bb);
         sg_ag_finish(T, P, lay, bt, dir, text, pattern, quality, patternLen, scoreInit, endBonus, useClippingOptimizations,

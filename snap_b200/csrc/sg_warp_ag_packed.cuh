@@ -25,7 +25,11 @@ __device__ __forceinline__ unsigned sg_pk2(int v) { return sg_pk(v, v); }
 __device__ __forceinline__ unsigned sg_nzmask2(unsigned x)
 {
     unsigned neg = __vsub2(0u, x), m;
+#if defined(__CUDA_ARCH__)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(neg), "r"(0u), "r"(0xbb99u));
+#else
+    m = ((neg & 0x8000u) ? 0xffffu : 0u) | ((neg & 0x80000000u) ? 0xffff0000u : 0u);       // (the SIMT emulator of tests/hostsim/warpsim.h)
+#endif
     return m;
 }
 __device__ __forceinline__ unsigned sg_relu2(unsigned x) { return __vimax_s16x2_relu(x, x); }

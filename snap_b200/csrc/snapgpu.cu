@@ -589,10 +589,12 @@ __global__ void sg_test_ag_warp_kernel(const SgTables *tb, SgParams pr, SgAgPara
     long long nW = ((long long)gridDim.x * blockDim.x) >> 5;
     SgScratch s;
     sg_scratch_carve(pr, scratchBase + (size_t)wid * scratchBytes, &s);
+    __shared__ uint32_t snapS[7 * 32];           // (one warp per block)
+    if (!(P.usePacked & 8)) s.agSnap = snapS;    // usePacked & 4: the experimental narrow-band form; & 8: with its per-round H in the arena
     for (long long j = wid; j < nJobs; j += nW) {
         SgAgResult r;
         r.agScore = -1; r.textOffset = 0; r.patternOffset = 0; r.nEdits = 0; r.matchProbability = 0.0;
-        sg_warp_ag_compute<2>(*tb, s, P, jobs[j].dir, jobs[j].banded != 0, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff,
+        sg_warp_ag_compute<3>(*tb, s, P, jobs[j].dir, jobs[j].banded != 0, textBuf + jobs[j].textOff, jobs[j].textLen, patBuf + jobs[j].patOff,
                            qualBuf + jobs[j].patOff, jobs[j].patternLen, jobs[j].w, jobs[j].scoreInit, jobs[j].isRC != 0,
                            jobs[j].useClippingOptimizations != 0, &r, lane);
         __syncwarp();

@@ -114,9 +114,10 @@ def test_warp_leaves_golden(engine, golden_dir):
         assert (g["out"]["patternOffset"] == got["patternOffset"]).all()
 
 
-@pytest.mark.parametrize("packed", ["1", "0", "2"])
+@pytest.mark.parametrize("packed", ["1", "0", "2", "5", "13"])
 def test_warp_leaves_fuzz_vs_scalar_and_reference(engine, reflib, monkeypatch, packed):
-    """packed = 1: unbanded jobs take the s16x2 (DPX) form used by the paired kernel (2: its unrolled instantiation); 0: the int form."""
+    """packed = 1: unbanded jobs take the s16x2 (DPX) form used by the paired kernel (2: its unrolled instantiation); 0: the int form;
+    5: narrow bands take the experimental two-units-per-step form of sg_warp_ag_duo.cuh (13: with its per-round H in the arena)."""
     monkeypatch.setenv("SNAPGPU_TEST_AG_PACKED", packed)
     for seed in (301, 302):
         t, p, q, jb = J.lv_jobs(3000, seed)
