@@ -669,6 +669,19 @@ def sam_phase(args, c, host_batch, paired):
         e1.record(st)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        # (1b) row N4: the coordinate sort of that batch's records on the device (keys, stable radix sort, scan, move)
+        d_sorted = torch.empty((cap,), dtype=torch.uint8, device=device)
+        d_keys = torch.empty((n,), dtype=torch.int64, device=device)
+        sorted_bytes = fmt.sort_device(d_sam.data_ptr(), d_sorted.data_ptr(), cap, d_keys.data_ptr(), 0, st.cuda_stream)
+        e0.record(st)
+        for _ in range(reps):
+            fmt.sort_device(d_sam.data_ptr(), d_sorted.data_ptr(), cap, d_keys.data_ptr(), 0, st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        sort_ms = e0.elapsed_time(e1) / reps
+        k = d_keys.cpu().numpy().view(np.uint64)
+        sort_ok = bool(sorted_bytes == nbytes and (k[1:] >= k[:-1]).all() and int((d_sorted[:sorted_bytes] == 10).sum().item()) == n)
+        del d_sorted, d_keys
         # (3) FASTQ text on the host -> SAM text on the host
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -693,6 +706,10 @@ def sam_phase(args, c, host_batch, paired):
             "roofline": {"bound": "hbm", "achieved": round(alg / (ms / 1e3) / 1e9, 2), "peak": c.peak, "unit": "GB/s", "frac": round(alg / (ms / 1e3) / 1e9 / c.peak, 5),
                          "note": "algorithmic bytes = SAM text written + reads, ids and result records read; the kernel is latency / issue bound (integer DP per read), not bandwidth bound"},
             "host_buffer_abi_reads_per_s": round(n / host_s, 1), "records_ok": ok, "device_and_host_paths_agree": same,
+            "sort": {"what": "snapgpu_sam_sort_device: SortedDataFilter's stable coordinate sort of the batch's records (SURVEY 8f N4), keys + cub radix sort + "
+                             "scan + one warp per record", "records": int(n), "ms": round(sort_ms, 3), "records_per_s": round(n / (sort_ms / 1e3), 1),
+                     "gbs": round(2 * nbytes / (sort_ms / 1e3) / 1e9, 1), "frac_of_hbm_peak": round(2 * nbytes / (sort_ms / 1e3) / 1e9 / c.peak, 4),
+                     "keys_ascending_and_all_records_present": sort_ok},
             "e2e_with_output": {"value": round(n / e2e_s, 1), "unit": "reads/s", "scope": "FASTQ text in pinned host memory -> H2D -> snapgpu_fastq_parse_device -> snapgpu_align_single_device -> "
                                 "snapgpu_sam_format_single_device -> D2H of the SAM text; batches one after the other (no overlap between batches)",
                                 "h2d_bytes_per_step": int(text.size), "d2h_bytes_per_step": int(nbytes), "ms_per_batch": round(e2e_s * 1e3, 2)},
@@ -1022,6 +1039,8 @@ def run_ours(args):
             out["sam_phase"] = sam_phase(args, c, head["_host0"], paired)
             if not out["sam_phase"].get("records_ok", True) or not out["sam_phase"].get("device_and_host_paths_agree", True):
                 failures.append("sam_phase: records malformed or the device-resident and host-buffer paths disagree")
+            if not out["sam_phase"].get("sort", {}).get("keys_ascending_and_all_records_present", True):
+                failures.append("sam_phase.sort: sorted records not in key order or not all there")
         except Exception as e:
             import traceback
             traceback.print_exc()

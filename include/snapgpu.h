@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-#define SNAPGPU_ABI_VERSION 3   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate */
+#define SNAPGPU_ABI_VERSION 4   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
+                                 * 4: snapgpu_sam_sort_device */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
@@ -390,6 +391,22 @@ int  snapgpu_sam_set_format(snapgpu_sam *s, int format);
  * payload bytes, each ONE STORED deflate block with its CRC-32 -- valid BGZF that inflates to exactly the payload (no compressor runs on
  * the device; the reference compresses, so files differ in size, not in content).  outCapacity >= nBytes + 31 per member.  Asynchronous on `cudaStream`. */
 int  snapgpu_bgzf_device(const char *d_in, int64_t nBytes, char *d_out, int64_t outCapacity, int64_t *outBytes, void *cudaStream);
+
+/* SURVEY 8(f) row N4, the sort: the reference's sorting writer (`-so`; SortedDataFilter, reference SNAPLib/SortedDataWriter.cpp:905-1010) files
+ * every record under the key of the genome location SimpleReadWriter passed to DataWriter::advance for it (ReadWriter.cpp:331, :601-615: the
+ * record's own final location, its mate's when it is unaligned itself) -- (original contig number, 1-based position in the contig), (0, 0)
+ * for location 0, (-1, 0) for an unaligned record with -1 compared as unsigned, so those come last -- stable-sorts each write batch by that key and copies the records
+ * out in that order as one sorted run of its final merge.  snapgpu_sam_sort_device does that for the batch the LAST snapgpu_sam_format_*
+ * call of `s` formatted (SAM or BAM records; d_text = where that call left them on the device, NULL = the handle's own staging buffer
+ * after a host-buffer format call): one stable radix sort of the keys on the device, the
+ * records moved by one warp each into d_sorted.  d_keysOut (optional, one uint64 per record, ascending: contig << 32 | position, contig 0xffffffff = unaligned) and
+ * d_offsetsOut (optional, start of each sorted record) are what a merge of several runs, a BAM index or duplicate marking go on from; with
+ * 180 GB of HBM a whole run's records can be ONE batch and no merge is left.  Synchronises `cudaStream` once.
+ * Not on the device yet: the k-way merge of runs (SortedDataFilterSupplier::mergeSort), duplicate marking (BAMDupMarkFilter, Bam.cpp:2619)
+ * and the .bai index (BAMIndexSupplier, Bam.cpp:3229). */
+int  snapgpu_sam_sort_device(snapgpu_sam *s, const char *d_text, char *d_sorted, int64_t sortedCapacity, int64_t *sortedBytes,
+                             uint64_t *d_keysOut, uint64_t *d_offsetsOut, void *cudaStream);
+int64_t snapgpu_sam_last_record_count(const snapgpu_sam *s);       /* records (2 per pair) of the last format call */
 
 /* Device-resident forms: every array, and the text buffer, is a DEVICE pointer -- the reads as parsed by snapgpu_fastq_parse_device, the
  * records as left by snapgpu_align_*_device -- so a batch goes from FASTQ text to SAM text without its reads or results visiting the

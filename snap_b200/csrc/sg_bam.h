@@ -117,7 +117,10 @@ SG_HDN int sg_bam_write_single(const SgSamContext &C, const SgBamContext &B, SgS
     for (;;) {
         const int n = affineGap ? sg_bam_format(C, B, R, res.status, res.mapq, finalLocation, res.direction, true, res.score, res.basesClippedBefore, res.basesClippedAfter, out, &addFrontClipping)
                                 : sg_bam_format(C, B, R, res.status, res.mapq, finalLocation, res.direction, false, 0, 0, 0, out, &addFrontClipping);
-        if (n > 0) return n;
+        if (n > 0) {
+            if (C.sort) { C.sort->nRecords = 1; C.sort->bytes[0] = (uint32_t)n; C.sort->location[0] = finalLocation == SG_SAM_INVALID_LOCATION ? SG_SORT_UNALIGNED : finalLocation; }
+            return n;
+        }
         nAdjustments++;
         if (addFrontClipping == 0) return 0;
         const int origC = res.status == SNAPGPU_NOT_FOUND ? -1 : sg_contig_at(ix, res.location);
@@ -287,6 +290,11 @@ SG_HDN int sg_bam_write_pair(const SgSamContext &C, const SgBamContext &B, SgSam
             *q++ = 'Q'; *q++ = 'S'; *q++ = 'i'; sg_put_le32(q, (uint32_t)mqs); q += 4;
             sg_put_le32(rec, (uint32_t)((int)(q - rec) - 4));
             p = (char *)q;
+            if (C.sort) {        // ReadWriter.cpp:601-606: filed under its own location, or its mate's when it has none
+                const int64_t l = locations[w] != SG_SAM_INVALID_LOCATION ? locations[w] : locations[m];
+                C.sort->nRecords = 2; C.sort->location[fs] = l == SG_SAM_INVALID_LOCATION ? SG_SORT_UNALIGNED : l;
+                C.sort->bytes[fs] = (uint32_t)((const uint8_t *)q - rec);
+            }
         }
         n = (int)(p - out);
         int newOrder0 = (locations[0] <= locations[1]) ? 0 : 1;

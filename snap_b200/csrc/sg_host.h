@@ -18,6 +18,7 @@ struct SgHostIndex {
     std::vector<uint8_t>  basesPadded;   // SG_N_PADDING 'n' + bases + SG_N_PADDING 'n'
     std::vector<int64_t>  contigStart;
     std::vector<uint8_t>  contigIsAlt;
+    std::vector<int32_t>  contigOriginal;   // Genome::Contig::originalContigNumber (order in the FASTA; what sorted output is ordered by)
     std::vector<std::string> contigName;
     int64_t  nBases = 0, altFirstLocation = LLONG_MAX;
     uint32_t seedLen = 0, keyBytes = 0, nTables = 0, large = 0, entryBytes = 0, chromosomePadding = 0, locationSize = 4;
@@ -84,7 +85,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
         if (!nl || 3 != sscanf(p, "%lld %d %d", &nBases, &nContigs, &flags)) { err = "Genome header unparsable"; return false; }
         p = nl + 1;
         ix.nBases = nBases;
-        ix.contigStart.clear(); ix.contigIsAlt.clear(); ix.contigName.clear();
+        ix.contigStart.clear(); ix.contigIsAlt.clear(); ix.contigName.clear(); ix.contigOriginal.clear();
         for (int i = 0; i < nContigs; i++) {
             nl = (const char *)memchr(p, '\n', endp - p);
             if (!nl) { err = "Genome contig line truncated"; return false; }
@@ -97,6 +98,7 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
             while (q < nl && spaces < 7) { if (*q == ' ') spaces++; q++; }
             ix.contigStart.push_back(start);
             ix.contigIsAlt.push_back((cflags & 1) ? 1 : 0);
+            ix.contigOriginal.push_back(origNum);
             if (nameLen < 0 || (long long)nameLen > (long long)(nl - q)) { err = "Genome contig line: name length runs past the line"; return false; }
             ix.contigName.push_back(std::string(q, (size_t)nameLen));
             p = nl + 1;

@@ -27,6 +27,12 @@ struct SgSamRead {                   // the Read object's view of one read (Read
     SG_HD void setAdditionalBackClipping(int c) { dataLength -= (uint32_t)(c - additionalBackClipping); additionalBackClipping = c; }
 };
 
+// What SimpleReadWriter hands DataWriter::advance for each record it wrote (ReadWriter.cpp:331, :605-615): its bytes and the genome location it
+// is filed under by a sorting writer (SortedDataFilter::onAdvance, SortedDataWriter.cpp:905-939) -- the record's own final location, or its
+// mate's when it is unaligned itself; SG_SORT_UNALIGNED when neither is.  Row N4 of SURVEY 8(f) sorts on these.
+#define SG_SORT_UNALIGNED (-1LL)
+struct SgSortInfo { int64_t location[2]; uint32_t bytes[2]; int nRecords; };
+
 struct SgSamContext {
     const SgIndexView *ix;
     const char *const *contigName;   // [nContigs], NUL-terminated
@@ -37,6 +43,7 @@ struct SgSamContext {
     SgAgCigarScratch agS;
     uint8_t *data, *quality;         // [maxReadLen] scratch for the oriented read
     uint8_t *data2, *quality2;       // the same for the second read of a pair
+    SgSortInfo *sort = (SgSortInfo *)0;   // NULL, or where the writers leave the sort keys of the records of this call
 };
 
 struct SgSamResult {                 // the SingleAlignmentResult fields the writer reads (ReadWriter.cpp:223-310)
@@ -172,7 +179,10 @@ SG_HDN int sg_sam_write_single(const SgSamContext &C, SgSamRead R, SgSamResult r
     for (;;) {
         const int n = affineGap ? sg_sam_format(C, R, res.status, res.mapq, finalLocation, res.direction, true, res.score, res.basesClippedBefore, res.basesClippedAfter, out, &addFrontClipping)
                                 : sg_sam_format(C, R, res.status, res.mapq, finalLocation, res.direction, false, 0, 0, 0, out, &addFrontClipping);
-        if (n > 0) return n;
+        if (n > 0) {
+            if (C.sort) { C.sort->nRecords = 1; C.sort->bytes[0] = (uint32_t)n; C.sort->location[0] = finalLocation < 0 ? SG_SORT_UNALIGNED : finalLocation; }
+            return n;
+        }
         nAdjustments++;
         if (addFrontClipping == 0) return 0;                      // (cannot happen here: out of buffer space in the reference)
         const int origC = res.status == SNAPGPU_NOT_FOUND ? -1 : sg_contig_at(ix, res.location);
@@ -325,6 +335,11 @@ SG_HDN int sg_sam_write_pair(const SgSamContext &C, SgSamRead R0, SgSamRead R1, 
         char *p = out;
         for (int fs = 0; fs < 2; fs++) {
             const int w = writeOrder[fs], m = 1 - w;
+            const char *const recStart = p;
+            if (C.sort) {        // ReadWriter.cpp:601-606: filed under its own location, or its mate's when it has none
+                const int64_t l = locations[w] != SG_SAM_INVALID_LOCATION ? locations[w] : locations[m];
+                C.sort->nRecords = 2; C.sort->location[fs] = l == SG_SAM_INVALID_LOCATION ? SG_SORT_UNALIGNED : l;
+            }
             const bool firstInPair = w == 0;
             int flags = line[w].flags | 0x1 | (firstInPair ? 0x40 : 0x80);
             int contig = line[w].contig; int64_t pos = line[w].positionInContig;
@@ -384,6 +399,7 @@ SG_HDN int sg_sam_write_pair(const SgSamContext &C, SgSamRead R0, SgSamRead R1, 
             for (uint32_t i = 0; i < line[m].fullLength; i++) { const int q = (int)qualBuf[m][i] - '!'; mqs += (q >= 15) ? (q != 255) * q : 0; }
             p = sg_put_str(p, "\tQS:i:"); p = sg_put_i64(p, mqs);
             *p++ = '\n';
+            if (C.sort) C.sort->bytes[fs] = (uint32_t)(p - recStart);
         }
         n = (int)(p - out);
         int newOrder0 = (locations[0] <= locations[1]) ? 0 : 1;

@@ -28,7 +28,7 @@ __device__ __forceinline__ unsigned sg_nzmask2(unsigned x)
 #if defined(__CUDA_ARCH__)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(neg), "r"(0u), "r"(0xbb99u));
 #else
-    m = ((neg & 0x8000u) ? 0xffffu : 0u) | ((neg & 0x80000000u) ? 0xffff0000u : 0u);       // (the SIMT emulator of tests/hostsim/warpsim.h)
+    m = ((neg & 0x8000u) ? 0xffffu : 0u) | ((neg & 0x80000000u) ? 0xffff0000u : 0u);       // (host build: the SIMT emulator of the CPU test suite)
 #endif
     return m;
 }

@@ -63,6 +63,7 @@ struct snapgpu_index {
     std::vector<int64_t> h_contigStart;
     std::vector<std::string> h_contigName;
     std::vector<uint8_t> h_contigIsAlt;
+    std::vector<int32_t> h_contigOriginal;   // originalContigNumber of each contig (Genome.h:470)
 };
 
 struct snapgpu_aligner {
@@ -735,7 +736,7 @@ static int upload_index(const SgHostIndex &h, int device, snapgpu_index **out)
     ix->info.chromosomePadding = h.chromosomePadding; ix->info.nContigs = (uint32_t)h.contigStart.size();
     ix->info.overflowTableSize = h.overflowSize; ix->info.hashTableSlots = h.totalSlots; ix->info.hbmBytes = hbm;
     ix->h_tableStart = h.tableStart; ix->h_tableSize = h.tableSize; ix->h_tableUsed = h.tableUsed;
-    ix->h_contigStart = h.contigStart; ix->h_contigName = h.contigName; ix->h_contigIsAlt = h.contigIsAlt;
+    ix->h_contigStart = h.contigStart; ix->h_contigName = h.contigName; ix->h_contigIsAlt = h.contigIsAlt; ix->h_contigOriginal = h.contigOriginal;
     ix->view.layout = SG_LAYOUT_SNAP; ix->view.pad0 = 0; ix->view.buckets = nullptr; ix->view.nBuckets = 0;
     if (wanted_layout() == SG_LAYOUT_BUCKET) {
         if (relayout_on_device(ix, &hbm)) { snapgpu_index_close(ix); return 1; }
@@ -883,7 +884,7 @@ static int build_index_on_device(uint8_t *d_basesPadded, int64_t nBases, const i
     ix->h_tableStart = tstart; ix->h_tableSize = tsize;
     ix->h_tableUsed.assign(stats.begin(), stats.begin() + nTables);
     ix->h_contigStart.assign(contigStarts, contigStarts + nContigs);
-    for (uint32_t c = 0; c < nContigs; c++) { ix->h_contigName.push_back("chr" + std::to_string(c + 1)); ix->h_contigIsAlt.push_back(0); }
+    for (uint32_t c = 0; c < nContigs; c++) { ix->h_contigName.push_back("chr" + std::to_string(c + 1)); ix->h_contigIsAlt.push_back(0); ix->h_contigOriginal.push_back((int32_t)c); }
     *out = ix;
     return 0;
 }
@@ -939,7 +940,7 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
         snapgpu_index *tmp = nullptr;
         if (build_index_on_device(d_padded, ix->view.nBases, ix->h_contigStart.data(), (uint32_t)ix->h_contigStart.size(), ix->view.seedLen,
                                   ix->view.chromosomePadding, ix->device, &tmp, SG_LAYOUT_SNAP)) { cudaFree(d_padded); return 1; }
-        tmp->h_contigName = ix->h_contigName; tmp->h_contigIsAlt = ix->h_contigIsAlt;
+        tmp->h_contigName = ix->h_contigName; tmp->h_contigIsAlt = ix->h_contigIsAlt; tmp->h_contigOriginal = ix->h_contigOriginal;
         const int rc = snapgpu_index_save(tmp, directory);
         snapgpu_index_close(tmp);
         return rc;
@@ -966,7 +967,7 @@ int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
         for (size_t c = 0; c < ix->h_contigStart.size(); c++) {
             std::string name = ix->h_contigName[c];
             for (size_t k = 0; k < name.size(); k++) if (name[k] == ' ') name[k] = '_';      // Genome::saveToFile does the same (Genome.cpp:230-236): the line is space-separated
-            fprintf(f, "%lld %x %d %lld %x %d %d %s %s\n", (long long)ix->h_contigStart[c], ix->h_contigIsAlt[c] ? 1 : 0, (int)c, 0LL, 0,
+            fprintf(f, "%lld %x %d %lld %x %d %d %s %s\n", (long long)ix->h_contigStart[c], ix->h_contigIsAlt[c] ? 1 : 0, (int)ix->h_contigOriginal[c], 0LL, 0,
                     (int)name.size(), 1, name.c_str(), "*");
         }
         for (size_t off = 0; off < (size_t)ix->view.nBases; off += CH) {
@@ -1056,7 +1057,7 @@ static int clone_alloc(const snapgpu_index *src, int device, snapgpu_index **out
     ix->info = src->info; ix->info.hbmBytes = hbm;
     ix->h_tables_prob = src->h_tables_prob;
     ix->h_tableStart = src->h_tableStart; ix->h_tableSize = src->h_tableSize; ix->h_tableUsed = src->h_tableUsed;
-    ix->h_contigStart = src->h_contigStart; ix->h_contigName = src->h_contigName; ix->h_contigIsAlt = src->h_contigIsAlt;
+    ix->h_contigStart = src->h_contigStart; ix->h_contigName = src->h_contigName; ix->h_contigIsAlt = src->h_contigIsAlt; ix->h_contigOriginal = src->h_contigOriginal;
     *out = ix;
     return 0;
 }
@@ -1893,7 +1894,8 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
               SgAgParams ag, int useM, int useAffineGap, long long nUnits, int paired, const uint8_t *bases, const uint8_t *quals,
               const unsigned long long *offsets, const uint32_t *lens, const uint8_t *ids, const unsigned long long *idOffsets, const uint32_t *idLens,
               const snapgpu_single_result *single, const snapgpu_paired_result *pairs, const uint32_t *frontClipped, const uint32_t *clippedLens,
-              char *slots, uint32_t slotBytes, uint32_t *recordBytes, int bam, const uint8_t *rgAuxBam, int rgAuxBamLen)
+              char *slots, uint32_t slotBytes, uint32_t *recordBytes, int bam, const uint8_t *rgAuxBam, int rgAuxBamLen,
+              long long *sortLocations, uint32_t *sortBytes)
 {
     SgBamContext Bc; Bc.readGroupAux = rgAuxBam; Bc.readGroupAuxLen = rgAuxBamLen;
     const long long octet = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -1901,9 +1903,12 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
     SgSamContext C;
     C.ix = &ix; C.contigName = contigNames; C.ag = ag; C.readGroupAux = readGroupAux; C.useM = useM != 0; C.useAffineGap = useAffineGap != 0;
     sam_carve(lay, scratch + (size_t)octet * lay.perOctet, &C);
+    SgSortInfo si;
+    C.sort = &si;
     for (long long u = octet; u < nUnits; u += nOctets) {
         char *out = slots + (size_t)u * slotBytes;
         uint32_t n;
+        si.nRecords = 0;
         if (!paired) {
             SgSamRead R;
             R.unclippedData = bases + offsets[u]; R.unclippedQuality = quals + offsets[u]; R.unclippedLength = lens[u];
@@ -1936,6 +1941,13 @@ sg_sam_kernel(const __grid_constant__ SgIndexView ix, SgSamScratchLayout lay, ui
             n = bam ? (uint32_t)sg_bam_write_pair(C, Bc, R[0], R[1], pr, out) : (uint32_t)sg_sam_write_pair(C, R[0], R[1], pr, out);
         }
         recordBytes[u] = n > slotBytes ? 0u : n;
+        if ((threadIdx.x & 7) == 0) {          // what a sorting writer files each record under (row N4)
+            const long long r0 = paired ? 2 * u : u;
+            for (int k = 0; k < (paired ? 2 : 1); k++) {
+                sortLocations[r0 + k] = k < si.nRecords ? (long long)si.location[k] : SG_SORT_UNALIGNED;
+                sortBytes[r0 + k] = k < si.nRecords ? si.bytes[k] : 0u;
+            }
+        }
         __syncwarp(0xffu << (threadIdx.x & 24u));        // the octet leaves its scratch together
     }
 }
@@ -1982,6 +1994,12 @@ struct snapgpu_sam {
     char *d_text = nullptr; size_t textBytes = 0;
     void *d_cub = nullptr; size_t cubBytes = 0;
     int *d_overflow = nullptr;
+    // row N4: what the last format call filed each RECORD under (2 per pair, in the order written), for snapgpu_sam_sort_device
+    long long *d_sortLocations = nullptr; uint32_t *d_sortBytes = nullptr;
+    int32_t *d_contigOriginal = nullptr;
+    unsigned long long *d_sortKeys = nullptr, *d_sortKeysOut = nullptr, *d_recOffsets = nullptr, *d_sortedOffsets = nullptr;
+    uint32_t *d_perm = nullptr, *d_permOut = nullptr, *d_sortedBytes = nullptr;
+    int64_t lastRecords = 0, lastUnits = 0; int lastPaired = 0;
     unsigned long long *h_meta = nullptr;        // pinned: [0] last offset, [1] last length (low word), [2] overflow
     cudaStream_t stream = nullptr;
 };
@@ -1994,6 +2012,8 @@ void snapgpu_sam_destroy(snapgpu_sam *s)
     cudaFree(s->d_scratch); cudaFree(s->d_names); cudaFree((void *)s->d_namePtrs); cudaFree(s->d_rgAux); cudaFree(s->d_bases); cudaFree(s->d_quals); cudaFree(s->d_ids);
     cudaFree(s->d_results); cudaFree(s->d_offsets); cudaFree(s->d_idOffsets); cudaFree(s->d_lens); cudaFree(s->d_idLens); cudaFree(s->d_recordBytes); cudaFree(s->d_front); cudaFree(s->d_clippedLens); cudaFree(s->d_slots);
     cudaFree(s->d_recordOffsets); cudaFree(s->d_text); cudaFree(s->d_cub); cudaFree(s->d_overflow); cudaFreeHost(s->h_meta); cudaFree(s->d_rgAuxBam);
+    cudaFree(s->d_sortLocations); cudaFree(s->d_sortBytes); cudaFree(s->d_contigOriginal); cudaFree(s->d_sortKeys); cudaFree(s->d_sortKeysOut); cudaFree(s->d_recOffsets);
+    cudaFree(s->d_sortedOffsets); cudaFree(s->d_perm); cudaFree(s->d_permOut); cudaFree(s->d_sortedBytes);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -2025,7 +2045,9 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     const char rg[] = "\tRG:Z:FASTQ\tPL:Z:Illumina\tPU:Z:pu\tLB:Z:lb\tSM:Z:sm";
     size_t c1 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, c1, (uint32_t *)nullptr, (unsigned long long *)nullptr, (int)maxBatchReads);
-    s->cubBytes = c1 + 256;
+    size_t c2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, c2, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)maxBatchReads);
+    s->cubBytes = (c1 > c2 ? c1 : c2) + 256;
     bool ok = cudaMalloc((void **)&s->d_names, blob.size() + 16) == cudaSuccess && cudaMalloc((void **)&s->d_namePtrs, (off.size() + 1) * sizeof(char *)) == cudaSuccess &&
               cudaMalloc((void **)&s->d_rgAux, sizeof(rg)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&s->d_ids, (size_t)maxBatchReads * SG_SAM_MAX_ID + 16) == cudaSuccess &&
@@ -2035,6 +2057,12 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
          cudaMalloc((void **)&s->d_recordBytes, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_recordOffsets, (size_t)maxBatchReads * 8) == cudaSuccess &&
          cudaMalloc((void **)&s->d_front, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_clippedLens, (size_t)maxBatchReads * 4) == cudaSuccess &&
          cudaMalloc((void **)&s->d_cub, s->cubBytes) == cudaSuccess && cudaMalloc((void **)&s->d_overflow, sizeof(int)) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_sortLocations, (size_t)maxBatchReads * 8) == cudaSuccess && cudaMalloc((void **)&s->d_sortBytes, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_sortKeys, (size_t)maxBatchReads * 8) == cudaSuccess && cudaMalloc((void **)&s->d_sortKeysOut, (size_t)maxBatchReads * 8) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_recOffsets, (size_t)maxBatchReads * 8) == cudaSuccess && cudaMalloc((void **)&s->d_sortedOffsets, (size_t)maxBatchReads * 8 + 8) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_perm, (size_t)maxBatchReads * 4) == cudaSuccess && cudaMalloc((void **)&s->d_permOut, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_sortedBytes, (size_t)maxBatchReads * 4) == cudaSuccess &&
+         cudaMalloc((void **)&s->d_contigOriginal, idx->h_contigOriginal.size() * 4 + 16) == cudaSuccess &&
          cudaMallocHost((void **)&s->h_meta, 4 * sizeof(unsigned long long)) == cudaSuccess &&
          cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) {
@@ -2047,6 +2075,8 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     SG_CUDA(cudaMemcpy(s->d_names, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     if (!ptrs.empty()) SG_CUDA(cudaMemcpy((void *)s->d_namePtrs, ptrs.data(), ptrs.size() * sizeof(char *), cudaMemcpyHostToDevice));
     SG_CUDA(cudaMemcpy(s->d_rgAux, rg, sizeof(rg), cudaMemcpyHostToDevice));
+    if (idx->h_contigOriginal.size() != idx->h_contigStart.size()) { snapgpu_sam_destroy(s); return sg_fail("snapgpu_sam_create: index without original contig numbers"); }
+    SG_CUDA(cudaMemcpy(s->d_contigOriginal, idx->h_contigOriginal.data(), idx->h_contigOriginal.size() * 4, cudaMemcpyHostToDevice));
     // the same read group line as BAM tags (ReaderContext::defaultReadGroupAux for a BAM writer): the literal's terminating NUL ends the last tag
     static const char rgBam[] = "RGZFASTQ\0PLZIllumina\0PUZpu\0LBZlb\0SMZsm";
     s->rgAuxBamLen = (int)sizeof(rgBam);
@@ -2159,11 +2189,13 @@ static int sam_format_device(snapgpu_sam *s, int paired, int64_t nReads, uint32_
 #define SG_SAM_LAUNCH(MB) sg_sam_kernel<MB><<<blocks, 256, 0, st>>>(s->index->view, s->lay, s->d_scratch, s->d_namePtrs, s->d_rgAux, s->ag, s->useM, s->useAffineGap, nUnits, paired, \
                                           d_bases, d_quals, d_offsets, d_lens, d_ids, d_idOffsets, d_idLens, \
                                           paired ? nullptr : (const snapgpu_single_result *)d_results, paired ? (const snapgpu_paired_result *)d_results : nullptr, \
-                                          d_front, d_clippedLens, s->d_slots, s->slotBytes, s->d_recordBytes, s->format == SNAPGPU_FORMAT_BAM, s->d_rgAuxBam, s->rgAuxBamLen)
+                                          d_front, d_clippedLens, s->d_slots, s->slotBytes, s->d_recordBytes, s->format == SNAPGPU_FORMAT_BAM, s->d_rgAuxBam, s->rgAuxBamLen, \
+                                          s->d_sortLocations, s->d_sortBytes)
     if (s->ctasPerSM == 8) SG_SAM_LAUNCH(8); else if (s->ctasPerSM == 6) SG_SAM_LAUNCH(6); else if (s->ctasPerSM == 4) SG_SAM_LAUNCH(4);
     else if (s->ctasPerSM == 3) SG_SAM_LAUNCH(3); else SG_SAM_LAUNCH(2);
 #undef SG_SAM_LAUNCH
     SG_CUDA(cudaGetLastError());
+    s->lastRecords = nReads; s->lastUnits = nUnits; s->lastPaired = paired;
     size_t cb = s->cubBytes;
     SG_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, cb, s->d_recordBytes, s->d_recordOffsets, (int)nUnits, st));
     long long warps = nUnits < 148LL * 64 ? nUnits : 148LL * 64;
@@ -2288,6 +2320,90 @@ int snapgpu_sam_format_paired_device(snapgpu_sam *s, int64_t nReads, uint32_t ma
                              (const unsigned long long *)d_idOffsets, d_idLens, d_frontClipped, d_clippedLens, d_results, d_text, textCapacity, textBytes,
                              cudaStream ? (cudaStream_t)cudaStream : s->stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Row N4, first piece: SortedDataFilter on the device.  The reference's sorting writer keeps, for every record, the key of the
+// location SimpleReadWriter filed it under -- (original contig number, 1-based position in the contig), (0, 0) for location 0, (-1, 0) for
+// an unaligned record, -1 comparing as unsigned, i.e. last (SortedDataFilter::onAdvance, SortedDataWriter.cpp:905-939) -- stable-sorts each write batch by it and copies the
+// records out in that order (onNextBatch, :942-1010) as one sorted run of its later merge.  Here: keys from the locations the formatter
+// kernel left, one stable radix sort of (key, record index), a scan of the permuted lengths, one warp per record to move the bytes.  A batch
+// is whatever was formatted last; with HBM to hold the whole output that is the whole run and no merge is left to do.
+// ------------------------------------------------------------------------------------------------
+__global__ void sg_sort_keys_kernel(SgIndexView ix, const int32_t *contigOriginal, long long nRecords, int paired, const long long *sortLocations, const uint32_t *sortBytes,
+                                    const unsigned long long *unitOffsets, unsigned long long *keys, uint32_t *perm, unsigned long long *recOffsets)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRecords) return;
+    const long long loc = sortLocations[r];
+    unsigned long long key;
+    if (loc == SG_SORT_UNALIGNED) key = 0xffffffffULL << 32;                               // contig -1 (compared UNSIGNED, Genome.h:156-182: after every contig), pos 0
+    else if (loc == 0) key = 0;                                                             // contig 0, pos 0 (onAdvance's special case)
+    else {
+        const int c = sg_contig_at(ix, loc);
+        key = ((unsigned long long)(uint32_t)contigOriginal[c] << 32) | (uint32_t)(loc - ix.contigStart[c] + 1);
+    }
+    keys[r] = key;
+    perm[r] = (uint32_t)r;
+    recOffsets[r] = paired ? unitOffsets[r >> 1] + ((r & 1) ? sortBytes[r - 1] : 0u) : unitOffsets[r];
+}
+
+__global__ void sg_sort_gather_bytes_kernel(long long nRecords, const uint32_t *perm, const uint32_t *sortBytes, uint32_t *sortedBytes)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nRecords) sortedBytes[r] = sortBytes[perm[r]];
+}
+
+__global__ void sg_sort_move_kernel(long long nRecords, const uint32_t *perm, const uint32_t *sortedBytes, const unsigned long long *sortedOffsets,
+                                    const unsigned long long *recOffsets, const char *text, char *sorted, unsigned long long capacity, int *overflow)
+{
+    const int lane = threadIdx.x & 31;
+    const long long nW = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nRecords; r += nW) {
+        const uint32_t n = sortedBytes[r];
+        const unsigned long long to = sortedOffsets[r], from = recOffsets[perm[r]];
+        if (to + n > capacity) { if (lane == 0) atomicMax(overflow, 2); continue; }
+        for (uint32_t k = lane; k < n; k += 32) sorted[to + k] = text[from + k];
+    }
+}
+
+int snapgpu_sam_sort_device(snapgpu_sam *s, const char *d_text, char *d_sorted, int64_t sortedCapacity, int64_t *sortedBytes, uint64_t *d_keysOut,
+                            uint64_t *d_offsetsOut, void *cudaStream)
+{
+    if (!s || !d_sorted || !sortedBytes) return sg_fail("null argument");
+    if (!d_text) d_text = s->d_text;             // the handle's own buffer: where a host-buffer format call left the records on the device
+    if (!d_text) return sg_fail("snapgpu_sam_sort_device: nothing formatted yet");
+    *sortedBytes = 0;
+    const long long n = s->lastRecords;
+    if (n == 0) return 0;
+    SG_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : s->stream;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    SG_CUDA(cudaMemsetAsync(s->d_overflow, 0, sizeof(int), st));
+    sg_sort_keys_kernel<<<blocks, 256, 0, st>>>(s->index->view, s->d_contigOriginal, n, s->lastPaired, s->d_sortLocations, s->d_sortBytes, s->d_recordOffsets,
+                                                s->d_sortKeys, s->d_perm, s->d_recOffsets);
+    SG_CUDA(cudaGetLastError());
+    size_t cb = s->cubBytes;
+    SG_CUDA(cub::DeviceRadixSort::SortPairs(s->d_cub, cb, s->d_sortKeys, s->d_sortKeysOut, s->d_perm, s->d_permOut, (int)n, 0, 64, st));      // (LSD radix sort: stable)
+    sg_sort_gather_bytes_kernel<<<blocks, 256, 0, st>>>(n, s->d_permOut, s->d_sortBytes, s->d_sortedBytes);
+    SG_CUDA(cudaGetLastError());
+    cb = s->cubBytes;
+    SG_CUDA(cub::DeviceScan::ExclusiveSum(s->d_cub, cb, s->d_sortedBytes, s->d_sortedOffsets, (int)n, st));
+    const long long warps = n < 148LL * 64 ? n : 148LL * 64;
+    sg_sort_move_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(n, s->d_permOut, s->d_sortedBytes, s->d_sortedOffsets, s->d_recOffsets, d_text, d_sorted,
+                                                                             (unsigned long long)sortedCapacity, s->d_overflow);
+    SG_CUDA(cudaGetLastError());
+    if (d_keysOut) SG_CUDA(cudaMemcpyAsync(d_keysOut, s->d_sortKeysOut, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_offsetsOut) SG_CUDA(cudaMemcpyAsync(d_offsetsOut, s->d_sortedOffsets, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[0], s->d_sortedOffsets + (n - 1), 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[1], s->d_sortedBytes + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[2], s->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    if ((int)(s->h_meta[2] & 0xffffffffu) != 0) return sg_fail("snapgpu_sam_sort_device: sorted buffer too small");
+    *sortedBytes = (int64_t)(s->h_meta[0] + (s->h_meta[1] & 0xffffffffu));
+    return 0;
+}
+
+int64_t snapgpu_sam_last_record_count(const snapgpu_sam *s) { return s ? s->lastRecords : 0; }
 
 struct snapgpu_fastq {
     int device = 0;

@@ -85,10 +85,10 @@ EXPORTS = [
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
-    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
-ABI_VERSION = 3          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
+ABI_VERSION = 4          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
 _lib = None
 
 
@@ -143,6 +143,9 @@ def lib():
         L.snapgpu_sam_format_paired_device.argtypes = L.snapgpu_sam_format_single_device.argtypes
         L.snapgpu_sam_set_format.argtypes = [C.c_void_p, C.c_int]
         L.snapgpu_bgzf_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.snapgpu_sam_sort_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_sam_last_record_count.restype = C.c_int64
+        L.snapgpu_sam_last_record_count.argtypes = [C.c_void_p]
         L.snapgpu_fastq_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.snapgpu_fastq_parse_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_aligner_launch_count.restype = C.c_int64
@@ -414,6 +417,17 @@ class SamFormatter:
                   C.c_void_p(d_id_offsets), C.c_void_p(d_id_lens), C.c_void_p(d_front), C.c_void_p(d_clipped_lens), C.c_void_p(d_results), C.c_void_p(d_text),
                   text_capacity, C.byref(used), C.c_void_p(stream)))
         return used.value
+
+    def sort_device(self, d_text, d_sorted, sorted_capacity, d_keys_out=0, d_offsets_out=0, stream=0) -> int:
+        """Coordinate-sorts the records the last format_device call left in d_text into d_sorted (device pointers as ints); returns the bytes
+        written (snapgpu_sam_sort_device: SortedDataFilter's per-batch stable sort, on the device)."""
+        used = C.c_int64(0)
+        _check(lib().snapgpu_sam_sort_device(self.handle, C.c_void_p(d_text), C.c_void_p(d_sorted), sorted_capacity, C.byref(used), C.c_void_p(d_keys_out),
+                                             C.c_void_p(d_offsets_out), C.c_void_p(stream)))
+        return used.value
+
+    def last_record_count(self) -> int:
+        return int(lib().snapgpu_sam_last_record_count(self.handle))
 
     def format(self, batch, ids, results, paired: bool = False, front_clipped=None, clipped_lens=None) -> bytes:
         """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one

@@ -861,3 +861,79 @@ def test_sam_records_of_quality_clipped_reads_from_the_device(engine, gidx, smal
     assert len(want) == len(got) == full.n
     bad = [i for i in range(full.n) if want[i] != got[i]]
     assert bad == [], (len(bad), want[bad[0]], got[bad[0]])
+
+
+def _sorted_on_device(engine, fmt, n_records, cap):
+    import torch
+    dev = torch.device("cuda", 0)
+    d_sorted = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    d_keys = torch.empty((n_records,), dtype=torch.int64, device=dev)
+    d_offs = torch.empty((n_records,), dtype=torch.int64, device=dev)
+    used = fmt.sort_device(0, d_sorted.data_ptr(), cap, d_keys.data_ptr(), d_offs.data_ptr())
+    keys = d_keys.cpu().numpy().view(np.uint64)
+    offs = d_offs.cpu().numpy()
+    return d_sorted[:used].cpu().numpy().tobytes(), keys, offs
+
+
+def test_records_sorted_on_the_device_equal_reference_sorted_output(engine, gidx, small_cfg, reflib, tmp_path):
+    """Row N4, the sort (snapgpu_sam_sort_device = SortedDataFilter's stable sort of a write batch, SortedDataWriter.cpp:905-1010): the records of
+    `snap-aligner single ... -so -S d -o sorted.sam -t 1` (one write batch, so its merge has one run), in the file's order -- unaligned
+    records last, equal keys in input order.  Then the same with BAM records against the sorted .bam."""
+    rb = small_cfg.reads["noisy150"]            # 212 of 1500 reads stay unaligned
+    fq = str(tmp_path / "r.fq"); out = str(tmp_path / "sorted.sam")
+    rb.write_fastq(fq)
+    want = _reference_sam_lines(reflib, ["single", small_cfg.idx, fq, "-o", out, "-t", "1", "-d", "14", "-so", "-S", "d"])
+    p = engine.default_params(maxDist=14)
+    al = engine.SingleAligner(gidx, p, 2048)
+    res, _ = al.align(rb)
+    al.close()
+    ids = [b"r%d" % i for i in range(rb.n)]
+    fmt = engine.SamFormatter(gidx, p, 2048)
+    unsorted = [l for l in fmt.format(rb, ids, res).split(b"\n") if l]
+    assert fmt.last_record_count() == rb.n
+    blob, keys, offs = _sorted_on_device(engine, fmt, rb.n, rb.n * 1024)
+    got = [l for l in blob.split(b"\n") if l]
+    assert sorted(got) == sorted(unsorted) and got != unsorted
+    assert len(want) == len(got) == rb.n
+    bad = [i for i in range(rb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]][:120], got[bad[0]][:120])
+    assert (np.diff(keys.astype(np.float64)) >= 0).all() and (keys >> np.uint64(32) == np.uint64(0xffffffff)).sum() == sum(1 for l in got if l.split(b"\t")[2] == b"*")
+    assert offs[0] == 0 and all(blob[o - 1:o] == b"\n" for o in offs[1:])
+    # BAM records of the same batch against the reference's sorted BAM
+    outb = str(tmp_path / "sorted.bam")
+    wantb = _reference_bam_records(reflib, ["single", small_cfg.idx, fq, "-o", outb, "-t", "1", "-d", "14", "-so", "-S", "di"], outb)
+    fmt.set_format(bam=True)
+    fmt.format(rb, ids, res)
+    blob, keys, offs = _sorted_on_device(engine, fmt, rb.n, rb.n * 1024)
+    fmt.close()
+    gotb = _split_bam(blob)
+    assert len(wantb) == len(gotb) == rb.n
+    bad = [i for i in range(rb.n) if wantb[i] != gotb[i]]
+    assert bad == [], (len(bad), wantb[bad[0]][:60], gotb[bad[0]][:60])
+
+
+def test_pair_records_sorted_on_the_device_equal_reference_sorted_output(engine, gidx, small_cfg, reflib, tmp_path):
+    """The same for pairs: every record is filed under its own final location, an unaligned end under its mate's (ReadWriter.cpp:601-606)."""
+    pb = small_cfg.pairs["std150"]               # chimeric mates, unaligned ends
+    f1 = str(tmp_path / "p1.fq"); f2 = str(tmp_path / "p2.fq"); out = str(tmp_path / "sorted.sam")
+    ids = []
+    with open(f1, "wb") as a, open(f2, "wb") as b:
+        for i in range(pb.n // 2):
+            x, q = pb.read(2 * i); a.write(b"@p%d/1\n%s\n+\n%s\n" % (i, x, q))
+            x, q = pb.read(2 * i + 1); b.write(b"@p%d/2\n%s\n+\n%s\n" % (i, x, q))
+            ids += [b"p%d/1" % i, b"p%d/2" % i]
+    want = _reference_sam_lines(reflib, ["paired", small_cfg.idx, f1, f2, "-o", out, "-t", "1", "-so", "-S", "d"])
+    p, pp = engine.default_params(maxDist=27, numSeedsFromCommandLine=8), engine.default_paired_params()
+    al = engine.PairedAligner(gidx, p, pp, 2048)
+    res, _ = al.align(pb)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096)
+    unsorted = [l for l in fmt.format(pb, ids, res, paired=True).split(b"\n") if l]
+    assert fmt.last_record_count() == pb.n
+    blob, keys, offs = _sorted_on_device(engine, fmt, pb.n, pb.n * 1024)
+    fmt.close()
+    got = [l for l in blob.split(b"\n") if l]
+    assert sorted(got) == sorted(unsorted)
+    assert len(want) == len(got) == pb.n
+    bad = [i for i in range(pb.n) if want[i] != got[i]]
+    assert bad == [], (len(bad), want[bad[0]][:120], got[bad[0]][:120])
