@@ -103,6 +103,13 @@ struct snapgpu_aligner {
     unsigned long long *d_next = nullptr;
     cudaStream_t stream = nullptr;       // compute stream (all kernels of this aligner are serialised on it: they share the arenas)
     cudaStream_t streamIn = nullptr, streamOut = nullptr;   // H2D / D2H copy streams of the host-buffer path
+    // overlapped two-pass launch (single-end): the second pass runs on stream2 while the first still produces its list
+    bool overlap = false;
+    int overlapPass1Blocks = 2;          // CTAs per SM of the first pass while the two run together (its 32-register build)
+    int64_t overlapMinReads = 0;         // smaller batches take the sequential two-pass form (three launches and a list fill do not pay)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    unsigned int *d_producersDone = nullptr;
     int64_t maxBatchReads = 0;
     int64_t chunkReads = 0;              // reads per pipeline stage of snapgpu_align_single
     size_t chunkBases = 0;
@@ -218,15 +225,44 @@ sg_lookup_bucket_kernel(const __grid_constant__ SgIndexView ix, const uint8_t *s
 //   MODE 1 is an instantiation without the affine-gap code: it finishes the reads that never need it and appends the others,
 //   at the moment they first would, to deferList.  MODE 2 (full code) then aligns deferList[0, *deferCount) from scratch.
 //   Results are those of MODE 0 by construction (a deferred read's partial work is discarded, counters included).
+#define SG_DEFER_EMPTY 0xffffffffu
+#define SG_OVERLAP_STARVE_NS 2000000ULL
 template <int MB, int MODE>
 __global__ void __launch_bounds__(256, MB)
 sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_constant__ SgParams prParam, const SgTables *tb, uint8_t *scratchBase,
                 size_t scratchBytesPerWorker, long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
-                snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next, unsigned long long *deferCount, uint32_t *deferList)
+                snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next, unsigned long long *deferCount, uint32_t *deferList,
+                unsigned int *producersDone, unsigned int producerCtas, unsigned int workerBase)
 {
-    if (MODE == 2) n = (long long)*deferCount;
+    // Overlapped form (producerCtas != 0): the two passes run at the same time on disjoint arenas.  The first pass publishes every
+    // deferred read by writing its index into a list pre-filled with SG_DEFER_EMPTY, and each of its CTAs counts itself in
+    // *producersDone on exit; a warp of the second pass takes the next list position and polls it until it holds an index or every
+    // producer CTA has left (then an empty position means the list ends before it).
+    // producersDone[1] counts producer CTAs that have STARTED.  A consumer CTA that finds none after SG_OVERLAP_STARVE_NS leaves without
+    // having taken a list position: if consumers ever filled the machine before a single producer CTA was placed, waiting would never end;
+    // the consumer launch that follows the producers in stream order finishes whatever such CTAs left.
+    const bool overlapped = producerCtas != 0;
+    if (MODE == 1 && overlapped && threadIdx.x == 0) atomicAdd(producersDone + 1, 1u);
+    if (MODE == 2 && overlapped) {
+        __shared__ int sGiveUp;
+        if (threadIdx.x == 0) {
+            int giveUp = 0;
+            unsigned long long t0 = 0, t1 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (((const volatile unsigned int *)producersDone)[1] == 0u && ((const volatile unsigned int *)producersDone)[0] < producerCtas) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > SG_OVERLAP_STARVE_NS) { giveUp = 1; break; }
+                __nanosleep(1000);
+            }
+            sGiveUp = giveUp;
+            if (giveUp) atomicAdd(producersDone + 2, 1u);
+        }
+        __syncthreads();
+        if (sGiveUp) return;
+    }
+    if (MODE == 2 && !overlapped) n = (long long)*deferCount;
     const int lane = threadIdx.x & 31;
-    const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long worker = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) + workerBase;
 
     // The aligner state is the same in all 32 lanes of a warp (they run the state machine uniformly), so it lives ONCE per warp in
     // shared memory rather than 32 times in local memory: as per-thread stack it was 95 % of the kernel's L2 traffic and, with
@@ -265,8 +301,30 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
         unsigned long long i = 0;
         if (lane == 0) i = atomicAdd(next, 1ULL);
         i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= (unsigned long long)n) break;
-        if (MODE == 2) i = deferList[i];
+        if (MODE == 2 && overlapped) {
+            if (i >= (unsigned long long)n) break;           // (n = the batch size here: the list cannot be longer)
+            // every lane polls (one broadcast transaction per load): the loop is warp-uniform, so the warp stays converged -- the state machine
+            // below updates its per-warp state from all lanes at once and must never run as two groups of lanes
+            unsigned int v;
+            {
+                const volatile uint32_t *slot = deferList + i;
+                for (;;) {
+                    v = *slot;
+                    v = __shfl_sync(0xffffffffu, v, 0);
+                    if (v != SG_DEFER_EMPTY) break;
+                    unsigned int done = *(const volatile unsigned int *)producersDone;
+                    done = __shfl_sync(0xffffffffu, done, 0);
+                    if (done >= producerCtas) { __threadfence(); v = *slot; v = __shfl_sync(0xffffffffu, v, 0); break; }
+                    __nanosleep(500);
+                }
+            }
+            __syncwarp();
+            if (v == SG_DEFER_EMPTY) break;
+            i = v;
+        } else {
+            if (i >= (unsigned long long)n) break;
+            if (MODE == 2) i = deferList[i];
+        }
         const uint8_t *rd = bases + offsets[i];
         const uint8_t *rq = quals + offsets[i];
         const uint32_t len = lens[i];
@@ -314,6 +372,11 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
     }
     // leave the scratch lookup table clean for the next launch
     A.clearCandidates();
+    if (MODE == 1 && overlapped) {
+        __threadfence();                 // this warp's list entries before its CTA's count
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(producersDone, 1u);
+    }
     if (counters && lane == 0) {
         atomicAdd((unsigned long long *)&counters->totalReads, cTotal);
         atomicAdd((unsigned long long *)&counters->uselessReads, cUseless);
@@ -1442,7 +1505,27 @@ int snapgpu_aligner_create(const snapgpu_index *idx, const snapgpu_params *param
     a->twoPass = !a->params.noEditDistance;
     if (const char *e = getenv("SNAPGPU_TWO_PASS")) a->twoPass = atoi(e) != 0;
     if (a->twoPass) {
-        if (cudaMalloc((void **)&a->d_retryList, (size_t)maxBatchReads * 4) != cudaSuccess ||
+        // overlapped launch (SNAPGPU_OVERLAP=1; off by default): needs arenas for both passes at once.  Measured on `snap single -d 14`, 1 M reads vs
+        // 3 Gbp (profiles/r02_overlap_two_pass.txt): 109 / 87 / 78 ms per step with 2 / 3 / 4 first-pass CTAs per SM beside the second pass,
+        // against 58 ms for the two passes one after the other -- with both kernels' code resident on an SM the first pass alone takes
+        // 36-85 ms instead of 15: instruction supply again, the reason the passes were split in the first place.
+        a->overlap = false;
+        if (const char *e = getenv("SNAPGPU_OVERLAP")) a->overlap = atoi(e) != 0;
+        a->overlapMinReads = 4LL * a->numSMs * a->warpsPerBlock;
+        if (const char *e = getenv("SNAPGPU_OVERLAP_MIN_READS")) a->overlapMinReads = atoll(e);
+        if (const char *e = getenv("SNAPGPU_OVERLAP_PASS1_BLOCKS")) { const int v = atoi(e); if (v >= 1 && v <= 4) a->overlapPass1Blocks = v; }
+        if (a->blocksPerSM != 4 || a->nWorkers < a->numSMs * 8 * a->warpsPerBlock) a->overlap = false;
+        if (a->overlap) {
+            // both kernels ask for the same shared-memory carve-out (room for 2 + 3 or for 4 CTAs of 27 KB), so that CTAs of either fit on an SM
+            // the other configured first
+            int carve = 72;
+            if (const char *e = getenv("SNAPGPU_OVERLAP_CARVEOUT")) carve = atoi(e);
+            cudaFuncSetAttribute(sg_align_kernel<8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(sg_align_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
+        if (cudaMalloc((void **)&a->d_retryList, (size_t)maxBatchReads * 4) != cudaSuccess || cudaMalloc((void **)&a->d_producersDone, 16) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&a->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a->evFork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&a->evJoin, cudaEventDisableTiming) != cudaSuccess ||
             cudaMalloc((void **)&a->d_retryCount, 8) != cudaSuccess || cudaMalloc((void **)&a->d_next2, 8) != cudaSuccess) {
             std::string msg = std::string("snapgpu_aligner_create: deferred-read list: ") + cudaGetErrorString(cudaGetLastError());
             snapgpu_aligner_destroy(a);
@@ -1539,7 +1622,10 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
     if (a->streamIn) cudaStreamDestroy(a->streamIn);
     if (a->streamOut) cudaStreamDestroy(a->streamOut);
     cudaFree(a->d_scratch); cudaFree(a->d_next); cudaFree(a->d_error);
-    cudaFree(a->d_bigScratch); cudaFree(a->d_retryList); cudaFree(a->d_retryCount); cudaFree(a->d_next2);
+    cudaFree(a->d_bigScratch); cudaFree(a->d_retryList); cudaFree(a->d_retryCount); cudaFree(a->d_next2); cudaFree(a->d_producersDone);
+    if (a->stream2) cudaStreamDestroy(a->stream2);
+    if (a->evFork) cudaEventDestroy(a->evFork);
+    if (a->evJoin) cudaEventDestroy(a->evJoin);
     cudaFree(a->d_handoff); cudaFree(a->d_candPool); cudaFree(a->d_candPoolUsed); cudaFree(a->d_next3);
     for (int k = 0; k < 2; k++) {
         snapgpu_aligner::Slot &sl = a->slot[k];
@@ -1566,10 +1652,58 @@ static int launch_align(snapgpu_aligner *a, int64_t n, const char *d_bases, cons
     if (!a->paired) {
 #define SG_LAUNCH(MB, MODE, GRID, NEXT) sg_align_kernel<MB, MODE><<<GRID, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, \
         a->d_scratch, a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, \
-        d_lens, (snapgpu_single_result *)d_results, d_counters, NEXT, a->d_retryCount, a->d_retryList)
+        d_lens, (snapgpu_single_result *)d_results, d_counters, NEXT, a->d_retryCount, a->d_retryList, a->d_producersDone, 0u, 0u)
 #define SG_LAUNCH_MB(MODE, GRID, NEXT) if (a->blocksPerSM >= 4) SG_LAUNCH(4, MODE, GRID, NEXT); else if (a->blocksPerSM == 3) SG_LAUNCH(3, MODE, GRID, NEXT); \
         else SG_LAUNCH(2, MODE, GRID, NEXT)      /* second pass measured the same at 4, 5 and 6 CTAs/SM (17.2 M reads/s) */
-        if (a->twoPass) {
+        if (a->twoPass && a->overlap && n >= a->overlapMinReads) {
+            // Overlapped form: both passes resident at once.  The first pass (latency-bound, a third of the issue slots used) runs its
+            // 32-register build at overlapPass1Blocks (2) CTAs per SM on the caller's stream; the second (affine gap, issue-bound) runs
+            // beside it on stream2 at 3 CTAs per SM -- 2 x 8 K + 3 x 16 K registers = the SM's file, so neither launch can keep the other
+            // off the machine whichever is placed first -- and consumes the deferred-read list while it is being produced (see
+            // sg_align_kernel); more CTAs of the second pass follow the first pass on the caller's stream and take over the registers it
+            // leaves.  Arenas: first pass workers [0, g1*8), then the second pass's two launches.
+            const int k2a = (64 - 8 * a->overlapPass1Blocks) / 16;          // 64-register CTAs that fit beside the first pass's 32-register ones
+            const int g1 = a->numSMs * a->overlapPass1Blocks, g2a = a->numSMs * k2a, g2b = a->numSMs * (8 - a->overlapPass1Blocks - k2a > 4 ? 4 : 8 - a->overlapPass1Blocks - k2a);
+            static const int dbg = getenv("SNAPGPU_OVERLAP_DEBUG") ? atoi(getenv("SNAPGPU_OVERLAP_DEBUG")) : 0;
+            cudaEvent_t dbgEv[4] = {nullptr, nullptr, nullptr, nullptr};
+            if (dbg) for (int k = 0; k < 4; k++) cudaEventCreate(&dbgEv[k]);
+            SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));
+            SG_CUDA(cudaMemsetAsync(a->d_next2, 0, 8, st));
+            SG_CUDA(cudaMemsetAsync(a->d_producersDone, 0, 16, st));
+            SG_CUDA(cudaMemsetAsync(a->d_retryList, 0xff, (size_t)n * 4, st));
+            SG_CUDA(cudaEventRecord(a->evFork, st));
+            SG_CUDA(cudaStreamWaitEvent(a->stream2, a->evFork, 0));
+#define SG_LAUNCH_OV(MB, MODE, GRID, STREAM, NEXT, BASE) sg_align_kernel<MB, MODE><<<GRID, a->warpsPerBlock * 32, 0, STREAM>>>(a->index->view, a->params, \
+                a->index->d_tables_prob, a->d_scratch, a->scratchBytesPerWorker, n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, \
+                (const unsigned long long *)d_offsets, d_lens, (snapgpu_single_result *)d_results, d_counters, NEXT, a->d_retryCount, a->d_retryList, \
+                a->d_producersDone, (unsigned)g1, (unsigned)(BASE))
+            if (dbg) cudaEventRecord(dbgEv[0], st);
+            SG_LAUNCH_OV(8, 1, g1, st, a->d_next, 0);
+            if (dbg) cudaEventRecord(dbgEv[1], st);
+            SG_CUDA(cudaGetLastError());
+            a->launches++;
+            SG_LAUNCH_OV(4, 2, g2a, a->stream2, a->d_next2, g1 * a->warpsPerBlock);
+            SG_CUDA(cudaGetLastError());
+            a->launches++;
+            // behind the first pass in stream order: one of its CTAs per SM fits beside the second pass's three as soon as the first pass
+            // has left; the other two only find room if CTAs of the launch above gave up (see sg_align_kernel), and then do their work
+            SG_LAUNCH_OV(4, 2, g2b, st, a->d_next2, (g1 + g2a) * a->warpsPerBlock);
+#undef SG_LAUNCH_OV
+            SG_CUDA(cudaGetLastError());
+            if (dbg) cudaEventRecord(dbgEv[2], st);
+            SG_CUDA(cudaEventRecord(a->evJoin, a->stream2));
+            SG_CUDA(cudaStreamWaitEvent(st, a->evJoin, 0));
+            if (dbg) {
+                cudaEventRecord(dbgEv[3], st);
+                cudaStreamSynchronize(st);
+                float t1 = 0, t2 = 0, t3 = 0; unsigned int c[4] = {0, 0, 0, 0}; unsigned long long deferred = 0;
+                cudaEventElapsedTime(&t1, dbgEv[0], dbgEv[1]); cudaEventElapsedTime(&t2, dbgEv[0], dbgEv[2]); cudaEventElapsedTime(&t3, dbgEv[0], dbgEv[3]);
+                cudaMemcpy(c, a->d_producersDone, 16, cudaMemcpyDeviceToHost); cudaMemcpy(&deferred, a->d_retryCount, 8, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[overlap] n=%lld p1=%d k2a=%d k2b=%d: first pass %.2f ms, + follow-up consumers %.2f ms, all %.2f ms; producers done %u started %u, consumer CTAs that gave up %u, deferred %llu\n",
+                        (long long)n, a->overlapPass1Blocks, k2a, g2b / a->numSMs, t1, t2, t3, c[0], c[1], c[2], deferred);
+                for (int k = 0; k < 4; k++) cudaEventDestroy(dbgEv[k]);
+            }
+        } else if (a->twoPass) {
             SG_CUDA(cudaMemsetAsync(a->d_retryCount, 0, 8, st));
             SG_CUDA(cudaMemsetAsync(a->d_next2, 0, 8, st));
             int64_t w1 = (int64_t)a->numSMs * a->pass1BlocksPerSM * a->warpsPerBlock;

@@ -517,8 +517,11 @@ def test_single_launch_forms_agree(engine, gidx, small_cfg, reflib, monkeypatch,
     rb = small_cfg.reads["noisy150"]
     want, wctr = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), reflib.default_params(**OPTION_SETS[opt])).align(rb)
     out = {}
-    for form in ("1", "0"):
-        monkeypatch.setenv("SNAPGPU_TWO_PASS", form)
+    monkeypatch.setenv("SNAPGPU_OVERLAP_MIN_READS", "1")
+    # "ov": the overlapped form of the two-pass launch (both passes resident at once, the second consuming the first's list as it grows)
+    for form, two_pass, overlap in (("ov", "1", "1"), ("1", "1", "0"), ("0", "0", "0")):
+        monkeypatch.setenv("SNAPGPU_TWO_PASS", two_pass)
+        monkeypatch.setenv("SNAPGPU_OVERLAP", overlap)
         al = engine.SingleAligner(gidx, p, 4096)
         got, ctr = al.align(rb)
         out[form] = (got, ctr, al.launch_count())
@@ -528,7 +531,9 @@ def test_single_launch_forms_agree(engine, gidx, small_cfg, reflib, monkeypatch,
             assert wctr[k] == ctr[k], (opt, form, k)
     for k in _CTR_KEYS:
         assert out["1"][1][k] == out["0"][1][k], (opt, k)
+        assert out["ov"][1][k] == out["0"][1][k], (opt, k)
     assert out["0"][2] == 1 and out["1"][2] == 2
+    assert out["ov"][2] == 3      # first pass, second pass beside it, the second pass's fourth CTA per SM behind the first
 
 
 @pytest.mark.parametrize("opt", ["default_d27", "hc_d14", "hc_noag", "hc_forcespacing"])
