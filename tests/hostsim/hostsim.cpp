@@ -18,6 +18,7 @@
 #include "../../snap_b200/csrc/sg_ag_cigar.h"
 #include "../../snap_b200/csrc/sg_sam.h"
 #include "../../snap_b200/csrc/sg_bam.h"
+#include "../../snap_b200/csrc/sg_bampost.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -630,6 +631,110 @@ int64_t hs_bam_single_batch(void *vix, const int *agParams, int useM, int useAff
         used += sg_bam_write_single(C, B, R, sr, (uint8_t *)out + used);
     }
     return used;
+}
+
+// ---- row N4 after the sort: duplicate marking and the .bai of a coordinate-sorted stream of BAM records (sg_bampost.h), host orchestration ----
+static bool split_records(const uint8_t *records, int64_t nBytes, std::vector<unsigned long long> &off)
+{
+    int64_t p = 0;
+    while (p + 4 <= nBytes) { off.push_back((unsigned long long)p); SgBamRec r; r.p = records + p; if (r.size() < 36) return false; p += r.size(); }
+    return p == nBytes;
+}
+
+// BAMDupMarkFilter over the whole stream as one batch: sets FLAG 0x400 in place, returns the number of records it set it on (-1: malformed stream)
+int64_t hs_bam_markdup(uint8_t *records, int64_t nBytes, const int64_t *contigStartByOriginal, int32_t nRef)
+{
+    std::vector<unsigned long long> off;
+    if (!split_records(records, nBytes, off)) return -1;
+    const long long n = (long long)off.size();
+    std::vector<SgDupFields> f((size_t)n);
+    for (long long i = 0; i < n; i++) { SgBamRec r; r.p = records + off[i]; sg_dup_fields(r, contigStartByOriginal, nRef, &f[i]); }
+    // the runs actually visited (the device marks this orbit by pointer jumping)
+    std::vector<long long> rs, re;
+    for (long long s = 0; s < n;) {
+        if (f[s].logical == SG_DUP_INVALID_LOCATION) { s++; continue; }
+        const long long e = sg_dup_first_beyond(f.data(), n, s, 2 * SG_DUP_RUN_REACH);
+        rs.push_back(s); re.push_back(e);
+        if (e == n) break;
+        s = sg_dup_first_beyond(f.data(), n, s, SG_DUP_RUN_REACH);
+    }
+    SgDupView V; V.n = n; V.records = records; V.offsets = off.data(); V.f = f.data(); V.nRuns = (long long)rs.size(); V.runStart = rs.data(); V.runEnd = re.data();
+    std::vector<int32_t> flagRun((size_t)n, -1);
+    std::vector<uint8_t> fragFlag((size_t)n, 0);
+    // pair keys
+    {
+        std::vector<uint32_t> idx;
+        for (long long i = 0; i < n; i++) if (f[i].flag & SG_BAM_FLAG_PAIRED) idx.push_back((uint32_t)i);
+        auto lo = [&](uint32_t i) { return std::min(f[i].info, f[i].mateInfo); };
+        auto hi = [&](uint32_t i) { return std::max(f[i].info, f[i].mateInfo); };
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+            if (f[a].lib != f[b].lib) return f[a].lib < f[b].lib;
+            if (lo(a) != lo(b)) return lo(a) < lo(b);
+            return hi(a) < hi(b); });
+        for (size_t j = 0; j < idx.size();) {
+            size_t e = j + 1;
+            while (e < idx.size() && f[idx[e]].lib == f[idx[j]].lib && lo(idx[e]) == lo(idx[j]) && hi(idx[e]) == hi(idx[j])) e++;
+            sg_dup_walk_pair_key(V, idx.data() + j, (long long)(e - j), lo(idx[j]), hi(idx[j]), flagRun.data());
+            j = e;
+        }
+    }
+    // fragment keys
+    {
+        std::vector<uint32_t> idx((size_t)n);
+        for (long long i = 0; i < n; i++) idx[(size_t)i] = (uint32_t)i;
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return f[a].lib != f[b].lib ? f[a].lib < f[b].lib : f[a].info < f[b].info; });
+        for (size_t j = 0; j < idx.size();) {
+            size_t e = j + 1;
+            while (e < idx.size() && f[idx[e]].lib == f[idx[j]].lib && f[idx[e]].info == f[idx[j]].info) e++;
+            sg_dup_walk_fragment_key(V, idx.data() + j, (long long)(e - j), flagRun.data(), fragFlag.data());
+            j = e;
+        }
+    }
+    int64_t marked = 0;
+    for (long long i = 0; i < n; i++) {
+        if ((flagRun[i] >= 0 || fragFlag[i]) && !(f[i].flag & SG_BAM_FLAG_DUPLICATE)) {
+            const uint32_t fl = f[i].flag | SG_BAM_FLAG_DUPLICATE;
+            records[off[i] + 18] = (uint8_t)fl; records[off[i] + 19] = (uint8_t)(fl >> 8);
+            marked++;
+        }
+    }
+    return marked;
+}
+
+// The .bai of the file header ‖ records wrapped into BGZF members of 0xff00 payload bytes + the end-of-file member.  Returns its size (-1: malformed, -2: bai too small).
+int64_t hs_bam_index(const uint8_t *records, int64_t nBytes, int64_t headerBytes, int32_t nRef, uint8_t *bai, int64_t cap)
+{
+    std::vector<unsigned long long> off;
+    if (!split_records(records, nBytes, off)) return -1;
+    const long long n = (long long)off.size();
+    std::vector<SgBaiChunk> chunks;
+    std::vector<SgBaiRef> refs((size_t)nRef);
+    for (long long i = 0; i < n; i++) {
+        SgBamRec r; r.p = records + off[i];
+        const uint64_t at = (uint64_t)headerBytes + off[i];
+        SgBamRec prev; prev.p = i ? records + off[i - 1] : nullptr;
+        if (i == 0 || prev.refID() != r.refID() || prev.bin() != r.bin()) {
+            if (!chunks.empty()) chunks.back().end = at;
+            SgBaiChunk c; c.ref = r.refID(); c.bin = r.bin(); c.start = at; c.end = 0; chunks.push_back(c);
+        }
+        if (r.refID() >= 0 && r.refID() < nRef) {
+            SgBaiRef &R = refs[r.refID()];
+            if (!R.any) { R.any = true; R.firstStart = at; }
+            R.lastEnd = at + (uint64_t)r.size();
+            if (r.flag() & SG_BAM_FLAG_UNMAPPED) R.unmapped++;
+            else {
+                R.mapped++;
+                const int32_t slot = sg_bai_linear_slot(r);
+                if ((size_t)slot >= R.intervals.size()) { R.intervals.resize((size_t)slot, ~0ULL); R.intervals.push_back(at); }
+            }
+        }
+    }
+    const uint64_t total = (uint64_t)headerBytes + (uint64_t)nBytes;
+    if (!chunks.empty()) chunks.back().end = total;
+    std::vector<uint8_t> o = sg_bai_compose(nRef, chunks, refs, total);
+    if ((int64_t)o.size() > cap) return -2;
+    memcpy(bai, o.data(), o.size());
+    return (int64_t)o.size();
 }
 
 } // extern "C"
