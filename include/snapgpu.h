@@ -22,8 +22,8 @@
 extern "C" {
 #endif
 
-#define SNAPGPU_ABI_VERSION 4   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
-                                 * 4: snapgpu_sam_sort_device */
+#define SNAPGPU_ABI_VERSION 5   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
+                                 * 4: snapgpu_sam_sort_device; 5: snapgpu_bam_markdup_device, snapgpu_bam_index_device */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
@@ -402,11 +402,32 @@ int  snapgpu_bgzf_device(const char *d_in, int64_t nBytes, char *d_out, int64_t 
  * records moved by one warp each into d_sorted.  d_keysOut (optional, one uint64 per record, ascending: contig << 32 | position, contig 0xffffffff = unaligned) and
  * d_offsetsOut (optional, start of each sorted record) are what a merge of several runs, a BAM index or duplicate marking go on from; with
  * 180 GB of HBM a whole run's records can be ONE batch and no merge is left.  Synchronises `cudaStream` once.
- * Not on the device yet: the k-way merge of runs (SortedDataFilterSupplier::mergeSort), duplicate marking (BAMDupMarkFilter, Bam.cpp:2619)
- * and the .bai index (BAMIndexSupplier, Bam.cpp:3229). */
+ * Duplicate marking and the .bai index of the sorted stream: snapgpu_bam_markdup_device / snapgpu_bam_index_device below.  Not on the device: the k-way
+ * merge of several runs (SortedDataFilterSupplier::mergeSort) -- a whole run is one batch here. */
 int  snapgpu_sam_sort_device(snapgpu_sam *s, const char *d_text, char *d_sorted, int64_t sortedCapacity, int64_t *sortedBytes,
                              uint64_t *d_keysOut, uint64_t *d_offsetsOut, void *cudaStream);
 int64_t snapgpu_sam_last_record_count(const snapgpu_sam *s);       /* records (2 per pair) of the last format call */
+
+/* SURVEY 8(f) row N4, after the sort: what the reference's sorting BAM writer runs over the merged, coordinate-sorted record stream.
+ * d_records: BAM alignment records back to back in DEVICE memory (snapgpu_sam_sort_device's output in SNAPGPU_FORMAT_BAM, or any sorted stream),
+ * d_offsets[i]: where record i starts.
+ *
+ * snapgpu_bam_markdup_device = BAMDupMarkFilter (reference SNAPLib/Bam.cpp:2619-3121): sets FLAG 0x400 in place on every record the reference would set it
+ * on -- fragments and pairs with the same library, unclipped 5' end(s) and strand(s); the copy with the largest sum of base qualities >= 15 (plus the
+ * mate's QS tag for pairs) stays unmarked, ties go to the smaller tile / x / y of an Illumina read name, then to file order; a mapped pair beats a
+ * fragment -- including the reference's windowing of the stream into overlapping runs of 2 x (MAX_READ_LENGTH + MAX_K) bases.  Bit-identical to the
+ * reference for a stream it handles as one write batch.  On the device: the runs by pointer jumping, the records radix-sorted by key, one thread per key
+ * (snap_b200/csrc/sg_bampost.h).  *nMarked = records newly flagged.  Synchronises `cudaStream` once.
+ *
+ * snapgpu_bam_index_device = BAMIndexSupplier (Bam.cpp:3229-3440): the .bai of the FILE whose uncompressed content is `headerBytes` bytes of BAM header
+ * and reference table followed by these records, wrapped by snapgpu_bgzf_device as ONE stream (members of 0xff00 payload bytes) and closed with the
+ * standard 28-byte end-of-file member.  Same bins, chunks (one per maximal stretch of equal (refID, bin)), per-reference metadata (pseudo-bin 37450:
+ * file range, mapped / unmapped counts) and 16 Kbp linear index as the reference writes -- including its filing of a record under the window of its
+ * END and 0 for windows no record opened -- with this file's virtual offsets; bins in ascending order.  `bai` is HOST memory; recordBytes = total size
+ * of the records.  Synchronises `cudaStream`. */
+int  snapgpu_bam_markdup_device(snapgpu_sam *s, char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t *nMarked, void *cudaStream);
+int  snapgpu_bam_index_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
+                              char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream);
 
 /* Device-resident forms: every array, and the text buffer, is a DEVICE pointer -- the reads as parsed by snapgpu_fastq_parse_device, the
  * records as left by snapgpu_align_*_device -- so a batch goes from FASTQ text to SAM text without its reads or results visiting the

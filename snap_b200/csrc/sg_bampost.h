@@ -1,7 +1,7 @@
 // sg_bampost.h -- what the reference's sorting writer does to a coordinate-sorted stream of BAM records after the sort:
 // duplicate marking (BAMDupMarkFilter, reference SNAPLib/Bam.cpp:2619-3121) and the .bai index (BAMIndexSupplier, Bam.cpp:3229-3440).
 // Host + device: the per-record field extraction and the per-key walks below are what the CUDA kernels run (snapgpu.cu) and what the
-// CPU test suite runs against the files the reference binary writes (tests/hostsim).
+// CPU test suite runs, built for the host, against the files the reference binary writes.
 //
 // Duplicate marking, restated for a device.  The reference walks the sorted records ONCE, sequentially: it cuts them into overlapping
 // "runs" (a run starts at a record, takes every following record whose unclipped start lies within 2*(MAX_READ_LENGTH + MAX_K) of the
@@ -364,7 +364,6 @@ SG_HD uint64_t sg_bai_virtual_offset(uint64_t u, uint64_t totalBytes)
     return ((u / SG_BGZF_PAYLOAD_BYTES) * (SG_BGZF_PAYLOAD_BYTES + 31ULL)) << 16 | (u % SG_BGZF_PAYLOAD_BYTES);
 }
 
-#if !defined(__CUDA_ARCH__)
 // ---- host side of the .bai: the file itself (BAMIndexSupplier::onClosed, Bam.cpp:3341-3392).  Inputs in UNCOMPRESSED offsets of the stream header ‖ records;
 //      the chunks of a bin in stream order.  Bins are written in ascending order (the reference writes them in the iteration order of its hash map; readers do not care). ----
 #include <vector>
@@ -408,4 +407,3 @@ inline std::vector<uint8_t> sg_bai_compose(int32_t nRef, std::vector<SgBaiChunk>
     }
     return o;
 }
-#endif

@@ -25,6 +25,7 @@
 #include "sg_fastq.cuh"
 #include "sg_sam.h"
 #include "sg_bam.h"
+#include "sg_bampost.h"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -2136,6 +2137,10 @@ struct snapgpu_sam {
     int64_t lastRecords = 0, lastUnits = 0; int lastPaired = 0;
     unsigned long long *h_meta = nullptr;        // pinned: [0] last offset, [1] last length (low word), [2] overflow
     cudaStream_t stream = nullptr;
+    // row N4 after the sort (snapgpu_bam_markdup_device / snapgpu_bam_index_device): work arrays, grown on demand
+    void *d_post = nullptr; size_t postBytes = 0;
+    int64_t *d_contigStartByOriginal = nullptr;
+    std::vector<int64_t> h_contigStartByOriginal, h_contigSpan;
 };
 
 void snapgpu_sam_destroy(snapgpu_sam *s)
@@ -2147,7 +2152,7 @@ void snapgpu_sam_destroy(snapgpu_sam *s)
     cudaFree(s->d_results); cudaFree(s->d_offsets); cudaFree(s->d_idOffsets); cudaFree(s->d_lens); cudaFree(s->d_idLens); cudaFree(s->d_recordBytes); cudaFree(s->d_front); cudaFree(s->d_clippedLens); cudaFree(s->d_slots);
     cudaFree(s->d_recordOffsets); cudaFree(s->d_text); cudaFree(s->d_cub); cudaFree(s->d_overflow); cudaFreeHost(s->h_meta); cudaFree(s->d_rgAuxBam);
     cudaFree(s->d_sortLocations); cudaFree(s->d_sortBytes); cudaFree(s->d_contigOriginal); cudaFree(s->d_sortKeys); cudaFree(s->d_sortKeysOut); cudaFree(s->d_recOffsets);
-    cudaFree(s->d_sortedOffsets); cudaFree(s->d_perm); cudaFree(s->d_permOut); cudaFree(s->d_sortedBytes);
+    cudaFree(s->d_sortedOffsets); cudaFree(s->d_perm); cudaFree(s->d_permOut); cudaFree(s->d_sortedBytes); cudaFree(s->d_post); cudaFree(s->d_contigStartByOriginal);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -2211,6 +2216,19 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     SG_CUDA(cudaMemcpy(s->d_rgAux, rg, sizeof(rg), cudaMemcpyHostToDevice));
     if (idx->h_contigOriginal.size() != idx->h_contigStart.size()) { snapgpu_sam_destroy(s); return sg_fail("snapgpu_sam_create: index without original contig numbers"); }
     SG_CUDA(cudaMemcpy(s->d_contigOriginal, idx->h_contigOriginal.data(), idx->h_contigOriginal.size() * 4, cudaMemcpyHostToDevice));
+    {
+        // beginningLocation by ORIGINAL contig number (what a BAM record's refID is), and an upper bound of each contig's length
+        const size_t nc = idx->h_contigStart.size();
+        s->h_contigStartByOriginal.assign(nc, 0); s->h_contigSpan.assign(nc, 0);
+        for (size_t c = 0; c < nc; c++) {
+            const int32_t o = idx->h_contigOriginal[c];
+            if (o < 0 || (size_t)o >= nc) { snapgpu_sam_destroy(s); return sg_fail("snapgpu_sam_create: original contig numbers are not a permutation"); }
+            s->h_contigStartByOriginal[o] = idx->h_contigStart[c];
+            s->h_contigSpan[o] = (c + 1 < nc ? idx->h_contigStart[c + 1] : (int64_t)idx->view.nBases) - idx->h_contigStart[c];
+        }
+        SG_CUDA(cudaMalloc((void **)&s->d_contigStartByOriginal, nc * 8 + 8));
+        SG_CUDA(cudaMemcpy(s->d_contigStartByOriginal, s->h_contigStartByOriginal.data(), nc * 8, cudaMemcpyHostToDevice));
+    }
     // the same read group line as BAM tags (ReaderContext::defaultReadGroupAux for a BAM writer): the literal's terminating NUL ends the last tag
     static const char rgBam[] = "RGZFASTQ\0PLZIllumina\0PUZpu\0LBZlb\0SMZsm";
     s->rgAuxBamLen = (int)sizeof(rgBam);
@@ -2534,6 +2552,331 @@ int snapgpu_sam_sort_device(snapgpu_sam *s, const char *d_text, char *d_sorted, 
     SG_CUDA(cudaStreamSynchronize(st));
     if ((int)(s->h_meta[2] & 0xffffffffu) != 0) return sg_fail("snapgpu_sam_sort_device: sorted buffer too small");
     *sortedBytes = (int64_t)(s->h_meta[0] + (s->h_meta[1] & 0xffffffffu));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row N4 after the sort: duplicate marking and the BAM index of a coordinate-sorted stream of BAM records in HBM (sg_bampost.h has the semantics;
+// here: the data-parallel plumbing around them).
+// ------------------------------------------------------------------------------------------------
+extern "C++" {
+struct SgPostCarve {               // bump allocator over the handle's work buffer
+    uint8_t *base; size_t used, cap;
+    template <typename T> T *take(size_t n) { used = (used + 255) & ~(size_t)255; T *p = (T *)(base + used); used += n * sizeof(T); return p; }
+};
+}
+static int sam_post_reserve(snapgpu_sam *s, size_t bytes)
+{
+    if (bytes <= s->postBytes) return 0;
+    cudaFree(s->d_post); s->d_post = nullptr; s->postBytes = 0;
+    SG_CUDA(cudaMalloc(&s->d_post, bytes));
+    s->postBytes = bytes;
+    return 0;
+}
+
+__global__ void sg_dup_fields_kernel(const uint8_t *records, const unsigned long long *offsets, long long n, const int64_t *contigStartByOriginal, int32_t nRef,
+                                     SgDupFields *f, int32_t *flagRun, uint8_t *fragFlag, uint32_t *iota)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SgBamRec r; r.p = records + offsets[i];
+    sg_dup_fields(r, contigStartByOriginal, nRef, &f[i]);
+    flagRun[i] = -1; fragFlag[i] = 0; iota[i] = (uint32_t)i;
+}
+
+// where a run starting at record s would end, and where the run after it would start (jump[s]; n = there is none).  jump has n + 1 entries, jump[n] = n.
+__global__ void sg_dup_runs_kernel(const SgDupFields *f, long long n, uint32_t *runEndOf, uint32_t *jump, uint8_t *mark)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    if (s == n) { jump[n] = (uint32_t)n; return; }
+    mark[s] = s == 0 ? 1 : 0;
+    if (f[s].logical == SG_DUP_INVALID_LOCATION) { runEndOf[s] = (uint32_t)(s + 1); jump[s] = (uint32_t)(s + 1); return; }
+    const long long e = sg_dup_first_beyond(f, n, s, 2 * SG_DUP_RUN_REACH);
+    runEndOf[s] = (uint32_t)e;
+    jump[s] = (uint32_t)(e == n ? n : sg_dup_first_beyond(f, n, s, SG_DUP_RUN_REACH));
+}
+
+// one round of pointer jumping: everything marked marks what it jumps to; the jump doubles
+__global__ void sg_dup_orbit_kernel(long long n, const uint32_t *jump, uint32_t *jumpNext, uint8_t *mark)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    const uint32_t j = jump[s];
+    if (s < n && mark[s] && j < n) mark[j] = 1;
+    jumpNext[s] = jump[j];
+}
+
+__global__ void sg_dup_run_flags_kernel(const SgDupFields *f, long long n, const uint8_t *mark, uint8_t *isRun)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) isRun[s] = (mark[s] && f[s].logical != SG_DUP_INVALID_LOCATION) ? 1 : 0;
+}
+
+__global__ void sg_dup_run_table_kernel(const uint32_t *runStarts, const long long *nRuns, const uint32_t *runEndOf, long long *runStart, long long *runEnd)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < *nRuns) { runStart[k] = runStarts[k]; runEnd[k] = runEndOf[runStarts[k]]; }
+}
+
+// sort keys of the current order `idx`: WHICH 0: the larger of (info, mateInfo), 1: the smaller, 2: the library, 3: info -- records without FLAG 0x1 sort last in the pair passes
+__global__ void sg_dup_keys_kernel(const SgDupFields *f, long long n, const uint32_t *idx, int which, unsigned long long *keys)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const SgDupFields &F = f[idx[j]];
+    unsigned long long k;
+    if (which == 3) k = F.info;
+    else if (which == 4) k = F.lib;
+    else if (!(F.flag & SG_BAM_FLAG_PAIRED)) k = ~0ULL;
+    else if (which == 0) k = F.info > F.mateInfo ? F.info : F.mateInfo;
+    else if (which == 1) k = F.info < F.mateInfo ? F.info : F.mateInfo;
+    else k = F.lib;
+    keys[j] = k;
+}
+
+__global__ void sg_dup_walk_kernel(const uint8_t *records, const unsigned long long *offsets, long long n, const SgDupFields *f, const long long *nRuns,
+                                   const long long *runStart, const long long *runEnd, const uint32_t *order, int pairs, int32_t *flagRun, uint8_t *fragFlag)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const SgDupFields &F = f[order[j]];
+    if (pairs) {
+        if (!(F.flag & SG_BAM_FLAG_PAIRED)) return;
+        const uint64_t lo = F.info < F.mateInfo ? F.info : F.mateInfo, hi = F.info < F.mateInfo ? F.mateInfo : F.info;
+        if (j > 0) {
+            const SgDupFields &P = f[order[j - 1]];
+            if ((P.flag & SG_BAM_FLAG_PAIRED) && P.lib == F.lib && (P.info < P.mateInfo ? P.info : P.mateInfo) == lo && (P.info < P.mateInfo ? P.mateInfo : P.info) == hi) return;   // not the head
+        }
+        long long e = j + 1;
+        while (e < n) {
+            const SgDupFields &Q = f[order[e]];
+            if (!((Q.flag & SG_BAM_FLAG_PAIRED) && Q.lib == F.lib && (Q.info < Q.mateInfo ? Q.info : Q.mateInfo) == lo && (Q.info < Q.mateInfo ? Q.mateInfo : Q.info) == hi)) break;
+            e++;
+        }
+        if (e - j < 2) return;
+        SgDupView V; V.n = n; V.records = records; V.offsets = offsets; V.f = f; V.nRuns = *nRuns; V.runStart = runStart; V.runEnd = runEnd;
+        sg_dup_walk_pair_key(V, order + j, e - j, lo, hi, flagRun);
+    } else {
+        if (j > 0) { const SgDupFields &P = f[order[j - 1]]; if (P.lib == F.lib && P.info == F.info) return; }
+        long long e = j + 1;
+        while (e < n && f[order[e]].lib == F.lib && f[order[e]].info == F.info) e++;
+        if (e - j < 2) return;
+        SgDupView V; V.n = n; V.records = records; V.offsets = offsets; V.f = f; V.nRuns = *nRuns; V.runStart = runStart; V.runEnd = runEnd;
+        sg_dup_walk_fragment_key(V, order + j, e - j, flagRun, fragFlag);
+    }
+}
+
+__global__ void sg_dup_apply_kernel(uint8_t *records, const unsigned long long *offsets, long long n, const SgDupFields *f, const int32_t *flagRun, const uint8_t *fragFlag,
+                                    unsigned long long *marked)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((flagRun[i] >= 0 || fragFlag[i]) && !(f[i].flag & SG_BAM_FLAG_DUPLICATE)) {
+        const uint32_t fl = f[i].flag | SG_BAM_FLAG_DUPLICATE;
+        uint8_t *p = records + offsets[i];
+        p[18] = (uint8_t)fl; p[19] = (uint8_t)(fl >> 8);
+        atomicAdd(marked, 1ULL);
+    }
+}
+
+int snapgpu_bam_markdup_device(snapgpu_sam *s, char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t *nMarked, void *cudaStream)
+{
+    if (!s || !d_records || !d_offsets || !nMarked) return sg_fail("null argument");
+    *nMarked = 0;
+    if (nRecords < 0 || nRecords >= 0x7fffffffLL) return sg_fail("snapgpu_bam_markdup_device: record count out of range");
+    if (nRecords < 2) return 0;
+    SG_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : s->stream;
+    const long long n = nRecords;
+    size_t cubSort = 0, cubSel = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cubSort, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    cub::DeviceSelect::Flagged(nullptr, cubSel, (uint32_t *)nullptr, (uint8_t *)nullptr, (uint32_t *)nullptr, (long long *)nullptr, (int)n);
+    const size_t cubBytes = (cubSort > cubSel ? cubSort : cubSel) + 256;
+    const size_t need = (size_t)n * (sizeof(SgDupFields) + 4 * 4 + 2 * 8 + 3 * 4 + 2 * 8 + 4 + 3) + cubBytes + 64 * 256;
+    if (sam_post_reserve(s, need)) return 1;
+    SgPostCarve C{(uint8_t *)s->d_post, 0, s->postBytes};
+    SgDupFields *f = C.take<SgDupFields>(n);
+    uint32_t *runEndOf = C.take<uint32_t>(n + 1), *jumpA = C.take<uint32_t>(n + 1), *jumpB = C.take<uint32_t>(n + 1), *iota = C.take<uint32_t>(n);
+    long long *runStart = C.take<long long>(n), *runEnd = C.take<long long>(n);
+    uint32_t *runStarts = C.take<uint32_t>(n), *idxA = C.take<uint32_t>(n), *idxB = C.take<uint32_t>(n);
+    unsigned long long *keysA = C.take<unsigned long long>(n), *keysB = C.take<unsigned long long>(n);
+    int32_t *flagRun = C.take<int32_t>(n);
+    uint8_t *mark = C.take<uint8_t>(n + 1), *isRun = C.take<uint8_t>(n), *fragFlag = C.take<uint8_t>(n);
+    long long *d_nRuns = C.take<long long>(1);
+    unsigned long long *d_marked = C.take<unsigned long long>(1);
+    void *d_cub = C.take<uint8_t>(cubBytes);
+    if (C.used > C.cap) return sg_fail("snapgpu_bam_markdup_device: work buffer accounting");
+    const unsigned blocks = (unsigned)((n + 1 + 255) / 256);
+    const uint8_t *rec = (const uint8_t *)d_records; const unsigned long long *off = (const unsigned long long *)d_offsets;
+    SG_CUDA(cudaMemsetAsync(d_marked, 0, 8, st));
+    sg_dup_fields_kernel<<<blocks, 256, 0, st>>>(rec, off, n, s->d_contigStartByOriginal, (int32_t)s->h_contigStartByOriginal.size(), f, flagRun, fragFlag, iota);
+    sg_dup_runs_kernel<<<blocks, 256, 0, st>>>(f, n, runEndOf, jumpA, mark);
+    SG_CUDA(cudaGetLastError());
+    { uint32_t *a = jumpA, *b = jumpB; for (long long span = 1; span <= n; span <<= 1) { sg_dup_orbit_kernel<<<blocks, 256, 0, st>>>(n, a, b, mark); uint32_t *t = a; a = b; b = t; } }
+    sg_dup_run_flags_kernel<<<blocks, 256, 0, st>>>(f, n, mark, isRun);
+    SG_CUDA(cudaGetLastError());
+    size_t cb = cubBytes;
+    SG_CUDA(cub::DeviceSelect::Flagged(d_cub, cb, iota, isRun, runStarts, d_nRuns, (int)n, st));
+    sg_dup_run_table_kernel<<<blocks, 256, 0, st>>>(runStarts, d_nRuns, runEndOf, runStart, runEnd);
+    SG_CUDA(cudaGetLastError());
+    // pair keys: stable LSD passes over (larger end, smaller end, library), then one thread per key
+    const uint32_t *order = iota;
+    uint32_t *out = idxA, *other = idxB;
+    const int pairPasses[3] = {0, 1, 2}, fragPasses[2] = {3, 4};
+    for (int p = 0; p < 3; p++) {
+        sg_dup_keys_kernel<<<blocks, 256, 0, st>>>(f, n, order, pairPasses[p], keysA);
+        cb = cubBytes;
+        SG_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, cb, keysA, keysB, order, out, (int)n, 0, 64, st));
+        order = out; uint32_t *t = out; out = other; other = t;
+    }
+    sg_dup_walk_kernel<<<blocks, 256, 0, st>>>(rec, off, n, f, d_nRuns, runStart, runEnd, order, 1, flagRun, fragFlag);
+    SG_CUDA(cudaGetLastError());
+    order = iota; out = idxA; other = idxB;
+    for (int p = 0; p < 2; p++) {
+        sg_dup_keys_kernel<<<blocks, 256, 0, st>>>(f, n, order, fragPasses[p], keysA);
+        cb = cubBytes;
+        SG_CUDA(cub::DeviceRadixSort::SortPairs(d_cub, cb, keysA, keysB, order, out, (int)n, 0, 64, st));
+        order = out; uint32_t *t = out; out = other; other = t;
+    }
+    sg_dup_walk_kernel<<<blocks, 256, 0, st>>>(rec, off, n, f, d_nRuns, runStart, runEnd, order, 0, flagRun, fragFlag);
+    sg_dup_apply_kernel<<<blocks, 256, 0, st>>>((uint8_t *)d_records, off, n, f, flagRun, fragFlag, d_marked);
+    SG_CUDA(cudaGetLastError());
+    SG_CUDA(cudaMemcpyAsync(&s->h_meta[0], d_marked, 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    *nMarked = (int64_t)s->h_meta[0];
+    return 0;
+}
+
+// ---- the index ----
+struct SgBaiRecord { int32_t ref; uint32_t bin; unsigned long long at; };
+__global__ void sg_bai_records_kernel(const uint8_t *records, const unsigned long long *offsets, long long n, unsigned long long headerBytes, int32_t nRef,
+                                      uint8_t *isHead, unsigned long long *composite, unsigned long long *refFirst, unsigned long long *refLast,
+                                      unsigned long long *refMapped, unsigned long long *refUnmapped, uint32_t *iota)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SgBamRec r; r.p = records + offsets[i];
+    const int32_t ref = r.refID();
+    const unsigned long long at = headerBytes + offsets[i];
+    bool head = i == 0;
+    if (!head) { SgBamRec q; q.p = records + offsets[i - 1]; head = q.refID() != ref || q.bin() != r.bin(); }
+    isHead[i] = head ? 1 : 0;
+    iota[i] = (uint32_t)i;
+    unsigned long long c = 0;
+    if (ref >= 0 && ref < nRef) {
+        atomicMin(&refFirst[ref], at);
+        atomicMax(&refLast[ref], at + (unsigned long long)r.size());
+        if (r.flag() & SG_BAM_FLAG_UNMAPPED) atomicAdd(&refUnmapped[ref], 1ULL);
+        else { atomicAdd(&refMapped[ref], 1ULL); c = ((unsigned long long)(ref + 1) << 32) | (unsigned long long)(sg_bai_linear_slot(r) + 1); }
+    }
+    composite[i] = c;
+}
+
+struct SgMaxU64 { __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; } };
+
+__global__ void sg_bai_chunks_kernel(const uint8_t *records, const unsigned long long *offsets, long long n, unsigned long long headerBytes, unsigned long long totalBytes,
+                                     const uint32_t *heads, const long long *nHeads, SgBaiRecord *chunkHead, unsigned long long *chunkEnd)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *nHeads) return;
+    SgBamRec r; r.p = records + offsets[heads[k]];
+    chunkHead[k].ref = r.refID(); chunkHead[k].bin = r.bin(); chunkHead[k].at = headerBytes + offsets[heads[k]];
+    chunkEnd[k] = (k + 1 < *nHeads) ? headerBytes + offsets[heads[k + 1]] : totalBytes;
+}
+
+// a record sets the linear-index entry of its window iff no earlier record of its reference reached that far (addInterval only ever appends, Bam.cpp:3425-3440)
+__global__ void sg_bai_linear_kernel(const unsigned long long *offsets, long long n, unsigned long long headerBytes, const unsigned long long *composite,
+                                     const unsigned long long *prefixMax, const unsigned long long *refSlotBase, unsigned long long *intervals, unsigned long long *refSlots)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long c = composite[i];
+    if (c == 0 || c <= prefixMax[i]) return;
+    const uint32_t ref = (uint32_t)(c >> 32) - 1u, slot = (uint32_t)c - 1u;
+    intervals[refSlotBase[ref] + slot] = headerBytes + offsets[i];
+    atomicMax(&refSlots[ref], (unsigned long long)slot + 1ULL);
+}
+
+int snapgpu_bam_index_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
+                             char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream)
+{
+    if (!s || !bai || !baiBytes || (nRecords > 0 && (!d_records || !d_offsets))) return sg_fail("null argument");
+    *baiBytes = 0;
+    if (nRecords < 0 || nRecords >= 0x7fffffffLL || recordBytes < 0 || headerBytes < 0) return sg_fail("snapgpu_bam_index_device: argument out of range");
+    SG_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : s->stream;
+    const long long n = nRecords;
+    const int32_t nRef = (int32_t)s->h_contigStartByOriginal.size();
+    const unsigned long long total = (unsigned long long)headerBytes + (unsigned long long)recordBytes;
+    std::vector<SgBaiChunk> chunks;
+    std::vector<SgBaiRef> refs((size_t)nRef);
+    if (n > 0) {
+        std::vector<unsigned long long> slotBase((size_t)nRef + 1, 0);
+        for (int32_t r = 0; r < nRef; r++) slotBase[r + 1] = slotBase[r] + (unsigned long long)(s->h_contigSpan[r] / 16384 + 3);
+        const size_t nSlots = (size_t)slotBase[nRef];
+        size_t cubSel = 0, cubScan = 0;
+        cub::DeviceSelect::Flagged(nullptr, cubSel, (uint32_t *)nullptr, (uint8_t *)nullptr, (uint32_t *)nullptr, (long long *)nullptr, (int)n);
+        cub::DeviceScan::ExclusiveScan(nullptr, cubScan, (unsigned long long *)nullptr, (unsigned long long *)nullptr, SgMaxU64(), 0ULL, (int)n);
+        const size_t cubBytes = (cubSel > cubScan ? cubSel : cubScan) + 256;
+        const size_t need = (size_t)n * (1 + 8 + 8 + 4 + 4 + sizeof(SgBaiRecord) + 8) + (size_t)nRef * 8 * 6 + nSlots * 8 + cubBytes + 64 * 256;
+        if (sam_post_reserve(s, need)) return 1;
+        SgPostCarve C{(uint8_t *)s->d_post, 0, s->postBytes};
+        uint8_t *isHead = C.take<uint8_t>(n);
+        unsigned long long *composite = C.take<unsigned long long>(n), *prefixMax = C.take<unsigned long long>(n);
+        uint32_t *iota = C.take<uint32_t>(n), *heads = C.take<uint32_t>(n);
+        SgBaiRecord *chunkHead = C.take<SgBaiRecord>(n);
+        unsigned long long *chunkEnd = C.take<unsigned long long>(n);
+        unsigned long long *refFirst = C.take<unsigned long long>(nRef), *refLast = C.take<unsigned long long>(nRef), *refMapped = C.take<unsigned long long>(nRef),
+                           *refUnmapped = C.take<unsigned long long>(nRef), *refSlots = C.take<unsigned long long>(nRef), *d_slotBase = C.take<unsigned long long>(nRef + 1);
+        unsigned long long *intervals = C.take<unsigned long long>(nSlots);
+        long long *d_nHeads = C.take<long long>(1);
+        void *d_cub = C.take<uint8_t>(cubBytes);
+        if (C.used > C.cap) return sg_fail("snapgpu_bam_index_device: work buffer accounting");
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        const uint8_t *rec = (const uint8_t *)d_records; const unsigned long long *off = (const unsigned long long *)d_offsets;
+        SG_CUDA(cudaMemsetAsync(refFirst, 0xff, (size_t)nRef * 8, st));
+        SG_CUDA(cudaMemsetAsync(refLast, 0, (size_t)nRef * 8, st));
+        SG_CUDA(cudaMemsetAsync(refMapped, 0, (size_t)nRef * 8, st));
+        SG_CUDA(cudaMemsetAsync(refUnmapped, 0, (size_t)nRef * 8, st));
+        SG_CUDA(cudaMemsetAsync(refSlots, 0, (size_t)nRef * 8, st));
+        SG_CUDA(cudaMemsetAsync(intervals, 0xff, nSlots * 8, st));
+        SG_CUDA(cudaMemcpyAsync(d_slotBase, slotBase.data(), (size_t)(nRef + 1) * 8, cudaMemcpyHostToDevice, st));
+        sg_bai_records_kernel<<<blocks, 256, 0, st>>>(rec, off, n, (unsigned long long)headerBytes, nRef, isHead, composite, refFirst, refLast, refMapped, refUnmapped, iota);
+        SG_CUDA(cudaGetLastError());
+        size_t cb = cubBytes;
+        SG_CUDA(cub::DeviceSelect::Flagged(d_cub, cb, iota, isHead, heads, d_nHeads, (int)n, st));
+        sg_bai_chunks_kernel<<<blocks, 256, 0, st>>>(rec, off, n, (unsigned long long)headerBytes, total, heads, d_nHeads, chunkHead, chunkEnd);
+        cb = cubBytes;
+        SG_CUDA(cub::DeviceScan::ExclusiveScan(d_cub, cb, composite, prefixMax, SgMaxU64(), 0ULL, (int)n, st));
+        sg_bai_linear_kernel<<<blocks, 256, 0, st>>>(off, n, (unsigned long long)headerBytes, composite, prefixMax, d_slotBase, intervals, refSlots);
+        SG_CUDA(cudaGetLastError());
+        long long nHeads = 0;
+        SG_CUDA(cudaMemcpyAsync(&nHeads, d_nHeads, 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        std::vector<SgBaiRecord> hHead((size_t)nHeads); std::vector<unsigned long long> hEnd((size_t)nHeads), hIntervals(nSlots);
+        std::vector<unsigned long long> hFirst(nRef), hLast(nRef), hMapped(nRef), hUnmapped(nRef), hSlots(nRef);
+        SG_CUDA(cudaMemcpy(hHead.data(), chunkHead, (size_t)nHeads * sizeof(SgBaiRecord), cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hEnd.data(), chunkEnd, (size_t)nHeads * 8, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hIntervals.data(), intervals, nSlots * 8, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hFirst.data(), refFirst, (size_t)nRef * 8, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hLast.data(), refLast, (size_t)nRef * 8, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hMapped.data(), refMapped, (size_t)nRef * 8, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hUnmapped.data(), refUnmapped, (size_t)nRef * 8, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(hSlots.data(), refSlots, (size_t)nRef * 8, cudaMemcpyDeviceToHost));
+        chunks.resize((size_t)nHeads);
+        for (long long k = 0; k < nHeads; k++) { chunks[k].ref = hHead[k].ref; chunks[k].bin = hHead[k].bin; chunks[k].start = hHead[k].at; chunks[k].end = hEnd[k]; }
+        for (int32_t r = 0; r < nRef; r++) {
+            SgBaiRef &R = refs[r];
+            R.any = hMapped[r] + hUnmapped[r] > 0;
+            R.firstStart = hFirst[r]; R.lastEnd = hLast[r]; R.mapped = hMapped[r]; R.unmapped = hUnmapped[r];
+            R.intervals.assign(hIntervals.begin() + slotBase[r], hIntervals.begin() + slotBase[r] + hSlots[r]);
+        }
+    }
+    std::vector<uint8_t> o = sg_bai_compose(nRef, chunks, refs, total);
+    if ((int64_t)o.size() > baiCapacity) return sg_fail("snapgpu_bam_index_device: bai buffer too small");
+    memcpy(bai, o.data(), o.size());
+    *baiBytes = (int64_t)o.size();
     return 0;
 }
 

@@ -85,10 +85,10 @@ EXPORTS = [
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
-    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_bam_markdup_device", "snapgpu_bam_index_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
-ABI_VERSION = 4          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
+ABI_VERSION = 5          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
 _lib = None
 
 
@@ -144,6 +144,8 @@ def lib():
         L.snapgpu_sam_set_format.argtypes = [C.c_void_p, C.c_int]
         L.snapgpu_bgzf_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_sam_sort_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_bam_markdup_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.snapgpu_bam_index_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_sam_last_record_count.restype = C.c_int64
         L.snapgpu_sam_last_record_count.argtypes = [C.c_void_p]
         L.snapgpu_fastq_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 7 + [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -428,6 +430,26 @@ class SamFormatter:
 
     def last_record_count(self) -> int:
         return int(lib().snapgpu_sam_last_record_count(self.handle))
+
+    def markdup_device(self, d_records, d_offsets, n_records, stream=0) -> int:
+        """BAMDupMarkFilter over a coordinate-sorted stream of BAM records in device memory (pointers as ints): FLAG 0x400 set in place; returns
+        the number of records newly flagged (snapgpu_bam_markdup_device)."""
+        marked = C.c_int64(0)
+        _check(lib().snapgpu_bam_markdup_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, C.byref(marked), C.c_void_p(stream)))
+        return marked.value
+
+    def index_device(self, d_records, d_offsets, n_records, record_bytes, header_bytes, stream=0) -> bytes:
+        """The .bai of header ‖ records as snapgpu_bgzf_device lays the file out (snapgpu_bam_index_device)."""
+        cap = 1 << 20
+        while True:
+            out = np.empty(cap, dtype=np.uint8); used = C.c_int64(0)
+            rc = lib().snapgpu_bam_index_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, record_bytes, header_bytes,
+                                               out.ctypes.data_as(C.c_void_p), cap, C.byref(used), C.c_void_p(stream))
+            if rc != 0 and b"too small" in lib().snapgpu_last_error() and cap < (1 << 32):
+                cap *= 8
+                continue
+            _check(rc)
+            return out[:used.value].tobytes()
 
     def format(self, batch, ids, results, paired: bool = False, front_clipped=None, clipped_lens=None) -> bytes:
         """batch: synth.ReadBatch (host arrays); ids: one bytes object per read; results: the aligner's records (one per read, or one

@@ -1,0 +1,129 @@
+"""Row N4 after the sort, on the device through the C ABI: snapgpu_bam_markdup_device / snapgpu_bam_index_device against the files the reference binary
+writes with `-so` (duplicates marked, .bai), and the whole chain align -> BAM records -> sort -> mark -> BGZF + .bai on the device."""
+import gzip
+import io
+import struct
+
+import numpy as np
+import pytest
+
+import sorted_data
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from snap_b200 import engine as e
+    assert e.lib().snapgpu_device_count() >= 1, "no CUDA device: the CUDA path has no fallback"
+    return e
+
+
+@pytest.fixture(scope="module")
+def gidx(engine, small_cfg):
+    ix = engine.Index.open(small_cfg.idx)
+    yield ix
+    ix.close()
+
+
+@pytest.fixture(scope="module")
+def cases(tmp_path_factory, small_cfg, reflib):
+    return sorted_data.make_cases(str(tmp_path_factory.mktemp("sorted_gpu")), small_cfg.contigs, small_cfg.idx, reflib.SNAP_ALIGNER)
+
+
+def _upload(records):
+    import torch
+    dev = torch.device("cuda", 0)
+    blob = b"".join(records)
+    offs = np.zeros(len(records), dtype=np.int64)
+    offs[1:] = np.cumsum([len(r) for r in records])[:-1]
+    d_rec = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    d_off = torch.from_numpy(offs).to(dev)
+    return blob, d_rec, d_off
+
+
+@pytest.mark.parametrize("name", ["single", "paired", "single_dense", "paired_dense"])
+def test_duplicates_marked_on_the_device_like_the_reference(engine, gidx, cases, name):
+    """The reference's sorted, unmarked record stream in HBM in; the reference's marked stream out, byte for byte; a second pass marks nothing."""
+    c = cases[name]
+    fmt = engine.SamFormatter(gidx, engine.default_params(maxDist=14), 4096)
+    blob, d_rec, d_off = _upload(c.unmarked)
+    marked = fmt.markdup_device(d_rec.data_ptr(), d_off.data_ptr(), len(c.unmarked))
+    got = d_rec.cpu().numpy().tobytes()
+    want = b"".join(c.marked)
+    assert marked == sum(1 for r in c.marked if r[19] & 4) and marked > len(c.marked) // 5
+    bad = [i for i, (a, b) in enumerate(zip(sorted_data_split(got), c.marked)) if a != b]
+    assert got == want, (len(bad), bad[:5])
+    assert fmt.markdup_device(d_rec.data_ptr(), d_off.data_ptr(), len(c.unmarked)) == 0
+    fmt.close()
+
+
+def sorted_data_split(blob):
+    out, p = [], 0
+    while p < len(blob):
+        b = struct.unpack("<i", blob[p:p + 4])[0]; out.append(blob[p:p + 4 + b]); p += 4 + b
+    return out
+
+
+@pytest.mark.parametrize("name", ["single", "paired", "single_dense", "paired_dense"])
+def test_bam_index_from_the_device_equals_the_reference_index(engine, gidx, cases, name):
+    c = cases[name]
+    fmt = engine.SamFormatter(gidx, engine.default_params(maxDist=14), 4096)
+    blob, d_rec, d_off = _upload(c.marked)
+    bai = fmt.index_device(d_rec.data_ptr(), d_off.data_ptr(), len(c.marked), len(blob), c.header_bytes)
+    fmt.close()
+    got = sorted_data.parse_bai(bai, sorted_data.our_blocks(c.header_bytes + len(blob)))
+    want = sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
+    assert got == want
+
+
+def test_reads_to_sorted_marked_indexed_bam_on_the_device(engine, gidx, small_cfg, cases, tmp_path):
+    """The whole `snap single ... -so -o out.bam` output stage on the device: reads aligned, BAM records formatted, coordinate-sorted, duplicates marked,
+    the file's BGZF members and its .bai made -- the records equal the reference file's (inflated), the index equals the reference's."""
+    import torch
+    from snap_b200 import synth
+    c = cases["single"]
+    lines = open(c.bam.replace("se_dup.bam", "se.fq"), "rb").read().split(b"\n")
+    ids = [lines[i][1:] for i in range(0, len(lines) - 1, 4)]
+    rb = synth.ReadBatch.from_lists([(lines[i + 1], lines[i + 3]) for i in range(0, len(lines) - 1, 4)])
+    p = engine.default_params(maxDist=14)
+    al = engine.SingleAligner(gidx, p, 4096)
+    res, _ = al.align(rb)
+    al.close()
+    fmt = engine.SamFormatter(gidx, p, 4096)
+    fmt.set_format(bam=True)
+    fmt.format(rb, ids, res)
+    n = fmt.last_record_count()
+    assert n == rb.n == len(c.marked)
+    dev = torch.device("cuda", 0)
+    cap = n * 1024
+    d_sorted = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    d_offs = torch.empty((n,), dtype=torch.int64, device=dev)
+    used = fmt.sort_device(0, d_sorted.data_ptr(), cap, 0, d_offs.data_ptr())
+    marked = fmt.markdup_device(d_sorted.data_ptr(), d_offs.data_ptr(), n)
+    records = d_sorted[:used].cpu().numpy().tobytes()
+    assert marked == sum(1 for r in c.marked if r[19] & 4)
+    assert records == b"".join(c.marked)
+    # the file: the reference file's own header bytes, then our records, as BGZF members made on the device + the end-of-file member
+    header = gzip.open(c.bam, "rb").read()[:c.header_bytes]
+    d_all = torch.cat([torch.frombuffer(bytearray(header), dtype=torch.uint8).to(dev), d_sorted[:used]])
+    total = len(header) + used
+    n_members = (total + 0xff00 - 1) // 0xff00
+    d_out = torch.empty((n_members * (0xff00 + 31),), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    out_bytes = engine.bgzf_device(d_all.data_ptr(), total, d_out.data_ptr(), d_out.numel())
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    file_bytes = d_out[:out_bytes].cpu().numpy().tobytes() + eof
+    assert gzip.GzipFile(fileobj=io.BytesIO(file_bytes)).read() == header + records
+    bai = fmt.index_device(d_sorted.data_ptr(), d_offs.data_ptr(), n, used, len(header))
+    fmt.close()
+    blocks = sorted_data.our_blocks(total)
+    assert blocks[-1][0] + 28 == len(file_bytes) and [b[0] for b in blocks] == _member_starts(file_bytes)
+    assert sorted_data.parse_bai(bai, blocks) == sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
+
+
+def _member_starts(raw):
+    p, out = 0, []
+    while p < len(raw):
+        out.append(p); p += struct.unpack("<H", raw[p + 16:p + 18])[0] + 1
+    return out
