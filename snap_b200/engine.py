@@ -331,6 +331,12 @@ class SingleAligner:
             lib().snapgpu_aligner_destroy(self.handle)
             self.handle = None
 
+    def __del__(self):       # a handle dropped without close() must not keep its arenas (tens of GB of HBM) until the process ends
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class PairedAligner:
     """ChimericPairedEndAligner(IntersectingPairedEndAligner) for batches of pairs (reference PairedAligner.cpp:547-800).
@@ -375,6 +381,12 @@ class PairedAligner:
         if self.handle:
             lib().snapgpu_aligner_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):       # a handle dropped without close() must not keep its arenas (tens of GB of HBM) until the process ends
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class SamFormatter:
@@ -464,6 +476,12 @@ class SamFormatter:
             lib().snapgpu_sam_destroy(self.handle)
             self.handle = None
 
+    def __del__(self):       # a handle dropped without close() must not keep its arenas (tens of GB of HBM) until the process ends
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 class FastqParser:
     """FASTQ text -> clipped, upper-cased reads in the aligners' layout (FASTQReader::getReadFromBuffer + Read::clip for a whole buffer)."""
@@ -506,6 +524,12 @@ class FastqParser:
         if self.handle:
             lib().snapgpu_fastq_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):       # a handle dropped without close() must not keep its arenas (tens of GB of HBM) until the process ends
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def bgzf_device(d_in: int, n_bytes: int, d_out: int, out_capacity: int, stream: int = 0) -> int:

@@ -392,6 +392,7 @@ def test_properties_at_scale(engine, small_cfg):
     assert both.sum() > 500
     assert (ra["location"][both] == rb2["location"][both]).all() and (ra["direction"][both] != rb2["direction"][both]).all()
     assert sum(c1["mapqHistogram"]) == int(aligned.sum()) == c1["singleHits"] + c1["multiHits"]
+    al.close(); small.close()
     ix.close()
 
 
@@ -522,7 +523,7 @@ def test_single_launch_forms_agree(engine, gidx, small_cfg, reflib, monkeypatch,
     for form, two_pass, overlap in (("ov", "1", "1"), ("1", "1", "0"), ("0", "0", "0")):
         monkeypatch.setenv("SNAPGPU_TWO_PASS", two_pass)
         monkeypatch.setenv("SNAPGPU_OVERLAP", overlap)
-        al = engine.SingleAligner(gidx, p, 4096)
+        al = engine.SingleAligner(gidx, p, 1 << 14)      # (the overlapped form needs the arenas of 8 CTAs per SM: a handle for at least 9472 reads)
         got, ctr = al.align(rb)
         out[form] = (got, ctr, al.launch_count())
         al.close()
