@@ -166,17 +166,53 @@ __global__ void sg_fastq_meta_kernel(const uint8_t *text, long long nBytes, cons
     meta[0] = L; meta[1] = R; meta[2] = consumed;
 }
 
-// One warp per record: upper-case + '.' -> 'N' (Tables.cpp:94-104) while copying.
+// One warp per record: upper-case + '.' -> 'N' (Tables.cpp:94-104) while copying.  Destination words: after the (up to 3) bytes that bring the
+// destination to a 4-byte boundary every lane stores one 32-bit word per step, its four source bytes cut out of two aligned source words with a
+// funnel shift and translated four at a time (byte-wise compares: __vcmp*4); the text is read once per array, 4 bytes per load instead of 1.
+__device__ __forceinline__ uint32_t sg_fastq_upper4(uint32_t w)
+{
+    const uint32_t lower = __vcmpgeu4(w, 0x61616161u) & __vcmpleu4(w, 0x7a7a7a7au);
+    w -= lower & 0x20202020u;
+    const uint32_t dot = __vcmpeq4(w, 0x2e2e2e2eu);
+    return (w & ~dot) | (0x4e4e4e4eu & dot);
+}
+__device__ __forceinline__ uint32_t sg_fastq_load4(const uint8_t *text, long long nBytes, long long at)      // bytes [at, at + 4) of the text, 0 past its end
+{
+    const long long w0 = at & ~3LL;
+    if (at >= 0 && w0 + 8 <= nBytes) {
+        const uint32_t a = *(const uint32_t *)(text + w0), b = *(const uint32_t *)(text + w0 + 4);
+        return __funnelshift_r(a, b, (uint32_t)(at & 3) * 8u);
+    }
+    uint32_t v = 0;
+    for (int k = 0; k < 4; k++) if (at + k >= 0 && at + k < nBytes) v |= (uint32_t)text[at + k] << (8 * k);
+    return v;
+}
 __global__ void sg_fastq_copy_kernel(const uint8_t *text, long long nBytes, const SgFastqRecord *rec, const unsigned long long *offsets, long long nRecords,
                                      uint8_t *bases, uint8_t *quals)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool aligned = (((size_t)text | (size_t)bases | (size_t)quals) & 3) == 0;
     for (long long r = warp; r < nRecords; r += nWarps) {
         const SgFastqRecord o = rec[r];
         const unsigned long long dst = offsets[r];
-        for (uint32_t k = lane; k < o.len; k += 32) {
+        uint32_t head = aligned ? (uint32_t)((4 - (dst & 3)) & 3) : o.len;          // bytes before the destination's first whole word
+        if (head > o.len) head = o.len;
+        const uint32_t words = (o.len - head) >> 2, tailAt = head + 4 * words;
+        for (uint32_t k = lane; k < head; k += 32) {
+            uint8_t c = text[o.dataStart + k];
+            if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+            else if (c == '.') c = 'N';
+            bases[dst + k] = c;
+            quals[dst + k] = ((long long)o.qualStart + k < nBytes) ? text[o.qualStart + k] : (uint8_t)0;
+        }
+        for (uint32_t w = lane; w < words; w += 32) {
+            const uint32_t k = head + 4 * w;
+            *(uint32_t *)(bases + dst + k) = sg_fastq_upper4(sg_fastq_load4(text, nBytes, (long long)o.dataStart + k));
+            *(uint32_t *)(quals + dst + k) = sg_fastq_load4(text, nBytes, (long long)o.qualStart + k);
+        }
+        for (uint32_t k = tailAt + lane; k < o.len; k += 32) {
             uint8_t c = text[o.dataStart + k];
             if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
             else if (c == '.') c = 'N';

@@ -112,7 +112,8 @@ struct snapgpu_aligner {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     unsigned int *d_producersDone = nullptr;
     int64_t maxBatchReads = 0;
-    int64_t chunkReads = 0;              // reads per pipeline stage of snapgpu_align_single
+    int64_t chunkReads = 0;              // reads per pipeline stage of snapgpu_align_single (the largest)
+    int64_t firstChunkReads = 0;         // the first stage of a call is this small; the second takes the rest of one full stage
     size_t chunkBases = 0;
     // two pipeline slots: while the GPU aligns chunk c the host packs chunk c+1 into the other slot's pinned staging
     struct Slot {
@@ -1450,10 +1451,18 @@ static int aligner_init_common(snapgpu_aligner *a, int64_t maxBatchReads, int64_
     SG_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&a->streamIn, cudaStreamNonBlocking));
     SG_CUDA(cudaStreamCreateWithFlags(&a->streamOut, cudaStreamNonBlocking));
-    a->chunkReads = 262144;              // host-buffer pipeline stage (measured e2e, M reads/s single / paired: 131072 -> 15.3 / 7.5, 262144 -> 15.6 / 7.9, 524288 -> 15.1 / 7.9)
+    // host-buffer pipeline stages: a small first chunk (the copy nothing overlaps with), then the rest of one full-size chunk, then full-size chunks --
+    // few launches, so little of the step is spent in the tails of the persistent kernels.  Equal chunks measured (e2e, M reads/s single / paired):
+    // 131072 -> 15.3 / 7.5, 262144 -> 15.6 / 7.9, 524288 -> 15.1 / 7.9.
+    a->chunkReads = 524288;
     if (const char *e = getenv("SNAPGPU_CHUNK_READS")) a->chunkReads = atoll(e) > 0 ? atoll(e) : a->chunkReads;
     if (a->chunkReads > maxBatchReads) a->chunkReads = maxBatchReads;
     a->chunkReads = (a->chunkReads + readsPerUnit - 1) / readsPerUnit * readsPerUnit;
+    a->firstChunkReads = a->chunkReads / 8;
+    if (const char *e = getenv("SNAPGPU_FIRST_CHUNK_READS")) a->firstChunkReads = atoll(e) > 0 ? atoll(e) : a->firstChunkReads;
+    if (a->firstChunkReads > a->chunkReads) a->firstChunkReads = a->chunkReads;
+    a->firstChunkReads = (a->firstChunkReads + readsPerUnit - 1) / readsPerUnit * readsPerUnit;
+    if (a->firstChunkReads < readsPerUnit) a->firstChunkReads = readsPerUnit;
     a->chunkBases = (size_t)a->chunkReads * (size_t)a->params.maxReadLen;
     const size_t resultBytes = (size_t)(a->chunkReads / readsPerUnit) * resultBytesPerUnit;
     for (int k = 0; k < 2; k++) {
@@ -1865,7 +1874,12 @@ static int align_host_impl(snapgpu_aligner *a, int64_t nUnits, int readsPerUnit,
         snapgpu_aligner::Slot &sl = a->slot[k];
         if (drain_slot(a, k, results, resultBytesPerUnit, resultsPinned)) return 1;     // slot k was used by chunk c-2
         int64_t m = 0; size_t total = 0;
-        while (done + m < n && m < a->chunkReads) {
+        // stage sizes: first small, second the rest of a full stage, then full stages (a batch that fits one stage and a half is not cut up further)
+        int64_t want = a->chunkReads;
+        if (n > a->chunkReads + a->chunkReads / 2) want = c == 0 ? a->firstChunkReads : (c == 1 ? a->chunkReads - a->firstChunkReads : a->chunkReads);
+        else if (n > a->firstChunkReads * 2) want = c == 0 ? a->firstChunkReads : a->chunkReads;
+        if (want < readsPerUnit) want = readsPerUnit;
+        while (done + m < n && m < want) {
             size_t unitBases = 0;
             for (int w = 0; w < readsPerUnit; w++) {
                 const uint32_t len = lens[done + m + w];
@@ -2248,18 +2262,40 @@ int snapgpu_sam_set_format(snapgpu_sam *s, int format)
 
 // ---- BGZF (the container of a BAM file; reference SNAPLib/GzipDataWriter.cpp + Bam.cpp): the payload cut into members of at most 0xff00 bytes,
 //      each a gzip member with the 'BC' extra field carrying its size.  The deflate stream of a member is ONE STORED block (BTYPE = 00): valid
-//      BGZF that any BAM reader inflates to exactly the payload, without a compressor on the device.  One CTA per member: the threads copy
-//      the payload while thread 0 runs the CRC-32 (table in shared memory). ----
+//      BGZF that any BAM reader inflates to exactly the payload, without a compressor on the device. ----
 #define SG_BGZF_PAYLOAD 0xff00u
+// CRC-32 arithmetic on the reflected polynomial (zlib's crc32_combine): a * b mod P, and x^(8 n) mod P by squaring
+__device__ __forceinline__ uint32_t sg_crc_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1u)) == 0) break; }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ 0xedb88320u : b >> 1;
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t sg_crc_x8n(const uint32_t *x2n, uint32_t nBytes)       // x2n[k] = x^(2^k) mod P
+{
+    uint32_t p = 1u << 31, k = 3;
+    while (nBytes) { if (nBytes & 1u) p = sg_crc_multmodp(x2n[k & 31u], p); nBytes >>= 1; k++; }
+    return p;
+}
+// One CTA per member.  The threads copy the payload; each also runs the table CRC over its own 1/256th of it, and thread 0 joins the 256 partial CRCs
+// (crc(A || B) = crc(A) * x^(8 |B|) + crc(B) over GF(2)[x] / P): ~255 dependent table steps per thread and 255 modular products instead of 65 280
+// steps on one thread.
 __global__ void __launch_bounds__(256)
 sg_bgzf_kernel(const uint8_t *in, unsigned long long nBytes, uint8_t *out, unsigned long long nBlocks)
 {
     __shared__ uint32_t table[256];
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t x2n[32];
     {
         uint32_t c = threadIdx.x;
         for (int k = 0; k < 8; k++) c = (c & 1u) ? (0xedb88320u ^ (c >> 1)) : (c >> 1);
         table[threadIdx.x] = c;
     }
+    if (threadIdx.x == 0) { uint32_t v = 1u << 30; x2n[0] = v; for (int k = 1; k < 32; k++) { v = sg_crc_multmodp(v, v); x2n[k] = v; } }
     __syncthreads();
     for (unsigned long long b = blockIdx.x; b < nBlocks; b += gridDim.x) {
         const unsigned long long off = b * SG_BGZF_PAYLOAD;
@@ -2267,10 +2303,22 @@ sg_bgzf_kernel(const uint8_t *in, unsigned long long nBytes, uint8_t *out, unsig
         uint8_t *o = out + b * (unsigned long long)(SG_BGZF_PAYLOAD + 31u);      // members are laid at a fixed pitch; the host (or a scan) closes the gaps
         const uint8_t *src = in + off;
         for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) o[23 + k] = src[k];
-        if (threadIdx.x == 0) {
+        const uint32_t slice = (len + 255u) / 256u;
+        {
+            const uint32_t lo = threadIdx.x * slice < len ? threadIdx.x * slice : len, hi = lo + slice < len ? lo + slice : len;
             uint32_t crc = 0xffffffffu;
-            for (uint32_t k = 0; k < len; k++) crc = table[(crc ^ src[k]) & 0xffu] ^ (crc >> 8);
-            crc ^= 0xffffffffu;
+            for (uint32_t k = lo; k < hi; k++) crc = table[(crc ^ src[k]) & 0xffu] ^ (crc >> 8);
+            part[threadIdx.x] = crc ^ 0xffffffffu;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t xs = sg_crc_x8n(x2n, slice);
+            uint32_t crc = part[0];
+            for (uint32_t t = 1; t < 256u; t++) {
+                const uint32_t lo = t * slice < len ? t * slice : len, hi = lo + slice < len ? lo + slice : len;
+                if (hi == lo) break;
+                crc = sg_crc_multmodp(hi - lo == slice ? xs : sg_crc_x8n(x2n, hi - lo), crc) ^ part[t];
+            }
             const uint32_t total = len + 31u;
             const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1u) & 0xffu), (uint8_t)((total - 1u) >> 8)};
             for (int k = 0; k < 18; k++) o[k] = hdr[k];
@@ -2279,6 +2327,7 @@ sg_bgzf_kernel(const uint8_t *in, unsigned long long nBytes, uint8_t *out, unsig
             t[0] = (uint8_t)crc; t[1] = (uint8_t)(crc >> 8); t[2] = (uint8_t)(crc >> 16); t[3] = (uint8_t)(crc >> 24);
             t[4] = (uint8_t)len; t[5] = (uint8_t)(len >> 8); t[6] = 0; t[7] = 0;
         }
+        __syncthreads();
     }
 }
 
