@@ -22,8 +22,9 @@
 extern "C" {
 #endif
 
-#define SNAPGPU_ABI_VERSION 5   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
-                                 * 4: snapgpu_sam_sort_device; 5: snapgpu_bam_markdup_device, snapgpu_bam_index_device */
+#define SNAPGPU_ABI_VERSION 6   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
+                                 * 4: snapgpu_sam_sort_device; 5: snapgpu_bam_markdup_device, snapgpu_bam_index_device;
+                                 * 6: snapgpu_align_single_secondary(_device) (-om) */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
@@ -91,7 +92,7 @@ typedef struct snapgpu_params {
     int32_t  maxScoreGapToPreferNonAltAlignment; /* (64) */
     int32_t  explorePopularSeeds;       /* -x (0) */
     int32_t  stopOnFirstHit;            /* -f (0) */
-    int32_t  maxSecondaryAlignmentAdditionalEditDistance; /* -om; only -1 (off) is supported */
+    int32_t  maxSecondaryAlignmentAdditionalEditDistance; /* -om (-1 = off); >= 0: single-end handles only, through snapgpu_align_single_secondary */
     int32_t  ignoreAlignmentAdjustmentsForOm; /* (1) -- AlignmentAdjuster is off by default; only 1 supported */
 } snapgpu_params;
 
@@ -290,6 +291,30 @@ int  snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_ba
                                  const uint64_t *d_offsets, const uint32_t *d_lens,
                                  snapgpu_single_result *d_results, snapgpu_counters *d_counters,
                                  void *cudaStream);
+
+/*
+ * Secondary alignments, `snap single -om <d> [-omax <n>] [-mpc <n>]`: what AlignRead does when its caller passes a secondaryResults
+ * buffer (reference SNAPLib/SingleAligner.cpp:250-318; recording in ScoreSet::updateBestScore, BaseAligner.cpp:2143-2299; pruning in
+ * BaseAligner::finalizeSecondaryResults, :2422-2553).  The handle must have been created with
+ * params.maxSecondaryAlignmentAdditionalEditDistance = <d> >= 0 (and <= extraSearchDepth, AlignerContext.cpp:784); such a handle only
+ * takes these two calls.  maxSecondaryAlignments = -omax (0x7fffffff = no limit), maxSecondaryAlignmentsPerContig = -mpc (<= 0 = no limit).
+ * results[n]: the primary results (they can differ from a run without -om: the "MAPQ cannot recover" early stop is off, :1512).
+ * secondary[n * secondaryCapacityPerRead]: read i's secondary results at [i * secondaryCapacityPerRead, +nSecondary[i]), in the order the
+ * reference leaves them in its buffer.  nSecondary[i] < 0: read i has -nSecondary[i] of them and they did not fit -- none were written;
+ * call again with at least that capacity (the reference's caller doubles its buffer and calls AlignRead again, SingleAligner.cpp:250-263).
+ */
+int  snapgpu_align_single_secondary(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals,
+                                    const uint64_t *offsets, const uint32_t *lens, snapgpu_single_result *results,
+                                    int32_t maxSecondaryAlignments, int32_t maxSecondaryAlignmentsPerContig,
+                                    int64_t secondaryCapacityPerRead, snapgpu_single_result *secondary, int32_t *nSecondary,
+                                    snapgpu_counters *counters);
+/* Device-pointer form (see snapgpu_align_single_device).  A worker whose raw record buffer fills up latches an error that
+ * snapgpu_aligner_check() reports (the host form grows the buffers and aligns the batch again by itself). */
+int  snapgpu_align_single_secondary_device(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals,
+                                           const uint64_t *d_offsets, const uint32_t *d_lens, snapgpu_single_result *d_results,
+                                           int32_t maxSecondaryAlignments, int32_t maxSecondaryAlignmentsPerContig,
+                                           int64_t secondaryCapacityPerRead, snapgpu_single_result *d_secondary, int32_t *d_nSecondary,
+                                           snapgpu_counters *d_counters, void *cudaStream);
 
 /*
  * Paired-end aligner handle: the ChimericPairedEndAligner(IntersectingPairedEndAligner) stack that

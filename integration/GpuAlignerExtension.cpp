@@ -21,7 +21,7 @@
  *   single: SingleAligner.cpp:197-338 (pre-filter :213, AlignRead :250, passFilter + writeReads :296-322, updateStats :354-374)
  *   paired: PairedAligner.cpp:654-927 (id check :664, useful0/1 :676-678, align :727, forceSpacing :822, passFilter :832-850,
  *           writePairs :870, updateStats :962-1010)
- * Not supported (fails loudly, never falls back to the CPU aligner): secondary alignments (-om), 64-bit indexes, -ins.
+ * Not supported (fails loudly, never falls back to the CPU aligner): secondary alignments (-om) of `paired`, 64-bit indexes, -ins.
  */
 #include "stdafx.h"
 #include "Compat.h"
@@ -44,6 +44,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
 
 #include "../include/snapgpu.h"
 
@@ -289,8 +290,8 @@ GpuEngine *GpuAlignerExtension::engineForThisThread(AlignerContext *context, boo
 {
     pthread_mutex_lock(&shared->lock);
     if (!shared->opened) {
-        if (context->maxSecondaryAlignmentAdditionalEditDistance >= 0) {
-            WriteErrorMessage("snap-aligner-gpu: secondary alignments (-om) are not supported by the GPU engine\n");
+        if (context->maxSecondaryAlignmentAdditionalEditDistance >= 0 && paired) {
+            WriteErrorMessage("snap-aligner-gpu: secondary alignments (-om) are supported for `single` only\n");
             soft_exit(1);
         }
         if (context->index == NULL || context->index->doesGenomeIndexHave64BitLocations()) {
@@ -386,6 +387,16 @@ bool GpuAlignerExtension::runIterationThread(ReadSupplier *supplier, AlignerCont
     if (!results) gpuFatal("allocating the result batch");
     snapgpu_counters counters;
     memset(&counters, 0, sizeof(counters));
+    const bool om = context->maxSecondaryAlignmentAdditionalEditDistance >= 0;
+    _int64 secCap = 31;              // SingleAligner.cpp:141: a buffer of 32 results, the first being the primary
+    snapgpu_single_result *secondary = NULL;
+    int32_t *nSecondary = NULL;
+    std::vector<SingleAlignmentResult> alignmentResults(1);
+    if (om) {
+        secondary = (snapgpu_single_result *)snapgpu_host_alloc((size_t)shared->batchReads * (size_t)secCap * sizeof(snapgpu_single_result));
+        nSecondary = (int32_t *)snapgpu_host_alloc((size_t)shared->batchReads * sizeof(int32_t));
+        if (!secondary || !nSecondary) gpuFatal("allocating the secondary-result batch");
+    }
 
     Read *read = supplier->getNextRead();
     while (read != NULL) {
@@ -395,9 +406,33 @@ bool GpuAlignerExtension::runIterationThread(ReadSupplier *supplier, AlignerCont
             read = supplier->getNextRead();
         }
         pthread_mutex_lock(&engine->lock);
-        const int rc = snapgpu_align_single(engine->aligner, batch.n, batch.bases, batch.quals, batch.offsets, batch.lens, results, &counters);
+        int rc;
+        if (om) {
+            // -om: the primary results plus, per read, up to secCap secondary ones; a read with more reports minus its count and the
+            // batch is aligned again with room for it (SingleAligner.cpp:250-263 doubles its buffer per read)
+            for (;;) {
+                snapgpu_counters c;
+                memset(&c, 0, sizeof(c));
+                rc = snapgpu_align_single_secondary(engine->aligner, batch.n, batch.bases, batch.quals, batch.offsets, batch.lens, results,
+                                                    context->maxSecondaryAlignments, context->maxSecondaryAlignmentsPerContig, secCap, secondary, nSecondary, &c);
+                if (rc) break;
+                _int64 need = 0;
+                for (_int64 i = 0; i < batch.n; i++) if (-(_int64)nSecondary[i] > need) need = -(_int64)nSecondary[i];
+                if (need == 0) {
+                    _int64 *dst = (_int64 *)&counters; const _int64 *src = (const _int64 *)&c;
+                    for (size_t k = 0; k < sizeof(c) / sizeof(_int64); k++) dst[k] += src[k];
+                    break;
+                }
+                while (secCap < need) secCap *= 2;
+                snapgpu_host_free(secondary);
+                secondary = (snapgpu_single_result *)snapgpu_host_alloc((size_t)shared->batchReads * (size_t)secCap * sizeof(snapgpu_single_result));
+                if (!secondary) gpuFatal("allocating the secondary-result batch");
+            }
+        } else {
+            rc = snapgpu_align_single(engine->aligner, batch.n, batch.bases, batch.quals, batch.offsets, batch.lens, results, &counters);
+        }
         pthread_mutex_unlock(&engine->lock);
-        if (rc) gpuFatal("snapgpu_align_single");
+        if (rc) gpuFatal(om ? "snapgpu_align_single_secondary" : "snapgpu_align_single");
 
         for (_int64 i = 0; i < batch.n; i++) {
             Read *r = &batch.reads[i];
@@ -421,6 +456,35 @@ bool GpuAlignerExtension::runIterationThread(ReadSupplier *supplier, AlignerCont
             }
             toSnap(results[i], &result);
             bool containsPrimary = true;
+            if (om) {
+                // SingleAligner.cpp:292-322: every result through the filter (the last one moves into a hole), then one writeReads call
+                _int64 nSec = nSecondary[i];
+                alignmentResults.resize((size_t)nSec + 1);
+                alignmentResults[0] = result;
+                for (_int64 k = 0; k < nSec; k++) {
+                    memset(&alignmentResults[(size_t)k + 1], 0, sizeof(SingleAlignmentResult));
+                    toSnap(secondary[i * secCap + k], &alignmentResults[(size_t)k + 1]);
+                }
+                if (NULL != readWriter) {
+                    for (_int64 k = 0; k <= nSec; k++) {
+                        if (!options->passFilter(r, alignmentResults[(size_t)k].status, false, k != 0 || !containsPrimary)) {
+                            if (k == 0) containsPrimary = false;
+                            alignmentResults[(size_t)k] = alignmentResults[(size_t)nSec];
+                            nSec--;
+                            k--;
+                        }
+                    }
+                    stats->extraAlignments += nSec + (containsPrimary ? 0 : 1);
+                    readWriter->writeReads(context->readerContext, r, alignmentResults.data(), nSec + 1, containsPrimary, context->useAffineGap);
+                }
+                if (containsPrimary) {
+                    updateSingleStats(stats, result.status, result.mapq);          // :330-334 (alignmentResults[0] is still the primary when containsPrimary)
+                } else {
+                    stats->filtered++;
+                }
+                this->writeRead(r, &result);
+                continue;
+            }
             if (NULL != readWriter) {
                 // SingleAligner.cpp:296-322 with nSecondaryResults == 0
                 if (!options->passFilter(r, result.status, false, false)) {
@@ -443,6 +507,8 @@ bool GpuAlignerExtension::runIterationThread(ReadSupplier *supplier, AlignerCont
     addCounters(engine, counters);
     batch.destroy();
     snapgpu_host_free(results);
+    snapgpu_host_free(secondary);
+    snapgpu_host_free(nSecondary);
     return true;             // this thread's share is consumed: the stock loop is skipped (SingleAligner.cpp:102-105)
 }
 

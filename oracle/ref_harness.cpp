@@ -646,6 +646,95 @@ int ref_single_align(void *v, _int64 n, const char *bases, const char *quals, co
 }
 
 /*
+ * The same loop with secondary alignments on (`-om`): AlignRead with a secondaryResults buffer that doubles when it overflows, exactly
+ * SingleAligner.cpp:137-142 and :250-263.  The aligner must have been created with maxSecondaryAlignmentsPerContig (see
+ * ref_single_create_om).  secondary[i * capacityPerRead ...] receives read i's records in buffer order; nSecondary[i] < 0 = -count when
+ * they do not fit.
+ */
+void *ref_single_create_om(void *vidx, const snapgpu_params *p, int maxSecondaryAlignmentsPerContig)
+{
+    ref_init();
+    GenomeIndex *index = (GenomeIndex *)vidx;
+    RefSingle *rs = new RefSingle;
+    rs->index = index;
+    rs->params = *p;
+    int maxReadSize = MAX_READ_LENGTH;
+    rs->allocator = new BigAllocator(BaseAligner::getBigAllocatorReservation(index, true, p->maxHits, maxReadSize, index->getSeedLength(),
+                                        p->numSeedsFromCommandLine, p->seedCoverage, maxSecondaryAlignmentsPerContig, p->extraSearchDepth) + 4096, 16);
+    DisabledOptimizations dis;
+    dis.noUkkonen = p->noUkkonen != 0;
+    dis.noOrderedEvaluation = p->noOrderedEvaluation != 0;
+    dis.noTruncation = p->noTruncation != 0;
+    dis.noEditDistance = p->noEditDistance != 0;
+    dis.noBandedAffineGap = p->noBandedAffineGap != 0;
+    rs->aligner = new (rs->allocator) BaseAligner(index, p->maxHits, p->maxDist, maxReadSize, p->numSeedsFromCommandLine, p->seedCoverage,
+        p->minWeightToCheck, p->extraSearchDepth, dis, p->useAffineGap != 0, p->ignoreAlignmentAdjustmentsForOm != 0,
+        p->altAwareness != 0, /*emitALT*/false, p->maxScoreGapToPreferNonAltAlignment, maxSecondaryAlignmentsPerContig,
+        NULL, NULL, p->matchReward, p->subPenalty, p->gapOpenPenalty, p->gapExtendPenalty, p->fivePrimeEndBonus, p->threePrimeEndBonus,
+        NULL, rs->allocator);
+    rs->aligner->setExplorePopularSeeds(p->explorePopularSeeds != 0);
+    rs->aligner->setStopOnFirstHit(p->stopOnFirstHit != 0);
+    return rs;
+}
+
+int ref_single_align_om(void *v, _int64 n, const char *bases, const char *quals, const _uint64 *offsets, const unsigned *lens,
+                        snapgpu_single_result *results, int maxSecondaryAlignments, _int64 capacityPerRead, snapgpu_single_result *secondary,
+                        int *nSecondaryOut, snapgpu_counters *counters)
+{
+    RefSingle *rs = (RefSingle *)v;
+    const snapgpu_params *p = &rs->params;
+    g_index = rs->index;            // SingleAlignmentResult::compareByContigAndScore reads it (AlignmentResult.cpp:31)
+    snapgpu_counters local;
+    memset(&local, 0, sizeof(local));
+    _int64 bufferCount = 32;
+    SingleAlignmentResult *buf = (SingleAlignmentResult *)BigAlloc(sizeof(SingleAlignmentResult) * bufferCount);
+    for (_int64 i = 0; i < n; i++) {
+        Read read;
+        read.init("r", 1, bases + offsets[i], quals + offsets[i], lens[i], NULL, 0);
+        SingleAlignmentResult alt;
+        memset(&alt, 0, sizeof(alt));
+        memset(buf, 0, sizeof(SingleAlignmentResult) * bufferCount);
+        nSecondaryOut[i] = 0;
+        local.totalReads++;
+        if (read.getDataLength() < p->minReadLength || read.countOfNs() > (int)p->maxDist) {
+            buf[0].status = NotFound;
+            buf[0].location = InvalidGenomeLocation;
+            buf[0].mapq = 0;
+            buf[0].direction = FORWARD;
+            local.uselessReads++;
+            copy_result(&buf[0], &results[i]);
+            continue;
+        }
+        _int64 nSecondary = 0;
+        while (!rs->aligner->AlignRead(&read, buf, &alt, p->maxSecondaryAlignmentAdditionalEditDistance, bufferCount - 1, &nSecondary, maxSecondaryAlignments,
+                                       buf + 1, 0, NULL, NULL)) {
+            BigDealloc(buf);
+            bufferCount *= 2;
+            buf = (SingleAlignmentResult *)BigAlloc(sizeof(SingleAlignmentResult) * bufferCount);
+            memset(buf, 0, sizeof(SingleAlignmentResult) * bufferCount);
+        }
+        copy_result(&buf[0], &results[i]);
+        if (nSecondary <= capacityPerRead) {
+            for (_int64 k = 0; k < nSecondary; k++) copy_result(&buf[1 + k], &secondary[i * capacityPerRead + k]);
+            nSecondaryOut[i] = (int)nSecondary;
+        } else {
+            nSecondaryOut[i] = -(int)nSecondary;
+        }
+        if (buf[0].status == SingleHit) local.singleHits++;
+        else if (buf[0].status == MultipleHits) local.multiHits++;
+        else local.notFound++;
+        if (buf[0].status != NotFound && buf[0].mapq >= 0 && buf[0].mapq <= 70) local.mapqHistogram[buf[0].mapq]++;
+    }
+    BigDealloc(buf);
+    if (counters) {
+        _int64 *dst = (_int64 *)counters;
+        const _int64 *src = (const _int64 *)&local;
+        for (size_t i = 0; i < sizeof(local) / sizeof(_int64); i++) dst[i] += src[i];
+    }
+    return 0;
+}
+
+/*
  * Multi-threaded variant: nThreads pthreads, each with its own BaseAligner over a contiguous range, the
  * way ParallelTask.h:40-120 runs SingleAlignerContext::runIterationThread.  Used for the CPU baseline.
  * Returns wall seconds spent aligning (aligner construction excluded, like AlignerContext.cpp:420).

@@ -132,6 +132,9 @@ def _load(path):
     L.ref_single_create.argtypes = [C.c_void_p, C.POINTER(Params)]
     L.ref_single_destroy.argtypes = [C.c_void_p]
     L.ref_single_align.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    L.ref_single_create_om.restype = C.c_void_p
+    L.ref_single_create_om.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int]
+    L.ref_single_align_om.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ref_single_align_mt.restype = C.c_double
     L.ref_single_align_mt.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int64] + [C.c_void_p] * 6
     L.ref_lookup_seed.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
@@ -224,6 +227,26 @@ class RefSingleAligner:
         if self.handle:
             lib().ref_single_destroy(self.handle)
             self.handle = None
+
+
+class RefSecondaryAligner(RefSingleAligner):
+    """`snap single -om` (params.maxSecondaryAlignmentAdditionalEditDistance >= 0): AlignRead with a secondaryResults buffer that doubles on
+    overflow, as SingleAligner.cpp:137-142 / :250-263."""
+
+    def __init__(self, index: RefIndex, params: Params, max_secondary: int = 0x7fffffff, max_per_contig: int = -1):
+        self.index = index
+        self.params = params
+        self.max_secondary = max_secondary
+        self.handle = lib().ref_single_create_om(index.handle, C.byref(params), max_per_contig)
+
+    def align(self, batch, capacity: int = 64):
+        res = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        sec = np.zeros((batch.n, capacity), dtype=RESULT_DTYPE)
+        nsec = np.zeros(batch.n, dtype=np.int32)
+        ctr = np.zeros(N_COUNTERS, dtype=np.int64)
+        lib().ref_single_align_om(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(res),
+                                  self.max_secondary, capacity, _p(sec), _p(nsec), _p(ctr))
+        return res, sec, nsec, counters_dict(ctr)
 
 
 def align_mt(index: RefIndex, params: Params, batch, threads: int, reps: int = 1):

@@ -129,6 +129,58 @@ struct SgScoreSet {                  // BaseAligner::ScoreSet, BaseAligner.h:260
         }
         return true;
     }
+    // ScoreSet::updateBestScore with a secondaryResults buffer and candidatesForAffineGap == NULL (`-om` on the single-end path, :1457-1467):
+    // the displaced best (:2176-2200) or the near-best candidate (:2247-2271) is appended when it is within
+    // maxEditDistanceForSecondaryResults of the best.  Returns false when the buffer is full (*overflowedSecondaryBuffer, :2177-2180).
+    SG_HD bool updateBestScoreSecondary(int64_t genomeLocation, int64_t origGenomeLocation, unsigned score, bool useAffineGap, int agScore,
+                                        double matchProbability, const SgElem *el, snapgpu_single_result *sec, int *nSec, int maxSec, int maxEditDistanceForSecondaryResults) {
+        bool seenNewBestScore;
+        if (useAffineGap) {
+            seenNewBestScore = (agScore > bestScoreAGScore) || (bestScoreAGScore == agScore && matchProbability > probabilityOfBestCandidate);
+        } else {
+            seenNewBestScore = (score < (unsigned)bestScore) || (score == (unsigned)bestScore && matchProbability > probabilityOfBestCandidate);
+        }
+        if (seenNewBestScore) {
+            if ((unsigned)bestScore >= score) {
+                if ((int)((unsigned)bestScore - score) <= maxEditDistanceForSecondaryResults) {
+                    if (maxSec <= *nSec) return false;
+                    snapgpu_single_result *r = &sec[*nSec];
+                    r->direction = bestScoreDirection; r->location = bestScoreGenomeLocation; r->origLocation = bestScoreOrigGenomeLocation;
+                    r->mapq = 0; r->score = bestScore; r->status = SNAPGPU_MULTIPLE_HITS; r->clippingForReadAdjustment = 0;
+                    r->usedAffineGapScoring = bestScoreUsedAffineGapScoring; r->basesClippedBefore = bestScoreBasesClippedBefore;
+                    r->basesClippedAfter = bestScoreBasesClippedAfter; r->agScore = bestScoreAGScore; r->matchProbability = bestScoreMatchProbability;
+                    r->seedOffset = bestScoreSeedOffset;
+                    r->scorePriorToClipping = 0; r->supplementary = 0; r->probabilityAllCandidates = 0; r->popularSeedsSkipped = 0; r->reserved = 0;
+                    (*nSec)++;
+                }
+            }
+            bestScore = (int)score;
+            bestScoreAGScore = agScore;
+            probabilityOfBestCandidate = matchProbability;
+            bestScoreGenomeLocation = genomeLocation;
+            bestScoreOrigGenomeLocation = origGenomeLocation;
+            bestScoreDirection = el->direction;
+            bestScoreUsedAffineGapScoring = el->usedAffineGapScoring;
+            bestScoreBasesClippedBefore = el->basesClippedBefore;
+            bestScoreBasesClippedAfter = el->basesClippedAfter;
+            bestScoreSeedOffset = el->seedOffset;
+            bestScoreMatchProbability = el->matchProbabilityForBestScore;
+        } else {
+            if (-1 != maxEditDistanceForSecondaryResults && (int)((unsigned)bestScore - score) <= maxEditDistanceForSecondaryResults &&
+                score != (unsigned)SG_SCORE_ABOVE_LIMIT && (unsigned)bestScore >= score) {
+                if (maxSec <= *nSec) return false;
+                snapgpu_single_result *r = &sec[*nSec];
+                r->direction = el->direction; r->location = genomeLocation; r->origLocation = origGenomeLocation;
+                r->mapq = 0; r->score = (int)score; r->status = SNAPGPU_MULTIPLE_HITS; r->clippingForReadAdjustment = 0;
+                r->usedAffineGapScoring = el->usedAffineGapScoring; r->basesClippedBefore = el->basesClippedBefore;
+                r->basesClippedAfter = el->basesClippedAfter; r->agScore = el->agScore; r->seedOffset = el->seedOffset;
+                r->matchProbability = el->matchProbabilityForBestScore;
+                r->scorePriorToClipping = 0; r->supplementary = 0; r->probabilityAllCandidates = 0; r->popularSeedsSkipped = 0; r->reserved = 0;
+                (*nSec)++;
+            }
+        }
+        return true;
+    }
     SG_HD void initFrom(const snapgpu_single_result *r) {               // ScoreSet::init(SingleAlignmentResult*), :2116-2130
         bestScore = r->score; bestScoreGenomeLocation = r->location; bestScoreOrigGenomeLocation = r->origLocation;
         bestScoreDirection = r->direction; bestScoreUsedAffineGapScoring = r->usedAffineGapScoring;
@@ -190,6 +242,11 @@ struct SgAligner {
     snapgpu_single_result *agCands; int nAgCands, maxAgCands; int agCandsOverflow;
     SgScoreSet wsAll, wsNonAlt; snapgpu_single_result wsKey;     // working storage of alignAffineGap (stack objects in the reference)
     int deferred;                    // set by the DEFER instantiation when the read needs affine-gap scoring (see sg_align_read_t)
+    // secondary alignments (`-om`; the SEC instantiation only): the caller's secondaryResults buffer and the three options that shape it
+    snapgpu_single_result *secResults; int nSec, maxSec, secOverflow;
+    int secMaxEditDist;              // maxEditDistanceForSecondaryResults = -om
+    int secMaxResults;               // maxSecondaryResults = -omax
+    int secMaxPerContig;             // maxSecondaryAlignmentsPerContig = -mpc (<= 0: no limit)
 
     // ---- weight lists: doubly linked FIFO per weight; link values are element indices or SG_SENTINEL+w ----
     SG_HD uint32_t getNext(uint32_t n) const { return (n & SG_SENTINEL) ? sc.listNext[n & ~SG_SENTINEL] : sc.pool[n].weightNext; }
@@ -454,7 +511,10 @@ SG_HDN void sg_score_candidate(SgAligner &A, const SgElem &el, int64_t genomeLoc
 }
 
 // BaseAligner::score (:917-1534).  Returns true iff a result was reached.
-template <bool HAM, bool DEFER>
+// SEC: the caller gave a secondaryResults buffer (`-om`): candidates within A.secMaxEditDist of the best are recorded as they are scored and the
+// "nothing can rescue MAPQ" stop (:1512) is off; an overflow of the buffer sets A.secOverflow and ends the read (the reference returns false
+// from AlignRead and its caller starts over with a larger buffer, SingleAligner.cpp:250-263).
+template <bool HAM, bool DEFER, bool SEC = false>
 SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *primaryResult)
 {
     const bool useHamming = HAM;
@@ -590,6 +650,16 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                                                                A.agCands, &A.nAgCands, A.maxAgCands, (int)pr.extraSearchDepth);
                     }
                     if (!ok || A.nAgCands >= A.maxAgCands) { A.agCandsOverflow = 1; return true; }      // :1475-1478 (the reference returns false = overflow)
+                } else if (SEC) {
+                    // :1457-1467: both score sets append to the same secondaryResults buffer (so, without ALT contigs, every record appears twice --
+                    // the reference's own behaviour); the third call (:1480-1486) passes no buffer and finds nothing left to update
+                    bool ok = A.all.updateBestScoreSecondary(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el,
+                                                             A.secResults, &A.nSec, A.maxSec, A.secMaxEditDist);
+                    if (ok && genomeLocationIsNonALT) {
+                        ok = A.nonAlt.updateBestScoreSecondary(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el,
+                                                               A.secResults, &A.nSec, A.maxSec, A.secMaxEditDist);
+                    }
+                    if (!ok) { A.secOverflow = 1; return true; }                                        // :1471-1473
                 } else {
                     A.all.updateBestScore(genomeLocation, origGenomeLocation, score, pr.useAffineGap != 0, cs.agScore, matchProbability, &el);
                     if (genomeLocationIsNonALT) {
@@ -604,7 +674,7 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
                     primaryResult->mapq = 0;
                     return true;
                 }
-                if ((pr.altAwareness ? A.nonAlt.probabilityOfAllCandidates : A.all.probabilityOfAllCandidates) >= 4.9) {
+                if ((pr.altAwareness ? A.nonAlt.probabilityOfAllCandidates : A.all.probabilityOfAllCandidates) >= 4.9 && (!SEC || -1 == A.secMaxEditDist)) {
                     (pr.altAwareness ? A.nonAlt : A.all).fillIn(T, primaryResult, (int)A.popularSeedsSkipped);
                     return true;
                 }
@@ -619,9 +689,90 @@ SG_HDN bool sg_score(SgAligner &A, bool forceResult, snapgpu_single_result *prim
     return false;
 }
 
+// BaseAligner::finalizeSecondaryResults (:2422-2553) with ignoreAlignmentAdjustmentsForOm (the default; the adjuster is not implemented, sg_derive_params
+// refuses it): drop what is no longer within -om of the best (the last record moves into the hole, :2468-2485), cap the records per contig
+// (-mpc, :2487-2547) and the total (-omax, :2549-2552).  The two qsort() calls are glibc's merge sort, i.e. stable: insertion sorts here.
+SG_HDN void sg_finalize_secondary(SgAligner &A, snapgpu_single_result *primaryResult)
+{
+    const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr;
+    snapgpu_single_result *sec = A.secResults;
+    int n = A.nSec;
+    const int bestScore = primaryResult->score;
+    const int bound = bestScore + A.secMaxEditDist;
+    const int worstScoreToKeep = (int)A.maxK < bound ? (int)A.maxK : bound;
+    int i = 0;
+    while (i < n) {
+        if (sec[i].score > worstScoreToKeep) {
+            sec[i] = sec[n - 1];
+            n--;
+        } else {
+            sec[i].scorePriorToClipping = sec[i].score;
+            sec[i].supplementary = (pr.altAwareness && A.isALT(sec[i].location)) ? 1 : 0;
+            i++;
+        }
+    }
+    if (A.secMaxPerContig > 0 && primaryResult->status != SNAPGPU_NOT_FOUND) {
+        // Genome::getContigNumAtLocation (Genome.cpp:573-600) is a binary search over the contigs' beginningLocation
+        #define SG_CONTIG_OF(LOC, OUT) { int lo_ = 0, hi_ = (int)ix.nContigs - 1; OUT = -1; const int64_t l_ = (LOC); \
+            while (lo_ <= hi_) { const int mid_ = (lo_ + hi_) / 2; const int64_t b_ = ix.contigStart[mid_]; \
+                if (b_ <= l_ && (mid_ == (int)ix.nContigs - 1 || ix.contigStart[mid_ + 1] > l_)) { OUT = mid_; break; } \
+                else if (b_ <= l_) lo_ = mid_ + 1; else hi_ = mid_ - 1; } }
+        int primaryContig; SG_CONTIG_OF(primaryResult->location, primaryContig);
+        // :2498-2511 counts per contig with an epoch-stamped array; what matters is only whether any contig (the primary's starts at one) exceeds the cap
+        bool anyContigHasTooManyResults = false;
+        for (i = 0; i < n && !anyContigHasTooManyResults; i++) {
+            int ci; SG_CONTIG_OF(sec[i].location, ci);
+            int hits = (ci == primaryContig) ? 1 : 0;
+            for (int j = 0; j <= i; j++) { int cj; SG_CONTIG_OF(sec[j].location, cj); if (cj == ci) hits++; }
+            if (hits > A.secMaxPerContig) anyContigHasTooManyResults = true;
+        }
+        if (anyContigHasTooManyResults) {
+            // qsort(compareByContigAndScore), AlignmentResult.cpp:29-50
+            for (i = 1; i < n; i++) {
+                snapgpu_single_result &key = A.wsKey;
+                key = sec[i];
+                int ck; SG_CONTIG_OF(key.location, ck);
+                int j = i - 1;
+                for (; j >= 0; j--) {
+                    int cj; SG_CONTIG_OF(sec[j].location, cj);
+                    if (cj > ck || (cj == ck && sec[j].score > key.score)) sec[j + 1] = sec[j]; else break;
+                }
+                sec[j + 1] = key;
+            }
+            int currentContigNum = -1, currentContigCount = 0, destResult = 0;
+            for (int sourceResult = 0; sourceResult < n; sourceResult++) {
+                int contigNum; SG_CONTIG_OF(sec[sourceResult].location, contigNum);
+                if (contigNum != currentContigNum) {
+                    currentContigNum = contigNum;
+                    currentContigCount = (contigNum == primaryContig) ? 1 : 0;
+                }
+                currentContigCount++;
+                if (currentContigCount <= A.secMaxPerContig) {
+                    if (destResult != sourceResult) sec[destResult] = sec[sourceResult];
+                    destResult++;
+                }
+            }
+            n = destResult;
+        }
+        #undef SG_CONTIG_OF
+    }
+    if (n > A.secMaxResults) {
+        // qsort(compareByScore), AlignmentResult.cpp:53-65, then truncate
+        for (i = 1; i < n; i++) {
+            snapgpu_single_result &key = A.wsKey;
+            key = sec[i];
+            int j = i - 1;
+            while (j >= 0 && sec[j].score > key.score) { sec[j + 1] = sec[j]; j--; }
+            sec[j + 1] = key;
+        }
+        n = A.secMaxResults;
+    }
+    A.nSec = n;
+}
+
 // BaseAligner::AlignRead (:272-763) for one read with the stock loop's arguments (SingleAligner.cpp:250).
 // `result` must be caller-zeroed POD; on return it holds what the reference would have put in primaryResult.
-template <bool HAM, bool DEFER = false>
+template <bool HAM, bool DEFER = false, bool SEC = false>
 SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult)
 {
     const SgIndexView &ix = *A.ix; const SgParams &pr = *A.pr; const SgTables &T = *A.tb;
@@ -651,6 +802,7 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
     A.nAddedToHashTable = 0;
     A.readLen = readLen;
     if (DEFER) A.deferred = 0;
+    if (SEC) { A.nSec = 0; A.secOverflow = 0; }            // :318-320
 
     if ((int)readLen < (int)seedLen) {
         return;                      // :360-366, "hopeless"
@@ -723,8 +875,9 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
         if (nextSeedToTest >= nPossibleSeeds) {
             A.wrapCount++;
             if (A.wrapCount >= seedLen) {
-                sg_score<HAM, DEFER>(A, true, primaryResult);
+                sg_score<HAM, DEFER, SEC>(A, true, primaryResult);
                 primaryResult->scorePriorToClipping = primaryResult->score;     // finalizeSecondaryResults, :2442
+                if (SEC && !A.secOverflow) sg_finalize_secondary(A, primaryResult);
                 return;
             }
             nextSeedToTest = T.wrapSeed[A.wrapCount];
@@ -804,14 +957,16 @@ SG_HDN void sg_align_read_t(SgAligner &A, const uint8_t *readData, const uint8_t
         nextSeedToTest += seedLen;
 
         if (appliedEitherSeed) {
-            if (sg_score<HAM, DEFER>(A, false, primaryResult)) {
+            if (sg_score<HAM, DEFER, SEC>(A, false, primaryResult)) {
                 primaryResult->scorePriorToClipping = primaryResult->score;
+                if (SEC && !A.secOverflow) sg_finalize_secondary(A, primaryResult);
                 return;
             }
         }
     }
-    sg_score<HAM, DEFER>(A, true, primaryResult);
+    sg_score<HAM, DEFER, SEC>(A, true, primaryResult);
     primaryResult->scorePriorToClipping = primaryResult->score;
+    if (SEC && !A.secOverflow) sg_finalize_secondary(A, primaryResult);
 }
 
 SG_HD void sg_align_read(SgAligner &A, const uint8_t *readData, const uint8_t *readQuality, uint32_t readLen, snapgpu_single_result *primaryResult,

@@ -289,7 +289,10 @@ static inline uint32_t sg_next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) 
 static inline bool sg_derive_params(const snapgpu_params &in, unsigned seedLen, uint32_t maxReadLen, SgParams &p, std::string &err)
 {
     if (in.struct_size != sizeof(snapgpu_params)) { err = "snapgpu_params.struct_size mismatch (ABI)"; return false; }
-    if (in.maxSecondaryAlignmentAdditionalEditDistance != -1) { err = "secondary alignments (-om) are not supported"; return false; }
+    if (in.maxSecondaryAlignmentAdditionalEditDistance < -1) { err = "maxSecondaryAlignmentAdditionalEditDistance (-om) must be -1 (off) or >= 0"; return false; }
+    if (in.maxSecondaryAlignmentAdditionalEditDistance > (int)in.extraSearchDepth) {
+        err = "the max edit distance for secondary alignments (-om) cannot be bigger than the max search depth (-D)"; return false;      // AlignerContext.cpp:784-788
+    }
     if (!in.ignoreAlignmentAdjustmentsForOm) { err = "alignment adjustment (-ae) is not supported"; return false; }
     if ((unsigned)in.subPenalty > (unsigned)(in.gapOpenPenalty + in.gapExtendPenalty)) {
         err = "subPenalty must be < gapOpen + gapExtend"; return false;                    // BaseAligner.cpp:141-144
@@ -329,6 +332,7 @@ static inline bool sg_derive_paired_params(const snapgpu_params &in, const snapg
                                            SgParams &pr, SgParams &prSingle, SgPairedParams &pp, std::string &err)
 {
     if (pin.struct_size != sizeof(snapgpu_paired_params)) { err = "snapgpu_paired_params.struct_size mismatch (ABI)"; return false; }
+    if (in.maxSecondaryAlignmentAdditionalEditDistance != -1) { err = "paired path: secondary alignments (-om) are not supported"; return false; }
     if (!sg_derive_params(in, seedLen, maxReadLen, pr, err)) return false;
     snapgpu_params s = in;
     s.maxDist = in.maxDist / 2;

@@ -126,6 +126,9 @@ struct snapgpu_aligner {
     } slot[2];
     snapgpu_counters *h_counters = nullptr, *d_counters = nullptr;
     int64_t launches = 0;
+    // `-om` (snapgpu_align_single_secondary*): one raw secondary-result buffer of secRawCap records per worker, grown on demand
+    snapgpu_single_result *d_secRaw = nullptr;
+    int secRawCap = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -379,6 +382,118 @@ sg_align_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_consta
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(producersDone, 1u);
     }
+    if (counters && lane == 0) {
+        atomicAdd((unsigned long long *)&counters->totalReads, cTotal);
+        atomicAdd((unsigned long long *)&counters->uselessReads, cUseless);
+        atomicAdd((unsigned long long *)&counters->singleHits, cSingle);
+        atomicAdd((unsigned long long *)&counters->multiHits, cMulti);
+        atomicAdd((unsigned long long *)&counters->notFound, cNotFound);
+        atomicAdd((unsigned long long *)&counters->nHashTableLookups, (unsigned long long)A.work.lookups);
+        atomicAdd((unsigned long long *)&counters->nHashEntriesProbed, (unsigned long long)A.work.entriesProbed);
+        atomicAdd((unsigned long long *)&counters->nOverflowWordsRead, (unsigned long long)A.work.overflowWords);
+        atomicAdd((unsigned long long *)&counters->lvCalls, (unsigned long long)A.work.lvCalls);
+        atomicAdd((unsigned long long *)&counters->affineGapCalls, (unsigned long long)A.work.agCalls);
+        atomicAdd((unsigned long long *)&counters->nHitsIgnoredBecauseOfTooHighPopularity, (unsigned long long)A.work.popularIgnored);
+    }
+}
+
+
+// `-om`: sg_align_kernel's one-launch form with the SEC instantiation of the aligner (sg_align.h): every read also leaves its secondary
+// alignments.  A warp records them in its own raw buffer of secRawCap records (the reference's secondaryResults buffer) and, once
+// finalizeSecondaryResults has pruned them, copies the survivors to secondary[i * secCap ...): nSecondary[i] = their number, or minus their
+// number when they do not fit secCap (none copied: the caller asks again with more room).  A raw buffer that fills up latches error 4
+// (the reference's AlignRead returns false there and SingleAligner.cpp:250-263 doubles the buffer; the host entry point does the same).
+__global__ void __launch_bounds__(256, 4)
+sg_align_secondary_kernel(const __grid_constant__ SgIndexView ixParam, const __grid_constant__ SgParams prParam, const SgTables *tb, uint8_t *scratchBase,
+                          size_t scratchBytesPerWorker, long long n, const uint8_t *bases, const uint8_t *quals, const unsigned long long *offsets, const uint32_t *lens,
+                          snapgpu_single_result *results, snapgpu_counters *counters, unsigned long long *next, int *error,
+                          snapgpu_single_result *secRaw, int secRawCap, int secMaxEditDist, int secMaxResults, int secMaxPerContig,
+                          snapgpu_single_result *secondary, long long secCap, int32_t *nSecondary)
+{
+    const int lane = threadIdx.x & 31;
+    const long long worker = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ SgIndexView sIx;
+    __shared__ SgParams sPr;
+    __shared__ SgAligner sA[8];
+    __shared__ snapgpu_single_result sR[8];
+    __shared__ SgWarpSmall sW[8];
+    if (threadIdx.x == 0) { sIx = ixParam; sPr = prParam; }
+    __syncthreads();
+    const SgIndexView &ix = sIx; const SgParams &pr = sPr;
+    SgAligner &A = sA[threadIdx.x >> 5];
+    snapgpu_single_result &r = sR[threadIdx.x >> 5];
+    SgWarpSmall &W = sW[threadIdx.x >> 5];
+    A.ix = &ix; A.pr = &pr; A.tb = tb;
+    A.maxK = pr.maxK;
+    A.agCands = nullptr; A.nAgCands = 0; A.maxAgCands = 0; A.agCandsOverflow = 0;
+    A.secResults = secRaw + (size_t)worker * (size_t)secRawCap; A.nSec = 0; A.maxSec = secRawCap; A.secOverflow = 0;
+    A.secMaxEditDist = secMaxEditDist; A.secMaxResults = secMaxResults; A.secMaxPerContig = secMaxPerContig;
+    sg_scratch_carve(pr, scratchBase + (size_t)worker * scratchBytesPerWorker, &A.sc);
+    A.sc.lvLs = W.lvL; A.sc.lvAs = W.lvA; A.sc.lvSmallCells = SG_SMALL_LV_CELLS;
+    A.sc.lvBtMatchedS = W.btMatched; A.sc.lvBtDS = W.btD; A.sc.lvBtActionS = W.btAction; A.sc.lvBtSmall = SG_SMALL_BT;
+    A.sc.hitStage = (uint32_t *)W.lvL; A.sc.hitStageWords = SG_SMALL_LV_CELLS * 2 / 4; A.sc.hitBar = &W.hitBar; A.sc.hitPhase = 0;
+    __syncwarp();
+    sg_warp_hits_barrier_init(A.sc, lane);
+    uint8_t *const arenaStr[5] = {A.sc.rcRead, A.sc.rcQual, A.sc.revRead[0], A.sc.revRead[1], A.sc.seedUsed};
+    A.ag = sg_ag_params(pr.matchReward, pr.subPenalty, pr.gapOpenPenalty, pr.gapExtendPenalty, pr.fivePrimeEndBonus, pr.threePrimeEndBonus);
+    A.invalidLocation = SNAPGPU_INVALID_LOCATION_32;
+    A.nUsedElements = 0;
+    A.work.lookups = A.work.entriesProbed = A.work.overflowWords = A.work.lvCalls = A.work.agCalls = A.work.popularIgnored = 0;
+    __syncwarp();
+    unsigned long long cTotal = 0, cUseless = 0, cSingle = 0, cMulti = 0, cNotFound = 0;
+
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(next, 1ULL);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= (unsigned long long)n) break;
+        const uint8_t *rd = bases + offsets[i];
+        const uint8_t *rq = quals + offsets[i];
+        const uint32_t len = lens[i];
+        memset(&r, 0, sizeof(r));
+        cTotal++;
+        uint32_t countOfNs = 0;
+        #pragma unroll 1
+        for (uint32_t k = lane; k < len; k += 32) countOfNs += (rd[k] == 'N');
+        countOfNs = __reduce_add_sync(0xffffffffu, countOfNs);
+        if (len < pr.minReadLength || countOfNs > pr.maxK || len > pr.maxReadLen) {
+            r.status = SNAPGPU_NOT_FOUND; r.location = A.invalidLocation; r.mapq = 0; r.direction = SNAPGPU_FORWARD;
+            r.reserved = (len > pr.maxReadLen) ? 1u : 0u;
+            cUseless++;
+            if (lane == 0) { results[i] = r; nSecondary[i] = 0; }
+            continue;
+        }
+        {
+            const bool shortRead = len <= SG_SMALL_READ_LEN;
+            A.sc.rcRead = shortRead ? W.str[0] : arenaStr[0]; A.sc.rcQual = shortRead ? W.str[1] : arenaStr[1];
+            A.sc.revRead[0] = shortRead ? W.str[2] : arenaStr[2]; A.sc.revRead[1] = shortRead ? W.str[3] : arenaStr[3];
+            A.sc.seedUsed = shortRead ? W.seedUsed : arenaStr[4];
+            __syncwarp();
+        }
+        sg_align_read_t<false, false, true>(A, rd, rq, len, &r);
+        __syncwarp();
+        if (A.secOverflow) {
+            if (lane == 0) { atomicCAS(error, 0, 4); results[i] = r; nSecondary[i] = 0; }
+            continue;
+        }
+        const int nSec = A.nSec;
+        if ((long long)nSec <= secCap) {
+            // 88-byte records, word by word across the lanes
+            const uint32_t *src = (const uint32_t *)A.secResults;
+            uint32_t *dst = (uint32_t *)(secondary + (size_t)i * (size_t)secCap);
+            const int words = nSec * (int)(sizeof(snapgpu_single_result) / 4);
+            for (int w = lane; w < words; w += 32) dst[w] = src[w];
+        }
+        if (lane == 0) { results[i] = r; nSecondary[i] = ((long long)nSec <= secCap) ? nSec : -nSec; }
+        __syncwarp();
+        if (r.status == SNAPGPU_SINGLE_HIT) cSingle++;
+        else if (r.status == SNAPGPU_MULTIPLE_HITS) cMulti++;
+        else cNotFound++;
+        if (lane == 0 && counters && r.status != SNAPGPU_NOT_FOUND && r.mapq >= 0 && r.mapq <= 70) {
+            atomicAdd((unsigned long long *)&counters->mapqHistogram[r.mapq], 1ULL);
+        }
+    }
+    A.clearCandidates();
     if (counters && lane == 0) {
         atomicAdd((unsigned long long *)&counters->totalReads, cTotal);
         atomicAdd((unsigned long long *)&counters->uselessReads, cUseless);
@@ -1646,6 +1761,7 @@ void snapgpu_aligner_destroy(snapgpu_aligner *a)
         if (sl.evOut) cudaEventDestroy(sl.evOut);
     }
     cudaFreeHost(a->h_counters); cudaFree(a->d_counters);
+    cudaFree(a->d_secRaw);
     delete a;
 }
 
@@ -1801,6 +1917,7 @@ int snapgpu_aligner_check(snapgpu_aligner *a, void *cudaStream)
     if (code == 1) return sg_fail("paired aligner: a scoring candidate / mate / merge-anchor pool overflowed (the reference exits here too; raise -mcp / -H)");
     if (code == 2) return sg_fail("paired aligner: more than 4096 phase-4 affine-gap candidates for one pair (buffer growth is not implemented)");
     if (code == 3) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+    if (code == 4) return sg_fail("secondary alignments: a worker's raw record buffer overflowed (SNAPGPU_SECONDARY_RAW_CAP; the host entry point grows it by itself)");
     return sg_fail("aligner kernel reported an unknown error");
 }
 
@@ -1809,6 +1926,7 @@ int snapgpu_align_single_device(snapgpu_aligner *a, int64_t n, const char *d_bas
 {
     if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results) return sg_fail("null argument");
     if (a->paired) return sg_fail("snapgpu_align_single_device called on a paired-end aligner handle");
+    if (a->userParams.maxSecondaryAlignmentAdditionalEditDistance >= 0) return sg_fail("this handle was created with -om: call snapgpu_align_single_secondary_device");
     if (n < 0) return sg_fail("negative read count");
     if (n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads (the deferred-read list and arenas are sized from it)");
     if (n == 0) return 0;
@@ -1963,9 +2081,132 @@ int snapgpu_align_single(snapgpu_aligner *a, int64_t n, const char *bases, const
 {
     if (!a || !bases || !quals || !offsets || !lens || !results) return sg_fail("null argument");
     if (a->paired) return sg_fail("snapgpu_align_single called on a paired-end aligner handle");
+    if (a->userParams.maxSecondaryAlignmentAdditionalEditDistance >= 0) return sg_fail("this handle was created with -om: call snapgpu_align_single_secondary");
     if (n < 0 || n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads");
     if (n == 0) return 0;
     return align_host(a, n, 1, sizeof(snapgpu_single_result), bases, quals, offsets, lens, (uint8_t *)results, counters);
+}
+
+// ---- secondary alignments (`-om`) ----
+static int secondary_check(snapgpu_aligner *a, int64_t n, int32_t maxSecondaryAlignments, int64_t secondaryCapacityPerRead, const char *who)
+{
+    if (a->paired) return sg_fail(std::string(who) + " called on a paired-end aligner handle");
+    if (a->userParams.maxSecondaryAlignmentAdditionalEditDistance < 0) return sg_fail(std::string(who) + ": the handle was created without -om (maxSecondaryAlignmentAdditionalEditDistance < 0)");
+    if (n < 0 || n > a->maxBatchReads) return sg_fail("read count exceeds maxBatchReads");
+    if (maxSecondaryAlignments <= 0) return sg_fail("maxSecondaryAlignments (-omax) must be positive");       // AlignerOptions.cpp:619-624
+    if (secondaryCapacityPerRead < 0) return sg_fail("negative secondaryCapacityPerRead");
+    return 0;
+}
+
+static int secondary_reserve(snapgpu_aligner *a, int cap)
+{
+    if (a->d_secRaw && a->secRawCap >= cap) return 0;
+    SG_CUDA(cudaStreamSynchronize(a->stream));
+    if (a->d_secRaw) { cudaFree(a->d_secRaw); a->d_secRaw = nullptr; a->secRawCap = 0; }
+    SG_CUDA(cudaMalloc((void **)&a->d_secRaw, (size_t)a->nWorkers * (size_t)cap * sizeof(snapgpu_single_result)));
+    a->secRawCap = cap;
+    return 0;
+}
+
+static int launch_align_secondary(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals, const uint64_t *d_offsets, const uint32_t *d_lens,
+                                  snapgpu_single_result *d_results, int32_t maxSecondaryAlignments, int32_t maxSecondaryAlignmentsPerContig,
+                                  int64_t secondaryCapacityPerRead, snapgpu_single_result *d_secondary, int32_t *d_nSecondary, snapgpu_counters *d_counters, cudaStream_t st)
+{
+    if (!a->d_secRaw) {
+        int cap = 256;                   // records per worker; the reference starts at 32 per thread and doubles (SingleAligner.cpp:137-142, :259)
+        if (const char *e = getenv("SNAPGPU_SECONDARY_RAW_CAP")) cap = atoi(e) > 0 ? atoi(e) : cap;
+        if (secondary_reserve(a, cap)) return 1;
+    }
+    SG_CUDA(cudaMemsetAsync(a->d_next, 0, 8, st));
+    int64_t workers = (int64_t)a->numSMs * 4 * a->warpsPerBlock;
+    if (workers > a->nWorkers) workers = a->nWorkers;
+    if (workers > n) workers = n;
+    int blocks = (int)((workers + a->warpsPerBlock - 1) / a->warpsPerBlock);
+    if (blocks < 1) blocks = 1;
+    sg_align_secondary_kernel<<<blocks, a->warpsPerBlock * 32, 0, st>>>(a->index->view, a->params, a->index->d_tables_prob, a->d_scratch, a->scratchBytesPerWorker,
+        n, (const uint8_t *)d_bases, (const uint8_t *)d_quals, (const unsigned long long *)d_offsets, d_lens, d_results, d_counters, a->d_next, a->d_error,
+        a->d_secRaw, a->secRawCap, a->userParams.maxSecondaryAlignmentAdditionalEditDistance, maxSecondaryAlignments, maxSecondaryAlignmentsPerContig,
+        d_secondary, (long long)secondaryCapacityPerRead, d_nSecondary);
+    SG_CUDA(cudaGetLastError());
+    a->launches++;
+    return 0;
+}
+
+int snapgpu_align_single_secondary_device(snapgpu_aligner *a, int64_t n, const char *d_bases, const char *d_quals, const uint64_t *d_offsets, const uint32_t *d_lens,
+                                          snapgpu_single_result *d_results, int32_t maxSecondaryAlignments, int32_t maxSecondaryAlignmentsPerContig,
+                                          int64_t secondaryCapacityPerRead, snapgpu_single_result *d_secondary, int32_t *d_nSecondary,
+                                          snapgpu_counters *d_counters, void *cudaStream)
+{
+    if (!a || !d_bases || !d_quals || !d_offsets || !d_lens || !d_results || !d_nSecondary || (!d_secondary && secondaryCapacityPerRead > 0)) return sg_fail("null argument");
+    if (secondary_check(a, n, maxSecondaryAlignments, secondaryCapacityPerRead, "snapgpu_align_single_secondary_device")) return 1;
+    if (n == 0) return 0;
+    SG_CUDA(cudaSetDevice(a->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : a->stream;
+    return launch_align_secondary(a, n, d_bases, d_quals, d_offsets, d_lens, d_results, maxSecondaryAlignments, maxSecondaryAlignmentsPerContig,
+                                  secondaryCapacityPerRead, d_secondary, d_nSecondary, d_counters, st);
+}
+
+int snapgpu_align_single_secondary(snapgpu_aligner *a, int64_t n, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
+                                   snapgpu_single_result *results, int32_t maxSecondaryAlignments, int32_t maxSecondaryAlignmentsPerContig,
+                                   int64_t secondaryCapacityPerRead, snapgpu_single_result *secondary, int32_t *nSecondary, snapgpu_counters *counters)
+{
+    if (!a || !bases || !quals || !offsets || !lens || !results || !nSecondary || (!secondary && secondaryCapacityPerRead > 0)) return sg_fail("null argument");
+    if (secondary_check(a, n, maxSecondaryAlignments, secondaryCapacityPerRead, "snapgpu_align_single_secondary")) return 1;
+    if (n == 0) return 0;
+    SG_CUDA(cudaSetDevice(a->device));
+    // a cold path: plain staging, no pipeline.  Reads are packed back to back.
+    std::vector<uint64_t> off((size_t)n);
+    uint64_t total = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (lens[i] > a->params.maxReadLen) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+        off[(size_t)i] = total; total += lens[i];
+    }
+    std::vector<char> hb((size_t)total + 1), hq((size_t)total + 1);
+    for (int64_t i = 0; i < n; i++) {
+        memcpy(hb.data() + off[(size_t)i], bases + offsets[i], lens[i]);
+        memcpy(hq.data() + off[(size_t)i], quals + offsets[i], lens[i]);
+    }
+    char *d_b = nullptr, *d_q = nullptr; uint64_t *d_o = nullptr; uint32_t *d_l = nullptr; snapgpu_single_result *d_r = nullptr, *d_s = nullptr; int32_t *d_n = nullptr;
+    const size_t secBytes = (size_t)n * (size_t)secondaryCapacityPerRead * sizeof(snapgpu_single_result);
+    int rc = 0;
+    auto fail = [&](const std::string &m) { rc = sg_fail(m); };
+#define SG_TRY(call) do { if (!rc) { cudaError_t e_ = (call); if (e_ != cudaSuccess) fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    SG_TRY(cudaMalloc((void **)&d_b, (size_t)total + 1)); SG_TRY(cudaMalloc((void **)&d_q, (size_t)total + 1));
+    SG_TRY(cudaMalloc((void **)&d_o, (size_t)n * 8)); SG_TRY(cudaMalloc((void **)&d_l, (size_t)n * 4));
+    SG_TRY(cudaMalloc((void **)&d_r, (size_t)n * sizeof(snapgpu_single_result))); SG_TRY(cudaMalloc((void **)&d_n, (size_t)n * 4));
+    if (secBytes) SG_TRY(cudaMalloc((void **)&d_s, secBytes));
+    cudaStream_t st = a->stream;
+    SG_TRY(cudaMemcpyAsync(d_b, hb.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+    SG_TRY(cudaMemcpyAsync(d_q, hq.data(), (size_t)total, cudaMemcpyHostToDevice, st));
+    SG_TRY(cudaMemcpyAsync(d_o, off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    SG_TRY(cudaMemcpyAsync(d_l, lens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    while (!rc) {
+        SG_TRY(cudaMemsetAsync(a->d_counters, 0, sizeof(snapgpu_counters), st));
+        if (!rc && launch_align_secondary(a, n, d_b, d_q, d_o, d_l, d_r, maxSecondaryAlignments, maxSecondaryAlignmentsPerContig, secondaryCapacityPerRead, d_s, d_n,
+                                          a->d_counters, st)) { rc = 1; break; }
+        int code = 0;
+        SG_TRY(cudaMemcpyAsync(&code, a->d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SG_TRY(cudaStreamSynchronize(st));
+        if (rc || code == 0) break;
+        SG_TRY(cudaMemsetAsync(a->d_error, 0, sizeof(int), st));
+        if (code != 4) { fail("aligner kernel reported an error"); break; }
+        // a worker's raw buffer filled up: double it and align the batch again (SingleAligner.cpp:250-263 does this per read)
+        if (a->secRawCap >= (1 << 16)) { fail("secondary alignments: more than 65536 candidate records for one read"); break; }
+        if (secondary_reserve(a, a->secRawCap * 2)) { rc = 1; break; }
+    }
+    SG_TRY(cudaMemcpyAsync(results, d_r, (size_t)n * sizeof(snapgpu_single_result), cudaMemcpyDeviceToHost, st));
+    SG_TRY(cudaMemcpyAsync(nSecondary, d_n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (secBytes) SG_TRY(cudaMemcpyAsync(secondary, d_s, secBytes, cudaMemcpyDeviceToHost, st));
+    SG_TRY(cudaMemcpyAsync(a->h_counters, a->d_counters, sizeof(snapgpu_counters), cudaMemcpyDeviceToHost, st));
+    SG_TRY(cudaStreamSynchronize(st));
+#undef SG_TRY
+    cudaFree(d_b); cudaFree(d_q); cudaFree(d_o); cudaFree(d_l); cudaFree(d_r); cudaFree(d_s); cudaFree(d_n);
+    if (rc) { const std::string keep = g_lastError; cudaStreamSynchronize(st); cudaGetLastError(); g_lastError = keep; return rc; }
+    if (counters) {
+        int64_t *dst = (int64_t *)counters; const int64_t *src = (const int64_t *)a->h_counters;
+        for (size_t k = 0; k < sizeof(snapgpu_counters) / sizeof(int64_t); k++) dst[k] += src[k];
+    }
+    return 0;
 }
 
 int snapgpu_align_paired(snapgpu_aligner *a, int64_t nPairs, const char *bases, const char *quals, const uint64_t *offsets,

@@ -83,12 +83,12 @@ EXPORTS = [
     "snapgpu_index_open", "snapgpu_index_build", "snapgpu_index_build_device", "snapgpu_index_save", "snapgpu_index_info_get", "snapgpu_index_close", "snapgpu_index_replicate", "snapgpu_host_alloc", "snapgpu_host_free",
     "snapgpu_group_create", "snapgpu_group_destroy", "snapgpu_group_size", "snapgpu_index_broadcast", "snapgpu_counters_allreduce",
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
-    "snapgpu_align_single_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
+    "snapgpu_align_single_device", "snapgpu_align_single_secondary", "snapgpu_align_single_secondary_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
     "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_bam_markdup_device", "snapgpu_bam_index_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
-ABI_VERSION = 5          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
+ABI_VERSION = 6          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
 _lib = None
 
 
@@ -128,6 +128,8 @@ def lib():
         L.snapgpu_aligner_destroy.argtypes = [C.c_void_p]
         L.snapgpu_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.snapgpu_align_single_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+        L.snapgpu_align_single_secondary.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snapgpu_align_single_secondary_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 4
         L.snapgpu_paired_params_default.argtypes = [C.POINTER(PairedParams)]
         L.snapgpu_paired_aligner_create.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PairedParams), C.c_int64, C.POINTER(C.c_void_p)]
         L.snapgpu_align_paired.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
@@ -317,6 +319,35 @@ class SingleAligner:
                                                C.c_void_p(res.ctypes.data + done * RESULT_DTYPE.itemsize), _p(ctr)))
             done += m
         return res, counters_dict(ctr)
+
+    def align_secondary(self, batch, capacity: int = 64, max_secondary: int = 0x7fffffff, max_per_contig: int = -1):
+        """`snap single -om` (the handle's params carry maxSecondaryAlignmentAdditionalEditDistance >= 0): snapgpu_align_single_secondary.
+        Returns (primary results [n], secondary results [n, capacity], counts [n] (negative: -count did not fit), counters)."""
+        res = np.zeros(batch.n, dtype=RESULT_DTYPE)
+        sec = np.zeros((batch.n, capacity), dtype=RESULT_DTYPE)
+        nsec = np.zeros(batch.n, dtype=np.int32)
+        ctr = np.zeros(N_COUNTERS, dtype=np.int64)
+        done = 0
+        while done < batch.n:
+            m = min(self.max_batch_reads, batch.n - done)
+            sub_off = batch.offsets[done:done + m]
+            sub_len = batch.lens[done:done + m]
+            _check(lib().snapgpu_align_single_secondary(self.handle, m, _p(batch.bases), _p(batch.quals), _p(sub_off), _p(sub_len),
+                                                         C.c_void_p(res.ctypes.data + done * RESULT_DTYPE.itemsize), max_secondary, max_per_contig, capacity,
+                                                         C.c_void_p(sec.ctypes.data + done * capacity * RESULT_DTYPE.itemsize),
+                                                         C.c_void_p(nsec.ctypes.data + done * 4), _p(ctr)))
+            done += m
+        return res, sec, nsec, counters_dict(ctr)
+
+    def align_secondary_device(self, n, d_bases, d_quals, d_offsets, d_lens, d_results, capacity, d_secondary, d_nsecondary, max_secondary=0x7fffffff,
+                               max_per_contig=-1, d_counters=0, stream=0):
+        """Device pointers (ints) in; enqueues on `stream`; no synchronisation: snapgpu_align_single_secondary_device."""
+        _check(lib().snapgpu_align_single_secondary_device(self.handle, n, C.c_void_p(d_bases), C.c_void_p(d_quals), C.c_void_p(d_offsets), C.c_void_p(d_lens),
+                                                            C.c_void_p(d_results), max_secondary, max_per_contig, capacity, C.c_void_p(d_secondary),
+                                                            C.c_void_p(d_nsecondary), C.c_void_p(d_counters), C.c_void_p(stream)))
+
+    def check(self, stream=0):
+        _check(lib().snapgpu_aligner_check(self.handle, C.c_void_p(stream)))
 
     def align_device(self, n, d_bases, d_quals, d_offsets, d_lens, d_results, d_counters=0, stream=0):
         """Device pointers (ints) in; enqueues on `stream`; no synchronisation: snapgpu_align_single_device."""

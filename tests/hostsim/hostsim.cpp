@@ -226,6 +226,62 @@ int hs_align_single(void *v, int64_t n, const char *bases, const char *quals, co
 }
 
 
+// Same contract as snapgpu_align_single_secondary (-om): the raw buffer grows like SingleAligner.cpp:250-263's.
+int hs_align_single_secondary(void *v, int64_t n, const char *bases, const char *quals, const uint64_t *offsets, const uint32_t *lens,
+                              snapgpu_single_result *results, int maxSecondaryAlignments, int maxSecondaryAlignmentsPerContig, int maxEditDistanceForSecondaryResults,
+                              int64_t capacityPerRead, snapgpu_single_result *secondary, int32_t *nSecondary, int rawCap, snapgpu_counters *ctr)
+{
+    HsAligner *a = (HsAligner *)v;
+    memset(&a->A.work, 0, sizeof(a->A.work));
+    std::vector<snapgpu_single_result> raw((size_t)(rawCap > 0 ? rawCap : 1));
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *rd = (const uint8_t *)bases + offsets[i];
+        const uint8_t *rq = (const uint8_t *)quals + offsets[i];
+        snapgpu_single_result *r = &results[i];
+        memset(r, 0, sizeof(*r));
+        nSecondary[i] = 0;
+        if (lens[i] > a->params.maxReadLen) { g_err = "read longer than maxReadLen"; return 1; }
+        uint32_t countOfNs = 0;
+        for (uint32_t k = 0; k < lens[i]; k++) countOfNs += (rd[k] == 'N');
+        if (ctr) ctr->totalReads++;
+        if (lens[i] < a->params.minReadLength || countOfNs > a->params.maxK) {
+            r->status = SNAPGPU_NOT_FOUND; r->location = a->A.invalidLocation; r->mapq = 0; r->direction = SNAPGPU_FORWARD;
+            if (ctr) ctr->uselessReads++;
+            continue;
+        }
+        for (;;) {
+            a->A.secResults = raw.data(); a->A.maxSec = (int)raw.size(); a->A.nSec = 0; a->A.secOverflow = 0;
+            a->A.secMaxEditDist = maxEditDistanceForSecondaryResults; a->A.secMaxResults = maxSecondaryAlignments; a->A.secMaxPerContig = maxSecondaryAlignmentsPerContig;
+            memset(r, 0, sizeof(*r));
+            const SgWork before = a->A.work;
+            sg_align_read_t<false, false, true>(a->A, rd, rq, lens[i], r);
+            if (!a->A.secOverflow) break;
+            a->A.work = before;
+            raw.resize(raw.size() * 2);
+        }
+        if ((int64_t)a->A.nSec <= capacityPerRead) {
+            for (int k = 0; k < a->A.nSec; k++) secondary[i * capacityPerRead + k] = raw[(size_t)k];
+            nSecondary[i] = a->A.nSec;
+        } else {
+            nSecondary[i] = -a->A.nSec;
+        }
+        if (ctr) {
+            if (r->status == SNAPGPU_SINGLE_HIT) ctr->singleHits++;
+            else if (r->status == SNAPGPU_MULTIPLE_HITS) ctr->multiHits++;
+            else ctr->notFound++;
+            if (r->status != SNAPGPU_NOT_FOUND && r->mapq >= 0 && r->mapq <= 70) ctr->mapqHistogram[r->mapq]++;
+        }
+    }
+    a->A.secResults = nullptr;
+    if (ctr) {
+        ctr->nHashTableLookups += a->A.work.lookups; ctr->nHashEntriesProbed += a->A.work.entriesProbed;
+        ctr->nOverflowWordsRead += a->A.work.overflowWords; ctr->lvCalls += a->A.work.lvCalls; ctr->affineGapCalls += a->A.work.agCalls;
+        ctr->nHitsIgnoredBecauseOfTooHighPopularity += a->A.work.popularIgnored;
+    }
+    return 0;
+}
+
+
 struct HsPaired {
     HsIndex *index;
     SgParams pr, prSingle;

@@ -62,6 +62,7 @@ def lib():
         L.hs_aligner_deferred.restype = C.c_int64
         L.hs_aligner_deferred.argtypes = [C.c_void_p]
         L.hs_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.hs_align_single_secondary.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_paired_create.restype = C.c_void_p
         L.hs_paired_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.hs_paired_retried.restype = C.c_int64
@@ -119,6 +120,17 @@ class HsAligner:
         if rc != 0:
             raise RuntimeError(lib().hs_last_error().decode())
         return res, ctr
+
+    def align_secondary(self, batch, result_dtype, n_counters, max_edit_dist, max_secondary=0x7fffffff, max_per_contig=-1, capacity=64, raw_cap=32):
+        res = np.zeros(batch.n, dtype=result_dtype)
+        sec = np.zeros((batch.n, capacity), dtype=result_dtype)
+        nsec = np.zeros(batch.n, dtype=np.int32)
+        ctr = np.zeros(n_counters, dtype=np.int64)
+        rc = lib().hs_align_single_secondary(self.handle, batch.n, _p(batch.bases), _p(batch.quals), _p(batch.offsets), _p(batch.lens), _p(res),
+                                             max_secondary, max_per_contig, max_edit_dist, capacity, _p(sec), _p(nsec), raw_cap, _p(ctr))
+        if rc != 0:
+            raise RuntimeError(lib().hs_last_error().decode())
+        return res, sec, nsec, ctr
 
 
 class HsPairedAligner:

@@ -943,3 +943,44 @@ def test_pair_records_sorted_on_the_device_equal_reference_sorted_output(engine,
     assert len(want) == len(got) == pb.n
     bad = [i for i in range(pb.n) if want[i] != got[i]]
     assert bad == [], (len(bad), want[bad[0]][:120], got[bad[0]][:120])
+
+
+def test_secondary_alignments_match_reference(engine, gidx, small_cfg, reflib):
+    """`snap single -om / -omax / -mpc` through snapgpu_align_single_secondary: primary results, counts and every secondary record in the
+    reference's buffer order; a raw buffer that starts too small (SNAPGPU_SECONDARY_RAW_CAP=4) is grown by the call itself; a capacity that
+    is too small reports minus the count; the plain entry point refuses an -om handle."""
+    from test_hostsim_parity import SECONDARY_SETS, differing_secondary
+    ridx = reflib.RefIndex(small_cfg.idx)
+    old = os.environ.get("SNAPGPU_SECONDARY_RAW_CAP")
+    for opt, (kw, omax, mpc) in SECONDARY_SETS.items():
+        if opt == "om3_esd3":
+            os.environ["SNAPGPU_SECONDARY_RAW_CAP"] = "4"
+        try:
+            al = engine.SingleAligner(gidx, engine.default_params(**kw), 4096)
+            for name, rb in small_cfg.reads.items():
+                ral = reflib.RefSecondaryAligner(ridx, reflib.default_params(**kw), omax, mpc)
+                want, wsec, wn, wctr = ral.align(rb, capacity=256)
+                ral.close()
+                got, gsec, gn, g = al.align_secondary(rb, capacity=256, max_secondary=omax, max_per_contig=mpc)
+                bad_p, bad_s = differing_secondary(want, wsec, wn, got, gsec, gn)
+                assert bad_p == [] and bad_s == [], (opt, name, bad_p[:5], bad_s[:5])
+                for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "mapqHistogram"):
+                    assert wctr[k] == g[k], (opt, name, k)
+            if opt == "om3_esd3":
+                rb = small_cfg.reads["std150"]
+                _, _, n_big, _ = al.align_secondary(rb, capacity=256, max_secondary=omax, max_per_contig=mpc)
+                _, _, n_one, _ = al.align_secondary(rb, capacity=1, max_secondary=omax, max_per_contig=mpc)
+                assert (n_one < -1).any() and np.array_equal(np.where(n_big > 1, -n_big, n_big), n_one)
+                with pytest.raises(engine.SnapGpuError):
+                    al.align(rb)
+            al.close()
+        finally:
+            if old is None:
+                os.environ.pop("SNAPGPU_SECONDARY_RAW_CAP", None)
+            else:
+                os.environ["SNAPGPU_SECONDARY_RAW_CAP"] = old
+    # a handle without -om refuses the secondary call
+    al = engine.SingleAligner(gidx, engine.default_params(maxDist=14), 4096)
+    with pytest.raises(engine.SnapGpuError):
+        al.align_secondary(small_cfg.reads["std150"])
+    al.close()

@@ -348,3 +348,60 @@ def test_pairs_pool_caps_do_not_change_results(reflib, small_cfg, caps):
         assert differing_pairs(want, got) == [], (caps, name)
         retried += al.retried()
     assert retried > 0
+
+
+# `snap single -om`: option sets x (omax, mpc).  -om cannot exceed -D (AlignerContext.cpp:784).
+SECONDARY_SETS = {
+    "om0": (dict(maxDist=14, maxSecondaryAlignmentAdditionalEditDistance=0), 0x7fffffff, -1),
+    "om1": (dict(maxDist=14, maxSecondaryAlignmentAdditionalEditDistance=1), 0x7fffffff, -1),
+    "om3_esd3": (dict(maxDist=14, extraSearchDepth=3, maxSecondaryAlignmentAdditionalEditDistance=3), 0x7fffffff, -1),
+    "om3_esd3_omax2": (dict(maxDist=14, extraSearchDepth=3, maxSecondaryAlignmentAdditionalEditDistance=3), 2, -1),
+    "om3_esd3_mpc1": (dict(maxDist=14, extraSearchDepth=3, maxSecondaryAlignmentAdditionalEditDistance=3), 0x7fffffff, 1),
+    "om2_esd2_noag": (dict(maxDist=14, extraSearchDepth=2, useAffineGap=0, maxSecondaryAlignmentAdditionalEditDistance=2), 0x7fffffff, 2),
+    "om4_esd4_d20_h50": (dict(maxDist=20, extraSearchDepth=4, maxHits=50, maxSecondaryAlignmentAdditionalEditDistance=4), 5, 2),
+}
+
+
+def differing_secondary(want, wsec, wn, got, gsec, gn):
+    """(reads whose primary differs, reads whose secondary lists differ): counts equal and records bytewise equal in buffer order."""
+    bad_p = differing(want, got)
+    bad_s = []
+    for i in range(len(want)):
+        if int(wn[i]) != int(gn[i]) or (wn[i] > 0 and wsec[i, :wn[i]].tobytes() != gsec[i, :gn[i]].tobytes()):
+            bad_s.append(i)
+    return bad_p, bad_s
+
+
+@pytest.mark.parametrize("opt", list(SECONDARY_SETS))
+def test_secondary_alignments_match_reference(reflib, small_cfg, opt):
+    """-om / -omax / -mpc: primary results, the number of secondary results and every secondary record in the reference's buffer order."""
+    kw, omax, mpc = SECONDARY_SETS[opt]
+    p = reflib.default_params(**kw)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    total = 0
+    for name, rb in small_cfg.reads.items():
+        ral = reflib.RefSecondaryAligner(ridx, p, omax, mpc)
+        want, wsec, wn, wctr = ral.align(rb, capacity=256)
+        ral.close()
+        assert (wn >= 0).all()
+        got, gsec, gn, gctr = hs.HsAligner(hidx, p).align_secondary(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS, kw["maxSecondaryAlignmentAdditionalEditDistance"],
+                                                                    omax, mpc, capacity=256, raw_cap=8)
+        bad_p, bad_s = differing_secondary(want, wsec, wn, got, gsec, gn)
+        assert bad_p == [] and bad_s == [], (opt, name, bad_p[:5], bad_s[:5])
+        total += int(wn.sum())
+        g = reflib.counters_dict(gctr)
+        for k in ("totalReads", "uselessReads", "singleHits", "multiHits", "notFound", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, name, k)
+    assert total > 100, total            # the repeat library gives reads with several placements
+
+
+def test_secondary_capacity_too_small_reports_the_count(reflib, small_cfg):
+    kw, omax, mpc = SECONDARY_SETS["om3_esd3"]
+    p = reflib.default_params(**kw)
+    hidx = hs.HsIndex(small_cfg.idx)
+    rb = small_cfg.reads["std150"]
+    al = hs.HsAligner(hidx, p)
+    _, _, n_big, _ = al.align_secondary(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS, 3, omax, mpc, capacity=256)
+    _, _, n_one, _ = al.align_secondary(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS, 3, omax, mpc, capacity=1)
+    assert (n_big > 1).any()
+    assert np.array_equal(np.where(n_big > 1, -n_big, n_big), n_one)

@@ -39,12 +39,12 @@ def _run(binary, argv, env=None):
     return r.stdout
 
 
-def _stats_line(stdout):
+def _stats_line(stdout, n=5):
     lines = [l for l in stdout.split("\n") if l.strip()]
     k = max(i for i, l in enumerate(lines) if "Reads/s" in l)
     import re
     toks = re.sub(r"\([^)]*\)", " ", lines[k + 1]).split()
-    return [t for t in toks if t.replace(",", "").isdigit()][:5]       # total, single, multi, unaligned, too short (rates / times differ)
+    return [t for t in toks if t.replace(",", "").isdigit()][:n]       # total, single, multi, unaligned, too short[, extra alignments] (rates / times differ)
 
 
 @pytest.mark.gpu
@@ -79,6 +79,23 @@ def test_snap_aligner_gpu_single_other_options(tmp_path, small_cfg, reflib):
         _run(GPU_BIN, ["single", small_cfg.idx, fq, "-o", gpu, "-t", "2"] + extra)
         a, b = _records(stock), _records(gpu)
         assert a == b, (extra, len(a), len(b))
+
+
+@pytest.mark.gpu
+def test_snap_aligner_gpu_single_secondary_alignments(tmp_path, small_cfg, reflib):
+    """`-om` (with -omax / -mpc): the records of the primary AND the secondary alignments (flag 0x100) are the ones stock snap-aligner writes,
+    and so are the totals it prints (extra alignments included)."""
+    reads = small_cfg.reads["std150"]
+    fq = str(tmp_path / "r.fq")
+    reads.write_fastq(fq)
+    for extra in (["-d", "14", "-om", "1"], ["-d", "14", "-D", "3", "-om", "3", "-omax", "4"], ["-d", "14", "-D", "2", "-om", "2", "-mpc", "1", "-G-"]):
+        stock, gpu = str(tmp_path / "stock.sam"), str(tmp_path / "gpu.sam")
+        so = _run(reflib.SNAP_ALIGNER, ["single", small_cfg.idx, fq, "-o", stock, "-t", "1"] + extra)
+        go = _run(GPU_BIN, ["single", small_cfg.idx, fq, "-o", gpu, "-t", "2"] + extra, env={"SNAPGPU_EXT_BATCH_READS": "512"})
+        a, b = _records(stock), _records(gpu)
+        assert len(a) > reads.n                    # there are secondary records
+        assert a == b, (extra, len(a), len(b))
+        assert _stats_line(so, 6) == _stats_line(go, 6) and int(_stats_line(so, 6)[5].replace(",", "")) == len(a) - reads.n
 
 
 @pytest.mark.gpu
