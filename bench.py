@@ -150,16 +150,9 @@ WORKLOADS = {
 }
 
 
-def csrc_sha16():
-    """Hash of the kernel sources: profiles/traffic.json records the one its ncu capture was taken at, and the line only quotes
-    `traffic` / `issue_slots` from a capture of THESE sources."""
-    import hashlib
-    h = hashlib.sha256()
-    d = os.path.join(ROOT, "snap_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
-    return h.hexdigest()[:16]
+sys.path.insert(0, os.path.join(ROOT, "profiles"))
+from kernel_stamp import csrc_sha16, sass_sha16_for       # noqa: E402  profiles/traffic.json records both stamps of the kernels its ncu capture
+                                                          # was taken of; the line only quotes `traffic` / `issue_slots` from a capture of THESE kernels
 
 
 def traffic_entry(workload, batch_reads, genome_mbp):
@@ -171,9 +164,16 @@ def traffic_entry(workload, batch_reads, genome_mbp):
     key = "%s_%dreads_%dmbp" % (workload, batch_reads, genome_mbp)
     if key not in t:
         return None, "no capture of this workload"
-    if t[key].get("csrc_sha16") != csrc_sha16():
-        return None, "capture is of other kernel sources (csrc_sha16 %s, now %s): refresh with profiles/refresh_traffic.sh" % (t[key].get("csrc_sha16"), csrc_sha16())
-    return t[key], None
+    e = dict(t[key])
+    if e.get("csrc_sha16") == csrc_sha16():
+        e["stamp"] = "csrc_sha16 %s" % e["csrc_sha16"]
+        return e, None
+    now = sass_sha16_for(key)
+    if e.get("sass_sha16") and now and e["sass_sha16"] == now:
+        e["stamp"] = "sass_sha16 %s (the SASS of these kernels is what was captured; other sources of the library changed since)" % now
+        return e, None
+    return None, "capture is of other kernels (csrc_sha16 %s, now %s; sass_sha16 %s, now %s): refresh with profiles/refresh_traffic.sh" % (
+        e.get("csrc_sha16"), csrc_sha16(), e.get("sass_sha16"), now)
 
 
 class Ctx:
@@ -342,7 +342,7 @@ def run_workload(c, args, name, batches, W, K, sample_clocks=False):
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
     if entry:
         roofline["traffic_over_algorithmic"] = round(entry["dram_bytes_per_launch"] / max(1.0, alg_bytes), 2)
-        roofline["traffic_source"] = "profiles/traffic.json, ncu --set full of these kernel sources (csrc_sha16 %s)" % entry["csrc_sha16"]
+        roofline["traffic_source"] = "profiles/traffic.json, ncu --set full of these kernels (%s)" % entry["stamp"]
         n_inst = entry.get("warp_instructions_per_step")
         sm_mhz = clocks.get("sm_mhz") or c.__dict__.get("sm_mhz")
         if n_inst and sm_mhz:
@@ -542,7 +542,7 @@ def seed_phase(args, idx, batches, device, peak, peak_src):
     if entry:
         out["dram_bytes_per_lookup"] = round(entry["dram_bytes_per_launch"] / n, 1)
         out["dram_over_algorithmic"] = round(entry["dram_bytes_per_launch"] / alg, 2)
-        out["dram_source"] = "profiles/traffic.json, ncu --set full of these kernel sources (csrc_sha16 %s)" % entry["csrc_sha16"]
+        out["dram_source"] = "profiles/traffic.json, ncu --set full of these kernels (%s)" % entry["stamp"]
     else:
         out["dram_bytes_per_lookup"] = None
         out["dram_note"] = why
@@ -716,6 +716,26 @@ def sam_phase(args, c, host_batch, paired):
                    "index_ms": round(idx_ms, 3), "bai_bytes": len(bai), "bai_references": n_ref,
                    "note": "uniform random reads over 3 Gbp hold next to no duplicates: the timing is of the machinery; parity with the reference's marked stream "
                            "and .bai is in tests/test_gpu_sorted_output.py"}
+            # the same stream through the compressor on the device (snapgpu_bgzf_deflate_device: one thread block per member) and the .bai of that file
+            try:
+                fmt.bgzf_deflate_device(d_sorted.data_ptr(), sb, d_bgzf.data_ptr(), d_bgzf.numel(), st.cuda_stream)      # warm-up: sizes the work buffer
+                torch.cuda.synchronize()
+                e0.record(st)
+                z_bytes, member_offsets = fmt.bgzf_deflate_device(d_sorted.data_ptr(), sb, d_bgzf.data_ptr(), d_bgzf.numel(), st.cuda_stream)
+                e1.record(st)
+                torch.cuda.synchronize()
+                z_ms = e0.elapsed_time(e1)
+                import zlib
+                k = int(member_offsets.size // 2)
+                probe = d_bgzf[int(member_offsets[k]):int(member_offsets[k + 1])].cpu().numpy().tobytes()
+                want = d_sorted[k * 0xff00:min(sb, (k + 1) * 0xff00)].cpu().numpy().tobytes()
+                zbai = fmt.index_device(d_sorted.data_ptr(), d_roffs.data_ptr(), n, sb, 0, st.cuda_stream, member_offsets=member_offsets)
+                bam["deflate"] = {"what": "snapgpu_bgzf_deflate_device: LZ77 + dynamic Huffman per 65280-byte member, one block of 1024 threads each (sg_deflate.h)",
+                                  "ms": round(z_ms, 3), "gbs_in": round(sb / (z_ms / 1e3) / 1e9, 2), "bytes": int(z_bytes), "ratio": round(z_bytes / max(1, sb), 4),
+                                  "zlib6_ratio_of_one_member": round(len(zlib.compress(want, 6)) / max(1, len(want)), 4),
+                                  "member_inflates_to_its_payload": bool(zlib.decompress(probe, 31) == want), "bai_bytes": len(zbai)}
+            except Exception as e:      # pragma: no cover
+                bam["deflate"] = {"error": str(e)[:200]}
             del d_bgzf, d_roffs
         except Exception as e:      # pragma: no cover
             bam = {"error": str(e)[:200]}

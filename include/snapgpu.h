@@ -24,7 +24,7 @@ extern "C" {
 
 #define SNAPGPU_ABI_VERSION 6   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
                                  * 4: snapgpu_sam_sort_device; 5: snapgpu_bam_markdup_device, snapgpu_bam_index_device;
-                                 * 6: snapgpu_align_single_secondary(_device) (-om) */
+                                 * 6: snapgpu_align_single_secondary(_device) (-om), snapgpu_bgzf_deflate_device, snapgpu_bam_index_members_device */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
@@ -416,6 +416,15 @@ int  snapgpu_sam_set_format(snapgpu_sam *s, int format);
  * payload bytes, each ONE STORED deflate block with its CRC-32 -- valid BGZF that inflates to exactly the payload (no compressor runs on
  * the device; the reference compresses, so files differ in size, not in content).  outCapacity >= nBytes + 31 per member.  Asynchronous on `cudaStream`. */
 int  snapgpu_bgzf_device(const char *d_in, int64_t nBytes, char *d_out, int64_t outCapacity, int64_t *outBytes, void *cudaStream);
+/* The same with a compressor on the device (reference: GzipCompressWorker hands every chunk to zlib's deflate(), SNAPLib/GzipDataWriter.cpp:153-276): every
+ * member is ONE dynamic-Huffman deflate block over an LZ77 parse of its 65280 payload bytes, built by a thread block (snap_b200/csrc/sg_deflate.h: strided
+ * hash match finding, the greedy parse by pointer jumping, minimum-redundancy codes, a prefix sum of token bit lengths); a member that would not shrink is
+ * stored.  Any inflater gives back exactly the payload (CRC-32 / ISIZE checked); the compressed bytes differ from zlib's, as zlib's do between levels.
+ * Members are contiguous in d_out; outCapacity >= nBytes + 31 per member is always enough.  memberOffsets (HOST, optional, one entry per member plus one):
+ * where each member starts in d_out, the last entry = *outBytes -- what a .bai of the compressed file needs (snapgpu_bam_index_members_device).
+ * `s` lends its work buffer and stream.  Synchronises `cudaStream` (NULL = the handle's own). */
+int  snapgpu_bgzf_deflate_device(snapgpu_sam *s, const char *d_in, int64_t nBytes, char *d_out, int64_t outCapacity, int64_t *outBytes,
+                                 uint64_t *memberOffsets, void *cudaStream);
 
 /* SURVEY 8(f) row N4, the sort: the reference's sorting writer (`-so`; SortedDataFilter, reference SNAPLib/SortedDataWriter.cpp:905-1010) files
  * every record under the key of the genome location SimpleReadWriter passed to DataWriter::advance for it (ReadWriter.cpp:331, :601-615: the
@@ -453,6 +462,10 @@ int64_t snapgpu_sam_last_record_count(const snapgpu_sam *s);       /* records (2
 int  snapgpu_bam_markdup_device(snapgpu_sam *s, char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t *nMarked, void *cudaStream);
 int  snapgpu_bam_index_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
                               char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream);
+/* The .bai of the same content wrapped by snapgpu_bgzf_deflate_device (compressed members): memberOffsets / nMembers as that call reported them for the
+ * stream header || records (nMembers = ceil((headerBytes + recordBytes) / 65280), memberOffsets[nMembers] = end of the last data member). */
+int  snapgpu_bam_index_members_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
+                                      const uint64_t *memberOffsets, int64_t nMembers, char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream);
 
 /* Device-resident forms: every array, and the text buffer, is a DEVICE pointer -- the reads as parsed by snapgpu_fastq_parse_device, the
  * records as left by snapgpu_align_*_device -- so a batch goes from FASTQ text to SAM text without its reads or results visiting the

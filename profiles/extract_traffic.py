@@ -14,14 +14,8 @@ def to_bytes(v, unit):
     return float(v.replace(",", "")) * mult[unit]
 
 
-def csrc_sha16():
-    """Same hash as bench.py's: the kernel sources a capture was taken of."""
-    h = hashlib.sha256()
-    d = os.path.join(os.path.dirname(HERE), "snap_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
-    return h.hexdigest()[:16]
+sys.path.insert(0, HERE)
+from kernel_stamp import csrc_sha16, sass_sha16_for       # the stamps bench.py compares (profiles/kernel_stamp.py)
 
 
 def main():
@@ -53,7 +47,7 @@ def main():
             per_launch.append({"kernel": vals[col["Kernel Name"]][:40], "dram_bytes": int(r + w),
                                "duration_under_ncu": vals[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]]})
         data[key] = {"dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr), "launches": per_launch,
-                     "warp_instructions_per_step": int(inst), "csrc_sha16": csrc_sha16(), "captured_with": desc, "report": os.path.basename(rep)}
+                     "warp_instructions_per_step": int(inst), "csrc_sha16": csrc_sha16(), "sass_sha16": sass_sha16_for(key), "captured_with": desc, "report": os.path.basename(rep)}
         print(key, data[key])
     json.dump(data, open(OUT, "w"), indent=1, sort_keys=True)
 

@@ -357,9 +357,15 @@ SG_HD int32_t sg_bai_linear_slot(const SgBamRec &r)
 // virtual file offset of uncompressed offset u in a file made of BGZF members of SG_BGZF_PAYLOAD_BYTES payload bytes each (snapgpu_bgzf_device) followed by the
 // 28-byte end-of-file member; the very end of the data translates to the end of the file, as GzipWriterFilterSupplier::translate has it.
 #define SG_BGZF_PAYLOAD_BYTES 0xff00ULL
-SG_HD uint64_t sg_bai_virtual_offset(uint64_t u, uint64_t totalBytes)
+// memberOffsets (optional, nMembers + 1 entries): where each member starts in the file when the members are compressed (snapgpu_bgzf_deflate_device), the
+// last entry being the end of the data members; NULL = stored members of fixed size.
+SG_HD uint64_t sg_bai_virtual_offset(uint64_t u, uint64_t totalBytes, const uint64_t *memberOffsets = (const uint64_t *)0)
 {
     const uint64_t nMembers = (totalBytes + SG_BGZF_PAYLOAD_BYTES - 1) / SG_BGZF_PAYLOAD_BYTES;
+    if (memberOffsets) {
+        if (u >= totalBytes) return (memberOffsets[nMembers] + 28ULL) << 16;
+        return memberOffsets[u / SG_BGZF_PAYLOAD_BYTES] << 16 | (u % SG_BGZF_PAYLOAD_BYTES);
+    }
     if (u >= totalBytes) return (nMembers * 31ULL + totalBytes + 28ULL) << 16;
     return ((u / SG_BGZF_PAYLOAD_BYTES) * (SG_BGZF_PAYLOAD_BYTES + 31ULL)) << 16 | (u % SG_BGZF_PAYLOAD_BYTES);
 }
@@ -377,7 +383,8 @@ struct SgBaiRef {
 inline void sg_bai_put64(std::vector<uint8_t> &o, uint64_t v) { for (int k = 0; k < 8; k++) o.push_back((uint8_t)(v >> (8 * k))); }
 inline void sg_bai_put32(std::vector<uint8_t> &o, uint32_t v) { for (int k = 0; k < 4; k++) o.push_back((uint8_t)(v >> (8 * k))); }
 // chunks: every maximal stretch of equal (refID, bin) in stream order (refID < 0 or >= nRef are dropped here, as addChunk drops them)
-inline std::vector<uint8_t> sg_bai_compose(int32_t nRef, std::vector<SgBaiChunk> chunks, const std::vector<SgBaiRef> &refs, uint64_t totalBytes)
+inline std::vector<uint8_t> sg_bai_compose(int32_t nRef, std::vector<SgBaiChunk> chunks, const std::vector<SgBaiRef> &refs, uint64_t totalBytes,
+                                           const uint64_t *memberOffsets = (const uint64_t *)0)
 {
     std::vector<uint8_t> o;
     o.push_back('B'); o.push_back('A'); o.push_back('I'); o.push_back(1);
@@ -395,15 +402,15 @@ inline std::vector<uint8_t> sg_bai_compose(int32_t nRef, std::vector<SgBaiChunk>
             size_t e = c;
             while (e < c1 && chunks[e].bin == chunks[c].bin) e++;
             sg_bai_put32(o, chunks[c].bin); sg_bai_put32(o, (uint32_t)(e - c));
-            for (; c < e; c++) { sg_bai_put64(o, sg_bai_virtual_offset(chunks[c].start, totalBytes)); sg_bai_put64(o, sg_bai_virtual_offset(chunks[c].end, totalBytes)); }
+            for (; c < e; c++) { sg_bai_put64(o, sg_bai_virtual_offset(chunks[c].start, totalBytes, memberOffsets)); sg_bai_put64(o, sg_bai_virtual_offset(chunks[c].end, totalBytes, memberOffsets)); }
         }
         if (R.any) {
             sg_bai_put32(o, SG_BAM_EXTRA_BIN); sg_bai_put32(o, 2);
-            sg_bai_put64(o, sg_bai_virtual_offset(R.firstStart, totalBytes)); sg_bai_put64(o, sg_bai_virtual_offset(R.lastEnd, totalBytes));
+            sg_bai_put64(o, sg_bai_virtual_offset(R.firstStart, totalBytes, memberOffsets)); sg_bai_put64(o, sg_bai_virtual_offset(R.lastEnd, totalBytes, memberOffsets));
             sg_bai_put64(o, R.mapped); sg_bai_put64(o, R.unmapped);
         }
         sg_bai_put32(o, (uint32_t)R.intervals.size());
-        for (uint64_t v : R.intervals) sg_bai_put64(o, v == ~0ULL ? 0ULL : sg_bai_virtual_offset(v, totalBytes));
+        for (uint64_t v : R.intervals) sg_bai_put64(o, v == ~0ULL ? 0ULL : sg_bai_virtual_offset(v, totalBytes, memberOffsets));
     }
     return o;
 }

@@ -26,6 +26,7 @@
 #include "sg_sam.h"
 #include "sg_bam.h"
 #include "sg_bampost.h"
+#include "sg_deflate.h"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -2588,6 +2589,88 @@ int snapgpu_bgzf_device(const char *d_in, int64_t nBytes, char *d_out, int64_t o
     return 0;
 }
 
+// ---- BGZF members with a compressor (sg_deflate.h): one block of 1024 threads per member, persistent over the members; each member is laid at a fixed
+//      pitch, a scan of the member sizes and one copy per member then close the gaps. ----
+extern "C++" {
+__global__ void __launch_bounds__(1024, 1)
+sg_bgzf_deflate_kernel(const uint8_t *in, unsigned long long nBytes, uint8_t *members, uint32_t *memberSizes, unsigned long long nMembers, uint16_t *arenas)
+{
+    extern __shared__ __align__(16) uint8_t sgDeflateSmem[];
+    SgDeflateShared &S = *(SgDeflateShared *)sgDeflateSmem;
+    SgDeflateArena G;
+    uint16_t *a = arenas + (size_t)blockIdx.x * (SG_DEFLATE_ARENA_BYTES / 2);
+    G.mlen = a; G.mdist = a + (SG_DEFLATE_MAX_PAYLOAD + 8); G.jumpA = a + 2 * (SG_DEFLATE_MAX_PAYLOAD + 8); G.jumpB = a + 3 * (SG_DEFLATE_MAX_PAYLOAD + 8);
+    for (unsigned long long m = blockIdx.x; m < nMembers; m += gridDim.x) {
+        const unsigned long long off = m * SG_DEFLATE_MAX_PAYLOAD;
+        const uint32_t len = (uint32_t)((nBytes - off) < SG_DEFLATE_MAX_PAYLOAD ? (nBytes - off) : SG_DEFLATE_MAX_PAYLOAD);
+        const uint32_t sz = sg_deflate_member(S, G, in + off, len, members + m * (unsigned long long)SG_DEFLATE_MEMBER_PITCH);
+        if (threadIdx.x == 0) memberSizes[m] = sz;
+        __syncthreads();
+    }
+}
+
+__global__ void sg_bgzf_compact_kernel(const uint8_t *members, const uint32_t *memberSizes, const unsigned long long *memberOffsets, unsigned long long nMembers, uint8_t *out)
+{
+    for (unsigned long long m = blockIdx.x; m < nMembers; m += gridDim.x) {
+        const uint8_t *src = members + m * (unsigned long long)SG_DEFLATE_MEMBER_PITCH;
+        uint8_t *dst = out + memberOffsets[m];
+        const uint32_t n = memberSizes[m];
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+    }
+}
+}
+
+static int sam_post_reserve(snapgpu_sam *s, size_t bytes);
+
+int snapgpu_bgzf_deflate_device(snapgpu_sam *s, const char *d_in, int64_t nBytes, char *d_out, int64_t outCapacity, int64_t *outBytes, uint64_t *memberOffsets,
+                                void *cudaStream)
+{
+    if (!s || !d_in || !d_out || !outBytes || nBytes < 0) return sg_fail("bad argument");
+    *outBytes = 0;
+    if (memberOffsets) memberOffsets[0] = 0;
+    if (nBytes == 0) return 0;
+    SG_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = cudaStream ? (cudaStream_t)cudaStream : s->stream;
+    const unsigned long long nMembers = ((unsigned long long)nBytes + SG_DEFLATE_MAX_PAYLOAD - 1) / SG_DEFLATE_MAX_PAYLOAD;
+    if (nMembers >= 0x7fffffffULL) return sg_fail("snapgpu_bgzf_deflate_device: too many members for one call");
+    int sms = 0;
+    SG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const unsigned grid = (unsigned)(nMembers < (unsigned long long)sms ? nMembers : (unsigned long long)sms);
+    size_t cubBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cubBytes, (uint32_t *)nullptr, (unsigned long long *)nullptr, (int)nMembers);
+    const size_t need = (size_t)nMembers * SG_DEFLATE_MEMBER_PITCH + 256 + (size_t)nMembers * 4 + 256 + ((size_t)nMembers + 1) * 8 + 256 + cubBytes + 256 +
+                        (size_t)grid * SG_DEFLATE_ARENA_BYTES + 256;
+    if (sam_post_reserve(s, need)) return 1;
+    uint8_t *base = (uint8_t *)s->d_post;
+    size_t at = 0;
+    auto take = [&](size_t bytes) { uint8_t *p = base + at; at += (bytes + 255) & ~(size_t)255; return p; };
+    uint8_t *members = take((size_t)nMembers * SG_DEFLATE_MEMBER_PITCH);
+    uint32_t *sizes = (uint32_t *)take((size_t)nMembers * 4);
+    unsigned long long *offs = (unsigned long long *)take(((size_t)nMembers + 1) * 8);
+    void *d_cub = take(cubBytes);
+    uint16_t *arenas = (uint16_t *)take((size_t)grid * SG_DEFLATE_ARENA_BYTES);
+    SG_CUDA(cudaFuncSetAttribute(sg_bgzf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgDeflateShared)));      // (per device)
+    sg_bgzf_deflate_kernel<<<grid, 1024, sizeof(SgDeflateShared), st>>>((const uint8_t *)d_in, (unsigned long long)nBytes, members, sizes, nMembers, arenas);
+    SG_CUDA(cudaGetLastError());
+    size_t cb = cubBytes;
+    SG_CUDA(cub::DeviceScan::ExclusiveSum(d_cub, cb, sizes, offs, (int)nMembers, st));
+    unsigned long long lastOff = 0; uint32_t lastSize = 0;
+    SG_CUDA(cudaMemcpyAsync(&lastOff, offs + (nMembers - 1), 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(&lastSize, sizes + (nMembers - 1), 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long total = lastOff + lastSize;
+    if ((unsigned long long)outCapacity < total) return sg_fail("snapgpu_bgzf_deflate_device: output buffer too small");
+    sg_bgzf_compact_kernel<<<(unsigned)(nMembers < 148ull * 8 ? nMembers : 148ull * 8), 256, 0, st>>>(members, sizes, offs, nMembers, (uint8_t *)d_out);
+    SG_CUDA(cudaGetLastError());
+    if (memberOffsets) {
+        SG_CUDA(cudaMemcpyAsync(memberOffsets, offs, (size_t)nMembers * 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+        memberOffsets[nMembers] = total;
+    }
+    *outBytes = (int64_t)total;
+    return 0;
+}
+
 // (Re)sizes the octets' scratch and the record slots for reads of up to maxLen bases.
 static int sam_reserve(snapgpu_sam *s, uint32_t maxLen, int64_t nUnits, int paired)
 {
@@ -3088,8 +3171,8 @@ __global__ void sg_bai_linear_kernel(const unsigned long long *offsets, long lon
     atomicMax(&refSlots[ref], (unsigned long long)slot + 1ULL);
 }
 
-int snapgpu_bam_index_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
-                             char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream)
+static int bam_index_impl(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
+                          const uint64_t *memberOffsets, char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream)
 {
     if (!s || !bai || !baiBytes || (nRecords > 0 && (!d_records || !d_offsets))) return sg_fail("null argument");
     *baiBytes = 0;
@@ -3163,11 +3246,26 @@ int snapgpu_bam_index_device(snapgpu_sam *s, const char *d_records, const uint64
             R.intervals.assign(hIntervals.begin() + slotBase[r], hIntervals.begin() + slotBase[r] + hSlots[r]);
         }
     }
-    std::vector<uint8_t> o = sg_bai_compose(nRef, chunks, refs, total);
+    std::vector<uint8_t> o = sg_bai_compose(nRef, chunks, refs, total, memberOffsets);
     if ((int64_t)o.size() > baiCapacity) return sg_fail("snapgpu_bam_index_device: bai buffer too small");
     memcpy(bai, o.data(), o.size());
     *baiBytes = (int64_t)o.size();
     return 0;
+}
+
+int snapgpu_bam_index_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
+                             char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream)
+{
+    return bam_index_impl(s, d_records, d_offsets, nRecords, recordBytes, headerBytes, nullptr, bai, baiCapacity, baiBytes, cudaStream);
+}
+
+int snapgpu_bam_index_members_device(snapgpu_sam *s, const char *d_records, const uint64_t *d_offsets, int64_t nRecords, int64_t recordBytes, int64_t headerBytes,
+                                     const uint64_t *memberOffsets, int64_t nMembers, char *bai, int64_t baiCapacity, int64_t *baiBytes, void *cudaStream)
+{
+    if (!memberOffsets) return sg_fail("null argument");
+    if (recordBytes < 0 || headerBytes < 0 || nMembers != (int64_t)(((uint64_t)recordBytes + (uint64_t)headerBytes + 0xff00ULL - 1) / 0xff00ULL))
+        return sg_fail("snapgpu_bam_index_members_device: nMembers is not the member count of headerBytes + recordBytes");
+    return bam_index_impl(s, d_records, d_offsets, nRecords, recordBytes, headerBytes, memberOffsets, bai, baiCapacity, baiBytes, cudaStream);
 }
 
 int64_t snapgpu_sam_last_record_count(const snapgpu_sam *s) { return s ? s->lastRecords : 0; }

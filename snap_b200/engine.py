@@ -85,7 +85,7 @@ EXPORTS = [
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_align_single_secondary", "snapgpu_align_single_secondary_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
-    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_bam_markdup_device", "snapgpu_bam_index_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_bgzf_deflate_device", "snapgpu_bam_index_members_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_bam_markdup_device", "snapgpu_bam_index_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 ABI_VERSION = 6          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
@@ -147,6 +147,9 @@ def lib():
         L.snapgpu_bgzf_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_sam_sort_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]
         L.snapgpu_bam_markdup_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.snapgpu_bgzf_deflate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+        L.snapgpu_bam_index_members_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                       C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_bam_index_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_sam_last_record_count.restype = C.c_int64
         L.snapgpu_sam_last_record_count.argtypes = [C.c_void_p]
@@ -481,13 +484,27 @@ class SamFormatter:
         _check(lib().snapgpu_bam_markdup_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, C.byref(marked), C.c_void_p(stream)))
         return marked.value
 
-    def index_device(self, d_records, d_offsets, n_records, record_bytes, header_bytes, stream=0) -> bytes:
-        """The .bai of header ‖ records as snapgpu_bgzf_device lays the file out (snapgpu_bam_index_device)."""
+    def bgzf_deflate_device(self, d_in, n_bytes, d_out, out_capacity, stream=0):
+        """Compressed BGZF members over device data (snapgpu_bgzf_deflate_device); returns (bytes written to d_out, member offsets [nMembers + 1])."""
+        n_members = (int(n_bytes) + 0xff00 - 1) // 0xff00
+        offs = np.zeros(n_members + 1, dtype=np.uint64)
+        used = C.c_int64(0)
+        _check(lib().snapgpu_bgzf_deflate_device(self.handle, C.c_void_p(d_in), n_bytes, C.c_void_p(d_out), out_capacity, C.byref(used), _p(offs), C.c_void_p(stream)))
+        return int(used.value), offs
+
+    def index_device(self, d_records, d_offsets, n_records, record_bytes, header_bytes, stream=0, member_offsets=None) -> bytes:
+        """The .bai of header ‖ records as snapgpu_bgzf_device lays the file out (snapgpu_bam_index_device) or, given the member offsets
+        snapgpu_bgzf_deflate_device reported, as that call laid it out (snapgpu_bam_index_members_device)."""
         cap = 1 << 20
+        mo = None if member_offsets is None else np.ascontiguousarray(member_offsets, dtype=np.uint64)
         while True:
             out = np.empty(cap, dtype=np.uint8); used = C.c_int64(0)
-            rc = lib().snapgpu_bam_index_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, record_bytes, header_bytes,
-                                               out.ctypes.data_as(C.c_void_p), cap, C.byref(used), C.c_void_p(stream))
+            if mo is not None:
+                rc = lib().snapgpu_bam_index_members_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, record_bytes, header_bytes,
+                                                            _p(mo), mo.size - 1, out.ctypes.data_as(C.c_void_p), cap, C.byref(used), C.c_void_p(stream))
+            else:
+                rc = lib().snapgpu_bam_index_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, record_bytes, header_bytes,
+                                                    out.ctypes.data_as(C.c_void_p), cap, C.byref(used), C.c_void_p(stream))
             if rc != 0 and b"too small" in lib().snapgpu_last_error() and cap < (1 << 32):
                 cap *= 8
                 continue

@@ -19,6 +19,7 @@
 #include "../../snap_b200/csrc/sg_sam.h"
 #include "../../snap_b200/csrc/sg_bam.h"
 #include "../../snap_b200/csrc/sg_bampost.h"
+#include "../../snap_b200/csrc/sg_deflate.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -279,6 +280,28 @@ int hs_align_single_secondary(void *v, int64_t n, const char *bases, const char 
         ctr->nHitsIgnoredBecauseOfTooHighPopularity += a->A.work.popularIgnored;
     }
     return 0;
+}
+
+
+// snapgpu_bgzf_deflate_device on the host: the block-cooperative compressor of sg_deflate.h run by one thread per member.  Returns the BGZF stream's
+// size, or -1 when `cap` is too small.  memberSizes (optional): one entry per member.
+int64_t hs_bgzf_deflate(const uint8_t *in, int64_t n, uint8_t *out, int64_t cap, uint32_t *memberSizes)
+{
+    static SgDeflateShared S;
+    std::vector<uint16_t> arena(SG_DEFLATE_ARENA_BYTES / 2);
+    SgDeflateArena G;
+    G.mlen = arena.data(); G.mdist = G.mlen + (SG_DEFLATE_MAX_PAYLOAD + 8); G.jumpA = G.mdist + (SG_DEFLATE_MAX_PAYLOAD + 8); G.jumpB = G.jumpA + (SG_DEFLATE_MAX_PAYLOAD + 8);
+    std::vector<uint8_t> member(SG_DEFLATE_MEMBER_PITCH + 64);
+    int64_t used = 0, m = 0;
+    for (int64_t off = 0; off < n; off += SG_DEFLATE_MAX_PAYLOAD, m++) {
+        const uint32_t len = (uint32_t)((n - off) < (int64_t)SG_DEFLATE_MAX_PAYLOAD ? (n - off) : (int64_t)SG_DEFLATE_MAX_PAYLOAD);
+        const uint32_t sz = sg_deflate_member(S, G, in + off, len, member.data());
+        if (used + sz > cap) return -1;
+        memcpy(out + used, member.data(), sz);
+        if (memberSizes) memberSizes[m] = sz;
+        used += sz;
+    }
+    return used;
 }
 
 
@@ -758,7 +781,17 @@ int64_t hs_bam_markdup(uint8_t *records, int64_t nBytes, const int64_t *contigSt
 }
 
 // The .bai of the file header ‖ records wrapped into BGZF members of 0xff00 payload bytes + the end-of-file member.  Returns its size (-1: malformed, -2: bai too small).
+static int64_t bam_index_impl(const uint8_t *records, int64_t nBytes, int64_t headerBytes, int32_t nRef, const uint64_t *memberOffsets, uint8_t *bai, int64_t cap);
 int64_t hs_bam_index(const uint8_t *records, int64_t nBytes, int64_t headerBytes, int32_t nRef, uint8_t *bai, int64_t cap)
+{
+    return bam_index_impl(records, nBytes, headerBytes, nRef, nullptr, bai, cap);
+}
+// the same for a file whose members are compressed: memberOffsets as hs_bgzf_deflate / snapgpu_bgzf_deflate_device report them (one per member + the end)
+int64_t hs_bam_index_members(const uint8_t *records, int64_t nBytes, int64_t headerBytes, int32_t nRef, const uint64_t *memberOffsets, uint8_t *bai, int64_t cap)
+{
+    return bam_index_impl(records, nBytes, headerBytes, nRef, memberOffsets, bai, cap);
+}
+static int64_t bam_index_impl(const uint8_t *records, int64_t nBytes, int64_t headerBytes, int32_t nRef, const uint64_t *memberOffsets, uint8_t *bai, int64_t cap)
 {
     std::vector<unsigned long long> off;
     if (!split_records(records, nBytes, off)) return -1;
@@ -787,7 +820,7 @@ int64_t hs_bam_index(const uint8_t *records, int64_t nBytes, int64_t headerBytes
     }
     const uint64_t total = (uint64_t)headerBytes + (uint64_t)nBytes;
     if (!chunks.empty()) chunks.back().end = total;
-    std::vector<uint8_t> o = sg_bai_compose(nRef, chunks, refs, total);
+    std::vector<uint8_t> o = sg_bai_compose(nRef, chunks, refs, total, memberOffsets);
     if ((int64_t)o.size() > cap) return -2;
     memcpy(bai, o.data(), o.size());
     return (int64_t)o.size();

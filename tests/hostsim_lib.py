@@ -62,6 +62,8 @@ def lib():
         L.hs_aligner_deferred.restype = C.c_int64
         L.hs_aligner_deferred.argtypes = [C.c_void_p]
         L.hs_align_single.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.hs_bgzf_deflate.restype = C.c_int64
+        L.hs_bgzf_deflate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.hs_align_single_secondary.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.hs_paired_create.restype = C.c_void_p
         L.hs_paired_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -253,3 +255,15 @@ def ag_batch(text, pat, qual, jobs, out_dtype, params):
     params = np.ascontiguousarray(params, dtype=np.int32)
     lib().hs_ag_batch(_p(params), _p(text), _p(pat), _p(qual), _p(jobs), jobs.size, _p(out), _p(poisoned))
     return out, poisoned
+
+
+def bgzf_deflate(data: np.ndarray):
+    """(BGZF stream, member sizes) of `data` (uint8) through the host build of sg_deflate.h."""
+    n = int(data.size)
+    n_members = (n + 0xff00 - 1) // 0xff00
+    out = np.zeros(n + 64 * n_members + 64, dtype=np.uint8)
+    sizes = np.zeros(max(1, n_members), dtype=np.uint32)
+    used = lib().hs_bgzf_deflate(_p(data), n, _p(out), out.size, _p(sizes))
+    if used < 0:
+        raise RuntimeError("hs_bgzf_deflate: output buffer too small")
+    return out[:used].copy(), sizes[:n_members]

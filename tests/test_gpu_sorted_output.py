@@ -2,6 +2,7 @@
 writes with `-so` (duplicates marked, .bai), and the whole chain align -> BAM records -> sort -> mark -> BGZF + .bai on the device."""
 import gzip
 import io
+import os
 import struct
 
 import numpy as np
@@ -116,10 +117,52 @@ def test_reads_to_sorted_marked_indexed_bam_on_the_device(engine, gidx, small_cf
     file_bytes = d_out[:out_bytes].cpu().numpy().tobytes() + eof
     assert gzip.GzipFile(fileobj=io.BytesIO(file_bytes)).read() == header + records
     bai = fmt.index_device(d_sorted.data_ptr(), d_offs.data_ptr(), n, used, len(header))
-    fmt.close()
     blocks = sorted_data.our_blocks(total)
     assert blocks[-1][0] + 28 == len(file_bytes) and [b[0] for b in blocks] == _member_starts(file_bytes)
     assert sorted_data.parse_bai(bai, blocks) == sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
+    # the same file with the members COMPRESSED on the device (snapgpu_bgzf_deflate_device): smaller, inflates to the same content, and the .bai made
+    # for its member offsets again says what the reference's says
+    d_out2 = torch.empty((n_members * (0xff00 + 31),), dtype=torch.uint8, device=dev)
+    z_bytes, member_offsets = fmt.bgzf_deflate_device(d_all.data_ptr(), total, d_out2.data_ptr(), d_out2.numel())
+    zfile = d_out2[:z_bytes].cpu().numpy().tobytes() + eof
+    assert z_bytes < out_bytes * 0.8 and int(member_offsets[-1]) == z_bytes
+    assert gzip.GzipFile(fileobj=io.BytesIO(zfile)).read() == header + records
+    assert _member_starts(zfile) == [int(x) for x in member_offsets]
+    zbai = fmt.index_device(d_sorted.data_ptr(), d_offs.data_ptr(), n, used, len(header), member_offsets=member_offsets)
+    zpath = str(tmp_path / "z.bam")
+    open(zpath, "wb").write(zfile)
+    assert sorted_data.parse_bai(zbai, sorted_data.bgzf_blocks(zpath)) == sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
+    fmt.close()
+
+
+def test_bgzf_deflate_on_the_device_inflates_to_the_payload(engine, gidx):
+    """snapgpu_bgzf_deflate_device on payloads of every kind: each member a valid gzip member (CRC-32, ISIZE, BSIZE) that inflates to its 65280-byte slice;
+    incompressible data falls back to stored members; sizes around the member boundary."""
+    import torch
+    dev = torch.device("cuda", 0)
+    fmt = engine.SamFormatter(gidx, engine.default_params(maxDist=14), 1024)
+    rng = np.random.default_rng(7)
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "DESIGN.md"), "rb").read()
+    payloads = {
+        "one": b"A", "three": b"ACG", "tiny": b"ACGTACGTAC", "zeros": bytes(200000), "random": rng.integers(0, 256, 150000, dtype=np.uint8).tobytes(),
+        "acgt": rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 300000).tobytes(), "text": text * 3, "exact": (text * 3)[:0xff00], "plus1": (text * 3)[:0xff00 + 1],
+        "quals": rng.choice(np.frombuffer(b"FFFFFFF:,#", dtype=np.uint8), 500000).tobytes(),
+    }
+    for name, data in payloads.items():
+        d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+        n_members = (len(data) + 0xff00 - 1) // 0xff00
+        d_out = torch.zeros((len(data) + 31 * n_members + 64,), dtype=torch.uint8, device=dev)
+        used, offs = fmt.bgzf_deflate_device(d_in.data_ptr(), len(data), d_out.data_ptr(), d_out.numel())
+        z = d_out[:used].cpu().numpy().tobytes()
+        assert _member_starts(z + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))[:-1] == [int(x) for x in offs[:-1]], name
+        assert int(offs[-1]) == used, name
+        for k in range(n_members):
+            assert gzip.decompress(z[int(offs[k]):int(offs[k + 1])]) == data[k * 0xff00:(k + 1) * 0xff00], (name, k)
+        if name == "random":
+            assert used == len(data) + 31 * n_members           # stored
+        if name in ("zeros", "acgt", "text", "quals"):
+            assert used < 0.55 * len(data), (name, used)
+    fmt.close()
 
 
 def _member_starts(raw):

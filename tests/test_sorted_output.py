@@ -19,6 +19,7 @@ def hs():
     L = C.CDLL(hostsim_lib.build())
     L.hs_bam_markdup.restype = C.c_int64
     L.hs_bam_index.restype = C.c_int64
+    L.hs_bam_index_members.restype = C.c_int64
     return L
 
 
@@ -51,3 +52,65 @@ def test_bam_index_equals_the_reference_index(cases, hs, name):
     want = sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
     assert got == want
     assert sum(len(b) for b, _ in want) > 3 * len(c.refs) or "dense" in name
+
+
+def _members(raw: bytes):
+    out, p = [], 0
+    while p < len(raw):
+        assert raw[p:p + 4] == bytes([31, 139, 8, 4]) and raw[p + 12:p + 14] == b"BC"
+        size = (raw[p + 16] | (raw[p + 17] << 8)) + 1
+        out.append(raw[p:p + size]); p += size
+    return out
+
+
+def test_deflate_members_inflate_to_the_payload():
+    """sg_deflate.h (host build): every member is a gzip member any inflater accepts -- header, BSIZE, CRC-32, ISIZE -- and gives back its slice of the
+    payload; incompressible data is stored; low-entropy data gets close to (or beats) zlib -6."""
+    import gzip, os, zlib
+    rng = np.random.default_rng(1)
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "DESIGN.md"), "rb").read()
+    lines = []
+    for i in range(3000):
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 150).tobytes()
+        q = rng.choice(np.frombuffer(b"FFFFFFF:,#", dtype=np.uint8), 150).tobytes()
+        lines.append(b"read%07d\t0\tchr1\t%d\t60\t150M\t*\t0\t0\t%s\t%s\tPG:Z:SNAP\tNM:i:0\tRG:Z:FASTQ\n" % (i, 1000 + i * 37, seq, q))
+    payloads = {"empty": b"", "random": rng.integers(0, 256, 150000, dtype=np.uint8).tobytes(), "zeros": bytes(200000),
+                "acgt": rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 300000).tobytes(), "text": text * 3, "exact": (text * 3)[:0xff00], "plus1": (text * 3)[:0xff00 + 1],
+                "sam": b"".join(lines),
+                "skewed": bytes(rng.choice(np.arange(256, dtype=np.uint8), 100000, p=(lambda w: w / w.sum())(1.0 / np.arange(1, 257) ** 3)))}
+    for n in (1, 2, 3, 4, 5, 7, 8, 9, 100):
+        payloads["tiny%d" % n] = bytes(rng.integers(65, 69, n, dtype=np.uint8))
+    for name, data in payloads.items():
+        z, sizes = hostsim_lib.bgzf_deflate(np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(0, dtype=np.uint8))
+        ms = _members(z.tobytes())
+        assert [len(m) for m in ms] == [int(x) for x in sizes], name
+        assert len(ms) == (len(data) + 0xff00 - 1) // 0xff00, name
+        for k, m in enumerate(ms):
+            assert gzip.decompress(m) == data[k * 0xff00:(k + 1) * 0xff00], (name, k)
+        if name == "random":
+            assert len(z) == len(data) + 31 * len(ms)
+        if name in ("acgt", "text", "sam", "skewed", "zeros"):
+            assert len(z) < 1.3 * len(zlib.compress(data, 6)) + 2000, (name, len(z), len(zlib.compress(data, 6)))
+
+
+@pytest.mark.parametrize("name", ["single", "paired_dense"])
+def test_bam_index_of_the_compressed_file_equals_the_reference_index(cases, hs, name):
+    """header ‖ records deflated member by member (sg_deflate.h, host build): the file inflates to the reference file's content and the .bai composed for
+    its member offsets says what the reference's .bai says."""
+    import gzip
+    c = cases[name]
+    blob = b"".join(c.marked)
+    header = gzip.open(c.bam, "rb").read()[:c.header_bytes]
+    z, sizes = hostsim_lib.bgzf_deflate(np.frombuffer(header + blob, dtype=np.uint8).copy())
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    zfile = z.tobytes() + eof
+    assert gzip.decompress(zfile) == header + blob and len(zfile) < 0.8 * (len(header) + len(blob))
+    offs = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))]).astype(np.uint64)
+    bai = (C.c_uint8 * (1 << 22))()
+    n = hs.hs_bam_index_members(blob, C.c_int64(len(blob)), C.c_int64(c.header_bytes), C.c_int32(len(c.refs)), offs.ctypes.data_as(C.c_void_p), bai, C.c_int64(1 << 22))
+    assert n > 8
+    blocks, u = [], 0
+    for k, m in enumerate(_members(zfile)):
+        isize = int.from_bytes(m[-4:], "little")
+        blocks.append((int(offs[k]) if k < len(offs) - 1 else int(offs[-1]), u, isize)); u += isize
+    assert sorted_data.parse_bai(bytes(bai[:n]), blocks) == sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
