@@ -342,7 +342,7 @@ def run_workload(c, args, name, batches, W, K, sample_clocks=False):
                 "note": "latency/issue-bound integer state machine: ~%.0f B of index+reference+read traffic per read" % (alg_bytes / B)}
     if entry:
         roofline["traffic_over_algorithmic"] = round(entry["dram_bytes_per_launch"] / max(1.0, alg_bytes), 2)
-        roofline["traffic_source"] = "profiles/traffic.json, ncu --set full of these kernels (%s)" % entry["stamp"]
+        roofline["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one step's launches of these kernels (%s), captured with `%s`" % (entry["stamp"], str(entry.get("captured_with", "ncu"))[:160])
         n_inst = entry.get("warp_instructions_per_step")
         sm_mhz = clocks.get("sm_mhz") or c.__dict__.get("sm_mhz")
         if n_inst and sm_mhz:
@@ -542,7 +542,7 @@ def seed_phase(args, idx, batches, device, peak, peak_src):
     if entry:
         out["dram_bytes_per_lookup"] = round(entry["dram_bytes_per_launch"] / n, 1)
         out["dram_over_algorithmic"] = round(entry["dram_bytes_per_launch"] / alg, 2)
-        out["dram_source"] = "profiles/traffic.json, ncu --set full of these kernels (%s)" % entry["stamp"]
+        out["dram_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (%s), captured with `%s`" % (entry["stamp"], str(entry.get("captured_with", "ncu"))[:160])
     else:
         out["dram_bytes_per_lookup"] = None
         out["dram_note"] = why

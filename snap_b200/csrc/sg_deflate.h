@@ -39,12 +39,14 @@
 #if defined(__CUDA_ARCH__)
 #define SGD_TID ((uint32_t)threadIdx.x)
 #define SGD_NT ((uint32_t)blockDim.x)
+#define SGD_WARP ((uint32_t)threadIdx.x >> 5)
 #define SGD_SYNC() __syncthreads()
 #define SGD_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define SGD_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #else
 #define SGD_TID 0u
 #define SGD_NT 1u
+#define SGD_WARP 0u
 #define SGD_SYNC() do { } while (0)
 #define SGD_ATOMIC_OR(p, v) (*(p) |= (v))
 #define SGD_ATOMIC_ADD(p, v) (*(p) += (v))
@@ -63,6 +65,9 @@ struct SgDeflateShared {
     uint32_t partial[1024 + 1];                        // per-thread sums of the prefix sums (block size <= 1024), CRC partials
     uint32_t crcTable[256];
     uint32_t byteFreq[256];
+    uint32_t warpHist[32][SG_DEFLATE_NLIT + 2];        // one histogram per warp (bytes, then literal/length symbols): a payload has few distinct values and
+                                                       // same-address shared-memory atomics serialise; summed into byteFreq / litFreq afterwards
+    uint32_t crcGroup[32], crcGroupBytes[32];
     uint8_t  litCost[256];                             // estimated cost of a literal of each byte value, in 1/8 bit (from the byte histogram)
     uint32_t x2n[32];
     uint32_t headerBits, totalBits, nUsedLit, nUsedDist, crc;
@@ -236,35 +241,51 @@ SG_HD uint32_t sg_deflate_member(SgDeflateShared &S, const SgDeflateArena &G, co
     for (uint32_t i = tid; i < 256u; i += nt) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1u) ? (0xedb88320u ^ (c >> 1)) : (c >> 1); S.crcTable[i] = c; }
     if (tid == 0) { uint32_t v = 1u << 30; S.x2n[0] = v; for (int k = 1; k < 32; k++) { v = sgd_crc_multmodp(v, v); S.x2n[k] = v; } }
     SGD_SYNC();
-    // ---- CRC-32 of the payload: one slice per thread, joined over GF(2) (crc(A || B) = crc(A) x^(8|B|) + crc(B)) ----
+    // ---- CRC-32 of the payload: 1024 slices, joined over GF(2) in two levels (crc(A || B) = crc(A) x^(8|B|) + crc(B)): 32 threads join 32 slices
+    //      each, one joins the 32 groups ----
     {
-        const uint32_t slices = nt < 1024u ? nt : 1024u;
-        const uint32_t slice = (n + slices - 1u) / slices;
-        for (uint32_t t = tid; t < slices; t += nt) {
+        const uint32_t slice = (n + 1023u) / 1024u;
+        for (uint32_t t = tid; t < 1024u; t += nt) {
             const uint32_t lo = t * slice < n ? t * slice : n, hi = lo + slice < n ? lo + slice : n;
             uint32_t crc = 0xffffffffu;
             for (uint32_t k = lo; k < hi; k++) crc = S.crcTable[(crc ^ S.buf[k]) & 0xffu] ^ (crc >> 8);
             S.partial[t] = crc ^ 0xffffffffu;
         }
         SGD_SYNC();
-        if (tid == 0) {
+        for (uint32_t g = tid; g < 32u; g += nt) {
             const uint32_t xs = sgd_crc_x8n(S.x2n, slice);
-            uint32_t crc = S.partial[0];
-            for (uint32_t t = 1; t < slices; t++) {
+            uint32_t crc = 0, bytes = 0;
+            for (uint32_t t = 32u * g; t < 32u * g + 32u; t++) {
                 const uint32_t lo = t * slice < n ? t * slice : n, hi = lo + slice < n ? lo + slice : n;
                 if (hi == lo) break;
-                crc = sgd_crc_multmodp(hi - lo == slice ? xs : sgd_crc_x8n(S.x2n, hi - lo), crc) ^ S.partial[t];
+                crc = bytes ? (sgd_crc_multmodp(hi - lo == slice ? xs : sgd_crc_x8n(S.x2n, hi - lo), crc) ^ S.partial[t]) : S.partial[t];
+                bytes += hi - lo;
             }
-            S.crc = n ? crc : 0u;
+            S.crcGroup[g] = crc; S.crcGroupBytes[g] = bytes;
+        }
+        SGD_SYNC();
+        if (tid == 0) {
+            uint32_t crc = 0, bytes = 0;
+            for (uint32_t g = 0; g < 32u; g++) {
+                const uint32_t b = S.crcGroupBytes[g];
+                if (b == 0) break;
+                crc = bytes ? (sgd_crc_multmodp(sgd_crc_x8n(S.x2n, b), crc) ^ S.crcGroup[g]) : S.crcGroup[g];
+                bytes += b;
+            }
+            S.crc = crc;
         }
         SGD_SYNC();
     }
     // ---- what a literal costs, roughly: -log2 of the byte's share of the payload.  A match is only worth taking when the literals it replaces
     //      would cost more than its own length / distance symbols (short far matches in low-entropy data -- 4-bit packed bases -- would not) ----
-    for (uint32_t i = tid; i < n; i += nt) SGD_ATOMIC_ADD(&S.byteFreq[S.buf[i]], 1u);
+    for (uint32_t i = tid; i < 32u * (SG_DEFLATE_NLIT + 2); i += nt) (&S.warpHist[0][0])[i] = 0;
+    SGD_SYNC();
+    for (uint32_t i = tid; i < n; i += nt) SGD_ATOMIC_ADD(&S.warpHist[SGD_WARP][S.buf[i]], 1u);
     SGD_SYNC();
     for (uint32_t b = tid; b < 256u; b += nt) {
-        const uint32_t f = S.byteFreq[b];
+        uint32_t f = 0;
+        for (uint32_t w = 0; w < 32u; w++) f += S.warpHist[w][b];
+        S.byteFreq[b] = f;
         uint32_t c = f ? sgd_log2_x8(n) - sgd_log2_x8(f) : 120u;
         S.litCost[b] = (uint8_t)(c < 8u ? 8u : (c > 120u ? 120u : c));
     }
@@ -307,21 +328,40 @@ SG_HD uint32_t sg_deflate_member(SgDeflateShared &S, const SgDeflateArena &G, co
     {
         uint16_t *cur = G.jumpA, *nxt = G.jumpB;
         for (uint32_t span = 1; span < n; span <<= 1) {
-            for (uint32_t i = tid; i < n; i += nt) {
-                const uint32_t j = cur[i];
-                if ((S.sel[i >> 5] >> (i & 31u)) & 1u) { if (j < n) SGD_ATOMIC_OR(&S.sel[j >> 5], 1u << (j & 31u)); }
-                nxt[i] = cur[j];
+            // four positions per step: the two dependent loads of each (cur[i], then cur[cur[i]]) are issued together, so the L2 latency of the
+            // jump tables is paid once per four positions
+            for (uint32_t i0 = tid; i0 < n; i0 += 4u * nt) {
+                uint32_t j[4], k[4];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) { const uint32_t i = i0 + (uint32_t)u * nt; j[u] = i < n ? cur[i] : n; }
+                #pragma unroll
+                for (int u = 0; u < 4; u++) k[u] = cur[j[u]];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + (uint32_t)u * nt;
+                    if (i >= n) continue;
+                    if ((S.sel[i >> 5] >> (i & 31u)) & 1u) { if (j[u] < n) SGD_ATOMIC_OR(&S.sel[j[u] >> 5], 1u << (j[u] & 31u)); }
+                    nxt[i] = (uint16_t)k[u];
+                }
             }
             SGD_SYNC();
             uint16_t *t = cur; cur = nxt; nxt = t;
         }
     }
     // ---- 3. histograms, codes ----
+    for (uint32_t i = tid; i < 32u * (SG_DEFLATE_NLIT + 2); i += nt) (&S.warpHist[0][0])[i] = 0;
+    SGD_SYNC();
     for (uint32_t i = tid; i < n; i += nt) {
         if (!((S.sel[i >> 5] >> (i & 31u)) & 1u)) continue;
         SgDeflateToken t; sgd_token(S, G, i, &t);
-        SGD_ATOMIC_ADD(&S.litFreq[t.litSym], 1u);
+        SGD_ATOMIC_ADD(&S.warpHist[SGD_WARP][t.litSym], 1u);
         if (t.match) SGD_ATOMIC_ADD(&S.distFreq[t.distSym], 1u);
+    }
+    SGD_SYNC();
+    for (uint32_t b = tid; b < (uint32_t)SG_DEFLATE_NLIT; b += nt) {
+        uint32_t f = 0;
+        for (uint32_t w = 0; w < 32u; w++) f += S.warpHist[w][b];
+        S.litFreq[b] = f;
     }
     SGD_SYNC();
     if (tid == 0) {

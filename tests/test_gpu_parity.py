@@ -378,7 +378,7 @@ def test_properties_at_scale(engine, small_cfg):
     assert differing(r1, r2[inv]) == []
     small = engine.SingleAligner(ix, engine.default_params(maxDist=14), 7000)
     r3, c3 = small.align(rb)
-    assert differing(r1, r3) == [] and c1["lvCalls"] == c3["lvCalls"] and small.launch_count() == 2 * ((n + 6999) // 7000 + 1)      # two-pass launch per pipeline stage; the first 7000 reads are cut into a small stage and the rest (align_host_impl)
+    assert differing(r1, r3) == [] and c1["lvCalls"] == c3["lvCalls"] and small.launch_count() == 2 * 2 * ((n + 6999) // 7000)      # calls of at most 7000 reads; each is cut into a small first pipeline stage and the rest (align_host_impl), two-pass launch per stage
     aligned = r1["status"] != 0
     assert aligned.mean() > 0.995
     start = np.array(starts)[rb.truth_contig] + rb.truth_pos
@@ -423,7 +423,7 @@ def test_pairs_large_index_and_split_batches(engine, small_cfg, reflib):
     assert differing_pairs(want, got) == []
     small = engine.PairedAligner(ix, engine.default_params(**{"numSeedsFromCommandLine": 8, **kw}), engine.default_paired_params(**pkw), 100)
     got2, c2 = small.align(pb)
-    assert differing_pairs(want, got2) == [] and c1["lvCalls"] == c2["lvCalls"] and small.launch_count() == 4 * ((pb.n // 2 + 99) // 100 + 1)      # three stages + retry launch per pipeline stage (the first 100 pairs go in two stages)
+    assert differing_pairs(want, got2) == [] and c1["lvCalls"] == c2["lvCalls"] and small.launch_count() == 4 * 2 * ((pb.n // 2 + 99) // 100)      # calls of at most 100 pairs, each in two pipeline stages (a small first one, then the rest); three stages + retry launch per pipeline stage
     big.close(); small.close(); ix.close()
 
 
