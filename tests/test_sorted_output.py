@@ -114,3 +114,44 @@ def test_bam_index_of_the_compressed_file_equals_the_reference_index(cases, hs, 
         isize = int.from_bytes(m[-4:], "little")
         blocks.append((int(offs[k]) if k < len(offs) - 1 else int(offs[-1]), u, isize)); u += isize
     assert sorted_data.parse_bai(bytes(bai[:n]), blocks) == sorted_data.parse_bai(c.bai, sorted_data.bgzf_blocks(c.bam))
+
+
+def test_deflate_fuzz_and_the_code_length_limit():
+    """Structured random payloads of every size class, and one whose byte counts are Fibonacci numbers (a Huffman tree 21 levels deep: the 15-bit
+    limit and the Kraft repair must kick in) -- every member inflates to its slice."""
+    import gzip
+    rng = np.random.default_rng(11)
+    fib = [1, 1]
+    while len(fib) < 22:
+        fib.append(fib[-1] + fib[-2])
+    deep = np.concatenate([np.full(c, 40 + k, dtype=np.uint8) for k, c in enumerate(fib)])
+    rng.shuffle(deep)
+    payloads = [deep.tobytes()]
+    for trial in range(60):
+        n = int(rng.choice([rng.integers(0, 300), rng.integers(300, 70000), rng.integers(65000, 66000), rng.integers(130000, 200000)]))
+        kind = trial % 6
+        if kind == 0:
+            a = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == 1:
+            a = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), n, p=[0.3, 0.2, 0.2, 0.29, 0.01])
+        elif kind == 2:      # runs
+            a = np.repeat(rng.integers(0, 256, n // 7 + 1, dtype=np.uint8), rng.integers(1, 600, n // 7 + 1))[:n]
+        elif kind == 3:      # repeats of a motif with mutations, periods around the stride and the window
+            m = rng.integers(0, 256, int(rng.choice([3, 5, 64, 1024, 1500, 33000])), dtype=np.uint8)
+            a = np.tile(m, n // m.size + 1)[:n].copy()
+            if n:
+                a[rng.integers(0, n, n // 50)] = 0
+        elif kind == 4:      # two alphabets glued
+            a = np.concatenate([rng.integers(0, 4, n // 2, dtype=np.uint8), rng.integers(0, 256, n - n // 2, dtype=np.uint8)])
+        else:
+            a = rng.integers(0, 2, n, dtype=np.uint8) * 255
+        payloads.append(np.ascontiguousarray(a, dtype=np.uint8).tobytes())
+    for k, data in enumerate(payloads):
+        z, sizes = hostsim_lib.bgzf_deflate(np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(0, dtype=np.uint8))
+        ms = _members(z.tobytes())
+        assert len(ms) == (len(data) + 0xff00 - 1) // 0xff00 and [len(m) for m in ms] == [int(x) for x in sizes], k
+        assert b"".join(gzip.decompress(m) for m in ms) == data, k
+        assert all(len(m) <= 0xff00 + 31 for m in ms), k
+    # the deep one really was compressed with codes (not stored), close to its entropy
+    z, _ = hostsim_lib.bgzf_deflate(np.frombuffer(payloads[0], dtype=np.uint8).copy())
+    assert len(z) < 0.5 * len(payloads[0])
