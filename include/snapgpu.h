@@ -24,7 +24,7 @@ extern "C" {
 
 #define SNAPGPU_ABI_VERSION 6   /* 2: snapgpu_sam_format_* take frontClipped / clippedLens before `results`; 3: groups, replicate, host_alloc, random-sector rate;
                                  * 4: snapgpu_sam_sort_device; 5: snapgpu_bam_markdup_device, snapgpu_bam_index_device;
-                                 * 6: snapgpu_align_single_secondary(_device) (-om), snapgpu_bgzf_deflate_device, snapgpu_bam_index_members_device */
+                                 * 6: snapgpu_align_single_secondary(_device) (-om), snapgpu_bgzf_deflate_device, snapgpu_bam_index_members_device, snapgpu_sam_header */
 
 /* AlignmentResult enum, reference SNAPLib/AlignmentResult.h:34 */
 enum { SNAPGPU_NOT_FOUND = 0, SNAPGPU_SINGLE_HIT = 1, SNAPGPU_MULTIPLE_HITS = 2 };
@@ -412,6 +412,14 @@ int  snapgpu_sam_format_paired(snapgpu_sam *s, int64_t nReads, const char *bases
  * to back instead of SAM text; snapgpu_bgzf_device wraps such a stream (or a header) into BGZF members, which is what a .bam file is made of. */
 enum { SNAPGPU_FORMAT_SAM = 0, SNAPGPU_FORMAT_BAM = 1 };
 int  snapgpu_sam_set_format(snapgpu_sam *s, int format);
+/* The header that goes in front of the records (HOST buffers; no kernel): SAMFormat::writeHeader (reference SNAPLib/SAM.cpp:1203-1305) for FASTQ input --
+ * @HD VN:1.6 GO:query | SO:coordinate (sorted), the read-group line (rgLine; NULL = the reference's fallback "@RG\tID:FASTQ\tSM:sample"; stock snap-aligner
+ * passes "@RG\tID:FASTQ\tPL:Illumina\tPU:pu\tLB:lb\tSM:sm"), @PG ID:SNAP PN:SNAP CL:<commandLine> VN:<version>, one @SQ per contig in original order
+ * (LN without the chromosome padding, AH:* for ALT contigs) -- or, in SNAPGPU_FORMAT_BAM, BAMFormat::writeHeader's block (Bam.cpp:969-1030): "BAM\1",
+ * l_text, that text, n_ref, the reference table.  header || records, wrapped by snapgpu_bgzf_[deflate_]device and closed with the 28-byte BGZF
+ * end-of-file member, is a complete .bam. */
+int  snapgpu_sam_header(const snapgpu_sam *s, int sorted, const char *commandLine, const char *version, const char *rgLine,
+                        char *out, int64_t outCapacity, int64_t *outBytes);
 /* BGZF members (reference SNAPLib/GzipDataWriter.cpp; SAM spec 4.1) over nBytes of DEVICE data, written to d_out: members of up to 65280
  * payload bytes, each ONE STORED deflate block with its CRC-32 -- valid BGZF that inflates to exactly the payload (no compressor runs on
  * the device; the reference compresses, so files differ in size, not in content).  outCapacity >= nBytes + 31 per member.  Asynchronous on `cudaStream`. */

@@ -27,6 +27,7 @@
 #include "sg_bam.h"
 #include "sg_bampost.h"
 #include "sg_deflate.h"
+#include "sg_samheader.h"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -2491,6 +2492,24 @@ int snapgpu_sam_create(const snapgpu_index *idx, const snapgpu_params *params, i
     SG_CUDA(cudaMalloc((void **)&s->d_rgAuxBam, sizeof(rgBam)));
     SG_CUDA(cudaMemcpy(s->d_rgAuxBam, rgBam, sizeof(rgBam), cudaMemcpyHostToDevice));
     *out = s;
+    return 0;
+}
+
+// The file header in front of the records (host code: sg_samheader.h): SAM text, or the BAM header block when the handle is in SNAPGPU_FORMAT_BAM.
+int snapgpu_sam_header(const snapgpu_sam *s, int sorted, const char *commandLine, const char *version, const char *rgLine, char *out, int64_t outCapacity, int64_t *outBytes)
+{
+    if (!s || !out || !outBytes) return sg_fail("null argument");
+    *outBytes = 0;
+    const snapgpu_index *ix = s->index;
+    std::vector<SgHeaderContig> contigs;
+    if (!sg_header_contigs(ix->h_contigName, ix->h_contigStart, ix->h_contigIsAlt, ix->h_contigOriginal, ix->view.nBases, ix->view.chromosomePadding, &contigs))
+        return sg_fail("snapgpu_sam_header: the index has no usable contig table");
+    std::vector<uint8_t> o;
+    if (s->format == SNAPGPU_FORMAT_BAM) o = sg_bam_header(contigs, sorted != 0, commandLine, version, rgLine);
+    else { const std::string t = sg_sam_header_text(contigs, sorted != 0, commandLine, version, rgLine); o.assign(t.begin(), t.end()); }
+    if ((int64_t)o.size() > outCapacity) return sg_fail("snapgpu_sam_header: output buffer too small");
+    memcpy(out, o.data(), o.size());
+    *outBytes = (int64_t)o.size();
     return 0;
 }
 

@@ -85,7 +85,7 @@ EXPORTS = [
     "snapgpu_lookup_seeds", "snapgpu_lookup_seeds_device", "snapgpu_measure_random_sector_rate", "snapgpu_aligner_create", "snapgpu_aligner_destroy", "snapgpu_align_single",
     "snapgpu_align_single_device", "snapgpu_align_single_secondary", "snapgpu_align_single_secondary_device", "snapgpu_paired_params_default", "snapgpu_paired_aligner_create", "snapgpu_align_paired",
     "snapgpu_align_paired_device", "snapgpu_aligner_check", "snapgpu_fastq_create", "snapgpu_fastq_destroy", "snapgpu_fastq_parse_device",
-    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_bgzf_device", "snapgpu_bgzf_deflate_device", "snapgpu_bam_index_members_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_bam_markdup_device", "snapgpu_bam_index_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
+    "snapgpu_fastq_parse", "snapgpu_sam_create", "snapgpu_sam_destroy", "snapgpu_sam_format_single", "snapgpu_sam_format_paired", "snapgpu_sam_format_single_device", "snapgpu_sam_format_paired_device", "snapgpu_sam_set_format", "snapgpu_sam_header", "snapgpu_bgzf_device", "snapgpu_bgzf_deflate_device", "snapgpu_bam_index_members_device", "snapgpu_sam_sort_device", "snapgpu_sam_last_record_count", "snapgpu_bam_markdup_device", "snapgpu_bam_index_device", "snapgpu_aligner_launch_count", "snapgpu_test_lv", "snapgpu_test_ag", "snapgpu_test_lv_warp", "snapgpu_test_ag_warp",
 ]
 
 ABI_VERSION = 6          # include/snapgpu.h SNAPGPU_ABI_VERSION this mirror was written against
@@ -147,6 +147,7 @@ def lib():
         L.snapgpu_bgzf_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         L.snapgpu_sam_sort_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]
         L.snapgpu_bam_markdup_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.snapgpu_sam_header.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.snapgpu_bgzf_deflate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
         L.snapgpu_bam_index_members_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                                        C.POINTER(C.c_int64), C.c_void_p]
@@ -483,6 +484,13 @@ class SamFormatter:
         marked = C.c_int64(0)
         _check(lib().snapgpu_bam_markdup_device(self.handle, C.c_void_p(d_records), C.c_void_p(d_offsets), n_records, C.byref(marked), C.c_void_p(stream)))
         return marked.value
+
+    def header(self, command_line: bytes, version: bytes, rg_line: bytes | None = b"@RG\tID:FASTQ\tPL:Illumina\tPU:pu\tLB:lb\tSM:sm", sorted_: bool = False) -> bytes:
+        """The file header in front of the records: SAM text, or the BAM header block after set_format(bam=True) (snapgpu_sam_header)."""
+        buf = np.zeros(1 << 20, dtype=np.uint8)
+        used = C.c_int64(0)
+        _check(lib().snapgpu_sam_header(self.handle, 1 if sorted_ else 0, command_line, version, rg_line, _p(buf), buf.size, C.byref(used)))
+        return buf[:used.value].tobytes()
 
     def bgzf_deflate_device(self, d_in, n_bytes, d_out, out_capacity, stream=0):
         """Compressed BGZF members over device data (snapgpu_bgzf_deflate_device); returns (bytes written to d_out, member offsets [nMembers + 1])."""

@@ -20,6 +20,7 @@
 #include "../../snap_b200/csrc/sg_bam.h"
 #include "../../snap_b200/csrc/sg_bampost.h"
 #include "../../snap_b200/csrc/sg_deflate.h"
+#include "../../snap_b200/csrc/sg_samheader.h"
 
 struct HsIndex {
     SgHostIndex host;
@@ -302,6 +303,22 @@ int64_t hs_bgzf_deflate(const uint8_t *in, int64_t n, uint8_t *out, int64_t cap,
         used += sz;
     }
     return used;
+}
+
+
+// snapgpu_sam_header on the host: the SAM header text (bam = 0) or the BAM header block (bam = 1) of a file over this index.  Returns its size, -1 if cap is
+// too small, -2 if the index has no usable contig table.
+int64_t hs_sam_header(void *vix, int bam, int sorted, const char *commandLine, const char *version, const char *rgLine, uint8_t *out, int64_t cap)
+{
+    HsIndex *ix = (HsIndex *)vix;
+    std::vector<SgHeaderContig> contigs;
+    if (!sg_header_contigs(ix->host.contigName, ix->host.contigStart, ix->host.contigIsAlt, ix->host.contigOriginal, ix->view.nBases, ix->host.chromosomePadding, &contigs)) return -2;
+    std::vector<uint8_t> o;
+    if (bam) o = sg_bam_header(contigs, sorted != 0, commandLine, version, rgLine);
+    else { const std::string t = sg_sam_header_text(contigs, sorted != 0, commandLine, version, rgLine); o.assign(t.begin(), t.end()); }
+    if ((int64_t)o.size() > cap) return -1;
+    memcpy(out, o.data(), o.size());
+    return (int64_t)o.size();
 }
 
 

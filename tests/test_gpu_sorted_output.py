@@ -170,3 +170,19 @@ def _member_starts(raw):
     while p < len(raw):
         out.append(p); p += struct.unpack("<H", raw[p + 16:p + 18])[0] + 1
     return out
+
+
+def test_file_header_composed_by_the_library_equals_the_reference_header(engine, gidx, cases):
+    """snapgpu_sam_header (host code behind the C ABI): the BAM header block of the reference binary's sorted .bam, byte for byte, given the command line,
+    version and read-group line that file carries; and the SAM form of the same header."""
+    c = cases["single"]
+    header = gzip.open(c.bam, "rb").read()[:c.header_bytes]
+    text = header[8:8 + int.from_bytes(header[4:8], "little")]
+    pg = [l for l in text.split(b"\n") if l.startswith(b"@PG\tID:SNAP\t")][0]
+    rg = [l for l in text.split(b"\n") if l.startswith(b"@RG")][0]
+    cl, vn = pg.split(b"\tCL:")[1].rsplit(b"\tVN:", 1)[0], pg.rsplit(b"\tVN:", 1)[1]
+    fmt = engine.SamFormatter(gidx, engine.default_params(maxDist=14), 1024)
+    assert fmt.header(cl, vn, rg, sorted_=True) == text          # SAM form
+    fmt.set_format(bam=True)
+    assert fmt.header(cl, vn, rg, sorted_=True) == header
+    fmt.close()

@@ -155,3 +155,45 @@ def test_deflate_fuzz_and_the_code_length_limit():
     # the deep one really was compressed with codes (not stored), close to its entropy
     z, _ = hostsim_lib.bgzf_deflate(np.frombuffer(payloads[0], dtype=np.uint8).copy())
     assert len(z) < 0.5 * len(payloads[0])
+
+
+def _header_via_hostsim(idx_dir, bam, sorted_, cl, vn, rg):
+    L = C.CDLL(hostsim_lib.build())
+    L.hs_index_open.restype = C.c_void_p
+    L.hs_index_open.argtypes = [C.c_char_p]
+    L.hs_sam_header.restype = C.c_int64
+    L.hs_sam_header.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64]
+    ix = L.hs_index_open(idx_dir.encode())
+    assert ix
+    buf = (C.c_uint8 * (1 << 20))()
+    n = L.hs_sam_header(ix, 1 if bam else 0, 1 if sorted_ else 0, cl, vn, rg, buf, C.c_int64(1 << 20))
+    assert n > 0
+    return bytes(buf[:n])
+
+
+def _pg_fields(text: bytes):
+    pg = [l for l in text.split(b"\n") if l.startswith(b"@PG\tID:SNAP\t")][0]
+    cl = pg.split(b"\tCL:")[1].rsplit(b"\tVN:", 1)[0]
+    vn = pg.rsplit(b"\tVN:", 1)[1]
+    rg = [l for l in text.split(b"\n") if l.startswith(b"@RG")][0]
+    return cl, vn, rg
+
+
+def test_file_headers_equal_the_reference_files(cases, small_cfg, reflib, tmp_path):
+    """sg_samheader.h: the BAM header block (magic, text, reference table) of the reference binary's sorted .bam, and the header lines of its unsorted .sam,
+    byte for byte -- given the command line, version and read-group line those files carry."""
+    import gzip, subprocess
+    c = cases["single"]
+    want = gzip.open(c.bam, "rb").read()[:c.header_bytes]
+    l_text = int.from_bytes(want[4:8], "little")
+    cl, vn, rg = _pg_fields(want[8:8 + l_text])
+    assert _header_via_hostsim(small_cfg.idx, True, True, cl, vn, rg) == want
+    fq = str(tmp_path / "r.fq")
+    small_cfg.reads["std150"].write_fastq(fq)
+    sam = str(tmp_path / "o.sam")
+    r = subprocess.run([reflib.SNAP_ALIGNER, "single", small_cfg.idx, fq, "-o", sam, "-t", "1"], capture_output=True, text=True)
+    assert r.returncode == 0
+    lines = open(sam, "rb").read().split(b"\n")
+    hdr = b"".join(l + b"\n" for l in lines if l.startswith(b"@"))
+    cl, vn, rg = _pg_fields(hdr)
+    assert _header_via_hostsim(small_cfg.idx, False, False, cl, vn, rg) == hdr
