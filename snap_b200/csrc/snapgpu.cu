@@ -2157,13 +2157,19 @@ int snapgpu_align_single_secondary(snapgpu_aligner *a, int64_t n, const char *ba
     if (n == 0) return 0;
     SG_CUDA(cudaSetDevice(a->device));
     // a cold path: plain staging, no pipeline.  Reads are packed back to back.
-    std::vector<uint64_t> off((size_t)n);
+    std::vector<uint64_t> off;
+    std::vector<char> hb, hq;
     uint64_t total = 0;
-    for (int64_t i = 0; i < n; i++) {
-        if (lens[i] > a->params.maxReadLen) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
-        off[(size_t)i] = total; total += lens[i];
+    try {
+        off.resize((size_t)n);
+        for (int64_t i = 0; i < n; i++) {
+            if (lens[i] > a->params.maxReadLen) return sg_fail("a read is longer than the aligner's configured maximum (SNAPGPU_MAX_READ_LEN)");
+            off[(size_t)i] = total; total += lens[i];
+        }
+        hb.resize((size_t)total + 1); hq.resize((size_t)total + 1);
+    } catch (const std::bad_alloc &) {
+        return sg_fail("snapgpu_align_single_secondary: out of host memory");
     }
-    std::vector<char> hb((size_t)total + 1), hq((size_t)total + 1);
     for (int64_t i = 0; i < n; i++) {
         memcpy(hb.data() + off[(size_t)i], bases + offsets[i], lens[i]);
         memcpy(hq.data() + off[(size_t)i], quals + offsets[i], lens[i]);
@@ -2501,15 +2507,19 @@ int snapgpu_sam_header(const snapgpu_sam *s, int sorted, const char *commandLine
     if (!s || !out || !outBytes) return sg_fail("null argument");
     *outBytes = 0;
     const snapgpu_index *ix = s->index;
-    std::vector<SgHeaderContig> contigs;
-    if (!sg_header_contigs(ix->h_contigName, ix->h_contigStart, ix->h_contigIsAlt, ix->h_contigOriginal, ix->view.nBases, ix->view.chromosomePadding, &contigs))
-        return sg_fail("snapgpu_sam_header: the index has no usable contig table");
-    std::vector<uint8_t> o;
-    if (s->format == SNAPGPU_FORMAT_BAM) o = sg_bam_header(contigs, sorted != 0, commandLine, version, rgLine);
-    else { const std::string t = sg_sam_header_text(contigs, sorted != 0, commandLine, version, rgLine); o.assign(t.begin(), t.end()); }
-    if ((int64_t)o.size() > outCapacity) return sg_fail("snapgpu_sam_header: output buffer too small");
-    memcpy(out, o.data(), o.size());
-    *outBytes = (int64_t)o.size();
+    try {
+        std::vector<SgHeaderContig> contigs;
+        if (!sg_header_contigs(ix->h_contigName, ix->h_contigStart, ix->h_contigIsAlt, ix->h_contigOriginal, ix->view.nBases, ix->view.chromosomePadding, &contigs))
+            return sg_fail("snapgpu_sam_header: the index has no usable contig table");
+        std::vector<uint8_t> o;
+        if (s->format == SNAPGPU_FORMAT_BAM) o = sg_bam_header(contigs, sorted != 0, commandLine, version, rgLine);
+        else { const std::string t = sg_sam_header_text(contigs, sorted != 0, commandLine, version, rgLine); o.assign(t.begin(), t.end()); }
+        if ((int64_t)o.size() > outCapacity) return sg_fail("snapgpu_sam_header: output buffer too small");
+        memcpy(out, o.data(), o.size());
+        *outBytes = (int64_t)o.size();
+    } catch (const std::bad_alloc &) {
+        return sg_fail("snapgpu_sam_header: out of host memory");
+    }
     return 0;
 }
 
