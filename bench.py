@@ -166,7 +166,7 @@ def traffic_entry(workload, batch_reads, genome_mbp):
         return None, "no capture of this workload"
     e = dict(t[key])
     if e.get("csrc_sha16") == csrc_sha16():
-        e["stamp"] = "csrc_sha16 %s" % e["csrc_sha16"]
+        e["stamp"] = "csrc_sha16 %s" % e["csrc_sha16"] + ("; captured at csrc_sha16 %s, %s" % (e.get("csrc_sha16_at_capture"), e["restamped"]) if e.get("restamped") else "")
         return e, None
     now = sass_sha16_for(key)
     if e.get("sass_sha16") and now and e["sass_sha16"] == now:
