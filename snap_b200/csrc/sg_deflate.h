@@ -36,7 +36,9 @@
 #define SG_DEFLATE_NDIST 30
 #define SG_DEFLATE_MEMBER_PITCH (SG_DEFLATE_MAX_PAYLOAD + 31u)    // the largest member: stored payload + 18 header + 5 block header + 8 trailer
 
-#if defined(__CUDA_ARCH__)
+// (a test build may bring its own threads: it defines SGD_CUSTOM_THREADS and the six macros before including this file)
+#if defined(SGD_CUSTOM_THREADS)
+#elif defined(__CUDA_ARCH__)
 #define SGD_TID ((uint32_t)threadIdx.x)
 #define SGD_NT ((uint32_t)blockDim.x)
 #define SGD_WARP ((uint32_t)threadIdx.x >> 5)

@@ -197,3 +197,23 @@ def test_file_headers_equal_the_reference_files(cases, small_cfg, reflib, tmp_pa
     hdr = b"".join(l + b"\n" for l in lines if l.startswith(b"@"))
     cl, vn, rg = _pg_fields(hdr)
     assert _header_via_hostsim(small_cfg.idx, False, False, cl, vn, rg) == hdr
+
+
+@pytest.mark.parametrize("threads", [32, 96, 256, 1024])
+def test_deflate_run_by_a_block_of_host_threads(threads):
+    """sg_deflate.h with its thread block made of REAL threads (tests/blocksim: threadIdx = a thread-local, __syncthreads = a pthread barrier, atomics =
+    relaxed atomic builtins): the per-thread ranges, per-warp histograms, strided loops and barrier placement the one-thread host build cannot exercise.
+    Every member inflates to its slice and every thread returns the same member size; partial warps' worth of threads (96) and the kernel's own 1024."""
+    import gzip, os
+    import blocksim_lib
+    rng = np.random.default_rng(5)
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "DESIGN.md"), "rb").read()
+    payloads = [text[:0xff00 + 700], rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 70000).tobytes(), bytes(40000),
+                rng.integers(0, 256, 30000, dtype=np.uint8).tobytes(), b"A", b"ACGTACGTAA", rng.choice(np.frombuffer(b"FFFFFFF:,#", dtype=np.uint8), 0xff00).tobytes()]
+    if threads == 1024:
+        payloads = payloads[:3] + payloads[4:6]
+    for k, data in enumerate(payloads):
+        z, sizes = blocksim_lib.bgzf_deflate(np.frombuffer(data, dtype=np.uint8).copy(), threads)
+        ms = _members(z.tobytes())
+        assert [len(m) for m in ms] == [int(x) for x in sizes] and len(ms) == (len(data) + 0xff00 - 1) // 0xff00, (threads, k)
+        assert b"".join(gzip.decompress(m) for m in ms) == data, (threads, k)
