@@ -146,13 +146,25 @@ static inline bool sg_load_index_directory(const std::string &dir, SgHostIndex &
         ix.tableMagic.assign(nHashTables, 0);
         for (unsigned t = 0; t < nHashTables; t++) ix.tableMagic[t] = ~0ULL / ix.tableSize[t];
     }
+    // The image keeps every entry 4-byte aligned: the lookup reads an entry's values -- and hands out a pointer to a singleton hit -- as 32-bit words
+    // (sg_fill_hits), which a GPU cannot do at an odd address.  Seed lengths whose key is not a multiple of 4 bytes (-s 21..32: 5-7 key bytes, entries of
+    // 9-11 bytes in the file; 13-15 with -large) are therefore re-strided to the next multiple of 4, the key's bytes followed by zero padding the
+    // lookup never reads (it loads keyBytes bytes).  Seed length 20 (8-byte entries; 12 with -large) is copied as it is.
+    const uint32_t fileEntryBytes = ix.entryBytes;
+    ix.entryBytes = (fileEntryBytes + 3u) & ~3u;
     ix.tables.assign((size_t)ix.totalSlots * ix.entryBytes + 16, 0);
     {
         size_t off = 0;
         for (unsigned t = 0; t < nHashTables; t++) {
             off += 36;
-            size_t bytes = (size_t)ix.tableSize[t] * ix.entryBytes;
-            memcpy(ix.tables.data() + (size_t)ix.tableStart[t] * ix.entryBytes, &buf[off], bytes);
+            size_t bytes = (size_t)ix.tableSize[t] * fileEntryBytes;
+            uint8_t *dst = ix.tables.data() + (size_t)ix.tableStart[t] * ix.entryBytes;
+            if (fileEntryBytes == ix.entryBytes) {
+                memcpy(dst, &buf[off], bytes);
+            } else {
+                const uint8_t *src = &buf[off];
+                for (uint64_t e = 0; e < ix.tableSize[t]; e++) memcpy(dst + (size_t)e * ix.entryBytes, src + (size_t)e * fileEntryBytes, fileEntryBytes);
+            }
             off += bytes;
         }
     }

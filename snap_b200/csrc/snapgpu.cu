@@ -1108,7 +1108,8 @@ int snapgpu_index_build_device(const char *d_bases, int64_t nBases, const int64_
 int snapgpu_index_save(const snapgpu_index *ix, const char *directory)
 {
     if (!ix || !directory) return sg_fail("null argument");
-    if (ix->view.entryBytes != 8 && ix->view.entryBytes != 12) return sg_fail("snapgpu_index_save: unsupported entry geometry");
+    if (ix->view.keyBytes != 4 || (ix->view.entryBytes != 8 && ix->view.entryBytes != 12))
+        return sg_fail("snapgpu_index_save: unsupported entry geometry (only 4-byte keys: the image of other seed lengths is re-strided, see sg_load_index_directory)");
     SG_CUDA(cudaSetDevice(ix->device));
     if (ix->view.layout == SG_LAYOUT_BUCKET) {
         // The reference's directory format holds the reference's tables.  An index built on the device is built once more, in that

@@ -405,3 +405,127 @@ def test_secondary_capacity_too_small_reports_the_count(reflib, small_cfg):
     _, _, n_one, _ = al.align_secondary(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS, 3, omax, mpc, capacity=1)
     assert (n_big > 1).any()
     assert np.array_equal(np.where(n_big > 1, -n_big, n_big), n_one)
+
+
+@pytest.fixture(scope="module")
+def alt_cfg(tmp_path_factory, reflib):
+    """A reference with ALT contigs: the reference's indexer marks contigs named *_alt / HLA-* as ALT (GenomeIndex.cpp:89-92), sorts them behind the
+    primary ones (so internal and original contig numbers differ) and the aligner then keeps a second score set for non-ALT placements
+    (BaseAligner.cpp:1436-1486, scoreLimit :2555-2570).  Two ALT haplotypes are near-copies (1 % / 3 % divergence + indels) of stretches of the
+    primary contigs -- reads from there have an ALT and a non-ALT placement -- and one is unrelated sequence."""
+    from snap_b200 import synth
+    d = str(tmp_path_factory.mktemp("altcfg"))
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    primary = synth.make_contigs(2, 100_000, seed=71, repeat_frac=0.15)
+
+    def haplo(src, lo, hi, div):
+        c = src[lo:hi].copy()
+        m = rng.random(c.size) < div
+        c[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+        for _ in range(6):
+            p = int(rng.integers(100, c.size - 100))
+            c = np.concatenate([c[:p], acgt[rng.integers(0, 4, int(rng.integers(1, 9)))], c[p + int(rng.integers(0, 6)):]])
+        return c
+
+    names = [b"chr1", b"chr1_KI270_alt", b"chr2", b"HLA-A*01:01", b"chrUn_decoy_alt"]
+    contigs = [primary[0], haplo(primary[0], 20_000, 50_000, 0.01), primary[1], haplo(primary[1], 60_000, 80_000, 0.03), acgt[rng.integers(0, 4, 15_000)]]
+    fa = os.path.join(d, "ref.fa")
+    with open(fa, "wb") as f:
+        for n, c in zip(names, contigs):
+            f.write(b">" + n + b"\n")
+            for i in range(0, c.size, 100):
+                f.write(c[i:i + 100].tobytes() + b"\n")
+    idx = os.path.join(d, "idx")
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fa, idx)
+    genome_lines = open(os.path.join(idx, "Genome"), "rb").read(2000).split(b"\n")[1:6]
+    assert [int(l.split()[1], 16) & 1 for l in genome_lines] == [0, 0, 1, 1, 1]          # three ALT contigs, behind the primary ones
+    assert [int(l.split()[2]) for l in genome_lines] == [0, 2, 1, 3, 4]                   # original contig numbers: the contigs were reordered
+    reads = synth.make_reads(contigs, 3000, 150, seed=78, sub_rate=0.01, ins_rate=0.002, del_rate=0.002)
+    return idx, reads
+
+
+ALT_SETS = {
+    "default": dict(maxDist=14),
+    "ea_off": dict(maxDist=14, altAwareness=0),
+    "gap2": dict(maxDist=14, maxScoreGapToPreferNonAltAlignment=2),
+    "noag_d20": dict(maxDist=20, useAffineGap=0),
+    "d8_esd3": dict(maxDist=8, extraSearchDepth=3),
+    "ne_d20": dict(maxDist=20, noEditDistance=1, useAffineGap=0),
+}
+
+
+@pytest.mark.parametrize("opt", list(ALT_SETS))
+def test_alt_contig_index_matches_reference(reflib, alt_cfg, opt):
+    """ALT-aware alignment (the default, -ea- turns it off) on an index with ALT contigs: every field and the work counters, one-launch and two-pass forms."""
+    idx, reads = alt_cfg
+    p = reflib.default_params(**ALT_SETS[opt])
+    ridx, hidx = reflib.RefIndex(idx), hs.HsIndex(idx)
+    ral = reflib.RefSingleAligner(ridx, p)
+    want, wctr = ral.align(reads)
+    ral.close()
+    for two_pass in (False, True):
+        if two_pass and opt == "ne_d20":
+            continue
+        al = hs.HsAligner(hidx, p)
+        al.set_two_pass(two_pass)
+        got, gctr = al.align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (opt, two_pass)
+        g = reflib.counters_dict(gctr)
+        for k in ("totalReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "lvCalls", "affineGapCalls", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, two_pass, k)
+    if opt == "ea_off":
+        # the ALT logic is live on this data: with it off the reference does other work
+        on, _ = reflib.RefSingleAligner(ridx, reflib.default_params(maxDist=14)).align(reads)
+        assert differing(on, want) != []
+
+
+def test_alt_contig_index_on_the_bucket_layout_and_with_secondary_alignments(reflib, alt_cfg):
+    """The same index re-laid into sector buckets, and `-om 2` on it: secondary records landing on ALT contigs carry supplementary = 1
+    (finalizeSecondaryResults, BaseAligner.cpp:2482)."""
+    idx, reads = alt_cfg
+    ridx = reflib.RefIndex(idx)
+    p = reflib.default_params(maxDist=14)
+    want, _ = reflib.RefSingleAligner(ridx, p).align(reads)
+    got, _ = hs.HsAligner(hs.HsIndex(idx).relayout(), p).align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+    assert differing(want, got) == []
+    kw = dict(maxDist=14, extraSearchDepth=2, maxSecondaryAlignmentAdditionalEditDistance=2)
+    p = reflib.default_params(**kw)
+    ral = reflib.RefSecondaryAligner(ridx, p)
+    want, wsec, wn, _ = ral.align(reads, capacity=256)
+    ral.close()
+    got, gsec, gn, _ = hs.HsAligner(hs.HsIndex(idx), p).align_secondary(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS, 2, capacity=256)
+    bad_p, bad_s = differing_secondary(want, wsec, wn, got, gsec, gn)
+    assert bad_p == [] and bad_s == []
+    assert sum(int(wsec[i, :wn[i]]["supplementary"].sum()) for i in range(len(wn))) > 0
+
+
+@pytest.mark.parametrize("seed_len,large", [(21, False), (22, False), (22, True), (24, False), (28, True), (32, False)])
+def test_other_seed_lengths_match_reference(reflib, tmp_path, seed_len, large):
+    """Indexes built by the reference with -s 21..32: 16 / 64 / ... hash tables and 5-7 byte keys (9-11 byte entries in the file, 13-15 with -large).
+    The loader re-strides such entries to a multiple of 4 bytes (the lookup reads values as 32-bit words; a GPU cannot at odd addresses) -- the
+    engine's headers on that image give the reference's results and probe counts."""
+    from snap_b200 import synth
+    contigs = synth.make_contigs(2, 100_000, seed=91, repeat_frac=0.2)
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, contigs)
+    idx = str(tmp_path / "idx")
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fa, idx, seed_len=seed_len, large=large)
+    key_size = int(open(os.path.join(idx, "GenomeIndex")).read().split()[6])
+    assert key_size == {21: 4, 22: 5, 24: 5, 28: 6, 32: 7}[seed_len]
+    reads = synth.make_reads(contigs, 1200, 150, seed=92, sub_rate=0.02, ins_rate=0.003, del_rate=0.003, n_run_frac=0.05, short_frac=0.05)
+    ridx, hidx = reflib.RefIndex(idx), hs.HsIndex(idx)
+    for kw in (dict(maxDist=14), dict(maxDist=14, numSeedsFromCommandLine=0, seedCoverage=4.0)):
+        p = reflib.default_params(**kw)
+        ral = reflib.RefSingleAligner(ridx, p)
+        want, wctr = ral.align(reads)
+        ral.close()
+        got, gctr = hs.HsAligner(hidx, p).align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (seed_len, large, kw)
+        g = reflib.counters_dict(gctr)
+        for k in ("nHashTableLookups", "lvCalls", "affineGapCalls", "mapqHistogram") + (() if large else ("nHashEntriesProbed",)):
+            assert wctr[k] == g[k], (seed_len, large, k)
+    if key_size == 4:
+        got, _ = hs.HsAligner(hs.HsIndex(idx).relayout(), reflib.default_params(maxDist=14)).align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        want, _ = reflib.RefSingleAligner(ridx, reflib.default_params(maxDist=14)).align(reads)
+        assert differing(want, got) == []          # 4-byte keys: the sector-bucket layout applies too
