@@ -345,6 +345,14 @@ static inline bool sg_derive_paired_params(const snapgpu_params &in, const snapg
 {
     if (pin.struct_size != sizeof(snapgpu_paired_params)) { err = "snapgpu_paired_params.struct_size mismatch (ABI)"; return false; }
     if (in.maxSecondaryAlignmentAdditionalEditDistance != -1) { err = "paired path: secondary alignments (-om) are not supported"; return false; }
+    if (!in.useAffineGap && pin.useSoftClipping && pin.enableHammingScoringBaseAligner) {
+        // The reference asserts against this combination (`_ASSERT(useAffineGap)` before the single-end aligner's alignAffineGap in the soft-clipping
+        // branch, ChimericPairedEndAligner.cpp:359); its release build runs on regardless, and on reads with junk tails a few pairs per thousand then
+        // come out differently from this engine.  `-G-` / `-ne` for pairs therefore needs `-hc` (no soft clipping) or `-eh-`, where results are identical.
+        err = "paired path: affine gap off (-G- / -ne) together with soft clipping and the Hamming base aligner is a combination the reference asserts "
+              "against (ChimericPairedEndAligner.cpp:359): add -hc or -eh-";
+        return false;
+    }
     if (!sg_derive_params(in, seedLen, maxReadLen, pr, err)) return false;
     snapgpu_params s = in;
     s.maxDist = in.maxDist / 2;

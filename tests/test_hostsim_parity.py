@@ -529,3 +529,94 @@ def test_other_seed_lengths_match_reference(reflib, tmp_path, seed_len, large):
         got, _ = hs.HsAligner(hs.HsIndex(idx).relayout(), reflib.default_params(maxDist=14)).align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
         want, _ = reflib.RefSingleAligner(ridx, reflib.default_params(maxDist=14)).align(reads)
         assert differing(want, got) == []          # 4-byte keys: the sector-bucket layout applies too
+
+
+# More of `snap single`'s option surface (host build only: the GPU suite keeps OPTION_SETS): the DisabledOptimizations switches one by one and together,
+# popular-seed exploration, seed counts, weights, search depth, distances 0 and 30, other gap scores and end bonuses.
+EXTRA_OPTION_SETS = {
+    "noUkkonen": dict(maxDist=14, noUkkonen=1),
+    "noOrdered": dict(maxDist=14, noOrderedEvaluation=1),
+    "noTrunc": dict(maxDist=14, noTruncation=1),
+    "all_off": dict(maxDist=14, noUkkonen=1, noOrderedEvaluation=1, noTruncation=1, noBandedAffineGap=1),
+    "explore_h30": dict(maxDist=14, explorePopularSeeds=1, maxHits=30),
+    "h5": dict(maxDist=14, maxHits=5),
+    "mrl100": dict(maxDist=14, minReadLength=100),
+    "n40": dict(maxDist=14, numSeedsFromCommandLine=40),
+    "n3": dict(maxDist=14, numSeedsFromCommandLine=3),
+    "ms3": dict(maxDist=14, minWeightToCheck=3),
+    "esd0": dict(maxDist=14, extraSearchDepth=0),
+    "d0": dict(maxDist=0),
+    "d30": dict(maxDist=30),
+    "gap_2_5_8_2": dict(maxDist=14, matchReward=2, subPenalty=5, gapOpenPenalty=8, gapExtendPenalty=2),
+    "sub_eq_open_plus_extend": dict(maxDist=14, subPenalty=7, gapOpenPenalty=6, gapExtendPenalty=1),
+    "bonus_0_0": dict(maxDist=14, fivePrimeEndBonus=0, threePrimeEndBonus=0),
+    "bonus_20_3": dict(maxDist=14, fivePrimeEndBonus=20, threePrimeEndBonus=3),
+}
+
+
+@pytest.mark.parametrize("opt", list(EXTRA_OPTION_SETS))
+def test_more_options_match_reference(reflib, small_cfg, opt):
+    p = reflib.default_params(**EXTRA_OPTION_SETS[opt])
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for name, two_pass in (("noisy150", False), ("indel100", True)):
+        rb = small_cfg.reads[name]
+        ral = reflib.RefSingleAligner(ridx, p)
+        want, wctr = ral.align(rb)
+        ral.close()
+        al = hs.HsAligner(hidx, p)
+        al.set_two_pass(two_pass)
+        got, gctr = al.align(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (opt, name, two_pass)
+        g = reflib.counters_dict(gctr)
+        for k in ("totalReads", "singleHits", "multiHits", "notFound", "nHashTableLookups", "lvCalls", "affineGapCalls", "mapqHistogram"):
+            assert wctr[k] == g[k], (opt, name, two_pass, k)
+
+
+_HCX = dict(useSoftClipping=0, minAGScoreImprovement=15)
+EXTRA_PAIRED_SETS = {
+    "n4": (dict(maxDist=27, numSeedsFromCommandLine=4), dict()),
+    "n16": (dict(maxDist=27, numSeedsFromCommandLine=16), dict()),
+    "N5": (dict(maxDist=27), dict(maxSeedsSingleEnd=5)),
+    "i10": (dict(maxDist=27), dict(maxDistForIndels=10)),
+    "fmb0": (dict(maxDist=27), dict(flattenMAPQAtOrBelow=0)),
+    "fmb10": (dict(maxDist=27), dict(flattenMAPQAtOrBelow=10)),
+    "msr0": (dict(maxDist=27), dict(minScoreRealignment=0)),
+    "msr8": (dict(maxDist=27), dict(minScoreRealignment=8)),
+    "magi0": (dict(maxDist=27), dict(minAGScoreImprovement=0)),
+    "d8": (dict(maxDist=8), dict()),
+    "h10": (dict(maxDist=27, maxHits=10), dict()),
+    "H20": (dict(maxDist=27), dict(intersectingAlignerMaxHits=20)),
+    "gap_2_5_8_2": (dict(maxDist=27, matchReward=2, subPenalty=5, gapOpenPenalty=8, gapExtendPenalty=2), dict()),
+    "spacing_100_2000": (dict(maxDist=27), dict(minSpacing=100, maxSpacing=2000)),
+    "mrl100": (dict(maxDist=27, minReadLength=100), dict()),
+    "noag_eh0": (dict(maxDist=27, useAffineGap=0), dict(enableHammingScoringBaseAligner=0)),
+    "noag_hc": (dict(maxDist=27, useAffineGap=0), dict(**_HCX)),
+    "ne_hc": (dict(maxDist=20, noEditDistance=1, useAffineGap=0), dict(**_HCX)),
+    "ne_ag": (dict(maxDist=20, noEditDistance=1, useAffineGap=1), dict()),
+}
+
+
+@pytest.mark.parametrize("opt", list(EXTRA_PAIRED_SETS))
+def test_more_paired_options_match_reference(reflib, small_cfg, opt):
+    """More of `snap paired`'s option surface on the host build (one-launch form on the noisy pairs, staged form on the junk-tailed ones): seeds, single-end seeds, indel distance, MAPQ flattening,
+    realignment thresholds, hit limits, spacing, other gap scores, and -G- / -ne where the reference allows them (-hc or -eh-)."""
+    kw, pkw = EXTRA_PAIRED_SETS[opt]
+    rp, pp = reflib.default_params_paired(**kw), reflib.default_paired_params(**pkw)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for name, staged in (("noisy150", False), ("clipped150", True)):
+        pairs = small_cfg.pairs[name]
+        want, _ = reflib.RefPairedAligner(ridx, rp, pp).align(pairs)
+        al = hs.HsPairedAligner(hidx, rp, pp)
+        al.set_staged(staged)
+        got, _, _ = al.align(pairs, reflib.PAIRED_RESULT_DTYPE)
+        assert differing_pairs(want, got) == [], (opt, name, staged)
+
+
+def test_paired_without_affine_gap_needs_hc_or_no_hamming(reflib, small_cfg):
+    """-G- / -ne for pairs with soft clipping AND the Hamming base aligner on is what the reference asserts against (ChimericPairedEndAligner.cpp:359);
+    the engine refuses it by name instead of returning slightly different pairs."""
+    hidx = hs.HsIndex(small_cfg.idx)
+    for kw in (dict(maxDist=27, useAffineGap=0), dict(maxDist=20, noEditDistance=1, useAffineGap=0)):
+        with pytest.raises(RuntimeError) as e:
+            hs.HsPairedAligner(hidx, reflib.default_params_paired(**kw), reflib.default_paired_params())
+        assert "ChimericPairedEndAligner.cpp:359" in str(e.value)
