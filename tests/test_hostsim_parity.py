@@ -620,3 +620,69 @@ def test_paired_without_affine_gap_needs_hc_or_no_hamming(reflib, small_cfg):
         with pytest.raises(RuntimeError) as e:
             hs.HsPairedAligner(hidx, reflib.default_params_paired(**kw), reflib.default_paired_params())
         assert "ChimericPairedEndAligner.cpp:359" in str(e.value)
+
+
+@pytest.mark.parametrize("seed_len,large", [(22, False), (24, True)])
+def test_pairs_on_other_seed_lengths_match_reference(reflib, tmp_path, seed_len, large):
+    """The paired path on reference-built indexes of other seed lengths (re-strided entries), one-launch and staged forms."""
+    from snap_b200 import synth
+    contigs = synth.make_contigs(2, 100_000, seed=91, repeat_frac=0.2)
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, contigs)
+    idx = str(tmp_path / "idx")
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, fa, idx, seed_len=seed_len, large=large)
+    pairs = synth.make_pairs(contigs, 400, 150, seed=93, sub_rate=0.03, ins_rate=0.004, del_rate=0.004, chimeric_frac=0.05, n_run_frac=0.05, short_frac=0.05)
+    rp, pp = reflib.default_params_paired(maxDist=27), reflib.default_paired_params()
+    want, _ = reflib.RefPairedAligner(reflib.RefIndex(idx), rp, pp).align(pairs)
+    for staged in (False, True):
+        al = hs.HsPairedAligner(hs.HsIndex(idx), rp, pp)
+        al.set_staged(staged)
+        got, _, _ = al.align(pairs, reflib.PAIRED_RESULT_DTYPE)
+        assert differing_pairs(want, got) == [], (seed_len, large, staged)
+
+
+def test_qualities_over_the_whole_printable_range(reflib, small_cfg):
+    """Base qualities drawn uniformly from '!'..'~' (every entry of the phred -> probability table; MAPQ spreads over 20+ values):
+    match probabilities and MAPQ bit-identical, LV-only and affine-gap-everywhere."""
+    from snap_b200 import synth
+    rb = small_cfg.reads["noisy150"]
+    q = rb.quals.copy()
+    q[:] = np.random.default_rng(5).integers(33, 127, q.size, dtype=np.uint8)
+    rq = synth.ReadBatch(rb.bases, q, rb.offsets, rb.lens)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for kw in (dict(maxDist=14), dict(maxDist=20, noEditDistance=1, useAffineGap=0)):
+        p = reflib.default_params(**kw)
+        ral = reflib.RefSingleAligner(ridx, p)
+        want, _ = ral.align(rq)
+        ral.close()
+        got, _ = hs.HsAligner(hidx, p).align(rq, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], kw
+        assert len(set(want["mapq"].tolist())) > 15
+
+
+EXTRA_SECONDARY_SETS = {      # host build only (the GPU suite keeps SECONDARY_SETS)
+    "om2_ne": (dict(maxDist=20, extraSearchDepth=2, noEditDistance=1, useAffineGap=0, maxSecondaryAlignmentAdditionalEditDistance=2), 0x7fffffff, -1),
+    "om1_h5": (dict(maxDist=14, maxHits=5, maxSecondaryAlignmentAdditionalEditDistance=1), 0x7fffffff, -1),
+    "om1_stopfirst": (dict(maxDist=14, stopOnFirstHit=1, maxSecondaryAlignmentAdditionalEditDistance=1), 0x7fffffff, -1),
+    "om5_esd5_d8": (dict(maxDist=8, extraSearchDepth=5, maxSecondaryAlignmentAdditionalEditDistance=5), 3, 1),
+    "om1_alloff": (dict(maxDist=14, noUkkonen=1, noOrderedEvaluation=1, noTruncation=1, maxSecondaryAlignmentAdditionalEditDistance=1), 0x7fffffff, 3),
+    "om1_cov": (dict(maxDist=14, numSeedsFromCommandLine=0, seedCoverage=4.0, maxSecondaryAlignmentAdditionalEditDistance=1), 10, -1),
+    "om0_d0": (dict(maxDist=0, maxSecondaryAlignmentAdditionalEditDistance=0), 0x7fffffff, -1),
+    "om1_x": (dict(maxDist=14, explorePopularSeeds=1, maxHits=30, maxSecondaryAlignmentAdditionalEditDistance=1), 0x7fffffff, -1),
+}
+
+
+@pytest.mark.parametrize("opt", list(EXTRA_SECONDARY_SETS))
+def test_more_secondary_option_sets_match_reference(reflib, small_cfg, opt):
+    kw, omax, mpc = EXTRA_SECONDARY_SETS[opt]
+    p = reflib.default_params(**kw)
+    ridx, hidx = reflib.RefIndex(small_cfg.idx), hs.HsIndex(small_cfg.idx)
+    for name in ("std150", "indel100"):
+        rb = small_cfg.reads[name]
+        ral = reflib.RefSecondaryAligner(ridx, p, omax, mpc)
+        want, wsec, wn, _ = ral.align(rb, capacity=512)
+        ral.close()
+        got, gsec, gn, _ = hs.HsAligner(hidx, p).align_secondary(rb, reflib.RESULT_DTYPE, reflib.N_COUNTERS, kw["maxSecondaryAlignmentAdditionalEditDistance"],
+                                                               omax, mpc, capacity=512, raw_cap=16)
+        bad_p, bad_s = differing_secondary(want, wsec, wn, got, gsec, gn)
+        assert bad_p == [] and bad_s == [], (opt, name, bad_p[:5], bad_s[:5])
