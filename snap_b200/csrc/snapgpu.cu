@@ -2528,6 +2528,16 @@ int snapgpu_sam_set_format(snapgpu_sam *s, int format)
 {
     if (!s) return sg_fail("null argument");
     if (format != SNAPGPU_FORMAT_SAM && format != SNAPGPU_FORMAT_BAM) return sg_fail("snapgpu_sam_set_format: unknown format");
+    if (format == SNAPGPU_FORMAT_BAM) {
+        // A BAM record's refID / next_refID index the header's reference table, which is in ORIGINAL contig order (BAMFormat::writeHeader, Bam.cpp:1012-1023);
+        // the record writer here files the internal contig number.  The two differ only for a FASTA whose ALT contigs are not already last (the reference's
+        // indexer then moves them behind the primary ones): found by the host-side sweep over an ALT-bearing index after the round's GPU budget was
+        // spent, so the mapping is not in the kernel yet -- SAM records (names, not numbers) and the header are right on such an index, BAM is refused.
+        const std::vector<int32_t> &o = s->index->h_contigOriginal;
+        for (size_t c = 0; c < o.size(); c++)
+            if (o[c] != (int32_t)c) return sg_fail("snapgpu_sam_set_format: BAM records on an index whose contigs were reordered (ALT contigs not last in the FASTA) "
+                                                   "are not supported yet (refID is the original contig number); SAM is");
+    }
     s->format = format;
     return 0;
 }

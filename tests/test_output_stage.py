@@ -569,3 +569,74 @@ def test_write_pairs_retry_loops_equal_reference(reflib, small_cfg):
     assert len(want) == len(got) == pb.n
     bad = [i for i in range(pb.n) if want[i] != got[i]]
     assert bad == [], (len(bad), res[bad[0] // 2], want[bad[0]], got[bad[0]])
+
+
+def test_output_stage_on_an_index_with_alt_contigs(reflib, tmp_path):
+    """A FASTA whose ALT contigs are interleaved with the primary ones: the reference's indexer moves them to the end (internal != original contig numbers).
+    SAM records (RNAME by name) and the file header (@SQ in original order, AH:* on ALT contigs) are byte-identical to the reference binary's.  BAM records
+    are identical EXCEPT refID: the writer files the internal contig number where the reference files the original one -- the library refuses BAM on such
+    an index (snapgpu_sam_set_format) until the mapping is in the kernel; this test pins the difference to exactly that field."""
+    import ctypes as C
+    import struct
+    import subprocess
+    import sorted_data
+    from snap_b200 import synth
+    P = lambda name: str(tmp_path / name)
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    primary = synth.make_contigs(2, 100_000, seed=71, repeat_frac=0.15)
+
+    def haplo(src, lo, hi, div):
+        c = src[lo:hi].copy()
+        m = rng.random(c.size) < div
+        c[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+        return c
+
+    names = [b"chr1", b"chr1_KI270_alt", b"chr2", b"HLA-A*01:01", b"chrUn_decoy_alt"]
+    contigs = [primary[0], haplo(primary[0], 20_000, 50_000, 0.01), primary[1], haplo(primary[1], 60_000, 80_000, 0.03), acgt[rng.integers(0, 4, 15_000)]]
+    with open(P("alt.fa"), "wb") as f:
+        for n, c in zip(names, contigs):
+            f.write(b">" + n + b"\n")
+            for i in range(0, c.size, 100):
+                f.write(c[i:i + 100].tobytes() + b"\n")
+    reflib.build_reference_index(reflib.SNAP_ALIGNER, P("alt.fa"), P("idx"))
+    rb = synth.make_reads(contigs, 1500, 150, seed=78, sub_rate=0.01, ins_rate=0.003, del_rate=0.003)
+    rb.write_fastq(P("r.fq"))
+    ids = [b"r%d" % i for i in range(rb.n)]
+    res, _ = reflib.RefSingleAligner(reflib.RefIndex(P("idx")), reflib.default_params(maxDist=14)).align(rb)
+    for fmt in ("sam", "bam"):
+        r = subprocess.run([reflib.SNAP_ALIGNER, "single", P("idx"), P("r.fq"), "-o", P("o." + fmt), "-t", "1", "-d", "14"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-500:]
+    # SAM records and header
+    lines = open(P("o.sam"), "rb").read().split(b"\n")
+    want = [l for l in lines if l and not l.startswith(b"@")]
+    got = [l for l in hs.sam_single(hs.HsIndex(P("idx")), rb, ids, res).split(b"\n") if l]
+    assert want == got
+    assert sum(1 for l in want if l.split(b"\t")[2] in (b"chr1_KI270_alt", b"HLA-A*01:01", b"chrUn_decoy_alt")) > 200
+    hdr = b"".join(l + b"\n" for l in lines if l.startswith(b"@"))
+    pg = [l for l in hdr.split(b"\n") if l.startswith(b"@PG\tID:SNAP\t")][0]
+    rg = [l for l in hdr.split(b"\n") if l.startswith(b"@RG")][0]
+    L = C.CDLL(hs.build())
+    L.hs_index_open.restype = C.c_void_p
+    L.hs_index_open.argtypes = [C.c_char_p]
+    L.hs_sam_header.restype = C.c_int64
+    L.hs_sam_header.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64]
+    buf = (C.c_uint8 * (1 << 20))()
+    n = L.hs_sam_header(L.hs_index_open(P("idx").encode()), 0, 0, pg.split(b"\tCL:")[1].rsplit(b"\tVN:", 1)[0], pg.rsplit(b"\tVN:", 1)[1], rg, buf, 1 << 20)
+    assert bytes(buf[:n]) == hdr and hdr.count(b"\tAH:*\n") == 3
+    # BAM records: identical but for refID (bytes 4..8 of a record), which holds the internal contig number
+    refs, want, _ = sorted_data.load_bam(P("o.bam"))
+    assert [r[0] for r in refs] == names                       # the header's reference table is in ORIGINAL order
+    blob = hs.bam_single(hs.HsIndex(P("idx")), rb, ids, res)
+    got, q = [], 0
+    while q < len(blob):
+        b = struct.unpack("<i", blob[q:q + 4])[0]; got.append(blob[q:q + 4 + b]); q += 4 + b
+    assert len(got) == len(want)
+    internal_to_original = {0: 0, 1: 2, 2: 1, 3: 3, 4: 4, -1: -1}      # chr1, chr2, then the three ALT contigs
+    n_diff = 0
+    for w, g in zip(want, got):
+        assert w[:4] == g[:4] and w[8:] == g[8:]
+        rw, rg_ = struct.unpack("<i", w[4:8])[0], struct.unpack("<i", g[4:8])[0]
+        assert rw == internal_to_original[rg_]
+        n_diff += rw != rg_
+    assert n_diff > 300
