@@ -686,3 +686,34 @@ def test_more_secondary_option_sets_match_reference(reflib, small_cfg, opt):
                                                                omax, mpc, capacity=512, raw_cap=16)
         bad_p, bad_s = differing_secondary(want, wsec, wn, got, gsec, gn)
         assert bad_p == [] and bad_s == [], (opt, name, bad_p[:5], bad_s[:5])
+
+
+@pytest.mark.parametrize("length,kw", [(600, dict(maxDist=30)), (950, dict(maxDist=40, extraSearchDepth=2)), (400, dict(maxDist=60))])
+def test_long_reads_and_wide_bands_match_reference(reflib, small_cfg, length, kw):
+    """Reads of 400-950 bases with -d 30..60 (Landau-Vishkin beyond the shared-memory cell budget, affine-gap bands of up to 121 columns, scratch sized for
+    MAX_READ_LENGTH): every field and the LV / affine-gap call counts, both launch forms.  (From ~992 bases on, with -d 40, the REFERENCE's banded affine-gap
+    layout needs more than its MAX_VEC_SEGMENTS = 125 vectors per row -- numSeg x segLen can reach 4/3 of the pattern -- and its edit counts then come from
+    beyond its own arrays: 14 % of such reads differ by one edit.  Not reproduced; 950 is the longest length tested.)"""
+    from snap_b200 import synth
+    reads = synth.make_reads(small_cfg.contigs, 150, length, seed=length, sub_rate=0.02, ins_rate=0.003, del_rate=0.003)
+    p = reflib.default_params(**kw)
+    ral = reflib.RefSingleAligner(reflib.RefIndex(small_cfg.idx), p)
+    want, wctr = ral.align(reads)
+    ral.close()
+    for two_pass in (False, True):
+        al = hs.HsAligner(hs.HsIndex(small_cfg.idx), p, max_read_len=1000)
+        al.set_two_pass(two_pass)
+        got, gctr = al.align(reads, reflib.RESULT_DTYPE, reflib.N_COUNTERS)
+        assert differing(want, got) == [], (length, two_pass)
+        g = reflib.counters_dict(gctr)
+        assert wctr["lvCalls"] == g["lvCalls"] and wctr["affineGapCalls"] == g["affineGapCalls"]
+    assert int((want["status"] != 0).sum()) > 140
+
+
+def test_long_pairs_match_reference(reflib, small_cfg):
+    from snap_b200 import synth
+    pairs = synth.make_pairs(small_cfg.contigs, 120, 400, seed=7, sub_rate=0.02, ins_rate=0.003, del_rate=0.003, insert_mean=900)
+    rp, pp = reflib.default_params_paired(maxDist=40), reflib.default_paired_params(maxSpacing=2000)
+    want, _ = reflib.RefPairedAligner(reflib.RefIndex(small_cfg.idx), rp, pp).align(pairs)
+    got, _, _ = hs.HsPairedAligner(hs.HsIndex(small_cfg.idx), rp, pp, max_read_len=400).align(pairs, reflib.PAIRED_RESULT_DTYPE)
+    assert differing_pairs(want, got) == []
