@@ -1682,7 +1682,10 @@ int snapgpu_paired_aligner_create(const snapgpu_index *idx, const snapgpu_params
     *out = nullptr;
     if (require_device(idx->device)) return 1;
     if (maxBatchPairs <= 0) return sg_fail("maxBatchPairs must be positive");
-    if (idx->view.altFirstLocation < idx->view.nBases) return sg_fail("snapgpu_paired_aligner_create: indices with ALT contigs are not supported by the paired path");
+    // ALT-aware pairing (a second score set for non-ALT pairs, ALT liftover) is not implemented; with ALT awareness off (-ea-) an index with ALT contigs
+    // is just an index, and results are the reference's (host build: 8 option sets x 2 pair sets on an ALT-bearing reference)
+    if (idx->view.altFirstLocation < idx->view.nBases && params->altAwareness)
+        return sg_fail("snapgpu_paired_aligner_create: ALT-aware pairing is not supported: an index with ALT contigs needs -ea- (altAwareness = 0) on the paired path");
     snapgpu_aligner *a = new (std::nothrow) snapgpu_aligner;
     if (!a) return sg_fail("out of memory");
     a->index = idx; a->device = idx->device; a->userParams = *params; a->maxBatchReads = 2 * maxBatchPairs; a->paired = true;
