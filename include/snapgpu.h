@@ -319,7 +319,7 @@ int  snapgpu_align_single_secondary_device(snapgpu_aligner *a, int64_t n, const 
 /*
  * Paired-end aligner handle: the ChimericPairedEndAligner(IntersectingPairedEndAligner) stack that
  * PairedAlignerContext::runIterationThread builds per thread (reference SNAPLib/PairedAligner.cpp:547-638).
- * Scope: no secondary results (-om unset), no ALT contigs.  Soft clipping (the default) runs the Hamming / gapless
+ * Scope: no secondary results (-om unset); an index with ALT contigs only with params->altAwareness = 0 (-ea-): ALT-aware pairing is not implemented.  Soft clipping (the default) runs the Hamming / gapless
  * passes of both aligners (IntersectingPairedEndAligner::alignHamming, BaseAligner::AlignRead(useHamming) +
  * alignAffineGap); useSoftClipping = 0 is `snap paired -hc`.
  */
